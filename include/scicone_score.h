@@ -1,0 +1,192 @@
+/*
+ * scicone_score.h - C ABI of the B200 tree-scoring engine (libscicone_score.so).
+ *
+ * The reference (cbg-ethz/SCICoNE) has no plugin / FFI boundary: its MCMC driver
+ * `Inference` (scicone/src/Inference.h) calls the scoring code in `Tree`
+ * (scicone/src/Tree.h) and `MathOp` (scicone/src/MathOp.cpp) directly and owns the
+ * cells x nodes score tables as std::vector<std::map<int,double>>.  This header
+ * cuts the seam at exactly those `Inference` methods.  Each entry point names
+ * the reference member it replaces (file:line relative to /root/reference).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, int return codes (0 = ok, <0 = error;
+ *     scicone_last_error() gives the message).  No exception crosses the ABI.
+ *     Where the reference throws std::logic_error (Tree.h:170-171, size
+ *     mismatch) the call returns SCICONE_ERR_ARG; where it asserts !isnan
+ *     (Inference.h:1150,1191) the call returns SCICONE_ERR_NAN.
+ *   - All host buffers are caller-owned and only read during the call.
+ *   - A dataset owns the device copy of D (cells x regions), region sizes,
+ *     neutral states and cluster sizes; it is immutable after creation and may
+ *     be shared by any number of chains.
+ *   - A chain owns what one reference `Inference` object owns for scoring:
+ *     t_scores / t_sums / t_maxs and their primed counterparts
+ *     (Inference.h:39-44), device resident.  A chain is not thread-safe.
+ *   - There is no CPU fallback: every compute entry point needs a CUDA device
+ *     and fails with SCICONE_ERR_CUDA otherwise.
+ */
+#ifndef SCICONE_SCORE_H
+#define SCICONE_SCORE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCICONE_ABI_VERSION 1
+
+enum {
+    SCICONE_OK = 0,
+    SCICONE_ERR_ARG = -1,   /* bad argument / inconsistent sizes (reference: std::logic_error) */
+    SCICONE_ERR_CUDA = -2,  /* CUDA runtime failure or no device */
+    SCICONE_ERR_STATE = -3, /* call sequence violated (e.g. sums without scores) */
+    SCICONE_ERR_NAN = -4,   /* a per-cell aggregate became NaN (reference: assert) */
+    SCICONE_ERR_COMM = -5   /* multi-GPU communicator failure */
+};
+
+typedef struct scicone_dataset scicone_dataset;
+typedef struct scicone_chain scicone_chain;
+
+/*
+ * Flat encoding of a reference `Tree` (Tree.h:36-118) / `Node` (Node.h:18-81).
+ * Nodes are listed parent-before-child; entry 0 is the root.  Only the fields
+ * that feed the score are carried: Node::id, parent link, Node::c_change and
+ * Node::c (both std::map<u_int,int>, i.e. region-ascending), and Tree::nu.
+ * Node::z is re-derived by the library with the reference's int truncation
+ * (Tree.h:178-179,197,241; Node.h:25).
+ */
+typedef struct scicone_tree {
+    int32_t n_nodes;           /* number of entries, root included */
+    const int32_t* node_id;    /* [n_nodes] Node::id (root = 0), unique */
+    const int32_t* parent;     /* [n_nodes] index of the parent entry, -1 for the root */
+    const int32_t* chg_off;    /* [n_nodes+1] CSR offsets of Node::c_change */
+    const int32_t* chg_region; /* region index, ascending inside a node */
+    const int32_t* chg_value;  /* event value (may be 0, see Node.h:389-418) */
+    const int32_t* gen_off;    /* [n_nodes+1] CSR offsets of Node::c (genotype relative to neutral) */
+    const int32_t* gen_region; /* region index, ascending inside a node */
+    const int32_t* gen_value;  /* non-zero copy-number offset */
+    double nu;                 /* Tree::nu */
+} scicone_tree;
+
+typedef struct scicone_dataset_desc {
+    int32_t n_cells;               /* rows of D handed to this dataset (this rank's shard) */
+    int32_t n_regions;             /* columns of D */
+    const double* D;               /* [n_cells][n_regions] row-major, as Utils::read_counts fills it (Utils.cpp:74-102) */
+    const int32_t* region_sizes;   /* [n_regions]  r */
+    const int32_t* neutral_states; /* [n_regions]  Tree::region_neutral_states */
+    const int32_t* cluster_sizes;  /* [n_cells]    weights of the sum over cells (Inference.h:269,294) */
+    double eta;                    /* globals.cpp eta: replaces copy number 0 (Tree.h:194-195) */
+    int32_t is_overdispersed;      /* globals.cpp is_overdispersed (Tree.h:212) */
+    int32_t max_scoring;           /* Inference::max_scoring (Inference.h:46) */
+    int32_t device;                /* CUDA device ordinal */
+    int64_t cell_offset;           /* global index of this shard's first cell (0 on a single GPU) */
+    int64_t n_cells_global;        /* total cells over all ranks (== n_cells on a single GPU) */
+} scicone_dataset_desc;
+
+int scicone_abi_version(void);
+const char* scicone_last_error(void);
+
+int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* desc);
+void scicone_dataset_destroy(scicone_dataset* ds);
+
+/* One chain == the score tables of one reference `Inference` object (Inference.h:183-198). */
+int scicone_chain_create(scicone_chain** out, scicone_dataset* ds);
+void scicone_chain_destroy(scicone_chain* ch);
+
+/*
+ * Inference::compute_t_table (Inference.h:224-279): full pass over every cell and
+ * every node of `t`; fills t_scores, t_sums (per-cell log-sum-exp, or max with
+ * argmax in t_maxs when max_scoring) and returns
+ * t_sum = sum_j aggregate_j * cluster_sizes[j].  Replaces any committed table
+ * (as assign_cells_to_nodes does at Inference.h:1320-1323).
+ */
+int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* t_sum);
+
+/*
+ * Inference::compute_t_od_scores (Inference.h:1406-1419) for the committed tree and
+ * Inference::compute_t_prime_od_scores (Inference.h:1421-1433) for the proposal:
+ * sum_j cluster_sizes[j] * Tree::get_od_root_score(cell j) (Tree.h:1774-1810) at `nu`.
+ */
+int scicone_compute_t_od_scores(scicone_chain* ch, double nu, double* od_score);
+int scicone_compute_t_prime_od_scores(scicone_chain* ch, double nu, double* od_score);
+
+/*
+ * Inference::compute_t_prime_scores (Inference.h:1015-1052): rescore the subtree of
+ * `t_prime` rooted at entry `node_idx`, relative to the committed table (the
+ * parent's score is re-read from t_scores, Inference.h:1034).  May be called
+ * several times before one compute_t_prime_sums (label swap, Inference.h:1059-1063).
+ * The work is queued; it runs fused with the aggregate in compute_t_prime_sums.
+ */
+int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t_prime, int32_t node_idx);
+
+/*
+ * Inference::compute_t_prime_sums (Inference.h:1069-1196) followed by the weighted
+ * sum over cells of Inference::comparison (Inference.h:292-294).  A node deleted by
+ * the move is found as Inference::deleted_node_idx does (Inference.h:1270-1289):
+ * the id present in the committed tree and absent from `t_prime`.
+ * Sum scoring reproduces MathOp::log_replace_sum (MathOp.cpp:307-361), max scoring
+ * the incremental argmax rule (Inference.h:1086-1152).
+ */
+int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t_prime, double* t_prime_sum);
+
+/*
+ * The same two steps for `n` chains in ONE kernel launch (independent restarts or
+ * proposals evaluated in lock-step).  Every chain must have queued its subtree
+ * roots with scicone_compute_t_prime_scores.  All chains must share one dataset.
+ */
+int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const* t_primes,
+                                       int32_t n, double* t_prime_sums);
+
+/*
+ * Accept (Inference.h:867-870: t_sums = t_prime_sums, t_maxs = t_prime_maxs,
+ * update_t_scores(), and the proposal's od score / nu become the committed ones)
+ * or reject (Inference.h:881,890) the queued proposal.  After a delete move the
+ * deleted id leaves the table (Inference.h:1001-1009).
+ */
+int scicone_accept(scicone_chain* ch);
+int scicone_reject(scicone_chain* ch);
+
+/* Number of nodes in the committed table and their ids in ascending order. */
+int scicone_t_n_nodes(scicone_chain* ch, int32_t* n_nodes);
+int scicone_t_node_ids(scicone_chain* ch, int32_t* ids /* [n_nodes] */);
+
+/*
+ * Read-back of the committed tables (row-major [n_cells][n_nodes], node columns in
+ * ascending id order = std::map iteration order; infer_trees.cpp:336-349).
+ */
+int scicone_read_t_scores(scicone_chain* ch, double* out);
+int scicone_read_t_sums(scicone_chain* ch, double* out /* [n_cells] */);
+int scicone_read_t_maxs(scicone_chain* ch, int32_t* ids /* [n_cells] */, double* vals /* [n_cells] */);
+/* Primed tables of the queued proposal after compute_t_prime_sums. */
+int scicone_read_t_prime_sums(scicone_chain* ch, double* out /* [n_cells] */);
+int scicone_read_t_prime_maxs(scicone_chain* ch, int32_t* ids, double* vals);
+/* t_prime_scores: rescored node ids (ascending) and their [n_cells][n_rescored] matrix. */
+int scicone_t_prime_n_rescored(scicone_chain* ch, int32_t* n);
+int scicone_read_t_prime_scores(scicone_chain* ch, int32_t* ids, double* out);
+
+/*
+ * Inference::assign_cells_to_nodes (Inference.h:1346-1362): per-cell argmax over the
+ * committed table (std::max_element: first maximum in ascending id order) and the
+ * cells x regions copy-number matrix neutral + c(argmax node).  `t` must be the
+ * committed tree (its genotypes are expanded on the device).
+ */
+int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int32_t* cell_node_ids /* [n_cells] */,
+                                  int32_t* cell_region_cn /* [n_cells][n_regions] or NULL */);
+
+/*
+ * Multi-GPU (cells sharded over ranks).  The host side
+ * exchanges the 128-byte NCCL unique id by its own means (the bench uses
+ * torch.distributed), then every rank attaches its dataset.  Afterwards every
+ * t_sum / od_score returned by the calls above is the sum over ALL ranks,
+ * combined in a fixed order so that it does not depend on the number of GPUs.
+ */
+int scicone_comm_unique_id(uint8_t out[128]);
+int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128], int32_t rank, int32_t world_size);
+
+/* Per-phase device time of the last flush in microseconds (CUDA events); for the bench. */
+int scicone_last_kernel_time_us(scicone_chain* ch, double* us);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCICONE_SCORE_H */
