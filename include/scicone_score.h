@@ -183,8 +183,14 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
 int scicone_comm_unique_id(uint8_t out[128]);
 int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128], int32_t rank, int32_t world_size);
 
-/* Per-phase device time of the last flush in microseconds (CUDA events); for the bench. */
-int scicone_last_kernel_time_us(scicone_chain* ch, double* us);
+/*
+ * Measurement hooks for bench.py (no reference counterpart; the reference's only timer is the
+ * wall clock around infer_mcmc, infer_trees.cpp:291-304).  With profiling on, every proposal
+ * launch is bracketed by CUDA events on the dataset's stream.
+ */
+int scicone_set_profiling(scicone_dataset* ds, int32_t on);
+int scicone_last_kernel_time_us(scicone_dataset* ds, double* us); /* device time of the last proposal kernel */
+int scicone_kernel_launches(scicone_dataset* ds, uint64_t* n);    /* kernels launched on this dataset so far */
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,292 @@
+"""ctypes binding of libscicone_score.so (the C ABI in include/scicone_score.h).
+
+The class and method names mirror the members of the reference's ``Inference`` class that own the
+scoring tables (reference: scicone/src/Inference.h:224 compute_t_table, :1015 compute_t_prime_scores,
+:1069 compute_t_prime_sums, :1406 compute_t_od_scores, :1421 compute_t_prime_od_scores,
+:996 update_t_scores via accept, :1311 assign_cells_to_nodes), so that parity tests read like the
+reference's own tests (scicone/tests/validation.h).
+
+There is no CPU fallback: loading fails loudly if the CUDA library has not been built
+(``python -c 'import __graft_entry__ as g; g.build()'``) and every compute call raises
+``SciconeError`` without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .flat_tree import CTree, FlatTree  # noqa: F401  (re-exported)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libscicone_score.so")
+
+# every symbol include/scicone_score.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "scicone_abi_version", "scicone_last_error", "scicone_dataset_create", "scicone_dataset_destroy",
+    "scicone_chain_create", "scicone_chain_destroy", "scicone_compute_t_table", "scicone_compute_t_od_scores",
+    "scicone_compute_t_prime_od_scores", "scicone_compute_t_prime_scores", "scicone_compute_t_prime_sums",
+    "scicone_batch_compute_t_prime_sums", "scicone_accept", "scicone_reject", "scicone_t_n_nodes",
+    "scicone_t_node_ids", "scicone_read_t_scores", "scicone_read_t_sums", "scicone_read_t_maxs",
+    "scicone_read_t_prime_sums", "scicone_read_t_prime_maxs", "scicone_t_prime_n_rescored",
+    "scicone_read_t_prime_scores", "scicone_assign_cells_to_nodes", "scicone_comm_unique_id",
+    "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_launches",
+]
+
+ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}
+
+
+class SciconeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class DatasetDesc(C.Structure):
+    _fields_ = [
+        ("n_cells", C.c_int32),
+        ("n_regions", C.c_int32),
+        ("D", C.POINTER(C.c_double)),
+        ("region_sizes", C.POINTER(C.c_int32)),
+        ("neutral_states", C.POINTER(C.c_int32)),
+        ("cluster_sizes", C.POINTER(C.c_int32)),
+        ("eta", C.c_double),
+        ("is_overdispersed", C.c_int32),
+        ("max_scoring", C.c_int32),
+        ("device", C.c_int32),
+        ("cell_offset", C.c_int64),
+        ("n_cells_global", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libscicone_score.so; raises if it was not built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() (needs nvcc)")
+        L = C.CDLL(LIB_PATH)
+        dp, ip, tp, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(CTree), C.c_void_p
+        L.scicone_last_error.restype = C.c_char_p
+        L.scicone_dataset_create.argtypes = [C.POINTER(vp), C.POINTER(DatasetDesc)]
+        L.scicone_dataset_destroy.argtypes = [vp]
+        L.scicone_dataset_destroy.restype = None
+        L.scicone_chain_create.argtypes = [C.POINTER(vp), vp]
+        L.scicone_chain_destroy.argtypes = [vp]
+        L.scicone_chain_destroy.restype = None
+        L.scicone_compute_t_table.argtypes = [vp, tp, dp]
+        L.scicone_compute_t_od_scores.argtypes = [vp, C.c_double, dp]
+        L.scicone_compute_t_prime_od_scores.argtypes = [vp, C.c_double, dp]
+        L.scicone_compute_t_prime_scores.argtypes = [vp, tp, C.c_int32]
+        L.scicone_compute_t_prime_sums.argtypes = [vp, tp, dp]
+        L.scicone_batch_compute_t_prime_sums.argtypes = [C.POINTER(vp), C.POINTER(tp), C.c_int32, dp]
+        L.scicone_accept.argtypes = [vp]
+        L.scicone_reject.argtypes = [vp]
+        L.scicone_t_n_nodes.argtypes = [vp, ip]
+        L.scicone_t_node_ids.argtypes = [vp, ip]
+        L.scicone_read_t_scores.argtypes = [vp, dp]
+        L.scicone_read_t_sums.argtypes = [vp, dp]
+        L.scicone_read_t_maxs.argtypes = [vp, ip, dp]
+        L.scicone_read_t_prime_sums.argtypes = [vp, dp]
+        L.scicone_read_t_prime_maxs.argtypes = [vp, ip, dp]
+        L.scicone_t_prime_n_rescored.argtypes = [vp, ip]
+        L.scicone_read_t_prime_scores.argtypes = [vp, ip, dp]
+        L.scicone_assign_cells_to_nodes.argtypes = [vp, tp, ip, ip]
+        L.scicone_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+        L.scicone_dataset_attach_comm.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]
+        L.scicone_set_profiling.argtypes = [vp, C.c_int32]
+        L.scicone_last_kernel_time_us.argtypes = [vp, dp]
+        L.scicone_kernel_launches.argtypes = [vp, C.POINTER(C.c_uint64)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise SciconeError(rc, lib().scicone_last_error().decode())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the host program broadcasts it)."""
+    buf = (C.c_uint8 * 128)()
+    _check(lib().scicone_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Dataset:
+    """Device-resident count matrix of one rank's cells (immutable; shared by any number of chains)."""
+
+    def __init__(self, D, region_sizes, neutral_states=None, cluster_sizes=None, eta=1e-4, is_overdispersed=1,
+                 max_scoring=0, ploidy=2, device=0, cell_offset=0, n_cells_global=None):
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        if D.ndim != 2:
+            raise ValueError("D must be cells x regions")
+        self.M, self.K = D.shape
+        r = np.ascontiguousarray(region_sizes, dtype=np.int32)
+        if r.shape != (self.K,):
+            # the reference throws std::logic_error when D and r disagree (scicone/src/Tree.h:170-171)
+            raise SciconeError(-1, f"region_sizes has {r.size} entries for {self.K} regions")
+        neutral = np.ascontiguousarray(neutral_states if neutral_states is not None else [ploidy] * self.K, dtype=np.int32)
+        w = np.ascontiguousarray(cluster_sizes if cluster_sizes is not None else [1] * self.M, dtype=np.int32)
+        if neutral.shape != (self.K,) or w.shape != (self.M,):
+            raise SciconeError(-1, "neutral_states / cluster_sizes have the wrong length")
+        desc = DatasetDesc(self.M, self.K, _dp(D), _ip(r), _ip(neutral), _ip(w), float(eta), int(is_overdispersed),
+                           int(max_scoring), int(device), int(cell_offset),
+                           int(n_cells_global if n_cells_global is not None else self.M))
+        self.max_scoring = int(max_scoring)
+        self.is_overdispersed = int(is_overdispersed)
+        self._h = C.c_void_p()
+        _check(lib().scicone_dataset_create(C.byref(self._h), C.byref(desc)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scicone_dataset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def attach_comm(self, unique_id, rank, world_size):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().scicone_dataset_attach_comm(self._h, buf, rank, world_size))
+
+    def set_profiling(self, on=True):
+        _check(lib().scicone_set_profiling(self._h, int(on)))
+
+    def last_kernel_time_us(self):
+        out = C.c_double()
+        _check(lib().scicone_last_kernel_time_us(self._h, C.byref(out)))
+        return out.value
+
+    def kernel_launches(self):
+        out = C.c_uint64()
+        _check(lib().scicone_kernel_launches(self._h, C.byref(out)))
+        return out.value
+
+
+class Chain:
+    """Score tables of one MCMC chain == one reference ``Inference`` object (Inference.h:39-44)."""
+
+    def __init__(self, D=None, region_sizes=None, dataset=None, **kw):
+        self._own = dataset is None
+        self.ds = dataset if dataset is not None else Dataset(D, region_sizes, **kw)
+        self.M, self.K = self.ds.M, self.ds.K
+        self.max_scoring = self.ds.max_scoring
+        self._h = C.c_void_p()
+        _check(lib().scicone_chain_create(C.byref(self._h), self.ds._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scicone_chain_destroy(self._h)
+            self._h = None
+        if self._own and self.ds is not None:
+            self.ds.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Inference::compute_t_table, Inference.h:224-279
+    def compute_t_table(self, tree):
+        out = C.c_double()
+        _check(lib().scicone_compute_t_table(self._h, tree.byref(), C.byref(out)))
+        return out.value
+
+    # ---- Inference::compute_t_od_scores / compute_t_prime_od_scores, Inference.h:1406-1433
+    def compute_t_od_scores(self, nu):
+        out = C.c_double()
+        _check(lib().scicone_compute_t_od_scores(self._h, float(nu), C.byref(out)))
+        return out.value
+
+    def compute_t_prime_od_scores(self, nu):
+        out = C.c_double()
+        _check(lib().scicone_compute_t_prime_od_scores(self._h, float(nu), C.byref(out)))
+        return out.value
+
+    # ---- Inference::compute_t_prime_scores, Inference.h:1015-1052
+    def compute_t_prime_scores(self, tree, node_idx):
+        _check(lib().scicone_compute_t_prime_scores(self._h, tree.byref(), int(node_idx)))
+
+    # ---- Inference::compute_t_prime_sums (Inference.h:1069-1196) + the sum of comparison (:292-294)
+    def compute_t_prime_sums(self, tree):
+        out = C.c_double()
+        _check(lib().scicone_compute_t_prime_sums(self._h, tree.byref(), C.byref(out)))
+        return out.value
+
+    def accept(self, tree=None):
+        _check(lib().scicone_accept(self._h))
+
+    def reject(self):
+        _check(lib().scicone_reject(self._h))
+
+    def t_node_ids(self):
+        n = C.c_int32()
+        _check(lib().scicone_t_n_nodes(self._h, C.byref(n)))
+        ids = np.zeros(n.value, dtype=np.int32)
+        _check(lib().scicone_t_node_ids(self._h, _ip(ids)))
+        return ids
+
+    def read_t_scores(self):
+        n = len(self.t_node_ids())
+        out = np.zeros((self.M, n))
+        _check(lib().scicone_read_t_scores(self._h, _dp(out)))
+        return out
+
+    def read_t_sums(self):
+        out = np.zeros(self.M)
+        _check(lib().scicone_read_t_sums(self._h, _dp(out)))
+        return out
+
+    def read_t_maxs(self):
+        ids, vals = np.zeros(self.M, dtype=np.int32), np.zeros(self.M)
+        _check(lib().scicone_read_t_maxs(self._h, _ip(ids), _dp(vals)))
+        return ids, vals
+
+    def read_t_prime_sums(self):
+        out = np.zeros(self.M)
+        _check(lib().scicone_read_t_prime_sums(self._h, _dp(out)))
+        return out
+
+    def read_t_prime_maxs(self):
+        ids, vals = np.zeros(self.M, dtype=np.int32), np.zeros(self.M)
+        _check(lib().scicone_read_t_prime_maxs(self._h, _ip(ids), _dp(vals)))
+        return ids, vals
+
+    def read_t_prime_scores(self):
+        n = C.c_int32()
+        _check(lib().scicone_t_prime_n_rescored(self._h, C.byref(n)))
+        ids, out = np.zeros(n.value, dtype=np.int32), np.zeros((self.M, n.value))
+        _check(lib().scicone_read_t_prime_scores(self._h, _ip(ids), _dp(out)))
+        return ids, out
+
+    # ---- Inference::assign_cells_to_nodes, Inference.h:1346-1362
+    def assign_cells_to_nodes(self, tree, with_cn=True):
+        ids = np.zeros(self.M, dtype=np.int32)
+        cn = np.zeros((self.M, self.K), dtype=np.int32) if with_cn else None
+        _check(lib().scicone_assign_cells_to_nodes(self._h, tree.byref(), _ip(ids), _ip(cn) if with_cn else None))
+        return ids, cn
+
+
+def batch_compute_t_prime_sums(chains, trees):
+    """One kernel launch for the queued proposals of several chains on one dataset."""
+    n = len(chains)
+    hs = (C.c_void_p * n)(*[c._h for c in chains])
+    ts = (C.POINTER(CTree) * n)(*[C.pointer(t.ctree) for t in trees])
+    out = np.zeros(n)
+    _check(lib().scicone_batch_compute_t_prime_sums(hs, ts, n, _dp(out)))
+    return out

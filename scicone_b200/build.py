@@ -1,0 +1,50 @@
+"""Build the native parts in-tree (the .so files travel to the GPU box with the repo snapshot).
+
+  scicone_b200/lib/libscicone_score.so   CUDA kernels + C ABI (include/scicone_score.h), sm_100a only
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_DIR = os.path.join(HERE, "lib")
+CSRC = os.path.join(HERE, "csrc")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: the CUDA library cannot be built (and there is no CPU fallback)")
+    return exe
+
+
+def build_score_lib(force=False, verbose=False):
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = os.path.join(LIB_DIR, "libscicone_score.so")
+    srcs = [os.path.join(CSRC, "scicone_score.cu"), os.path.join(CSRC, "kernels.cuh"),
+            os.path.join(ROOT, "include", "scicone_score.h")]
+    if force or _newer(out, srcs):
+        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", out, srcs[0], "-ldl"]
+        subprocess.check_call(cmd)
+    return out
+
+
+def build_all(force=False, verbose=False):
+    return [build_score_lib(force, verbose)]
+
+
+if __name__ == "__main__":
+    for p in build_all(force="--force" in sys.argv, verbose="-v" in sys.argv):
+        print(p)

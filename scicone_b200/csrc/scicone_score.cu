@@ -1,0 +1,1167 @@
+// libscicone_score.so - host side of the B200 tree-scoring engine behind include/scicone_score.h.
+//
+// What lives where
+//   dataset  device copy of the count matrix (region-major Dt[K][Mp]), read totals S, cluster sizes w,
+//            the row pool (every device vector of Mp doubles comes from it), one CUDA stream, the pinned
+//            staging arena through which proposals travel, the reduction scratch, the NCCL communicator.
+//   chain    what one reference `Inference` object owns for scoring (scicone/src/Inference.h:39-44):
+//            the committed table t_scores as {node id -> score row, Node::z}, t_sums / t_maxs, the primed
+//            rows of the queued proposal, and the lgamma rows L(k, cn) of the chain's current nu.
+//
+// A proposal is compiled on the host into a small "blob" (header, one task per rescored node in
+// parent-before-child order, one event per touched region, aggregate bookkeeping) and evaluated by ONE
+// launch of score_proposals_kernel (kernels.cuh) - for any number of chains at once (grid.y).
+// Accept / reject are pointer swaps; no score is ever copied.
+//
+// There is no CPU implementation of any scoring step in this file: without a CUDA device every
+// compute entry point fails with SCICONE_ERR_CUDA.
+#include "../../include/scicone_score.h"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace scicone;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return fail(SCICONE_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                             \
+    } while (0)
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time so that single-GPU users need no NCCL at all.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) return false;
+        GetUniqueId = (int (*)(UniqueId*))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (int (*)(void**, int, UniqueId, int))dlsym(handle, "ncclCommInitRank");
+        CommDestroy = (int (*)(void*))dlsym(handle, "ncclCommDestroy");
+        AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(handle, "ncclAllGather");
+        GetErrorString = (const char* (*)(int))dlsym(handle, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclDouble = 8;  // ncclFloat64
+
+// ------------------------------------------------------------------------------------------------
+// Pool of device rows (Mp doubles each).  Slabs are only released with the dataset.
+// ------------------------------------------------------------------------------------------------
+struct RowPool {
+    size_t Mp = 0;
+    size_t rows_per_slab = 0;
+    std::vector<double*> free_rows;
+    std::vector<void*> slabs;
+    size_t n_rows = 0;
+
+    void init(size_t mp) {
+        Mp = mp;
+        const size_t row_bytes = Mp * sizeof(double);
+        rows_per_slab = std::max<size_t>(8, std::min<size_t>(512, (size_t(64) << 20) / row_bytes));
+    }
+    cudaError_t get(double** out) {
+        if (free_rows.empty()) {
+            void* p = nullptr;
+            cudaError_t e = cudaMalloc(&p, rows_per_slab * Mp * sizeof(double));
+            if (e != cudaSuccess) return e;
+            slabs.push_back(p);
+            for (size_t i = rows_per_slab; i-- > 0;) free_rows.push_back(static_cast<double*>(p) + i * Mp);
+            n_rows += rows_per_slab;
+        }
+        *out = free_rows.back();
+        free_rows.pop_back();
+        return cudaSuccess;
+    }
+    void put(double* r) {
+        if (r) free_rows.push_back(r);
+    }
+    void destroy() {
+        for (void* p : slabs) cudaFree(p);
+        slabs.clear();
+        free_rows.clear();
+    }
+};
+
+struct NodeRow {
+    double* row;
+    int z;  // Node::z, an int in the reference (scicone/src/Node.h:25)
+};
+
+// Host copy of a scicone_tree (the caller's buffers are only valid during the call).
+struct TreeCopy {
+    int n = 0;
+    double nu = 0.0;
+    std::vector<int> id, parent, chg_off, chg_region, chg_value, gen_off, gen_region, gen_value;
+    void assign(const scicone_tree* t) {
+        n = t->n_nodes;
+        nu = t->nu;
+        id.assign(t->node_id, t->node_id + n);
+        parent.assign(t->parent, t->parent + n);
+        chg_off.assign(t->chg_off, t->chg_off + n + 1);
+        chg_region.assign(t->chg_region, t->chg_region + chg_off[n]);
+        chg_value.assign(t->chg_value, t->chg_value + chg_off[n]);
+        gen_off.assign(t->gen_off, t->gen_off + n + 1);
+        gen_region.assign(t->gen_region, t->gen_region + gen_off[n]);
+        gen_value.assign(t->gen_value, t->gen_value + gen_off[n]);
+    }
+    // node->c.count(k) ? node->c[k] : 0   (scicone/src/Tree.h:189-190)
+    int genotype_at(int node, int k) const {
+        const int* b = gen_region.data() + gen_off[node];
+        const int* e = gen_region.data() + gen_off[node + 1];
+        const int* it = std::lower_bound(b, e, k);
+        return (it != e && *it == k) ? gen_value[it - gen_region.data()] : 0;
+    }
+};
+
+int validate_tree(const scicone_tree* t, int K) {
+    if (!t || t->n_nodes <= 0 || !t->node_id || !t->parent || !t->chg_off || !t->gen_off)
+        return fail(SCICONE_ERR_ARG, "tree: null or empty");
+    if (t->parent[0] != -1) return fail(SCICONE_ERR_ARG, "tree: entry 0 must be the root");
+    for (int i = 1; i < t->n_nodes; ++i)
+        if (t->parent[i] < 0 || t->parent[i] >= i)
+            return fail(SCICONE_ERR_ARG, "tree: entries must be parent-before-child (entry %d has parent %d)", i, t->parent[i]);
+    for (int i = 0; i < t->n_nodes; ++i) {
+        if (t->node_id[i] < 0) return fail(SCICONE_ERR_ARG, "tree: negative node id");
+        if (t->chg_off[i + 1] < t->chg_off[i] || t->gen_off[i + 1] < t->gen_off[i])
+            return fail(SCICONE_ERR_ARG, "tree: CSR offsets not monotone");
+        for (int e = t->chg_off[i]; e < t->chg_off[i + 1]; ++e)
+            if (t->chg_region[e] < 0 || t->chg_region[e] >= K)  // reference: D.size() != r.size() -> std::logic_error
+                return fail(SCICONE_ERR_ARG, "tree: event region %d outside [0,%d)", t->chg_region[e], K);
+        for (int e = t->gen_off[i]; e < t->gen_off[i + 1]; ++e)
+            if (t->gen_region[e] < 0 || t->gen_region[e] >= K)
+                return fail(SCICONE_ERR_ARG, "tree: genotype region %d outside [0,%d)", t->gen_region[e], K);
+    }
+    return SCICONE_OK;
+}
+
+typedef std::unordered_map<uint64_t, double*> LCache;  // (region, copy number) -> lgamma row
+inline uint64_t lkey(int k, int cn) { return (uint64_t(uint32_t(k)) << 32) | uint32_t(cn); }
+
+}  // namespace
+
+// ================================================================================================
+struct scicone_dataset {
+    int M = 0, K = 0;
+    size_t Mp = 0;
+    int device = 0;
+    double eta = 0;
+    bool od = false, maxs = false;
+    long long cell_offset = 0, M_global = 0;
+    std::vector<int> r, neutral;
+    int root_z = 0;  // Tree::compute_root_score, Tree.h:145-160
+    long long sum_r = 0;
+
+    double* dDt = nullptr;
+    double* dS = nullptr;
+    int* dW = nullptr;
+    cudaStream_t stream = nullptr;
+    RowPool pool;
+
+    // staging arena (proposal blobs), pinned + device
+    unsigned char* h_arena = nullptr;
+    unsigned char* d_arena = nullptr;
+    size_t arena_cap = 0;
+    // per batch slot: reduction scratch and results
+    int n_cta = 0, n_chunks = 0;
+    int slots = 0;
+    double* d_partial = nullptr;  // [slots][n_cta]
+    double* d_chunk = nullptr;    // [slots][n_chunks]
+    double* d_total = nullptr;    // [slots]
+    unsigned* d_counter = nullptr;
+    unsigned* d_status = nullptr;
+    double* h_total = nullptr;    // pinned [slots]
+    unsigned* h_status = nullptr; // pinned [slots]
+    // multi-GPU
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    int max_chunks_rank = 0;
+    double* d_gather = nullptr;  // [world][slots][max_chunks_rank]
+    double* d_send = nullptr;    // [slots][max_chunks_rank]
+    double* h_gather = nullptr;
+    size_t gather_cap = 0;
+    // profiling
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_kernel_us = 0.0;
+    unsigned long long n_launches = 0;
+
+    int set_device() const {
+        CUDA_TRY(cudaSetDevice(device));
+        return SCICONE_OK;
+    }
+    int ensure_arena(size_t bytes) {
+        if (bytes <= arena_cap) return SCICONE_OK;
+        size_t cap = std::max<size_t>(bytes * 2, size_t(1) << 16);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (h_arena) cudaFreeHost(h_arena);
+        if (d_arena) cudaFree(d_arena);
+        h_arena = nullptr;
+        d_arena = nullptr;
+        arena_cap = 0;
+        CUDA_TRY(cudaMallocHost(&h_arena, cap));
+        CUDA_TRY(cudaMalloc(&d_arena, cap));
+        arena_cap = cap;
+        return SCICONE_OK;
+    }
+    int ensure_slots(int n) {
+        if (n <= slots) return SCICONE_OK;
+        int ns = std::max(n, std::max(4, slots * 2));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(d_partial); cudaFree(d_chunk); cudaFree(d_total); cudaFree(d_counter); cudaFree(d_status);
+        if (h_total) cudaFreeHost(h_total);
+        if (h_status) cudaFreeHost(h_status);
+        d_partial = d_chunk = d_total = nullptr;
+        d_counter = d_status = nullptr;
+        h_total = nullptr;
+        h_status = nullptr;
+        slots = 0;
+        CUDA_TRY(cudaMalloc(&d_partial, sizeof(double) * size_t(ns) * n_cta));
+        CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * size_t(ns) * n_chunks));
+        CUDA_TRY(cudaMalloc(&d_total, sizeof(double) * ns));
+        CUDA_TRY(cudaMalloc(&d_counter, sizeof(unsigned) * ns));
+        CUDA_TRY(cudaMalloc(&d_status, sizeof(unsigned) * ns));
+        CUDA_TRY(cudaMemset(d_counter, 0, sizeof(unsigned) * ns));
+        CUDA_TRY(cudaMemset(d_status, 0, sizeof(unsigned) * ns));
+        CUDA_TRY(cudaMallocHost(&h_total, sizeof(double) * ns));
+        CUDA_TRY(cudaMallocHost(&h_status, sizeof(unsigned) * ns));
+        slots = ns;
+        if (world > 1) {
+            cudaFree(d_gather); cudaFree(d_send);
+            if (h_gather) cudaFreeHost(h_gather);
+            d_gather = d_send = nullptr;
+            h_gather = nullptr;
+            size_t per_rank = size_t(ns) * max_chunks_rank;
+            CUDA_TRY(cudaMalloc(&d_send, sizeof(double) * per_rank));
+            CUDA_TRY(cudaMalloc(&d_gather, sizeof(double) * per_rank * world));
+            CUDA_TRY(cudaMallocHost(&h_gather, sizeof(double) * per_rank * world));
+            CUDA_TRY(cudaMemset(d_send, 0, sizeof(double) * per_rank));
+            gather_cap = per_rank;
+        }
+        return SCICONE_OK;
+    }
+};
+
+struct scicone_chain {
+    scicone_dataset* ds = nullptr;
+    std::map<int, NodeRow> t;  // committed table, ascending node id (std::map order of the reference)
+    double* sums[2] = {nullptr, nullptr};  // [0] committed t_sums, [1] primed
+    int* maxid[2] = {nullptr, nullptr};
+    // lgamma rows of the committed nu and of a proposed nu
+    LCache Lt, Lp;
+    double Lt_nu = 0.0, Lp_nu = 0.0;
+    bool Lt_valid = false, Lp_valid = false;
+    // queued proposal
+    bool pending = false;
+    bool evaluated = false;
+    TreeCopy tp;
+    std::vector<int> roots;
+    std::map<int, NodeRow> p;  // rescored node id -> primed row
+    int deleted_id = -1;
+    bool p_full = false;
+    // blob under construction
+    std::vector<unsigned char> blob;
+};
+
+namespace {
+
+void release_cache(scicone_dataset* ds, LCache& c) {
+    for (auto& kv : c) ds->pool.put(kv.second);
+    c.clear();
+}
+
+LCache* cache_for(scicone_chain* ch, double nu) {
+    if (ch->Lt_valid && ch->Lt_nu == nu) return &ch->Lt;
+    if (!ch->Lt_valid) {
+        ch->Lt_valid = true;
+        ch->Lt_nu = nu;
+        return &ch->Lt;
+    }
+    if (ch->Lp_valid && ch->Lp_nu == nu) return &ch->Lp;
+    release_cache(ch->ds, ch->Lp);
+    ch->Lp_valid = true;
+    ch->Lp_nu = nu;
+    return &ch->Lp;
+}
+
+void drop_pending(scicone_chain* ch) {
+    for (auto& kv : ch->p) ch->ds->pool.put(kv.second.row);
+    ch->p.clear();
+    ch->roots.clear();
+    ch->pending = false;
+    ch->evaluated = false;
+    ch->deleted_id = -1;
+    ch->p_full = false;
+    release_cache(ch->ds, ch->Lp);
+    ch->Lp_valid = false;
+}
+
+template <class T>
+size_t blob_append(std::vector<unsigned char>& b, const std::vector<T>& v) {
+    size_t off = round_up(b.size(), 16);
+    b.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
+    if (!v.empty()) memcpy(b.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+}
+
+// Compile the queued proposal of `ch` into ch->blob.  `slot` selects the reduction scratch.
+int compile_proposal(scicone_chain* ch, int slot, bool full) {
+    scicone_dataset* ds = ch->ds;
+    const TreeCopy& T = ch->tp;
+    const double nu = T.nu;
+    const bool od = ds->od;
+    LCache* L = od ? cache_for(ch, nu) : nullptr;
+
+    std::vector<int> child_off(T.n + 1, 0), child(T.n > 1 ? T.n - 1 : 0);
+    for (int i = 1; i < T.n; ++i) child_off[T.parent[i] + 1]++;
+    for (int i = 0; i < T.n; ++i) child_off[i + 1] += child_off[i];
+    {
+        std::vector<int> fill(child_off.begin(), child_off.end() - 1);
+        for (int i = 1; i < T.n; ++i) child[fill[T.parent[i]]++] = i;
+    }
+
+    std::vector<DevTask> tasks;
+    std::vector<DevEvent> events;
+    std::vector<int> task_of_node(T.n, -1);
+    std::vector<short> free_slots;
+    for (short s = kSlots - 1; s >= 0; --s) free_slots.push_back(s);
+
+    struct Frame { int node; bool post; };
+    std::vector<Frame> stack;
+    for (size_t ri = 0; ri < ch->roots.size(); ++ri) {
+        const int root = ch->roots[ri];
+        stack.push_back({root, false});
+        while (!stack.empty()) {
+            Frame f = stack.back();
+            stack.pop_back();
+            const int n = f.node;
+            if (f.post) {  // all descendants emitted: the shared-memory slot is free again
+                const short s = tasks[task_of_node[n]].own_slot;
+                if (s >= 0) free_slots.push_back(s);
+                continue;
+            }
+            const int id = T.id[n];
+            const int pidx = T.parent[n];
+            DevTask tk;
+            memset(&tk, 0, sizeof tk);
+            tk.node_id = id;
+            tk.parent_slot = tk.own_slot = -1;
+            tk.ev_begin = tk.ev_end = (int)events.size();
+            int z_int;
+            if (pidx < 0) {  // Tree::compute_root_score, Tree.h:145-160
+                tk.flags = TASK_ROOT;
+                z_int = ds->root_z;
+                tk.nz = nu * (double)z_int;
+            } else {
+                const int pid = T.id[pidx];
+                int pz;
+                const bool is_subtree_root = (n == root);
+                auto pit = ch->p.find(pid);
+                if (is_subtree_root) {
+                    // Inference.h:1034: the parent's score is restored from the COMMITTED table;
+                    // its Node::z is whatever the tree copy carries (primed if rescored before, else committed).
+                    auto cit = ch->t.find(pid);
+                    if (cit == ch->t.end())
+                        return fail(SCICONE_ERR_STATE, "parent id %d of the rescored subtree is not in the committed table", pid);
+                    tk.parent_row = cit->second.row;
+                    pz = (pit != ch->p.end()) ? pit->second.z : cit->second.z;
+                } else {
+                    const DevTask& ptk = tasks[task_of_node[pidx]];
+                    if (ptk.own_slot >= 0)
+                        tk.parent_slot = ptk.own_slot;
+                    else
+                        tk.parent_row = ptk.dst;
+                    pz = pit->second.z;
+                }
+                // Tree::compute_score, Tree.h:177-198: z = parent.z + sum_k r_k (cn_node - cn_parent)
+                double zd = (double)pz;
+                const double zp = (double)pz;
+                for (int e = T.chg_off[n]; e < T.chg_off[n + 1]; ++e) {
+                    const int k = T.chg_region[e];
+                    const int cn_i = T.genotype_at(n, k) + ds->neutral[k];
+                    const int cp_i = T.genotype_at(pidx, k) + ds->neutral[k];
+                    const double node_cn = cn_i == 0 ? ds->eta : (double)cn_i;
+                    const double parent_cn = cp_i == 0 ? ds->eta : (double)cp_i;
+                    zd += ds->r[k] * (node_cn - parent_cn);
+                }
+                for (int e = T.chg_off[n]; e < T.chg_off[n + 1]; ++e) {
+                    const int k = T.chg_region[e];
+                    const int cn_i = T.genotype_at(n, k) + ds->neutral[k];
+                    const int cp_i = T.genotype_at(pidx, k) + ds->neutral[k];
+                    const double node_cn = cn_i == 0 ? ds->eta : (double)cn_i;
+                    const double parent_cn = cp_i == 0 ? ds->eta : (double)cp_i;
+                    DevEvent ev;
+                    memset(&ev, 0, sizeof ev);
+                    ev.drow = ds->dDt + (size_t)k * ds->Mp;
+                    if (od) {  // Tree.h:214-218
+                        ev.argN = nu * node_cn * ds->r[k];
+                        ev.argP = nu * parent_cn * ds->r[k];
+                        ev.cN = lgamma(ev.argN);
+                        ev.cP = lgamma(ev.argP);
+                        double** slotN = &(*L)[lkey(k, cn_i)];
+                        if (!*slotN) {
+                            CUDA_TRY(ds->pool.get(slotN));
+                            ev.flags |= EV_BUILD_N;
+                        }
+                        ev.rowN = *slotN;
+                        double** slotP = &(*L)[lkey(k, cp_i)];
+                        if (!*slotP) {
+                            CUDA_TRY(ds->pool.get(slotP));
+                            ev.flags |= EV_BUILD_P;
+                        }
+                        ev.rowP = *slotP;
+                    } else  // Tree.h:221
+                        ev.cN = log(node_cn) - log(parent_cn);
+                    events.push_back(ev);
+                }
+                tk.ev_end = (int)events.size();
+                if (od) {  // Tree.h:227-231
+                    tk.nz = nu * zd;
+                    tk.nzp = nu * zp;
+                    tk.lg_nz = lgamma(tk.nz);
+                    tk.lg_nzp = lgamma(tk.nzp);
+                    if (tk.parent_slot >= 0) {
+                        const DevTask& ptk = tasks[task_of_node[pidx]];
+                        if (memcmp(&ptk.nz, &tk.nzp, sizeof(double)) == 0) tk.flags |= TASK_REUSE_G;
+                    }
+                } else {  // Tree.h:236-237
+                    tk.lg_nz = log(zd);
+                    tk.lg_nzp = log(zp);
+                }
+                z_int = (int)zd;  // Tree.h:241 into the int Node::z (quirk Q1)
+            }
+            auto own = ch->p.find(id);
+            if (own == ch->p.end()) {
+                double* row = nullptr;
+                CUDA_TRY(ds->pool.get(&row));
+                own = ch->p.emplace(id, NodeRow{row, z_int}).first;
+            } else
+                own->second.z = z_int;
+            tk.dst = own->second.row;
+            const int nc = child_off[n + 1] - child_off[n];
+            if (nc > 0 && !free_slots.empty()) {
+                tk.own_slot = free_slots.back();
+                free_slots.pop_back();
+            }
+            task_of_node[n] = (int)tasks.size();
+            tasks.push_back(tk);
+            if (nc > 0) {
+                stack.push_back({n, true});
+                for (int c = child_off[n + 1] - 1; c >= child_off[n]; --c) stack.push_back({child[c], false});
+            }
+        }
+    }
+
+    // aggregate bookkeeping: Inference::compute_t_prime_sums, Inference.h:1069-1196
+    std::map<int, int> by_id;  // rescored id -> last task writing it (std::map order = ascending id)
+    for (size_t i = 0; i < tasks.size(); ++i) by_id[tasks[i].node_id] = (int)i;
+    std::vector<int> addorder;
+    for (auto& kv : by_id) addorder.push_back(kv.second);
+    std::vector<const double*> old_rows;
+    std::vector<DevUnch> unch;
+    ch->deleted_id = -1;
+    if (!full) {
+        // Inference::deleted_node_idx, Inference.h:1270-1289
+        if ((size_t)T.n < ch->t.size()) {
+            std::vector<char> present;
+            for (auto& kv : ch->t) {
+                bool found = false;
+                for (int i = 0; i < T.n && !found; ++i) found = (T.id[i] == kv.first);
+                if (!found) ch->deleted_id = kv.first;
+            }
+        }
+        for (auto& kv : ch->p) {
+            auto it = ch->t.find(kv.first);
+            if (it != ch->t.end()) old_rows.push_back(it->second.row);
+        }
+        if (ch->deleted_id != -1) old_rows.push_back(ch->t[ch->deleted_id].row);
+        for (auto& kv : ch->t)
+            if (!ch->p.count(kv.first) && kv.first != ch->deleted_id) {
+                DevUnch u;
+                u.row = kv.second.row;
+                u.id = kv.first;
+                u.pad = 0;
+                unch.push_back(u);
+            }
+    }
+
+    DevHeader H;
+    memset(&H, 0, sizeof H);
+    H.n_tasks = (int)tasks.size();
+    H.n_add = (int)addorder.size();
+    H.n_old = (int)old_rows.size();
+    H.n_unch = (int)unch.size();
+    H.deleted_id = ch->deleted_id;
+    H.flags = (ds->maxs ? PROP_MAX : 0u) | (od ? PROP_OD : 0u) | (full ? PROP_FULL : 0u);
+    if (!full && addorder.size() >= unch.size()) H.flags |= PROP_SCRATCH;  // MathOp.cpp:315
+    H.n_cells = ds->M;
+    H.S = ds->dS;
+    H.w = ds->dW;
+    H.sums_old = ch->sums[0];
+    H.sums_new = ch->sums[1];
+    H.maxid_old = ch->maxid[0];
+    H.maxid_new = ch->maxid[1];
+    H.partial = ds->d_partial + (size_t)slot * ds->n_cta;
+    H.chunk_sums = ds->d_chunk + (size_t)slot * ds->n_chunks;
+    H.total = ds->d_total + slot;
+    H.counter = ds->d_counter + slot;
+    H.status = ds->d_status + slot;
+
+    std::vector<unsigned char>& b = ch->blob;
+    b.clear();
+    b.resize(sizeof(DevHeader));
+    H.off_tasks = (unsigned)blob_append(b, tasks);
+    H.off_events = (unsigned)blob_append(b, events);
+    H.off_addorder = (unsigned)blob_append(b, addorder);
+    H.off_old = (unsigned)blob_append(b, old_rows);
+    H.off_unch = (unsigned)blob_append(b, unch);
+    b.resize(round_up(b.size(), 16));
+    memcpy(b.data(), &H, sizeof H);
+    return SCICONE_OK;
+}
+
+// Launch the compiled blobs of `n` chains (all on one dataset) and fetch their totals.
+int launch_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, double* totals) {
+    size_t head = round_up(sizeof(unsigned) * n, 16);
+    size_t bytes = head;
+    for (int i = 0; i < n; ++i) bytes += chains[i]->blob.size();
+    int rc = ds->ensure_arena(bytes);
+    if (rc) return rc;
+    unsigned* offs = reinterpret_cast<unsigned*>(ds->h_arena);
+    size_t at = head;
+    for (int i = 0; i < n; ++i) {
+        offs[i] = (unsigned)at;
+        memcpy(ds->h_arena + at, chains[i]->blob.data(), chains[i]->blob.size());
+        at += chains[i]->blob.size();
+    }
+    CUDA_TRY(cudaMemcpyAsync(ds->d_arena, ds->h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
+    if (ds->profiling) CUDA_TRY(cudaEventRecord(ds->ev0, ds->stream));
+    score_proposals_kernel<<<dim3(ds->n_cta, n), kBlock, 0, ds->stream>>>(ds->d_arena);
+    if (ds->profiling) CUDA_TRY(cudaEventRecord(ds->ev1, ds->stream));
+    CUDA_TRY(cudaGetLastError());
+    ds->n_launches++;
+    if (ds->world > 1) {
+        // Each rank contributes its per-chunk sums; every rank adds all chunks in global chunk order,
+        // so the total does not depend on the number of GPUs.
+        pack_chunks_kernel<<<n, 128, 0, ds->stream>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
+        CUDA_TRY(cudaGetLastError());
+        const size_t cnt = (size_t)n * ds->max_chunks_rank;
+        int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, ds->stream);
+        if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
+        CUDA_TRY(cudaMemcpyAsync(ds->h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
+    } else
+        CUDA_TRY(cudaMemcpyAsync(ds->h_total, ds->d_total, sizeof(double) * n, cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaMemcpyAsync(ds->h_status, ds->d_status, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaStreamSynchronize(ds->stream));
+    if (ds->profiling) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ds->ev0, ds->ev1));
+        ds->last_kernel_us = 1e3 * ms;
+    }
+    bool nan = false;
+    for (int i = 0; i < n; ++i) {
+        if (ds->world > 1) {
+            double s = 0.0;
+            for (int rk = 0; rk < ds->world; ++rk) {
+                const double* c = ds->h_gather + ((size_t)rk * n + i) * ds->max_chunks_rank;
+                for (int q = 0; q < ds->max_chunks_rank; ++q) s += c[q];
+            }
+            totals[i] = s;
+        } else
+            totals[i] = ds->h_total[i];
+        if (ds->h_status[i]) nan = true;
+    }
+    if (nan) {
+        CUDA_TRY(cudaMemsetAsync(ds->d_status, 0, sizeof(unsigned) * n, ds->stream));
+        return fail(SCICONE_ERR_NAN, "a per-cell aggregate is NaN (reference: assert(!isnan), Inference.h:1150,1191)");
+    }
+    return SCICONE_OK;
+}
+
+int od_scores(scicone_chain* ch, double nu, double* out) {
+    scicone_dataset* ds = ch->ds;
+    int rc = ds->set_device();
+    if (rc) return rc;
+    rc = ds->ensure_slots(1);
+    if (rc) return rc;
+    const int K = ds->K;
+    std::vector<double*> rows(K, nullptr);
+    std::vector<double> arg(K), cc(K);
+    std::vector<unsigned char> build(round_up(K, 16), 0);
+    DevOdHeader H;
+    memset(&H, 0, sizeof H);
+    H.n_regions = K;
+    H.n_cells = ds->M;
+    H.flags = ds->od ? PROP_OD : 0u;
+    H.S = ds->dS;
+    H.w = ds->dW;
+    H.Dt = ds->dDt;
+    H.row_stride = (long long)ds->Mp;
+    H.partial = ds->d_partial;
+    H.chunk_sums = ds->d_chunk;
+    H.total = ds->d_total;
+    H.counter = ds->d_counter;
+    if (ds->od) {  // Tree::get_od_root_score, Tree.h:1783-1797 (no eta substitution here, quirk Q2)
+        LCache* L = cache_for(ch, nu);
+        H.nz = nu * ds->root_z;
+        H.lg_nz = lgamma(H.nz);
+        for (int k = 0; k < K; ++k) {
+            arg[k] = nu * ds->neutral[k] * ds->r[k];
+            cc[k] = lgamma(arg[k]);
+            if (ds->neutral[k] != 0) {  // L(k, 0) means eta in compute_score: do not alias it
+                double** slot = &(*L)[lkey(k, ds->neutral[k])];
+                if (!*slot) {
+                    CUDA_TRY(ds->pool.get(slot));
+                    build[k] = 1;
+                }
+                rows[k] = *slot;
+            } else
+                build[k] = 1;
+        }
+    } else {  // Tree.h:1799-1806
+        H.lg_nz = log((double)ds->sum_r);
+        for (int k = 0; k < K; ++k) arg[k] = log((double)ds->r[k]);
+    }
+    std::vector<unsigned char> b(sizeof H);
+    H.off_rows = (unsigned)blob_append(b, rows);
+    H.off_arg = (unsigned)blob_append(b, arg);
+    H.off_c = (unsigned)blob_append(b, cc);
+    H.off_build = (unsigned)blob_append(b, build);
+    b.resize(round_up(b.size(), 16));
+    memcpy(b.data(), &H, sizeof H);
+    const size_t head = 16;
+    rc = ds->ensure_arena(head + b.size());
+    if (rc) return rc;
+    reinterpret_cast<unsigned*>(ds->h_arena)[0] = (unsigned)head;
+    memcpy(ds->h_arena + head, b.data(), b.size());
+    CUDA_TRY(cudaMemcpyAsync(ds->d_arena, ds->h_arena, head + b.size(), cudaMemcpyHostToDevice, ds->stream));
+    od_root_kernel<<<dim3(ds->n_cta, 1), kBlock, 0, ds->stream>>>(ds->d_arena);
+    CUDA_TRY(cudaGetLastError());
+    ds->n_launches++;
+    double total = 0.0;
+    if (ds->world > 1) {
+        pack_chunks_kernel<<<1, 128, 0, ds->stream>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
+        const size_t cnt = ds->max_chunks_rank;
+        int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, ds->stream);
+        if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
+        CUDA_TRY(cudaMemcpyAsync(ds->h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaStreamSynchronize(ds->stream));
+        for (size_t q = 0; q < cnt * ds->world; ++q) total += ds->h_gather[q];
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(ds->h_total, ds->d_total, sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaStreamSynchronize(ds->stream));
+        total = ds->h_total[0];
+    }
+    if (out) *out = total;
+    return SCICONE_OK;
+}
+
+int gather_rows(scicone_dataset* ds, const std::vector<const double*>& rows, double* out) {
+    const int n = (int)rows.size();
+    if (n == 0 || ds->M == 0) return SCICONE_OK;
+    const double** d_rows = nullptr;
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_rows, sizeof(double*) * n));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)n * ds->M);
+    if (e != cudaSuccess) {
+        cudaFree(d_rows);
+        return fail(SCICONE_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    cudaMemcpyAsync(d_rows, rows.data(), sizeof(double*) * n, cudaMemcpyHostToDevice, ds->stream);
+    dim3 grid((n + 31) / 32, (ds->M + 31) / 32), block(32, 8);
+    gather_rows_kernel<<<grid, block, 0, ds->stream>>>(d_rows, n, ds->M, d_out);
+    cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n * ds->M, cudaMemcpyDeviceToHost, ds->stream);
+    e = cudaStreamSynchronize(ds->stream);
+    cudaFree(d_rows);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(SCICONE_ERR_CUDA, "gather_rows: %s", cudaGetErrorString(e));
+    return SCICONE_OK;
+}
+
+template <class T>
+int read_vec(scicone_dataset* ds, const T* dev, T* out, size_t n) {
+    CUDA_TRY(cudaMemcpyAsync(out, dev, sizeof(T) * n, cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaStreamSynchronize(ds->stream));
+    return SCICONE_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int scicone_abi_version(void) { return SCICONE_ABI_VERSION; }
+const char* scicone_last_error(void) { return g_err.c_str(); }
+
+int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d) {
+    if (!out || !d) return fail(SCICONE_ERR_ARG, "dataset_create: null argument");
+    *out = nullptr;
+    if (d->n_cells <= 0 || d->n_regions <= 0 || !d->D || !d->region_sizes || !d->neutral_states || !d->cluster_sizes)
+        return fail(SCICONE_ERR_ARG, "dataset_create: empty matrix or null buffer (n_cells=%d, n_regions=%d)", d->n_cells, d->n_regions);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(SCICONE_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (d->device < 0 || d->device >= n_dev) return fail(SCICONE_ERR_ARG, "device %d out of range (%d devices)", d->device, n_dev);
+    scicone_dataset* ds = new scicone_dataset();
+    ds->M = d->n_cells;
+    ds->K = d->n_regions;
+    ds->Mp = round_up(ds->M, kBlock);
+    ds->device = d->device;
+    ds->eta = d->eta;
+    ds->od = d->is_overdispersed != 0;
+    ds->maxs = d->max_scoring != 0;
+    ds->cell_offset = d->cell_offset;
+    ds->M_global = d->n_cells_global > 0 ? d->n_cells_global : d->n_cells;
+    ds->r.assign(d->region_sizes, d->region_sizes + ds->K);
+    ds->neutral.assign(d->neutral_states, d->neutral_states + ds->K);
+    for (int k = 0; k < ds->K; ++k) {
+        ds->root_z += ds->r[k] * ds->neutral[k];
+        ds->sum_r += ds->r[k];
+    }
+    ds->n_cta = (int)(ds->Mp / kBlock);
+    ds->n_chunks = (ds->n_cta + kCtasPerChunk - 1) / kCtasPerChunk;
+    ds->pool.init(ds->Mp);
+    auto cleanup = [&](int rc) {
+        scicone_dataset_destroy(ds);
+        return rc;
+    };
+#define DS_TRY(expr)                                                                                         \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return cleanup(fail(SCICONE_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+    DS_TRY(cudaSetDevice(ds->device));
+    DS_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+    DS_TRY(cudaEventCreate(&ds->ev0));
+    DS_TRY(cudaEventCreate(&ds->ev1));
+    DS_TRY(cudaMalloc(&ds->dDt, sizeof(double) * ds->Mp * ds->K));
+    DS_TRY(cudaMalloc(&ds->dS, sizeof(double) * ds->Mp));
+    DS_TRY(cudaMalloc(&ds->dW, sizeof(int) * ds->Mp));
+    DS_TRY(cudaMemsetAsync(ds->dDt, 0, sizeof(double) * ds->Mp * ds->K, ds->stream));
+    DS_TRY(cudaMemsetAsync(ds->dW, 0, sizeof(int) * ds->Mp, ds->stream));
+    DS_TRY(cudaMemsetAsync(ds->dS, 0, sizeof(double) * ds->Mp, ds->stream));
+    {
+        double* dD = nullptr;
+        DS_TRY(cudaMalloc(&dD, sizeof(double) * (size_t)ds->M * ds->K));
+        cudaError_t e1 = cudaMemcpyAsync(dD, d->D, sizeof(double) * (size_t)ds->M * ds->K, cudaMemcpyHostToDevice, ds->stream);
+        dim3 grid((ds->K + 31) / 32, (ds->M + 31) / 32), block(32, 8);
+        transpose_kernel<<<grid, block, 0, ds->stream>>>(dD, ds->dDt, ds->M, ds->K, (long long)ds->Mp);
+        row_sum_kernel<<<(ds->M + 127) / 128, 128, 0, ds->stream>>>(ds->dDt, ds->dS, ds->M, ds->K, (long long)ds->Mp);
+        cudaError_t e2 = cudaMemcpyAsync(ds->dW, d->cluster_sizes, sizeof(int) * ds->M, cudaMemcpyHostToDevice, ds->stream);
+        cudaError_t e3 = cudaStreamSynchronize(ds->stream);
+        cudaFree(dD);
+        DS_TRY(e1);
+        DS_TRY(e2);
+        DS_TRY(e3);
+        DS_TRY(cudaGetLastError());
+    }
+#undef DS_TRY
+    int rc = ds->ensure_slots(4);
+    if (rc) return cleanup(rc);
+    rc = ds->ensure_arena(size_t(1) << 16);
+    if (rc) return cleanup(rc);
+    *out = ds;
+    return SCICONE_OK;
+}
+
+void scicone_dataset_destroy(scicone_dataset* ds) {
+    if (!ds) return;
+    cudaSetDevice(ds->device);
+    if (ds->stream) cudaStreamSynchronize(ds->stream);
+    if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm);
+    ds->pool.destroy();
+    cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW);
+    cudaFree(ds->d_arena); cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
+    cudaFree(ds->d_counter); cudaFree(ds->d_status); cudaFree(ds->d_gather); cudaFree(ds->d_send);
+    if (ds->h_arena) cudaFreeHost(ds->h_arena);
+    if (ds->h_total) cudaFreeHost(ds->h_total);
+    if (ds->h_status) cudaFreeHost(ds->h_status);
+    if (ds->h_gather) cudaFreeHost(ds->h_gather);
+    if (ds->ev0) cudaEventDestroy(ds->ev0);
+    if (ds->ev1) cudaEventDestroy(ds->ev1);
+    if (ds->stream) cudaStreamDestroy(ds->stream);
+    delete ds;
+}
+
+int scicone_chain_create(scicone_chain** out, scicone_dataset* ds) {
+    if (!out || !ds) return fail(SCICONE_ERR_ARG, "chain_create: null argument");
+    *out = nullptr;
+    int rc = ds->set_device();
+    if (rc) return rc;
+    scicone_chain* ch = new scicone_chain();
+    ch->ds = ds;
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaMalloc(&ch->sums[i], sizeof(double) * ds->Mp);
+        if (e == cudaSuccess) e = cudaMalloc(&ch->maxid[i], sizeof(int) * ds->Mp);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ch->sums[i], 0, sizeof(double) * ds->Mp, ds->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ch->maxid[i], 0, sizeof(int) * ds->Mp, ds->stream);
+        if (e != cudaSuccess) {
+            scicone_chain_destroy(ch);
+            return fail(SCICONE_ERR_CUDA, "chain_create: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = ch;
+    return SCICONE_OK;
+}
+
+void scicone_chain_destroy(scicone_chain* ch) {
+    if (!ch) return;
+    scicone_dataset* ds = ch->ds;
+    cudaSetDevice(ds->device);
+    cudaStreamSynchronize(ds->stream);
+    drop_pending(ch);
+    for (auto& kv : ch->t) ds->pool.put(kv.second.row);
+    release_cache(ds, ch->Lt);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(ch->sums[i]);
+        cudaFree(ch->maxid[i]);
+    }
+    delete ch;
+}
+
+int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* t_sum) {
+    if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    scicone_dataset* ds = ch->ds;
+    int rc = validate_tree(t, ds->K);
+    if (rc) return rc;
+    rc = ds->set_device();
+    if (rc) return rc;
+    drop_pending(ch);
+    for (auto& kv : ch->t) ds->pool.put(kv.second.row);
+    ch->t.clear();
+    if (ch->Lt_valid && ch->Lt_nu != t->nu) {
+        release_cache(ds, ch->Lt);
+        ch->Lt_valid = false;
+    }
+    ch->tp.assign(t);
+    ch->roots.assign(1, 0);
+    ch->pending = true;
+    ch->p_full = true;
+    rc = ds->ensure_slots(1);
+    if (!rc) rc = compile_proposal(ch, 0, true);
+    double total = 0.0;
+    if (!rc) rc = launch_proposals(ds, &ch, 1, &total);
+    if (rc && rc != SCICONE_ERR_NAN) {
+        drop_pending(ch);
+        return rc;
+    }
+    ch->evaluated = true;
+    int rc2 = scicone_accept(ch);
+    if (t_sum) *t_sum = total;
+    return rc ? rc : rc2;
+}
+
+int scicone_compute_t_od_scores(scicone_chain* ch, double nu, double* od_score) {
+    if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    return od_scores(ch, nu, od_score);
+}
+int scicone_compute_t_prime_od_scores(scicone_chain* ch, double nu, double* od_score) {
+    if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    return od_scores(ch, nu, od_score);
+}
+
+int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t_prime, int32_t node_idx) {
+    if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    if (ch->t.empty()) return fail(SCICONE_ERR_STATE, "compute_t_prime_scores before compute_t_table");
+    if (ch->evaluated) return fail(SCICONE_ERR_STATE, "the previous proposal was neither accepted nor rejected");
+    if (!ch->pending) {
+        int rc = validate_tree(t_prime, ch->ds->K);
+        if (rc) return rc;
+        ch->tp.assign(t_prime);
+        ch->pending = true;
+        ch->p_full = false;
+    }
+    if (node_idx < 0 || node_idx >= ch->tp.n) return fail(SCICONE_ERR_ARG, "node index %d outside the tree", node_idx);
+    ch->roots.push_back(node_idx);
+    return SCICONE_OK;
+}
+
+int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const* t_primes, int32_t n,
+                                       double* t_prime_sums) {
+    if (!chains || n <= 0 || !t_prime_sums) return fail(SCICONE_ERR_ARG, "batch: null or empty");
+    scicone_dataset* ds = chains[0]->ds;
+    for (int i = 0; i < n; ++i) {
+        if (!chains[i] || chains[i]->ds != ds) return fail(SCICONE_ERR_ARG, "batch: all chains must share one dataset");
+        if (!chains[i]->pending || chains[i]->roots.empty())
+            return fail(SCICONE_ERR_STATE, "compute_t_prime_sums without compute_t_prime_scores (chain %d)", i);
+        if (chains[i]->evaluated) return fail(SCICONE_ERR_STATE, "proposal of chain %d already evaluated", i);
+        if (t_primes && t_primes[i] && t_primes[i]->n_nodes != chains[i]->tp.n)
+            return fail(SCICONE_ERR_ARG, "batch: t_prime of chain %d differs from the tree given to compute_t_prime_scores", i);
+    }
+    int rc = ds->set_device();
+    if (rc) return rc;
+    rc = ds->ensure_slots(n);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        rc = compile_proposal(chains[i], i, false);
+        if (rc) {
+            for (int q = 0; q <= i; ++q) drop_pending(chains[q]);
+            return rc;
+        }
+    }
+    rc = launch_proposals(ds, chains, n, t_prime_sums);
+    if (rc && rc != SCICONE_ERR_NAN) return rc;
+    for (int i = 0; i < n; ++i) chains[i]->evaluated = true;
+    return rc;
+}
+
+int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t_prime, double* t_prime_sum) {
+    if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    double total = 0.0;
+    int rc = scicone_batch_compute_t_prime_sums(&ch, &t_prime, 1, &total);
+    if (t_prime_sum) *t_prime_sum = total;
+    return rc;
+}
+
+int scicone_accept(scicone_chain* ch) {
+    if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    if (!ch->pending || !ch->evaluated) return fail(SCICONE_ERR_STATE, "accept without an evaluated proposal");
+    scicone_dataset* ds = ch->ds;
+    // Inference::update_t_scores, Inference.h:996-1012 - as pointer swaps
+    for (auto& kv : ch->p) {
+        auto it = ch->t.find(kv.first);
+        if (it != ch->t.end()) {
+            ds->pool.put(it->second.row);
+            it->second = kv.second;
+        } else
+            ch->t.emplace(kv.first, kv.second);
+    }
+    ch->p.clear();
+    if (ch->deleted_id != -1) {
+        auto it = ch->t.find(ch->deleted_id);
+        if (it != ch->t.end()) {
+            ds->pool.put(it->second.row);
+            ch->t.erase(it);
+        }
+    }
+    std::swap(ch->sums[0], ch->sums[1]);    // t_sums = t_prime_sums, Inference.h:867
+    std::swap(ch->maxid[0], ch->maxid[1]);  // t_maxs = t_prime_maxs, Inference.h:868
+    if (ds->od && ch->Lp_valid && ch->Lp_nu == ch->tp.nu) {  // the proposal's nu becomes the chain's nu
+        release_cache(ds, ch->Lt);
+        ch->Lt.swap(ch->Lp);
+        ch->Lt_nu = ch->Lp_nu;
+        ch->Lp_valid = false;
+    }
+    drop_pending(ch);
+    return SCICONE_OK;
+}
+
+int scicone_reject(scicone_chain* ch) {
+    if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    drop_pending(ch);
+    return SCICONE_OK;
+}
+
+int scicone_t_n_nodes(scicone_chain* ch, int32_t* n_nodes) {
+    if (!ch || !n_nodes) return fail(SCICONE_ERR_ARG, "null argument");
+    *n_nodes = (int32_t)ch->t.size();
+    return SCICONE_OK;
+}
+int scicone_t_node_ids(scicone_chain* ch, int32_t* ids) {
+    if (!ch || !ids) return fail(SCICONE_ERR_ARG, "null argument");
+    int i = 0;
+    for (auto& kv : ch->t) ids[i++] = kv.first;
+    return SCICONE_OK;
+}
+
+int scicone_read_t_scores(scicone_chain* ch, double* out) {
+    if (!ch || !out) return fail(SCICONE_ERR_ARG, "null argument");
+    int rc = ch->ds->set_device();
+    if (rc) return rc;
+    std::vector<const double*> rows;
+    for (auto& kv : ch->t) rows.push_back(kv.second.row);
+    return gather_rows(ch->ds, rows, out);
+}
+int scicone_read_t_sums(scicone_chain* ch, double* out) {
+    if (!ch || !out) return fail(SCICONE_ERR_ARG, "null argument");
+    return read_vec(ch->ds, ch->sums[0], out, ch->ds->M);
+}
+int scicone_read_t_maxs(scicone_chain* ch, int32_t* ids, double* vals) {
+    if (!ch || !ids || !vals) return fail(SCICONE_ERR_ARG, "null argument");
+    if (!ch->ds->maxs) return fail(SCICONE_ERR_STATE, "t_maxs only exists with max_scoring");
+    int rc = read_vec(ch->ds, ch->maxid[0], ids, ch->ds->M);
+    return rc ? rc : read_vec(ch->ds, ch->sums[0], vals, ch->ds->M);
+}
+int scicone_read_t_prime_sums(scicone_chain* ch, double* out) {
+    if (!ch || !out) return fail(SCICONE_ERR_ARG, "null argument");
+    if (!ch->evaluated) return fail(SCICONE_ERR_STATE, "no evaluated proposal");
+    return read_vec(ch->ds, ch->sums[1], out, ch->ds->M);
+}
+int scicone_read_t_prime_maxs(scicone_chain* ch, int32_t* ids, double* vals) {
+    if (!ch || !ids || !vals) return fail(SCICONE_ERR_ARG, "null argument");
+    if (!ch->evaluated) return fail(SCICONE_ERR_STATE, "no evaluated proposal");
+    if (!ch->ds->maxs) return fail(SCICONE_ERR_STATE, "t_prime_maxs only exists with max_scoring");
+    int rc = read_vec(ch->ds, ch->maxid[1], ids, ch->ds->M);
+    return rc ? rc : read_vec(ch->ds, ch->sums[1], vals, ch->ds->M);
+}
+int scicone_t_prime_n_rescored(scicone_chain* ch, int32_t* n) {
+    if (!ch || !n) return fail(SCICONE_ERR_ARG, "null argument");
+    *n = (int32_t)ch->p.size();
+    return SCICONE_OK;
+}
+int scicone_read_t_prime_scores(scicone_chain* ch, int32_t* ids, double* out) {
+    if (!ch || !out) return fail(SCICONE_ERR_ARG, "null argument");
+    if (!ch->evaluated) return fail(SCICONE_ERR_STATE, "no evaluated proposal");
+    int rc = ch->ds->set_device();
+    if (rc) return rc;
+    std::vector<const double*> rows;
+    int i = 0;
+    for (auto& kv : ch->p) {
+        if (ids) ids[i++] = kv.first;
+        rows.push_back(kv.second.row);
+    }
+    return gather_rows(ch->ds, rows, out);
+}
+
+int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int32_t* cell_node_ids, int32_t* cell_region_cn) {
+    if (!ch || !cell_node_ids) return fail(SCICONE_ERR_ARG, "null argument");
+    scicone_dataset* ds = ch->ds;
+    int rc = validate_tree(t, ds->K);
+    if (rc) return rc;
+    if (ch->t.empty()) return fail(SCICONE_ERR_STATE, "assign_cells_to_nodes before compute_t_table");
+    rc = ds->set_device();
+    if (rc) return rc;
+    const int n = (int)ch->t.size(), M = ds->M, K = ds->K;
+    std::vector<const double*> rows;
+    std::vector<int> ids;
+    std::vector<int> cn((size_t)n * K);
+    for (auto& kv : ch->t) {
+        int idx = -1;
+        for (int i = 0; i < t->n_nodes; ++i)
+            if (t->node_id[i] == kv.first) idx = i;
+        if (idx < 0) return fail(SCICONE_ERR_ARG, "node id %d of the committed table is not in the tree", kv.first);
+        int* dst = cn.data() + rows.size() * K;
+        for (int k = 0; k < K; ++k) dst[k] = ds->neutral[k];
+        for (int e = t->gen_off[idx]; e < t->gen_off[idx + 1]; ++e) dst[t->gen_region[e]] += t->gen_value[e];
+        rows.push_back(kv.second.row);
+        ids.push_back(kv.first);
+    }
+    const double** d_rows = nullptr;
+    int *d_ids = nullptr, *d_cn = nullptr, *d_out_id = nullptr, *d_out_col = nullptr, *d_out_cn = nullptr;
+    cudaError_t e = cudaMalloc(&d_rows, sizeof(double*) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_ids, sizeof(int) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_cn, sizeof(int) * (size_t)n * K);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out_id, sizeof(int) * M);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out_col, sizeof(int) * M);
+    if (e == cudaSuccess && cell_region_cn) e = cudaMalloc(&d_out_cn, sizeof(int) * (size_t)M * K);
+    if (e == cudaSuccess) {
+        cudaMemcpyAsync(d_rows, rows.data(), sizeof(double*) * n, cudaMemcpyHostToDevice, ds->stream);
+        cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ds->stream);
+        cudaMemcpyAsync(d_cn, cn.data(), sizeof(int) * (size_t)n * K, cudaMemcpyHostToDevice, ds->stream);
+        argmax_kernel<<<(M + 127) / 128, 128, 0, ds->stream>>>(d_rows, d_ids, n, M, d_out_id, d_out_col);
+        cudaMemcpyAsync(cell_node_ids, d_out_id, sizeof(int) * M, cudaMemcpyDeviceToHost, ds->stream);
+        if (cell_region_cn) {
+            const long long tot = (long long)M * K;
+            expand_cn_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ds->stream>>>(d_out_col, d_cn, M, K, d_out_cn);
+            cudaMemcpyAsync(cell_region_cn, d_out_cn, sizeof(int) * (size_t)M * K, cudaMemcpyDeviceToHost, ds->stream);
+        }
+        e = cudaStreamSynchronize(ds->stream);
+    }
+    cudaFree(d_rows); cudaFree(d_ids); cudaFree(d_cn); cudaFree(d_out_id); cudaFree(d_out_col); cudaFree(d_out_cn);
+    if (e != cudaSuccess) return fail(SCICONE_ERR_CUDA, "assign_cells_to_nodes: %s", cudaGetErrorString(e));
+    return SCICONE_OK;
+}
+
+int scicone_comm_unique_id(uint8_t out[128]) {
+    if (!out) return fail(SCICONE_ERR_ARG, "null argument");
+    if (!g_nccl.load()) return fail(SCICONE_ERR_COMM, "libnccl.so.2 not found: %s", dlerror());
+    NcclApi::UniqueId id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail(SCICONE_ERR_COMM, "ncclGetUniqueId failed (%d)", rc);
+    memcpy(out, &id, 128);
+    return SCICONE_OK;
+}
+
+int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128], int32_t rank, int32_t world_size) {
+    if (!ds || !unique_id || world_size < 1 || rank < 0 || rank >= world_size) return fail(SCICONE_ERR_ARG, "attach_comm: bad argument");
+    if (ds->comm) return fail(SCICONE_ERR_STATE, "attach_comm: communicator already attached");
+    if (!g_nccl.load()) return fail(SCICONE_ERR_COMM, "libnccl.so.2 not found");
+    int rc = ds->set_device();
+    if (rc) return rc;
+    NcclApi::UniqueId id;
+    memcpy(&id, unique_id, 128);
+    int nrc = g_nccl.CommInitRank(&ds->comm, world_size, id, rank);
+    if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclCommInitRank failed (%d)", nrc);
+    ds->rank = rank;
+    ds->world = world_size;
+    // every rank pads to the same chunk count: the largest shard a rank can hold
+    const long long chunk_cells = (long long)kBlock * kCtasPerChunk;
+    const long long global_chunks = (ds->M_global + chunk_cells - 1) / chunk_cells;
+    ds->max_chunks_rank = (int)std::max<long long>((global_chunks + world_size - 1) / world_size + 1, ds->n_chunks);
+    // all ranks must agree on max_chunks_rank: exchange through the communicator
+    {
+        double mine = (double)ds->max_chunks_rank;
+        double *d_one = nullptr, *d_all = nullptr;
+        std::vector<double> all(world_size);
+        CUDA_TRY(cudaMalloc(&d_one, sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d_all, sizeof(double) * world_size));
+        CUDA_TRY(cudaMemcpyAsync(d_one, &mine, sizeof(double), cudaMemcpyHostToDevice, ds->stream));
+        nrc = g_nccl.AllGather(d_one, d_all, 1, kNcclDouble, ds->comm, ds->stream);
+        if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
+        CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(double) * world_size, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaStreamSynchronize(ds->stream));
+        cudaFree(d_one);
+        cudaFree(d_all);
+        for (double v : all) ds->max_chunks_rank = std::max(ds->max_chunks_rank, (int)v);
+    }
+    const int keep = ds->slots;
+    ds->slots = 0;  // force reallocation with the gather buffers
+    return ds->ensure_slots(std::max(keep, 4));
+}
+
+int scicone_set_profiling(scicone_dataset* ds, int32_t on) {
+    if (!ds) return fail(SCICONE_ERR_ARG, "null dataset");
+    ds->profiling = on != 0;
+    return SCICONE_OK;
+}
+int scicone_last_kernel_time_us(scicone_dataset* ds, double* us) {
+    if (!ds || !us) return fail(SCICONE_ERR_ARG, "null argument");
+    *us = ds->last_kernel_us;
+    return SCICONE_OK;
+}
+int scicone_kernel_launches(scicone_dataset* ds, uint64_t* n) {
+    if (!ds || !n) return fail(SCICONE_ERR_ARG, "null argument");
+    *n = ds->n_launches;
+    return SCICONE_OK;
+}
+
+}  // extern "C"

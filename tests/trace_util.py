@@ -1,0 +1,67 @@
+"""Drive two chains (CUDA engine and oracle port) through the same random proposal trace."""
+import numpy as np
+
+from golden_util import rel_err
+from scicone_b200.synth import TreeState, make_counts
+
+
+def make_case(n_cells, n_bins, n_regions, n_nodes, seed, cluster_rows=None, nu=1.0):
+    data = make_counts(n_cells, n_bins, n_regions, seed=seed, cluster_rows=cluster_rows)
+    rng = np.random.default_rng(seed + 1)
+    tree = TreeState(n_regions, data["neutral_states"], rng, nu=nu).grow(n_nodes)
+    return data, tree
+
+
+def run_trace(gpu, cpu, tree, n_moves, tol, kinds=None, check_tables_every=10):
+    """Returns dict of worst relative errors.  Asserts id sets equal and errors <= tol."""
+    worst = {"total": 0.0, "t_prime_scores": 0.0, "t_prime_sums": 0.0, "t_scores": 0.0, "od": 0.0, "argmax_mismatch": 0}
+    ft = tree.flat()
+    a, b = gpu.compute_t_table(ft), cpu.compute_t_table(ft)
+    worst["total"] = max(worst["total"], abs(a - b) / max(1.0, abs(b)))
+    a, b = gpu.compute_t_od_scores(ft.nu), cpu.compute_t_od_scores(ft.nu)
+    worst["od"] = max(worst["od"], abs(a - b) / max(1.0, abs(b)))
+    worst["t_scores"] = rel_err(gpu.read_t_scores(), cpu.read_t_scores())
+    kw = {} if kinds is None else {"kinds": kinds}
+    n_done = 0
+    for step in range(n_moves):
+        prop = tree.propose(**kw)
+        if prop is None:
+            continue
+        t2, roots, kind = prop
+        ft = t2.flat()
+        if kind == "nu":
+            a, b = gpu.compute_t_prime_od_scores(ft.nu), cpu.compute_t_prime_od_scores(ft.nu)
+            worst["od"] = max(worst["od"], abs(a - b) / max(1.0, abs(b)))
+        for rid in roots:
+            idx = ft.index_of(rid)
+            gpu.compute_t_prime_scores(ft, idx)
+            cpu.compute_t_prime_scores(ft, idx)
+        a, b = gpu.compute_t_prime_sums(ft), cpu.compute_t_prime_sums(ft)
+        worst["total"] = max(worst["total"], abs(a - b) / max(1.0, abs(b)))
+        gi, gs = gpu.read_t_prime_scores()
+        ci, cs = cpu.read_t_prime_scores()
+        assert list(gi) == list(ci), (step, kind, gi, ci)
+        worst["t_prime_scores"] = max(worst["t_prime_scores"], rel_err(gs, cs))
+        worst["t_prime_sums"] = max(worst["t_prime_sums"], rel_err(gpu.read_t_prime_sums(), cpu.read_t_prime_sums()))
+        if gpu.max_scoring:
+            g_ids, _ = gpu.read_t_prime_maxs()
+            c_ids, _ = cpu.read_t_prime_maxs()
+            worst["argmax_mismatch"] += int(np.sum(g_ids != c_ids))
+        if tree.rng.random() < 0.5:
+            gpu.accept(ft)
+            cpu.accept(ft)
+            tree = t2
+        else:
+            gpu.reject()
+            cpu.reject()
+        n_done += 1
+        if n_done % check_tables_every == 0:
+            assert list(gpu.t_node_ids()) == list(cpu.t_node_ids())
+            worst["t_scores"] = max(worst["t_scores"], rel_err(gpu.read_t_scores(), cpu.read_t_scores()))
+    assert list(gpu.t_node_ids()) == list(cpu.t_node_ids())
+    worst["t_scores"] = max(worst["t_scores"], rel_err(gpu.read_t_scores(), cpu.read_t_scores()))
+    for k, v in worst.items():
+        if k != "argmax_mismatch":
+            assert v <= tol, (k, v)
+    worst["n_moves"] = n_done
+    return worst, tree
