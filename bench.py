@@ -1,0 +1,404 @@
+#!/usr/bin/env python3
+"""bench.py - MCMC tree-scoring throughput of the B200 engine (and of the reference's CPU path beside it).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU `inference` on the host cores
+
+Workload (BASELINE.json configs[2], the "10k cells" headline): synthetic 10 000 cells x 18 000 bins collapsed to
+200 regions PER GPU, B independent MCMC chains (restarts, as pyscicone's learn_tree_parallel runs them) advanced in
+lock-step on trees of ~50 nodes.  One STEP = one MCMC iteration of every chain = ONE launch of the fused
+score/aggregate/reduce kernel over B proposals (+ the cell-shard all-gather when N > 1).
+
+Metric: cell x MCMC-iterations per second ("cell_iters/s" = chain iterations/s x cells), which aggregates over
+cell-sharded GPUs (weak scaling: every rank holds its own 10 000 cells) and over chains, and which the
+reference's `inference` timer yields directly (iterations/s x cells).  Chain iterations/s and cell x node
+attachment scores/s are reported next to it.
+
+  value  device pipeline: proposals are queued on the stream without waiting for their totals (accept/reject are
+         host-side pointer swaps), count matrix / score tables / lgamma rows resident in HBM, region timed with
+         CUDA events on the engine's stream.
+  e2e    the real MCMC loop through the C ABI: every step stages its proposals from host memory, launches, and
+         reads the B totals back before the next step can start (wall clock, sync on both sides).
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L2_BYTES = 126e6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        self.path = None
+        if shutil.which("nvidia-smi"):
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def build_chain_traces(data, n_chains, n_nodes, n_steps, seed, nu):
+    """Pre-generated proposal traces: per chain a start tree and per step (FlatTree, root indices, accept coin)."""
+    from scicone_b200.synth import TreeState
+
+    kinds = ("prune_reattach", "swap", "add_remove", "insert", "delete", "nu")
+    # default move weights of the reference CLI (infer_trees.cpp:120): five weighted structural moves at 1.0
+    # (prune/reattach, swap, add/remove, insert/delete, condense/split) and the nu move at 1.0
+    weights = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+    weights = weights / weights.sum()
+    traces = []
+    for c in range(n_chains):
+        rng = np.random.default_rng(seed + 42 + c)
+        tree = TreeState(data["D"].shape[1], data["neutral_states"], rng, nu=nu).grow(n_nodes)
+        start = tree.flat()
+        steps = []
+        for _ in range(n_steps):
+            t2, roots, kind = tree.propose(kinds=kinds, weights=weights)
+            ft = t2.flat()
+            acc = bool(rng.random() < 0.3)
+            steps.append((ft, [ft.index_of(r) for r in roots], acc, kind))
+            if acc:
+                tree = t2
+        traces.append((start, steps))
+    return traces
+
+
+def run_engine(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from scicone_b200.api import BatchLauncher, Chain, Dataset, comm_unique_id
+    from scicone_b200.synth import SEED, make_counts
+
+    K, W, B = args.steps, args.warmup, args.chains
+    M = args.cells
+    # weak scaling: every rank draws its own 10k-cell shard of one (world x M)-cell matrix; region sizes are shared
+    data = make_counts(M, args.bins, args.regions, seed=SEED)
+    if world > 1:
+        shard = make_counts(M, args.bins, args.regions, seed=SEED + 1000 * rank)
+        shard["region_sizes"] = data["region_sizes"]
+        data = shard if rank > 0 else data
+    ds = Dataset(data["D"], data["region_sizes"], neutral_states=data["neutral_states"], cluster_sizes=data["cluster_sizes"],
+                 is_overdispersed=1, max_scoring=args.max_scoring, device=local, cell_offset=rank * M, n_cells_global=world * M)
+    if world > 1:
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ds.attach_comm(uid[0], rank, world)
+    # identical proposal streams on every rank (the tree is replicated, only cells are sharded)
+    ref_data = make_counts(64, args.bins, args.regions, seed=SEED)  # only region count / neutral states matter here
+    traces = build_chain_traces(ref_data, B, args.nodes, 2 * (W + K), SEED, args.nu)
+    chains = [Chain(dataset=ds) for _ in range(B)]
+    for ch, (start, _) in zip(chains, traces):
+        ch.compute_t_table(start)
+        ch.compute_t_od_scores(start.nu)
+    launcher = BatchLauncher(chains)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def queue_step(s):
+        for ch, (_, steps) in zip(chains, traces):
+            ft, roots, _, kind = steps[s]
+            if kind == "nu":
+                ch.compute_t_prime_od_scores(ft.nu)
+            for idx in roots:
+                ch.compute_t_prime_scores(ft, idx)
+
+    def settle_step(s):
+        for ch, (_, steps) in zip(chains, traces):
+            if steps[s][2]:
+                ch.accept()
+            else:
+                ch.reject()
+
+    # ---------------- e2e: lock-step MCMC loop through the C ABI (totals read back every step)
+    for s in range(W):
+        queue_step(s)
+        launcher.run()
+        settle_step(s)
+    ds.counters(reset=True)
+    launches0 = ds.kernel_launches()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        queue_step(s)
+        launcher.run()
+        settle_step(s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    cnt_e2e = ds.counters(reset=True)
+    launches_e2e = ds.kernel_launches() - launches0
+
+    # ---------------- value: device pipeline, totals collected with a lag, timed by CUDA events on the engine stream
+    base = W + K
+    ds.set_profiling(True)
+    for s in range(base, base + W):
+        queue_step(s)
+        launcher.run()
+        settle_step(s)
+    ds.kernel_time_stats(reset=True)
+    ds.counters(reset=True)
+    launches1 = ds.kernel_launches()
+    barrier()
+    ds.region_mark(0)
+    tickets = []
+    for s in range(base + W, base + W + K):
+        queue_step(s)
+        tickets.append(launcher.submit())
+        settle_step(s)
+        if len(tickets) >= 6:
+            launcher.wait(tickets.pop(0))
+    for tk in tickets:
+        launcher.wait(tk)
+    ds.region_mark(1)
+    barrier()
+    dev_ms = ds.region_elapsed_ms()
+    clocks = sampler.stop() if sampler else None
+    kern_us, n_timed = ds.kernel_time_stats()
+    cnt_dev = ds.counters()
+    launches_dev = ds.kernel_launches() - launches1
+    ds.set_profiling(False)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s, kern_us], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s, kern_us = (float(x) for x in t.cpu())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        cells_total = world * M
+        iters = B * K
+        value = iters * cells_total / (dev_ms * 1e-3)
+        e2e = iters * cells_total / e2e_s
+        achieved = cnt_dev["alg_bytes"] / (kern_us * 1e-6) / 1e9 if kern_us > 0 else 0.0
+        resident = ds.device_bytes()
+        out = {
+            "metric": "mcmc_cell_iters_per_s", "value": value, "unit": "cell_iters/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"configs[2]: {M} cells x {args.bins} bins -> {args.regions} regions per GPU, "
+                                   f"{B} chains x ~{args.nodes}-node trees, overdispersed, "
+                                   f"{'max' if args.max_scoring else 'sum'} scoring, default move mix",
+                       "cells_per_gpu": M, "regions": args.regions, "chains": B, "tree_nodes": args.nodes,
+                       "max_scoring": int(args.max_scoring), "parallelism": f"cells sharded x{world}" if world > 1 else "1 GPU",
+                       "proposal_source": "pre-generated valid proposals (scicone_b200.synth.TreeState), accept prob 0.3",
+                       "l2": f"inputs larger than L2: {resident / 1e6:.0f} MB of score/lgamma rows + counts resident vs 126 MB L2"},
+            "mcmc_iters_per_s": iters / (dev_ms * 1e-3),
+            "scores_per_s": cnt_dev["n_scores"] * world / (dev_ms * 1e-3),
+            "e2e": {"value": e2e, "unit": "cell_iters/s", "mcmc_iters_per_s": iters / e2e_s, "ms_per_step": 1e3 * e2e_s / K,
+                    "h2d_bytes_per_step": cnt_e2e["h2d_bytes"] / K, "d2h_bytes_per_step": cnt_e2e["d2h_bytes"] / K},
+            "gpu_launches": int(launches_dev),
+            "roofline": {"bound": "hbm", "kernel": "score_proposals_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_launch": cnt_dev["alg_bytes"] / max(1, n_timed),
+                         "avg_launch_us": kern_us / max(1, n_timed), "kernel_share_of_step": kern_us * 1e-3 / dev_ms},
+            "clocks": clocks,
+        }
+        out["cpu_baseline"] = cpu_baseline(args, data) if world == 1 and not args.no_cpu_baseline else None
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def write_inputs(tmp, data):
+    d = os.path.join(tmp, "d.csv")
+    np.savetxt(d, data["D"], delimiter=",", fmt="%.0f" if np.allclose(data["D"], np.round(data["D"])) else "%.18e")
+    r = os.path.join(tmp, "r.txt")
+    np.savetxt(r, data["region_sizes"], fmt="%d")
+    return d, r
+
+
+def run_reference_inference(args, data, n_iters, n_procs, omp_threads):
+    """The UNMODIFIED reference `inference` (oracle/_ref, built by oracle/Makefile) on this box's host cores."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "inference")
+    if not os.path.exists(exe):
+        return None
+    tmp = tempfile.mkdtemp(prefix="scicone_ref_")
+    try:
+        d, r = write_inputs(tmp, data)
+        M, K = data["D"].shape
+        procs = []
+        env = dict(os.environ, OMP_NUM_THREADS=str(omp_threads))
+        t0 = time.perf_counter()
+        for p in range(n_procs):
+            cmd = [exe, f"--d_matrix_file={d}", f"--region_sizes_file={r}", f"--n_cells={M}", f"--n_regions={K}",
+                   f"--n_iters={n_iters}", f"--n_nodes={args.nodes - 1}", f"--seed={42 + p}", f"--nu={args.nu}", "--verbosity=1",
+                   f"--max_scoring={'true' if args.max_scoring else 'false'}", f"--postfix=ref{p}"]
+            procs.append(subprocess.Popen(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+        times = []
+        for pr in procs:
+            out, _ = pr.communicate()
+            m = re.search(r"Time taken by infer_mcmc function: (\d+) microseconds", out)
+            if pr.returncode != 0 or not m:
+                raise RuntimeError("reference inference failed:\n" + out[-2000:])
+            times.append(int(m.group(1)) * 1e-6)
+        wall = time.perf_counter() - t0
+        return {"mcmc_s_max": max(times), "wall_s": wall, "iters_per_s": n_procs * n_iters / max(times)}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def cpu_baseline(args, data):
+    """Bounded sample of the same workload on the host CPU: the reference binary if it travelled, else the oracle port."""
+    M = data["D"].shape[0]
+    n_iters = args.cpu_iters
+    res = run_reference_inference(args, data, n_iters, 1, os.cpu_count() or 1)
+    if res is not None:
+        return {"value": res["iters_per_s"] * M, "unit": "cell_iters/s", "mcmc_iters_per_s": res["iters_per_s"],
+                "cores": os.cpu_count(), "kind": "reference",
+                "sample": f"1 chain x {n_iters} iterations of oracle/_ref/inference (unmodified reference, -O3 -fopenmp, no ASan), "
+                          f"OMP_NUM_THREADS={os.cpu_count()}, same matrix, random {args.nodes}-node start tree, infer_mcmc timer"}
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_ffi import OracleChain
+
+    traces = build_chain_traces(data, 1, args.nodes, n_iters, 7, args.nu)
+    ch = OracleChain(D=data["D"], region_sizes=data["region_sizes"], neutral_states=data["neutral_states"],
+                     cluster_sizes=data["cluster_sizes"], is_overdispersed=1, max_scoring=args.max_scoring)
+    start, steps = traces[0]
+    ch.compute_t_table(start)
+    t0 = time.perf_counter()
+    for ft, roots, acc, kind in steps:
+        if kind == "nu":
+            ch.compute_t_prime_od_scores(ft.nu)
+        for idx in roots:
+            ch.compute_t_prime_scores(ft, idx)
+        ch.compute_t_prime_sums(ft)
+        ch.accept(ft) if acc else ch.reject()
+    dt = time.perf_counter() - t0
+    return {"value": n_iters * M / dt, "unit": "cell_iters/s", "mcmc_iters_per_s": n_iters / dt, "cores": 1, "kind": "port",
+            "sample": f"1 chain x {n_iters} proposals through oracle/scicone_oracle.c (scoring only, no move logic)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from scicone_b200.synth import SEED, make_counts
+
+    M = args.cells * world  # our arm's config at N GPUs: every GPU holds args.cells cells
+    data = make_counts(M, args.bins, args.regions, seed=SEED)
+    cores = os.cpu_count() or 1
+    n_procs = max(1, min(cores, args.chains))
+    K, W = args.steps, args.warmup
+    # one "step" = a bounded sample: every process advances its chain by `iters_per_step` iterations
+    iters_per_step = max(1, args.ref_iters_per_step)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "inference")):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/inference was not built (needs /root/reference at build time)"}))
+        return
+    for _ in range(min(W, 1)):
+        run_reference_inference(args, data, 2, n_procs, 1)
+    t0 = time.perf_counter()
+    res = run_reference_inference(args, data, iters_per_step * K, n_procs, 1)
+    wall = time.perf_counter() - t0
+    v = res["iters_per_s"] * M
+    sample = (f"{n_procs} concurrent restarts (seeds 42..) of the unmodified reference `inference` (oracle/_ref, -O3 -fopenmp, no ASan), "
+              f"OMP_NUM_THREADS=1 each, {iters_per_step * K} iterations each on {M} cells x {args.regions} regions, "
+              f"random {args.nodes}-node start trees; rate = iterations / max infer_mcmc time")
+    out = {"impl": "reference", "metric": "mcmc_cell_iters_per_s", "value": v, "unit": "cell_iters/s", "n_gpus": world, "steps": K,
+           "warmup": W, "ms_per_step": 1e3 * res["mcmc_s_max"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"configs[2]: {M} cells x {args.bins} bins -> {args.regions} regions, {n_procs} chains x "
+                                  f"{args.nodes}-node trees, overdispersed, {'max' if args.max_scoring else 'sum'} scoring, default move mix",
+                      "cells": M, "regions": args.regions, "chains": n_procs, "tree_nodes": args.nodes},
+           "mcmc_iters_per_s": res["iters_per_s"], "wall_s": wall,
+           "cpu_baseline": {"value": v, "unit": "cell_iters/s", "cores": cores, "kind": "reference", "sample": sample},
+           "e2e": {"value": v, "unit": "cell_iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=10000, help="cells per GPU")
+    ap.add_argument("--bins", type=int, default=18000)
+    ap.add_argument("--regions", type=int, default=200)
+    ap.add_argument("--nodes", type=int, default=50)
+    ap.add_argument("--chains", type=int, default=32)
+    ap.add_argument("--nu", type=float, default=1.0)
+    ap.add_argument("--max_scoring", type=int, default=1)
+    ap.add_argument("--cpu_iters", type=int, default=150)
+    ap.add_argument("--ref_iters_per_step", type=int, default=1)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

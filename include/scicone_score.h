@@ -138,6 +138,16 @@ int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scico
                                        int32_t n, double* t_prime_sums);
 
 /*
+ * Pipelined form of the batch call: submit queues the copy-in, the kernel and the copy-out on the
+ * dataset's stream and returns at once; wait blocks until that launch is done and returns its totals.
+ * Accept / reject of the submitted proposals are host-side pointer swaps and may be issued before the
+ * wait (later launches are ordered behind earlier ones by the stream).  At most 8 tickets may be
+ * outstanding.  Reads (scicone_read_*) always see the finished state.
+ */
+int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const* t_primes, int32_t n, uint64_t* ticket);
+int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* t_prime_sums);
+
+/*
  * Accept (Inference.h:867-870: t_sums = t_prime_sums, t_maxs = t_prime_maxs,
  * update_t_scores(), and the proposal's od score / nu become the committed ones)
  * or reject (Inference.h:881,890) the queued proposal.  After a delete move the
@@ -190,7 +200,15 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
  */
 int scicone_set_profiling(scicone_dataset* ds, int32_t on);
 int scicone_last_kernel_time_us(scicone_dataset* ds, double* us); /* device time of the last proposal kernel */
-int scicone_kernel_launches(scicone_dataset* ds, uint64_t* n);    /* kernels launched on this dataset so far */
+int scicone_kernel_time_stats(scicone_dataset* ds, double* sum_us, uint64_t* n_timed, int32_t reset);
+int scicone_kernel_launches(scicone_dataset* ds, uint64_t* n);
+/* out = {bytes staged host->device, device->host, algorithmic bytes, cell x node scores} of all launches */
+int scicone_counters(scicone_dataset* ds, double out[4], int32_t reset);
+/* CUDA events on the dataset's stream bracketing a timed region (which = 0 start, 1 end). */
+int scicone_region_mark(scicone_dataset* ds, int32_t which);
+int scicone_region_elapsed_ms(scicone_dataset* ds, double* ms);
+/* Device bytes in use: count matrix + score / lgamma rows handed out by the row pool. */
+int scicone_device_bytes(scicone_dataset* ds, uint64_t* bytes);    /* kernels launched on this dataset so far */
 
 #ifdef __cplusplus
 }

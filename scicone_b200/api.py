@@ -25,11 +25,12 @@ ABI_SYMBOLS = [
     "scicone_abi_version", "scicone_last_error", "scicone_dataset_create", "scicone_dataset_destroy",
     "scicone_chain_create", "scicone_chain_destroy", "scicone_compute_t_table", "scicone_compute_t_od_scores",
     "scicone_compute_t_prime_od_scores", "scicone_compute_t_prime_scores", "scicone_compute_t_prime_sums",
-    "scicone_batch_compute_t_prime_sums", "scicone_accept", "scicone_reject", "scicone_t_n_nodes",
+    "scicone_batch_compute_t_prime_sums", "scicone_batch_submit", "scicone_batch_wait", "scicone_accept", "scicone_reject", "scicone_t_n_nodes",
     "scicone_t_node_ids", "scicone_read_t_scores", "scicone_read_t_sums", "scicone_read_t_maxs",
     "scicone_read_t_prime_sums", "scicone_read_t_prime_maxs", "scicone_t_prime_n_rescored",
     "scicone_read_t_prime_scores", "scicone_assign_cells_to_nodes", "scicone_comm_unique_id",
-    "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_launches",
+    "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_kernel_launches",
+    "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
 ]
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}
@@ -82,6 +83,13 @@ def lib():
         L.scicone_compute_t_prime_scores.argtypes = [vp, tp, C.c_int32]
         L.scicone_compute_t_prime_sums.argtypes = [vp, tp, dp]
         L.scicone_batch_compute_t_prime_sums.argtypes = [C.POINTER(vp), C.POINTER(tp), C.c_int32, dp]
+        L.scicone_batch_submit.argtypes = [C.POINTER(vp), C.POINTER(tp), C.c_int32, C.POINTER(C.c_uint64)]
+        L.scicone_batch_wait.argtypes = [vp, C.c_uint64, dp]
+        L.scicone_kernel_time_stats.argtypes = [vp, dp, C.POINTER(C.c_uint64), C.c_int32]
+        L.scicone_counters.argtypes = [vp, dp, C.c_int32]
+        L.scicone_region_mark.argtypes = [vp, C.c_int32]
+        L.scicone_region_elapsed_ms.argtypes = [vp, dp]
+        L.scicone_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.scicone_accept.argtypes = [vp]
         L.scicone_reject.argtypes = [vp]
         L.scicone_t_n_nodes.argtypes = [vp, ip]
@@ -169,6 +177,30 @@ class Dataset:
     def last_kernel_time_us(self):
         out = C.c_double()
         _check(lib().scicone_last_kernel_time_us(self._h, C.byref(out)))
+        return out.value
+
+    def kernel_time_stats(self, reset=False):
+        """(sum of proposal-kernel device time in us, number of timed launches) since the last reset."""
+        us, n = C.c_double(), C.c_uint64()
+        _check(lib().scicone_kernel_time_stats(self._h, C.byref(us), C.byref(n), int(reset)))
+        return us.value, n.value
+
+    def counters(self, reset=False):
+        out = np.zeros(4)
+        _check(lib().scicone_counters(self._h, _dp(out), int(reset)))
+        return dict(h2d_bytes=out[0], d2h_bytes=out[1], alg_bytes=out[2], n_scores=out[3])
+
+    def region_mark(self, which):
+        _check(lib().scicone_region_mark(self._h, int(which)))
+
+    def region_elapsed_ms(self):
+        out = C.c_double()
+        _check(lib().scicone_region_elapsed_ms(self._h, C.byref(out)))
+        return out.value
+
+    def device_bytes(self):
+        out = C.c_uint64()
+        _check(lib().scicone_device_bytes(self._h, C.byref(out)))
         return out.value
 
     def kernel_launches(self):
@@ -290,3 +322,26 @@ def batch_compute_t_prime_sums(chains, trees):
     out = np.zeros(n)
     _check(lib().scicone_batch_compute_t_prime_sums(hs, ts, n, _dp(out)))
     return out
+
+
+class BatchLauncher:
+    """Pre-marshalled handles for repeated batch launches of the same chains (keeps ctypes overhead out of loops)."""
+
+    def __init__(self, chains):
+        self.chains = list(chains)
+        self.n = len(self.chains)
+        self.ds = self.chains[0].ds
+        self._hs = (C.c_void_p * self.n)(*[c._h for c in self.chains])
+        self._out = np.zeros(self.n)
+        self._ticket = C.c_uint64()
+
+    def submit(self):
+        _check(lib().scicone_batch_submit(self._hs, None, self.n, C.byref(self._ticket)))
+        return self._ticket.value
+
+    def wait(self, ticket):
+        _check(lib().scicone_batch_wait(self.ds._h, ticket, _dp(self._out)))
+        return self._out
+
+    def run(self):
+        return self.wait(self.submit())

@@ -195,8 +195,21 @@ struct scicone_dataset {
     cudaStream_t stream = nullptr;
     RowPool pool;
 
-    // staging arena (proposal blobs), pinned + device
-    unsigned char* h_arena = nullptr;
+    // staging: a ring of pinned segments (proposal blobs out, totals back) so that launches can be queued
+    // without a host round trip; one device arena (copies and kernels are ordered by the stream)
+    struct Segment {
+        unsigned char* h_arena = nullptr;
+        double* h_total = nullptr;     // pinned [slots]
+        unsigned* h_status = nullptr;  // pinned [slots]
+        double* h_gather = nullptr;    // pinned [world][slots][max_chunks_rank]
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+        int n = 0;
+        bool busy = false;
+        unsigned long long ticket = 0;
+    };
+    static constexpr int kRing = 8;
+    Segment seg[kRing];
+    unsigned long long next_ticket = 1;
     unsigned char* d_arena = nullptr;
     size_t arena_cap = 0;
     // per batch slot: reduction scratch and results
@@ -207,21 +220,28 @@ struct scicone_dataset {
     double* d_total = nullptr;    // [slots]
     unsigned* d_counter = nullptr;
     unsigned* d_status = nullptr;
-    double* h_total = nullptr;    // pinned [slots]
-    unsigned* h_status = nullptr; // pinned [slots]
     // multi-GPU
     void* comm = nullptr;
     int rank = 0, world = 1;
     int max_chunks_rank = 0;
     double* d_gather = nullptr;  // [world][slots][max_chunks_rank]
     double* d_send = nullptr;    // [slots][max_chunks_rank]
-    double* h_gather = nullptr;
     size_t gather_cap = 0;
     // profiling
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double last_kernel_us = 0.0;
+    double last_kernel_us = 0.0, sum_kernel_us = 0.0;
+    unsigned long long n_timed = 0;
     unsigned long long n_launches = 0;
+    // bookkeeping for the bench: bytes staged per direction, algorithmic bytes / scores of the launched proposals
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0;
+    double alg_bytes = 0.0, n_scores = 0.0;
+    cudaEvent_t region_ev[2] = {nullptr, nullptr};
+
+    int drain() {  // wait for every queued launch (results of unclaimed tickets are dropped)
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (Segment& g : seg) g.busy = false;
+        return SCICONE_OK;
+    }
 
     int set_device() const {
         CUDA_TRY(cudaSetDevice(device));
@@ -231,12 +251,15 @@ struct scicone_dataset {
         if (bytes <= arena_cap) return SCICONE_OK;
         size_t cap = std::max<size_t>(bytes * 2, size_t(1) << 16);
         CUDA_TRY(cudaStreamSynchronize(stream));
-        if (h_arena) cudaFreeHost(h_arena);
+        for (Segment& g : seg) {
+            if (g.busy) return fail(SCICONE_ERR_STATE, "staging arena must grow while launches are outstanding");
+            if (g.h_arena) cudaFreeHost(g.h_arena);
+            g.h_arena = nullptr;
+        }
         if (d_arena) cudaFree(d_arena);
-        h_arena = nullptr;
         d_arena = nullptr;
         arena_cap = 0;
-        CUDA_TRY(cudaMallocHost(&h_arena, cap));
+        for (Segment& g : seg) CUDA_TRY(cudaMallocHost(&g.h_arena, cap));
         CUDA_TRY(cudaMalloc(&d_arena, cap));
         arena_cap = cap;
         return SCICONE_OK;
@@ -245,13 +268,19 @@ struct scicone_dataset {
         if (n <= slots) return SCICONE_OK;
         int ns = std::max(n, std::max(4, slots * 2));
         CUDA_TRY(cudaStreamSynchronize(stream));
+        for (Segment& g : seg)
+            if (g.busy) return fail(SCICONE_ERR_STATE, "batch size must grow while launches are outstanding");
         cudaFree(d_partial); cudaFree(d_chunk); cudaFree(d_total); cudaFree(d_counter); cudaFree(d_status);
-        if (h_total) cudaFreeHost(h_total);
-        if (h_status) cudaFreeHost(h_status);
         d_partial = d_chunk = d_total = nullptr;
         d_counter = d_status = nullptr;
-        h_total = nullptr;
-        h_status = nullptr;
+        for (Segment& g : seg) {
+            if (g.h_total) cudaFreeHost(g.h_total);
+            if (g.h_status) cudaFreeHost(g.h_status);
+            if (g.h_gather) cudaFreeHost(g.h_gather);
+            g.h_total = nullptr;
+            g.h_status = nullptr;
+            g.h_gather = nullptr;
+        }
         slots = 0;
         CUDA_TRY(cudaMalloc(&d_partial, sizeof(double) * size_t(ns) * n_cta));
         CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * size_t(ns) * n_chunks));
@@ -260,18 +289,18 @@ struct scicone_dataset {
         CUDA_TRY(cudaMalloc(&d_status, sizeof(unsigned) * ns));
         CUDA_TRY(cudaMemset(d_counter, 0, sizeof(unsigned) * ns));
         CUDA_TRY(cudaMemset(d_status, 0, sizeof(unsigned) * ns));
-        CUDA_TRY(cudaMallocHost(&h_total, sizeof(double) * ns));
-        CUDA_TRY(cudaMallocHost(&h_status, sizeof(unsigned) * ns));
+        for (Segment& g : seg) {
+            CUDA_TRY(cudaMallocHost(&g.h_total, sizeof(double) * ns));
+            CUDA_TRY(cudaMallocHost(&g.h_status, sizeof(unsigned) * ns));
+        }
         slots = ns;
         if (world > 1) {
             cudaFree(d_gather); cudaFree(d_send);
-            if (h_gather) cudaFreeHost(h_gather);
             d_gather = d_send = nullptr;
-            h_gather = nullptr;
             size_t per_rank = size_t(ns) * max_chunks_rank;
             CUDA_TRY(cudaMalloc(&d_send, sizeof(double) * per_rank));
             CUDA_TRY(cudaMalloc(&d_gather, sizeof(double) * per_rank * world));
-            CUDA_TRY(cudaMallocHost(&h_gather, sizeof(double) * per_rank * world));
+            for (Segment& g : seg) CUDA_TRY(cudaMallocHost(&g.h_gather, sizeof(double) * per_rank * world));
             CUDA_TRY(cudaMemset(d_send, 0, sizeof(double) * per_rank));
             gather_cap = per_rank;
         }
@@ -298,6 +327,7 @@ struct scicone_chain {
     bool p_full = false;
     // blob under construction
     std::vector<unsigned char> blob;
+    double alg_bytes = 0.0, n_scores = 0.0;
 };
 
 namespace {
@@ -544,6 +574,11 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     H.counter = ds->d_counter + slot;
     H.status = ds->d_status + slot;
 
+    {   // 16 + 8 E_n bytes per rescored cell x node score, 8 N + 12 per cell aggregate
+        const double n_table = full ? (double)addorder.size() : (double)(unch.size() + addorder.size());
+        ch->alg_bytes = (double)ds->M * (16.0 * tasks.size() + 8.0 * events.size() + 8.0 * n_table + 12.0);
+        ch->n_scores = (double)ds->M * tasks.size();
+    }
     std::vector<unsigned char>& b = ch->blob;
     b.clear();
     b.resize(sizeof(DevHeader));
@@ -557,24 +592,27 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     return SCICONE_OK;
 }
 
-// Launch the compiled blobs of `n` chains (all on one dataset) and fetch their totals.
-int launch_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, double* totals) {
+// Queue the compiled blobs of `n` chains (all on one dataset) as ONE kernel launch; returns a ticket.
+int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, unsigned long long* ticket) {
     size_t head = round_up(sizeof(unsigned) * n, 16);
     size_t bytes = head;
     for (int i = 0; i < n; ++i) bytes += chains[i]->blob.size();
     int rc = ds->ensure_arena(bytes);
     if (rc) return rc;
-    unsigned* offs = reinterpret_cast<unsigned*>(ds->h_arena);
+    const unsigned long long tk = ds->next_ticket;
+    scicone_dataset::Segment& g = ds->seg[tk % scicone_dataset::kRing];
+    if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
+    unsigned* offs = reinterpret_cast<unsigned*>(g.h_arena);
     size_t at = head;
     for (int i = 0; i < n; ++i) {
         offs[i] = (unsigned)at;
-        memcpy(ds->h_arena + at, chains[i]->blob.data(), chains[i]->blob.size());
+        memcpy(g.h_arena + at, chains[i]->blob.data(), chains[i]->blob.size());
         at += chains[i]->blob.size();
     }
-    CUDA_TRY(cudaMemcpyAsync(ds->d_arena, ds->h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
-    if (ds->profiling) CUDA_TRY(cudaEventRecord(ds->ev0, ds->stream));
+    CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
+    if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, ds->stream));
     score_proposals_kernel<<<dim3(ds->n_cta, n), kBlock, 0, ds->stream>>>(ds->d_arena);
-    if (ds->profiling) CUDA_TRY(cudaEventRecord(ds->ev1, ds->stream));
+    if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, ds->stream));
     CUDA_TRY(cudaGetLastError());
     ds->n_launches++;
     if (ds->world > 1) {
@@ -582,37 +620,67 @@ int launch_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, d
         // so the total does not depend on the number of GPUs.
         pack_chunks_kernel<<<n, 128, 0, ds->stream>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
         CUDA_TRY(cudaGetLastError());
+        ds->n_launches++;
         const size_t cnt = (size_t)n * ds->max_chunks_rank;
         int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, ds->stream);
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
-        CUDA_TRY(cudaMemcpyAsync(ds->h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
     } else
-        CUDA_TRY(cudaMemcpyAsync(ds->h_total, ds->d_total, sizeof(double) * n, cudaMemcpyDeviceToHost, ds->stream));
-    CUDA_TRY(cudaMemcpyAsync(ds->h_status, ds->d_status, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ds->stream));
-    CUDA_TRY(cudaStreamSynchronize(ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, sizeof(double) * n, cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaMemcpyAsync(g.h_status, ds->d_status, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaEventRecord(g.done, ds->stream));
+    ds->h2d_bytes += bytes;
+    ds->d2h_bytes += (ds->world > 1 ? sizeof(double) * n * ds->max_chunks_rank * ds->world : sizeof(double) * n) + sizeof(unsigned) * n;
+    for (int i = 0; i < n; ++i) {
+        ds->alg_bytes += chains[i]->alg_bytes;
+        ds->n_scores += chains[i]->n_scores;
+    }
+    g.busy = true;
+    g.n = n;
+    g.ticket = tk;
+    ds->next_ticket++;
+    *ticket = tk;
+    return SCICONE_OK;
+}
+
+// Wait for a queued launch and fetch its totals.
+int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* totals) {
+    scicone_dataset::Segment& g = ds->seg[ticket % scicone_dataset::kRing];
+    if (!g.busy || g.ticket != ticket) return fail(SCICONE_ERR_STATE, "unknown or already collected ticket %llu", ticket);
+    CUDA_TRY(cudaEventSynchronize(g.done));
+    g.busy = false;
+    const int n = g.n;
     if (ds->profiling) {
         float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, ds->ev0, ds->ev1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
         ds->last_kernel_us = 1e3 * ms;
+        ds->sum_kernel_us += ds->last_kernel_us;
+        ds->n_timed++;
     }
     bool nan = false;
     for (int i = 0; i < n; ++i) {
         if (ds->world > 1) {
             double s = 0.0;
             for (int rk = 0; rk < ds->world; ++rk) {
-                const double* c = ds->h_gather + ((size_t)rk * n + i) * ds->max_chunks_rank;
+                const double* c = g.h_gather + ((size_t)rk * n + i) * ds->max_chunks_rank;
                 for (int q = 0; q < ds->max_chunks_rank; ++q) s += c[q];
             }
             totals[i] = s;
         } else
-            totals[i] = ds->h_total[i];
-        if (ds->h_status[i]) nan = true;
+            totals[i] = g.h_total[i];
+        if (g.h_status[i]) nan = true;
     }
     if (nan) {
-        CUDA_TRY(cudaMemsetAsync(ds->d_status, 0, sizeof(unsigned) * n, ds->stream));
+        CUDA_TRY(cudaMemsetAsync(ds->d_status, 0, sizeof(unsigned) * ds->slots, ds->stream));
         return fail(SCICONE_ERR_NAN, "a per-cell aggregate is NaN (reference: assert(!isnan), Inference.h:1150,1191)");
     }
     return SCICONE_OK;
+}
+
+int launch_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, double* totals) {
+    unsigned long long tk = 0;
+    int rc = submit_proposals(ds, chains, n, &tk);
+    return rc ? rc : wait_proposals(ds, tk, totals);
 }
 
 int od_scores(scicone_chain* ch, double nu, double* out) {
@@ -667,11 +735,13 @@ int od_scores(scicone_chain* ch, double nu, double* out) {
     b.resize(round_up(b.size(), 16));
     memcpy(b.data(), &H, sizeof H);
     const size_t head = 16;
-    rc = ds->ensure_arena(head + b.size());
+    rc = ds->drain();
+    if (!rc) rc = ds->ensure_arena(head + b.size());
     if (rc) return rc;
-    reinterpret_cast<unsigned*>(ds->h_arena)[0] = (unsigned)head;
-    memcpy(ds->h_arena + head, b.data(), b.size());
-    CUDA_TRY(cudaMemcpyAsync(ds->d_arena, ds->h_arena, head + b.size(), cudaMemcpyHostToDevice, ds->stream));
+    scicone_dataset::Segment& g = ds->seg[0];
+    reinterpret_cast<unsigned*>(g.h_arena)[0] = (unsigned)head;
+    memcpy(g.h_arena + head, b.data(), b.size());
+    CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, head + b.size(), cudaMemcpyHostToDevice, ds->stream));
     od_root_kernel<<<dim3(ds->n_cta, 1), kBlock, 0, ds->stream>>>(ds->d_arena);
     CUDA_TRY(cudaGetLastError());
     ds->n_launches++;
@@ -681,13 +751,13 @@ int od_scores(scicone_chain* ch, double nu, double* out) {
         const size_t cnt = ds->max_chunks_rank;
         int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, ds->stream);
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
-        CUDA_TRY(cudaMemcpyAsync(ds->h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
         CUDA_TRY(cudaStreamSynchronize(ds->stream));
-        for (size_t q = 0; q < cnt * ds->world; ++q) total += ds->h_gather[q];
+        for (size_t q = 0; q < cnt * ds->world; ++q) total += g.h_gather[q];
     } else {
-        CUDA_TRY(cudaMemcpyAsync(ds->h_total, ds->d_total, sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
         CUDA_TRY(cudaStreamSynchronize(ds->stream));
-        total = ds->h_total[0];
+        total = g.h_total[0];
     }
     if (out) *out = total;
     return SCICONE_OK;
@@ -771,8 +841,11 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     } while (0)
     DS_TRY(cudaSetDevice(ds->device));
     DS_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
-    DS_TRY(cudaEventCreate(&ds->ev0));
-    DS_TRY(cudaEventCreate(&ds->ev1));
+    for (scicone_dataset::Segment& g : ds->seg) {
+        DS_TRY(cudaEventCreate(&g.ev0));
+        DS_TRY(cudaEventCreate(&g.ev1));
+        DS_TRY(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    }
     DS_TRY(cudaMalloc(&ds->dDt, sizeof(double) * ds->Mp * ds->K));
     DS_TRY(cudaMalloc(&ds->dS, sizeof(double) * ds->Mp));
     DS_TRY(cudaMalloc(&ds->dW, sizeof(int) * ds->Mp));
@@ -812,12 +885,15 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW);
     cudaFree(ds->d_arena); cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
     cudaFree(ds->d_counter); cudaFree(ds->d_status); cudaFree(ds->d_gather); cudaFree(ds->d_send);
-    if (ds->h_arena) cudaFreeHost(ds->h_arena);
-    if (ds->h_total) cudaFreeHost(ds->h_total);
-    if (ds->h_status) cudaFreeHost(ds->h_status);
-    if (ds->h_gather) cudaFreeHost(ds->h_gather);
-    if (ds->ev0) cudaEventDestroy(ds->ev0);
-    if (ds->ev1) cudaEventDestroy(ds->ev1);
+    for (scicone_dataset::Segment& g : ds->seg) {
+        if (g.h_arena) cudaFreeHost(g.h_arena);
+        if (g.h_total) cudaFreeHost(g.h_total);
+        if (g.h_status) cudaFreeHost(g.h_status);
+        if (g.h_gather) cudaFreeHost(g.h_gather);
+        if (g.ev0) cudaEventDestroy(g.ev0);
+        if (g.ev1) cudaEventDestroy(g.ev1);
+        if (g.done) cudaEventDestroy(g.done);
+    }
     if (ds->stream) cudaStreamDestroy(ds->stream);
     delete ds;
 }
@@ -915,9 +991,8 @@ int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t_prim
     return SCICONE_OK;
 }
 
-int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const* t_primes, int32_t n,
-                                       double* t_prime_sums) {
-    if (!chains || n <= 0 || !t_prime_sums) return fail(SCICONE_ERR_ARG, "batch: null or empty");
+int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const* t_primes, int32_t n, uint64_t* ticket) {
+    if (!chains || n <= 0 || !ticket) return fail(SCICONE_ERR_ARG, "batch: null or empty");
     scicone_dataset* ds = chains[0]->ds;
     for (int i = 0; i < n; ++i) {
         if (!chains[i] || chains[i]->ds != ds) return fail(SCICONE_ERR_ARG, "batch: all chains must share one dataset");
@@ -938,10 +1013,29 @@ int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scico
             return rc;
         }
     }
-    rc = launch_proposals(ds, chains, n, t_prime_sums);
-    if (rc && rc != SCICONE_ERR_NAN) return rc;
+    unsigned long long tk = 0;
+    rc = submit_proposals(ds, chains, n, &tk);
+    if (rc) {
+        for (int q = 0; q < n; ++q) drop_pending(chains[q]);
+        return rc;
+    }
     for (int i = 0; i < n; ++i) chains[i]->evaluated = true;
-    return rc;
+    *ticket = tk;
+    return SCICONE_OK;
+}
+
+int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* t_prime_sums) {
+    if (!ds || !t_prime_sums) return fail(SCICONE_ERR_ARG, "batch_wait: null argument");
+    int rc = ds->set_device();
+    return rc ? rc : wait_proposals(ds, ticket, t_prime_sums);
+}
+
+int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const* t_primes, int32_t n,
+                                       double* t_prime_sums) {
+    if (!t_prime_sums) return fail(SCICONE_ERR_ARG, "batch: null output");
+    uint64_t tk = 0;
+    int rc = scicone_batch_submit(chains, t_primes, n, &tk);
+    return rc ? rc : scicone_batch_wait(chains[0]->ds, tk, t_prime_sums);
 }
 
 int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t_prime, double* t_prime_sum) {
@@ -1156,6 +1250,49 @@ int scicone_set_profiling(scicone_dataset* ds, int32_t on) {
 int scicone_last_kernel_time_us(scicone_dataset* ds, double* us) {
     if (!ds || !us) return fail(SCICONE_ERR_ARG, "null argument");
     *us = ds->last_kernel_us;
+    return SCICONE_OK;
+}
+int scicone_kernel_time_stats(scicone_dataset* ds, double* sum_us, uint64_t* n_timed, int32_t reset) {
+    if (!ds) return fail(SCICONE_ERR_ARG, "null dataset");
+    if (sum_us) *sum_us = ds->sum_kernel_us;
+    if (n_timed) *n_timed = ds->n_timed;
+    if (reset) {
+        ds->sum_kernel_us = 0.0;
+        ds->n_timed = 0;
+    }
+    return SCICONE_OK;
+}
+int scicone_counters(scicone_dataset* ds, double out[4], int32_t reset) {
+    if (!ds || !out) return fail(SCICONE_ERR_ARG, "null argument");
+    out[0] = (double)ds->h2d_bytes;
+    out[1] = (double)ds->d2h_bytes;
+    out[2] = ds->alg_bytes;
+    out[3] = ds->n_scores;
+    if (reset) {
+        ds->h2d_bytes = ds->d2h_bytes = 0;
+        ds->alg_bytes = ds->n_scores = 0.0;
+    }
+    return SCICONE_OK;
+}
+int scicone_region_mark(scicone_dataset* ds, int32_t which) {
+    if (!ds || which < 0 || which > 1) return fail(SCICONE_ERR_ARG, "region_mark: bad argument");
+    int rc = ds->set_device();
+    if (rc) return rc;
+    if (!ds->region_ev[which]) CUDA_TRY(cudaEventCreate(&ds->region_ev[which]));
+    CUDA_TRY(cudaEventRecord(ds->region_ev[which], ds->stream));
+    return SCICONE_OK;
+}
+int scicone_region_elapsed_ms(scicone_dataset* ds, double* ms) {
+    if (!ds || !ms || !ds->region_ev[0] || !ds->region_ev[1]) return fail(SCICONE_ERR_ARG, "region_elapsed: marks missing");
+    CUDA_TRY(cudaEventSynchronize(ds->region_ev[1]));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, ds->region_ev[0], ds->region_ev[1]));
+    *ms = f;
+    return SCICONE_OK;
+}
+int scicone_device_bytes(scicone_dataset* ds, uint64_t* bytes) {
+    if (!ds || !bytes) return fail(SCICONE_ERR_ARG, "null argument");
+    *bytes = (uint64_t)(ds->pool.n_rows - ds->pool.free_rows.size()) * ds->Mp * sizeof(double) + (uint64_t)ds->Mp * ds->K * sizeof(double);
     return SCICONE_OK;
 }
 int scicone_kernel_launches(scicone_dataset* ds, uint64_t* n) {
