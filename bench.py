@@ -161,9 +161,7 @@ def run_engine(args):
 
     def queue_step(s):
         for ch, (_, steps) in zip(chains, traces):
-            ft, roots, _, kind = steps[s]
-            if kind == "nu":
-                ch.compute_t_prime_od_scores(ft.nu)
+            ft, roots, _, kind = steps[s]  # a nu proposal gets its root score from the same launch
             for idx in roots:
                 ch.compute_t_prime_scores(ft, idx)
 

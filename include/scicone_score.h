@@ -133,9 +133,13 @@ int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t_prime,
  * The same two steps for `n` chains in ONE kernel launch (independent restarts or
  * proposals evaluated in lock-step).  Every chain must have queued its subtree
  * roots with scicone_compute_t_prime_scores.  All chains must share one dataset.
+ * A proposal whose nu differs from the committed tree's (Inference::apply_overdispersion_change,
+ * Inference.h:916-954) also gets its root score at the new nu from the same launch, returned in
+ * od_scores[i] (NaN for the other proposals) - unless scicone_compute_t_prime_od_scores was already
+ * called for that nu.
  */
 int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const* t_primes,
-                                       int32_t n, double* t_prime_sums);
+                                       int32_t n, double* t_prime_sums, double* od_scores /* [n] or NULL */);
 
 /*
  * Pipelined form of the batch call: submit queues the copy-in, the kernel and the copy-out on the
@@ -145,7 +149,7 @@ int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scico
  * outstanding.  Reads (scicone_read_*) always see the finished state.
  */
 int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const* t_primes, int32_t n, uint64_t* ticket);
-int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* t_prime_sums);
+int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* t_prime_sums, double* od_scores /* [n] or NULL */);
 
 /*
  * Accept (Inference.h:867-870: t_sums = t_prime_sums, t_maxs = t_prime_maxs,

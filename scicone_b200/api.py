@@ -82,9 +82,9 @@ def lib():
         L.scicone_compute_t_prime_od_scores.argtypes = [vp, C.c_double, dp]
         L.scicone_compute_t_prime_scores.argtypes = [vp, tp, C.c_int32]
         L.scicone_compute_t_prime_sums.argtypes = [vp, tp, dp]
-        L.scicone_batch_compute_t_prime_sums.argtypes = [C.POINTER(vp), C.POINTER(tp), C.c_int32, dp]
+        L.scicone_batch_compute_t_prime_sums.argtypes = [C.POINTER(vp), C.POINTER(tp), C.c_int32, dp, dp]
         L.scicone_batch_submit.argtypes = [C.POINTER(vp), C.POINTER(tp), C.c_int32, C.POINTER(C.c_uint64)]
-        L.scicone_batch_wait.argtypes = [vp, C.c_uint64, dp]
+        L.scicone_batch_wait.argtypes = [vp, C.c_uint64, dp, dp]
         L.scicone_kernel_time_stats.argtypes = [vp, dp, C.POINTER(C.c_uint64), C.c_int32]
         L.scicone_counters.argtypes = [vp, dp, C.c_int32]
         L.scicone_region_mark.argtypes = [vp, C.c_int32]
@@ -314,14 +314,14 @@ class Chain:
         return ids, cn
 
 
-def batch_compute_t_prime_sums(chains, trees):
+def batch_compute_t_prime_sums(chains, trees, with_od=False):
     """One kernel launch for the queued proposals of several chains on one dataset."""
     n = len(chains)
     hs = (C.c_void_p * n)(*[c._h for c in chains])
     ts = (C.POINTER(CTree) * n)(*[C.pointer(t.ctree) for t in trees])
-    out = np.zeros(n)
-    _check(lib().scicone_batch_compute_t_prime_sums(hs, ts, n, _dp(out)))
-    return out
+    out, od = np.zeros(n), np.zeros(n)
+    _check(lib().scicone_batch_compute_t_prime_sums(hs, ts, n, _dp(out), _dp(od)))
+    return (out, od) if with_od else out
 
 
 class BatchLauncher:
@@ -333,6 +333,7 @@ class BatchLauncher:
         self.ds = self.chains[0].ds
         self._hs = (C.c_void_p * self.n)(*[c._h for c in self.chains])
         self._out = np.zeros(self.n)
+        self._od = np.zeros(self.n)
         self._ticket = C.c_uint64()
 
     def submit(self):
@@ -340,7 +341,7 @@ class BatchLauncher:
         return self._ticket.value
 
     def wait(self, ticket):
-        _check(lib().scicone_batch_wait(self.ds._h, ticket, _dp(self._out)))
+        _check(lib().scicone_batch_wait(self.ds._h, ticket, _dp(self._out), _dp(self._od)))
         return self._out
 
     def run(self):

@@ -36,7 +36,8 @@ enum : unsigned {
     PROP_MAX = 1u,       // max scoring (Inference::max_scoring)
     PROP_OD = 2u,        // overdispersed likelihood (globals is_overdispersed)
     PROP_FULL = 4u,      // full table pass (Inference::compute_t_table): no committed state is read
-    PROP_SCRATCH = 8u    // to_add.size() >= unchanged_vals.size(): recompute the log-sum from scratch
+    PROP_SCRATCH = 8u,   // to_add.size() >= unchanged_vals.size(): recompute the log-sum from scratch
+    PROP_WITH_OD = 16u   // the proposal changes nu: also evaluate the root ("overdispersed") score at the new nu
 };
 
 struct alignas(16) DevTask {
@@ -79,12 +80,13 @@ struct alignas(16) DevHeader {
     double* sums_new;
     const int* maxid_old;
     int* maxid_new;
-    double* partial;      // [gridDim.x] per-CTA partial sums
-    double* chunk_sums;   // [ceil(gridDim.x / kCtasPerChunk)]
-    double* total;        // [1]
+    double* partial;      // [2][gridDim.x] per-CTA partial sums (0: tree score, 1: root score)
+    double* chunk_sums;   // [2][ceil(gridDim.x / kCtasPerChunk)]
+    double* total;        // [2]
     unsigned* counter;    // arrival counter for the last-CTA reduction
     unsigned* status;     // bit 0: NaN aggregate
-    unsigned off_tasks, off_events, off_addorder, off_old, off_unch, pad2;
+    unsigned off_tasks, off_events, off_addorder, off_old, off_unch;
+    unsigned off_od;      // DevOdHeader of the root-score part (PROP_WITH_OD)
 };
 
 struct alignas(16) DevOdHeader {
@@ -120,11 +122,15 @@ __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
 // Last CTA to arrive adds the per-CTA partials in a fixed order: first inside
 // 1024-cell chunks, then the chunks.  The result does not depend on the CTA
 // schedule, and (because shards are whole chunks) not on the number of GPUs.
-__device__ __forceinline__ void finish_reduction(double cta_sum, double* partial, double* chunk_sums, double* total,
-                                                 unsigned* counter, double* smem_chunks) {
+// Two sums travel together: [0] the tree score, [1] the root score (0 when not requested).
+__device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum1, double* partial, double* chunk_sums,
+                                                 double* total, unsigned* counter, double* smem_chunks) {
     __shared__ bool is_last;
+    const int n_cta = gridDim.x;
+    const int n_chunks = (n_cta + kCtasPerChunk - 1) / kCtasPerChunk;
     if (threadIdx.x == 0) {
-        partial[blockIdx.x] = cta_sum;
+        partial[blockIdx.x] = cta_sum0;
+        partial[n_cta + blockIdx.x] = cta_sum1;
         __threadfence();
         unsigned ticket = atomicAdd(counter, 1u);
         is_last = (ticket == gridDim.x - 1);
@@ -132,30 +138,62 @@ __device__ __forceinline__ void finish_reduction(double cta_sum, double* partial
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const int n_cta = gridDim.x;
-    const int n_chunks = (n_cta + kCtasPerChunk - 1) / kCtasPerChunk;
-    double grand = 0.0;
-    for (int base = 0; base < n_chunks; base += kBlock) {
-        int c = base + threadIdx.x;
-        double cs = 0.0;
-        if (c < n_chunks) {
-            const int b0 = c * kCtasPerChunk;
-            const int b1 = min(b0 + kCtasPerChunk, n_cta);
-            for (int b = b0; b < b1; ++b) cs += __ldcg(partial + b);
-            chunk_sums[c] = cs;
+    for (int v = 0; v < 2; ++v) {
+        const double* part = partial + (size_t)v * n_cta;
+        double* chunks = chunk_sums + (size_t)v * n_chunks;
+        double grand = 0.0;
+        for (int base = 0; base < n_chunks; base += kBlock) {
+            int c = base + threadIdx.x;
+            double cs = 0.0;
+            if (c < n_chunks) {
+                const int b0 = c * kCtasPerChunk;
+                const int b1 = min(b0 + kCtasPerChunk, n_cta);
+                for (int b = b0; b < b1; ++b) cs += __ldcg(part + b);
+                chunks[c] = cs;
+            }
+            smem_chunks[threadIdx.x] = cs;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int lim = min(kBlock, n_chunks - base);
+                for (int i = 0; i < lim; ++i) grand += smem_chunks[i];
+            }
+            __syncthreads();
         }
-        smem_chunks[threadIdx.x] = cs;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int lim = min(kBlock, n_chunks - base);
-            for (int i = 0; i < lim; ++i) grand += smem_chunks[i];
+        if (threadIdx.x == 0) total[v] = grand;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+}
+
+// Tree::get_od_root_score, Tree.h:1774-1810, for one cell (also materialises the neutral-state lgamma rows it
+// computes anyway).
+__device__ __forceinline__ double od_root_cell(const DevOdHeader& H, const unsigned char* blob, int j) {
+    double* const* rows = reinterpret_cast<double* const*>(blob + H.off_rows);
+    const double* arg = reinterpret_cast<const double*>(blob + H.off_arg);
+    const double* cc = reinterpret_cast<const double*>(blob + H.off_c);
+    const unsigned char* build = blob + H.off_build;
+    const double S = H.S[j];
+    const int K = H.n_regions;
+    double od = 0.0;
+    if (H.flags & PROP_OD) {
+        od += H.lg_nz;
+        od -= lgamma(S + H.nz);
+        for (int k = 0; k < K; ++k) {
+            double v;
+            if (build[k]) {
+                v = lgamma(H.Dt[(long long)k * H.row_stride + j] + arg[k]);
+                if (rows[k]) rows[k][j] = v;
+            } else
+                v = rows[k][j];
+            od += v;
+            od -= cc[k];
         }
-        __syncthreads();
+    } else {
+        const double term1 = -S * H.lg_nz;
+        double term2 = 0.0;
+        for (int k = 0; k < K; ++k) term2 += H.Dt[(long long)k * H.row_stride + j] * arg[k];
+        od += term1 + term2;
     }
-    if (threadIdx.x == 0) {
-        *total = grand;
-        *counter = 0u;
-    }
+    return od;
 }
 
 // ---------------------------------------------------------------------------------
@@ -181,7 +219,7 @@ __global__ void __launch_bounds__(kBlock) score_proposals_kernel(const unsigned 
     const bool live = j < H.n_cells;
     const unsigned pflags = H.flags;
     const bool od = pflags & PROP_OD;
-    double contrib = 0.0;
+    double contrib = 0.0, contrib_od = 0.0;
 
     if (live) {
         const double S = H.S[j];
@@ -332,12 +370,19 @@ __global__ void __launch_bounds__(kBlock) score_proposals_kernel(const unsigned 
         if (res != res) atomicOr(H.status, 1u);
         H.sums_new[j] = res;
         contrib = res * (double)H.w[j];
+        if (pflags & PROP_WITH_OD)  // Inference::compute_t_prime_od_scores, Inference.h:1421-1433
+            contrib_od = od_root_cell(*reinterpret_cast<const DevOdHeader*>(blob + H.off_od), blob + H.off_od, j) * (double)H.w[j];
     }
     // ---- weighted sum over cells: Inference::comparison, Inference.h:292-294 ----
     __syncthreads();
     const double cta_sum = block_sum(contrib, red_buf);
     __syncthreads();
-    finish_reduction(cta_sum, H.partial, H.chunk_sums, H.total, H.counter, red_buf);
+    double cta_od = 0.0;
+    if (pflags & PROP_WITH_OD) {  // uniform per proposal
+        cta_od = block_sum(contrib_od, red_buf);
+        __syncthreads();
+    }
+    finish_reduction(cta_sum, cta_od, H.partial, H.chunk_sums, H.total, H.counter, red_buf);
 }
 
 // ---------------------------------------------------------------------------------
@@ -351,50 +396,28 @@ __global__ void __launch_bounds__(kBlock) od_root_kernel(const unsigned char* __
     __shared__ double red_buf[kBlock];
     const unsigned char* blob = arena + blob_off[blockIdx.y];
     const DevOdHeader& H = *reinterpret_cast<const DevOdHeader*>(blob);
-    double* const* rows = reinterpret_cast<double* const*>(blob + H.off_rows);
-    const double* arg = reinterpret_cast<const double*>(blob + H.off_arg);
-    const double* cc = reinterpret_cast<const double*>(blob + H.off_c);
-    const unsigned char* build = blob + H.off_build;
     const int j = blockIdx.x * kBlock + threadIdx.x;
     double contrib = 0.0;
     if (j < H.n_cells) {
-        const double S = H.S[j];
-        const int K = H.n_regions;
-        double od = 0.0;
-        if (H.flags & PROP_OD) {
-            od += H.lg_nz;
-            od -= lgamma(S + H.nz);
-            for (int k = 0; k < K; ++k) {
-                double v;
-                if (build[k]) {
-                    v = lgamma(H.Dt[(long long)k * H.row_stride + j] + arg[k]);
-                    if (rows[k]) rows[k][j] = v;
-                } else
-                    v = rows[k][j];
-                od += v;
-                od -= cc[k];
-            }
-        } else {
-            const double term1 = -S * H.lg_nz;
-            double term2 = 0.0;
-            for (int k = 0; k < K; ++k) term2 += H.Dt[(long long)k * H.row_stride + j] * arg[k];
-            od += term1 + term2;
-        }
+        const double od = od_root_cell(H, blob, j);
         if (H.cell_out) H.cell_out[j] = od;
         contrib = od * (double)H.w[j];
     }
     __syncthreads();
     const double cta_sum = block_sum(contrib, red_buf);
     __syncthreads();
-    finish_reduction(cta_sum, H.partial, H.chunk_sums, H.total, H.counter, red_buf);
+    finish_reduction(0.0, cta_sum, H.partial, H.chunk_sums, H.total, H.counter, red_buf);
 }
 
 // Multi-GPU: copy the per-chunk sums of each proposal into the fixed-width, zero-padded send buffer of
 // the all-gather (one CTA per proposal).
 __global__ void pack_chunks_kernel(const double* __restrict__ chunk_sums, int n_chunks, double* __restrict__ send,
                                    int width) {
-    for (int c = threadIdx.x; c < width; c += blockDim.x)
-        send[(long long)blockIdx.x * width + c] = c < n_chunks ? chunk_sums[(long long)blockIdx.x * n_chunks + c] : 0.0;
+    // per proposal: [2][n_chunks] -> [2][width]
+    for (int c = threadIdx.x; c < 2 * width; c += blockDim.x) {
+        const int v = c / width, q = c % width;
+        send[(long long)blockIdx.x * 2 * width + c] = q < n_chunks ? chunk_sums[((long long)blockIdx.x * 2 + v) * n_chunks + q] : 0.0;
+    }
 }
 
 // ---------------------------------------------------------------------------------

@@ -199,11 +199,12 @@ struct scicone_dataset {
     // without a host round trip; one device arena (copies and kernels are ordered by the stream)
     struct Segment {
         unsigned char* h_arena = nullptr;
-        double* h_total = nullptr;     // pinned [slots]
+        double* h_total = nullptr;     // pinned [slots][2]
         unsigned* h_status = nullptr;  // pinned [slots]
-        double* h_gather = nullptr;    // pinned [world][slots][max_chunks_rank]
+        double* h_gather = nullptr;    // pinned [world][slots][2][max_chunks_rank]
         cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
         int n = 0;
+        std::vector<char> with_od;
         bool busy = false;
         unsigned long long ticket = 0;
     };
@@ -215,9 +216,9 @@ struct scicone_dataset {
     // per batch slot: reduction scratch and results
     int n_cta = 0, n_chunks = 0;
     int slots = 0;
-    double* d_partial = nullptr;  // [slots][n_cta]
-    double* d_chunk = nullptr;    // [slots][n_chunks]
-    double* d_total = nullptr;    // [slots]
+    double* d_partial = nullptr;  // [slots][2][n_cta]   (0: tree score, 1: root score)
+    double* d_chunk = nullptr;    // [slots][2][n_chunks]
+    double* d_total = nullptr;    // [slots][2]
     unsigned* d_counter = nullptr;
     unsigned* d_status = nullptr;
     // multi-GPU
@@ -282,22 +283,22 @@ struct scicone_dataset {
             g.h_gather = nullptr;
         }
         slots = 0;
-        CUDA_TRY(cudaMalloc(&d_partial, sizeof(double) * size_t(ns) * n_cta));
-        CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * size_t(ns) * n_chunks));
-        CUDA_TRY(cudaMalloc(&d_total, sizeof(double) * ns));
+        CUDA_TRY(cudaMalloc(&d_partial, sizeof(double) * size_t(ns) * 2 * n_cta));
+        CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * size_t(ns) * 2 * n_chunks));
+        CUDA_TRY(cudaMalloc(&d_total, sizeof(double) * ns * 2));
         CUDA_TRY(cudaMalloc(&d_counter, sizeof(unsigned) * ns));
         CUDA_TRY(cudaMalloc(&d_status, sizeof(unsigned) * ns));
         CUDA_TRY(cudaMemset(d_counter, 0, sizeof(unsigned) * ns));
         CUDA_TRY(cudaMemset(d_status, 0, sizeof(unsigned) * ns));
         for (Segment& g : seg) {
-            CUDA_TRY(cudaMallocHost(&g.h_total, sizeof(double) * ns));
+            CUDA_TRY(cudaMallocHost(&g.h_total, sizeof(double) * ns * 2));
             CUDA_TRY(cudaMallocHost(&g.h_status, sizeof(unsigned) * ns));
         }
         slots = ns;
         if (world > 1) {
             cudaFree(d_gather); cudaFree(d_send);
             d_gather = d_send = nullptr;
-            size_t per_rank = size_t(ns) * max_chunks_rank;
+            size_t per_rank = size_t(ns) * 2 * max_chunks_rank;
             CUDA_TRY(cudaMalloc(&d_send, sizeof(double) * per_rank));
             CUDA_TRY(cudaMalloc(&d_gather, sizeof(double) * per_rank * world));
             for (Segment& g : seg) CUDA_TRY(cudaMallocHost(&g.h_gather, sizeof(double) * per_rank * world));
@@ -317,6 +318,10 @@ struct scicone_chain {
     LCache Lt, Lp;
     double Lt_nu = 0.0, Lp_nu = 0.0;
     bool Lt_valid = false, Lp_valid = false;
+    double t_nu = 0.0;  // Tree::nu of the committed tree
+    bool od_p_valid = false;  // compute_t_prime_od_scores was already called for od_p_nu
+    double od_p_nu = 0.0;
+    bool with_od = false;     // the compiled proposal carries the root-score part
     // queued proposal
     bool pending = false;
     bool evaluated = false;
@@ -359,6 +364,8 @@ void drop_pending(scicone_chain* ch) {
     ch->evaluated = false;
     ch->deleted_id = -1;
     ch->p_full = false;
+    ch->od_p_valid = false;
+    ch->with_od = false;
     release_cache(ch->ds, ch->Lp);
     ch->Lp_valid = false;
 }
@@ -369,6 +376,57 @@ size_t blob_append(std::vector<unsigned char>& b, const std::vector<T>& v) {
     b.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
     if (!v.empty()) memcpy(b.data() + off, v.data(), v.size() * sizeof(T));
     return off;
+}
+
+// Root-score request (Tree::get_od_root_score, Tree.h:1774-1810) as a self-contained block: header + per-region arrays.
+int build_od_block(scicone_chain* ch, double nu, int slot, std::vector<unsigned char>& b) {
+    scicone_dataset* ds = ch->ds;
+    const int K = ds->K;
+    std::vector<double*> rows(K, nullptr);
+    std::vector<double> arg(K), cc(K);
+    std::vector<unsigned char> build(round_up(K, 16), 0);
+    DevOdHeader H;
+    memset(&H, 0, sizeof H);
+    H.n_regions = K;
+    H.n_cells = ds->M;
+    H.flags = ds->od ? PROP_OD : 0u;
+    H.S = ds->dS;
+    H.w = ds->dW;
+    H.Dt = ds->dDt;
+    H.row_stride = (long long)ds->Mp;
+    H.partial = ds->d_partial + (size_t)slot * 2 * ds->n_cta;
+    H.chunk_sums = ds->d_chunk + (size_t)slot * 2 * ds->n_chunks;
+    H.total = ds->d_total + (size_t)slot * 2;
+    H.counter = ds->d_counter + slot;
+    if (ds->od) {  // Tree.h:1783-1797 (no eta substitution here, quirk Q2)
+        LCache* L = cache_for(ch, nu);
+        H.nz = nu * ds->root_z;
+        H.lg_nz = lgamma(H.nz);
+        for (int k = 0; k < K; ++k) {
+            arg[k] = nu * ds->neutral[k] * ds->r[k];
+            cc[k] = lgamma(arg[k]);
+            if (ds->neutral[k] != 0) {  // L(k, 0) means eta in compute_score: do not alias it
+                double** slotp = &(*L)[lkey(k, ds->neutral[k])];
+                if (!*slotp) {
+                    CUDA_TRY(ds->pool.get(slotp));
+                    build[k] = 1;
+                }
+                rows[k] = *slotp;
+            } else
+                build[k] = 1;
+        }
+    } else {  // Tree.h:1799-1806
+        H.lg_nz = log((double)ds->sum_r);
+        for (int k = 0; k < K; ++k) arg[k] = log((double)ds->r[k]);
+    }
+    b.assign(sizeof H, 0);
+    H.off_rows = (unsigned)blob_append(b, rows);
+    H.off_arg = (unsigned)blob_append(b, arg);
+    H.off_c = (unsigned)blob_append(b, cc);
+    H.off_build = (unsigned)blob_append(b, build);
+    b.resize(round_up(b.size(), 16));
+    memcpy(b.data(), &H, sizeof H);
+    return SCICONE_OK;
 }
 
 // Compile the queued proposal of `ch` into ch->blob.  `slot` selects the reduction scratch.
@@ -568,9 +626,9 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     H.sums_new = ch->sums[1];
     H.maxid_old = ch->maxid[0];
     H.maxid_new = ch->maxid[1];
-    H.partial = ds->d_partial + (size_t)slot * ds->n_cta;
-    H.chunk_sums = ds->d_chunk + (size_t)slot * ds->n_chunks;
-    H.total = ds->d_total + slot;
+    H.partial = ds->d_partial + (size_t)slot * 2 * ds->n_cta;
+    H.chunk_sums = ds->d_chunk + (size_t)slot * 2 * ds->n_chunks;
+    H.total = ds->d_total + (size_t)slot * 2;
     H.counter = ds->d_counter + slot;
     H.status = ds->d_status + slot;
 
@@ -587,6 +645,19 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     H.off_addorder = (unsigned)blob_append(b, addorder);
     H.off_old = (unsigned)blob_append(b, old_rows);
     H.off_unch = (unsigned)blob_append(b, unch);
+    // a proposal that changes nu also needs Inference::compute_t_prime_od_scores (Inference.h:942): evaluated by
+    // the same launch unless the caller already asked for it separately
+    ch->with_od = !full && nu != ch->t_nu && !(ch->od_p_valid && ch->od_p_nu == nu);
+    if (ch->with_od) {
+        std::vector<unsigned char> odb;
+        int rc = build_od_block(ch, nu, slot, odb);
+        if (rc) return rc;
+        H.flags |= PROP_WITH_OD;
+        H.off_od = (unsigned)round_up(b.size(), 16);
+        b.resize(H.off_od);
+        b.insert(b.end(), odb.begin(), odb.end());
+        ch->alg_bytes += (double)ds->M * 8.0 * ds->K;
+    }
     b.resize(round_up(b.size(), 16));
     memcpy(b.data(), &H, sizeof H);
     return SCICONE_OK;
@@ -602,6 +673,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     const unsigned long long tk = ds->next_ticket;
     scicone_dataset::Segment& g = ds->seg[tk % scicone_dataset::kRing];
     if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
+    g.with_od.assign(n, 0);
     unsigned* offs = reinterpret_cast<unsigned*>(g.h_arena);
     size_t at = head;
     for (int i = 0; i < n; ++i) {
@@ -621,20 +693,21 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         pack_chunks_kernel<<<n, 128, 0, ds->stream>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
-        const size_t cnt = (size_t)n * ds->max_chunks_rank;
+        const size_t cnt = (size_t)n * 2 * ds->max_chunks_rank;
         int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, ds->stream);
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
         CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
     } else
-        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, sizeof(double) * n, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ds->stream));
     CUDA_TRY(cudaMemcpyAsync(g.h_status, ds->d_status, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ds->stream));
     CUDA_TRY(cudaEventRecord(g.done, ds->stream));
     ds->h2d_bytes += bytes;
-    ds->d2h_bytes += (ds->world > 1 ? sizeof(double) * n * ds->max_chunks_rank * ds->world : sizeof(double) * n) + sizeof(unsigned) * n;
+    ds->d2h_bytes += (ds->world > 1 ? sizeof(double) * 2 * n * ds->max_chunks_rank * ds->world : sizeof(double) * 2 * n) + sizeof(unsigned) * n;
     for (int i = 0; i < n; ++i) {
         ds->alg_bytes += chains[i]->alg_bytes;
         ds->n_scores += chains[i]->n_scores;
     }
+    for (int i = 0; i < n; ++i) g.with_od[i] = chains[i]->with_od;
     g.busy = true;
     g.n = n;
     g.ticket = tk;
@@ -644,7 +717,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
 }
 
 // Wait for a queued launch and fetch its totals.
-int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* totals) {
+int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* totals, double* od_scores) {
     scicone_dataset::Segment& g = ds->seg[ticket % scicone_dataset::kRing];
     if (!g.busy || g.ticket != ticket) return fail(SCICONE_ERR_STATE, "unknown or already collected ticket %llu", ticket);
     CUDA_TRY(cudaEventSynchronize(g.done));
@@ -659,15 +732,19 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
     }
     bool nan = false;
     for (int i = 0; i < n; ++i) {
+        double v[2] = {0.0, 0.0};
         if (ds->world > 1) {
-            double s = 0.0;
-            for (int rk = 0; rk < ds->world; ++rk) {
-                const double* c = g.h_gather + ((size_t)rk * n + i) * ds->max_chunks_rank;
-                for (int q = 0; q < ds->max_chunks_rank; ++q) s += c[q];
-            }
-            totals[i] = s;
-        } else
-            totals[i] = g.h_total[i];
+            for (int q2 = 0; q2 < 2; ++q2)
+                for (int rk = 0; rk < ds->world; ++rk) {
+                    const double* c = g.h_gather + (((size_t)rk * n + i) * 2 + q2) * ds->max_chunks_rank;
+                    for (int q = 0; q < ds->max_chunks_rank; ++q) v[q2] += c[q];
+                }
+        } else {
+            v[0] = g.h_total[2 * i];
+            v[1] = g.h_total[2 * i + 1];
+        }
+        totals[i] = v[0];
+        if (od_scores) od_scores[i] = g.with_od[i] ? v[1] : NAN;
         if (g.h_status[i]) nan = true;
     }
     if (nan) {
@@ -680,7 +757,7 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
 int launch_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, double* totals) {
     unsigned long long tk = 0;
     int rc = submit_proposals(ds, chains, n, &tk);
-    return rc ? rc : wait_proposals(ds, tk, totals);
+    return rc ? rc : wait_proposals(ds, tk, totals, nullptr);
 }
 
 int od_scores(scicone_chain* ch, double nu, double* out) {
@@ -689,56 +766,16 @@ int od_scores(scicone_chain* ch, double nu, double* out) {
     if (rc) return rc;
     rc = ds->ensure_slots(1);
     if (rc) return rc;
-    const int K = ds->K;
-    std::vector<double*> rows(K, nullptr);
-    std::vector<double> arg(K), cc(K);
-    std::vector<unsigned char> build(round_up(K, 16), 0);
-    DevOdHeader H;
-    memset(&H, 0, sizeof H);
-    H.n_regions = K;
-    H.n_cells = ds->M;
-    H.flags = ds->od ? PROP_OD : 0u;
-    H.S = ds->dS;
-    H.w = ds->dW;
-    H.Dt = ds->dDt;
-    H.row_stride = (long long)ds->Mp;
-    H.partial = ds->d_partial;
-    H.chunk_sums = ds->d_chunk;
-    H.total = ds->d_total;
-    H.counter = ds->d_counter;
-    if (ds->od) {  // Tree::get_od_root_score, Tree.h:1783-1797 (no eta substitution here, quirk Q2)
-        LCache* L = cache_for(ch, nu);
-        H.nz = nu * ds->root_z;
-        H.lg_nz = lgamma(H.nz);
-        for (int k = 0; k < K; ++k) {
-            arg[k] = nu * ds->neutral[k] * ds->r[k];
-            cc[k] = lgamma(arg[k]);
-            if (ds->neutral[k] != 0) {  // L(k, 0) means eta in compute_score: do not alias it
-                double** slot = &(*L)[lkey(k, ds->neutral[k])];
-                if (!*slot) {
-                    CUDA_TRY(ds->pool.get(slot));
-                    build[k] = 1;
-                }
-                rows[k] = *slot;
-            } else
-                build[k] = 1;
-        }
-    } else {  // Tree.h:1799-1806
-        H.lg_nz = log((double)ds->sum_r);
-        for (int k = 0; k < K; ++k) arg[k] = log((double)ds->r[k]);
-    }
-    std::vector<unsigned char> b(sizeof H);
-    H.off_rows = (unsigned)blob_append(b, rows);
-    H.off_arg = (unsigned)blob_append(b, arg);
-    H.off_c = (unsigned)blob_append(b, cc);
-    H.off_build = (unsigned)blob_append(b, build);
-    b.resize(round_up(b.size(), 16));
-    memcpy(b.data(), &H, sizeof H);
-    const size_t head = 16;
-    rc = ds->drain();
-    if (!rc) rc = ds->ensure_arena(head + b.size());
+    std::vector<unsigned char> b;
+    rc = build_od_block(ch, nu, 0, b);
     if (rc) return rc;
-    scicone_dataset::Segment& g = ds->seg[0];
+    const size_t head = 16;
+    rc = ds->ensure_arena(head + b.size());
+    if (rc) return rc;
+    // takes the next staging segment like a proposal launch does (earlier tickets stay collectable)
+    scicone_dataset::Segment& g = ds->seg[ds->next_ticket % scicone_dataset::kRing];
+    if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
+    ds->next_ticket++;
     reinterpret_cast<unsigned*>(g.h_arena)[0] = (unsigned)head;
     memcpy(g.h_arena + head, b.data(), b.size());
     CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, head + b.size(), cudaMemcpyHostToDevice, ds->stream));
@@ -748,16 +785,20 @@ int od_scores(scicone_chain* ch, double nu, double* out) {
     double total = 0.0;
     if (ds->world > 1) {
         pack_chunks_kernel<<<1, 128, 0, ds->stream>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
-        const size_t cnt = ds->max_chunks_rank;
+        ds->n_launches++;
+        const size_t cnt = (size_t)2 * ds->max_chunks_rank;
         int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, ds->stream);
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
         CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
         CUDA_TRY(cudaStreamSynchronize(ds->stream));
-        for (size_t q = 0; q < cnt * ds->world; ++q) total += g.h_gather[q];
+        for (int rk = 0; rk < ds->world; ++rk) {
+            const double* c = g.h_gather + (size_t)rk * cnt + ds->max_chunks_rank;  // value 1 = root score
+            for (int q = 0; q < ds->max_chunks_rank; ++q) total += c[q];
+        }
     } else {
-        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, 2 * sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
         CUDA_TRY(cudaStreamSynchronize(ds->stream));
-        total = g.h_total[0];
+        total = g.h_total[1];
     }
     if (out) *out = total;
     return SCICONE_OK;
@@ -972,7 +1013,12 @@ int scicone_compute_t_od_scores(scicone_chain* ch, double nu, double* od_score) 
 }
 int scicone_compute_t_prime_od_scores(scicone_chain* ch, double nu, double* od_score) {
     if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
-    return od_scores(ch, nu, od_score);
+    int rc = od_scores(ch, nu, od_score);
+    if (!rc) {
+        ch->od_p_valid = true;
+        ch->od_p_nu = nu;
+    }
+    return rc;
 }
 
 int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t_prime, int32_t node_idx) {
@@ -1024,24 +1070,24 @@ int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const
     return SCICONE_OK;
 }
 
-int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* t_prime_sums) {
+int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* t_prime_sums, double* od_scores) {
     if (!ds || !t_prime_sums) return fail(SCICONE_ERR_ARG, "batch_wait: null argument");
     int rc = ds->set_device();
-    return rc ? rc : wait_proposals(ds, ticket, t_prime_sums);
+    return rc ? rc : wait_proposals(ds, ticket, t_prime_sums, od_scores);
 }
 
 int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const* t_primes, int32_t n,
-                                       double* t_prime_sums) {
+                                       double* t_prime_sums, double* od_scores) {
     if (!t_prime_sums) return fail(SCICONE_ERR_ARG, "batch: null output");
     uint64_t tk = 0;
     int rc = scicone_batch_submit(chains, t_primes, n, &tk);
-    return rc ? rc : scicone_batch_wait(chains[0]->ds, tk, t_prime_sums);
+    return rc ? rc : scicone_batch_wait(chains[0]->ds, tk, t_prime_sums, od_scores);
 }
 
 int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t_prime, double* t_prime_sum) {
     if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
     double total = 0.0;
-    int rc = scicone_batch_compute_t_prime_sums(&ch, &t_prime, 1, &total);
+    int rc = scicone_batch_compute_t_prime_sums(&ch, &t_prime, 1, &total, nullptr);
     if (t_prime_sum) *t_prime_sum = total;
     return rc;
 }
@@ -1067,6 +1113,7 @@ int scicone_accept(scicone_chain* ch) {
             ch->t.erase(it);
         }
     }
+    ch->t_nu = ch->tp.nu;
     std::swap(ch->sums[0], ch->sums[1]);    // t_sums = t_prime_sums, Inference.h:867
     std::swap(ch->maxid[0], ch->maxid[1]);  // t_maxs = t_prime_maxs, Inference.h:868
     if (ds->od && ch->Lp_valid && ch->Lp_nu == ch->tp.nu) {  // the proposal's nu becomes the chain's nu

@@ -107,6 +107,46 @@ def test_batched_chains_match_single_launches():
                 single[b].reject()
 
 
+def test_nu_proposal_root_score_comes_with_the_launch():
+    """Inference::apply_overdispersion_change (Inference.h:916-954): od score at the proposed nu + full rescoring;
+    the batch call returns both from one launch and they equal the two-call sequence."""
+    from scicone_b200.api import Chain, Dataset, batch_compute_t_prime_sums
+
+    data, tree = make_case(1500, 2000, 20, 8, seed=91)
+    ds = Dataset(data["D"], data["region_sizes"], neutral_states=data["neutral_states"], cluster_sizes=data["cluster_sizes"])
+    a, b = Chain(dataset=ds), Chain(dataset=ds)
+    cpu = OracleChain(D=data["D"], region_sizes=data["region_sizes"], neutral_states=data["neutral_states"],
+                      cluster_sizes=data["cluster_sizes"])
+    ft = tree.flat()
+    for ch in (a, b, cpu):
+        ch.compute_t_table(ft)
+    for step in range(6):
+        t2, roots, kind = tree.propose(kinds=("nu", "add_remove"), weights=[0.7, 0.3])
+        f2 = t2.flat()
+        od_ref = b.compute_t_prime_od_scores(f2.nu) if kind == "nu" else None
+        for rid in roots:
+            for ch in (a, b, cpu):
+                ch.compute_t_prime_scores(f2, f2.index_of(rid))
+        totals, ods = batch_compute_t_prime_sums([a], [f2], with_od=True)
+        tb, tc = b.compute_t_prime_sums(f2), cpu.compute_t_prime_sums(f2)
+        assert totals[0] == tb
+        assert abs(tb - tc) <= 1e-9 * max(1.0, abs(tc))
+        if kind == "nu":
+            assert ods[0] == od_ref
+            oc = cpu.compute_t_prime_od_scores(f2.nu)
+            assert abs(od_ref - oc) <= 1e-9 * abs(oc)
+        else:
+            assert np.isnan(ods[0])
+        if step % 2 == 0:
+            for ch in (a, b):
+                ch.accept()
+            cpu.accept(f2)
+            tree = t2
+        else:
+            for ch in (a, b, cpu):
+                ch.reject()
+
+
 def test_errors_are_reported_not_thrown():
     from scicone_b200.api import Chain, SciconeError
 
