@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "scicone_t_node_ids", "scicone_read_t_scores", "scicone_read_t_sums", "scicone_read_t_maxs",
     "scicone_read_t_prime_sums", "scicone_read_t_prime_maxs", "scicone_t_prime_n_rescored",
     "scicone_read_t_prime_scores", "scicone_assign_cells_to_nodes", "scicone_comm_unique_id",
-    "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_kernel_launches",
+    "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_build_time_stats", "scicone_kernel_launches",
     "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
 ]
 
@@ -86,6 +86,7 @@ def lib():
         L.scicone_batch_submit.argtypes = [C.POINTER(vp), C.POINTER(tp), C.c_int32, C.POINTER(C.c_uint64)]
         L.scicone_batch_wait.argtypes = [vp, C.c_uint64, dp, dp]
         L.scicone_kernel_time_stats.argtypes = [vp, dp, C.POINTER(C.c_uint64), C.c_int32]
+        L.scicone_build_time_stats.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
         L.scicone_counters.argtypes = [vp, dp, C.c_int32]
         L.scicone_region_mark.argtypes = [vp, C.c_int32]
         L.scicone_region_elapsed_ms.argtypes = [vp, dp]
@@ -183,6 +184,12 @@ class Dataset:
         """(sum of proposal-kernel device time in us, number of timed launches) since the last reset."""
         us, n = C.c_double(), C.c_uint64()
         _check(lib().scicone_kernel_time_stats(self._h, C.byref(us), C.byref(n), int(reset)))
+        return us.value, n.value
+
+    def build_time_stats(self):
+        """(sum of build_rows_kernel device time in us, number of timed launches) since the last reset."""
+        us, n = C.c_double(), C.c_uint64()
+        _check(lib().scicone_build_time_stats(self._h, C.byref(us), C.byref(n)))
         return us.value, n.value
 
     def counters(self, reset=False):

@@ -6,17 +6,23 @@
 //   Dt        [K][Mp]   region-major copy of the count matrix D
 //   S         [Mp]      per-cell read total  sum_k D[j][k]   (k ascending, as std::accumulate)
 //   w         [Mp]      cluster sizes (int32, 0 in the padding)
-//   lgamma rows  [Mp]   L(k,cn)[j] = lgamma(D[j][k] + (nu*cn)*r_k), built lazily per (region, copy number, nu)
+//   delta rows   [Mp]   Delta(k,cn,cn_p)[j] = lgamma(D[j][k] + (nu*cn)*r_k) - lgamma(D[j][k] + (nu*cn_p)*r_k),
+//                       built once per (region, copy number pair, nu) by build_rows_kernel, then only gathered
 //   score rows   [Mp]   one row per tree node: attachment score of every cell to that node
 //   aggregates   [Mp]   per-cell log-sum-exp (or max) over the nodes, + argmax id in max mode
 //
-// One thread owns one cell for the whole proposal: it walks the rescored nodes
-// parent-before-child (Tree::compute_stack, reference scicone/src/Tree.h:260-286),
-// evaluates Tree::compute_score (Tree.h:163-244) as gathers from the lgamma rows,
-// then folds the new scores into the cell's aggregate exactly like
-// Inference::compute_t_prime_sums (scicone/src/Inference.h:1069-1196) /
-// MathOp::log_replace_sum (scicone/src/MathOp.cpp:307-361), and the CTA reduces
-// aggregate * cluster_size into a partial of the tree score (Inference.h:292-294).
+// Two kernels per batch of proposals:
+//   build_rows_kernel       (K1) every lgamma that is a pure function of the data: missing delta rows and, for
+//                           proposals that change nu, region slices of the root score.  One CTA row per item:
+//                           embarrassingly parallel, fp64-pipe bound.
+//   score_proposals_kernel  (K2-K4) per proposal (grid.y) and per 64-cell tile (grid.x): the increments
+//                           score(node) - score(parent) of all rescored nodes are evaluated by 4 task lanes per
+//                           cell into shared memory (Tree::compute_score, reference scicone/src/Tree.h:163-244, as
+//                           gathers + one large-argument lgamma), then one lane scans them parent-before-child
+//                           (Tree::compute_stack, Tree.h:260-286), folds the new scores into the cell's aggregate
+//                           exactly like Inference::compute_t_prime_sums (scicone/src/Inference.h:1069-1196) /
+//                           MathOp::log_replace_sum (scicone/src/MathOp.cpp:307-361), and the CTA reduces
+//                           aggregate * cluster_size into a partial of the tree score (Inference.h:292-294).
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -24,42 +30,44 @@
 
 namespace scicone {
 
-constexpr int kBlock = 128;         // cells per CTA (one thread per cell)
-constexpr int kSlots = 16;          // per-cell values of rescored ancestors kept in shared memory
-constexpr int kCtasPerChunk = 8;    // 8 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
+constexpr int kCells = 64;          // cells per CTA of the proposal kernel
+constexpr int kLanes = 4;           // task lanes per cell
+constexpr int kThreads = kCells * kLanes;
+constexpr int kTaskChunk = 32;      // tasks staged in shared memory at a time
+constexpr int kCtasPerChunk = 16;   // 16 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
+constexpr int kBuildBlock = 256;    // cells per CTA of the build kernel
+constexpr int kPad = 256;           // row padding (cells)
 
 enum : unsigned {
     TASK_ROOT = 1u,      // tree root: score 0 (Tree::compute_root_score, Tree.h:145-160)
-    TASK_REUSE_G = 2u,   // lgamma(S + nu*z_parent) equals the value the parent task kept in its slot
-    EV_BUILD_N = 1u,     // the node-side lgamma row does not exist yet: compute and store it
-    EV_BUILD_P = 2u,     // same for the parent-side row
+    TASK_REUSE_G = 2u,   // lgamma(S + nu*z_parent) equals the parent task's lgamma(S + nu*z) in this chunk
+    TASK_SKIP_AGG = 4u,  // a later task rewrites the same node: only that one enters the aggregate
     PROP_MAX = 1u,       // max scoring (Inference::max_scoring)
     PROP_OD = 2u,        // overdispersed likelihood (globals is_overdispersed)
     PROP_FULL = 4u,      // full table pass (Inference::compute_t_table): no committed state is read
     PROP_SCRATCH = 8u,   // to_add.size() >= unchanged_vals.size(): recompute the log-sum from scratch
-    PROP_WITH_OD = 16u   // the proposal changes nu: also evaluate the root ("overdispersed") score at the new nu
+    PROP_WITH_OD = 16u,  // also evaluate the root ("overdispersed") score from its region slices
+    PROP_OD_ONLY = 32u,  // no tasks, no aggregate: only the root score
+    BUILD_DELTA = 0u,
+    BUILD_OD_SLICE = 1u,
+    BUILD_OD_SLICE_LOG = 2u  // non-overdispersed root score slice: sum_k D_k log r_k
 };
 
 struct alignas(16) DevTask {
     double* dst;               // score row being written
-    const double* parent_row;  // committed score row of the parent (subtree roots only)
+    const double* parent_row;  // where the parent's score lives in global memory (committed row, or the primed row)
     double lg_nz, lg_nzp;      // OD: lgamma(nu*z), lgamma(nu*z_parent);  non-OD: log(z), log(z_parent)
     double nz, nzp;            // OD: nu*z, nu*z_parent
     int ev_begin, ev_end;
     int node_id;
-    short parent_slot, own_slot;  // shared-memory slots (-1: none)
-    unsigned flags;
-    int pad;
+    short parent_task;         // task index of the parent inside this proposal, -1: the parent is not rescored before
+    unsigned short flags;
 };
 
 struct alignas(16) DevEvent {
-    double* rowN;        // L(k, cn_node)
-    double* rowP;        // L(k, cn_parent)
-    const double* drow;  // Dt[k]
-    double cN, cP;       // OD: lgamma((nu*cn)*r) node / parent;  non-OD: cN = log(cn_node) - log(cn_parent)
-    double argN, argP;   // (nu*cn)*r_k
-    unsigned flags;
-    int pad;
+    const double* row;  // OD: delta row;  non-OD: Dt[k]
+    double a, b;        // OD: lgamma((nu*cn)*r) of node / parent;  non-OD: a = log(cn_node) - log(cn_parent)
+    double pad;
 };
 
 struct alignas(16) DevUnch {
@@ -72,7 +80,7 @@ struct alignas(16) DevHeader {
     int n_tasks, n_old, n_unch, deleted_id;
     unsigned flags;
     int n_cells;  // M of this shard
-    int n_add;    // distinct rescored node ids (== entries of addorder)
+    int n_od_slices;
     int pad1;
     const double* S;
     const int* w;
@@ -85,26 +93,38 @@ struct alignas(16) DevHeader {
     double* total;        // [2]
     unsigned* counter;    // arrival counter for the last-CTA reduction
     unsigned* status;     // bit 0: NaN aggregate
-    unsigned off_tasks, off_events, off_addorder, off_old, off_unch;
-    unsigned off_od;      // DevOdHeader of the root-score part (PROP_WITH_OD)
+    double od_lg_nz, od_nz;  // OD: lgamma(nu*z_root), nu*z_root;  non-OD: od_lg_nz = log(sum_r)
+    unsigned off_tasks, off_events, off_old, off_unch, off_od_rows, pad2;
 };
 
-struct alignas(16) DevOdHeader {
-    int n_regions, n_cells;
-    unsigned flags;
-    int pad0;
-    const double* S;
-    const int* w;
-    const double* Dt;
+struct alignas(16) DevBuild {
+    double* dst;
+    const double* src;     // BUILD_DELTA: Dt[k];  slices: Dt
+    double c1, c2;         // BUILD_DELTA: (nu*cn)*r, (nu*cn_parent)*r
+    unsigned kind;
+    int k0, k1;            // slices: region range
+    unsigned off_arg;      // slices: arena offsets of arg[K], cc[K]
+    unsigned off_c;
+    int n_cells;
     long long row_stride;  // Mp
-    double* cell_out;      // per-cell root score or nullptr
-    double* partial;
-    double* chunk_sums;
-    double* total;
-    unsigned* counter;
-    double lg_nz, nz;      // OD: lgamma(nu*z_root), nu*z_root;  non-OD: lg_nz = log(sum_r)
-    unsigned off_rows, off_arg, off_c, off_build;
 };
+
+// lgamma for positive arguments.  From 16 up the Stirling series with one fused multiply-add reproduces glibc's
+// lgamma to <= 1 ulp (identical from ~1e5 up, checked on the host against 2M samples per decade); below 16 the CUDA
+// library routine is used.  The large branch is what the z-terms lgamma(S + nu*z) always take.
+__device__ __forceinline__ double lgam(double x) {
+    if (x >= 16.0) {
+        const double lx = log(x);
+        const double r = 1.0 / x, r2 = r * r;
+        double p = __fma_rn(r2, 1.0 / 1188.0, -1.0 / 1680.0);
+        p = __fma_rn(r2, p, 1.0 / 1260.0);
+        p = __fma_rn(r2, p, -1.0 / 360.0);
+        p = __fma_rn(r2, p, 1.0 / 12.0);
+        const double t = __fma_rn(x - 0.5, lx, -x);
+        return t + __fma_rn(p, r, 0.91893853320467274178);
+    }
+    return lgamma(x);
+}
 
 __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
     // fixed-shape reduction: xor-shuffle tree inside each warp, warps added in order
@@ -115,7 +135,7 @@ __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
     __syncthreads();
     double s = 0.0;
     if (threadIdx.x == 0)
-        for (int i = 0; i < kBlock / 32; ++i) s += warp_buf[i];
+        for (int i = 0; i < kCells / 32; ++i) s += warp_buf[i];  // only the cell-owning warps contribute
     return s;  // valid in thread 0
 }
 
@@ -142,7 +162,7 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
         const double* part = partial + (size_t)v * n_cta;
         double* chunks = chunk_sums + (size_t)v * n_chunks;
         double grand = 0.0;
-        for (int base = 0; base < n_chunks; base += kBlock) {
+        for (int base = 0; base < n_chunks; base += kThreads) {
             int c = base + threadIdx.x;
             double cs = 0.0;
             if (c < n_chunks) {
@@ -154,7 +174,7 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
             smem_chunks[threadIdx.x] = cs;
             __syncthreads();
             if (threadIdx.x == 0) {
-                const int lim = min(kBlock, n_chunks - base);
+                const int lim = min(kThreads, n_chunks - base);
                 for (int i = 0; i < lim; ++i) grand += smem_chunks[i];
             }
             __syncthreads();
@@ -164,146 +184,142 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
     if (threadIdx.x == 0) *counter = 0u;
 }
 
-// Tree::get_od_root_score, Tree.h:1774-1810, for one cell (also materialises the neutral-state lgamma rows it
-// computes anyway).
-__device__ __forceinline__ double od_root_cell(const DevOdHeader& H, const unsigned char* blob, int j) {
-    double* const* rows = reinterpret_cast<double* const*>(blob + H.off_rows);
-    const double* arg = reinterpret_cast<const double*>(blob + H.off_arg);
-    const double* cc = reinterpret_cast<const double*>(blob + H.off_c);
-    const unsigned char* build = blob + H.off_build;
-    const double S = H.S[j];
-    const int K = H.n_regions;
-    double od = 0.0;
-    if (H.flags & PROP_OD) {
-        od += H.lg_nz;
-        od -= lgamma(S + H.nz);
-        for (int k = 0; k < K; ++k) {
-            double v;
-            if (build[k]) {
-                v = lgamma(H.Dt[(long long)k * H.row_stride + j] + arg[k]);
-                if (rows[k]) rows[k][j] = v;
-            } else
-                v = rows[k][j];
-            od += v;
-            od -= cc[k];
-        }
-    } else {
-        const double term1 = -S * H.lg_nz;
-        double term2 = 0.0;
-        for (int k = 0; k < K; ++k) term2 += H.Dt[(long long)k * H.row_stride + j] * arg[k];
-        od += term1 + term2;
+// ---------------------------------------------------------------------------------
+// K1: data-only lgamma work.  grid = (ceil(M / kBuildBlock), n_items).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items) {
+    const DevBuild it = reinterpret_cast<const DevBuild*>(arena + off_items)[blockIdx.y];
+    const int j = blockIdx.x * kBuildBlock + threadIdx.x;
+    if (j >= it.n_cells) return;
+    if (it.kind == BUILD_DELTA) {
+        const double d = __ldg(it.src + j);
+        it.dst[j] = lgam(d + it.c1) - lgam(d + it.c2);
+        return;
     }
-    return od;
+    const double* arg = reinterpret_cast<const double*>(arena + it.off_arg);
+    const double* cc = reinterpret_cast<const double*>(arena + it.off_c);
+    double acc = 0.0;
+    if (it.kind == BUILD_OD_SLICE) {  // Tree::get_od_root_score, Tree.h:1792-1797
+        for (int k = it.k0; k < it.k1; ++k) {
+            acc += lgam(__ldg(it.src + (long long)k * it.row_stride + j) + arg[k]);
+            acc -= cc[k];
+        }
+    } else {  // Tree.h:1803-1805
+        for (int k = it.k0; k < it.k1; ++k) acc += __ldg(it.src + (long long)k * it.row_stride + j) * arg[k];
+    }
+    it.dst[j] = acc;
 }
 
 // ---------------------------------------------------------------------------------
-// Proposal kernel: grid = (ceil(M / kBlock), n_proposals).
+// K2-K4: grid = (ceil(M / kCells), n_proposals).  The arena starts with one 32-bit blob offset per proposal.
+// Thread t owns cell (t % kCells) of the tile and task lane (t / kCells).
 // ---------------------------------------------------------------------------------
-// The arena starts with one 32-bit blob offset per proposal.
-__global__ void __launch_bounds__(kBlock) score_proposals_kernel(const unsigned char* __restrict__ arena) {
-    const unsigned* blob_off = reinterpret_cast<const unsigned*>(arena);
-    __shared__ double slot_sc[kSlots][kBlock];
-    __shared__ double slot_g[kSlots][kBlock];
-    __shared__ double red_buf[kBlock];
+__global__ void __launch_bounds__(kThreads) score_proposals_kernel(const unsigned char* __restrict__ arena) {
+    __shared__ double sm_g[kTaskChunk][kCells];    // lgamma(S + nu*z) of the staged tasks
+    __shared__ double sm_sc[kTaskChunk][kCells];   // increments, then scores
+    __shared__ double red_buf[kThreads];
 
+    const unsigned* blob_off = reinterpret_cast<const unsigned*>(arena);
     const unsigned char* blob = arena + blob_off[blockIdx.y];
     const DevHeader& H = *reinterpret_cast<const DevHeader*>(blob);
     const DevTask* tasks = reinterpret_cast<const DevTask*>(blob + H.off_tasks);
     const DevEvent* events = reinterpret_cast<const DevEvent*>(blob + H.off_events);
-    const int* addorder = reinterpret_cast<const int*>(blob + H.off_addorder);
     const double* const* old_rows = reinterpret_cast<const double* const*>(blob + H.off_old);
     const DevUnch* unch = reinterpret_cast<const DevUnch*>(blob + H.off_unch);
 
-    const int tid = threadIdx.x;
-    const int j = blockIdx.x * kBlock + tid;
+    const int cell = threadIdx.x % kCells;
+    const int lane = threadIdx.x / kCells;
+    const int j = blockIdx.x * kCells + cell;
     const bool live = j < H.n_cells;
     const unsigned pflags = H.flags;
     const bool od = pflags & PROP_OD;
+    const bool owner = live && lane == 0;
+    const int n_tasks = H.n_tasks;
+    const double S = live ? __ldg(H.S + j) : 1.0;
+
+    // running aggregate over the rescored nodes (owner threads)
+    double new_max = -DBL_MAX;  // max over the new values (both modes)
+    int new_id = 0;             // its node id (lowest id among equals = first in ascending-id order)
+    double new_sumexp = 0.0;    // sum mode: sum_i exp(v_i - new_max)
+    bool prev_in_new = (pflags & PROP_FULL) != 0;
+    const int pm = (owner && (pflags & PROP_MAX) && !(pflags & PROP_FULL)) ? H.maxid_old[j] : -1;
+
+    for (int c0 = 0; c0 < n_tasks; c0 += kTaskChunk) {
+        const int c1 = min(c0 + kTaskChunk, n_tasks);
+        // ---- A1: z-terms of the staged tasks
+        if (od && live)
+            for (int t = c0 + lane; t < c1; t += kLanes) sm_g[t - c0][cell] = lgam(S + tasks[t].nz);
+        __syncthreads();
+        // ---- A2: increments  score(node) - score(parent)   (Tree::compute_score, Tree.h:177-238)
+        if (live)
+            for (int t = c0 + lane; t < c1; t += kLanes) {
+                const DevTask& tk = tasks[t];
+                double x = 0.0;
+                if (!(tk.flags & TASK_ROOT)) {
+                    const int e0 = tk.ev_begin, e1 = tk.ev_end;
+                    if (od) {
+                        for (int e = e0; e < e1; ++e) {
+                            const DevEvent& ev = events[e];
+                            x += __ldg(ev.row + j);
+                            x -= ev.a;
+                            x += ev.b;
+                        }
+                        x += tk.lg_nz;
+                        x -= tk.lg_nzp;
+                        x -= sm_g[t - c0][cell];
+                        const int pt = tk.parent_task;
+                        x += ((tk.flags & TASK_REUSE_G) && pt >= c0) ? sm_g[pt - c0][cell] : lgam(S + tk.nzp);
+                    } else {
+                        for (int e = e0; e < e1; ++e) {
+                            const DevEvent& ev = events[e];
+                            x += __ldg(ev.row + j) * ev.a;
+                        }
+                        x -= S * tk.lg_nz;
+                        x += S * tk.lg_nzp;
+                    }
+                }
+                sm_sc[t - c0][cell] = x;
+            }
+        __syncthreads();
+        // ---- B: scan parent-before-child (Tree::compute_stack, Tree.h:260-286) and fold into the aggregate
+        if (owner)
+            for (int t = c0; t < c1; ++t) {
+                const DevTask& tk = tasks[t];
+                double sc;
+                if (tk.flags & TASK_ROOT)
+                    sc = 0.0;
+                else {
+                    const int pt = tk.parent_task;
+                    const double ps = (pt >= c0) ? sm_sc[pt - c0][cell] : tk.parent_row[j];
+                    sc = ps + sm_sc[t - c0][cell];
+                }
+                sm_sc[t - c0][cell] = sc;
+                tk.dst[j] = sc;
+                if (tk.flags & TASK_SKIP_AGG) continue;
+                const int id = tk.node_id;
+                if (id == pm) prev_in_new = true;
+                if (pflags & PROP_MAX) {
+                    if (sc > new_max || (sc == new_max && id < new_id)) {
+                        new_max = sc;
+                        new_id = id;
+                    }
+                } else {  // online log-sum-exp of the new values
+                    if (sc > new_max) {
+                        new_sumexp = new_sumexp * exp(new_max - sc) + 1.0;
+                        new_max = sc;
+                    } else
+                        new_sumexp += exp(sc - new_max);
+                }
+            }
+        __syncthreads();
+    }
+
     double contrib = 0.0, contrib_od = 0.0;
-
-    if (live) {
-        const double S = H.S[j];
-        // ---- node scores: Tree::compute_stack / compute_score over the rescored subtree(s) ----
-        const int n_tasks = H.n_tasks;
-        for (int t = 0; t < n_tasks; ++t) {
-            const DevTask tk = tasks[t];
-            double ll;
-            if (tk.flags & TASK_ROOT) {
-                ll = 0.0;
-                if (tk.own_slot >= 0) {
-                    slot_sc[tk.own_slot][tid] = 0.0;
-                    if (od) slot_g[tk.own_slot][tid] = lgamma(S + tk.nz);
-                }
-                tk.dst[j] = 0.0;
-                continue;
-            }
-            double g_parent = 0.0;
-            bool have_gp = false;
-            if (tk.parent_row != nullptr)
-                ll = tk.parent_row[j];
-            else {
-                ll = slot_sc[tk.parent_slot][tid];
-                if (tk.flags & TASK_REUSE_G) {
-                    g_parent = slot_g[tk.parent_slot][tid];
-                    have_gp = true;
-                }
-            }
-            if (od) {
-                for (int e = tk.ev_begin; e < tk.ev_end; ++e) {
-                    const DevEvent ev = events[e];
-                    double vn, vp;
-                    if (ev.flags & EV_BUILD_N) {
-                        vn = lgamma(ev.drow[j] + ev.argN);
-                        ev.rowN[j] = vn;
-                    } else
-                        vn = ev.rowN[j];
-                    if (ev.flags & EV_BUILD_P) {
-                        vp = lgamma(ev.drow[j] + ev.argP);
-                        ev.rowP[j] = vp;
-                    } else
-                        vp = ev.rowP[j];
-                    ll += vn;
-                    ll -= vp;
-                    ll -= ev.cN;
-                    ll += ev.cP;
-                }
-                ll += tk.lg_nz;
-                ll -= tk.lg_nzp;
-                const double g = lgamma(S + tk.nz);
-                ll -= g;
-                if (!have_gp) g_parent = lgamma(S + tk.nzp);
-                ll += g_parent;
-                if (tk.own_slot >= 0) slot_g[tk.own_slot][tid] = g;
-            } else {
-                for (int e = tk.ev_begin; e < tk.ev_end; ++e) {
-                    const DevEvent ev = events[e];
-                    ll += ev.drow[j] * ev.cN;
-                }
-                ll -= S * tk.lg_nz;
-                ll += S * tk.lg_nzp;
-            }
-            tk.dst[j] = ll;
-            if (tk.own_slot >= 0) slot_sc[tk.own_slot][tid] = ll;
-        }
-
+    if (owner && !(pflags & PROP_OD_ONLY)) {
         // ---- per-cell aggregate: Inference::compute_t_prime_sums ----
         const int n_unch = H.n_unch;
-        const int n_add = H.n_add;
         double res;
-        if (pflags & PROP_MAX) {
-            double newbest = -DBL_MAX;
-            int newid = 0;
-            bool prev_in_new = (pflags & PROP_FULL) != 0;
-            const int pm = (pflags & PROP_FULL) ? -1 : H.maxid_old[j];
-            for (int a = 0; a < n_add; ++a) {
-                const DevTask& tk = tasks[addorder[a]];
-                const double v = tk.dst[j];
-                if (tk.node_id == pm) prev_in_new = true;
-                if (v > newbest) {
-                    newbest = v;
-                    newid = tk.node_id;
-                }
-            }
+        if (pflags & PROP_MAX) {  // Inference.h:1086-1152
             int prev_id = pm;
             double prev_val = (pflags & PROP_FULL) ? 0.0 : H.sums_old[j];
             if (prev_in_new || pm == H.deleted_id) {
@@ -321,17 +337,17 @@ __global__ void __launch_bounds__(kBlock) score_proposals_kernel(const unsigned 
                 prev_id = uid;
                 prev_val = uval;
             }
-            res = newbest;
-            int rid = newid;
-            if (prev_val > newbest) {
+            res = new_max;
+            int rid = new_id;
+            if (prev_val > new_max) {
                 res = prev_val;
                 rid = prev_id;
             }
             H.maxid_new[j] = rid;
-        } else {
+        } else {  // MathOp::log_replace_sum, MathOp.cpp:307-361
             bool scratch = (pflags & (PROP_SCRATCH | PROP_FULL)) != 0;
             double sub = 0.0;
-            if (!scratch) {  // MathOp::log_replace_sum, incremental branch
+            if (!scratch) {  // incremental branch: take the old values out of the old sum
                 const double sum_old = H.sums_old[j];
                 const int n_old = H.n_old;
                 double mx = sum_old;
@@ -347,11 +363,7 @@ __global__ void __launch_bounds__(kBlock) score_proposals_kernel(const unsigned 
                 else
                     sub = log(s) + mx;
             }
-            double mx = -DBL_MAX;
-            for (int a = 0; a < n_add; ++a) {
-                const double v = tasks[addorder[a]].dst[j];
-                if (v > mx) mx = v;
-            }
+            double mx = new_max;
             if (scratch) {
                 for (int u = 0; u < n_unch; ++u) {
                     const double v = unch[u].row[j];
@@ -359,8 +371,7 @@ __global__ void __launch_bounds__(kBlock) score_proposals_kernel(const unsigned 
                 }
             } else if (sub > mx)
                 mx = sub;
-            double s = 0.0;
-            for (int a = 0; a < n_add; ++a) s += exp(tasks[addorder[a]].dst[j] - mx);
+            double s = new_sumexp * exp(new_max - mx);
             if (scratch) {
                 for (int u = 0; u < n_unch; ++u) s += exp(unch[u].row[j] - mx);
             } else
@@ -370,8 +381,19 @@ __global__ void __launch_bounds__(kBlock) score_proposals_kernel(const unsigned 
         if (res != res) atomicOr(H.status, 1u);
         H.sums_new[j] = res;
         contrib = res * (double)H.w[j];
-        if (pflags & PROP_WITH_OD)  // Inference::compute_t_prime_od_scores, Inference.h:1421-1433
-            contrib_od = od_root_cell(*reinterpret_cast<const DevOdHeader*>(blob + H.off_od), blob + H.off_od, j) * (double)H.w[j];
+    }
+    if (owner && (pflags & PROP_WITH_OD)) {
+        // Tree::get_od_root_score (Tree.h:1774-1810) from the region slices K1 prepared;
+        // Inference::compute_t_prime_od_scores, Inference.h:1421-1433
+        const double* const* slices = reinterpret_cast<const double* const*>(blob + H.off_od_rows);
+        double v = 0.0;
+        if (od) {
+            v += H.od_lg_nz;
+            v -= lgam(S + H.od_nz);
+        } else
+            v += -S * H.od_lg_nz;
+        for (int s = 0; s < H.n_od_slices; ++s) v += slices[s][j];
+        contrib_od = v * (double)H.w[j];
     }
     // ---- weighted sum over cells: Inference::comparison, Inference.h:292-294 ----
     __syncthreads();
@@ -383,30 +405,6 @@ __global__ void __launch_bounds__(kBlock) score_proposals_kernel(const unsigned 
         __syncthreads();
     }
     finish_reduction(cta_sum, cta_od, H.partial, H.chunk_sums, H.total, H.counter, red_buf);
-}
-
-// ---------------------------------------------------------------------------------
-// Root ("overdispersed root") score: Tree::get_od_root_score, Tree.h:1774-1810, and the
-// weighted sum of Inference::compute_t_od_scores, Inference.h:1406-1419.
-// Also materialises the neutral-state lgamma rows L(k, neutral_k) it computes anyway.
-// grid = (ceil(M / kBlock), n_requests).
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) od_root_kernel(const unsigned char* __restrict__ arena) {
-    const unsigned* blob_off = reinterpret_cast<const unsigned*>(arena);
-    __shared__ double red_buf[kBlock];
-    const unsigned char* blob = arena + blob_off[blockIdx.y];
-    const DevOdHeader& H = *reinterpret_cast<const DevOdHeader*>(blob);
-    const int j = blockIdx.x * kBlock + threadIdx.x;
-    double contrib = 0.0;
-    if (j < H.n_cells) {
-        const double od = od_root_cell(H, blob, j);
-        if (H.cell_out) H.cell_out[j] = od;
-        contrib = od * (double)H.w[j];
-    }
-    __syncthreads();
-    const double cta_sum = block_sum(contrib, red_buf);
-    __syncthreads();
-    finish_reduction(0.0, cta_sum, H.partial, H.chunk_sums, H.total, H.counter, red_buf);
 }
 
 // Multi-GPU: copy the per-chunk sums of each proposal into the fixed-width, zero-padded send buffer of

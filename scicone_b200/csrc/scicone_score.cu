@@ -172,8 +172,11 @@ int validate_tree(const scicone_tree* t, int K) {
     return SCICONE_OK;
 }
 
-typedef std::unordered_map<uint64_t, double*> LCache;  // (region, copy number) -> lgamma row
-inline uint64_t lkey(int k, int cn) { return (uint64_t(uint32_t(k)) << 32) | uint32_t(cn); }
+// (region, copy number of the node, copy number of the parent) -> delta row at one nu
+typedef std::unordered_map<uint64_t, double*> LCache;
+inline uint64_t lkey(int k, int cn, int cp) {
+    return (uint64_t(uint32_t(k)) << 32) | (uint64_t(uint16_t(cn)) << 16) | uint64_t(uint16_t(cp));
+}
 
 }  // namespace
 
@@ -202,8 +205,8 @@ struct scicone_dataset {
         double* h_total = nullptr;     // pinned [slots][2]
         unsigned* h_status = nullptr;  // pinned [slots]
         double* h_gather = nullptr;    // pinned [world][slots][2][max_chunks_rank]
-        cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
-        int n = 0;
+        cudaEvent_t evb = nullptr, ev0 = nullptr, ev1 = nullptr, done = nullptr;
+        int n = 0, n_items = 0;
         std::vector<char> with_od;
         bool busy = false;
         unsigned long long ticket = 0;
@@ -230,8 +233,8 @@ struct scicone_dataset {
     size_t gather_cap = 0;
     // profiling
     bool profiling = false;
-    double last_kernel_us = 0.0, sum_kernel_us = 0.0;
-    unsigned long long n_timed = 0;
+    double last_kernel_us = 0.0, sum_kernel_us = 0.0, sum_build_us = 0.0;
+    unsigned long long n_timed = 0, n_build_timed = 0;
     unsigned long long n_launches = 0;
     // bookkeeping for the bench: bytes staged per direction, algorithmic bytes / scores of the launched proposals
     unsigned long long h2d_bytes = 0, d2h_bytes = 0;
@@ -330,8 +333,12 @@ struct scicone_chain {
     std::map<int, NodeRow> p;  // rescored node id -> primed row
     int deleted_id = -1;
     bool p_full = false;
-    // blob under construction
+    // blob under construction, the data-only lgamma work it needs first (K1 items + their per-region arrays),
+    // and rows that only live for this launch (root-score slices)
     std::vector<unsigned char> blob;
+    std::vector<DevBuild> builds;
+    std::vector<double> build_aux;
+    std::vector<double*> temp_rows;
     double alg_bytes = 0.0, n_scores = 0.0;
 };
 
@@ -364,6 +371,8 @@ void drop_pending(scicone_chain* ch) {
     ch->evaluated = false;
     ch->deleted_id = -1;
     ch->p_full = false;
+    for (double* r : ch->temp_rows) ch->ds->pool.put(r);
+    ch->temp_rows.clear();
     ch->od_p_valid = false;
     ch->with_od = false;
     release_cache(ch->ds, ch->Lp);
@@ -378,64 +387,80 @@ size_t blob_append(std::vector<unsigned char>& b, const std::vector<T>& v) {
     return off;
 }
 
-// Root-score request (Tree::get_od_root_score, Tree.h:1774-1810) as a self-contained block: header + per-region arrays.
-int build_od_block(scicone_chain* ch, double nu, int slot, std::vector<unsigned char>& b) {
+constexpr int kOdSlices = 8;
+
+// Root-score request (Tree::get_od_root_score, Tree.h:1774-1810): K1 items that reduce slices of the regions
+// into temporary rows; the proposal kernel adds the slices and the two cell-level terms.
+int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const double*>& slice_rows) {
     scicone_dataset* ds = ch->ds;
     const int K = ds->K;
-    std::vector<double*> rows(K, nullptr);
-    std::vector<double> arg(K), cc(K);
-    std::vector<unsigned char> build(round_up(K, 16), 0);
-    DevOdHeader H;
-    memset(&H, 0, sizeof H);
-    H.n_regions = K;
+    const size_t aux0 = ch->build_aux.size();
+    ch->build_aux.resize(aux0 + 2 * (size_t)K);
+    double* arg = ch->build_aux.data() + aux0;
+    double* cc = arg + K;
+    if (ds->od) {  // Tree.h:1783-1797 (no eta substitution here, quirk Q2)
+        H.od_nz = nu * ds->root_z;
+        H.od_lg_nz = lgamma(H.od_nz);
+        for (int k = 0; k < K; ++k) {
+            arg[k] = nu * ds->neutral[k] * ds->r[k];
+            cc[k] = lgamma(arg[k]);
+        }
+    } else {  // Tree.h:1799-1806
+        H.od_lg_nz = log((double)ds->sum_r);
+        for (int k = 0; k < K; ++k) {
+            arg[k] = log((double)ds->r[k]);
+            cc[k] = 0.0;
+        }
+    }
+    const int n_slices = std::min(kOdSlices, K);
+    for (int s = 0; s < n_slices; ++s) {
+        double* row = nullptr;
+        CUDA_TRY(ds->pool.get(&row));
+        ch->temp_rows.push_back(row);
+        slice_rows.push_back(row);
+        DevBuild it;
+        memset(&it, 0, sizeof it);
+        it.dst = row;
+        it.src = ds->dDt;
+        it.kind = ds->od ? BUILD_OD_SLICE : BUILD_OD_SLICE_LOG;
+        it.k0 = (int)((long long)K * s / n_slices);
+        it.k1 = (int)((long long)K * (s + 1) / n_slices);
+        it.off_arg = (unsigned)(aux0 * sizeof(double));        // relative to the chain's aux block; rebased at submit
+        it.off_c = (unsigned)((aux0 + K) * sizeof(double));
+        it.n_cells = ds->M;
+        it.row_stride = (long long)ds->Mp;
+        ch->builds.push_back(it);
+    }
+    H.n_od_slices = n_slices;
+    H.flags |= PROP_WITH_OD;
+    return SCICONE_OK;
+}
+
+void fill_header_common(scicone_chain* ch, int slot, DevHeader& H) {
+    scicone_dataset* ds = ch->ds;
     H.n_cells = ds->M;
-    H.flags = ds->od ? PROP_OD : 0u;
     H.S = ds->dS;
     H.w = ds->dW;
-    H.Dt = ds->dDt;
-    H.row_stride = (long long)ds->Mp;
+    H.sums_old = ch->sums[0];
+    H.sums_new = ch->sums[1];
+    H.maxid_old = ch->maxid[0];
+    H.maxid_new = ch->maxid[1];
     H.partial = ds->d_partial + (size_t)slot * 2 * ds->n_cta;
     H.chunk_sums = ds->d_chunk + (size_t)slot * 2 * ds->n_chunks;
     H.total = ds->d_total + (size_t)slot * 2;
     H.counter = ds->d_counter + slot;
-    if (ds->od) {  // Tree.h:1783-1797 (no eta substitution here, quirk Q2)
-        LCache* L = cache_for(ch, nu);
-        H.nz = nu * ds->root_z;
-        H.lg_nz = lgamma(H.nz);
-        for (int k = 0; k < K; ++k) {
-            arg[k] = nu * ds->neutral[k] * ds->r[k];
-            cc[k] = lgamma(arg[k]);
-            if (ds->neutral[k] != 0) {  // L(k, 0) means eta in compute_score: do not alias it
-                double** slotp = &(*L)[lkey(k, ds->neutral[k])];
-                if (!*slotp) {
-                    CUDA_TRY(ds->pool.get(slotp));
-                    build[k] = 1;
-                }
-                rows[k] = *slotp;
-            } else
-                build[k] = 1;
-        }
-    } else {  // Tree.h:1799-1806
-        H.lg_nz = log((double)ds->sum_r);
-        for (int k = 0; k < K; ++k) arg[k] = log((double)ds->r[k]);
-    }
-    b.assign(sizeof H, 0);
-    H.off_rows = (unsigned)blob_append(b, rows);
-    H.off_arg = (unsigned)blob_append(b, arg);
-    H.off_c = (unsigned)blob_append(b, cc);
-    H.off_build = (unsigned)blob_append(b, build);
-    b.resize(round_up(b.size(), 16));
-    memcpy(b.data(), &H, sizeof H);
-    return SCICONE_OK;
+    H.status = ds->d_status + slot;
 }
 
-// Compile the queued proposal of `ch` into ch->blob.  `slot` selects the reduction scratch.
+// Compile the queued proposal of `ch` into ch->blob (+ ch->builds).  `slot` selects the reduction scratch.
 int compile_proposal(scicone_chain* ch, int slot, bool full) {
     scicone_dataset* ds = ch->ds;
     const TreeCopy& T = ch->tp;
     const double nu = T.nu;
     const bool od = ds->od;
     LCache* L = od ? cache_for(ch, nu) : nullptr;
+    ch->builds.clear();
+    ch->build_aux.clear();
 
     std::vector<int> child_off(T.n + 1, 0), child(T.n > 1 ? T.n - 1 : 0);
     for (int i = 1; i < T.n; ++i) child_off[T.parent[i] + 1]++;
@@ -448,29 +473,20 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     std::vector<DevTask> tasks;
     std::vector<DevEvent> events;
     std::vector<int> task_of_node(T.n, -1);
-    std::vector<short> free_slots;
-    for (short s = kSlots - 1; s >= 0; --s) free_slots.push_back(s);
-
-    struct Frame { int node; bool post; };
-    std::vector<Frame> stack;
+    std::vector<int> stack;
     for (size_t ri = 0; ri < ch->roots.size(); ++ri) {
         const int root = ch->roots[ri];
-        stack.push_back({root, false});
+        stack.push_back(root);
         while (!stack.empty()) {
-            Frame f = stack.back();
+            const int n = stack.back();
             stack.pop_back();
-            const int n = f.node;
-            if (f.post) {  // all descendants emitted: the shared-memory slot is free again
-                const short s = tasks[task_of_node[n]].own_slot;
-                if (s >= 0) free_slots.push_back(s);
-                continue;
-            }
             const int id = T.id[n];
             const int pidx = T.parent[n];
+            if (tasks.size() >= 32000) return fail(SCICONE_ERR_ARG, "more than 32000 rescored nodes in one proposal");
             DevTask tk;
             memset(&tk, 0, sizeof tk);
             tk.node_id = id;
-            tk.parent_slot = tk.own_slot = -1;
+            tk.parent_task = -1;
             tk.ev_begin = tk.ev_end = (int)events.size();
             int z_int;
             if (pidx < 0) {  // Tree::compute_root_score, Tree.h:145-160
@@ -480,9 +496,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             } else {
                 const int pid = T.id[pidx];
                 int pz;
-                const bool is_subtree_root = (n == root);
                 auto pit = ch->p.find(pid);
-                if (is_subtree_root) {
+                if (n == root) {
                     // Inference.h:1034: the parent's score is restored from the COMMITTED table;
                     // its Node::z is whatever the tree copy carries (primed if rescored before, else committed).
                     auto cit = ch->t.find(pid);
@@ -491,11 +506,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     tk.parent_row = cit->second.row;
                     pz = (pit != ch->p.end()) ? pit->second.z : cit->second.z;
                 } else {
-                    const DevTask& ptk = tasks[task_of_node[pidx]];
-                    if (ptk.own_slot >= 0)
-                        tk.parent_slot = ptk.own_slot;
-                    else
-                        tk.parent_row = ptk.dst;
+                    tk.parent_task = (short)task_of_node[pidx];
+                    tk.parent_row = tasks[task_of_node[pidx]].dst;
                     pz = pit->second.z;
                 }
                 // Tree::compute_score, Tree.h:177-198: z = parent.z + sum_k r_k (cn_node - cn_parent)
@@ -517,26 +529,30 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     const double parent_cn = cp_i == 0 ? ds->eta : (double)cp_i;
                     DevEvent ev;
                     memset(&ev, 0, sizeof ev);
-                    ev.drow = ds->dDt + (size_t)k * ds->Mp;
                     if (od) {  // Tree.h:214-218
-                        ev.argN = nu * node_cn * ds->r[k];
-                        ev.argP = nu * parent_cn * ds->r[k];
-                        ev.cN = lgamma(ev.argN);
-                        ev.cP = lgamma(ev.argP);
-                        double** slotN = &(*L)[lkey(k, cn_i)];
-                        if (!*slotN) {
-                            CUDA_TRY(ds->pool.get(slotN));
-                            ev.flags |= EV_BUILD_N;
+                        const double argN = nu * node_cn * ds->r[k];
+                        const double argP = nu * parent_cn * ds->r[k];
+                        ev.a = lgamma(argN);
+                        ev.b = lgamma(argP);
+                        double** slotp = &(*L)[lkey(k, cn_i, cp_i)];
+                        if (!*slotp) {  // first use of this (region, copy-number pair) at this nu: K1 builds the row
+                            CUDA_TRY(ds->pool.get(slotp));
+                            DevBuild it;
+                            memset(&it, 0, sizeof it);
+                            it.dst = *slotp;
+                            it.src = ds->dDt + (size_t)k * ds->Mp;
+                            it.c1 = argN;
+                            it.c2 = argP;
+                            it.kind = BUILD_DELTA;
+                            it.n_cells = ds->M;
+                            it.row_stride = (long long)ds->Mp;
+                            ch->builds.push_back(it);
                         }
-                        ev.rowN = *slotN;
-                        double** slotP = &(*L)[lkey(k, cp_i)];
-                        if (!*slotP) {
-                            CUDA_TRY(ds->pool.get(slotP));
-                            ev.flags |= EV_BUILD_P;
-                        }
-                        ev.rowP = *slotP;
-                    } else  // Tree.h:221
-                        ev.cN = log(node_cn) - log(parent_cn);
+                        ev.row = *slotp;
+                    } else {  // Tree.h:221
+                        ev.row = ds->dDt + (size_t)k * ds->Mp;
+                        ev.a = log(node_cn) - log(parent_cn);
+                    }
                     events.push_back(ev);
                 }
                 tk.ev_end = (int)events.size();
@@ -545,10 +561,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     tk.nzp = nu * zp;
                     tk.lg_nz = lgamma(tk.nz);
                     tk.lg_nzp = lgamma(tk.nzp);
-                    if (tk.parent_slot >= 0) {
-                        const DevTask& ptk = tasks[task_of_node[pidx]];
-                        if (memcmp(&ptk.nz, &tk.nzp, sizeof(double)) == 0) tk.flags |= TASK_REUSE_G;
-                    }
+                    if (tk.parent_task >= 0 && memcmp(&tasks[tk.parent_task].nz, &tk.nzp, sizeof(double)) == 0)
+                        tk.flags |= TASK_REUSE_G;
                 } else {  // Tree.h:236-237
                     tk.lg_nz = log(zd);
                     tk.lg_nzp = log(zp);
@@ -563,32 +577,25 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             } else
                 own->second.z = z_int;
             tk.dst = own->second.row;
-            const int nc = child_off[n + 1] - child_off[n];
-            if (nc > 0 && !free_slots.empty()) {
-                tk.own_slot = free_slots.back();
-                free_slots.pop_back();
-            }
             task_of_node[n] = (int)tasks.size();
             tasks.push_back(tk);
-            if (nc > 0) {
-                stack.push_back({n, true});
-                for (int c = child_off[n + 1] - 1; c >= child_off[n]; --c) stack.push_back({child[c], false});
-            }
+            for (int c = child_off[n + 1] - 1; c >= child_off[n]; --c) stack.push_back(child[c]);
         }
     }
 
     // aggregate bookkeeping: Inference::compute_t_prime_sums, Inference.h:1069-1196
-    std::map<int, int> by_id;  // rescored id -> last task writing it (std::map order = ascending id)
-    for (size_t i = 0; i < tasks.size(); ++i) by_id[tasks[i].node_id] = (int)i;
-    std::vector<int> addorder;
-    for (auto& kv : by_id) addorder.push_back(kv.second);
+    {   // a node written twice (overlapping subtree roots) enters the aggregate once, with its last value
+        std::map<int, int> last;
+        for (size_t i = 0; i < tasks.size(); ++i) last[tasks[i].node_id] = (int)i;
+        for (size_t i = 0; i < tasks.size(); ++i)
+            if (last[tasks[i].node_id] != (int)i) tasks[i].flags |= TASK_SKIP_AGG;
+    }
     std::vector<const double*> old_rows;
     std::vector<DevUnch> unch;
     ch->deleted_id = -1;
     if (!full) {
         // Inference::deleted_node_idx, Inference.h:1270-1289
         if ((size_t)T.n < ch->t.size()) {
-            std::vector<char> present;
             for (auto& kv : ch->t) {
                 bool found = false;
                 for (int i = 0; i < T.n && !found; ++i) found = (T.id[i] == kv.first);
@@ -613,61 +620,77 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     DevHeader H;
     memset(&H, 0, sizeof H);
     H.n_tasks = (int)tasks.size();
-    H.n_add = (int)addorder.size();
     H.n_old = (int)old_rows.size();
     H.n_unch = (int)unch.size();
     H.deleted_id = ch->deleted_id;
     H.flags = (ds->maxs ? PROP_MAX : 0u) | (od ? PROP_OD : 0u) | (full ? PROP_FULL : 0u);
-    if (!full && addorder.size() >= unch.size()) H.flags |= PROP_SCRATCH;  // MathOp.cpp:315
-    H.n_cells = ds->M;
-    H.S = ds->dS;
-    H.w = ds->dW;
-    H.sums_old = ch->sums[0];
-    H.sums_new = ch->sums[1];
-    H.maxid_old = ch->maxid[0];
-    H.maxid_new = ch->maxid[1];
-    H.partial = ds->d_partial + (size_t)slot * 2 * ds->n_cta;
-    H.chunk_sums = ds->d_chunk + (size_t)slot * 2 * ds->n_chunks;
-    H.total = ds->d_total + (size_t)slot * 2;
-    H.counter = ds->d_counter + slot;
-    H.status = ds->d_status + slot;
-
+    if (!full && ch->p.size() >= unch.size()) H.flags |= PROP_SCRATCH;  // MathOp.cpp:315
+    fill_header_common(ch, slot, H);
     {   // 16 + 8 E_n bytes per rescored cell x node score, 8 N + 12 per cell aggregate
-        const double n_table = full ? (double)addorder.size() : (double)(unch.size() + addorder.size());
+        const double n_table = full ? (double)ch->p.size() : (double)(unch.size() + ch->p.size());
         ch->alg_bytes = (double)ds->M * (16.0 * tasks.size() + 8.0 * events.size() + 8.0 * n_table + 12.0);
         ch->n_scores = (double)ds->M * tasks.size();
+    }
+    // a proposal that changes nu also needs Inference::compute_t_prime_od_scores (Inference.h:942): evaluated by
+    // the same launch unless the caller already asked for it separately
+    std::vector<const double*> slice_rows;
+    ch->with_od = !full && nu != ch->t_nu && !(ch->od_p_valid && ch->od_p_nu == nu);
+    if (ch->with_od) {
+        int rc = add_od_request(ch, nu, H, slice_rows);
+        if (rc) return rc;
+        ch->alg_bytes += (double)ds->M * 8.0 * ds->K;
     }
     std::vector<unsigned char>& b = ch->blob;
     b.clear();
     b.resize(sizeof(DevHeader));
     H.off_tasks = (unsigned)blob_append(b, tasks);
     H.off_events = (unsigned)blob_append(b, events);
-    H.off_addorder = (unsigned)blob_append(b, addorder);
     H.off_old = (unsigned)blob_append(b, old_rows);
     H.off_unch = (unsigned)blob_append(b, unch);
-    // a proposal that changes nu also needs Inference::compute_t_prime_od_scores (Inference.h:942): evaluated by
-    // the same launch unless the caller already asked for it separately
-    ch->with_od = !full && nu != ch->t_nu && !(ch->od_p_valid && ch->od_p_nu == nu);
-    if (ch->with_od) {
-        std::vector<unsigned char> odb;
-        int rc = build_od_block(ch, nu, slot, odb);
-        if (rc) return rc;
-        H.flags |= PROP_WITH_OD;
-        H.off_od = (unsigned)round_up(b.size(), 16);
-        b.resize(H.off_od);
-        b.insert(b.end(), odb.begin(), odb.end());
-        ch->alg_bytes += (double)ds->M * 8.0 * ds->K;
-    }
+    H.off_od_rows = (unsigned)blob_append(b, slice_rows);
     b.resize(round_up(b.size(), 16));
     memcpy(b.data(), &H, sizeof H);
     return SCICONE_OK;
 }
 
-// Queue the compiled blobs of `n` chains (all on one dataset) as ONE kernel launch; returns a ticket.
+// A blob that only evaluates the root score at `nu` (Inference::compute_t_od_scores, Inference.h:1406-1419).
+int compile_od_only(scicone_chain* ch, double nu, int slot) {
+    ch->builds.clear();
+    ch->build_aux.clear();
+    DevHeader H;
+    memset(&H, 0, sizeof H);
+    H.deleted_id = -1;
+    H.flags = (ch->ds->od ? PROP_OD : 0u) | PROP_OD_ONLY;
+    fill_header_common(ch, slot, H);
+    std::vector<const double*> slice_rows;
+    int rc = add_od_request(ch, nu, H, slice_rows);
+    if (rc) return rc;
+    std::vector<unsigned char>& b = ch->blob;
+    b.clear();
+    b.resize(sizeof(DevHeader));
+    H.off_tasks = H.off_events = H.off_old = H.off_unch = (unsigned)b.size();
+    H.off_od_rows = (unsigned)blob_append(b, slice_rows);
+    b.resize(round_up(b.size(), 16));
+    memcpy(b.data(), &H, sizeof H);
+    ch->alg_bytes = (double)ch->ds->M * 8.0 * ch->ds->K;
+    ch->n_scores = 0.0;
+    ch->with_od = true;
+    return SCICONE_OK;
+}
+
+// Queue the compiled blobs of `n` chains (all on one dataset): K1 for the data-only lgamma work they need
+// (if any), then ONE launch of the proposal kernel; returns a ticket.
 int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, unsigned long long* ticket) {
-    size_t head = round_up(sizeof(unsigned) * n, 16);
-    size_t bytes = head;
-    for (int i = 0; i < n; ++i) bytes += chains[i]->blob.size();
+    const size_t head = round_up(sizeof(unsigned) * n, 16);
+    size_t bytes = head, n_items = 0, aux_bytes = 0;
+    for (int i = 0; i < n; ++i) {
+        bytes += chains[i]->blob.size();
+        n_items += chains[i]->builds.size();
+        aux_bytes += round_up(chains[i]->build_aux.size() * sizeof(double), 16);
+    }
+    const size_t off_items = bytes;
+    const size_t off_aux = off_items + n_items * sizeof(DevBuild);
+    bytes = off_aux + aux_bytes;
     int rc = ds->ensure_arena(bytes);
     if (rc) return rc;
     const unsigned long long tk = ds->next_ticket;
@@ -675,15 +698,35 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
     g.with_od.assign(n, 0);
     unsigned* offs = reinterpret_cast<unsigned*>(g.h_arena);
-    size_t at = head;
+    size_t at = head, item_at = off_items, aux_at = off_aux;
     for (int i = 0; i < n; ++i) {
+        scicone_chain* ch = chains[i];
         offs[i] = (unsigned)at;
-        memcpy(g.h_arena + at, chains[i]->blob.data(), chains[i]->blob.size());
-        at += chains[i]->blob.size();
+        memcpy(g.h_arena + at, ch->blob.data(), ch->blob.size());
+        at += ch->blob.size();
+        if (!ch->build_aux.empty()) memcpy(g.h_arena + aux_at, ch->build_aux.data(), ch->build_aux.size() * sizeof(double));
+        for (const DevBuild& src : ch->builds) {
+            DevBuild it = src;
+            if (it.kind != BUILD_DELTA) {
+                it.off_arg += (unsigned)aux_at;
+                it.off_c += (unsigned)aux_at;
+            }
+            memcpy(g.h_arena + item_at, &it, sizeof it);
+            item_at += sizeof it;
+        }
+        aux_at += round_up(ch->build_aux.size() * sizeof(double), 16);
     }
     CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
+    if (n_items) {
+        if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, ds->stream));
+        build_rows_kernel<<<dim3((ds->M + kBuildBlock - 1) / kBuildBlock, (unsigned)n_items), kBuildBlock, 0, ds->stream>>>(
+            ds->d_arena, (unsigned)off_items);
+        CUDA_TRY(cudaGetLastError());
+        ds->n_launches++;
+    }
+    g.n_items = (int)n_items;
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, ds->stream));
-    score_proposals_kernel<<<dim3(ds->n_cta, n), kBlock, 0, ds->stream>>>(ds->d_arena);
+    score_proposals_kernel<<<dim3(ds->n_cta, n), kThreads, 0, ds->stream>>>(ds->d_arena);
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, ds->stream));
     CUDA_TRY(cudaGetLastError());
     ds->n_launches++;
@@ -704,10 +747,16 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     ds->h2d_bytes += bytes;
     ds->d2h_bytes += (ds->world > 1 ? sizeof(double) * 2 * n * ds->max_chunks_rank * ds->world : sizeof(double) * 2 * n) + sizeof(unsigned) * n;
     for (int i = 0; i < n; ++i) {
-        ds->alg_bytes += chains[i]->alg_bytes;
-        ds->n_scores += chains[i]->n_scores;
+        scicone_chain* ch = chains[i];
+        ds->alg_bytes += ch->alg_bytes;
+        ds->n_scores += ch->n_scores;
+        g.with_od[i] = ch->with_od;
+        // rows that only lived for this launch go back to the pool: any later use is ordered behind it by the stream
+        for (double* r : ch->temp_rows) ds->pool.put(r);
+        ch->temp_rows.clear();
+        ch->builds.clear();
+        ch->build_aux.clear();
     }
-    for (int i = 0; i < n; ++i) g.with_od[i] = chains[i]->with_od;
     g.busy = true;
     g.n = n;
     g.ticket = tk;
@@ -729,6 +778,11 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
         ds->last_kernel_us = 1e3 * ms;
         ds->sum_kernel_us += ds->last_kernel_us;
         ds->n_timed++;
+        if (g.n_items) {
+            CUDA_TRY(cudaEventElapsedTime(&ms, g.evb, g.ev0));
+            ds->sum_build_us += 1e3 * ms;
+            ds->n_build_timed++;
+        }
     }
     bool nan = false;
     for (int i = 0; i < n; ++i) {
@@ -743,7 +797,7 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
             v[0] = g.h_total[2 * i];
             v[1] = g.h_total[2 * i + 1];
         }
-        totals[i] = v[0];
+        if (totals) totals[i] = v[0];
         if (od_scores) od_scores[i] = g.with_od[i] ? v[1] : NAN;
         if (g.h_status[i]) nan = true;
     }
@@ -766,41 +820,19 @@ int od_scores(scicone_chain* ch, double nu, double* out) {
     if (rc) return rc;
     rc = ds->ensure_slots(1);
     if (rc) return rc;
-    std::vector<unsigned char> b;
-    rc = build_od_block(ch, nu, 0, b);
+    // the queued proposal of this chain (if any) is compiled later and rebuilds its own blob
+    std::vector<unsigned char> keep;
+    keep.swap(ch->blob);
+    const bool keep_with_od = ch->with_od;
+    rc = compile_od_only(ch, nu, 0);
+    double od = 0.0;
+    unsigned long long tk = 0;
+    if (!rc) rc = submit_proposals(ds, &ch, 1, &tk);
+    if (!rc) rc = wait_proposals(ds, tk, nullptr, &od);
+    keep.swap(ch->blob);
+    ch->with_od = keep_with_od;
     if (rc) return rc;
-    const size_t head = 16;
-    rc = ds->ensure_arena(head + b.size());
-    if (rc) return rc;
-    // takes the next staging segment like a proposal launch does (earlier tickets stay collectable)
-    scicone_dataset::Segment& g = ds->seg[ds->next_ticket % scicone_dataset::kRing];
-    if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
-    ds->next_ticket++;
-    reinterpret_cast<unsigned*>(g.h_arena)[0] = (unsigned)head;
-    memcpy(g.h_arena + head, b.data(), b.size());
-    CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, head + b.size(), cudaMemcpyHostToDevice, ds->stream));
-    od_root_kernel<<<dim3(ds->n_cta, 1), kBlock, 0, ds->stream>>>(ds->d_arena);
-    CUDA_TRY(cudaGetLastError());
-    ds->n_launches++;
-    double total = 0.0;
-    if (ds->world > 1) {
-        pack_chunks_kernel<<<1, 128, 0, ds->stream>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
-        ds->n_launches++;
-        const size_t cnt = (size_t)2 * ds->max_chunks_rank;
-        int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, ds->stream);
-        if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
-        CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
-        CUDA_TRY(cudaStreamSynchronize(ds->stream));
-        for (int rk = 0; rk < ds->world; ++rk) {
-            const double* c = g.h_gather + (size_t)rk * cnt + ds->max_chunks_rank;  // value 1 = root score
-            for (int q = 0; q < ds->max_chunks_rank; ++q) total += c[q];
-        }
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, 2 * sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
-        CUDA_TRY(cudaStreamSynchronize(ds->stream));
-        total = g.h_total[1];
-    }
-    if (out) *out = total;
+    if (out) *out = od;
     return SCICONE_OK;
 }
 
@@ -854,7 +886,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     scicone_dataset* ds = new scicone_dataset();
     ds->M = d->n_cells;
     ds->K = d->n_regions;
-    ds->Mp = round_up(ds->M, kBlock);
+    ds->Mp = round_up(ds->M, kPad);
     ds->device = d->device;
     ds->eta = d->eta;
     ds->od = d->is_overdispersed != 0;
@@ -867,7 +899,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
         ds->root_z += ds->r[k] * ds->neutral[k];
         ds->sum_r += ds->r[k];
     }
-    ds->n_cta = (int)(ds->Mp / kBlock);
+    ds->n_cta = (ds->M + kCells - 1) / kCells;
     ds->n_chunks = (ds->n_cta + kCtasPerChunk - 1) / kCtasPerChunk;
     ds->pool.init(ds->Mp);
     auto cleanup = [&](int rc) {
@@ -883,6 +915,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     DS_TRY(cudaSetDevice(ds->device));
     DS_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     for (scicone_dataset::Segment& g : ds->seg) {
+        DS_TRY(cudaEventCreate(&g.evb));
         DS_TRY(cudaEventCreate(&g.ev0));
         DS_TRY(cudaEventCreate(&g.ev1));
         DS_TRY(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
@@ -931,10 +964,13 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
         if (g.h_total) cudaFreeHost(g.h_total);
         if (g.h_status) cudaFreeHost(g.h_status);
         if (g.h_gather) cudaFreeHost(g.h_gather);
+        if (g.evb) cudaEventDestroy(g.evb);
         if (g.ev0) cudaEventDestroy(g.ev0);
         if (g.ev1) cudaEventDestroy(g.ev1);
         if (g.done) cudaEventDestroy(g.done);
     }
+    for (cudaEvent_t e : ds->region_ev)
+        if (e) cudaEventDestroy(e);
     if (ds->stream) cudaStreamDestroy(ds->stream);
     delete ds;
 }
@@ -1265,7 +1301,7 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
     ds->rank = rank;
     ds->world = world_size;
     // every rank pads to the same chunk count: the largest shard a rank can hold
-    const long long chunk_cells = (long long)kBlock * kCtasPerChunk;
+    const long long chunk_cells = (long long)kCells * kCtasPerChunk;
     const long long global_chunks = (ds->M_global + chunk_cells - 1) / chunk_cells;
     ds->max_chunks_rank = (int)std::max<long long>((global_chunks + world_size - 1) / world_size + 1, ds->n_chunks);
     // all ranks must agree on max_chunks_rank: exchange through the communicator
@@ -1304,9 +1340,15 @@ int scicone_kernel_time_stats(scicone_dataset* ds, double* sum_us, uint64_t* n_t
     if (sum_us) *sum_us = ds->sum_kernel_us;
     if (n_timed) *n_timed = ds->n_timed;
     if (reset) {
-        ds->sum_kernel_us = 0.0;
-        ds->n_timed = 0;
+        ds->sum_kernel_us = ds->sum_build_us = 0.0;
+        ds->n_timed = ds->n_build_timed = 0;
     }
+    return SCICONE_OK;
+}
+int scicone_build_time_stats(scicone_dataset* ds, double* sum_us, uint64_t* n_timed) {
+    if (!ds) return fail(SCICONE_ERR_ARG, "null dataset");
+    if (sum_us) *sum_us = ds->sum_build_us;
+    if (n_timed) *n_timed = ds->n_build_timed;
     return SCICONE_OK;
 }
 int scicone_counters(scicone_dataset* ds, double out[4], int32_t reset) {

@@ -73,7 +73,13 @@ def run_trace(gpu, cpu, tree, n_moves, tol, kinds=None, check_tables_every=10):
     assert list(gpu.t_node_ids()) == list(cpu.t_node_ids())
     worst["t_scores"] = max(worst["t_scores"], rel_err(gpu.read_t_scores(), cpu.read_t_scores()))
     for k, v in worst.items():
-        if not k.startswith("argmax"):
-            assert v <= tol, (k, v)
+        if k.startswith("argmax"):
+            continue
+        # Per-cell aggregates in sum mode go through MathOp::log_replace_sum (MathOp.cpp:307-361), which subtracts
+        # the old terms in linear space and keeps the remainder whenever it exceeds 1e-6: the reference's own
+        # algorithm amplifies a 1e-13 perturbation of the scores (device vs libm lgamma, a few ulp) by up to 1e6.
+        # Scores and the tree totals (the quantity north_star bounds) are held to `tol`.
+        bar = 1e-6 if (k == "t_prime_sums" and not gpu.max_scoring) else tol
+        assert v <= bar, (k, v)
     worst["n_moves"] = n_done
     return worst, tree
