@@ -1,0 +1,118 @@
+// cpu_backend.cpp - the C ABI of include/scicone_score.h implemented on top of the oracle port.
+//
+// TEST INFRASTRUCTURE ONLY.  Built by oracle/Makefile into oracle/_ref/cpu_backend/libscicone_score.so and put on
+// LD_LIBRARY_PATH by tests/ so that the MCMC host (scicone_b200/host, a product binary that normally links the CUDA
+// library) can be exercised in the GPU-less container: move logic, RNG consumption and file formats are compared
+// with the unmodified reference `inference`.  Nothing in the product loads this library; scoring numbers produced
+// through it are the oracle's, not the engine's, and are never reported as results.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "scicone_oracle.h"
+
+struct scicone_dataset {
+    int M, K;
+    std::vector<double> D;
+    std::vector<int32_t> r, neutral, w;
+    double eta;
+    int od, maxs;
+};
+struct scicone_chain {
+    scicone_dataset* ds;
+    orc_ctx* ctx;
+    bool pending = false;
+    // copy of the queued tree
+    std::vector<int32_t> id, parent, co, cr, cv, go, gr, gv;
+    scicone_tree pod;
+    double t_nu = 0.0;
+    void keep(const scicone_tree* t) {
+        int n = t->n_nodes;
+        id.assign(t->node_id, t->node_id + n);
+        parent.assign(t->parent, t->parent + n);
+        co.assign(t->chg_off, t->chg_off + n + 1);
+        cr.assign(t->chg_region, t->chg_region + co[n]); cr.push_back(0);
+        cv.assign(t->chg_value, t->chg_value + co[n]); cv.push_back(0);
+        go.assign(t->gen_off, t->gen_off + n + 1);
+        gr.assign(t->gen_region, t->gen_region + go[n]); gr.push_back(0);
+        gv.assign(t->gen_value, t->gen_value + go[n]); gv.push_back(0);
+        pod.n_nodes = n; pod.node_id = id.data(); pod.parent = parent.data(); pod.chg_off = co.data(); pod.chg_region = cr.data();
+        pod.chg_value = cv.data(); pod.gen_off = go.data(); pod.gen_region = gr.data(); pod.gen_value = gv.data(); pod.nu = t->nu;
+    }
+};
+static thread_local std::string g_err;
+static int fail(int rc, const char* m) { g_err = m; return rc; }
+
+extern "C" {
+int scicone_abi_version(void) { return SCICONE_ABI_VERSION; }
+const char* scicone_last_error(void) { return g_err.c_str(); }
+int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d) {
+    scicone_dataset* ds = new scicone_dataset();
+    ds->M = d->n_cells; ds->K = d->n_regions;
+    ds->D.assign(d->D, d->D + (size_t)ds->M * ds->K);
+    ds->r.assign(d->region_sizes, d->region_sizes + ds->K);
+    ds->neutral.assign(d->neutral_states, d->neutral_states + ds->K);
+    ds->w.assign(d->cluster_sizes, d->cluster_sizes + ds->M);
+    ds->eta = d->eta; ds->od = d->is_overdispersed; ds->maxs = d->max_scoring;
+    *out = ds;
+    return 0;
+}
+void scicone_dataset_destroy(scicone_dataset* ds) { delete ds; }
+int scicone_chain_create(scicone_chain** out, scicone_dataset* ds) {
+    scicone_chain* ch = new scicone_chain();
+    ch->ds = ds;
+    ch->ctx = orc_create(ds->M, ds->K, ds->D.data(), ds->r.data(), ds->neutral.data(), ds->w.data(), ds->eta, ds->od, ds->maxs);
+    *out = ch;
+    return 0;
+}
+void scicone_chain_destroy(scicone_chain* ch) { if (ch) { orc_destroy(ch->ctx); delete ch; } }
+int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* s) { ch->pending = false; ch->t_nu = t->nu; return orc_compute_t_table(ch->ctx, t, s); }
+int scicone_compute_t_od_scores(scicone_chain* ch, double nu, double* od) { return orc_compute_od_scores(ch->ctx, nu, od, nullptr); }
+int scicone_compute_t_prime_od_scores(scicone_chain* ch, double nu, double* od) { return orc_compute_od_scores(ch->ctx, nu, od, nullptr); }
+int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t, int32_t idx) {
+    if (!ch->pending) { ch->keep(t); ch->pending = true; }
+    return orc_compute_t_prime_scores(ch->ctx, &ch->pod, idx) ? fail(-3, "oracle: compute_t_prime_scores failed") : 0;
+}
+int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const*, int32_t n, double* sums, double* ods) {
+    int rc = 0;
+    for (int i = 0; i < n; ++i) {
+        scicone_chain* ch = chains[i];
+        if (!ch->pending) return fail(-3, "compute_t_prime_sums without compute_t_prime_scores");
+        int r = orc_compute_t_prime_sums(ch->ctx, &ch->pod, &sums[i]);
+        if (r) rc = -4;
+        if (ods) {
+            ods[i] = NAN;
+            if (ch->pod.nu != ch->t_nu) orc_compute_od_scores(ch->ctx, ch->pod.nu, &ods[i], nullptr);
+        }
+    }
+    return rc ? fail(rc, "NaN aggregate") : 0;
+}
+int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t, double* s) { return scicone_batch_compute_t_prime_sums(&ch, &t, 1, s, nullptr); }
+int scicone_accept(scicone_chain* ch) { ch->pending = false; ch->t_nu = ch->pod.nu; return orc_accept(ch->ctx, &ch->pod); }
+int scicone_reject(scicone_chain* ch) { ch->pending = false; return orc_reject(ch->ctx); }
+int scicone_t_n_nodes(scicone_chain* ch, int32_t* n) { *n = orc_t_n_nodes(ch->ctx); return 0; }
+int scicone_t_node_ids(scicone_chain* ch, int32_t* ids) { orc_t_node_ids(ch->ctx, ids); return 0; }
+int scicone_read_t_scores(scicone_chain* ch, double* out) { orc_read_t_scores(ch->ctx, out); return 0; }
+int scicone_read_t_sums(scicone_chain* ch, double* out) { orc_read_t_sums(ch->ctx, out); return 0; }
+int scicone_read_t_maxs(scicone_chain* ch, int32_t* ids, double* v) { orc_read_t_maxs(ch->ctx, ids, v); return 0; }
+int scicone_read_t_prime_sums(scicone_chain* ch, double* out) { orc_read_t_prime_sums(ch->ctx, out); return 0; }
+int scicone_read_t_prime_maxs(scicone_chain* ch, int32_t* ids, double* v) { orc_read_t_prime_maxs(ch->ctx, ids, v); return 0; }
+int scicone_t_prime_n_rescored(scicone_chain* ch, int32_t* n) { *n = orc_t_prime_n_rescored(ch->ctx); return 0; }
+int scicone_read_t_prime_scores(scicone_chain* ch, int32_t* ids, double* out) { orc_read_t_prime_scores(ch->ctx, ids, out); return 0; }
+int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int32_t* ids, int32_t* cn) { orc_assign_cells_to_nodes(ch->ctx, t, ids, cn); return 0; }
+int scicone_comm_unique_id(uint8_t*) { return fail(-5, "cpu backend: no communicator"); }
+int scicone_dataset_attach_comm(scicone_dataset*, const uint8_t*, int32_t, int32_t) { return fail(-5, "cpu backend: no communicator"); }
+int scicone_batch_submit(scicone_chain* const*, const scicone_tree* const*, int32_t, uint64_t*) { return fail(-3, "cpu backend: no pipelining"); }
+int scicone_batch_wait(scicone_dataset*, uint64_t, double*, double*) { return fail(-3, "cpu backend: no pipelining"); }
+int scicone_set_profiling(scicone_dataset*, int32_t) { return 0; }
+int scicone_last_kernel_time_us(scicone_dataset*, double* us) { *us = 0; return 0; }
+int scicone_kernel_time_stats(scicone_dataset*, double* s, uint64_t* n, int32_t) { if (s) *s = 0; if (n) *n = 0; return 0; }
+int scicone_build_time_stats(scicone_dataset*, double* s, uint64_t* n) { if (s) *s = 0; if (n) *n = 0; return 0; }
+int scicone_kernel_launches(scicone_dataset*, uint64_t* n) { *n = 0; return 0; }
+int scicone_counters(scicone_dataset*, double out[4], int32_t) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
+int scicone_region_mark(scicone_dataset*, int32_t) { return 0; }
+int scicone_region_elapsed_ms(scicone_dataset*, double* ms) { *ms = 0; return 0; }
+int scicone_device_bytes(scicone_dataset*, uint64_t* b) { *b = 0; return 0; }
+}

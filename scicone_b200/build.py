@@ -41,8 +41,27 @@ def build_score_lib(force=False, verbose=False):
     return out
 
 
+def build_host(force=False):
+    """The MCMC host: scicone_b200/bin/inference (CLI of the reference's `inference`) and lib/libscicone_host.so."""
+    host = os.path.join(HERE, "host")
+    bin_dir = os.path.join(HERE, "bin")
+    os.makedirs(bin_dir, exist_ok=True)
+    srcs = [os.path.join(host, f) for f in ("inference_main.cpp", "mcmc.hpp", "tree.hpp", "rng_dist.hpp")]
+    srcs.append(os.path.join(ROOT, "include", "scicone_score.h"))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    common = [cxx, "-std=c++17", "-O2", "-fno-fast-math", "-ffp-contract=off", "-Wall", "-Wno-sign-compare", srcs[0],
+              "-L" + LIB_DIR, "-lscicone_score"]
+    exe = os.path.join(bin_dir, "inference")
+    lib = os.path.join(LIB_DIR, "libscicone_host.so")
+    if force or _newer(exe, srcs):
+        subprocess.check_call(common + ["-Wl,-rpath,$ORIGIN/../lib", "-o", exe])
+    if force or _newer(lib, srcs):
+        subprocess.check_call(common + ["-DSCICONE_HOST_NO_MAIN", "-fPIC", "-shared", "-Wl,-rpath,$ORIGIN", "-o", lib])
+    return [exe, lib]
+
+
 def build_all(force=False, verbose=False):
-    return [build_score_lib(force, verbose)]
+    return [build_score_lib(force, verbose)] + build_host(force)
 
 
 if __name__ == "__main__":

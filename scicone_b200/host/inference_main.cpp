@@ -1,0 +1,365 @@
+// `inference` - tree inference by MCMC on the B200 scoring engine.
+//
+// Keeps the command line, input files and output files of the reference's `inference` binary
+// (reference: scicone/src/infer_trees.cpp; formats in SURVEY.md App. D) so that pyscicone and the tutorial
+// commands work unchanged.  Additions (all optional): --n_chains=B runs B independent restarts (seeds seed, seed+1, ...)
+// in lock-step on one GPU with one kernel launch per step, --device, --stats_file (JSON timing for bench.py),
+// and --rank/--world/--nccl_id for cell-sharded multi-GPU runs.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "mcmc.hpp"
+
+using namespace scicone_host;
+
+namespace {
+
+struct Args {
+    std::map<std::string, std::string> kv;
+    bool has(const std::string& k) const { return kv.count(k) != 0; }
+    std::string str(const std::string& k, const std::string& d = "") const { return has(k) ? kv.at(k) : d; }
+    double num(const std::string& k, double d) const { return has(k) ? std::stod(kv.at(k)) : d; }
+    long integer(const std::string& k, long d) const { return has(k) ? std::stol(kv.at(k)) : d; }
+    bool flag(const std::string& k, bool d) const {  // cxxopts: (t|T)(rue)?|1 is true, (f|F)(alse)?|0 is false
+        if (!has(k)) return d;
+        const std::string& v = kv.at(k);
+        if (v.empty() || v == "1" || v == "t" || v == "T" || v == "true" || v == "True") return true;
+        if (v == "0" || v == "f" || v == "F" || v == "false" || v == "False") return false;
+        throw std::runtime_error("Argument '" + v + "' failed to parse for option --" + k);
+    }
+};
+
+Args parse(int argc, char** argv) {
+    Args a;
+    for (int i = 1; i < argc; ++i) {
+        std::string s = argv[i];
+        if (s.rfind("--", 0) != 0) continue;
+        s = s.substr(2);
+        size_t eq = s.find('=');
+        if (eq != std::string::npos)
+            a.kv[s.substr(0, eq)] = s.substr(eq + 1);
+        else if (i + 1 < argc && std::string(argv[i + 1]).rfind("--", 0) != 0)
+            a.kv[s] = argv[++i];
+        else
+            a.kv[s] = "";
+    }
+    return a;
+}
+
+// Utils::read_counts (Utils.cpp:74-102): comma separated doubles into a pre-sized cells x regions matrix
+void read_counts(std::vector<double>& mat, int n_cells, int n_regions, const std::string& path) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("cannot open " + path);
+    std::string line;
+    int i = 0;
+    while (std::getline(in, line)) {
+        if (i >= n_cells) throw std::runtime_error("more rows in " + path + " than --n_cells");
+        const char* p = line.c_str();
+        int j = 0;
+        while (*p) {
+            char* end = nullptr;
+            double v = std::strtod(p, &end);
+            if (end == p) break;
+            if (j < n_regions) mat[static_cast<size_t>(i) * n_regions + j] = v;
+            ++j;
+            p = end;
+            while (*p == ',' || *p == ' ' || *p == '\r') ++p;
+        }
+        ++i;
+    }
+    if (i != n_cells) throw std::runtime_error("the counts file has " + std::to_string(i) + " rows, --n_cells says " + std::to_string(n_cells));
+}
+
+// Utils::read_vector (Utils.cpp:141-163): one number per line
+void read_vector(std::vector<int>& vec, const std::string& path) {
+    std::ifstream in(path);
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        vec.push_back(static_cast<int>(std::stod(line)));
+    }
+    if (vec.empty()) throw std::logic_error("The size of the vector should not be zero!");
+}
+
+std::vector<float> parse_floats(const std::string& s) {
+    std::vector<float> out;
+    std::stringstream ss(s);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) out.push_back(std::stof(tok));
+    return out;
+}
+
+void hex_to_bytes(const std::string& hex, uint8_t* out, size_t n) {
+    if (hex.size() != 2 * n) throw std::runtime_error("--nccl_id must be 256 hex characters");
+    for (size_t i = 0; i < n; ++i) out[i] = static_cast<uint8_t>(std::stoi(hex.substr(2 * i, 2), nullptr, 16));
+}
+
+}  // namespace
+
+extern "C" int scicone_inference_main(int argc, char** argv) {
+    try {
+        Args a = parse(argc, argv);
+        Params P;
+        int n_iters = static_cast<int>(a.integer("n_iters", 5000));
+        int ploidy = static_cast<int>(a.integer("ploidy", 2));
+        P.verbosity = static_cast<int>(a.integer("verbosity", 0));
+        int seed = static_cast<int>(a.integer("seed", 0));
+        unsigned size_limit = a.has("size_limit") ? static_cast<unsigned>(a.integer("size_limit", 0)) : std::numeric_limits<unsigned>::max();
+        int n_nodes = static_cast<int>(a.integer("n_nodes", 3));
+        P.lambda_r = a.num("lambda_r", 0.1);
+        P.lambda_c = a.num("lambda_c", 0.2);
+        P.cf = a.num("cf", 0.0);
+        P.c_penalise = a.num("c_penalise", 10.0);
+        P.is_overdispersed = 1;
+        P.eta = a.num("eta", 1e-4);
+        P.print_precision = static_cast<int>(a.integer("print_precision", 15));
+        P.lambda_s = 0.5;
+        P.copy_number_limit = static_cast<int>(a.integer("copy_number_limit", 5));
+        P.postfix = a.str("postfix");
+        double nu = a.num("nu", 1.0);
+        double alpha = a.num("alpha", 0.0);
+        double gamma = a.num("gamma", 1.0);
+        bool max_scoring = a.flag("max_scoring", true);
+        std::vector<float> move_probs = a.has("move_probs")
+                                            ? parse_floats(a.str("move_probs"))
+                                            : std::vector<float>{0.0f, 1.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.01f, 0.1f, 0.01f, 1.0f, 0.01f};
+        if (move_probs.size() != 15) throw std::runtime_error("--move_probs needs 15 comma separated values");
+        const int n_chains = static_cast<int>(a.integer("n_chains", 1));
+        const int device = static_cast<int>(a.integer("device", 0));
+        const int rank = static_cast<int>(a.integer("rank", 0)), world = static_cast<int>(a.integer("world", 1));
+
+        if (!a.has("region_sizes_file")) { std::cerr << "the region sizes file is not provided." << std::endl; return EXIT_FAILURE; }
+        if (!a.has("d_matrix_file")) { std::cerr << "the D matrix file is not provided." << std::endl; return EXIT_FAILURE; }
+        if (!a.has("n_regions")) { std::cerr << "the number of regions is not provided." << std::endl; return EXIT_FAILURE; }
+        if (!a.has("n_cells")) { std::cerr << "the number of cells is not provided." << std::endl; return EXIT_FAILURE; }
+        const int n_cells = static_cast<int>(a.integer("n_cells", 0));
+        const int n_regions = static_cast<int>(a.integer("n_regions", 0));
+        if (!a.has("seed")) seed = -1;  // the reference seeds from std::random_device when --seed is absent
+        bool random_init = a.flag("random_init", true);
+        if (a.has("tree_file")) random_init = false;
+
+        if (P.verbosity > 0) {
+            if (a.has("alpha")) std::cout << "the learning rate alpha constant is specified to be " << alpha << std::endl;
+            else std::cout << "the learning rate alpha constant is " << alpha << " since it is not specified" << std::endl;
+            if (a.has("gamma")) std::cout << "initial gamma is specified to be " << gamma << std::endl;
+            else std::cout << "gamma value is not specified, the default value is: " << gamma << std::endl;
+            if (a.has("cf")) std::cout << "Cluster fraction in tree prior is: " << P.cf << std::endl;
+            std::cout << "Reading the input matrix..." << std::endl;
+        }
+        std::vector<double> D(static_cast<size_t>(n_cells) * n_regions, 0.0);
+        read_counts(D, n_cells, n_regions, a.str("d_matrix_file"));
+        if (P.verbosity > 0) std::cout << "Reading the region_sizes file..." << std::endl;
+        std::vector<int> region_sizes;
+        read_vector(region_sizes, a.str("region_sizes_file"));
+        if (static_cast<int>(region_sizes.size()) != n_regions)
+            throw std::logic_error("Size of the counts per cell needs to be equal to the number of regions!");  // Tree.h:170-171
+        std::vector<int> cluster_sizes;
+        if (a.has("cluster_sizes_file") && !a.str("cluster_sizes_file").empty()) {
+            if (P.verbosity > 0) std::cout << "Reading the cluster_sizes file..." << std::endl;
+            read_vector(cluster_sizes, a.str("cluster_sizes_file"));
+        } else {
+            cluster_sizes.assign(n_cells, 1);
+            if (n_cells < 20)
+                std::cout << "Warning: there are only " << n_cells
+                          << " observations. If these are clusters, the cluster_sizes_file parameter should be specified for accurate tree scoring." << std::endl;
+        }
+        if (!max_scoring) {  // infer_trees.cpp:198-210
+            if (P.verbosity > 0) std::cout << "Will perform sum scoring." << std::endl;
+            P.cf = 1.0;
+            move_probs[11] = 0.0f;
+            move_probs[12] = 0.0f;
+        } else {
+            if (P.verbosity > 0) std::cout << "Will perform maximum scoring." << std::endl;
+            move_probs.back() = 0.0f;
+        }
+        std::vector<int> neutral;
+        if (a.has("region_neutral_states_file") && !a.str("region_neutral_states_file").empty()) {
+            if (P.verbosity > 0) std::cout << "Reading the region_neutral_states file..." << std::endl;
+            read_vector(neutral, a.str("region_neutral_states_file"));
+        } else {
+            if (P.verbosity > 0) std::cout << "Assuming root to have copy number state " << ploidy << " in all regions" << std::endl;
+            neutral.assign(n_regions, ploidy);
+        }
+
+        // nu / likelihood branch (infer_trees.cpp:250-281): without --nu and without the nu move the model is the plain multinomial
+        const bool learn_nu = static_cast<bool>(move_probs[13]);
+        if (!learn_nu && !a.has("nu") && !a.has("tree_file")) P.is_overdispersed = 0;
+        if (!learn_nu && !a.has("nu") && a.has("tree_file")) P.is_overdispersed = 0;
+
+        // this rank's block of cells (chunk aligned so that totals do not depend on the number of GPUs)
+        long lo = 0, hi = n_cells;
+        if (world > 1) {
+            const long chunk = 1024, n_chunks = (n_cells + chunk - 1) / chunk;
+            const long base = n_chunks / world, extra = n_chunks % world;
+            long c0 = 0;
+            for (int r = 0; r < rank; ++r) c0 += base + (r < extra ? 1 : 0);
+            long c1 = c0 + base + (rank < extra ? 1 : 0);
+            lo = std::min<long>(c0 * chunk, n_cells);
+            hi = std::min<long>(c1 * chunk, n_cells);
+            if (hi <= lo) throw std::runtime_error("this rank has no cells: use fewer GPUs");
+        }
+        std::vector<int32_t> r32(region_sizes.begin(), region_sizes.end()), n32(neutral.begin(), neutral.end()),
+            w32(cluster_sizes.begin() + lo, cluster_sizes.begin() + hi);
+        scicone_dataset_desc desc;
+        desc.n_cells = static_cast<int32_t>(hi - lo);
+        desc.n_regions = n_regions;
+        desc.D = D.data() + static_cast<size_t>(lo) * n_regions;
+        desc.region_sizes = r32.data();
+        desc.neutral_states = n32.data();
+        desc.cluster_sizes = w32.data();
+        desc.eta = P.eta;
+        desc.is_overdispersed = static_cast<int32_t>(P.is_overdispersed);
+        desc.max_scoring = max_scoring ? 1 : 0;
+        desc.device = device;
+        desc.cell_offset = lo;
+        desc.n_cells_global = n_cells;
+        scicone_dataset* ds = nullptr;
+        abi_check(scicone_dataset_create(&ds, &desc));
+        if (world > 1) {
+            uint8_t id[128];
+            hex_to_bytes(a.str("nccl_id"), id, 128);
+            abi_check(scicone_dataset_attach_comm(ds, id, rank, world));
+        }
+        const bool stats = a.has("stats_file");
+        if (stats) scicone_set_profiling(ds, 1);
+
+        std::vector<std::unique_ptr<Inference>> owned;
+        std::vector<Inference*> chains;
+        for (int c = 0; c < n_chains; ++c) {
+            Params Pc = P;
+            if (n_chains > 1) Pc.postfix = P.postfix + "_c" + std::to_string(c);
+            owned.emplace_back(new Inference(Pc, seed == -1 ? -1 : seed + c, static_cast<unsigned>(n_regions), n_cells, neutral, ploidy, max_scoring));
+            Inference* inf = owned.back().get();
+            inf->attach_chain(ds);
+            inf->gamma = gamma;
+            inf->alpha = alpha;
+            if (random_init) {
+                if (P.verbosity > 0 && c == 0) std::cout << "Trying to randomly initialise a valid tree with " << 10000 << " iterations." << std::endl;
+                try {
+                    inf->random_initialize(static_cast<unsigned>(n_nodes), 10000);
+                } catch (const std::runtime_error& e) {
+                    std::cerr << "A runtime error was caught during the random tree initialize function, with message '" << e.what() << '\'' << std::endl;
+                    return EXIT_FAILURE;
+                }
+            }
+            if (a.has("tree_file")) {
+                inf->initialize_from_file(a.str("tree_file"));
+                nu = inf->t.nu;
+            }
+            if (a.has("nu") && !a.has("tree_file")) inf->t.nu = inf->t_prime.nu = nu;
+            else if (a.has("nu") && a.has("tree_file")) inf->t.nu = inf->t_prime.nu = nu;  // nu == the file's value (infer_trees.cpp:247)
+            inf->compute_t_table();
+            inf->compute_t_od_scores();
+            inf->update_t_prime();
+            chains.push_back(inf);
+        }
+
+        if (P.verbosity > 0) std::cout << "Inferring the tree using MCMC with " << n_iters << " iterations..." << std::endl;
+        double k0[4];
+        scicone_counters(ds, k0, 1);
+        scicone_kernel_time_stats(ds, nullptr, nullptr, 1);
+        uint64_t launches0 = 0;
+        scicone_kernel_launches(ds, &launches0);
+        scicone_region_mark(ds, 0);
+        auto start = std::chrono::high_resolution_clock::now();
+        infer_mcmc(chains, move_probs, n_iters, size_limit);
+        scicone_region_mark(ds, 1);
+        double region_ms = 0.0;
+        scicone_region_elapsed_ms(ds, &region_ms);
+        auto stop = std::chrono::high_resolution_clock::now();
+        auto duration = std::chrono::duration_cast<std::chrono::microseconds>(stop - start);
+        if (P.verbosity > 0) std::cout << "Time taken by infer_mcmc function: " << duration.count() << " microseconds" << std::endl;
+        if (stats && rank == 0) {
+            double k[4], kern_us = 0, build_us = 0;
+            uint64_t n_timed = 0, n_build = 0, launches = 0;
+            scicone_counters(ds, k, 0);
+            scicone_kernel_time_stats(ds, &kern_us, &n_timed, 0);
+            scicone_build_time_stats(ds, &build_us, &n_build);
+            scicone_kernel_launches(ds, &launches);
+            uint64_t dev_bytes = 0;
+            scicone_device_bytes(ds, &dev_bytes);
+            unsigned long long acc = 0, rej = 0, resc = 0;
+            for (Inference* c : chains) { acc += c->n_accepted; rej += c->n_rejected; resc += c->n_rescored_nodes; }
+            std::ofstream sf(a.str("stats_file"));
+            sf << std::setprecision(17) << "{\"n_chains\":" << n_chains << ",\"n_iters\":" << n_iters << ",\"n_cells\":" << n_cells
+               << ",\"wall_us\":" << duration.count() << ",\"device_region_ms\":" << region_ms << ",\"score_kernel_us\":" << kern_us
+               << ",\"score_kernel_launches\":" << n_timed << ",\"build_kernel_us\":" << build_us << ",\"build_kernel_launches\":" << n_build
+               << ",\"gpu_launches\":" << (launches - launches0) << ",\"h2d_bytes\":" << k[0] << ",\"d2h_bytes\":" << k[1]
+               << ",\"alg_bytes\":" << k[2] << ",\"n_scores\":" << k[3] << ",\"device_bytes\":" << dev_bytes << ",\"accepted\":" << acc
+               << ",\"rejected\":" << rej << ",\"rescored_nodes\":" << resc << "}" << std::endl;
+        }
+
+        if (P.verbosity > 0) std::cout << "Writing the inferred tree and cnvs..." << std::endl;
+        for (Inference* inf : chains) {
+            if (world > 1 && rank != 0 && !a.has("write_all_ranks")) {
+                // every rank must still take part in the full pass below (collective), but only rank 0 writes files
+            }
+            // Inference::assign_cells_to_nodes, Inference.h:1311-1377
+            inf->t.copy_from(inf->best_tree);
+            inf->compute_t_table();
+            const int M = desc.n_cells;
+            std::vector<int32_t> ids(M), cn(static_cast<size_t>(M) * n_regions);
+            abi_check(scicone_assign_cells_to_nodes(inf->chain, &inf->flat.pod, ids.data(), cn.data()));
+            if (world > 1) continue;  // sharded runs report the tree; per-cell outputs are per rank and not merged here
+            const std::string& pf = inf->P.postfix;
+            if (P.verbosity > 1) {
+                std::ofstream f_ids(pf + "_cell_node_ids.tsv"), f_cn(pf + "_cell_region_cnvs.csv");
+                for (int j = 0; j < M; ++j) f_ids << j << '\t' << ids[j] << '\n';
+                for (int j = 0; j < M; ++j) {
+                    for (int k = 0; k < n_regions; ++k) f_cn << cn[static_cast<size_t>(j) * n_regions + k] << (k == n_regions - 1 ? "" : ",");
+                    f_cn << '\n';
+                }
+            }
+            std::ofstream f_tree("./" + pf + "_tree_inferred.txt");
+            inf->best_tree.write(f_tree);
+            std::ofstream f_cnvs("./" + pf + "_inferred_cnvs.csv");  // Utils::regions_to_bins_cnvs, Utils.cpp:165-188
+            std::string row;
+            for (int j = 0; j < M; ++j) {
+                row.clear();
+                for (int k = 0; k < n_regions; ++k) {
+                    const std::string v = std::to_string(cn[static_cast<size_t>(j) * n_regions + k]);
+                    for (int b = 0; b < region_sizes[k]; ++b) {
+                        row += v;
+                        row += ',';
+                    }
+                }
+                if (!row.empty()) row.pop_back();
+                f_cnvs << row << std::endl;
+            }
+            if (P.verbosity > 1) {
+                int32_t nn = 0;
+                abi_check(scicone_t_n_nodes(inf->chain, &nn));
+                std::vector<double> sc(static_cast<size_t>(M) * nn);
+                abi_check(scicone_read_t_scores(inf->chain, sc.data()));
+                std::ofstream f_sc("./" + pf + "_attachment_scores.csv");
+                for (int j = 0; j < M; ++j) {
+                    for (int c = 0; c < nn; ++c) f_sc << sc[static_cast<size_t>(j) * nn + c] << (c == nn - 1 ? "" : ",");
+                    f_sc << std::endl;
+                }
+            }
+        }
+        if (world > 1 && rank == 0)
+            for (Inference* inf : chains) {
+                std::ofstream f_tree("./" + inf->P.postfix + "_tree_inferred.txt");
+                inf->best_tree.write(f_tree);
+            }
+        owned.clear();
+        scicone_dataset_destroy(ds);
+        if (P.verbosity > 0) std::cout << "Tree inference is successfully completed!" << std::endl;
+        return EXIT_SUCCESS;
+    } catch (const std::exception& e) {
+        std::cerr << "inference: " << e.what() << std::endl;
+        return EXIT_FAILURE;
+    }
+}
+
+#ifndef SCICONE_HOST_NO_MAIN
+int main(int argc, char** argv) { return scicone_inference_main(argc, argv); }
+#endif

@@ -1,0 +1,483 @@
+// MCMC driver of the host: move dispatch, retry policy, Metropolis-Hastings comparison, commit / rollback.
+//
+// Mirrors the reference's `Inference` class (reference: scicone/src/Inference.h) with the same member names at the
+// seam, but every cell-dependent number comes from libscicone_score.so (include/scicone_score.h): the class
+// keeps no score table on the host.  An iteration is split in two halves so that any number of chains can be
+// advanced in lock-step with ONE kernel launch per step:
+//     propose()  - draw the move, mutate t_prime (up to 50 attempts, Inference::apply_multiple_times), queue the
+//                  subtree(s) to rescore with scicone_compute_t_prime_scores;
+//     [driver]   - scicone_batch_compute_t_prime_sums over all chains that have something queued;
+//     finish()   - Inference::comparison with the returned totals, then accept (pointer swaps on the device) or reject.
+#ifndef SCICONE_B200_HOST_MCMC_HPP
+#define SCICONE_B200_HOST_MCMC_HPP
+
+#include <cfloat>
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <memory>
+
+#include "../../include/scicone_score.h"
+#include "tree.hpp"
+
+namespace scicone_host {
+
+inline void abi_check(int rc) {
+    if (rc != SCICONE_OK) throw std::runtime_error(std::string("libscicone_score: ") + scicone_last_error());
+}
+
+// Flat C-ABI view of a Tree (parent-before-child, root first).
+struct FlatTree {
+    std::vector<int32_t> id, parent, chg_off, chg_region, chg_value, gen_off, gen_region, gen_value;
+    std::vector<int> index_of_node;  // pool index -> entry
+    scicone_tree pod;
+    void build(const Tree& t) {
+        std::vector<int> walk = t.descendents(t.root, true);
+        id.clear(); parent.clear(); chg_region.clear(); chg_value.clear(); gen_region.clear(); gen_value.clear();
+        chg_off.assign(1, 0);
+        gen_off.assign(1, 0);
+        index_of_node.assign(t.pool.size(), -1);
+        for (size_t i = 0; i < walk.size(); ++i) index_of_node[walk[i]] = static_cast<int>(i);
+        for (int n : walk) {
+            const Node& nd = t.pool[n];
+            id.push_back(nd.id);
+            parent.push_back(nd.parent == -1 ? -1 : index_of_node[nd.parent]);
+            for (auto const& e : nd.c_change) {
+                chg_region.push_back(static_cast<int32_t>(e.first));
+                chg_value.push_back(e.second);
+            }
+            chg_off.push_back(static_cast<int32_t>(chg_region.size()));
+            for (auto const& e : nd.c) {
+                gen_region.push_back(static_cast<int32_t>(e.first));
+                gen_value.push_back(e.second);
+            }
+            gen_off.push_back(static_cast<int32_t>(gen_region.size()));
+        }
+        chg_region.push_back(0); chg_value.push_back(0); gen_region.push_back(0); gen_value.push_back(0);
+        pod.n_nodes = static_cast<int32_t>(walk.size());
+        pod.node_id = id.data();
+        pod.parent = parent.data();
+        pod.chg_off = chg_off.data();
+        pod.chg_region = chg_region.data();
+        pod.chg_value = chg_value.data();
+        pod.gen_off = gen_off.data();
+        pod.gen_region = gen_region.data();
+        pod.gen_value = gen_value.data();
+        pod.nu = t.nu;
+    }
+};
+
+class Inference {
+public:
+    Params P;
+    Rng rng;
+    Tree t, t_prime, best_tree;
+    unsigned n_regions;
+    int n_cells;  // cells on all ranks
+    int ploidy;
+    bool max_scoring;
+    std::vector<int> region_neutral_states;
+    scicone_chain* chain = nullptr;
+    FlatTree flat;
+
+    // state of the iteration in flight
+    unsigned move_id = 0;
+    bool queued = false;            // t_prime has subtrees queued on the device
+    bool nu_move = false;
+    double t_total = 0.0;           // committed sum_j aggregate_j * cluster_size_j
+    double gamma = 1.0, alpha = 0.0;
+    unsigned n_accepted = 0, n_rejected = 0;
+    unsigned long long n_rescored_nodes = 0;  // sum over scored proposals of the rescored subtree sizes
+    bool have_first_score = false;
+    double first_score = 0.0;
+    std::ofstream f_chain, f_rel, f_acc, f_gamma;
+    bool tracing = false;
+    int n_iters_total = 0;
+
+    Inference(const Params& params, int seed, unsigned n_regions_, int n_cells_, const std::vector<int>& neutral, int ploidy_, bool max_scoring_)
+        : P(params), rng(seed), n_regions(n_regions_), n_cells(n_cells_), ploidy(ploidy_), max_scoring(max_scoring_),
+          region_neutral_states(neutral) {
+        t = Tree(ploidy, n_regions, neutral, &P, &rng);
+        t_prime = Tree(ploidy, n_regions, neutral, &P, &rng);
+        best_tree = Tree(ploidy, n_regions, neutral, &P, &rng);
+    }
+    Inference(const Inference&) = delete;
+    ~Inference() {
+        if (chain) scicone_chain_destroy(chain);
+    }
+    void attach_chain(scicone_dataset* ds) { abi_check(scicone_chain_create(&chain, ds)); }
+
+    // ---- initial tree (Inference::random_initialize, Inference.h:99-156) ------------------------------------------
+    void random_initialize(unsigned n_nodes, int max_iters, int max_regions_per_node = 1) {
+        if (n_nodes == 0) return;
+        std::unique_ptr<Tree> cand;
+        for (int i = 1;; ++i) {
+            cand.reset(new Tree(ploidy, n_regions, region_neutral_states, &P, &rng));
+            for (unsigned j = 0; j < n_nodes; ++j) {
+                EventMap labels;
+                try {
+                    labels = cand->random_labels(max_regions_per_node, P.lambda_r);
+                } catch (const std::out_of_range&) {
+                    cand.reset(new Tree(ploidy, n_regions, region_neutral_states, &P, &rng));
+                    break;
+                }
+                cand->new_child(cand->uniform_sample(true), labels);
+            }
+            if (i > max_iters)
+                throw std::runtime_error("a valid tree cannot be found after " + std::to_string(max_iters) +
+                                         " iterations. Please re-set the lambda_r, lambda_c and n_nodes variables.");
+            if (cand->n_nodes == 0) continue;
+            if (cand->is_valid_subtree(cand->root) && !cand->is_redundant()) break;
+        }
+        t.copy_from(*cand);
+        t.compute_weights();
+    }
+    void initialize_from_file(const std::string& path) { t.load_from_file(path); }
+    void update_t_prime() { t_prime.copy_from(t); }
+
+    // ---- priors (Inference::log_tree_prior / log_tree_posterior, Inference.h:956-994) -----------------------------
+    double log_tree_prior(int m, int n) const {
+        double combinatorial = -P.cf * m * n * std::log(2);
+        if (max_scoring) m = 0;
+        return -(n - 1 + m) * std::log(n + 1) + combinatorial;
+    }
+    double log_tree_posterior(double tree_sum, int m, const Tree& tree) const {
+        double lp = tree_sum + log_tree_prior(m, static_cast<int>(tree.n_nodes));
+        lp += tree.event_prior();
+        return lp;
+    }
+
+    // ---- full passes on the device ----------------------------------------------------------------------------------
+    void compute_t_table() {  // Inference::compute_t_table, Inference.h:224-279
+        flat.build(t);
+        double sum = 0.0;
+        abi_check(scicone_compute_t_table(chain, &flat.pod, &sum));
+        t_total = sum;
+        t.total_attachment_score = sum;
+        t.prior_score = log_tree_prior(n_cells, static_cast<int>(t.n_nodes));
+        t.posterior_score = log_tree_posterior(sum, n_cells, t);
+    }
+    void compute_t_od_scores() {  // Inference::compute_t_od_scores, Inference.h:1406-1419
+        double od = 0.0;
+        abi_check(scicone_compute_t_od_scores(chain, t.nu, &od));
+        t.od_score = od;
+    }
+
+    // ---- one attempt of each move: mutate t_prime, queue the rescoring (Inference::apply_*) -------------------------
+    void queue(int node) {
+        if (!queued) flat.build(t_prime);
+        abi_check(scicone_compute_t_prime_scores(chain, &flat.pod, flat.index_of_node[node]));
+        queued = true;
+    }
+    bool attempt(unsigned size_limit) {
+        switch (move_id) {
+            case 0: case 1: {  // Inference::apply_prune_reattach, :204
+                int n = t_prime.prune_reattach(move_id == 1);
+                if (n < 0) return false;
+                queue(n);
+                return true;
+            }
+            case 2: case 3: {  // apply_swap, :1054
+                std::vector<int> nodes = t_prime.swap_labels(move_id == 3);
+                for (int n : nodes) queue(n);
+                return true;
+            }
+            case 4: case 5: {  // apply_add_remove_events, :1198
+                int n = t_prime.add_remove_events(move_id == 5);
+                if (n < 0) return false;
+                queue(n);
+                return true;
+            }
+            case 6: case 7: {  // apply_insert_delete_node, :1247
+                int n = t_prime.insert_delete_node(size_limit, move_id == 7, max_scoring);
+                if (n < 0) return false;
+                queue(n);
+                return true;
+            }
+            case 8: case 9: {  // apply_condense_split, :1291
+                int n = t_prime.condense_split_node(size_limit, move_id == 9, max_scoring);
+                if (n < 0) return false;
+                queue(n);
+                return true;
+            }
+            case 11: {  // apply_expand_shrink_blocks, :1223
+                int n = t_prime.expand_shrink_blocks(false);
+                if (n < 0) return false;
+                queue(n);
+                return true;
+            }
+            case 12: {  // apply_add_common_ancestor, :1516
+                int n = t_prime.add_common_ancestor();
+                if (n < 0) return false;
+                queue(n);
+                return true;
+            }
+            case 13: {  // apply_overdispersion_change, :916-954: Gaussian random walk on log nu
+                double step = rng.normal(0.0, 0.02);
+                double log_nu = std::log(t_prime.nu) + step;
+                if (log_nu > 10.0) return false;
+                t_prime.nu = std::exp(log_nu);
+                nu_move = true;  // the root score at the new nu comes back with the proposal's launch
+                queue(t_prime.root);
+                return true;
+            }
+            case 14: {  // apply_delete_leaf, :1500
+                queue(t_prime.delete_leaf());
+                return true;
+            }
+            default:
+                throw std::logic_error("undefined move index");
+        }
+    }
+
+    // First half of an iteration.  Returns true when a proposal is queued on the device and finish() must be given its totals.
+    bool propose(const std::vector<float>& move_probs, unsigned size_limit) {
+        move_id = static_cast<unsigned>(rng.discrete(move_probs.begin(), move_probs.end()));
+        queued = false;
+        nu_move = false;
+        if (move_id == 10) return false;  // handled entirely on the host in finish()
+        for (unsigned a = 0; a < 50; ++a) {  // Inference::apply_multiple_times, Inference.h:1462-1498
+            bool ok = false;
+            try {
+                ok = attempt(size_limit);
+            } catch (const InvalidMove&) {
+                break;  // no point in retrying
+            } catch (const std::exception&) {
+                drop_queue();
+                t_prime.copy_from(t);
+                continue;
+            }
+            if (ok) return true;
+            drop_queue();
+            t_prime.copy_from(t);
+        }
+        return false;
+    }
+    void drop_queue() {
+        if (queued) {
+            scicone_reject(chain);
+            queued = false;
+        }
+    }
+
+    // Inference::comparison (Inference.h:285-516) given the weighted total of t_prime from the device.
+    bool comparison(double t_prime_sum, int m) {
+        const unsigned t_n = t.n_nodes, tp_n = t_prime.n_nodes;
+        t_prime.posterior_score = log_tree_posterior(t_prime_sum, m, t_prime);
+        t_prime.prior_score = log_tree_prior(m, static_cast<int>(tp_n));
+        t_prime.total_attachment_score = t_prime_sum;
+        const bool weighted = (move_id % 2 == 1) && (move_id <= 9);
+        double score_diff;
+        if (move_id == 13)
+            score_diff = (t_prime.od_score - t.od_score) + (t_prime.posterior_score - t.posterior_score);
+        else
+            score_diff = t_prime.posterior_score - t.posterior_score;
+        double nbd = 0.0;
+        if (!max_scoring) {  // neighbourhood corrections of the posterior sampler
+            nbd = 1.0;
+            double sum_chi = 0.0, sum_chi_p = 0.0, sum_omega = 0.0, sum_omega_p = 0.0;
+            if (move_id == 1) {
+                double c = t.cost() / t_prime.cost();
+                if (std::isinf(c)) return false;
+                nbd *= c;
+            } else if (move_id == 6 || move_id == 7) {
+                std::vector<double> v = t.chi_insert_delete(weighted);
+                sum_chi = std::accumulate(v.begin(), v.end(), 0.0);
+                v = t_prime.chi_insert_delete(weighted);
+                sum_chi_p = std::accumulate(v.begin(), v.end(), 0.0);
+                if (std::isinf(sum_chi)) throw std::out_of_range("sum_chi is infinity, insert/delete move will be rejected");
+                v = t.omega_insert_delete(weighted, max_scoring);
+                sum_omega = std::accumulate(v.begin(), v.end(), 0.0);
+                v = t_prime.omega_insert_delete(weighted, max_scoring);
+                sum_omega_p = std::accumulate(v.begin(), v.end(), 0.0);
+            } else if (move_id == 8 || move_id == 9) {
+                std::vector<double> v = t.chi_condense_split(weighted);
+                sum_chi = std::accumulate(v.begin(), v.end(), 0.0);
+                v = t_prime.chi_condense_split(weighted);
+                sum_chi_p = std::accumulate(v.begin(), v.end(), 0.0);
+                v = t.omega_condense_split(weighted, max_scoring);
+                sum_omega = std::accumulate(v.begin(), v.end(), 0.0);
+                v = t_prime.omega_condense_split(weighted, max_scoring);
+                sum_omega_p = std::accumulate(v.begin(), v.end(), 0.0);
+            }
+            if (move_id >= 6 && move_id <= 9) nbd *= (t_n < tp_n) ? sum_chi / sum_omega_p : sum_omega / sum_chi_p;
+            if (move_id == 7 || move_id == 9) {
+                auto ids_of = [](const Tree& tr) {
+                    std::set<int> s;
+                    for (int n : tr.descendents(tr.root, true)) s.insert(tr.pool[n].id);
+                    return s;
+                };
+                if (t_n > tp_n) {  // a node of t is gone
+                    std::set<int> kept = ids_of(t_prime);
+                    int gone = -1;
+                    for (int n : t.descendents(t.root, false))
+                        if (!kept.count(t.pool[n].id)) {
+                            gone = n;
+                            break;
+                        }
+                    if (gone < 0) throw std::logic_error("The deleted node could not be found in t!");
+                    unsigned d_t = t.pool[gone].n_desc, d_tp = 0;
+                    int pid = t.pool[t.pool[gone].parent].id;
+                    for (int n : t_prime.descendents(t_prime.root, true))
+                        if (t_prime.pool[n].id == pid) {
+                            d_tp = t_prime.pool[n].n_desc;
+                            break;
+                        }
+                    if (d_t == 0) throw std::logic_error("The deleted node's parent could not be found in t_prime!");
+                    double num = d_tp + 1, den = 2 * d_t;
+                    nbd *= num / den;
+                } else {  // a node was added
+                    std::set<int> had = ids_of(t);
+                    int added = -1;
+                    for (int n : t_prime.descendents(t_prime.root, false))
+                        if (!had.count(t_prime.pool[n].id)) {
+                            added = n;
+                            break;
+                        }
+                    if (added < 0) throw std::logic_error("The inserted node could not be found in t_prime!");
+                    unsigned d_tp = t_prime.pool[added].n_desc, d_t = 0;
+                    int pid = t_prime.pool[t_prime.pool[added].parent].id;
+                    for (int n : t.descendents(t.root, true))
+                        if (t.pool[n].id == pid) {
+                            d_t = t.pool[n].n_desc;
+                            break;
+                        }
+                    if (d_t == 0) throw std::logic_error("The inserted node's parent could not be found in t!");
+                    double num = 2 * d_tp, den = d_t + 1;
+                    nbd *= num / den;
+                }
+            }
+        }
+        const double log_nbd = nbd == 0.0 ? 0.0 : std::log(nbd);
+        const double log_acc = log_nbd + gamma * score_diff;
+        if (std::isnan(log_acc) || std::isinf(log_acc)) return false;
+        if (!t_prime.is_valid_subtree(t_prime.root)) return false;
+        if (log_acc > 0) return true;
+        return log_acc > std::log(rng.uniform_real01());
+    }
+
+    // Second half of an iteration.  `scored`: propose() returned true and (total, od) are the device results.
+    void finish(bool scored, double total, double od, int iter) {
+        const int m = n_cells;
+        Tree* accepted = &t;
+        if (move_id == 10) {  // Gibbs move on the committed tree (Inference.h:731-757)
+            bool ok = true;
+            try {
+                t.genotype_preserving_prune_reattach(gamma);
+            } catch (const std::exception&) {
+                ok = false;
+            }
+            if (!ok) {
+                ++n_rejected;
+                trace_move(-1, iter);
+            } else {
+                ++n_accepted;
+                trace_move(static_cast<int>(move_id), iter);
+                t.posterior_score = log_tree_posterior(t_total, m, t);
+                t_prime.copy_from(t);
+            }
+        } else {
+            bool take = false;
+            if (scored) {
+                if (nu_move) t_prime.od_score = od;
+                n_rescored_nodes += rescored_last;
+                try {
+                    take = comparison(total, m);
+                } catch (const std::exception&) {
+                    take = false;
+                }
+            }
+            const double score_diff = t_prime.posterior_score - t.posterior_score;
+            if (take) {
+                accepted = &t_prime;
+                if (move_id != 13 && std::abs(score_diff) > 0.1) gamma *= std::exp((1.0 - alpha) * alpha);
+                trace_move(static_cast<int>(move_id), iter);
+                ++n_accepted;
+                abi_check(scicone_accept(chain));  // t_sums = t_prime_sums; t_maxs = t_prime_maxs; update_t_scores()
+                queued = false;
+                t_total = total;
+                t.copy_from(t_prime);
+                if ((t_prime.posterior_score + t_prime.od_score) > (best_tree.posterior_score + best_tree.od_score)) best_tree.copy_from(t_prime);
+            } else {
+                if (move_id != 13 && std::abs(score_diff) > 0.1) gamma *= std::exp((0.0 - alpha) * alpha);
+                trace_move(-1, iter);
+                ++n_rejected;
+                drop_queue();
+                t_prime.copy_from(t);
+            }
+            if (gamma > 100.0) gamma = 100.0;
+            if (gamma < 1.0 / 100.0) gamma = 1.0 / 100.0;
+        }
+        if (tracing) {
+            const double s = accepted->posterior_score + accepted->od_score;
+            if (!have_first_score) {
+                first_score = s;
+                have_first_score = true;
+            }
+            const bool last = iter == n_iters_total - 1;
+            f_chain << std::setprecision(P.print_precision) << s;
+            f_rel << std::setprecision(P.print_precision) << s - first_score;
+            f_gamma << gamma;
+            if (!last) {
+                f_chain << ',';
+                f_rel << ',';
+                f_gamma << ',';
+            }
+        }
+    }
+    unsigned rescored_last = 0;
+
+    void open_traces(int n_iters) {  // Inference.h:532-538
+        n_iters_total = n_iters;
+        if (P.verbosity > 1) {
+            tracing = true;
+            f_chain.open(P.postfix + "_markov_chain.csv");
+            f_rel.open(P.postfix + "_rel_markov_chain.csv");
+            f_acc.open(P.postfix + "_acceptance_ratio.csv");
+            f_gamma.open(P.postfix + "_gamma_values.csv");
+        }
+    }
+    void trace_move(int id, int iter) {
+        if (tracing) f_acc << std::setprecision(P.print_precision) << id << ((iter == n_iters_total - 1) ? "" : ",");
+    }
+};
+
+// Advance `chains` (all on one dataset) by n_iters iterations in lock-step: one launch per step.
+inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit) {
+    const int B = static_cast<int>(chains.size());
+    for (Inference* c : chains) {
+        c->best_tree.copy_from(c->t);  // Inference.h:540
+        c->open_traces(n_iters);
+    }
+    std::vector<scicone_chain*> handles;
+    std::vector<int> who;
+    std::vector<double> totals(B), ods(B);
+    std::vector<char> scored(B);
+    for (int it = 0; it < n_iters; ++it) {
+        handles.clear();
+        who.clear();
+        for (int b = 0; b < B; ++b) {
+            scored[b] = chains[b]->propose(move_probs, size_limit);
+            if (scored[b]) {
+                handles.push_back(chains[b]->chain);
+                who.push_back(b);
+            }
+        }
+        if (!handles.empty()) {
+            int rc = scicone_batch_compute_t_prime_sums(handles.data(), nullptr, static_cast<int32_t>(handles.size()), totals.data(), ods.data());
+            if (rc != SCICONE_OK && rc != SCICONE_ERR_NAN) abi_check(rc);
+        }
+        std::vector<double> tot_b(B, 0.0), od_b(B, 0.0);
+        for (size_t i = 0; i < who.size(); ++i) {
+            tot_b[who[i]] = totals[i];
+            od_b[who[i]] = ods[i];
+            int32_t nr = 0;
+            scicone_t_prime_n_rescored(chains[who[i]]->chain, &nr);
+            chains[who[i]]->rescored_last = static_cast<unsigned>(nr);
+        }
+        for (int b = 0; b < B; ++b) chains[b]->finish(scored[b], tot_b[b], od_b[b], it);
+    }
+}
+
+}  // namespace scicone_host
+#endif

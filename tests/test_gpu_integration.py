@@ -11,59 +11,12 @@ import numpy as np
 import pytest
 
 from golden_util import load_golden
+from host_util import REF, REF_ON_ABI, compare_runs as _compare, run_inference as _run
 from scicone_b200.synth import make_counts
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.path.join(ROOT, "oracle", "_ref", "inference")
-B200 = os.path.join(ROOT, "oracle", "_ref", "inference_b200")
-
-
-def _run(exe, tmp, tag, D, r, extra, w=None):
-    d = os.path.join(tmp, "d.csv")
-    integer = np.allclose(D, np.round(D))
-    np.savetxt(d, D, delimiter=",", fmt="%.0f" if integer else "%.18e")
-    rf = os.path.join(tmp, "r.txt")
-    np.savetxt(rf, r, fmt="%d")
-    cmd = [exe, f"--d_matrix_file={d}", f"--region_sizes_file={rf}", f"--n_cells={D.shape[0]}", f"--n_regions={D.shape[1]}",
-           "--verbosity=2", f"--postfix={tag}"] + extra
-    if w is not None:
-        wf = os.path.join(tmp, "w.txt")
-        np.savetxt(wf, w, fmt="%d")
-        cmd.append(f"--cluster_sizes_file={wf}")
-    res = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=900)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-
-    def csv(name):
-        return np.array([float(x) for x in open(os.path.join(tmp, f"{tag}_{name}.csv")).read().strip().split(",")])
-
-    return {"acc": csv("acceptance_ratio"), "chain": csv("markov_chain"), "gamma": csv("gamma_values"),
-            "tree": open(os.path.join(tmp, f"{tag}_tree_inferred.txt")).read(),
-            "cell_nodes": open(os.path.join(tmp, f"{tag}_cell_node_ids.tsv")).read(),
-            "cnvs": open(os.path.join(tmp, f"{tag}_inferred_cnvs.csv")).read(),
-            "scores": np.loadtxt(os.path.join(tmp, f"{tag}_attachment_scores.csv"), delimiter=",", ndmin=2)}
-
-
-def _tree_parts(txt):
-    lines = txt.strip().split("\n")
-    head = [float(l.split(":")[1]) for l in lines[:7]]
-    return head, lines[7:]
-
-
-def _compare(a, b):
-    assert np.array_equal(a["acc"], b["acc"]), "accepted-move trajectories differ"
-    rel = np.max(np.abs(a["chain"] - b["chain"]) / np.maximum(1.0, np.abs(a["chain"])))
-    assert rel <= 1e-9, rel
-    assert np.allclose(a["gamma"], b["gamma"], rtol=1e-12)
-    ha, na = _tree_parts(a["tree"])
-    hb, nb = _tree_parts(b["tree"])
-    assert na == nb, "final trees differ"
-    assert np.allclose(ha, hb, rtol=1e-9, atol=1e-9)
-    assert a["cell_nodes"] == b["cell_nodes"]
-    assert a["cnvs"] == b["cnvs"]
-    assert a["scores"].shape == b["scores"].shape
-    assert np.max(np.abs(a["scores"] - b["scores"]) / np.maximum(1.0, np.abs(a["scores"]))) <= 1e-9
-    return rel
+B200 = REF_ON_ABI
 
 
 needs_bins = pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(B200)),

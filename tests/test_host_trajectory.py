@@ -1,0 +1,118 @@
+"""The native MCMC host (scicone_b200/host -> scicone_b200/bin/inference: move set, priors, RNG consumption, CLI and
+writers re-implemented on top of the C ABI) against the unmodified reference `inference` (oracle/_ref/inference):
+identical accepted-move trajectory, final tree and per-cell outputs; per-move scores within 1e-9 relative.
+
+CPU half (not gpu): the host binary runs with oracle/_ref/cpu_backend on LD_LIBRARY_PATH, i.e. the C ABI served by the
+oracle port - this checks the HOST logic (moves, validity rules, neighbourhood corrections, retries, file formats)
+where no GPU exists.  GPU half: the same binary with its normal rpath, i.e. the CUDA library."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import load_golden
+from host_util import CPU_BACKEND_DIR, NATIVE, REF, compare_runs, run_inference
+from scicone_b200.synth import make_counts
+
+needs_bins = pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(NATIVE)),
+                                reason="oracle/_ref/inference or scicone_b200/bin/inference not built")
+CPU_ENV = {"LD_LIBRARY_PATH": CPU_BACKEND_DIR}
+
+
+def _tutorial():
+    doc = load_golden("tutorial_full_sum")
+    return np.array(doc["D"]), np.array(doc["region_sizes"])
+
+
+CASES = {
+    # configs[0]: docs/tutorial.md command, both scoring modes
+    "tutorial_max": (lambda: _tutorial() + (None,), ["--n_iters=3000", "--n_nodes=3", "--seed=42", "--ploidy=2", "--copy_number_limit=2", "--max_scoring=true"]),
+    "tutorial_sum": (lambda: _tutorial() + (None,), ["--n_iters=3000", "--n_nodes=3", "--seed=42", "--ploidy=2", "--copy_number_limit=2", "--max_scoring=false"]),
+    # every move enabled (genotype-preserving prune-reattach, expand/shrink, common ancestor, delete leaf)
+    "all_moves_max": (lambda: _tutorial() + (None,), ["--n_iters=2500", "--n_nodes=6", "--seed=7", "--nu=2.0", "--max_scoring=true",
+                                                       "--move_probs=1,1,1,1,1,1,1,1,1,1,1,1,1,1,1"]),
+    "all_moves_sum": (lambda: _tutorial() + (None,), ["--n_iters=2500", "--n_nodes=6", "--seed=8", "--nu=2.0", "--max_scoring=false",
+                                                       "--move_probs=1,1,1,1,1,1,1,1,1,1,1,0,0,1,1"]),
+    # plain multinomial branch: no nu given and the nu move disabled
+    "multinomial": (lambda: _tutorial() + (None,), ["--n_iters=1500", "--n_nodes=4", "--seed=9", "--max_scoring=true",
+                                                     "--move_probs=0,1,0,1,0,1,0,1,0,1,0.01,0.1,0.01,0,0"]),
+    # learning rate / tempering and a size limit
+    "alpha_gamma": (lambda: _tutorial() + (None,), ["--n_iters=1500", "--n_nodes=5", "--seed=10", "--nu=1.0", "--alpha=0.2", "--gamma=2.0",
+                                                     "--size_limit=8", "--max_scoring=true"]),
+}
+
+
+def _config2():
+    d = make_counts(1000, 10000, 50, seed=5)
+    return d["D"], d["region_sizes"], None
+
+
+def _cluster():
+    d = make_counts(3000, 10000, 40, seed=6, cluster_rows=30)
+    return d["D"], d["region_sizes"], d["cluster_sizes"]
+
+
+CASES["config2_max"] = (_config2, ["--n_iters=300", "--n_nodes=10", "--seed=43", "--nu=1.0", "--max_scoring=true"])
+CASES["config2_sum"] = (_config2, ["--n_iters=200", "--n_nodes=20", "--seed=44", "--nu=1.0", "--max_scoring=false"])
+CASES["cluster_max"] = (_cluster, ["--n_iters=1500", "--n_nodes=5", "--seed=44", "--nu=1.0", "--max_scoring=true"])
+
+
+def _both(tmp_path, case, env):
+    data, extra = CASES[case]
+    D, r, w = data()
+    a = run_inference(REF, str(tmp_path), "ref", D, r, extra, w=w)
+    b = run_inference(NATIVE, str(tmp_path), "new", D, r, extra, w=w, env=env)
+    rel = compare_runs(a, b)
+    print(case, "accepted", int(np.sum(a["acc"] >= 0)), "of", a["acc"].size, "max rel diff", rel)
+    return a, b
+
+
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_native_host_logic_on_cpu(tmp_path, case):
+    _both(tmp_path, case, CPU_ENV)
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_native_host_on_gpu(tmp_path, case):
+    _both(tmp_path, case, None)
+
+
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+def test_tree_file_start_on_cpu(tmp_path):
+    """--tree_file: continue from a stored tree (format of Tree::load_from_file, Tree.h:1565-1660)."""
+    D, r = _tutorial()
+    first = ["--n_iters=400", "--n_nodes=4", "--seed=3", "--nu=1.5", "--max_scoring=true"]
+    run_inference(REF, str(tmp_path), "seed", D, r, first)
+    tf = os.path.join(str(tmp_path), "seed_tree_inferred.txt")
+    extra = ["--n_iters=600", "--seed=4", f"--tree_file={tf}", "--max_scoring=true"]
+    a = run_inference(REF, str(tmp_path), "ref", D, r, extra)
+    b = run_inference(NATIVE, str(tmp_path), "new", D, r, extra, env=CPU_ENV)
+    compare_runs(a, b)
+
+
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+def test_lockstep_chains_equal_single_runs_on_cpu(tmp_path):
+    """--n_chains=3: restarts advanced in lock-step must each equal the single-chain run with seed+c."""
+    D, r = _tutorial()
+    base = ["--n_iters=800", "--n_nodes=4", "--nu=1.0", "--max_scoring=true"]
+    import subprocess
+    from host_util import read_outputs
+    # the multi-chain run writes <postfix>_c<k>_* files
+    d = os.path.join(str(tmp_path), "d.csv")
+    np.savetxt(d, D, delimiter=",", fmt="%.0f")
+    rf = os.path.join(str(tmp_path), "r.txt")
+    np.savetxt(rf, r, fmt="%d")
+    env = dict(os.environ, **CPU_ENV)
+    cmd = [NATIVE, f"--d_matrix_file={d}", f"--region_sizes_file={rf}", f"--n_cells={D.shape[0]}", f"--n_regions={D.shape[1]}",
+           "--verbosity=2", "--postfix=multi", "--seed=20", "--n_chains=3"] + base
+    res = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    for c in range(3):
+        single = run_inference(REF, str(tmp_path), f"single{c}", D, r, base + [f"--seed={20 + c}"])
+        compare_runs(single, read_outputs(str(tmp_path), f"multi_c{c}"))
