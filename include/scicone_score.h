@@ -188,6 +188,17 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
                                   int32_t* cell_region_cn /* [n_cells][n_regions] or NULL */);
 
 /*
+ * Host-side parallel loop on the library's worker pool: fn(i, ctx) for i in [0, n), returns when all are done.
+ * No reference counterpart (the reference is one chain per process: global RNG singleton and `extern` tunables,
+ * SURVEY.md section 8b).  The per-chain calls above - scicone_compute_t_prime_scores, scicone_accept,
+ * scicone_reject, scicone_t_prime_n_rescored - may be issued concurrently for DIFFERENT chains of one dataset, so
+ * a multi-chain host draws, queues and commits its chains inside this loop and launches from the calling thread;
+ * scicone_batch_submit compiles its n proposals on the same pool.  Pool size: SCICONE_THREADS, else the cores (<= 16).
+ */
+int scicone_parallel_for(int32_t n, void (*fn)(int32_t index, void* ctx), void* ctx);
+int scicone_host_threads(void);
+
+/*
  * Multi-GPU (cells sharded over ranks).  The host side
  * exchanges the 128-byte NCCL unique id by its own means (the bench uses
  * torch.distributed), then every rank attaches its dataset.  Afterwards every

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "scicone_oracle.h"
+#include "../scicone_b200/csrc/parallel_for.hpp"  // the same pool as the CUDA library, so the host's threading is exercised
 
 struct scicone_dataset {
     int M, K;
@@ -19,6 +20,9 @@ struct scicone_dataset {
     std::vector<int32_t> r, neutral, w;
     double eta;
     int od, maxs;
+    struct Result { std::vector<double> sums, ods; int rc; };
+    std::map<uint64_t, Result> results;
+    uint64_t next_ticket = 1;
 };
 struct scicone_chain {
     scicone_dataset* ds;
@@ -76,17 +80,20 @@ int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t, int
     return orc_compute_t_prime_scores(ch->ctx, &ch->pod, idx) ? fail(-3, "oracle: compute_t_prime_scores failed") : 0;
 }
 int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const*, int32_t n, double* sums, double* ods) {
-    int rc = 0;
-    for (int i = 0; i < n; ++i) {
-        scicone_chain* ch = chains[i];
-        if (!ch->pending) return fail(-3, "compute_t_prime_sums without compute_t_prime_scores");
-        int r = orc_compute_t_prime_sums(ch->ctx, &ch->pod, &sums[i]);
-        if (r) rc = -4;
-        if (ods) {
-            ods[i] = NAN;
-            if (ch->pod.nu != ch->t_nu) orc_compute_od_scores(ch->ctx, ch->pod.nu, &ods[i], nullptr);
+    for (int i = 0; i < n; ++i)
+        if (!chains[i]->pending) return fail(-3, "compute_t_prime_sums without compute_t_prime_scores");
+    struct Job { scicone_chain* const* chains; double* sums; double* ods; std::vector<int> rc; } job{chains, sums, ods, std::vector<int>(n, 0)};
+    scicone::ForkJoinPool::instance().run(n, [](int i, void* p) {
+        Job& j = *static_cast<Job*>(p);
+        scicone_chain* ch = j.chains[i];
+        if (orc_compute_t_prime_sums(ch->ctx, &ch->pod, &j.sums[i])) j.rc[i] = -4;
+        if (j.ods) {
+            j.ods[i] = NAN;
+            if (ch->pod.nu != ch->t_nu) orc_compute_od_scores(ch->ctx, ch->pod.nu, &j.ods[i], nullptr);
         }
-    }
+    }, &job);
+    int rc = 0;
+    for (int r : job.rc) if (r) rc = r;
     return rc ? fail(rc, "NaN aggregate") : 0;
 }
 int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t, double* s) { return scicone_batch_compute_t_prime_sums(&ch, &t, 1, s, nullptr); }
@@ -104,13 +111,36 @@ int scicone_read_t_prime_scores(scicone_chain* ch, int32_t* ids, double* out) { 
 int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int32_t* ids, int32_t* cn) { orc_assign_cells_to_nodes(ch->ctx, t, ids, cn); return 0; }
 int scicone_comm_unique_id(uint8_t*) { return fail(-5, "cpu backend: no communicator"); }
 int scicone_dataset_attach_comm(scicone_dataset*, const uint8_t*, int32_t, int32_t) { return fail(-5, "cpu backend: no communicator"); }
-int scicone_batch_submit(scicone_chain* const*, const scicone_tree* const*, int32_t, uint64_t*) { return fail(-3, "cpu backend: no pipelining"); }
-int scicone_batch_wait(scicone_dataset*, uint64_t, double*, double*) { return fail(-3, "cpu backend: no pipelining"); }
+// "pipelined" form: evaluated at submit, handed out at wait (keeps the host's two-group schedule testable without a GPU)
+int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const* tp, int32_t n, uint64_t* ticket) {
+    scicone_dataset* ds = chains[0]->ds;
+    scicone_dataset::Result r;
+    r.sums.assign(n, 0.0);
+    r.ods.assign(n, NAN);
+    r.rc = scicone_batch_compute_t_prime_sums(chains, tp, n, r.sums.data(), r.ods.data());
+    if (r.rc && r.rc != -4) return r.rc;
+    *ticket = ds->next_ticket++;
+    ds->results[*ticket] = r;
+    return 0;
+}
+int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* sums, double* ods) {
+    auto it = ds->results.find(ticket);
+    if (it == ds->results.end()) return fail(-3, "unknown ticket");
+    for (size_t i = 0; i < it->second.sums.size(); ++i) {
+        sums[i] = it->second.sums[i];
+        if (ods) ods[i] = it->second.ods[i];
+    }
+    int rc = it->second.rc;
+    ds->results.erase(it);
+    return rc ? fail(rc, "NaN aggregate") : 0;
+}
 int scicone_set_profiling(scicone_dataset*, int32_t) { return 0; }
 int scicone_last_kernel_time_us(scicone_dataset*, double* us) { *us = 0; return 0; }
 int scicone_kernel_time_stats(scicone_dataset*, double* s, uint64_t* n, int32_t) { if (s) *s = 0; if (n) *n = 0; return 0; }
 int scicone_build_time_stats(scicone_dataset*, double* s, uint64_t* n) { if (s) *s = 0; if (n) *n = 0; return 0; }
 int scicone_kernel_launches(scicone_dataset*, uint64_t* n) { *n = 0; return 0; }
+int scicone_parallel_for(int32_t n, void (*fn)(int32_t, void*), void* ctx) { scicone::ForkJoinPool::instance().run(n, fn, ctx); return 0; }
+int scicone_host_threads(void) { return scicone::ForkJoinPool::instance().n_threads(); }
 int scicone_counters(scicone_dataset*, double out[4], int32_t) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
 int scicone_region_mark(scicone_dataset*, int32_t) { return 0; }
 int scicone_region_elapsed_ms(scicone_dataset*, double* ms) { *ms = 0; return 0; }

@@ -34,6 +34,9 @@ constexpr int kCells = 64;          // cells per CTA of the proposal kernel
 constexpr int kLanes = 4;           // task lanes per cell
 constexpr int kThreads = kCells * kLanes;
 constexpr int kTaskChunk = 32;      // tasks staged in shared memory at a time
+constexpr int kEvStage = 96;        // event records staged with them (the rest is read from global memory)
+constexpr int kExtSlots = 8;        // parent scores from outside a chunk that are prefetched into shared memory
+constexpr int kMaxOdSlices = kTaskChunk;  // region slices of a root score (buffered in the task arrays)
 constexpr int kCtasPerChunk = 16;   // 16 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
 constexpr int kBuildBlock = 256;    // cells per CTA of the build kernel
 constexpr int kPad = 256;           // row padding (cells)
@@ -58,17 +61,22 @@ struct alignas(16) DevTask {
     const double* parent_row;  // where the parent's score lives in global memory (committed row, or the primed row)
     double lg_nz, lg_nzp;      // OD: lgamma(nu*z), lgamma(nu*z_parent);  non-OD: log(z), log(z_parent)
     double nz, nzp;            // OD: nu*z, nu*z_parent
-    int ev_begin, ev_end;
+    int ev_begin;              // first event record
     int node_id;
+    unsigned short n_ev;       // number of event records (Node::c_change entries)
     short parent_task;         // task index of the parent inside this proposal, -1: the parent is not rescored before
-    unsigned short flags;
+    signed char ext_slot;      // parent score comes from outside this task chunk: shared-memory slot it is fetched into (-1: none)
+    unsigned char flags;
+    short pad;
 };
+static_assert(sizeof(DevTask) == 64, "DevTask is staged as four 16-byte pieces");
 
 struct alignas(16) DevEvent {
     const double* row;  // OD: delta row;  non-OD: Dt[k]
     double a, b;        // OD: lgamma((nu*cn)*r) of node / parent;  non-OD: a = log(cn_node) - log(cn_parent)
     double pad;
 };
+static_assert(sizeof(DevEvent) == 32, "DevEvent is staged as two 16-byte pieces");
 
 struct alignas(16) DevUnch {
     const double* row;
@@ -212,12 +220,32 @@ __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned 
 
 // ---------------------------------------------------------------------------------
 // K2-K4: grid = (ceil(M / kCells), n_proposals).  The arena starts with one 32-bit blob offset per proposal.
-// Thread t owns cell (t % kCells) of the tile and task lane (t / kCells).
+// Thread t owns cell (t % kCells) of the tile and task lane (t / kCells); warps are uniform in the lane.
+//
+// Per chunk of kTaskChunk tasks:   stage   task + event records -> shared memory (one coalesced 16-byte copy per thread)
+//                                  A1      4 lanes: lgamma(S + nu z) of each staged task; scores of parents that were
+//                                          rescored outside this chunk (or are committed rows) fetched into shared memory
+//                                  A2      4 lanes: increment score(node) - score(parent): delta-row gathers (issued
+//                                          together, then added in the reference's order) + z-terms
+//                                  B       lane 0: one add per node along parent -> child, rows written, running max / LSE
+// then                             C       aggregate: the rescan of the unchanged rows (max scoring) is split over the
+//                                          4 lanes and skipped by warps in which no cell needs it
+//                                  D       root score from its region slices (nu proposals)
+//                                  reduce  aggregate * cluster_size -> CTA partial -> fixed-order chunk / grand totals
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) score_proposals_kernel(const unsigned char* __restrict__ arena) {
-    __shared__ double sm_g[kTaskChunk][kCells];    // lgamma(S + nu*z) of the staged tasks
+__device__ __forceinline__ void copy16(void* dst, const void* src) {
+    *reinterpret_cast<int4*>(dst) = __ldg(reinterpret_cast<const int4*>(src));
+}
+
+__global__ void __launch_bounds__(kThreads, 4) score_proposals_kernel(const unsigned char* __restrict__ arena) {
+    __shared__ double sm_g[kTaskChunk][kCells];    // lgamma(S + nu*z) of the staged tasks; later: slices / rescan buffers
     __shared__ double sm_sc[kTaskChunk][kCells];   // increments, then scores
+    __shared__ double sm_ps[kExtSlots][kCells];    // scores of parents outside the chunk
     __shared__ double red_buf[kThreads];
+    __shared__ __align__(16) DevTask sm_task[kTaskChunk];
+    __shared__ __align__(16) DevEvent sm_ev[kEvStage];
+    __shared__ int sm_uid[kLanes][kCells];
+    __shared__ unsigned char sm_need[kCells];
 
     const unsigned* blob_off = reinterpret_cast<const unsigned*>(arena);
     const unsigned char* blob = arena + blob_off[blockIdx.y];
@@ -242,58 +270,106 @@ __global__ void __launch_bounds__(kThreads) score_proposals_kernel(const unsigne
     int new_id = 0;             // its node id (lowest id among equals = first in ascending-id order)
     double new_sumexp = 0.0;    // sum mode: sum_i exp(v_i - new_max)
     bool prev_in_new = (pflags & PROP_FULL) != 0;
-    const int pm = (owner && (pflags & PROP_MAX) && !(pflags & PROP_FULL)) ? H.maxid_old[j] : -1;
+    const bool incremental = owner && !(pflags & (PROP_FULL | PROP_OD_ONLY));
+    const int pm = (incremental && (pflags & PROP_MAX)) ? H.maxid_old[j] : -1;
+    const double agg_old = incremental ? H.sums_old[j] : 0.0;  // fetched now, needed in phase C
 
     for (int c0 = 0; c0 < n_tasks; c0 += kTaskChunk) {
         const int c1 = min(c0 + kTaskChunk, n_tasks);
-        // ---- A1: z-terms of the staged tasks
-        if (od && live)
-            for (int t = c0 + lane; t < c1; t += kLanes) sm_g[t - c0][cell] = lgam(S + tasks[t].nz);
+        const int nt = c1 - c0;
+        // ---- stage the task and event records of this chunk
+        const int e_base = tasks[c0].ev_begin;
+        const int e_stop = tasks[c1 - 1].ev_begin + tasks[c1 - 1].n_ev;
+        const int n_stage = min(e_stop - e_base, kEvStage);
+        if ((int)threadIdx.x < nt * 4)
+            copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * threadIdx.x,
+                   reinterpret_cast<const unsigned char*>(tasks + c0) + 16 * threadIdx.x);
+        if ((int)threadIdx.x < n_stage * 2)
+            copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * threadIdx.x,
+                   reinterpret_cast<const unsigned char*>(events + e_base) + 16 * threadIdx.x);
+        __syncthreads();
+        // ---- A1: z-terms of the staged tasks; parent scores that do not come from this chunk
+        if (live)
+            for (int t = lane; t < nt; t += kLanes) {
+                const DevTask& tk = sm_task[t];
+                if (od) sm_g[t][cell] = lgam(S + tk.nz);
+                if (tk.ext_slot >= 0) sm_ps[tk.ext_slot][cell] = __ldcg(tk.parent_row + j);
+            }
         __syncthreads();
         // ---- A2: increments  score(node) - score(parent)   (Tree::compute_score, Tree.h:177-238)
         if (live)
-            for (int t = c0 + lane; t < c1; t += kLanes) {
-                const DevTask& tk = tasks[t];
+            for (int t = lane; t < nt; t += kLanes) {
+                const DevTask& tk = sm_task[t];
                 double x = 0.0;
                 if (!(tk.flags & TASK_ROOT)) {
-                    const int e0 = tk.ev_begin, e1 = tk.ev_end;
+                    const int e0 = tk.ev_begin - e_base, ne = tk.n_ev;
+                    // the first four gathers are issued together; they are added in event order below
+                    double d[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int e = e0 + q;
+                        d[q] = 0.0;
+                        if (q < ne) {
+                            const double* row = (e < kEvStage) ? sm_ev[e].row : events[e_base + e].row;
+                            d[q] = __ldg(row + j);
+                        }
+                    }
                     if (od) {
-                        for (int e = e0; e < e1; ++e) {
-                            const DevEvent& ev = events[e];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < ne) {
+                                const int e = e0 + q;
+                                const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
+                                x += d[q];
+                                x -= ev.a;
+                                x += ev.b;
+                            }
+                        for (int q = 4; q < ne; ++q) {
+                            const int e = e0 + q;
+                            const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
                             x += __ldg(ev.row + j);
                             x -= ev.a;
                             x += ev.b;
                         }
                         x += tk.lg_nz;
                         x -= tk.lg_nzp;
-                        x -= sm_g[t - c0][cell];
+                        x -= sm_g[t][cell];
                         const int pt = tk.parent_task;
                         x += ((tk.flags & TASK_REUSE_G) && pt >= c0) ? sm_g[pt - c0][cell] : lgam(S + tk.nzp);
                     } else {
-                        for (int e = e0; e < e1; ++e) {
-                            const DevEvent& ev = events[e];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < ne) {
+                                const int e = e0 + q;
+                                const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
+                                x += d[q] * ev.a;
+                            }
+                        for (int q = 4; q < ne; ++q) {
+                            const int e = e0 + q;
+                            const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
                             x += __ldg(ev.row + j) * ev.a;
                         }
                         x -= S * tk.lg_nz;
                         x += S * tk.lg_nzp;
                     }
                 }
-                sm_sc[t - c0][cell] = x;
+                sm_sc[t][cell] = x;
             }
         __syncthreads();
         // ---- B: scan parent-before-child (Tree::compute_stack, Tree.h:260-286) and fold into the aggregate
         if (owner)
-            for (int t = c0; t < c1; ++t) {
-                const DevTask& tk = tasks[t];
+            for (int t = 0; t < nt; ++t) {
+                const DevTask& tk = sm_task[t];
                 double sc;
                 if (tk.flags & TASK_ROOT)
                     sc = 0.0;
                 else {
                     const int pt = tk.parent_task;
-                    const double ps = (pt >= c0) ? sm_sc[pt - c0][cell] : tk.parent_row[j];
-                    sc = ps + sm_sc[t - c0][cell];
+                    const double ps = (pt >= c0) ? sm_sc[pt - c0][cell]
+                                                 : (tk.ext_slot >= 0 ? sm_ps[tk.ext_slot][cell] : __ldcg(tk.parent_row + j));
+                    sc = ps + sm_sc[t][cell];
                 }
-                sm_sc[t - c0][cell] = sc;
+                sm_sc[t][cell] = sc;
                 tk.dst[j] = sc;
                 if (tk.flags & TASK_SKIP_AGG) continue;
                 const int id = tk.node_id;
@@ -315,49 +391,87 @@ __global__ void __launch_bounds__(kThreads) score_proposals_kernel(const unsigne
     }
 
     double contrib = 0.0, contrib_od = 0.0;
-    if (owner && !(pflags & PROP_OD_ONLY)) {
+    if (!(pflags & PROP_OD_ONLY)) {
         // ---- per-cell aggregate: Inference::compute_t_prime_sums ----
         const int n_unch = H.n_unch;
-        double res;
         if (pflags & PROP_MAX) {  // Inference.h:1086-1152
-            int prev_id = pm;
-            double prev_val = (pflags & PROP_FULL) ? 0.0 : H.sums_old[j];
-            if (prev_in_new || pm == H.deleted_id) {
-                double cur = -DBL_MAX;
-                int uid = 0;
-                double uval = 0.0;  // value-initialised std::pair when nothing is unchanged
-                for (int u = 0; u < n_unch; ++u) {
-                    const double v = unch[u].row[j];
-                    if (v > cur) {
-                        uid = unch[u].id;
-                        uval = v;
-                        cur = v;
+            // The unchanged rows are rescanned only for cells whose previous argmax was rescored or deleted.  The scan is
+            // split over the 4 lanes (contiguous index ranges, so "first maximum in ascending id order" is kept by
+            // merging the lanes in order with a strict comparison) and skipped by warps where no cell needs it.
+            const bool want = owner && n_unch > 0 && (prev_in_new || pm == H.deleted_id);
+            if (lane == 0) sm_need[cell] = want ? 1 : 0;
+            __syncthreads();
+            const bool need = sm_need[cell] != 0;
+            double cur = -DBL_MAX;
+            int uid = 0;
+            if (__any_sync(0xffffffffu, need)) {
+                const int per = (n_unch + kLanes - 1) / kLanes;
+                const int u0 = lane * per, u1 = min(n_unch, u0 + per);
+                if (need) {
+                    int u = u0;
+                    for (; u + 4 <= u1; u += 4) {
+                        double v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[q] = __ldcg(unch[u + q].row + j);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (v[q] > cur) {
+                                cur = v[q];
+                                uid = unch[u + q].id;
+                            }
+                    }
+                    for (; u < u1; ++u) {
+                        const double v = __ldcg(unch[u].row + j);
+                        if (v > cur) {
+                            cur = v;
+                            uid = unch[u].id;
+                        }
                     }
                 }
-                prev_id = uid;
-                prev_val = uval;
             }
-            res = new_max;
-            int rid = new_id;
-            if (prev_val > new_max) {
-                res = prev_val;
-                rid = prev_id;
+            sm_g[lane][cell] = cur;
+            sm_uid[lane][cell] = uid;
+            __syncthreads();
+            if (owner) {
+                int prev_id = pm;
+                double prev_val = agg_old;
+                if (prev_in_new || pm == H.deleted_id) {
+                    double best = -DBL_MAX;
+                    int bid = 0;
+#pragma unroll
+                    for (int l = 0; l < kLanes; ++l)
+                        if (sm_g[l][cell] > best) {
+                            best = sm_g[l][cell];
+                            bid = sm_uid[l][cell];
+                        }
+                    prev_id = bid;
+                    prev_val = best > -DBL_MAX ? best : 0.0;  // value-initialised std::pair when nothing is unchanged
+                }
+                double res = new_max;
+                int rid = new_id;
+                if (prev_val > new_max) {
+                    res = prev_val;
+                    rid = prev_id;
+                }
+                H.maxid_new[j] = rid;
+                if (res != res) atomicOr(H.status, 1u);
+                H.sums_new[j] = res;
+                contrib = res * (double)H.w[j];
             }
-            H.maxid_new[j] = rid;
-        } else {  // MathOp::log_replace_sum, MathOp.cpp:307-361
+        } else if (owner) {  // MathOp::log_replace_sum, MathOp.cpp:307-361
             bool scratch = (pflags & (PROP_SCRATCH | PROP_FULL)) != 0;
             double sub = 0.0;
             if (!scratch) {  // incremental branch: take the old values out of the old sum
-                const double sum_old = H.sums_old[j];
+                const double sum_old = agg_old;
                 const int n_old = H.n_old;
                 double mx = sum_old;
                 for (int o = 0; o < n_old; ++o) {
-                    const double v = old_rows[o][j];
+                    const double v = __ldcg(old_rows[o] + j);
                     if (v > mx) mx = v;
                 }
                 double s = 0.0;
                 s += exp(sum_old - mx);
-                for (int o = 0; o < n_old; ++o) s -= exp(old_rows[o][j] - mx);
+                for (int o = 0; o < n_old; ++o) s -= exp(__ldcg(old_rows[o] + j) - mx);
                 if (s <= 1e-6)
                     scratch = true;  // possible precision loss: recompute from every node
                 else
@@ -366,41 +480,48 @@ __global__ void __launch_bounds__(kThreads) score_proposals_kernel(const unsigne
             double mx = new_max;
             if (scratch) {
                 for (int u = 0; u < n_unch; ++u) {
-                    const double v = unch[u].row[j];
+                    const double v = __ldcg(unch[u].row + j);
                     if (v > mx) mx = v;
                 }
             } else if (sub > mx)
                 mx = sub;
             double s = new_sumexp * exp(new_max - mx);
             if (scratch) {
-                for (int u = 0; u < n_unch; ++u) s += exp(unch[u].row[j] - mx);
+                for (int u = 0; u < n_unch; ++u) s += exp(__ldcg(unch[u].row + j) - mx);
             } else
                 s += exp(sub - mx);
-            res = log(s) + mx;
+            const double res = log(s) + mx;
+            if (res != res) atomicOr(H.status, 1u);
+            H.sums_new[j] = res;
+            contrib = res * (double)H.w[j];
         }
-        if (res != res) atomicOr(H.status, 1u);
-        H.sums_new[j] = res;
-        contrib = res * (double)H.w[j];
     }
-    if (owner && (pflags & PROP_WITH_OD)) {
-        // Tree::get_od_root_score (Tree.h:1774-1810) from the region slices K1 prepared;
-        // Inference::compute_t_prime_od_scores, Inference.h:1421-1433
+    if (pflags & PROP_WITH_OD) {  // uniform per proposal
+        // Tree::get_od_root_score (Tree.h:1774-1810) from the region slices K1 prepared (fetched by the 4 lanes, added
+        // in slice order by the owner); Inference::compute_t_prime_od_scores, Inference.h:1421-1433
         const double* const* slices = reinterpret_cast<const double* const*>(blob + H.off_od_rows);
-        double v = 0.0;
-        if (od) {
-            v += H.od_lg_nz;
-            v -= lgam(S + H.od_nz);
-        } else
-            v += -S * H.od_lg_nz;
-        for (int s = 0; s < H.n_od_slices; ++s) v += slices[s][j];
-        contrib_od = v * (double)H.w[j];
+        const int ns = H.n_od_slices;  // <= kTaskChunk
+        __syncthreads();
+        if (live)
+            for (int s = lane; s < ns; s += kLanes) sm_g[s][cell] = __ldcg(slices[s] + j);
+        __syncthreads();
+        if (owner) {
+            double v = 0.0;
+            if (od) {
+                v += H.od_lg_nz;
+                v -= lgam(S + H.od_nz);
+            } else
+                v += -S * H.od_lg_nz;
+            for (int s = 0; s < ns; ++s) v += sm_g[s][cell];
+            contrib_od = v * (double)H.w[j];
+        }
     }
     // ---- weighted sum over cells: Inference::comparison, Inference.h:292-294 ----
     __syncthreads();
     const double cta_sum = block_sum(contrib, red_buf);
     __syncthreads();
     double cta_od = 0.0;
-    if (pflags & PROP_WITH_OD) {  // uniform per proposal
+    if (pflags & PROP_WITH_OD) {
         cta_od = block_sum(contrib_od, red_buf);
         __syncthreads();
     }

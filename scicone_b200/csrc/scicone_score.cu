@@ -17,6 +17,7 @@
 // compute entry point fails with SCICONE_ERR_CUDA.
 #include "../../include/scicone_score.h"
 #include "kernels.cuh"
+#include "parallel_for.hpp"
 
 #include <dlfcn.h>
 
@@ -26,6 +27,8 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <numeric>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -91,16 +94,21 @@ struct RowPool {
     std::vector<double*> free_rows;
     std::vector<void*> slabs;
     size_t n_rows = 0;
+    int device = 0;
+    std::mutex mu;  // chains of one dataset may be compiled / committed from several host threads
 
-    void init(size_t mp) {
+    void init(size_t mp, int dev) {
+        device = dev;
         Mp = mp;
         const size_t row_bytes = Mp * sizeof(double);
         rows_per_slab = std::max<size_t>(8, std::min<size_t>(512, (size_t(64) << 20) / row_bytes));
     }
     cudaError_t get(double** out) {
+        std::lock_guard<std::mutex> lk(mu);
         if (free_rows.empty()) {
             void* p = nullptr;
-            cudaError_t e = cudaMalloc(&p, rows_per_slab * Mp * sizeof(double));
+            cudaError_t e = cudaSetDevice(device);  // the calling thread may be a pool worker
+            if (e == cudaSuccess) e = cudaMalloc(&p, rows_per_slab * Mp * sizeof(double));
             if (e != cudaSuccess) return e;
             slabs.push_back(p);
             for (size_t i = rows_per_slab; i-- > 0;) free_rows.push_back(static_cast<double*>(p) + i * Mp);
@@ -111,7 +119,9 @@ struct RowPool {
         return cudaSuccess;
     }
     void put(double* r) {
-        if (r) free_rows.push_back(r);
+        if (!r) return;
+        std::lock_guard<std::mutex> lk(mu);
+        free_rows.push_back(r);
     }
     void destroy() {
         for (void* p : slabs) cudaFree(p);
@@ -340,6 +350,7 @@ struct scicone_chain {
     std::vector<double> build_aux;
     std::vector<double*> temp_rows;
     double alg_bytes = 0.0, n_scores = 0.0;
+    double cost = 0.0;  // relative device time of the compiled proposal (orders the blobs inside a launch)
 };
 
 namespace {
@@ -387,7 +398,7 @@ size_t blob_append(std::vector<unsigned char>& b, const std::vector<T>& v) {
     return off;
 }
 
-constexpr int kOdSlices = 8;
+constexpr int kOdRegionsPerSlice = 6;  // 200 regions -> 32 slices: enough CTAs for one nu proposal to fill the GPU
 
 // Root-score request (Tree::get_od_root_score, Tree.h:1774-1810): K1 items that reduce slices of the regions
 // into temporary rows; the proposal kernel adds the slices and the two cell-level terms.
@@ -412,7 +423,7 @@ int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const
             cc[k] = 0.0;
         }
     }
-    const int n_slices = std::min(kOdSlices, K);
+    const int n_slices = std::max(1, std::min(kMaxOdSlices, K / kOdRegionsPerSlice));
     for (int s = 0; s < n_slices; ++s) {
         double* row = nullptr;
         CUDA_TRY(ds->pool.get(&row));
@@ -487,7 +498,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             memset(&tk, 0, sizeof tk);
             tk.node_id = id;
             tk.parent_task = -1;
-            tk.ev_begin = tk.ev_end = (int)events.size();
+            tk.ext_slot = -1;
+            tk.ev_begin = (int)events.size();
             int z_int;
             if (pidx < 0) {  // Tree::compute_root_score, Tree.h:145-160
                 tk.flags = TASK_ROOT;
@@ -555,7 +567,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     }
                     events.push_back(ev);
                 }
-                tk.ev_end = (int)events.size();
+                if (events.size() - (size_t)tk.ev_begin > 65535) return fail(SCICONE_ERR_ARG, "more than 65535 events in one node");
+                tk.n_ev = (unsigned short)(events.size() - (size_t)tk.ev_begin);
                 if (od) {  // Tree.h:227-231
                     tk.nz = nu * zd;
                     tk.nzp = nu * zp;
@@ -589,6 +602,12 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         for (size_t i = 0; i < tasks.size(); ++i) last[tasks[i].node_id] = (int)i;
         for (size_t i = 0; i < tasks.size(); ++i)
             if (last[tasks[i].node_id] != (int)i) tasks[i].flags |= TASK_SKIP_AGG;
+    }
+    // parents whose score does not come out of the same task chunk are fetched into shared memory ahead of the scan
+    for (size_t c0 = 0; c0 < tasks.size(); c0 += kTaskChunk) {
+        int used = 0;
+        for (size_t i = c0; i < std::min(tasks.size(), c0 + kTaskChunk); ++i)
+            if (!(tasks[i].flags & TASK_ROOT) && tasks[i].parent_task < (int)c0 && used < kExtSlots) tasks[i].ext_slot = (signed char)used++;
     }
     std::vector<const double*> old_rows;
     std::vector<DevUnch> unch;
@@ -630,6 +649,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         const double n_table = full ? (double)ch->p.size() : (double)(unch.size() + ch->p.size());
         ch->alg_bytes = (double)ds->M * (16.0 * tasks.size() + 8.0 * events.size() + 8.0 * n_table + 12.0);
         ch->n_scores = (double)ds->M * tasks.size();
+        ch->cost = 4.0 * tasks.size() + events.size() + (full ? 0.0 : 0.5 * unch.size());
     }
     // a proposal that changes nu also needs Inference::compute_t_prime_od_scores (Inference.h:942): evaluated by
     // the same launch unless the caller already asked for it separately
@@ -699,9 +719,17 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     g.with_od.assign(n, 0);
     unsigned* offs = reinterpret_cast<unsigned*>(g.h_arena);
     size_t at = head, item_at = off_items, aux_at = off_aux;
+    // grid.y order = longest proposal first (CTAs are dispatched in block-id order): the heavy full-tree
+    // rescorings of nu proposals start at once and the short ones fill in behind them.  Results are addressed by
+    // the slot pointers inside each header, so the order of the blobs is free.
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return chains[a]->cost > chains[b]->cost; });
+    for (int q = 0; q < n; ++q) offs[q] = 0;
+    std::vector<unsigned> blob_at(n);
     for (int i = 0; i < n; ++i) {
         scicone_chain* ch = chains[i];
-        offs[i] = (unsigned)at;
+        blob_at[i] = (unsigned)at;
         memcpy(g.h_arena + at, ch->blob.data(), ch->blob.size());
         at += ch->blob.size();
         if (!ch->build_aux.empty()) memcpy(g.h_arena + aux_at, ch->build_aux.data(), ch->build_aux.size() * sizeof(double));
@@ -716,6 +744,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         }
         aux_at += round_up(ch->build_aux.size() * sizeof(double), 16);
     }
+    for (int q = 0; q < n; ++q) offs[q] = blob_at[order[q]];
     CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, ds->stream));
@@ -901,7 +930,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     }
     ds->n_cta = (ds->M + kCells - 1) / kCells;
     ds->n_chunks = (ds->n_cta + kCtasPerChunk - 1) / kCtasPerChunk;
-    ds->pool.init(ds->Mp);
+    ds->pool.init(ds->Mp, ds->device);
     auto cleanup = [&](int rc) {
         scicone_dataset_destroy(ds);
         return rc;
@@ -1088,12 +1117,23 @@ int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const
     if (rc) return rc;
     rc = ds->ensure_slots(n);
     if (rc) return rc;
-    for (int i = 0; i < n; ++i) {
-        rc = compile_proposal(chains[i], i, false);
-        if (rc) {
-            for (int q = 0; q <= i; ++q) drop_pending(chains[q]);
-            return rc;
-        }
+    {   // the blobs of the n proposals are independent: compile them on the pool (the row pool is locked inside)
+        struct Job {
+            scicone_chain* const* chains;
+            std::vector<int> rc;
+            std::vector<std::string> msg;
+        } job{chains, std::vector<int>(n, 0), std::vector<std::string>(n)};
+        scicone::ForkJoinPool::instance().run(n, [](int i, void* ctx) {
+            Job& j = *static_cast<Job*>(ctx);
+            j.rc[i] = compile_proposal(j.chains[i], i, false);
+            if (j.rc[i]) j.msg[i] = g_err;  // thread-local in the worker
+        }, &job);
+        for (int i = 0; i < n; ++i)
+            if (job.rc[i]) {
+                for (int q = 0; q < n; ++q) drop_pending(chains[q]);
+                g_err = job.msg[i];
+                return job.rc[i];
+            }
     }
     unsigned long long tk = 0;
     rc = submit_proposals(ds, chains, n, &tk);
@@ -1277,6 +1317,13 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
     if (e != cudaSuccess) return fail(SCICONE_ERR_CUDA, "assign_cells_to_nodes: %s", cudaGetErrorString(e));
     return SCICONE_OK;
 }
+
+int scicone_parallel_for(int32_t n, void (*fn)(int32_t index, void* ctx), void* ctx) {
+    if (n < 0 || !fn) return fail(SCICONE_ERR_ARG, "parallel_for: bad argument");
+    scicone::ForkJoinPool::instance().run(n, fn, ctx);
+    return SCICONE_OK;
+}
+int scicone_host_threads(void) { return scicone::ForkJoinPool::instance().n_threads(); }
 
 int scicone_comm_unique_id(uint8_t out[128]) {
     if (!out) return fail(SCICONE_ERR_ARG, "null argument");

@@ -15,7 +15,9 @@
 #include <chrono>
 #include <cstring>
 #include <iostream>
+#include <exception>
 #include <memory>
+#include <mutex>
 
 #include "../../include/scicone_score.h"
 #include "tree.hpp"
@@ -77,6 +79,7 @@ public:
     int ploidy;
     bool max_scoring;
     std::vector<int> region_neutral_states;
+    scicone_dataset* ds = nullptr;
     scicone_chain* chain = nullptr;
     FlatTree flat;
 
@@ -105,7 +108,10 @@ public:
     ~Inference() {
         if (chain) scicone_chain_destroy(chain);
     }
-    void attach_chain(scicone_dataset* ds) { abi_check(scicone_chain_create(&chain, ds)); }
+    void attach_chain(scicone_dataset* dataset) {
+        ds = dataset;
+        abi_check(scicone_chain_create(&chain, ds));
+    }
 
     // ---- initial tree (Inference::random_initialize, Inference.h:99-156) ------------------------------------------
     void random_initialize(unsigned n_nodes, int max_iters, int max_regions_per_node = 1) {
@@ -442,41 +448,120 @@ public:
     }
 };
 
-// Advance `chains` (all on one dataset) by n_iters iterations in lock-step: one launch per step.
-inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit) {
+// fn(i) for i in [0, n) on the scoring library's worker pool; the first exception is rethrown on the caller.
+template <class F>
+inline void parallel_chains(int n, F&& fn) {
+    struct Ctx {
+        F* fn;
+        std::exception_ptr err;
+        std::mutex mu;
+    } ctx{&fn, nullptr, {}};
+    abi_check(scicone_parallel_for(n, [](int32_t i, void* p) {
+        Ctx& c = *static_cast<Ctx*>(p);
+        try {
+            (*c.fn)(i);
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(c.mu);
+            if (!c.err) c.err = std::current_exception();
+        }
+    }, &ctx));
+    if (ctx.err) std::rethrow_exception(ctx.err);
+}
+
+// Advance `chains` (all on one dataset) by n_iters iterations.  The chains are split into `n_groups` groups (default:
+// two when there are at least 8 chains); a group moves in lock-step - its chains draw and queue their proposals in
+// parallel on the host pool, ONE kernel launch scores them all, then they accept / reject in parallel - and while the
+// launch of one group is in flight the host works on the other group.  Every chain still sees exactly the sequence
+// propose -> score -> compare of the reference's loop (Inference::infer_mcmc, Inference.h:518-913), so its trajectory
+// does not depend on the grouping or on the number of threads.
+struct HostPhaseTimes {  // wall time of the driver thread per phase, microseconds (for --stats_file)
+    double propose_us = 0, submit_us = 0, wait_us = 0, finish_us = 0;
+};
+
+inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
+                       int n_groups = 0, HostPhaseTimes* times = nullptr) {
+    typedef std::chrono::steady_clock Clock;
+    auto us_since = [](Clock::time_point t0) { return std::chrono::duration<double, std::micro>(Clock::now() - t0).count(); };
+    HostPhaseTimes local_times;
+    HostPhaseTimes& T = times ? *times : local_times;
     const int B = static_cast<int>(chains.size());
-    for (Inference* c : chains) {
-        c->best_tree.copy_from(c->t);  // Inference.h:540
-        c->open_traces(n_iters);
+    if (B == 0 || n_iters <= 0) return;
+    scicone_dataset* ds = chains[0]->ds;
+    int G = n_groups > 0 ? n_groups : (B >= 8 ? 2 : 1);
+    if (G > B) G = B;
+    if (G > 4) G = 4;  // the library keeps at most 8 launches in flight
+    parallel_chains(B, [&](int b) {
+        chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
+        chains[b]->open_traces(n_iters);
+    });
+    struct Group {
+        std::vector<int> members;
+        std::vector<char> scored;
+        std::vector<scicone_chain*> handles;
+        std::vector<int> who;  // member position of each handle
+        std::vector<double> totals, ods, tot_m, od_m;
+        uint64_t ticket = 0;
+        bool in_flight = false;
+    };
+    std::vector<Group> groups(G);
+    for (int g = 0; g < G; ++g) {
+        for (int b = static_cast<int>(static_cast<long long>(B) * g / G); b < static_cast<int>(static_cast<long long>(B) * (g + 1) / G); ++b)
+            groups[g].members.push_back(b);
+        const size_t n = groups[g].members.size();
+        groups[g].scored.assign(n, 0);
+        groups[g].totals.assign(n, 0.0);
+        groups[g].ods.assign(n, 0.0);
+        groups[g].tot_m.assign(n, 0.0);
+        groups[g].od_m.assign(n, 0.0);
     }
-    std::vector<scicone_chain*> handles;
-    std::vector<int> who;
-    std::vector<double> totals(B), ods(B);
-    std::vector<char> scored(B);
-    for (int it = 0; it < n_iters; ++it) {
-        handles.clear();
-        who.clear();
-        for (int b = 0; b < B; ++b) {
-            scored[b] = chains[b]->propose(move_probs, size_limit);
-            if (scored[b]) {
-                handles.push_back(chains[b]->chain);
-                who.push_back(b);
+    auto propose_group = [&](Group& g) {
+        const int n = static_cast<int>(g.members.size());
+        Clock::time_point t0 = Clock::now();
+        parallel_chains(n, [&](int i) { g.scored[i] = chains[g.members[i]]->propose(move_probs, size_limit) ? 1 : 0; });
+        T.propose_us += us_since(t0);
+        t0 = Clock::now();
+        g.handles.clear();
+        g.who.clear();
+        for (int i = 0; i < n; ++i)
+            if (g.scored[i]) {
+                g.handles.push_back(chains[g.members[i]]->chain);
+                g.who.push_back(i);
             }
-        }
-        if (!handles.empty()) {
-            int rc = scicone_batch_compute_t_prime_sums(handles.data(), nullptr, static_cast<int32_t>(handles.size()), totals.data(), ods.data());
+        g.in_flight = !g.handles.empty();
+        if (g.in_flight) abi_check(scicone_batch_submit(g.handles.data(), nullptr, static_cast<int32_t>(g.handles.size()), &g.ticket));
+        T.submit_us += us_since(t0);
+    };
+    auto finish_group = [&](Group& g, int it) {
+        const int n = static_cast<int>(g.members.size());
+        Clock::time_point t0 = Clock::now();
+        if (g.in_flight) {
+            int rc = scicone_batch_wait(ds, g.ticket, g.totals.data(), g.ods.data());
             if (rc != SCICONE_OK && rc != SCICONE_ERR_NAN) abi_check(rc);
+            g.in_flight = false;
         }
-        std::vector<double> tot_b(B, 0.0), od_b(B, 0.0);
-        for (size_t i = 0; i < who.size(); ++i) {
-            tot_b[who[i]] = totals[i];
-            od_b[who[i]] = ods[i];
-            int32_t nr = 0;
-            scicone_t_prime_n_rescored(chains[who[i]]->chain, &nr);
-            chains[who[i]]->rescored_last = static_cast<unsigned>(nr);
+        T.wait_us += us_since(t0);
+        t0 = Clock::now();
+        for (size_t h = 0; h < g.who.size(); ++h) {
+            g.tot_m[g.who[h]] = g.totals[h];
+            g.od_m[g.who[h]] = g.ods[h];
         }
-        for (int b = 0; b < B; ++b) chains[b]->finish(scored[b], tot_b[b], od_b[b], it);
-    }
+        parallel_chains(n, [&](int i) {
+            Inference* c = chains[g.members[i]];
+            if (g.scored[i]) {
+                int32_t nr = 0;
+                scicone_t_prime_n_rescored(c->chain, &nr);
+                c->rescored_last = static_cast<unsigned>(nr);
+            }
+            c->finish(g.scored[i] != 0, g.tot_m[i], g.od_m[i], it);
+        });
+        T.finish_us += us_since(t0);
+    };
+    for (int it = 0; it < n_iters; ++it)
+        for (Group& g : groups) {
+            if (it > 0) finish_group(g, it - 1);
+            propose_group(g);
+        }
+    for (Group& g : groups) finish_group(g, n_iters - 1);
 }
 
 }  // namespace scicone_host

@@ -20,6 +20,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <iterator>
+#include <type_traits>
 #include <iomanip>
 #include <limits>
 #include <map>
@@ -38,7 +41,144 @@
 
 namespace scicone_host {
 
-typedef std::map<unsigned, int> EventMap;  // region -> value; ordered like the reference's std::map<u_int,int>
+// Ordered map on a sorted array with inline storage for the first N entries: the event maps of a node hold a handful
+// of regions, and a chain copies its whole tree (every node, three maps each) at least twice per iteration, so a
+// node-per-entry std::map would spend the host's time in malloc.  Iteration order, lookup semantics and comparison are
+// those of std::map (the reference's std::map<u_int,int>), which the move set and the redundancy check rely on.
+template <class K, class V, unsigned N>
+class SmallMap {
+public:
+    typedef std::pair<K, V> value_type;
+    typedef value_type* iterator;
+    typedef const value_type* const_iterator;
+    typedef std::reverse_iterator<const_iterator> const_reverse_iterator;
+
+    SmallMap() {}
+    SmallMap(const SmallMap& o) { assign(o); }
+    SmallMap(SmallMap&& o) noexcept { steal(o); }
+    SmallMap& operator=(const SmallMap& o) {
+        if (this != &o) assign(o);
+        return *this;
+    }
+    SmallMap& operator=(SmallMap&& o) noexcept {
+        if (this != &o) {
+            release();
+            steal(o);
+        }
+        return *this;
+    }
+    ~SmallMap() { release(); }
+
+    iterator begin() { return data(); }
+    iterator end() { return data() + n_; }
+    const_iterator begin() const { return data(); }
+    const_iterator end() const { return data() + n_; }
+    const_reverse_iterator rbegin() const { return const_reverse_iterator(end()); }
+    const_reverse_iterator rend() const { return const_reverse_iterator(begin()); }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    void clear() { n_ = 0; }
+
+    iterator find(const K& k) {
+        iterator it = lower(k);
+        return (it != end() && it->first == k) ? it : end();
+    }
+    const_iterator find(const K& k) const {
+        const_iterator it = const_cast<SmallMap*>(this)->lower(k);
+        return (it != end() && it->first == k) ? it : end();
+    }
+    size_t count(const K& k) const { return find(k) != end() ? 1 : 0; }
+    V& operator[](const K& k) {
+        iterator it = lower(k);
+        if (it != end() && it->first == k) return it->second;
+        const size_t pos = static_cast<size_t>(it - data());
+        grow(n_ + 1);
+        value_type* d = data();
+        std::memmove(static_cast<void*>(d + pos + 1), static_cast<const void*>(d + pos), (n_ - pos) * sizeof(value_type));
+        d[pos] = value_type(k, V());
+        ++n_;
+        return d[pos].second;
+    }
+    V& at(const K& k) {
+        iterator it = find(k);
+        if (it == end()) throw std::out_of_range("map::at");
+        return it->second;
+    }
+    const V& at(const K& k) const {
+        const_iterator it = find(k);
+        if (it == end()) throw std::out_of_range("map::at");
+        return it->second;
+    }
+    iterator erase(iterator it) {
+        std::memmove(static_cast<void*>(it), static_cast<const void*>(it + 1), static_cast<size_t>(end() - (it + 1)) * sizeof(value_type));
+        --n_;
+        return it;
+    }
+    size_t erase(const K& k) {
+        iterator it = find(k);
+        if (it == end()) return 0;
+        erase(it);
+        return 1;
+    }
+    void swap(SmallMap& o) {
+        SmallMap tmp(std::move(o));
+        o = std::move(*this);
+        *this = std::move(tmp);
+    }
+    friend bool operator==(const SmallMap& a, const SmallMap& b) { return a.n_ == b.n_ && std::equal(a.begin(), a.end(), b.begin()); }
+    friend bool operator!=(const SmallMap& a, const SmallMap& b) { return !(a == b); }
+    friend bool operator<(const SmallMap& a, const SmallMap& b) { return std::lexicographical_compare(a.begin(), a.end(), b.begin(), b.end()); }
+
+private:
+    static_assert(std::is_trivially_copy_constructible<K>::value && std::is_trivially_copy_constructible<V>::value &&
+                      std::is_trivially_destructible<K>::value && std::is_trivially_destructible<V>::value,
+                  "entries are moved with memmove");
+    value_type* data() { return heap_ ? heap_ : reinterpret_cast<value_type*>(inline_); }
+    const value_type* data() const { return heap_ ? heap_ : reinterpret_cast<const value_type*>(inline_); }
+    iterator lower(const K& k) {
+        return std::lower_bound(begin(), end(), k, [](const value_type& e, const K& key) { return e.first < key; });
+    }
+    void grow(size_t want) {
+        if (want <= cap_) return;
+        size_t cap = std::max<size_t>(want, 2 * static_cast<size_t>(cap_));
+        value_type* fresh = static_cast<value_type*>(::operator new(cap * sizeof(value_type)));
+        std::memcpy(static_cast<void*>(fresh), static_cast<const void*>(data()), n_ * sizeof(value_type));
+        if (heap_) ::operator delete(heap_);
+        heap_ = fresh;
+        cap_ = static_cast<unsigned>(cap);
+    }
+    void assign(const SmallMap& o) {
+        n_ = 0;
+        grow(o.n_);
+        std::memcpy(static_cast<void*>(data()), static_cast<const void*>(o.data()), o.n_ * sizeof(value_type));
+        n_ = o.n_;
+    }
+    void steal(SmallMap& o) {
+        if (o.heap_) {
+            heap_ = o.heap_;
+            cap_ = o.cap_;
+            o.heap_ = nullptr;
+            o.cap_ = N;
+        } else {
+            heap_ = nullptr;
+            cap_ = N;
+            std::memcpy(static_cast<void*>(inline_), static_cast<const void*>(o.inline_), o.n_ * sizeof(value_type));
+        }
+        n_ = o.n_;
+        o.n_ = 0;
+    }
+    void release() {
+        if (heap_) ::operator delete(heap_);
+        heap_ = nullptr;
+        cap_ = N;
+        n_ = 0;
+    }
+    alignas(value_type) unsigned char inline_[N * sizeof(value_type)];
+    value_type* heap_ = nullptr;
+    unsigned n_ = 0, cap_ = N;
+};
+
+typedef SmallMap<unsigned, int, 8> EventMap;  // region -> value; ordered like the reference's std::map<u_int,int>
 
 // A move that cannot be made on this tree at all: the driver stops retrying (reference: CustomExceptions.h InvalidMove).
 struct InvalidMove : std::exception {
@@ -125,7 +265,7 @@ struct Node {
     int id = 0;
     EventMap c;                   // genotype relative to the neutral state (Node::c)
     mutable EventMap c_change;    // events relative to the parent (Node::c_change)
-    mutable std::map<unsigned, std::pair<int, int>> event_blocks;  // filled by event_prior(), read by expand/shrink
+    mutable SmallMap<unsigned, std::pair<int, int>, 4> event_blocks;  // filled by event_prior(), read by expand/shrink
     unsigned n_desc = 1;          // subtree size including the node (Node::n_descendents); may be stale, as in the reference
     int first_child = -1, next = -1, parent = -1;  // indices into Tree::pool
 };

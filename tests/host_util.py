@@ -50,8 +50,28 @@ def tree_parts(txt):
     return head, lines[7:]
 
 
-def compare_runs(a, b, tol=1e-9):
-    """Identical accepted-move trajectory and final tree, per-move scores within `tol` relative (north_star)."""
+def compare_runs(a, b, tol=1e-9, knife_edge_ok=False):
+    """Identical accepted-move trajectory and final tree, per-move scores within `tol` relative (north_star).
+
+    knife_edge_ok: the reference's accept rule (Inference.h:497-515) draws a uniform only when log_acc <= 0.  After a
+    move that is likelihood-NEUTRAL in exact arithmetic (e.g. swapping two labels no cell is attached to), log_acc is
+    +-(a few ulp of a 4e6-sized total), and the SIGN of that rounding noise decides whether the random stream advances.
+    No two libm's / summation orders agree on that sign, so from such a move on the two hosts may legitimately walk
+    different (equally valid) chains.  With this flag a divergence is tolerated ONLY directly after an accepted move
+    whose score change in the reference is below `tol` relative, and everything before it must still agree; the
+    function then returns ("knife_edge", iteration)."""
+    n = min(a["acc"].size, b["acc"].size)
+    diff = np.nonzero(a["acc"][:n] != b["acc"][:n])[0]
+    if knife_edge_ok and a["acc"].size == b["acc"].size and diff.size:
+        i = int(diff[0])
+        assert i >= 2, "trajectories differ from the start"
+        assert a["acc"][i - 1] >= 0 and b["acc"][i - 1] >= 0, "divergence is not preceded by an accepted move"
+        step = abs(a["chain"][i - 1] - a["chain"][i - 2]) / max(1.0, abs(a["chain"][i - 1]))
+        assert step <= tol, f"trajectories diverge at iteration {i} after a non-neutral move (relative step {step})"
+        rel = float(np.max(np.abs(a["chain"][:i] - b["chain"][:i]) / np.maximum(1.0, np.abs(a["chain"][:i]))))
+        assert rel <= tol, rel
+        assert np.allclose(a["gamma"][:i], b["gamma"][:i], rtol=1e-12)
+        return ("knife_edge", i)
     assert np.array_equal(a["acc"], b["acc"]), "accepted-move trajectories differ"
     rel = float(np.max(np.abs(a["chain"] - b["chain"]) / np.maximum(1.0, np.abs(a["chain"]))))
     assert rel <= tol, rel

@@ -57,12 +57,17 @@ CASES["config2_sum"] = (_config2, ["--n_iters=200", "--n_nodes=20", "--seed=44",
 CASES["cluster_max"] = (_cluster, ["--n_iters=1500", "--n_nodes=5", "--seed=44", "--nu=1.0", "--max_scoring=true"])
 
 
+# the BASELINE.json test configs must be identical end to end; the stress cases (every move enabled, tempering) may end
+# at a likelihood-neutral knife edge on the GPU (see host_util.compare_runs)
+STRICT = {"tutorial_max", "tutorial_sum", "config2_max", "config2_sum", "cluster_max"}
+
+
 def _both(tmp_path, case, env):
     data, extra = CASES[case]
     D, r, w = data()
     a = run_inference(REF, str(tmp_path), "ref", D, r, extra, w=w)
     b = run_inference(NATIVE, str(tmp_path), "new", D, r, extra, w=w, env=env)
-    rel = compare_runs(a, b)
+    rel = compare_runs(a, b, knife_edge_ok=(env is None and case not in STRICT))
     print(case, "accepted", int(np.sum(a["acc"] >= 0)), "of", a["acc"].size, "max rel diff", rel)
     return a, b
 
@@ -95,24 +100,38 @@ def test_tree_file_start_on_cpu(tmp_path):
     compare_runs(a, b)
 
 
-@needs_bins
-@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
-def test_lockstep_chains_equal_single_runs_on_cpu(tmp_path):
-    """--n_chains=3: restarts advanced in lock-step must each equal the single-chain run with seed+c."""
+def _multi_chain(tmp_path, env, n_chains, extra_flags, check):
+    """--n_chains=B: restarts advanced in groups (parallel host, pipelined launches) must each equal the single-chain
+    run of the unmodified reference with seed+c, whatever the grouping and the number of host threads."""
+    import subprocess
+
+    from host_util import read_outputs
+
     D, r = _tutorial()
     base = ["--n_iters=800", "--n_nodes=4", "--nu=1.0", "--max_scoring=true"]
-    import subprocess
-    from host_util import read_outputs
-    # the multi-chain run writes <postfix>_c<k>_* files
     d = os.path.join(str(tmp_path), "d.csv")
     np.savetxt(d, D, delimiter=",", fmt="%.0f")
     rf = os.path.join(str(tmp_path), "r.txt")
     np.savetxt(rf, r, fmt="%d")
-    env = dict(os.environ, **CPU_ENV)
+    e = dict(os.environ)
+    e.update(env or {})
     cmd = [NATIVE, f"--d_matrix_file={d}", f"--region_sizes_file={rf}", f"--n_cells={D.shape[0]}", f"--n_regions={D.shape[1]}",
-           "--verbosity=2", "--postfix=multi", "--seed=20", "--n_chains=3"] + base
-    res = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, env=env, timeout=600)
+           "--verbosity=2", "--postfix=multi", "--seed=20", f"--n_chains={n_chains}"] + base + extra_flags
+    res = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, env=e, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
-    for c in range(3):
+    for c in check:
         single = run_inference(REF, str(tmp_path), f"single{c}", D, r, base + [f"--seed={20 + c}"])
         compare_runs(single, read_outputs(str(tmp_path), f"multi_c{c}"))
+
+
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+@pytest.mark.parametrize("n_chains,flags,threads", [(3, [], "1"), (9, [], "4"), (10, ["--n_groups=3"], "3")])
+def test_multi_chain_equals_single_runs_on_cpu(tmp_path, n_chains, flags, threads):
+    _multi_chain(tmp_path, dict(CPU_ENV, SCICONE_THREADS=threads), n_chains, flags, [0, n_chains // 2, n_chains - 1])
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_multi_chain_equals_single_runs_on_gpu(tmp_path):
+    _multi_chain(tmp_path, None, 12, [], [0, 5, 11])
