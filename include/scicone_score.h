@@ -188,6 +188,12 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
                                   int32_t* cell_region_cn /* [n_cells][n_regions] or NULL */);
 
 /*
+ * Test hook: the device log-gamma used for every data and z term (reference: libm lgamma called from
+ * Tree::compute_score, Tree.h:214-231) evaluated on `n` caller-provided positive arguments.
+ */
+int scicone_test_lgamma(int32_t device, const double* x, int32_t n, double* out);
+
+/*
  * Host-side parallel loop on the library's worker pool: fn(i, ctx) for i in [0, n), returns when all are done.
  * No reference counterpart (the reference is one chain per process: global RNG singleton and `extern` tunables,
  * SURVEY.md section 8b).  The per-chain calls above - scicone_compute_t_prime_scores, scicone_accept,

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "scicone_read_t_prime_scores", "scicone_assign_cells_to_nodes", "scicone_comm_unique_id",
     "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_build_time_stats", "scicone_kernel_launches",
     "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
-    "scicone_parallel_for", "scicone_host_threads",
+    "scicone_parallel_for", "scicone_host_threads", "scicone_test_lgamma",
 ]
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}
@@ -92,6 +92,7 @@ def lib():
         L.scicone_region_mark.argtypes = [vp, C.c_int32]
         L.scicone_region_elapsed_ms.argtypes = [vp, dp]
         L.scicone_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.scicone_test_lgamma.argtypes = [C.c_int32, dp, C.c_int32, dp]
         L.scicone_accept.argtypes = [vp]
         L.scicone_reject.argtypes = [vp]
         L.scicone_t_n_nodes.argtypes = [vp, ip]
@@ -354,3 +355,14 @@ class BatchLauncher:
 
     def run(self):
         return self.wait(self.submit())
+
+
+def device_lgamma(x, device=0):
+    """The engine's device log-gamma on an array of positive arguments (test hook, scicone_test_lgamma)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    L = lib()
+    rc = L.scicone_test_lgamma(int(device), x.ctypes.data_as(C.POINTER(C.c_double)), int(x.size), out.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        raise SciconeError(rc, L.scicone_last_error().decode())
+    return out

@@ -28,16 +28,17 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "lgam_core.h"
+
 namespace scicone {
 
-constexpr int kCells = 64;          // cells per CTA of the proposal kernel
-constexpr int kLanes = 4;           // task lanes per cell
-constexpr int kThreads = kCells * kLanes;
-constexpr int kTaskChunk = 32;      // tasks staged in shared memory at a time
+constexpr int kCells = 128;         // cells per CTA of the proposal kernel: one thread per cell
+constexpr int kThreads = kCells;
+constexpr int kMinCtasPerSm = 8;   // register budget of the proposal kernel: 65536 / (10 * 128) = 51 -> 48 registers
+constexpr int kTaskChunk = 32;      // task records staged in shared memory at a time
 constexpr int kEvStage = 96;        // event records staged with them (the rest is read from global memory)
-constexpr int kExtSlots = 8;        // parent scores from outside a chunk that are prefetched into shared memory
-constexpr int kMaxOdSlices = kTaskChunk;  // region slices of a root score (buffered in the task arrays)
-constexpr int kCtasPerChunk = 16;   // 16 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
+constexpr int kMaxOdSlices = 32;    // region slices of a root score
+constexpr int kCtasPerChunk = 8;    // 8 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
 constexpr int kBuildBlock = 256;    // cells per CTA of the build kernel
 constexpr int kPad = 256;           // row padding (cells)
 
@@ -65,7 +66,7 @@ struct alignas(16) DevTask {
     int node_id;
     unsigned short n_ev;       // number of event records (Node::c_change entries)
     short parent_task;         // task index of the parent inside this proposal, -1: the parent is not rescored before
-    signed char ext_slot;      // parent score comes from outside this task chunk: shared-memory slot it is fetched into (-1: none)
+    signed char pad0;
     unsigned char flags;
     short pad;
 };
@@ -117,20 +118,18 @@ struct alignas(16) DevBuild {
     long long row_stride;  // Mp
 };
 
-// lgamma for positive arguments.  From 16 up the Stirling series with one fused multiply-add reproduces glibc's
-// lgamma to <= 1 ulp (identical from ~1e5 up, checked on the host against 2M samples per decade); below 16 the CUDA
-// library routine is used.  The large branch is what the z-terms lgamma(S + nu*z) always take.
-__device__ __forceinline__ double lgam(double x) {
-    if (x >= 16.0) {
-        const double lx = log(x);
-        const double r = 1.0 / x, r2 = r * r;
-        double p = __fma_rn(r2, 1.0 / 1188.0, -1.0 / 1680.0);
-        p = __fma_rn(r2, p, 1.0 / 1260.0);
-        p = __fma_rn(r2, p, -1.0 / 360.0);
-        p = __fma_rn(r2, p, 1.0 / 12.0);
-        const double t = __fma_rn(x - 0.5, lx, -x);
-        return t + __fma_rn(p, r, 0.91893853320467274178);
-    }
+// lgamma for positive arguments: from 16 up the Stirling series of lgam_core.h (table-driven logarithm, <= 2 ulp from
+// glibc's lgamma and bit-identical for 99.9 % of arguments: tests/test_lgam_cpu.py); below 16 the CUDA library routine.
+// The large branch is what the z-terms lgamma(S + nu*z) always take, and what the data terms take unless a region has
+// (almost) no reads.  `tbl` is the shared-memory copy of the logarithm's reduction table.
+__device__ const double g_log_table[kLogTableDoubles] = {SCICONE_LOG_TABLE_VALUES};
+
+__device__ __forceinline__ void load_log_table(double* tbl) {
+    for (int i = threadIdx.x; i < kLogTableDoubles; i += blockDim.x) tbl[i] = g_log_table[i];
+}
+
+__device__ __forceinline__ double lgam(double x, const double* tbl) {
+    if (x >= 16.0) return lgam_large(x, tbl);
     return lgamma(x);
 }
 
@@ -143,7 +142,7 @@ __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
     __syncthreads();
     double s = 0.0;
     if (threadIdx.x == 0)
-        for (int i = 0; i < kCells / 32; ++i) s += warp_buf[i];  // only the cell-owning warps contribute
+        for (int i = 0; i < kThreads / 32; ++i) s += warp_buf[i];
     return s;  // valid in thread 0
 }
 
@@ -152,8 +151,9 @@ __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
 // schedule, and (because shards are whole chunks) not on the number of GPUs.
 // Two sums travel together: [0] the tree score, [1] the root score (0 when not requested).
 __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum1, double* partial, double* chunk_sums,
-                                                 double* total, unsigned* counter, double* smem_chunks) {
+                                                 double* total, unsigned* counter) {
     __shared__ bool is_last;
+    __shared__ double smem_chunks[kThreads];
     const int n_cta = gridDim.x;
     const int n_chunks = (n_cta + kCtasPerChunk - 1) / kCtasPerChunk;
     if (threadIdx.x == 0) {
@@ -196,20 +196,24 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
 // K1: data-only lgamma work.  grid = (ceil(M / kBuildBlock), n_items).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items) {
+    __shared__ double tbl[kLogTableDoubles];
+    load_log_table(tbl);
     const DevBuild it = reinterpret_cast<const DevBuild*>(arena + off_items)[blockIdx.y];
     const int j = blockIdx.x * kBuildBlock + threadIdx.x;
+    __syncthreads();
     if (j >= it.n_cells) return;
     if (it.kind == BUILD_DELTA) {
         const double d = __ldg(it.src + j);
-        it.dst[j] = lgam(d + it.c1) - lgam(d + it.c2);
+        it.dst[j] = lgam(d + it.c1, tbl) - lgam(d + it.c2, tbl);
         return;
     }
     const double* arg = reinterpret_cast<const double*>(arena + it.off_arg);
     const double* cc = reinterpret_cast<const double*>(arena + it.off_c);
     double acc = 0.0;
     if (it.kind == BUILD_OD_SLICE) {  // Tree::get_od_root_score, Tree.h:1792-1797
+#pragma unroll 2
         for (int k = it.k0; k < it.k1; ++k) {
-            acc += lgam(__ldg(it.src + (long long)k * it.row_stride + j) + arg[k]);
+            acc += lgam(__ldg(it.src + (long long)k * it.row_stride + j) + arg[k], tbl);
             acc -= cc[k];
         }
     } else {  // Tree.h:1803-1805
@@ -219,33 +223,34 @@ __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned 
 }
 
 // ---------------------------------------------------------------------------------
-// K2-K4: grid = (ceil(M / kCells), n_proposals).  The arena starts with one 32-bit blob offset per proposal.
-// Thread t owns cell (t % kCells) of the tile and task lane (t / kCells); warps are uniform in the lane.
+// K2-K4: grid = (ceil(M / kCells), n_proposals), one THREAD per cell.  The arena starts with one 32-bit blob offset
+// per proposal.
 //
-// Per chunk of kTaskChunk tasks:   stage   task + event records -> shared memory (one coalesced 16-byte copy per thread)
-//                                  A1      4 lanes: lgamma(S + nu z) of each staged task; scores of parents that were
-//                                          rescored outside this chunk (or are committed rows) fetched into shared memory
-//                                  A2      4 lanes: increment score(node) - score(parent): delta-row gathers (issued
-//                                          together, then added in the reference's order) + z-terms
-//                                  B       lane 0: one add per node along parent -> child, rows written, running max / LSE
-// then                             C       aggregate: the rescan of the unchanged rows (max scoring) is split over the
-//                                          4 lanes and skipped by warps in which no cell needs it
-//                                  D       root score from its region slices (nu proposals)
-//                                  reduce  aggregate * cluster_size -> CTA partial -> fixed-order chunk / grand totals
+// A thread walks the rescored nodes of its proposal parent-before-child (Tree::compute_stack, Tree.h:260-286):
+//   stage   (CTA) task + event records of the next kTaskChunk nodes -> shared memory, one coalesced 16-byte copy per thread
+//   score   delta-row gathers issued together and added in the reference's order, z-terms by the table-driven lgamma
+//           (lgamma(S + nu z_parent) is the previous node's lgamma(S + nu z) when the parent was visited just before),
+//           score = parent score + increment: the parent's score is the previous node's (register) or was prefetched one
+//           node ahead from the row this thread wrote earlier / from the committed table; row written, running max / LSE
+//   C       aggregate (Inference::compute_t_prime_sums): the unchanged rows are only read by cells that need them,
+//           four loads in flight
+//   D       root score from its region slices (nu proposals)
+//   reduce  aggregate * cluster_size -> warp shuffle -> CTA partial -> fixed-order chunk / grand totals (last CTA)
+// There is no per-cell state in shared memory, so occupancy is bounded by registers only and the only barriers are the
+// two around each staging step; with B proposals x M cells >= 300 k threads the SMs stay full (LPT order of the
+// proposals in grid.y handles the long full-tree rescorings of nu proposals).
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void copy16(void* dst, const void* src) {
     *reinterpret_cast<int4*>(dst) = __ldg(reinterpret_cast<const int4*>(src));
 }
 
-__global__ void __launch_bounds__(kThreads, 4) score_proposals_kernel(const unsigned char* __restrict__ arena) {
-    __shared__ double sm_g[kTaskChunk][kCells];    // lgamma(S + nu*z) of the staged tasks; later: slices / rescan buffers
-    __shared__ double sm_sc[kTaskChunk][kCells];   // increments, then scores
-    __shared__ double sm_ps[kExtSlots][kCells];    // scores of parents outside the chunk
-    __shared__ double red_buf[kThreads];
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kernel(const unsigned char* __restrict__ arena) {
     __shared__ __align__(16) DevTask sm_task[kTaskChunk];
     __shared__ __align__(16) DevEvent sm_ev[kEvStage];
-    __shared__ int sm_uid[kLanes][kCells];
-    __shared__ unsigned char sm_need[kCells];
+    __shared__ double red_buf[kThreads / 32];
+    __shared__ double tbl[kLogTableDoubles];
+    load_log_table(tbl);
+    __syncthreads();
 
     const unsigned* blob_off = reinterpret_cast<const unsigned*>(arena);
     const unsigned char* blob = arena + blob_off[blockIdx.y];
@@ -255,210 +260,169 @@ __global__ void __launch_bounds__(kThreads, 4) score_proposals_kernel(const unsi
     const double* const* old_rows = reinterpret_cast<const double* const*>(blob + H.off_old);
     const DevUnch* unch = reinterpret_cast<const DevUnch*>(blob + H.off_unch);
 
-    const int cell = threadIdx.x % kCells;
-    const int lane = threadIdx.x / kCells;
-    const int j = blockIdx.x * kCells + cell;
+    const int j = blockIdx.x * kCells + threadIdx.x;
     const bool live = j < H.n_cells;
     const unsigned pflags = H.flags;
     const bool od = pflags & PROP_OD;
-    const bool owner = live && lane == 0;
     const int n_tasks = H.n_tasks;
     const double S = live ? __ldg(H.S + j) : 1.0;
 
-    // running aggregate over the rescored nodes (owner threads)
+    // running aggregate over the rescored nodes
     double new_max = -DBL_MAX;  // max over the new values (both modes)
     int new_id = 0;             // its node id (lowest id among equals = first in ascending-id order)
     double new_sumexp = 0.0;    // sum mode: sum_i exp(v_i - new_max)
     bool prev_in_new = (pflags & PROP_FULL) != 0;
-    const bool incremental = owner && !(pflags & (PROP_FULL | PROP_OD_ONLY));
+    const bool incremental = live && !(pflags & (PROP_FULL | PROP_OD_ONLY));
     const int pm = (incremental && (pflags & PROP_MAX)) ? H.maxid_old[j] : -1;
     const double agg_old = incremental ? H.sums_old[j] : 0.0;  // fetched now, needed in phase C
 
+    double sc_prev = 0.0, g_prev = 0.0;  // score and lgamma(S + nu z) of the node visited just before
+    double ps_next = 0.0;                // prefetched parent score of the next node
+    if (live && n_tasks > 0 && !(tasks[0].flags & TASK_ROOT)) ps_next = __ldcg(tasks[0].parent_row + j);
+
     for (int c0 = 0; c0 < n_tasks; c0 += kTaskChunk) {
-        const int c1 = min(c0 + kTaskChunk, n_tasks);
-        const int nt = c1 - c0;
-        // ---- stage the task and event records of this chunk
+        const int nt = min(kTaskChunk, n_tasks - c0);
+        // ---- stage the task and event records of this chunk (+ the first record of the next one, for the prefetch)
         const int e_base = tasks[c0].ev_begin;
-        const int e_stop = tasks[c1 - 1].ev_begin + tasks[c1 - 1].n_ev;
+        const int e_stop = tasks[c0 + nt - 1].ev_begin + tasks[c0 + nt - 1].n_ev;
         const int n_stage = min(e_stop - e_base, kEvStage);
-        if ((int)threadIdx.x < nt * 4)
-            copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * threadIdx.x,
-                   reinterpret_cast<const unsigned char*>(tasks + c0) + 16 * threadIdx.x);
-        if ((int)threadIdx.x < n_stage * 2)
-            copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * threadIdx.x,
-                   reinterpret_cast<const unsigned char*>(events + e_base) + 16 * threadIdx.x);
         __syncthreads();
-        // ---- A1: z-terms of the staged tasks; parent scores that do not come from this chunk
-        if (live)
-            for (int t = lane; t < nt; t += kLanes) {
-                const DevTask& tk = sm_task[t];
-                if (od) sm_g[t][cell] = lgam(S + tk.nz);
-                if (tk.ext_slot >= 0) sm_ps[tk.ext_slot][cell] = __ldcg(tk.parent_row + j);
+        for (int q = threadIdx.x; q < nt * 4; q += kThreads)
+            copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, reinterpret_cast<const unsigned char*>(tasks + c0) + 16 * q);
+        for (int q = threadIdx.x; q < n_stage * 2; q += kThreads)
+            copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, reinterpret_cast<const unsigned char*>(events + e_base) + 16 * q);
+        __syncthreads();
+        if (!live) continue;
+        for (int t = 0; t < nt; ++t) {
+            const DevTask& tk = sm_task[t];
+            const bool root = tk.flags & TASK_ROOT;
+            const bool chained = tk.parent_task >= 0 && tk.parent_task == c0 + t - 1;  // the parent is the node visited just before
+            const double ps = chained ? sc_prev : ps_next;
+            // parent score of the NEXT node: its row was written by this thread at least one node ago (or is committed)
+            {
+                const DevTask* nx = (t + 1 < nt) ? &sm_task[t + 1] : ((c0 + t + 1 < n_tasks) ? &tasks[c0 + t + 1] : nullptr);
+                if (nx && nx->parent_task != c0 + t && !(nx->flags & TASK_ROOT)) ps_next = __ldcg(nx->parent_row + j);
             }
-        __syncthreads();
-        // ---- A2: increments  score(node) - score(parent)   (Tree::compute_score, Tree.h:177-238)
-        if (live)
-            for (int t = lane; t < nt; t += kLanes) {
-                const DevTask& tk = sm_task[t];
+            double sc = 0.0;
+            // ---- increment  score(node) - score(parent)   (Tree::compute_score, Tree.h:177-238)
+            if (!root) {
                 double x = 0.0;
-                if (!(tk.flags & TASK_ROOT)) {
-                    const int e0 = tk.ev_begin - e_base, ne = tk.n_ev;
-                    // the first four gathers are issued together; they are added in event order below
-                    double d[4];
+                const int e0 = tk.ev_begin - e_base, ne = tk.n_ev;
+                double d[4];  // the first four gathers are issued together; they are added in event order below
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int e = e0 + q;
-                        d[q] = 0.0;
-                        if (q < ne) {
-                            const double* row = (e < kEvStage) ? sm_ev[e].row : events[e_base + e].row;
-                            d[q] = __ldg(row + j);
-                        }
+                for (int q = 0; q < 4; ++q) {
+                    const int e = e0 + q;
+                    d[q] = 0.0;
+                    if (q < ne) {
+                        const double* row = (e < kEvStage) ? sm_ev[e].row : events[e_base + e].row;
+                        d[q] = __ldg(row + j);
                     }
-                    if (od) {
+                }
+                if (od) {
+                    const double g = lgam(S + tk.nz, tbl);
+                    const double gp = ((tk.flags & TASK_REUSE_G) && chained) ? g_prev : lgam(S + tk.nzp, tbl);
+                    g_prev = g;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < ne) {
-                                const int e = e0 + q;
-                                const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
-                                x += d[q];
-                                x -= ev.a;
-                                x += ev.b;
-                            }
-                        for (int q = 4; q < ne; ++q) {
+                    for (int q = 0; q < 4; ++q)
+                        if (q < ne) {
                             const int e = e0 + q;
                             const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
-                            x += __ldg(ev.row + j);
+                            x += d[q];
                             x -= ev.a;
                             x += ev.b;
                         }
-                        x += tk.lg_nz;
-                        x -= tk.lg_nzp;
-                        x -= sm_g[t][cell];
-                        const int pt = tk.parent_task;
-                        x += ((tk.flags & TASK_REUSE_G) && pt >= c0) ? sm_g[pt - c0][cell] : lgam(S + tk.nzp);
-                    } else {
+                    for (int q = 4; q < ne; ++q) {
+                        const int e = e0 + q;
+                        const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
+                        x += __ldg(ev.row + j);
+                        x -= ev.a;
+                        x += ev.b;
+                    }
+                    x += tk.lg_nz;
+                    x -= tk.lg_nzp;
+                    x -= g;
+                    x += gp;
+                } else {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < ne) {
-                                const int e = e0 + q;
-                                const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
-                                x += d[q] * ev.a;
-                            }
-                        for (int q = 4; q < ne; ++q) {
+                    for (int q = 0; q < 4; ++q)
+                        if (q < ne) {
                             const int e = e0 + q;
                             const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
-                            x += __ldg(ev.row + j) * ev.a;
+                            x += d[q] * ev.a;
                         }
-                        x -= S * tk.lg_nz;
-                        x += S * tk.lg_nzp;
+                    for (int q = 4; q < ne; ++q) {
+                        const int e = e0 + q;
+                        const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
+                        x += __ldg(ev.row + j) * ev.a;
                     }
+                    x -= S * tk.lg_nz;
+                    x += S * tk.lg_nzp;
                 }
-                sm_sc[t][cell] = x;
+                sc = ps + x;
+            } else if (od)
+                g_prev = lgam(S + tk.nz, tbl);
+            sc_prev = sc;
+            tk.dst[j] = sc;
+            if (tk.flags & TASK_SKIP_AGG) continue;
+            const int id = tk.node_id;
+            if (id == pm) prev_in_new = true;
+            if (pflags & PROP_MAX) {
+                if (sc > new_max || (sc == new_max && id < new_id)) {
+                    new_max = sc;
+                    new_id = id;
+                }
+            } else {  // online log-sum-exp of the new values
+                if (sc > new_max) {
+                    new_sumexp = new_sumexp * exp(new_max - sc) + 1.0;
+                    new_max = sc;
+                } else
+                    new_sumexp += exp(sc - new_max);
             }
-        __syncthreads();
-        // ---- B: scan parent-before-child (Tree::compute_stack, Tree.h:260-286) and fold into the aggregate
-        if (owner)
-            for (int t = 0; t < nt; ++t) {
-                const DevTask& tk = sm_task[t];
-                double sc;
-                if (tk.flags & TASK_ROOT)
-                    sc = 0.0;
-                else {
-                    const int pt = tk.parent_task;
-                    const double ps = (pt >= c0) ? sm_sc[pt - c0][cell]
-                                                 : (tk.ext_slot >= 0 ? sm_ps[tk.ext_slot][cell] : __ldcg(tk.parent_row + j));
-                    sc = ps + sm_sc[t][cell];
-                }
-                sm_sc[t][cell] = sc;
-                tk.dst[j] = sc;
-                if (tk.flags & TASK_SKIP_AGG) continue;
-                const int id = tk.node_id;
-                if (id == pm) prev_in_new = true;
-                if (pflags & PROP_MAX) {
-                    if (sc > new_max || (sc == new_max && id < new_id)) {
-                        new_max = sc;
-                        new_id = id;
-                    }
-                } else {  // online log-sum-exp of the new values
-                    if (sc > new_max) {
-                        new_sumexp = new_sumexp * exp(new_max - sc) + 1.0;
-                        new_max = sc;
-                    } else
-                        new_sumexp += exp(sc - new_max);
-                }
-            }
-        __syncthreads();
+        }
     }
 
     double contrib = 0.0, contrib_od = 0.0;
-    if (!(pflags & PROP_OD_ONLY)) {
+    if (live && !(pflags & PROP_OD_ONLY)) {
         // ---- per-cell aggregate: Inference::compute_t_prime_sums ----
         const int n_unch = H.n_unch;
+        double res;
         if (pflags & PROP_MAX) {  // Inference.h:1086-1152
-            // The unchanged rows are rescanned only for cells whose previous argmax was rescored or deleted.  The scan is
-            // split over the 4 lanes (contiguous index ranges, so "first maximum in ascending id order" is kept by
-            // merging the lanes in order with a strict comparison) and skipped by warps where no cell needs it.
-            const bool want = owner && n_unch > 0 && (prev_in_new || pm == H.deleted_id);
-            if (lane == 0) sm_need[cell] = want ? 1 : 0;
-            __syncthreads();
-            const bool need = sm_need[cell] != 0;
-            double cur = -DBL_MAX;
-            int uid = 0;
-            if (__any_sync(0xffffffffu, need)) {
-                const int per = (n_unch + kLanes - 1) / kLanes;
-                const int u0 = lane * per, u1 = min(n_unch, u0 + per);
-                if (need) {
-                    int u = u0;
-                    for (; u + 4 <= u1; u += 4) {
-                        double v[4];
+            int prev_id = pm;
+            double prev_val = agg_old;
+            if (prev_in_new || pm == H.deleted_id) {
+                // the previous argmax was rescored or deleted: first maximum of the unchanged rows in ascending id order
+                double cur = -DBL_MAX;
+                int uid = 0;
+                int u = 0;
+                for (; u + 4 <= n_unch; u += 4) {
+                    double v[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) v[q] = __ldcg(unch[u + q].row + j);
+                    for (int q = 0; q < 4; ++q) v[q] = __ldcg(unch[u + q].row + j);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (v[q] > cur) {
-                                cur = v[q];
-                                uid = unch[u + q].id;
-                            }
-                    }
-                    for (; u < u1; ++u) {
-                        const double v = __ldcg(unch[u].row + j);
-                        if (v > cur) {
-                            cur = v;
-                            uid = unch[u].id;
+                    for (int q = 0; q < 4; ++q)
+                        if (v[q] > cur) {
+                            cur = v[q];
+                            uid = unch[u + q].id;
                         }
+                }
+                for (; u < n_unch; ++u) {
+                    const double v = __ldcg(unch[u].row + j);
+                    if (v > cur) {
+                        cur = v;
+                        uid = unch[u].id;
                     }
                 }
+                prev_id = uid;
+                prev_val = cur > -DBL_MAX ? cur : 0.0;  // value-initialised std::pair when nothing is unchanged
             }
-            sm_g[lane][cell] = cur;
-            sm_uid[lane][cell] = uid;
-            __syncthreads();
-            if (owner) {
-                int prev_id = pm;
-                double prev_val = agg_old;
-                if (prev_in_new || pm == H.deleted_id) {
-                    double best = -DBL_MAX;
-                    int bid = 0;
-#pragma unroll
-                    for (int l = 0; l < kLanes; ++l)
-                        if (sm_g[l][cell] > best) {
-                            best = sm_g[l][cell];
-                            bid = sm_uid[l][cell];
-                        }
-                    prev_id = bid;
-                    prev_val = best > -DBL_MAX ? best : 0.0;  // value-initialised std::pair when nothing is unchanged
-                }
-                double res = new_max;
-                int rid = new_id;
-                if (prev_val > new_max) {
-                    res = prev_val;
-                    rid = prev_id;
-                }
-                H.maxid_new[j] = rid;
-                if (res != res) atomicOr(H.status, 1u);
-                H.sums_new[j] = res;
-                contrib = res * (double)H.w[j];
+            res = new_max;
+            int rid = new_id;
+            if (prev_val > new_max) {
+                res = prev_val;
+                rid = prev_id;
             }
-        } else if (owner) {  // MathOp::log_replace_sum, MathOp.cpp:307-361
+            H.maxid_new[j] = rid;
+        } else {  // MathOp::log_replace_sum, MathOp.cpp:307-361
             bool scratch = (pflags & (PROP_SCRATCH | PROP_FULL)) != 0;
             double sub = 0.0;
             if (!scratch) {  // incremental branch: take the old values out of the old sum
@@ -490,42 +454,53 @@ __global__ void __launch_bounds__(kThreads, 4) score_proposals_kernel(const unsi
                 for (int u = 0; u < n_unch; ++u) s += exp(__ldcg(unch[u].row + j) - mx);
             } else
                 s += exp(sub - mx);
-            const double res = log(s) + mx;
-            if (res != res) atomicOr(H.status, 1u);
-            H.sums_new[j] = res;
-            contrib = res * (double)H.w[j];
+            res = log(s) + mx;
         }
+        if (res != res) atomicOr(H.status, 1u);
+        H.sums_new[j] = res;
+        contrib = res * (double)H.w[j];
     }
-    if (pflags & PROP_WITH_OD) {  // uniform per proposal
-        // Tree::get_od_root_score (Tree.h:1774-1810) from the region slices K1 prepared (fetched by the 4 lanes, added
-        // in slice order by the owner); Inference::compute_t_prime_od_scores, Inference.h:1421-1433
+    if (live && (pflags & PROP_WITH_OD)) {
+        // Tree::get_od_root_score (Tree.h:1774-1810) from the region slices K1 prepared;
+        // Inference::compute_t_prime_od_scores, Inference.h:1421-1433
         const double* const* slices = reinterpret_cast<const double* const*>(blob + H.off_od_rows);
-        const int ns = H.n_od_slices;  // <= kTaskChunk
-        __syncthreads();
-        if (live)
-            for (int s = lane; s < ns; s += kLanes) sm_g[s][cell] = __ldcg(slices[s] + j);
-        __syncthreads();
-        if (owner) {
-            double v = 0.0;
-            if (od) {
-                v += H.od_lg_nz;
-                v -= lgam(S + H.od_nz);
-            } else
-                v += -S * H.od_lg_nz;
-            for (int s = 0; s < ns; ++s) v += sm_g[s][cell];
-            contrib_od = v * (double)H.w[j];
+        const int ns = H.n_od_slices;
+        double v = 0.0;
+        if (od) {
+            v += H.od_lg_nz;
+            v -= lgam(S + H.od_nz, tbl);
+        } else
+            v += -S * H.od_lg_nz;
+        int s = 0;
+        for (; s + 4 <= ns; s += 4) {
+            double q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = __ldcg(slices[s + i] + j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v += q[i];
         }
+        for (; s < ns; ++s) v += __ldcg(slices[s] + j);
+        contrib_od = v * (double)H.w[j];
     }
     // ---- weighted sum over cells: Inference::comparison, Inference.h:292-294 ----
     __syncthreads();
     const double cta_sum = block_sum(contrib, red_buf);
     __syncthreads();
     double cta_od = 0.0;
-    if (pflags & PROP_WITH_OD) {
+    if (pflags & PROP_WITH_OD) {  // uniform per proposal
         cta_od = block_sum(contrib_od, red_buf);
         __syncthreads();
     }
-    finish_reduction(cta_sum, cta_od, H.partial, H.chunk_sums, H.total, H.counter, red_buf);
+    finish_reduction(cta_sum, cta_od, H.partial, H.chunk_sums, H.total, H.counter);
+}
+
+// Test hook: the device lgamma on caller-provided arguments (scicone_test_lgamma).
+__global__ void lgam_probe_kernel(const double* __restrict__ x, double* __restrict__ out, int n) {
+    __shared__ double tbl[kLogTableDoubles];
+    load_log_table(tbl);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lgam(x[i], tbl);
 }
 
 // Multi-GPU: copy the per-chunk sums of each proposal into the fixed-width, zero-padded send buffer of

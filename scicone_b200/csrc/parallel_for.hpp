@@ -1,10 +1,11 @@
 // A small fork-join pool for the host side of the engine: the per-chain work of one MCMC step (drawing a move,
 // compiling the proposal blob, committing / rolling back) is independent across chains, so a step of B chains is a
-// parallel-for over B items followed by ONE kernel launch.  Steps are ~100 us apart, so the workers spin briefly
-// before they sleep, and the calling thread takes part in the loop.
+// parallel-for over B items followed by ONE kernel launch.  Steps are ~100 us apart, so the workers spin (SCICONE_SPIN_US,
+// default 1000 us) before they sleep, and the calling thread takes part in the loop.
 //
 // No reference counterpart: the reference is one chain per process (global RNG singleton).
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -59,6 +60,7 @@ private:
             if (n > 16) n = 16;
         }
         if (n < 1) n = 1;
+        if (const char* e = std::getenv("SCICONE_SPIN_US")) spin_us_ = std::max(0, std::atoi(e));
         for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
     }
     ~ForkJoinPool() {
@@ -89,12 +91,12 @@ private:
         in_worker_ = true;
         unsigned long long seen = 0;
         for (;;) {
-            // spin for ~50 us, then sleep until the next generation
+            // spin, then sleep until the next generation (waking 15 sleepers costs more than a whole MCMC step)
             const auto t0 = std::chrono::steady_clock::now();
             bool fresh = false;
             while (!(fresh = generation_.load(std::memory_order_acquire) != seen)) {
                 cpu_relax();
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(50)) break;
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) break;
             }
             if (!fresh) {
                 std::unique_lock<std::mutex> lk(mu_);
@@ -115,6 +117,7 @@ private:
     std::atomic<int> next_{0}, pending_{0}, active_{0};
     std::atomic<bool> busy_{false};
     bool stop_ = false;
+    int spin_us_ = 1000;
     Fn fn_ = nullptr;
     void* ctx_ = nullptr;
     int n_ = 0;

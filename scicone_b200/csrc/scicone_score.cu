@@ -498,7 +498,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             memset(&tk, 0, sizeof tk);
             tk.node_id = id;
             tk.parent_task = -1;
-            tk.ext_slot = -1;
             tk.ev_begin = (int)events.size();
             int z_int;
             if (pidx < 0) {  // Tree::compute_root_score, Tree.h:145-160
@@ -602,12 +601,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         for (size_t i = 0; i < tasks.size(); ++i) last[tasks[i].node_id] = (int)i;
         for (size_t i = 0; i < tasks.size(); ++i)
             if (last[tasks[i].node_id] != (int)i) tasks[i].flags |= TASK_SKIP_AGG;
-    }
-    // parents whose score does not come out of the same task chunk are fetched into shared memory ahead of the scan
-    for (size_t c0 = 0; c0 < tasks.size(); c0 += kTaskChunk) {
-        int used = 0;
-        for (size_t i = c0; i < std::min(tasks.size(), c0 + kTaskChunk); ++i)
-            if (!(tasks[i].flags & TASK_ROOT) && tasks[i].parent_task < (int)c0 && used < kExtSlots) tasks[i].ext_slot = (signed char)used++;
     }
     std::vector<const double*> old_rows;
     std::vector<DevUnch> unch;
@@ -1315,6 +1308,27 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
     }
     cudaFree(d_rows); cudaFree(d_ids); cudaFree(d_cn); cudaFree(d_out_id); cudaFree(d_out_col); cudaFree(d_out_cn);
     if (e != cudaSuccess) return fail(SCICONE_ERR_CUDA, "assign_cells_to_nodes: %s", cudaGetErrorString(e));
+    return SCICONE_OK;
+}
+
+int scicone_test_lgamma(int32_t device, const double* x, int32_t n, double* out) {
+    if (!x || !out || n <= 0) return fail(SCICONE_ERR_ARG, "test_lgamma: bad argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev)
+        return fail(SCICONE_ERR_CUDA, "test_lgamma: no such CUDA device; this library has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    double *dx = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc(&dx, sizeof(double) * n));
+    cudaError_t e = cudaMalloc(&dout, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        lgam_probe_kernel<<<(n + 255) / 256, 256>>>(dx, dout, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail(SCICONE_ERR_CUDA, "test_lgamma: %s", cudaGetErrorString(e));
     return SCICONE_OK;
 }
 
