@@ -130,6 +130,14 @@ int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t_prim
 int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t_prime, double* t_prime_sum);
 
 /*
+ * Optional, between the last scicone_compute_t_prime_scores and the sums call: build the launch description of the
+ * queued proposal now, on the calling thread (Node::z re-derivation, host-side lgamma constants, row bookkeeping).
+ * Thread-safe for different chains, so a multi-chain host spreads this work over its threads instead of leaving it
+ * to the (serial) batch call.  No reference counterpart.
+ */
+int scicone_prepare_t_prime(scicone_chain* ch);
+
+/*
  * The same two steps for `n` chains in ONE kernel launch (independent restarts or
  * proposals evaluated in lock-step).  Every chain must have queued its subtree
  * roots with scicone_compute_t_prime_scores.  All chains must share one dataset.

@@ -141,6 +141,7 @@ int scicone_build_time_stats(scicone_dataset*, double* s, uint64_t* n) { if (s) 
 int scicone_kernel_launches(scicone_dataset*, uint64_t* n) { *n = 0; return 0; }
 int scicone_parallel_for(int32_t n, void (*fn)(int32_t, void*), void* ctx) { scicone::ForkJoinPool::instance().run(n, fn, ctx); return 0; }
 int scicone_test_lgamma(int32_t, const double*, int32_t, double*) { return fail(-2, "cpu backend: no device lgamma"); }
+int scicone_prepare_t_prime(scicone_chain*) { return 0; }
 int scicone_host_threads(void) { return scicone::ForkJoinPool::instance().n_threads(); }
 int scicone_counters(scicone_dataset*, double out[4], int32_t) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
 int scicone_region_mark(scicone_dataset*, int32_t) { return 0; }

@@ -39,13 +39,16 @@ constexpr int kTaskChunk = 32;      // task records staged in shared memory at a
 constexpr int kEvStage = 96;        // event records staged with them (the rest is read from global memory)
 constexpr int kMaxOdSlices = 32;    // region slices of a root score
 constexpr int kCtasPerChunk = 8;    // 8 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
-constexpr int kBuildBlock = 256;    // cells per CTA of the build kernel
+constexpr int kBuildBlock = 256;    // threads per CTA of the build kernel
+constexpr int kBuildCells = 4;      // cells per thread of the build kernel
 constexpr int kPad = 256;           // row padding (cells)
 
 enum : unsigned {
     TASK_ROOT = 1u,      // tree root: score 0 (Tree::compute_root_score, Tree.h:145-160)
     TASK_REUSE_G = 2u,   // lgamma(S + nu*z_parent) equals the parent task's lgamma(S + nu*z) in this chunk
     TASK_SKIP_AGG = 4u,  // a later task rewrites the same node: only that one enters the aggregate
+    TASK_CHAINED = 8u,   // the parent is the task right before this one: its score (and z-term) are still in registers
+    TASK_BIG = 16u,      // more events than the staging buffer holds: read from global memory
     PROP_MAX = 1u,       // max scoring (Inference::max_scoring)
     PROP_OD = 2u,        // overdispersed likelihood (globals is_overdispersed)
     PROP_FULL = 4u,      // full table pass (Inference::compute_t_table): no committed state is read
@@ -58,19 +61,22 @@ enum : unsigned {
 };
 
 struct alignas(16) DevTask {
-    double* dst;               // score row being written
-    const double* parent_row;  // where the parent's score lives in global memory (committed row, or the primed row)
-    double lg_nz, lg_nzp;      // OD: lgamma(nu*z), lgamma(nu*z_parent);  non-OD: log(z), log(z_parent)
-    double nz, nzp;            // OD: nu*z, nu*z_parent
-    int ev_begin;              // first event record
+    double* dst;                 // score row being written
+    const double* prefetch_row;  // parent score row of the NEXT task when that task is neither chained nor the root, else null
+    double lg_nz, lg_nzp;        // OD: lgamma(nu*z), lgamma(nu*z_parent);  non-OD: log(z), log(z_parent)
+    double nz, nzp;              // OD: nu*z, nu*z_parent
+    int ev_begin;                // first event record (index into the proposal's event array)
     int node_id;
-    unsigned short n_ev;       // number of event records (Node::c_change entries)
-    short parent_task;         // task index of the parent inside this proposal, -1: the parent is not rescored before
-    signed char pad0;
+    unsigned short n_ev;         // number of event records (Node::c_change entries)
+    unsigned short ev_rel;       // first event record relative to the chunk's staged events
     unsigned char flags;
-    short pad;
+    unsigned char pad[3];
 };
 static_assert(sizeof(DevTask) == 64, "DevTask is staged as four 16-byte pieces");
+
+struct alignas(16) DevChunk {  // tasks [first_task, first_task + n_tasks) and events [ev_base, ev_base + n_ev) are staged together
+    int first_task, n_tasks, ev_base, n_ev;
+};
 
 struct alignas(16) DevEvent {
     const double* row;  // OD: delta row;  non-OD: Dt[k]
@@ -90,7 +96,7 @@ struct alignas(16) DevHeader {
     unsigned flags;
     int n_cells;  // M of this shard
     int n_od_slices;
-    int pad1;
+    int n_chunks;
     const double* S;
     const int* w;
     const double* sums_old;
@@ -103,7 +109,9 @@ struct alignas(16) DevHeader {
     unsigned* counter;    // arrival counter for the last-CTA reduction
     unsigned* status;     // bit 0: NaN aggregate
     double od_lg_nz, od_nz;  // OD: lgamma(nu*z_root), nu*z_root;  non-OD: od_lg_nz = log(sum_r)
-    unsigned off_tasks, off_events, off_old, off_unch, off_od_rows, pad2;
+    unsigned off_tasks, off_events, off_old, off_unch, off_od_rows, off_chunks;
+    const double* first_parent_row;  // parent score row of task 0 (null for a root)
+    double pad3;
 };
 
 struct alignas(16) DevBuild {
@@ -192,25 +200,13 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
     if (threadIdx.x == 0) *counter = 0u;
 }
 
-// ---------------------------------------------------------------------------------
-// K1: data-only lgamma work.  grid = (ceil(M / kBuildBlock), n_items).
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items) {
-    __shared__ double tbl[kLogTableDoubles];
-    load_log_table(tbl);
-    const DevBuild it = reinterpret_cast<const DevBuild*>(arena + off_items)[blockIdx.y];
-    const int j = blockIdx.x * kBuildBlock + threadIdx.x;
-    __syncthreads();
+// A slice of the root score of one cell: sum over the regions [k0, k1) (Tree::get_od_root_score, Tree.h:1792-1805).
+__device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned char* __restrict__ arena, int j, const double* tbl) {
     if (j >= it.n_cells) return;
-    if (it.kind == BUILD_DELTA) {
-        const double d = __ldg(it.src + j);
-        it.dst[j] = lgam(d + it.c1, tbl) - lgam(d + it.c2, tbl);
-        return;
-    }
     const double* arg = reinterpret_cast<const double*>(arena + it.off_arg);
     const double* cc = reinterpret_cast<const double*>(arena + it.off_c);
     double acc = 0.0;
-    if (it.kind == BUILD_OD_SLICE) {  // Tree::get_od_root_score, Tree.h:1792-1797
+    if (it.kind == BUILD_OD_SLICE) {  // Tree.h:1792-1797
 #pragma unroll 2
         for (int k = it.k0; k < it.k1; ++k) {
             acc += lgam(__ldg(it.src + (long long)k * it.row_stride + j) + arg[k], tbl);
@@ -220,6 +216,34 @@ __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned 
         for (int k = it.k0; k < it.k1; ++k) acc += __ldg(it.src + (long long)k * it.row_stride + j) * arg[k];
     }
     it.dst[j] = acc;
+}
+
+// ---------------------------------------------------------------------------------
+// K1: data-only lgamma work.  grid = (ceil(M / (kBuildBlock * kBuildCells)), n_items).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items) {
+    __shared__ double tbl[kLogTableDoubles];
+    load_log_table(tbl);
+    const DevBuild it = reinterpret_cast<const DevBuild*>(arena + off_items)[blockIdx.y];
+    const int j0 = blockIdx.x * (kBuildBlock * kBuildCells) + threadIdx.x;
+    if (it.kind == BUILD_DELTA) {
+        // kBuildCells cells per thread: the loads go out together, and the table copy / item fetch is paid once
+        double d[kBuildCells];
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) {
+            const int j = j0 + q * kBuildBlock;
+            d[q] = j < it.n_cells ? __ldg(it.src + j) : 32.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) {
+            const int j = j0 + q * kBuildBlock;
+            if (j < it.n_cells) it.dst[j] = lgam(d[q] + it.c1, tbl) - lgam(d[q] + it.c2, tbl);
+        }
+        return;
+    }
+    __syncthreads();
+    for (int q = 0; q < kBuildCells; ++q) build_slice(it, arena, j0 + q * kBuildBlock, tbl);
 }
 
 // ---------------------------------------------------------------------------------
@@ -264,7 +288,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
     const bool live = j < H.n_cells;
     const unsigned pflags = H.flags;
     const bool od = pflags & PROP_OD;
-    const int n_tasks = H.n_tasks;
     const double S = live ? __ldg(H.S + j) : 1.0;
 
     // running aggregate over the rescored nodes
@@ -278,83 +301,74 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
 
     double sc_prev = 0.0, g_prev = 0.0;  // score and lgamma(S + nu z) of the node visited just before
     double ps_next = 0.0;                // prefetched parent score of the next node
-    if (live && n_tasks > 0 && !(tasks[0].flags & TASK_ROOT)) ps_next = __ldcg(tasks[0].parent_row + j);
+    if (live && H.first_parent_row) ps_next = __ldcg(H.first_parent_row + j);
+    const DevChunk* chunks = reinterpret_cast<const DevChunk*>(blob + H.off_chunks);
 
-    for (int c0 = 0; c0 < n_tasks; c0 += kTaskChunk) {
-        const int nt = min(kTaskChunk, n_tasks - c0);
-        // ---- stage the task and event records of this chunk (+ the first record of the next one, for the prefetch)
-        const int e_base = tasks[c0].ev_begin;
-        const int e_stop = tasks[c0 + nt - 1].ev_begin + tasks[c0 + nt - 1].n_ev;
-        const int n_stage = min(e_stop - e_base, kEvStage);
+    for (int c = 0; c < H.n_chunks; ++c) {
+        const DevChunk ck = chunks[c];
+        // ---- stage the task and event records of this chunk
         __syncthreads();
-        for (int q = threadIdx.x; q < nt * 4; q += kThreads)
-            copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, reinterpret_cast<const unsigned char*>(tasks + c0) + 16 * q);
-        for (int q = threadIdx.x; q < n_stage * 2; q += kThreads)
-            copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, reinterpret_cast<const unsigned char*>(events + e_base) + 16 * q);
+        for (int q = threadIdx.x; q < ck.n_tasks * 4; q += kThreads)
+            copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, reinterpret_cast<const unsigned char*>(tasks + ck.first_task) + 16 * q);
+        for (int q = threadIdx.x; q < ck.n_ev * 2; q += kThreads)
+            copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, reinterpret_cast<const unsigned char*>(events + ck.ev_base) + 16 * q);
         __syncthreads();
         if (!live) continue;
-        for (int t = 0; t < nt; ++t) {
+        for (int t = 0; t < ck.n_tasks; ++t) {
             const DevTask& tk = sm_task[t];
-            const bool root = tk.flags & TASK_ROOT;
-            const bool chained = tk.parent_task >= 0 && tk.parent_task == c0 + t - 1;  // the parent is the node visited just before
-            const double ps = chained ? sc_prev : ps_next;
+            const unsigned tf = tk.flags;
+            const double ps = (tf & TASK_CHAINED) ? sc_prev : ps_next;
             // parent score of the NEXT node: its row was written by this thread at least one node ago (or is committed)
-            {
-                const DevTask* nx = (t + 1 < nt) ? &sm_task[t + 1] : ((c0 + t + 1 < n_tasks) ? &tasks[c0 + t + 1] : nullptr);
-                if (nx && nx->parent_task != c0 + t && !(nx->flags & TASK_ROOT)) ps_next = __ldcg(nx->parent_row + j);
-            }
+            if (tk.prefetch_row) ps_next = __ldcg(tk.prefetch_row + j);
             double sc = 0.0;
             // ---- increment  score(node) - score(parent)   (Tree::compute_score, Tree.h:177-238)
-            if (!root) {
+            if (!(tf & TASK_ROOT)) {
                 double x = 0.0;
-                const int e0 = tk.ev_begin - e_base, ne = tk.n_ev;
-                double d[4];  // the first four gathers are issued together; they are added in event order below
+                const int ne = tk.n_ev;
+                if (!(tf & TASK_BIG)) {
+                    const DevEvent* ev = sm_ev + tk.ev_rel;
+                    double d[4];  // the first four gathers are issued together; they are added in event order below
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int e = e0 + q;
-                    d[q] = 0.0;
-                    if (q < ne) {
-                        const double* row = (e < kEvStage) ? sm_ev[e].row : events[e_base + e].row;
-                        d[q] = __ldg(row + j);
+                    for (int q = 0; q < 4; ++q) d[q] = (q < ne) ? __ldg(ev[q].row + j) : 0.0;
+                    if (od) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < ne) {
+                                x += d[q];
+                                x -= ev[q].a;
+                                x += ev[q].b;
+                            }
+                        for (int q = 4; q < ne; ++q) {
+                            x += __ldg(ev[q].row + j);
+                            x -= ev[q].a;
+                            x += ev[q].b;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < ne) x += d[q] * ev[q].a;
+                        for (int q = 4; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
                     }
+                } else {  // a node with more events than the staging buffer holds
+                    const DevEvent* ev = events + tk.ev_begin;
+                    if (od)
+                        for (int q = 0; q < ne; ++q) {
+                            x += __ldg(ev[q].row + j);
+                            x -= ev[q].a;
+                            x += ev[q].b;
+                        }
+                    else
+                        for (int q = 0; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
                 }
                 if (od) {
                     const double g = lgam(S + tk.nz, tbl);
-                    const double gp = ((tk.flags & TASK_REUSE_G) && chained) ? g_prev : lgam(S + tk.nzp, tbl);
+                    const double gp = (tf & TASK_REUSE_G) ? g_prev : lgam(S + tk.nzp, tbl);
                     g_prev = g;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (q < ne) {
-                            const int e = e0 + q;
-                            const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
-                            x += d[q];
-                            x -= ev.a;
-                            x += ev.b;
-                        }
-                    for (int q = 4; q < ne; ++q) {
-                        const int e = e0 + q;
-                        const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
-                        x += __ldg(ev.row + j);
-                        x -= ev.a;
-                        x += ev.b;
-                    }
                     x += tk.lg_nz;
                     x -= tk.lg_nzp;
                     x -= g;
                     x += gp;
                 } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (q < ne) {
-                            const int e = e0 + q;
-                            const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
-                            x += d[q] * ev.a;
-                        }
-                    for (int q = 4; q < ne; ++q) {
-                        const int e = e0 + q;
-                        const DevEvent& ev = (e < kEvStage) ? sm_ev[e] : events[e_base + e];
-                        x += __ldg(ev.row + j) * ev.a;
-                    }
                     x -= S * tk.lg_nz;
                     x += S * tk.lg_nzp;
                 }
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
                 g_prev = lgam(S + tk.nz, tbl);
             sc_prev = sc;
             tk.dst[j] = sc;
-            if (tk.flags & TASK_SKIP_AGG) continue;
+            if (tf & TASK_SKIP_AGG) continue;
             const int id = tk.node_id;
             if (id == pm) prev_in_new = true;
             if (pflags & PROP_MAX) {

@@ -284,12 +284,11 @@ struct scicone_dataset {
         CUDA_TRY(cudaStreamSynchronize(stream));
         for (Segment& g : seg)
             if (g.busy) return fail(SCICONE_ERR_STATE, "batch size must grow while launches are outstanding");
-        cudaFree(d_partial); cudaFree(d_chunk); cudaFree(d_total); cudaFree(d_counter); cudaFree(d_status);
+        cudaFree(d_partial); cudaFree(d_chunk); cudaFree(d_total); cudaFree(d_counter);
         d_partial = d_chunk = d_total = nullptr;
         d_counter = d_status = nullptr;
         for (Segment& g : seg) {
             if (g.h_total) cudaFreeHost(g.h_total);
-            if (g.h_status) cudaFreeHost(g.h_status);
             if (g.h_gather) cudaFreeHost(g.h_gather);
             g.h_total = nullptr;
             g.h_status = nullptr;
@@ -298,14 +297,14 @@ struct scicone_dataset {
         slots = 0;
         CUDA_TRY(cudaMalloc(&d_partial, sizeof(double) * size_t(ns) * 2 * n_cta));
         CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * size_t(ns) * 2 * n_chunks));
-        CUDA_TRY(cudaMalloc(&d_total, sizeof(double) * ns * 2));
+        CUDA_TRY(cudaMalloc(&d_total, (sizeof(double) * 2 + sizeof(unsigned)) * ns));  // totals, then the status words: one copy back
         CUDA_TRY(cudaMalloc(&d_counter, sizeof(unsigned) * ns));
-        CUDA_TRY(cudaMalloc(&d_status, sizeof(unsigned) * ns));
+        d_status = reinterpret_cast<unsigned*>(d_total + (size_t)ns * 2);
         CUDA_TRY(cudaMemset(d_counter, 0, sizeof(unsigned) * ns));
         CUDA_TRY(cudaMemset(d_status, 0, sizeof(unsigned) * ns));
         for (Segment& g : seg) {
-            CUDA_TRY(cudaMallocHost(&g.h_total, sizeof(double) * ns * 2));
-            CUDA_TRY(cudaMallocHost(&g.h_status, sizeof(unsigned) * ns));
+            CUDA_TRY(cudaMallocHost(&g.h_total, (sizeof(double) * 2 + sizeof(unsigned)) * ns));
+            g.h_status = reinterpret_cast<unsigned*>(g.h_total + (size_t)ns * 2);
         }
         slots = ns;
         if (world > 1) {
@@ -337,6 +336,7 @@ struct scicone_chain {
     bool with_od = false;     // the compiled proposal carries the root-score part
     // queued proposal
     bool pending = false;
+    bool compiled = false;  // the queued proposal's blob is built (scicone_prepare_t_prime or the batch call)
     bool evaluated = false;
     TreeCopy tp;
     std::vector<int> roots;
@@ -379,6 +379,7 @@ void drop_pending(scicone_chain* ch) {
     ch->p.clear();
     ch->roots.clear();
     ch->pending = false;
+    ch->compiled = false;
     ch->evaluated = false;
     ch->deleted_id = -1;
     ch->p_full = false;
@@ -463,6 +464,14 @@ void fill_header_common(scicone_chain* ch, int slot, DevHeader& H) {
     H.status = ds->d_status + slot;
 }
 
+// The reduction scratch of a compiled blob is chosen when the batch is put together.
+void patch_slot(scicone_chain* ch, int slot) {
+    DevHeader H;
+    memcpy(&H, ch->blob.data(), sizeof H);
+    fill_header_common(ch, slot, H);
+    memcpy(ch->blob.data(), &H, sizeof H);
+}
+
 // Compile the queued proposal of `ch` into ch->blob (+ ch->builds).  `slot` selects the reduction scratch.
 int compile_proposal(scicone_chain* ch, int slot, bool full) {
     scicone_dataset* ds = ch->ds;
@@ -483,6 +492,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
 
     std::vector<DevTask> tasks;
     std::vector<DevEvent> events;
+    std::vector<const double*> prow;  // per task: where its parent's score lives
+    std::vector<int> ptask;           // per task: task index of the parent, -1 when the parent is not rescored before
     std::vector<int> task_of_node(T.n, -1);
     std::vector<int> stack;
     for (size_t ri = 0; ri < ch->roots.size(); ++ri) {
@@ -497,7 +508,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             DevTask tk;
             memset(&tk, 0, sizeof tk);
             tk.node_id = id;
-            tk.parent_task = -1;
+            int parent_task = -1;
+            const double* parent_row = nullptr;
             tk.ev_begin = (int)events.size();
             int z_int;
             if (pidx < 0) {  // Tree::compute_root_score, Tree.h:145-160
@@ -514,11 +526,11 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     auto cit = ch->t.find(pid);
                     if (cit == ch->t.end())
                         return fail(SCICONE_ERR_STATE, "parent id %d of the rescored subtree is not in the committed table", pid);
-                    tk.parent_row = cit->second.row;
+                    parent_row = cit->second.row;
                     pz = (pit != ch->p.end()) ? pit->second.z : cit->second.z;
                 } else {
-                    tk.parent_task = (short)task_of_node[pidx];
-                    tk.parent_row = tasks[task_of_node[pidx]].dst;
+                    parent_task = task_of_node[pidx];
+                    parent_row = tasks[parent_task].dst;
                     pz = pit->second.z;
                 }
                 // Tree::compute_score, Tree.h:177-198: z = parent.z + sum_k r_k (cn_node - cn_parent)
@@ -573,7 +585,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     tk.nzp = nu * zp;
                     tk.lg_nz = lgamma(tk.nz);
                     tk.lg_nzp = lgamma(tk.nzp);
-                    if (tk.parent_task >= 0 && memcmp(&tasks[tk.parent_task].nz, &tk.nzp, sizeof(double)) == 0)
+                    if (parent_task >= 0 && memcmp(&tasks[parent_task].nz, &tk.nzp, sizeof(double)) == 0)
                         tk.flags |= TASK_REUSE_G;
                 } else {  // Tree.h:236-237
                     tk.lg_nz = log(zd);
@@ -591,6 +603,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             tk.dst = own->second.row;
             task_of_node[n] = (int)tasks.size();
             tasks.push_back(tk);
+            prow.push_back(parent_row);
+            ptask.push_back(parent_task);
             for (int c = child_off[n + 1] - 1; c >= child_off[n]; --c) stack.push_back(child[c]);
         }
     }
@@ -601,6 +615,29 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         for (size_t i = 0; i < tasks.size(); ++i) last[tasks[i].node_id] = (int)i;
         for (size_t i = 0; i < tasks.size(); ++i)
             if (last[tasks[i].node_id] != (int)i) tasks[i].flags |= TASK_SKIP_AGG;
+    }
+    // Walk order bookkeeping for the one-thread-per-cell kernel: a node whose parent was visited just before takes the
+    // parent's score (and, with TASK_REUSE_G, its z-term) from registers; any other parent score is prefetched while
+    // the previous node is processed.  Chunks: what is staged in shared memory together.
+    std::vector<DevChunk> chunks;
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        if (ptask[i] >= 0 && ptask[i] == (int)i - 1) tasks[i].flags |= TASK_CHAINED;
+        else tasks[i].flags &= (unsigned char)~TASK_REUSE_G;  // the previous node's z-term is only at hand when chained
+        if (i + 1 < tasks.size() && !(tasks[i + 1].flags & TASK_ROOT) && ptask[i + 1] != (int)i) tasks[i].prefetch_row = prow[i + 1];
+        if (tasks[i].n_ev > kEvStage) tasks[i].flags |= TASK_BIG;
+        const int staged = (tasks[i].flags & TASK_BIG) ? 0 : tasks[i].n_ev;
+        if (chunks.empty() || chunks.back().n_tasks >= kTaskChunk || chunks.back().n_ev + staged > kEvStage) {
+            DevChunk c;
+            c.first_task = (int)i;
+            c.n_tasks = 0;
+            c.ev_base = tasks[i].ev_begin;
+            c.n_ev = 0;
+            chunks.push_back(c);
+        }
+        DevChunk& c = chunks.back();
+        tasks[i].ev_rel = (unsigned short)(tasks[i].ev_begin - c.ev_base);
+        c.n_tasks++;
+        if (!(tasks[i].flags & TASK_BIG)) c.n_ev = tasks[i].ev_begin + tasks[i].n_ev - c.ev_base;
     }
     std::vector<const double*> old_rows;
     std::vector<DevUnch> unch;
@@ -632,6 +669,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     DevHeader H;
     memset(&H, 0, sizeof H);
     H.n_tasks = (int)tasks.size();
+    H.n_chunks = (int)chunks.size();
+    H.first_parent_row = (!tasks.empty() && !(tasks[0].flags & TASK_ROOT)) ? prow[0] : nullptr;
     H.n_old = (int)old_rows.size();
     H.n_unch = (int)unch.size();
     H.deleted_id = ch->deleted_id;
@@ -658,6 +697,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     b.resize(sizeof(DevHeader));
     H.off_tasks = (unsigned)blob_append(b, tasks);
     H.off_events = (unsigned)blob_append(b, events);
+    H.off_chunks = (unsigned)blob_append(b, chunks);
     H.off_old = (unsigned)blob_append(b, old_rows);
     H.off_unch = (unsigned)blob_append(b, unch);
     H.off_od_rows = (unsigned)blob_append(b, slice_rows);
@@ -741,7 +781,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, ds->stream));
-        build_rows_kernel<<<dim3((ds->M + kBuildBlock - 1) / kBuildBlock, (unsigned)n_items), kBuildBlock, 0, ds->stream>>>(
+        build_rows_kernel<<<dim3((ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells), (unsigned)n_items), kBuildBlock, 0, ds->stream>>>(
             ds->d_arena, (unsigned)off_items);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
@@ -763,8 +803,9 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
         CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
     } else
-        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ds->stream));
-    CUDA_TRY(cudaMemcpyAsync(g.h_status, ds->d_status, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, (sizeof(double) * 2 + sizeof(unsigned)) * ds->slots, cudaMemcpyDeviceToHost, ds->stream));
+    if (ds->world > 1)
+        CUDA_TRY(cudaMemcpyAsync(g.h_status, ds->d_status, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ds->stream));
     CUDA_TRY(cudaEventRecord(g.done, ds->stream));
     ds->h2d_bytes += bytes;
     ds->d2h_bytes += (ds->world > 1 ? sizeof(double) * 2 * n * ds->max_chunks_rank * ds->world : sizeof(double) * 2 * n) + sizeof(unsigned) * n;
@@ -838,6 +879,7 @@ int launch_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, d
 
 int od_scores(scicone_chain* ch, double nu, double* out) {
     scicone_dataset* ds = ch->ds;
+    if (ch->compiled && !ch->evaluated) return fail(SCICONE_ERR_STATE, "root scores must be requested before scicone_prepare_t_prime");
     int rc = ds->set_device();
     if (rc) return rc;
     rc = ds->ensure_slots(1);
@@ -980,11 +1022,10 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     ds->pool.destroy();
     cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW);
     cudaFree(ds->d_arena); cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
-    cudaFree(ds->d_counter); cudaFree(ds->d_status); cudaFree(ds->d_gather); cudaFree(ds->d_send);
+    cudaFree(ds->d_counter); cudaFree(ds->d_gather); cudaFree(ds->d_send);
     for (scicone_dataset::Segment& g : ds->seg) {
         if (g.h_arena) cudaFreeHost(g.h_arena);
         if (g.h_total) cudaFreeHost(g.h_total);
-        if (g.h_status) cudaFreeHost(g.h_status);
         if (g.h_gather) cudaFreeHost(g.h_gather);
         if (g.evb) cudaEventDestroy(g.evb);
         if (g.ev0) cudaEventDestroy(g.ev0);
@@ -1083,6 +1124,7 @@ int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t_prim
     if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
     if (ch->t.empty()) return fail(SCICONE_ERR_STATE, "compute_t_prime_scores before compute_t_table");
     if (ch->evaluated) return fail(SCICONE_ERR_STATE, "the previous proposal was neither accepted nor rejected");
+    if (ch->compiled) return fail(SCICONE_ERR_STATE, "compute_t_prime_scores after scicone_prepare_t_prime");
     if (!ch->pending) {
         int rc = validate_tree(t_prime, ch->ds->K);
         if (rc) return rc;
@@ -1092,6 +1134,20 @@ int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t_prim
     }
     if (node_idx < 0 || node_idx >= ch->tp.n) return fail(SCICONE_ERR_ARG, "node index %d outside the tree", node_idx);
     ch->roots.push_back(node_idx);
+    return SCICONE_OK;
+}
+
+int scicone_prepare_t_prime(scicone_chain* ch) {
+    if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    if (!ch->pending || ch->roots.empty()) return fail(SCICONE_ERR_STATE, "prepare_t_prime without compute_t_prime_scores");
+    if (ch->evaluated) return fail(SCICONE_ERR_STATE, "proposal already evaluated");
+    if (ch->compiled) return SCICONE_OK;
+    int rc = compile_proposal(ch, 0, false);
+    if (rc) {
+        drop_pending(ch);
+        return rc;
+    }
+    ch->compiled = true;
     return SCICONE_OK;
 }
 
@@ -1110,14 +1166,17 @@ int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const
     if (rc) return rc;
     rc = ds->ensure_slots(n);
     if (rc) return rc;
-    {   // the blobs of the n proposals are independent: compile them on the pool (the row pool is locked inside)
+    {   // blobs not yet built by scicone_prepare_t_prime are independent of each other: compile them on the pool
         struct Job {
             scicone_chain* const* chains;
-            std::vector<int> rc;
+            std::vector<int> todo, rc;
             std::vector<std::string> msg;
-        } job{chains, std::vector<int>(n, 0), std::vector<std::string>(n)};
-        scicone::ForkJoinPool::instance().run(n, [](int i, void* ctx) {
+        } job{chains, {}, std::vector<int>(n, 0), std::vector<std::string>(n)};
+        for (int i = 0; i < n; ++i)
+            if (!chains[i]->compiled) job.todo.push_back(i);
+        scicone::ForkJoinPool::instance().run((int)job.todo.size(), [](int q, void* ctx) {
             Job& j = *static_cast<Job*>(ctx);
+            const int i = j.todo[q];
             j.rc[i] = compile_proposal(j.chains[i], i, false);
             if (j.rc[i]) j.msg[i] = g_err;  // thread-local in the worker
         }, &job);
@@ -1127,6 +1186,10 @@ int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const
                 g_err = job.msg[i];
                 return job.rc[i];
             }
+        for (int i = 0; i < n; ++i) {
+            chains[i]->compiled = true;
+            patch_slot(chains[i], i);
+        }
     }
     unsigned long long tk = 0;
     rc = submit_proposals(ds, chains, n, &tk);

@@ -469,13 +469,13 @@ inline void parallel_chains(int n, F&& fn) {
 }
 
 // Advance `chains` (all on one dataset) by n_iters iterations.  The chains are split into `n_groups` groups (default:
-// two when there are at least 8 chains); a group moves in lock-step - its chains draw and queue their proposals in
-// parallel on the host pool, ONE kernel launch scores them all, then they accept / reject in parallel - and while the
-// launch of one group is in flight the host works on the other group.  Every chain still sees exactly the sequence
+// two when there are at least 8 chains); a group moves in lock-step - its chains finish the previous step, draw the
+// next proposal and build its launch description in parallel on the host pool, then ONE kernel launch scores them
+// all - and while the launch of one group is in flight the host works on the other group.  Every chain still sees exactly the sequence
 // propose -> score -> compare of the reference's loop (Inference::infer_mcmc, Inference.h:518-913), so its trajectory
 // does not depend on the grouping or on the number of threads.
 struct HostPhaseTimes {  // wall time of the driver thread per phase, microseconds (for --stats_file)
-    double propose_us = 0, submit_us = 0, wait_us = 0, finish_us = 0;
+    double host_us = 0, submit_us = 0, wait_us = 0;  // parallel finish+propose+prepare region / launch / waiting for the GPU
 };
 
 inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
@@ -514,11 +514,40 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
         groups[g].tot_m.assign(n, 0.0);
         groups[g].od_m.assign(n, 0.0);
     }
-    auto propose_group = [&](Group& g) {
+    // One visit of a group: collect the launch of its previous step, then ONE parallel region in which every chain
+    // finishes that step (compare, accept / reject), draws its next proposal and builds the launch description, then
+    // one launch for the whole group.
+    auto visit = [&](Group& g, int it) {  // `it` = step to propose; step it-1 (if any) is finished first
         const int n = static_cast<int>(g.members.size());
         Clock::time_point t0 = Clock::now();
-        parallel_chains(n, [&](int i) { g.scored[i] = chains[g.members[i]]->propose(move_probs, size_limit) ? 1 : 0; });
-        T.propose_us += us_since(t0);
+        if (g.in_flight) {
+            int rc = scicone_batch_wait(ds, g.ticket, g.totals.data(), g.ods.data());
+            if (rc != SCICONE_OK && rc != SCICONE_ERR_NAN) abi_check(rc);
+            g.in_flight = false;
+            for (size_t h = 0; h < g.who.size(); ++h) {
+                g.tot_m[g.who[h]] = g.totals[h];
+                g.od_m[g.who[h]] = g.ods[h];
+            }
+        }
+        T.wait_us += us_since(t0);
+        t0 = Clock::now();
+        parallel_chains(n, [&](int i) {
+            Inference* c = chains[g.members[i]];
+            if (it > 0) {
+                if (g.scored[i]) {
+                    int32_t nr = 0;
+                    scicone_t_prime_n_rescored(c->chain, &nr);
+                    c->rescored_last = static_cast<unsigned>(nr);
+                }
+                c->finish(g.scored[i] != 0, g.tot_m[i], g.od_m[i], it - 1);
+            }
+            if (it < n_iters) {
+                g.scored[i] = c->propose(move_probs, size_limit) ? 1 : 0;
+                if (g.scored[i]) abi_check(scicone_prepare_t_prime(c->chain));
+            }
+        });
+        T.host_us += us_since(t0);
+        if (it >= n_iters) return;
         t0 = Clock::now();
         g.handles.clear();
         g.who.clear();
@@ -531,37 +560,8 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
         if (g.in_flight) abi_check(scicone_batch_submit(g.handles.data(), nullptr, static_cast<int32_t>(g.handles.size()), &g.ticket));
         T.submit_us += us_since(t0);
     };
-    auto finish_group = [&](Group& g, int it) {
-        const int n = static_cast<int>(g.members.size());
-        Clock::time_point t0 = Clock::now();
-        if (g.in_flight) {
-            int rc = scicone_batch_wait(ds, g.ticket, g.totals.data(), g.ods.data());
-            if (rc != SCICONE_OK && rc != SCICONE_ERR_NAN) abi_check(rc);
-            g.in_flight = false;
-        }
-        T.wait_us += us_since(t0);
-        t0 = Clock::now();
-        for (size_t h = 0; h < g.who.size(); ++h) {
-            g.tot_m[g.who[h]] = g.totals[h];
-            g.od_m[g.who[h]] = g.ods[h];
-        }
-        parallel_chains(n, [&](int i) {
-            Inference* c = chains[g.members[i]];
-            if (g.scored[i]) {
-                int32_t nr = 0;
-                scicone_t_prime_n_rescored(c->chain, &nr);
-                c->rescored_last = static_cast<unsigned>(nr);
-            }
-            c->finish(g.scored[i] != 0, g.tot_m[i], g.od_m[i], it);
-        });
-        T.finish_us += us_since(t0);
-    };
-    for (int it = 0; it < n_iters; ++it)
-        for (Group& g : groups) {
-            if (it > 0) finish_group(g, it - 1);
-            propose_group(g);
-        }
-    for (Group& g : groups) finish_group(g, n_iters - 1);
+    for (int it = 0; it <= n_iters; ++it)
+        for (Group& g : groups) visit(g, it);
 }
 
 }  // namespace scicone_host
