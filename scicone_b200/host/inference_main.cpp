@@ -289,15 +289,20 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
             scicone_kernel_launches(ds, &launches);
             uint64_t dev_bytes = 0;
             scicone_device_bytes(ds, &dev_bytes);
-            unsigned long long acc = 0, rej = 0, resc = 0;
-            for (Inference* c : chains) { acc += c->n_accepted; rej += c->n_rejected; resc += c->n_rescored_nodes; }
+            unsigned long long acc = 0, rej = 0, resc = 0, attempts = 0;
+            double cf = 0, cp = 0, cq = 0, cmax = 0;
+            for (Inference* c : chains) {
+                acc += c->n_accepted; rej += c->n_rejected; resc += c->n_rescored_nodes; attempts += c->n_attempts;
+                cf += c->t_finish_us; cp += c->t_propose_us; cq += c->t_prepare_us; cmax = std::max(cmax, c->t_max_visit_us);
+            }
             std::ofstream sf(a.str("stats_file"));
             sf << std::setprecision(17) << "{\"n_chains\":" << n_chains << ",\"n_iters\":" << n_iters << ",\"n_cells\":" << n_cells
                << ",\"wall_us\":" << duration.count() << ",\"device_region_ms\":" << region_ms << ",\"score_kernel_us\":" << kern_us
                << ",\"score_kernel_launches\":" << n_timed << ",\"build_kernel_us\":" << build_us << ",\"build_kernel_launches\":" << n_build
                << ",\"gpu_launches\":" << (launches - launches0) << ",\"h2d_bytes\":" << k[0] << ",\"d2h_bytes\":" << k[1]
                << ",\"alg_bytes\":" << k[2] << ",\"n_scores\":" << k[3] << ",\"device_bytes\":" << dev_bytes << ",\"accepted\":" << acc
-               << ",\"rejected\":" << rej << ",\"rescored_nodes\":" << resc << ",\"host_threads\":" << scicone_host_threads() << ",\"host_us\":" << phase.host_us
+               << ",\"rejected\":" << rej << ",\"rescored_nodes\":" << resc << ",\"host_threads\":" << scicone_host_threads() << ",\"attempts\":" << attempts << ",\"chain_finish_us\":" << cf << ",\"chain_propose_us\":" << cp
+               << ",\"chain_prepare_us\":" << cq << ",\"chain_max_visit_us\":" << cmax << ",\"host_us\":" << phase.host_us
                << ",\"submit_us\":" << phase.submit_us << ",\"wait_us\":" << phase.wait_us << "}" << std::endl;
         }
 

@@ -86,10 +86,13 @@ public:
     // state of the iteration in flight
     unsigned move_id = 0;
     bool queued = false;            // t_prime has subtrees queued on the device
+    bool tp_pristine = false;       // t_prime is exactly the copy of t made by the last restore (and t has not changed since)
     bool nu_move = false;
     double t_total = 0.0;           // committed sum_j aggregate_j * cluster_size_j
     double gamma = 1.0, alpha = 0.0;
     unsigned n_accepted = 0, n_rejected = 0;
+    double t_finish_us = 0, t_propose_us = 0, t_prepare_us = 0, t_max_visit_us = 0;  // time spent in this chain's host work
+    unsigned long long n_attempts = 0;
     unsigned long long n_rescored_nodes = 0;  // sum over scored proposals of the rescored subtree sizes
     bool have_first_score = false;
     double first_score = 0.0;
@@ -139,7 +142,17 @@ public:
         t.compute_weights();
     }
     void initialize_from_file(const std::string& path) { t.load_from_file(path); }
-    void update_t_prime() { t_prime.copy_from(t); }
+    void update_t_prime() {
+        t_prime.copy_from(t);
+        tp_pristine = true;
+    }
+    // Tree::operator= of the reference after a failed attempt / a rejection (Inference.h:1489,1495,881).  The copy is a
+    // pure function of `t` (sibling order included), so it is skipped when t_prime already is that copy, untouched.
+    void restore_t_prime() {
+        if (tp_pristine && !t_prime.dirty) return;
+        t_prime.copy_from(t);
+        tp_pristine = true;
+    }
 
     // ---- priors (Inference::log_tree_prior / log_tree_posterior, Inference.h:956-994) -----------------------------
     double log_tree_prior(int m, int n) const {
@@ -222,6 +235,7 @@ public:
                 double step = rng.normal(0.0, 0.02);
                 double log_nu = std::log(t_prime.nu) + step;
                 if (log_nu > 10.0) return false;
+                t_prime.dirty = true;
                 t_prime.nu = std::exp(log_nu);
                 nu_move = true;  // the root score at the new nu comes back with the proposal's launch
                 queue(t_prime.root);
@@ -244,18 +258,19 @@ public:
         if (move_id == 10) return false;  // handled entirely on the host in finish()
         for (unsigned a = 0; a < 50; ++a) {  // Inference::apply_multiple_times, Inference.h:1462-1498
             bool ok = false;
+            ++n_attempts;
             try {
                 ok = attempt(size_limit);
             } catch (const InvalidMove&) {
                 break;  // no point in retrying
             } catch (const std::exception&) {
                 drop_queue();
-                t_prime.copy_from(t);
+                restore_t_prime();
                 continue;
             }
             if (ok) return true;
             drop_queue();
-            t_prime.copy_from(t);
+            restore_t_prime();
         }
         return false;
     }
@@ -381,6 +396,7 @@ public:
                 trace_move(static_cast<int>(move_id), iter);
                 t.posterior_score = log_tree_posterior(t_total, m, t);
                 t_prime.copy_from(t);
+                tp_pristine = true;
             }
         } else {
             bool take = false;
@@ -403,13 +419,14 @@ public:
                 queued = false;
                 t_total = total;
                 t.copy_from(t_prime);
+                tp_pristine = false;  // t changed: t_prime is the original, not the copy
                 if ((t_prime.posterior_score + t_prime.od_score) > (best_tree.posterior_score + best_tree.od_score)) best_tree.copy_from(t_prime);
             } else {
                 if (move_id != 13 && std::abs(score_diff) > 0.1) gamma *= std::exp((0.0 - alpha) * alpha);
                 trace_move(-1, iter);
                 ++n_rejected;
                 drop_queue();
-                t_prime.copy_from(t);
+                restore_t_prime();
             }
             if (gamma > 100.0) gamma = 100.0;
             if (gamma < 1.0 / 100.0) gamma = 1.0 / 100.0;
@@ -533,6 +550,8 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
         t0 = Clock::now();
         parallel_chains(n, [&](int i) {
             Inference* c = chains[g.members[i]];
+            const Clock::time_point c0 = Clock::now();
+            Clock::time_point c1 = c0, c2 = c0;
             if (it > 0) {
                 if (g.scored[i]) {
                     int32_t nr = 0;
@@ -540,11 +559,19 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
                     c->rescored_last = static_cast<unsigned>(nr);
                 }
                 c->finish(g.scored[i] != 0, g.tot_m[i], g.od_m[i], it - 1);
+                c1 = c2 = Clock::now();
             }
             if (it < n_iters) {
                 g.scored[i] = c->propose(move_probs, size_limit) ? 1 : 0;
+                c2 = Clock::now();
                 if (g.scored[i]) abi_check(scicone_prepare_t_prime(c->chain));
             }
+            const Clock::time_point c3 = Clock::now();
+            auto us = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+            c->t_finish_us += us(c0, c1);
+            c->t_propose_us += us(c1, c2);
+            c->t_prepare_us += us(c2, c3);
+            c->t_max_visit_us = std::max(c->t_max_visit_us, us(c0, c3));
         });
         T.host_us += us_since(t0);
         if (it >= n_iters) return;

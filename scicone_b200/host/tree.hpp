@@ -284,6 +284,7 @@ public:
     Rng* rng = nullptr;
     double posterior_score = 0.0, prior_score = 0.0, od_score = 0.0, total_attachment_score = 0.0;
     double nu = 1.0;
+    bool dirty = false;          // set by a move right before its first change: an untouched copy need not be re-made after a failed attempt
 
     Tree() {}
     Tree(int ploidy_, unsigned n_regions_, const std::vector<int>& neutral_, const Params* p, Rng* r)
@@ -414,6 +415,7 @@ public:
     // reversed and `order` becomes that walk (Tree::copy_tree / copy_tree_nodes, Tree.h:490-542).
     void copy_from(const Tree& src) {
         if (this == &src) return;
+        dirty = false;
         neutral = src.neutral;
         ploidy = src.ploidy;
         total_attachment_score = src.total_attachment_score;
@@ -477,9 +479,12 @@ public:
     // two nodes with the same genotype (Tree::is_redundant, Tree.h:1198-1223; the reference compares 64-bit hashes of
     // the genotype first and the maps on a hit - equal maps always hit, so the exact comparison decides)
     bool is_redundant() const {
-        std::map<EventMap, int> seen;
-        for (int n : order)
-            if (!seen.emplace(pool[n].c, n).second) return true;
+        std::vector<const EventMap*> g;
+        g.reserve(order.size());
+        for (int n : order) g.push_back(&pool[n].c);
+        std::sort(g.begin(), g.end(), [](const EventMap* a, const EventMap* b) { return *a < *b; });
+        for (size_t i = 1; i < g.size(); ++i)
+            if (*g[i - 1] == *g[i]) return true;
         return false;
     }
 
@@ -698,6 +703,7 @@ public:
         for (int d : descendents(pruned, true)) dest.erase(std::remove(dest.begin(), dest.end(), d), dest.end());
         int target = dest[rng->uniform_int(1, static_cast<int>(dest.size())) - 1];
         if (pool[pool[pruned].parent].id == pool[target].id) return -1;
+        dirty = true;
         detach(pruned);
         attach(target, pruned);
         update_desc_labels(pruned);
@@ -722,6 +728,7 @@ public:
             throw std::logic_error("swapping 2 nodes with the same labels does not make sense, the move will be rejected");
         if (pool[a].parent == pool[b].parent && pool[a].first_child == -1 && pool[b].first_child == -1)
             throw std::logic_error("swapping the sibling leaves will have no impact, move will be rejected.");
+        dirty = true;
         pool[a].c_change.swap(pool[b].c_change);
         std::vector<int> out;
         if (is_ancestor(a, b))
@@ -749,6 +756,7 @@ public:
         std::set<unsigned> regions;
         while (static_cast<int>(regions.size()) < want) regions.insert(static_cast<unsigned>(rng->uniform_int(0, static_cast<int>(n_regions) - 1)));
         EventMap& ev = pool[node].c_change;
+        dirty = true;
         for (unsigned k : regions) {  // ascending region order
             int copies = rng->poisson(P->lambda_c) + 1;
             bool up = rng->coin();
@@ -797,6 +805,7 @@ public:
         int block = rng->uniform_int(0, static_cast<int>(pool[node].event_blocks.size() - 1));
         bool from_end = rng->coin();
         bool expand = rng->coin();
+        dirty = true;
         expand_shrink_block(node, block, expand, from_end);
         if (all_zero(pool[node].c_change)) return -1;
         update_desc_labels(node);
@@ -813,6 +822,7 @@ public:
             int parent = order[rng->discrete(chi.begin(), chi.end())];
             EventMap labels = random_labels(1, 0.1);  // default arguments of the reference, not the chain's lambda_r (quirk Q14)
             std::vector<int> kids = children(parent);
+            dirty = true;
             int fresh = new_child(parent, labels);
             for (int k : kids)
                 if (rng->coin()) {
@@ -823,6 +833,7 @@ public:
         } else {  // delete
             if (order.size() <= 1) throw std::logic_error("Root cannot be deleted, delete move will be rejected");
             int idx = rng->discrete(omega.begin(), omega.end());
+            dirty = true;
             rescore = remove_node(descendents(root, false)[idx]);
         }
         update_desc_labels(rescore);
@@ -856,6 +867,7 @@ public:
                 if (upper.at(e.first) == 0) upper.erase(e.first);
                 if (lower.at(e.first) == 0) lower.erase(e.first);
             }
+            dirty = true;
             pool[node].c_change = upper;
             std::vector<int> kids = children(node);
             int fresh = new_child(node, lower);
@@ -883,6 +895,7 @@ public:
             }
             if (merged.size() == 1 && merged.begin()->second == 1)
                 throw std::logic_error("Nodes cannot be combined if they result in a single event");
+            dirty = true;
             pool[par].c_change = merged;
             rescore = remove_node(node);
         }
@@ -917,6 +930,7 @@ public:
         int b = sibs[rng->discrete(idx.begin(), idx.end())];
         EventMap common = shared_events(a, b);
         if (common.empty()) throw std::logic_error("Can not create common ancestor from siblings with no intersection.");
+        dirty = true;
         for (auto const& e : common)
             for (int n : {a, b}) {
                 EventMap& ev = pool[n].c_change;
@@ -939,7 +953,9 @@ public:
         std::vector<int> leaves;
         for (int n : order)
             if (pool[n].first_child == -1) leaves.push_back(n);
-        return remove_node(leaves[rng->uniform_int(0, static_cast<int>(leaves.size()) - 1)]);
+        const int victim = leaves[rng->uniform_int(0, static_cast<int>(leaves.size()) - 1)];
+        dirty = true;
+        return remove_node(victim);
     }
 
     // Gibbs move over all re-attachments that keep every genotype (Tree.h:1842-1999).  Acts on the committed tree and
