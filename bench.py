@@ -14,11 +14,13 @@ cell-sharded GPUs (weak scaling: every rank holds its own 10 000 cells) and over
 reference's `inference` timer yields directly (iterations/s x cells).  Chain iterations/s and cell x node
 attachment scores/s are reported next to it.
 
-  value  device pipeline: proposals are queued on the stream without waiting for their totals (accept/reject are
-         host-side pointer swaps), count matrix / score tables / lgamma rows resident in HBM, region timed with
-         CUDA events on the engine's stream.
-  e2e    the real MCMC loop through the C ABI: every step stages its proposals from host memory, launches, and
-         reads the B totals back before the next step can start (wall clock, sync on both sides).
+  value  device pipeline: proposals (pre-generated valid moves, scicone_b200.synth.TreeState) are queued on the stream
+         without waiting for their totals (accept/reject are host-side pointer swaps), count matrix / score tables /
+         lgamma rows resident in HBM, region timed with CUDA events on the engine's stream.
+  e2e    the real MCMC: this repo's native host (scicone_b200/bin/inference - the reference's CLI, move set, priors and
+         accept rule on top of the C ABI) runs the same B restarts with the same flags and seeds as the reference arm;
+         every step stages its proposal blobs from host memory, launches, and reads the B totals back before the chains
+         can decide.  Timer = the host's own clock around infer_mcmc, exactly what the reference arm reports.
 """
 import argparse
 import json
@@ -147,7 +149,7 @@ def run_engine(args):
         ds.attach_comm(uid[0], rank, world)
     # identical proposal streams on every rank (the tree is replicated, only cells are sharded)
     ref_data = make_counts(64, args.bins, args.regions, seed=SEED)  # only region count / neutral states matter here
-    traces = build_chain_traces(ref_data, B, args.nodes, 2 * (W + K), SEED, args.nu)
+    traces = build_chain_traces(ref_data, B, args.nodes, W + K, SEED, args.nu)
     chains = [Chain(dataset=ds) for _ in range(B)]
     for ch, (start, _) in zip(chains, traces):
         ch.compute_t_table(start)
@@ -160,39 +162,22 @@ def run_engine(args):
         torch.cuda.synchronize()
 
     def queue_step(s):
-        for ch, (_, steps) in zip(chains, traces):
-            ft, roots, _, kind = steps[s]  # a nu proposal gets its root score from the same launch
-            for idx in roots:
-                ch.compute_t_prime_scores(ft, idx)
+        firsts, idx = [], []
+        for _, steps in traces:
+            ft, roots, _, _ = steps[s]  # a nu proposal gets its root score from the same launch
+            firsts.append(ft)
+            idx.append(roots[0])
+        launcher.queue(firsts, idx)
+        for ch, (_, steps) in zip(chains, traces):  # label swaps rescore two subtrees
+            ft, roots, _, _ = steps[s]
+            for extra in roots[1:]:
+                ch.compute_t_prime_scores(ft, extra)
 
     def settle_step(s):
-        for ch, (_, steps) in zip(chains, traces):
-            if steps[s][2]:
-                ch.accept()
-            else:
-                ch.reject()
-
-    # ---------------- e2e: lock-step MCMC loop through the C ABI (totals read back every step)
-    for s in range(W):
-        queue_step(s)
-        launcher.run()
-        settle_step(s)
-    ds.counters(reset=True)
-    launches0 = ds.kernel_launches()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    t0 = time.perf_counter()
-    for s in range(W, W + K):
-        queue_step(s)
-        launcher.run()
-        settle_step(s)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    cnt_e2e = ds.counters(reset=True)
-    launches_e2e = ds.kernel_launches() - launches0
+        launcher.settle([steps[s][2] for _, steps in traces])
 
     # ---------------- value: device pipeline, totals collected with a lag, timed by CUDA events on the engine stream
-    base = W + K
+    base = 0
     ds.set_profiling(True)
     for s in range(base, base + W):
         queue_step(s)
@@ -202,6 +187,7 @@ def run_engine(args):
     ds.counters(reset=True)
     launches1 = ds.kernel_launches()
     barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
     ds.region_mark(0)
     tickets = []
     for s in range(base + W, base + W + K):
@@ -215,11 +201,15 @@ def run_engine(args):
     ds.region_mark(1)
     barrier()
     dev_ms = ds.region_elapsed_ms()
-    clocks = sampler.stop() if sampler else None
     kern_us, n_timed = ds.kernel_time_stats()
     cnt_dev = ds.counters()
     launches_dev = ds.kernel_launches() - launches1
     ds.set_profiling(False)
+
+    # ---------------- e2e: the native MCMC host on the same matrix (all ranks: cell-sharded run of ONE set of chains)
+    host = None if args.no_e2e else run_native_host(args, data, rank, world, local, dist if world > 1 else None, comm_unique_id)
+    e2e_s = host["wall_us"] * 1e-6 if host else float("nan")
+    clocks = sampler.stop() if sampler else None
 
     # max over ranks
     if world > 1:
@@ -233,6 +223,9 @@ def run_engine(args):
         iters = B * K
         value = iters * cells_total / (dev_ms * 1e-3)
         e2e = iters * cells_total / e2e_s
+        if host is None:  # profiling runs (--no_e2e): placeholders, never a bench line
+            host = {"h2d_bytes": 0, "d2h_bytes": 0, "host_threads": 0, "accepted": 0, "rejected": 0, "gpu_launches": 0,
+                    "score_kernel_us": 0.0, "build_kernel_us": 0.0}
         achieved = cnt_dev["alg_bytes"] / (kern_us * 1e-6) / 1e9 if kern_us > 0 else 0.0
         resident = ds.device_bytes()
         out = {
@@ -244,12 +237,17 @@ def run_engine(args):
                                    f"{'max' if args.max_scoring else 'sum'} scoring, default move mix",
                        "cells_per_gpu": M, "regions": args.regions, "chains": B, "tree_nodes": args.nodes,
                        "max_scoring": int(args.max_scoring), "parallelism": f"cells sharded x{world}" if world > 1 else "1 GPU",
-                       "proposal_source": "pre-generated valid proposals (scicone_b200.synth.TreeState), accept prob 0.3",
+                       "proposal_source": "value: pre-generated valid proposals (scicone_b200.synth.TreeState), accept prob 0.3; "
+                                          "e2e: real MCMC (native host)",
                        "l2": f"inputs larger than L2: {resident / 1e6:.0f} MB of score/lgamma rows + counts resident vs 126 MB L2"},
             "mcmc_iters_per_s": iters / (dev_ms * 1e-3),
             "scores_per_s": cnt_dev["n_scores"] * world / (dev_ms * 1e-3),
             "e2e": {"value": e2e, "unit": "cell_iters/s", "mcmc_iters_per_s": iters / e2e_s, "ms_per_step": 1e3 * e2e_s / K,
-                    "h2d_bytes_per_step": cnt_e2e["h2d_bytes"] / K, "d2h_bytes_per_step": cnt_e2e["d2h_bytes"] / K},
+                    "h2d_bytes_per_step": host["h2d_bytes"] / K, "d2h_bytes_per_step": host["d2h_bytes"] / K,
+                    "what": "scicone_b200/bin/inference (native MCMC host on the C ABI): real moves + Metropolis-Hastings, "
+                            f"{B} restarts (seeds 42..), {host['host_threads']} host threads, timer around infer_mcmc",
+                    "accepted": host["accepted"], "rejected": host["rejected"], "gpu_launches": host["gpu_launches"],
+                    "score_kernel_us_per_step": host["score_kernel_us"] / K, "build_kernel_us_per_step": host["build_kernel_us"] / K},
             "gpu_launches": int(launches_dev),
             "roofline": {"bound": "hbm", "kernel": "score_proposals_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -262,6 +260,59 @@ def run_engine(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_native_host(args, data, rank, world, local, dist, comm_unique_id):
+    """Real MCMC through the C ABI: scicone_b200/bin/inference with the reference arm's flags, B restarts in one process
+    per GPU.  With world > 1 the ranks' matrices are stacked into one (world x cells)-cell matrix and every rank's host
+    takes its chunk-aligned block of rows (cells sharded, tree replicated, NCCL all-gather of the chunk sums)."""
+    exe = os.path.join(ROOT, "scicone_b200", "bin", "inference")
+    if not os.path.exists(exe):
+        raise SystemExit("bench.py: scicone_b200/bin/inference is missing - run __graft_entry__.build()")
+    M, Kr = data["D"].shape
+    if world > 1:
+        import torch
+
+        mine = torch.from_numpy(np.ascontiguousarray(data["D"])).cuda()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        full = torch.cat(parts).cpu().numpy()
+        box = [tempfile.mkdtemp(prefix="scicone_e2e_") if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        tmp = box[0]
+        uid = [comm_unique_id().hex() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+    else:
+        full, tmp, uid = data["D"], tempfile.mkdtemp(prefix="scicone_e2e_"), [None]
+    try:
+        d = os.path.join(tmp, "d.f64")
+        r = os.path.join(tmp, "r.txt")
+        if rank == 0:
+            np.ascontiguousarray(full, dtype="<f8").tofile(d)
+            np.savetxt(r, data["region_sizes"], fmt="%d")
+        if world > 1:
+            dist.barrier()
+        stats = os.path.join(tmp, f"stats{rank}.json")
+        cmd = [exe, f"--d_matrix_file={d}", f"--region_sizes_file={r}", f"--n_cells={full.shape[0]}", f"--n_regions={Kr}",
+               f"--n_iters={args.steps}", f"--warmup_iters={args.warmup}", f"--n_nodes={args.nodes - 1}", "--seed=42", f"--nu={args.nu}",
+               "--verbosity=0", f"--max_scoring={'true' if args.max_scoring else 'false'}", f"--postfix=e2e{rank}",
+               f"--n_chains={args.chains}", f"--device={local}", f"--stats_file={stats}", "--stats_all_ranks=1"]
+        if world > 1:
+            cmd += [f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"]
+        env = dict(os.environ)
+        if world > 1:  # the host cores are shared by the ranks
+            env.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+        res = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise SystemExit("bench.py: native host failed:\n" + res.stdout[-2000:] + res.stderr[-2000:])
+        out = json.load(open(stats))
+        if world > 1:
+            dist.barrier()
+        return out
+    finally:
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -389,6 +440,7 @@ def main():
     ap.add_argument("--cpu_iters", type=int, default=150)
     ap.add_argument("--ref_iters_per_step", type=int, default=1)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_e2e", action="store_true", help="skip the native-host run (profiling passes only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -160,6 +160,15 @@ int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const
 int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* t_prime_sums, double* od_scores /* [n] or NULL */);
 
 /*
+ * Batched forms of the per-chain calls for hosts that drive many chains (one call instead of n, run on the worker
+ * pool): queue subtree root node_idx[i] of t_primes[i] on chains[i] (scicone_compute_t_prime_scores), and accept
+ * (accept[i] != 0) or reject chains[i].  The chains must be distinct.
+ */
+int scicone_batch_compute_t_prime_scores(scicone_chain* const* chains, const scicone_tree* const* t_primes,
+                                         const int32_t* node_idx, int32_t n);
+int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, int32_t n);
+
+/*
  * Accept (Inference.h:867-870: t_sums = t_prime_sums, t_maxs = t_prime_maxs,
  * update_t_scores(), and the proposal's od score / nu become the committed ones)
  * or reject (Inference.h:881,890) the queued proposal.  After a delete move the

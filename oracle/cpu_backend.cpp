@@ -142,6 +142,16 @@ int scicone_kernel_launches(scicone_dataset*, uint64_t* n) { *n = 0; return 0; }
 int scicone_parallel_for(int32_t n, void (*fn)(int32_t, void*), void* ctx) { scicone::ForkJoinPool::instance().run(n, fn, ctx); return 0; }
 int scicone_test_lgamma(int32_t, const double*, int32_t, double*) { return fail(-2, "cpu backend: no device lgamma"); }
 int scicone_prepare_t_prime(scicone_chain*) { return 0; }
+int scicone_batch_compute_t_prime_scores(scicone_chain* const* chains, const scicone_tree* const* t, const int32_t* idx, int32_t n) {
+    int rc = 0;
+    for (int i = 0; i < n; ++i) if (int r = scicone_compute_t_prime_scores(chains[i], t[i], idx[i])) rc = r;
+    return rc;
+}
+int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, int32_t n) {
+    int rc = 0;
+    for (int i = 0; i < n; ++i) if (int r = accept[i] ? scicone_accept(chains[i]) : scicone_reject(chains[i])) rc = r;
+    return rc;
+}
 int scicone_host_threads(void) { return scicone::ForkJoinPool::instance().n_threads(); }
 int scicone_counters(scicone_dataset*, double out[4], int32_t) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
 int scicone_region_mark(scicone_dataset*, int32_t) { return 0; }

@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_build_time_stats", "scicone_kernel_launches",
     "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
     "scicone_parallel_for", "scicone_host_threads", "scicone_test_lgamma", "scicone_prepare_t_prime",
+    "scicone_batch_compute_t_prime_scores", "scicone_batch_settle",
 ]
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}
@@ -92,6 +93,8 @@ def lib():
         L.scicone_region_mark.argtypes = [vp, C.c_int32]
         L.scicone_region_elapsed_ms.argtypes = [vp, dp]
         L.scicone_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.scicone_batch_compute_t_prime_scores.argtypes = [C.POINTER(vp), C.POINTER(tp), ip, C.c_int32]
+        L.scicone_batch_settle.argtypes = [C.POINTER(vp), ip, C.c_int32]
         L.scicone_test_lgamma.argtypes = [C.c_int32, dp, C.c_int32, dp]
         L.scicone_accept.argtypes = [vp]
         L.scicone_reject.argtypes = [vp]
@@ -355,6 +358,19 @@ class BatchLauncher:
 
     def run(self):
         return self.wait(self.submit())
+
+    def queue(self, trees, node_idx):
+        """scicone_batch_compute_t_prime_scores: subtree root node_idx[i] of trees[i] on chain i (one call for all chains)."""
+        tp = C.POINTER(CTree)
+        arr = (tp * self.n)(*[C.pointer(t.ctree) for t in trees])
+        idx = (C.c_int32 * self.n)(*[int(i) for i in node_idx])
+        self._keep = trees  # the CTree buffers must outlive the call
+        _check(lib().scicone_batch_compute_t_prime_scores(self._hs, arr, idx, self.n))
+
+    def settle(self, accept):
+        """scicone_batch_settle: accept[i] ? accept : reject for every chain."""
+        flags = (C.c_int32 * self.n)(*[1 if a else 0 for a in accept])
+        _check(lib().scicone_batch_settle(self._hs, flags, self.n))
 
 
 def device_lgamma(x, device=0):

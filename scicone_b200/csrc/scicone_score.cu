@@ -123,6 +123,28 @@ struct RowPool {
         std::lock_guard<std::mutex> lk(mu);
         free_rows.push_back(r);
     }
+    // bulk forms: one lock for a whole batch (the per-chain stashes below use these)
+    cudaError_t get_many(size_t n, std::vector<double*>& out) {
+        std::lock_guard<std::mutex> lk(mu);
+        while (free_rows.size() < n) {
+            void* p = nullptr;
+            cudaError_t e = cudaSetDevice(device);
+            if (e == cudaSuccess) e = cudaMalloc(&p, rows_per_slab * Mp * sizeof(double));
+            if (e != cudaSuccess) return e;
+            slabs.push_back(p);
+            for (size_t i = rows_per_slab; i-- > 0;) free_rows.push_back(static_cast<double*>(p) + i * Mp);
+            n_rows += rows_per_slab;
+        }
+        out.insert(out.end(), free_rows.end() - n, free_rows.end());
+        free_rows.resize(free_rows.size() - n);
+        return cudaSuccess;
+    }
+    void put_many(std::vector<double*>& rows, size_t keep) {
+        if (rows.size() <= keep) return;
+        std::lock_guard<std::mutex> lk(mu);
+        free_rows.insert(free_rows.end(), rows.begin() + keep, rows.end());
+        rows.resize(keep);
+    }
     void destroy() {
         for (void* p : slabs) cudaFree(p);
         slabs.clear();
@@ -182,8 +204,42 @@ int validate_tree(const scicone_tree* t, int K) {
     return SCICONE_OK;
 }
 
+// Ordered map on a sorted vector (find / emplace / erase / operator[] / ascending iteration, the subset of std::map used
+// here).  The tables have tens to hundreds of entries and are rebuilt for every proposal: contiguous storage keeps the
+// host side of a proposal free of per-entry heap allocations.
+template <class K, class V>
+class FlatMap {
+public:
+    typedef std::pair<K, V> value_type;
+    typedef typename std::vector<value_type>::iterator iterator;
+    iterator begin() { return v_.begin(); }
+    iterator end() { return v_.end(); }
+    size_t size() const { return v_.size(); }
+    bool empty() const { return v_.empty(); }
+    void clear() { v_.clear(); }
+    iterator find(const K& k) {
+        iterator it = lower(k);
+        return (it != v_.end() && it->first == k) ? it : v_.end();
+    }
+    size_t count(const K& k) { return find(k) != v_.end() ? 1 : 0; }
+    std::pair<iterator, bool> emplace(const K& k, const V& val) {
+        iterator it = lower(k);
+        if (it != v_.end() && it->first == k) return std::make_pair(it, false);
+        return std::make_pair(v_.insert(it, value_type(k, val)), true);
+    }
+    V& operator[](const K& k) { return emplace(k, V()).first->second; }
+    void erase(iterator it) { v_.erase(it); }
+    void swap(FlatMap& o) { v_.swap(o.v_); }
+
+private:
+    iterator lower(const K& k) {
+        return std::lower_bound(v_.begin(), v_.end(), k, [](const value_type& e, const K& key) { return e.first < key; });
+    }
+    std::vector<value_type> v_;
+};
+
 // (region, copy number of the node, copy number of the parent) -> delta row at one nu
-typedef std::unordered_map<uint64_t, double*> LCache;
+typedef FlatMap<uint64_t, double*> LCache;
 inline uint64_t lkey(int k, int cn, int cp) {
     return (uint64_t(uint32_t(k)) << 32) | (uint64_t(uint16_t(cn)) << 16) | uint64_t(uint16_t(cp));
 }
@@ -321,9 +377,11 @@ struct scicone_dataset {
     }
 };
 
+constexpr size_t kStashRefill = 32, kStashMax = 160;
+
 struct scicone_chain {
     scicone_dataset* ds = nullptr;
-    std::map<int, NodeRow> t;  // committed table, ascending node id (std::map order of the reference)
+    FlatMap<int, NodeRow> t;  // committed table, ascending node id (std::map order of the reference)
     double* sums[2] = {nullptr, nullptr};  // [0] committed t_sums, [1] primed
     int* maxid[2] = {nullptr, nullptr};
     // lgamma rows of the committed nu and of a proposed nu
@@ -340,7 +398,7 @@ struct scicone_chain {
     bool evaluated = false;
     TreeCopy tp;
     std::vector<int> roots;
-    std::map<int, NodeRow> p;  // rescored node id -> primed row
+    FlatMap<int, NodeRow> p;  // rescored node id -> primed row
     int deleted_id = -1;
     bool p_full = false;
     // blob under construction, the data-only lgamma work it needs first (K1 items + their per-region arrays),
@@ -350,13 +408,38 @@ struct scicone_chain {
     std::vector<double> build_aux;
     std::vector<double*> temp_rows;
     double alg_bytes = 0.0, n_scores = 0.0;
+    // rows handed out by the dataset's pool in bulk: the chain takes and returns rows here without a lock, so chains
+    // compiled / committed on different host threads do not meet at the pool's mutex on every row
+    struct Scratch {
+        std::vector<int> child_off, child, fill, ptask, task_of_node, stack;
+        std::vector<DevTask> tasks;
+        std::vector<DevEvent> events;
+        std::vector<const double*> prow, old_rows;
+        std::vector<DevUnch> unch;
+        std::vector<DevChunk> chunks;
+    } scratch;
+    std::vector<double*> stash;
+    cudaError_t row_get(double** out) {
+        if (stash.empty()) {
+            cudaError_t e = ds->pool.get_many(kStashRefill, stash);
+            if (e != cudaSuccess) return e;
+        }
+        *out = stash.back();
+        stash.pop_back();
+        return cudaSuccess;
+    }
+    void row_put(double* r) {
+        if (!r) return;
+        stash.push_back(r);
+        if (stash.size() > kStashMax) ds->pool.put_many(stash, kStashMax / 2);
+    }
     double cost = 0.0;  // relative device time of the compiled proposal (orders the blobs inside a launch)
 };
 
 namespace {
 
-void release_cache(scicone_dataset* ds, LCache& c) {
-    for (auto& kv : c) ds->pool.put(kv.second);
+void release_cache(scicone_chain* ch, LCache& c) {
+    for (auto& kv : c) ch->row_put(kv.second);
     c.clear();
 }
 
@@ -368,14 +451,14 @@ LCache* cache_for(scicone_chain* ch, double nu) {
         return &ch->Lt;
     }
     if (ch->Lp_valid && ch->Lp_nu == nu) return &ch->Lp;
-    release_cache(ch->ds, ch->Lp);
+    release_cache(ch, ch->Lp);
     ch->Lp_valid = true;
     ch->Lp_nu = nu;
     return &ch->Lp;
 }
 
 void drop_pending(scicone_chain* ch) {
-    for (auto& kv : ch->p) ch->ds->pool.put(kv.second.row);
+    for (auto& kv : ch->p) ch->row_put(kv.second.row);
     ch->p.clear();
     ch->roots.clear();
     ch->pending = false;
@@ -383,11 +466,11 @@ void drop_pending(scicone_chain* ch) {
     ch->evaluated = false;
     ch->deleted_id = -1;
     ch->p_full = false;
-    for (double* r : ch->temp_rows) ch->ds->pool.put(r);
+    for (double* r : ch->temp_rows) ch->row_put(r);
     ch->temp_rows.clear();
     ch->od_p_valid = false;
     ch->with_od = false;
-    release_cache(ch->ds, ch->Lp);
+    release_cache(ch, ch->Lp);
     ch->Lp_valid = false;
 }
 
@@ -427,7 +510,7 @@ int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const
     const int n_slices = std::max(1, std::min(kMaxOdSlices, K / kOdRegionsPerSlice));
     for (int s = 0; s < n_slices; ++s) {
         double* row = nullptr;
-        CUDA_TRY(ds->pool.get(&row));
+        CUDA_TRY(ch->row_get(&row));
         ch->temp_rows.push_back(row);
         slice_rows.push_back(row);
         DevBuild it;
@@ -482,20 +565,28 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     ch->builds.clear();
     ch->build_aux.clear();
 
-    std::vector<int> child_off(T.n + 1, 0), child(T.n > 1 ? T.n - 1 : 0);
+    // scratch vectors live in the chain: a proposal is compiled every ~100 us per chain, so no heap traffic here
+    scicone_chain::Scratch& W = ch->scratch;
+    std::vector<int>&child_off = W.child_off, &child = W.child, &fill = W.fill;
+    child_off.assign(T.n + 1, 0);
+    child.assign(T.n > 1 ? T.n - 1 : 0, 0);
     for (int i = 1; i < T.n; ++i) child_off[T.parent[i] + 1]++;
     for (int i = 0; i < T.n; ++i) child_off[i + 1] += child_off[i];
-    {
-        std::vector<int> fill(child_off.begin(), child_off.end() - 1);
-        for (int i = 1; i < T.n; ++i) child[fill[T.parent[i]]++] = i;
-    }
+    fill.assign(child_off.begin(), child_off.end() - 1);
+    for (int i = 1; i < T.n; ++i) child[fill[T.parent[i]]++] = i;
 
-    std::vector<DevTask> tasks;
-    std::vector<DevEvent> events;
-    std::vector<const double*> prow;  // per task: where its parent's score lives
-    std::vector<int> ptask;           // per task: task index of the parent, -1 when the parent is not rescored before
-    std::vector<int> task_of_node(T.n, -1);
-    std::vector<int> stack;
+    std::vector<DevTask>& tasks = W.tasks;
+    std::vector<DevEvent>& events = W.events;
+    std::vector<const double*>& prow = W.prow;  // per task: where its parent's score lives
+    std::vector<int>& ptask = W.ptask;          // per task: task index of the parent, -1 when the parent is not rescored before
+    std::vector<int>& task_of_node = W.task_of_node;
+    std::vector<int>& stack = W.stack;
+    tasks.clear();
+    events.clear();
+    prow.clear();
+    ptask.clear();
+    stack.clear();
+    task_of_node.assign(T.n, -1);
     for (size_t ri = 0; ri < ch->roots.size(); ++ri) {
         const int root = ch->roots[ri];
         stack.push_back(root);
@@ -559,7 +650,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                         ev.b = lgamma(argP);
                         double** slotp = &(*L)[lkey(k, cn_i, cp_i)];
                         if (!*slotp) {  // first use of this (region, copy-number pair) at this nu: K1 builds the row
-                            CUDA_TRY(ds->pool.get(slotp));
+                            CUDA_TRY(ch->row_get(slotp));
                             DevBuild it;
                             memset(&it, 0, sizeof it);
                             it.dst = *slotp;
@@ -596,7 +687,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             auto own = ch->p.find(id);
             if (own == ch->p.end()) {
                 double* row = nullptr;
-                CUDA_TRY(ds->pool.get(&row));
+                CUDA_TRY(ch->row_get(&row));
                 own = ch->p.emplace(id, NodeRow{row, z_int}).first;
             } else
                 own->second.z = z_int;
@@ -610,7 +701,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     }
 
     // aggregate bookkeeping: Inference::compute_t_prime_sums, Inference.h:1069-1196
-    {   // a node written twice (overlapping subtree roots) enters the aggregate once, with its last value
+    if (ch->roots.size() > 1) {  // a node written twice (overlapping subtree roots) enters the aggregate once, with its last value
         std::map<int, int> last;
         for (size_t i = 0; i < tasks.size(); ++i) last[tasks[i].node_id] = (int)i;
         for (size_t i = 0; i < tasks.size(); ++i)
@@ -619,7 +710,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     // Walk order bookkeeping for the one-thread-per-cell kernel: a node whose parent was visited just before takes the
     // parent's score (and, with TASK_REUSE_G, its z-term) from registers; any other parent score is prefetched while
     // the previous node is processed.  Chunks: what is staged in shared memory together.
-    std::vector<DevChunk> chunks;
+    std::vector<DevChunk>& chunks = W.chunks;
+    chunks.clear();
     for (size_t i = 0; i < tasks.size(); ++i) {
         if (ptask[i] >= 0 && ptask[i] == (int)i - 1) tasks[i].flags |= TASK_CHAINED;
         else tasks[i].flags &= (unsigned char)~TASK_REUSE_G;  // the previous node's z-term is only at hand when chained
@@ -639,8 +731,10 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         c.n_tasks++;
         if (!(tasks[i].flags & TASK_BIG)) c.n_ev = tasks[i].ev_begin + tasks[i].n_ev - c.ev_base;
     }
-    std::vector<const double*> old_rows;
-    std::vector<DevUnch> unch;
+    std::vector<const double*>& old_rows = W.old_rows;
+    std::vector<DevUnch>& unch = W.unch;
+    old_rows.clear();
+    unch.clear();
     ch->deleted_id = -1;
     if (!full) {
         // Inference::deleted_node_idx, Inference.h:1270-1289
@@ -815,7 +909,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         ds->n_scores += ch->n_scores;
         g.with_od[i] = ch->with_od;
         // rows that only lived for this launch go back to the pool: any later use is ordered behind it by the stream
-        for (double* r : ch->temp_rows) ds->pool.put(r);
+        for (double* r : ch->temp_rows) ch->row_put(r);
         ch->temp_rows.clear();
         ch->builds.clear();
         ch->build_aux.clear();
@@ -1065,8 +1159,9 @@ void scicone_chain_destroy(scicone_chain* ch) {
     cudaSetDevice(ds->device);
     cudaStreamSynchronize(ds->stream);
     drop_pending(ch);
-    for (auto& kv : ch->t) ds->pool.put(kv.second.row);
-    release_cache(ds, ch->Lt);
+    for (auto& kv : ch->t) ch->row_put(kv.second.row);
+    release_cache(ch, ch->Lt);
+    ds->pool.put_many(ch->stash, 0);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ch->sums[i]);
         cudaFree(ch->maxid[i]);
@@ -1082,10 +1177,10 @@ int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* t_
     rc = ds->set_device();
     if (rc) return rc;
     drop_pending(ch);
-    for (auto& kv : ch->t) ds->pool.put(kv.second.row);
+    for (auto& kv : ch->t) ch->row_put(kv.second.row);
     ch->t.clear();
     if (ch->Lt_valid && ch->Lt_nu != t->nu) {
-        release_cache(ds, ch->Lt);
+        release_cache(ch, ch->Lt);
         ch->Lt_valid = false;
     }
     ch->tp.assign(t);
@@ -1232,7 +1327,7 @@ int scicone_accept(scicone_chain* ch) {
     for (auto& kv : ch->p) {
         auto it = ch->t.find(kv.first);
         if (it != ch->t.end()) {
-            ds->pool.put(it->second.row);
+            ch->row_put(it->second.row);
             it->second = kv.second;
         } else
             ch->t.emplace(kv.first, kv.second);
@@ -1241,7 +1336,7 @@ int scicone_accept(scicone_chain* ch) {
     if (ch->deleted_id != -1) {
         auto it = ch->t.find(ch->deleted_id);
         if (it != ch->t.end()) {
-            ds->pool.put(it->second.row);
+            ch->row_put(it->second.row);
             ch->t.erase(it);
         }
     }
@@ -1249,7 +1344,7 @@ int scicone_accept(scicone_chain* ch) {
     std::swap(ch->sums[0], ch->sums[1]);    // t_sums = t_prime_sums, Inference.h:867
     std::swap(ch->maxid[0], ch->maxid[1]);  // t_maxs = t_prime_maxs, Inference.h:868
     if (ds->od && ch->Lp_valid && ch->Lp_nu == ch->tp.nu) {  // the proposal's nu becomes the chain's nu
-        release_cache(ds, ch->Lt);
+        release_cache(ch, ch->Lt);
         ch->Lt.swap(ch->Lp);
         ch->Lt_nu = ch->Lp_nu;
         ch->Lp_valid = false;
@@ -1262,6 +1357,47 @@ int scicone_reject(scicone_chain* ch) {
     if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
     drop_pending(ch);
     return SCICONE_OK;
+}
+
+namespace {
+struct PerChainJob {
+    scicone_chain* const* chains;
+    const scicone_tree* const* trees;
+    const int32_t* arg;
+    std::vector<int> rc;
+    std::vector<std::string> msg;
+};
+int finish_job(PerChainJob& job) {
+    for (size_t i = 0; i < job.rc.size(); ++i)
+        if (job.rc[i]) {
+            g_err = job.msg[i];
+            return job.rc[i];
+        }
+    return SCICONE_OK;
+}
+}  // namespace
+
+int scicone_batch_compute_t_prime_scores(scicone_chain* const* chains, const scicone_tree* const* t_primes,
+                                         const int32_t* node_idx, int32_t n) {
+    if (!chains || !t_primes || !node_idx || n <= 0) return fail(SCICONE_ERR_ARG, "batch: null or empty");
+    PerChainJob job{chains, t_primes, node_idx, std::vector<int>(n, 0), std::vector<std::string>(n)};
+    scicone::ForkJoinPool::instance().run(n, [](int i, void* ctx) {
+        PerChainJob& j = *static_cast<PerChainJob*>(ctx);
+        j.rc[i] = scicone_compute_t_prime_scores(j.chains[i], j.trees[i], j.arg[i]);
+        if (j.rc[i]) j.msg[i] = g_err;
+    }, &job);
+    return finish_job(job);
+}
+
+int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, int32_t n) {
+    if (!chains || !accept || n <= 0) return fail(SCICONE_ERR_ARG, "batch: null or empty");
+    PerChainJob job{chains, nullptr, accept, std::vector<int>(n, 0), std::vector<std::string>(n)};
+    scicone::ForkJoinPool::instance().run(n, [](int i, void* ctx) {
+        PerChainJob& j = *static_cast<PerChainJob*>(ctx);
+        j.rc[i] = j.arg[i] ? scicone_accept(j.chains[i]) : scicone_reject(j.chains[i]);
+        if (j.rc[i]) j.msg[i] = g_err;
+    }, &job);
+    return finish_job(job);
 }
 
 int scicone_t_n_nodes(scicone_chain* ch, int32_t* n_nodes) {

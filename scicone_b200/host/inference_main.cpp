@@ -55,6 +55,16 @@ Args parse(int argc, char** argv) {
 
 // Utils::read_counts (Utils.cpp:74-102): comma separated doubles into a pre-sized cells x regions matrix
 void read_counts(std::vector<double>& mat, int n_cells, int n_regions, const std::string& path) {
+    if (path.size() > 4 && path.compare(path.size() - 4, 4, ".f64") == 0) {
+        // binary side format for large matrices: n_cells x n_regions little-endian doubles, row-major (no reference
+        // counterpart; the CSV parser below is the reference's format)
+        std::ifstream bin(path, std::ios::binary);
+        if (!bin) throw std::runtime_error("cannot open " + path);
+        bin.read(reinterpret_cast<char*>(mat.data()), static_cast<std::streamsize>(mat.size() * sizeof(double)));
+        if (static_cast<size_t>(bin.gcount()) != mat.size() * sizeof(double))
+            throw std::runtime_error(path + " holds fewer than n_cells x n_regions doubles");
+        return;
+    }
     std::ifstream in(path);
     if (!in) throw std::runtime_error("cannot open " + path);
     std::string line;
@@ -262,6 +272,15 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         }
 
         if (P.verbosity > 0) std::cout << "Inferring the tree using MCMC with " << n_iters << " iterations..." << std::endl;
+        const int warmup_iters = static_cast<int>(a.integer("warmup_iters", 0));
+        if (warmup_iters > 0) {  // untimed iterations before the measured run (bench.py); the chains simply continue afterwards
+            infer_mcmc(chains, move_probs, warmup_iters, size_limit, static_cast<int>(a.integer("n_groups", 0)));
+            for (Inference* c : chains) {
+                c->n_accepted = c->n_rejected = 0;
+                c->n_rescored_nodes = c->n_attempts = 0;
+                c->t_finish_us = c->t_propose_us = c->t_prepare_us = c->t_max_visit_us = 0;
+            }
+        }
         double k0[4];
         scicone_counters(ds, k0, 1);
         scicone_kernel_time_stats(ds, nullptr, nullptr, 1);
@@ -280,7 +299,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         auto stop = std::chrono::high_resolution_clock::now();
         auto duration = std::chrono::duration_cast<std::chrono::microseconds>(stop - start);
         if (P.verbosity > 0) std::cout << "Time taken by infer_mcmc function: " << duration.count() << " microseconds" << std::endl;
-        if (stats && rank == 0) {
+        if (stats && (rank == 0 || a.has("stats_all_ranks"))) {
             double k[4], kern_us = 0, build_us = 0;
             uint64_t n_timed = 0, n_build = 0, launches = 0;
             scicone_counters(ds, k, 0);

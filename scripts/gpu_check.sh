@@ -21,7 +21,7 @@ fi
 python scripts/host_bench.py --iters 300 --ref_iters ${REF_ITERS:-0} > "$OUT/host_bench.json" 2> "$OUT/host_bench.err"; echo "host_bench rc=$?" | tee -a "$OUT/summary.txt"
 cat "$OUT/host_bench.json"; tail -3 "$OUT/host_bench.err"
 if [ -z "${SKIP_NCU:-}" ]; then
-SHORT="--steps 5 --warmup 3 --no_cpu_baseline"
+SHORT="--steps 5 --warmup 3 --no_cpu_baseline --no_e2e"
 python bench.py $SHORT > "$OUT/plain.log" 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" python bench.py $SHORT > "$OUT/ncu_launches.log" 2>&1
 echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
