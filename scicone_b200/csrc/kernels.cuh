@@ -34,7 +34,7 @@ namespace scicone {
 
 constexpr int kCells = 128;         // cells per CTA of the proposal kernel: one thread per cell
 constexpr int kThreads = kCells;
-constexpr int kMinCtasPerSm = 8;   // register budget of the proposal kernel: 65536 / (10 * 128) = 51 -> 48 registers
+constexpr int kMinCtasPerSm = 12;   // register budget of the proposal kernel: 65536 / (10 * 128) = 51 -> 48 registers
 constexpr int kTaskChunk = 32;      // task records staged in shared memory at a time
 constexpr int kEvStage = 96;        // event records staged with them (the rest is read from global memory)
 constexpr int kMaxOdSlices = 32;    // region slices of a root score
@@ -132,8 +132,13 @@ struct alignas(16) DevBuild {
 // (almost) no reads.  `tbl` is the shared-memory copy of the logarithm's reduction table.
 __device__ const double g_log_table[kLogTableDoubles] = {SCICONE_LOG_TABLE_VALUES};
 
+template <int kBlock>  // compile-time block size: a run-time stride costs an integer division in every CTA
 __device__ __forceinline__ void load_log_table(double* tbl) {
-    for (int i = threadIdx.x; i < kLogTableDoubles; i += blockDim.x) tbl[i] = g_log_table[i];
+#pragma unroll
+    for (int i = 0; i < (kLogTableDoubles + kBlock - 1) / kBlock; ++i) {
+        const int q = i * kBlock + threadIdx.x;
+        if (q < kLogTableDoubles) tbl[q] = g_log_table[q];
+    }
 }
 
 __device__ __forceinline__ double lgam(double x, const double* tbl) {
@@ -200,22 +205,43 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
     if (threadIdx.x == 0) *counter = 0u;
 }
 
-// A slice of the root score of one cell: sum over the regions [k0, k1) (Tree::get_od_root_score, Tree.h:1792-1805).
-__device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned char* __restrict__ arena, int j, const double* tbl) {
-    if (j >= it.n_cells) return;
+// A slice of the root score of kBuildCells cells: sum over the regions [k0, k1) (Tree::get_od_root_score, Tree.h:1792-1805).
+// The cells of a thread advance together, so their loads are in flight together and their lgamma chains interleave.
+__device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned char* __restrict__ arena, int j0, const double* tbl) {
     const double* arg = reinterpret_cast<const double*>(arena + it.off_arg);
     const double* cc = reinterpret_cast<const double*>(arena + it.off_c);
-    double acc = 0.0;
+    double acc[kBuildCells];
+    bool ok[kBuildCells];
+#pragma unroll
+    for (int q = 0; q < kBuildCells; ++q) {
+        acc[q] = 0.0;
+        ok[q] = j0 + q * kBuildBlock < it.n_cells;
+    }
     if (it.kind == BUILD_OD_SLICE) {  // Tree.h:1792-1797
-#pragma unroll 2
         for (int k = it.k0; k < it.k1; ++k) {
-            acc += lgam(__ldg(it.src + (long long)k * it.row_stride + j) + arg[k], tbl);
-            acc -= cc[k];
+            const double* row = it.src + (long long)k * it.row_stride + j0;
+            const double a = arg[k], c = cc[k];
+            double d[kBuildCells];
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) d[q] = ok[q] ? __ldg(row + q * kBuildBlock) : 32.0;
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) {
+                acc[q] += lgam(d[q] + a, tbl);
+                acc[q] -= c;
+            }
         }
     } else {  // Tree.h:1803-1805
-        for (int k = it.k0; k < it.k1; ++k) acc += __ldg(it.src + (long long)k * it.row_stride + j) * arg[k];
+        for (int k = it.k0; k < it.k1; ++k) {
+            const double* row = it.src + (long long)k * it.row_stride + j0;
+            const double a = arg[k];
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q)
+                if (ok[q]) acc[q] += __ldg(row + q * kBuildBlock) * a;
+        }
     }
-    it.dst[j] = acc;
+#pragma unroll
+    for (int q = 0; q < kBuildCells; ++q)
+        if (ok[q]) it.dst[j0 + q * kBuildBlock] = acc[q];
 }
 
 // ---------------------------------------------------------------------------------
@@ -223,7 +249,7 @@ __device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned c
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items) {
     __shared__ double tbl[kLogTableDoubles];
-    load_log_table(tbl);
+    load_log_table<kBuildBlock>(tbl);
     const DevBuild it = reinterpret_cast<const DevBuild*>(arena + off_items)[blockIdx.y];
     const int j0 = blockIdx.x * (kBuildBlock * kBuildCells) + threadIdx.x;
     if (it.kind == BUILD_DELTA) {
@@ -243,7 +269,7 @@ __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned 
         return;
     }
     __syncthreads();
-    for (int q = 0; q < kBuildCells; ++q) build_slice(it, arena, j0 + q * kBuildBlock, tbl);
+    build_slice(it, arena, j0, tbl);
 }
 
 // ---------------------------------------------------------------------------------
@@ -268,26 +294,23 @@ __device__ __forceinline__ void copy16(void* dst, const void* src) {
     *reinterpret_cast<int4*>(dst) = __ldg(reinterpret_cast<const int4*>(src));
 }
 
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kernel(const unsigned char* __restrict__ arena) {
+template <bool kMax, bool kOd, int kOcc>
+__global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const unsigned char* __restrict__ arena) {
     __shared__ __align__(16) DevTask sm_task[kTaskChunk];
     __shared__ __align__(16) DevEvent sm_ev[kEvStage];
     __shared__ double red_buf[kThreads / 32];
     __shared__ double tbl[kLogTableDoubles];
-    load_log_table(tbl);
+    load_log_table<kThreads>(tbl);
     __syncthreads();
 
     const unsigned* blob_off = reinterpret_cast<const unsigned*>(arena);
     const unsigned char* blob = arena + blob_off[blockIdx.y];
     const DevHeader& H = *reinterpret_cast<const DevHeader*>(blob);
-    const DevTask* tasks = reinterpret_cast<const DevTask*>(blob + H.off_tasks);
-    const DevEvent* events = reinterpret_cast<const DevEvent*>(blob + H.off_events);
-    const double* const* old_rows = reinterpret_cast<const double* const*>(blob + H.off_old);
-    const DevUnch* unch = reinterpret_cast<const DevUnch*>(blob + H.off_unch);
 
     const int j = blockIdx.x * kCells + threadIdx.x;
     const bool live = j < H.n_cells;
     const unsigned pflags = H.flags;
-    const bool od = pflags & PROP_OD;
+    constexpr bool od = kOd;
     const double S = live ? __ldg(H.S + j) : 1.0;
 
     // running aggregate over the rescored nodes
@@ -296,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
     double new_sumexp = 0.0;    // sum mode: sum_i exp(v_i - new_max)
     bool prev_in_new = (pflags & PROP_FULL) != 0;
     const bool incremental = live && !(pflags & (PROP_FULL | PROP_OD_ONLY));
-    const int pm = (incremental && (pflags & PROP_MAX)) ? H.maxid_old[j] : -1;
+    const int pm = (kMax && incremental) ? H.maxid_old[j] : -1;
     const double agg_old = incremental ? H.sums_old[j] : 0.0;  // fetched now, needed in phase C
 
     double sc_prev = 0.0, g_prev = 0.0;  // score and lgamma(S + nu z) of the node visited just before
@@ -304,8 +327,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
     if (live && H.first_parent_row) ps_next = __ldcg(H.first_parent_row + j);
     const DevChunk* chunks = reinterpret_cast<const DevChunk*>(blob + H.off_chunks);
 
-    for (int c = 0; c < H.n_chunks; ++c) {
+    const int n_chunks = H.n_chunks;
+    for (int c = 0; c < n_chunks; ++c) {
         const DevChunk ck = chunks[c];
+        const DevTask* tasks = reinterpret_cast<const DevTask*>(blob + H.off_tasks);
+        const DevEvent* events = reinterpret_cast<const DevEvent*>(blob + H.off_events);
         // ---- stage the task and event records of this chunk
         __syncthreads();
         for (int q = threadIdx.x; q < ck.n_tasks * 4; q += kThreads)
@@ -314,9 +340,21 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
             copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, reinterpret_cast<const unsigned char*>(events + ck.ev_base) + 16 * q);
         __syncthreads();
         if (!live) continue;
+        // the first two delta-row gathers of a node are issued while the node before it is being scored
+        double dn0 = 0.0, dn1 = 0.0;
+        auto prefetch_gathers = [&](const DevTask& nx) {
+            dn0 = dn1 = 0.0;
+            if (nx.flags & (TASK_ROOT | TASK_BIG)) return;
+            const DevEvent* ev = sm_ev + nx.ev_rel;
+            if (nx.n_ev > 0) dn0 = __ldg(ev[0].row + j);
+            if (nx.n_ev > 1) dn1 = __ldg(ev[1].row + j);
+        };
+        prefetch_gathers(sm_task[0]);
         for (int t = 0; t < ck.n_tasks; ++t) {
             const DevTask& tk = sm_task[t];
             const unsigned tf = tk.flags;
+            const double d0 = dn0, d1 = dn1;
+            if (t + 1 < ck.n_tasks) prefetch_gathers(sm_task[t + 1]);
             const double ps = (tf & TASK_CHAINED) ? sc_prev : ps_next;
             // parent score of the NEXT node: its row was written by this thread at least one node ago (or is committed)
             if (tk.prefetch_row) ps_next = __ldcg(tk.prefetch_row + j);
@@ -325,50 +363,41 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
             if (!(tf & TASK_ROOT)) {
                 double x = 0.0;
                 const int ne = tk.n_ev;
-                if (!(tf & TASK_BIG)) {
-                    const DevEvent* ev = sm_ev + tk.ev_rel;
-                    double d[4];  // the first four gathers are issued together; they are added in event order below
+                const bool big = tf & TASK_BIG;  // more events than the staging buffer holds (rare): read from global memory
+                const DevEvent* ev = big ? reinterpret_cast<const DevEvent*>(blob + H.off_events) + tk.ev_begin : sm_ev + tk.ev_rel;
+                double d[4];  // gathers 0 and 1 were issued one node ago, 2 and 3 go out now ...
+                d[0] = big ? (ne > 0 ? __ldg(ev[0].row + j) : 0.0) : d0;
+                d[1] = big ? (ne > 1 ? __ldg(ev[1].row + j) : 0.0) : d1;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) d[q] = (q < ne) ? __ldg(ev[q].row + j) : 0.0;
-                    if (od) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < ne) {
-                                x += d[q];
-                                x -= ev[q].a;
-                                x += ev[q].b;
-                            }
-                        for (int q = 4; q < ne; ++q) {
-                            x += __ldg(ev[q].row + j);
-                            x -= ev[q].a;
-                            x += ev[q].b;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < ne) x += d[q] * ev[q].a;
-                        for (int q = 4; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
-                    }
-                } else {  // a node with more events than the staging buffer holds
-                    const DevEvent* ev = events + tk.ev_begin;
-                    if (od)
-                        for (int q = 0; q < ne; ++q) {
-                            x += __ldg(ev[q].row + j);
-                            x -= ev[q].a;
-                            x += ev[q].b;
-                        }
-                    else
-                        for (int q = 0; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
-                }
+                for (int q = 2; q < 4; ++q) d[q] = (q < ne) ? __ldg(ev[q].row + j) : 0.0;
+                double g = 0.0, gp = 0.0;  // ... the z-terms are evaluated while they are in flight ...
                 if (od) {
-                    const double g = lgam(S + tk.nz, tbl);
-                    const double gp = (tf & TASK_REUSE_G) ? g_prev : lgam(S + tk.nzp, tbl);
+                    g = lgam(S + tk.nz, tbl);
+                    gp = (tf & TASK_REUSE_G) ? g_prev : lgam(S + tk.nzp, tbl);
                     g_prev = g;
+                }
+                if (od) {  // ... and they are added in event order (Tree.h:214-218)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q < ne) {
+                            x += d[q];
+                            x -= ev[q].a;
+                            x += ev[q].b;
+                        }
+                    for (int q = 4; q < ne; ++q) {
+                        x += __ldg(ev[q].row + j);
+                        x -= ev[q].a;
+                        x += ev[q].b;
+                    }
                     x += tk.lg_nz;
                     x -= tk.lg_nzp;
                     x -= g;
                     x += gp;
-                } else {
+                } else {  // Tree.h:221,236-237
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q < ne) x += d[q] * ev[q].a;
+                    for (int q = 4; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
                     x -= S * tk.lg_nz;
                     x += S * tk.lg_nzp;
                 }
@@ -379,8 +408,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
             tk.dst[j] = sc;
             if (tf & TASK_SKIP_AGG) continue;
             const int id = tk.node_id;
-            if (id == pm) prev_in_new = true;
-            if (pflags & PROP_MAX) {
+            if (kMax && id == pm) prev_in_new = true;
+            if (kMax) {
                 if (sc > new_max || (sc == new_max && id < new_id)) {
                     new_max = sc;
                     new_id = id;
@@ -399,8 +428,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
     if (live && !(pflags & PROP_OD_ONLY)) {
         // ---- per-cell aggregate: Inference::compute_t_prime_sums ----
         const int n_unch = H.n_unch;
+        const DevUnch* unch = reinterpret_cast<const DevUnch*>(blob + H.off_unch);
         double res;
-        if (pflags & PROP_MAX) {  // Inference.h:1086-1152
+        if (kMax) {  // Inference.h:1086-1152
             int prev_id = pm;
             double prev_val = agg_old;
             if (prev_in_new || pm == H.deleted_id) {
@@ -440,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
             bool scratch = (pflags & (PROP_SCRATCH | PROP_FULL)) != 0;
             double sub = 0.0;
             if (!scratch) {  // incremental branch: take the old values out of the old sum
+                const double* const* old_rows = reinterpret_cast<const double* const*>(blob + H.off_old);
                 const double sum_old = agg_old;
                 const int n_old = H.n_old;
                 double mx = sum_old;
@@ -511,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) score_proposals_kerne
 // Test hook: the device lgamma on caller-provided arguments (scicone_test_lgamma).
 __global__ void lgam_probe_kernel(const double* __restrict__ x, double* __restrict__ out, int n) {
     __shared__ double tbl[kLogTableDoubles];
-    load_log_table(tbl);
+    load_log_table<256>(tbl);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = lgam(x[i], tbl);

@@ -378,6 +378,7 @@ struct scicone_dataset {
 };
 
 constexpr size_t kStashRefill = 32, kStashMax = 160;
+constexpr int kDefaultOcc = 8;
 
 struct scicone_chain {
     scicone_dataset* ds = nullptr;
@@ -882,7 +883,26 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     }
     g.n_items = (int)n_items;
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, ds->stream));
-    score_proposals_kernel<<<dim3(ds->n_cta, n), kThreads, 0, ds->stream>>>(ds->d_arena);
+    {   // scoring mode and likelihood are properties of the dataset: one specialisation per launch.  kOcc = CTAs per SM the
+        // register allocation aims at (6 -> 80 registers, 8 -> 64, 10 -> 48); SCICONE_OCC overrides the default for tuning.
+        static const int occ = [] {
+            const char* e = getenv("SCICONE_OCC");
+            const int v = e ? atoi(e) : 0;
+            return (v == 6 || v == 8 || v == 10) ? v : kDefaultOcc;
+        }();
+        const dim3 grid(ds->n_cta, n);
+#define SCICONE_LAUNCH(OCC)                                                                                                \
+    do {                                                                                                                   \
+        if (ds->maxs && ds->od) score_proposals_kernel<true, true, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);   \
+        else if (ds->maxs) score_proposals_kernel<true, false, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);        \
+        else if (ds->od) score_proposals_kernel<false, true, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);          \
+        else score_proposals_kernel<false, false, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);                     \
+    } while (0)
+        if (occ == 6) SCICONE_LAUNCH(6);
+        else if (occ == 10) SCICONE_LAUNCH(10);
+        else SCICONE_LAUNCH(8);
+#undef SCICONE_LAUNCH
+    }
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, ds->stream));
     CUDA_TRY(cudaGetLastError());
     ds->n_launches++;
