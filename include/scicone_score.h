@@ -205,6 +205,17 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
                                   int32_t* cell_region_cn /* [n_cells][n_regions] or NULL */);
 
 /*
+ * Utils::condense_matrix (Utils.cpp:104-138; the same collapse in pyscicone, scicone.py:276-299): cells x bins ->
+ * cells x regions, out[i][r] = sum of the region_sizes[r] consecutive bins of region r, added in bin order (so the sums
+ * are bit-identical to the reference's).  Bins beyond sum(region_sizes) are ignored, as in the reference.  Both
+ * matrices are caller-owned host buffers; the work runs on `device` (TMA-staged streaming kernel, csrc/condense.cuh).
+ * kernel_us (optional) receives the device time of the condensation kernel(s).
+ */
+int scicone_condense_matrix(int32_t device, const double* D_bins /* [n_cells][n_bins] */, int64_t n_cells, int64_t n_bins,
+                            const int32_t* region_sizes, int32_t n_regions, double* D_regions /* [n_cells][n_regions] */,
+                            double* kernel_us);
+
+/*
  * Test hook: the device log-gamma used for every data and z term (reference: libm lgamma called from
  * Tree::compute_score, Tree.h:214-231) evaluated on `n` caller-provided positive arguments.
  */

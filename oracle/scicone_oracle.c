@@ -523,3 +523,26 @@ void orc_assign_cells_to_nodes(orc_ctx* c, const scicone_tree* t, int32_t* cell_
         }
     }
 }
+
+/* Utils::condense_matrix (reference scicone/src/Utils.cpp:104-138): walk the first sum(region_sizes) bins of every row and
+ * add each to the current region's cell, moving to the next region when region_sizes[region] bins have been taken. */
+int orc_condense_matrix(const double* D_bins, int64_t n_cells, int64_t n_bins, const int32_t* region_sizes, int32_t n_regions,
+                        double* D_regions) {
+    int64_t total = 0;
+    for (int32_t r = 0; r < n_regions; ++r) total += region_sizes[r];
+    if (total > n_bins) return -1;
+    for (int64_t i = 0; i < n_cells; ++i) {
+        double* out = D_regions + i * n_regions;
+        const double* in = D_bins + i * n_bins;
+        for (int32_t r = 0; r < n_regions; ++r) out[r] = 0.0;
+        int32_t region = 0, taken = 0;
+        for (int64_t j = 0; j < total; ++j) {
+            out[region] += in[j];
+            if (++taken == region_sizes[region]) {
+                ++region;
+                taken = 0;
+            }
+        }
+    }
+    return 0;
+}

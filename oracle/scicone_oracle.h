@@ -58,6 +58,10 @@ double orc_log_sum(const double* v, int n);
 double orc_log_replace_sum(double sum, const double* to_subtract, int n_sub, const double* to_add, int n_add,
                            const double* unchanged, int n_unch);
 
+/* Utils::condense_matrix, Utils.cpp:104-138: bins -> regions, one bin after the other (row-major in and out) */
+int orc_condense_matrix(const double* D_bins, int64_t n_cells, int64_t n_bins, const int32_t* region_sizes, int32_t n_regions,
+                        double* D_regions);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_build_time_stats", "scicone_kernel_launches",
     "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
     "scicone_parallel_for", "scicone_host_threads", "scicone_test_lgamma", "scicone_prepare_t_prime",
-    "scicone_batch_compute_t_prime_scores", "scicone_batch_settle",
+    "scicone_batch_compute_t_prime_scores", "scicone_batch_settle", "scicone_condense_matrix",
 ]
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}
@@ -95,6 +95,7 @@ def lib():
         L.scicone_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.scicone_batch_compute_t_prime_scores.argtypes = [C.POINTER(vp), C.POINTER(tp), ip, C.c_int32]
         L.scicone_batch_settle.argtypes = [C.POINTER(vp), ip, C.c_int32]
+        L.scicone_condense_matrix.argtypes = [C.c_int32, dp, C.c_int64, C.c_int64, ip, C.c_int32, dp, dp]
         L.scicone_test_lgamma.argtypes = [C.c_int32, dp, C.c_int32, dp]
         L.scicone_accept.argtypes = [vp]
         L.scicone_reject.argtypes = [vp]
@@ -382,3 +383,17 @@ def device_lgamma(x, device=0):
     if rc != 0:
         raise SciconeError(rc, L.scicone_last_error().decode())
     return out
+
+
+def condense_matrix(D_bins, region_sizes, device=0, return_kernel_us=False):
+    """Utils::condense_matrix (Utils.cpp:104-138) on the device: cells x bins -> cells x regions, bins added in order."""
+    D_bins = np.ascontiguousarray(D_bins, dtype=np.float64)
+    r = np.ascontiguousarray(region_sizes, dtype=np.int32)
+    out = np.empty((D_bins.shape[0], r.size), dtype=np.float64)
+    us = C.c_double(0.0)
+    L = lib()
+    rc = L.scicone_condense_matrix(int(device), D_bins.ctypes.data_as(C.POINTER(C.c_double)), D_bins.shape[0], D_bins.shape[1],
+                                   r.ctypes.data_as(C.POINTER(C.c_int32)), int(r.size), out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(us))
+    if rc != 0:
+        raise SciconeError(rc, L.scicone_last_error().decode())
+    return (out, us.value) if return_kernel_us else out

@@ -1,0 +1,122 @@
+// K0: bins -> regions.  Utils::condense_matrix (reference scicone/src/Utils.cpp:104-138; pyscicone does the same in
+// scicone.py:276-299): out[i][r] = sum of the bins of region r of row i, added one bin after the other in bin order,
+// which this kernel keeps (bit-identical sums also for non-integer inputs).
+//
+// The only multi-GB stream of the pipeline (10 000 x 18 000 doubles = 1.44 GB, 100 000 x 20 000 = 16 GB): HBM bound,
+// algorithmic traffic 8 * n_bins read + 8 * n_regions written per row.  One persistent CTA per SM walks groups of
+// kRows rows; a row group is cut into tiles of kTile bins which the TMA unit copies into a two-stage shared-memory ring
+// (cp.async.bulk + mbarrier transaction counts, one elected thread issues), so the next tile streams in while the
+// current one is reduced.  A thread owns one (row, region) piece of a tile and adds its bins sequentially; the region
+// that straddles a tile boundary hands its partial sum to the next tile through a per-row carry.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace scicone {
+
+constexpr int kK0Rows = 8;       // rows per group
+constexpr int kK0Tile = 1024;    // bins per tile and row
+constexpr int kK0Threads = 256;
+constexpr int kK0Stride = kK0Tile + 2;  // doubles per row in a stage: one leading element of slack for 16-byte alignment
+constexpr size_t kK0SmemBytes = sizeof(double) * 2 * kK0Rows * kK0Stride + 2 * sizeof(double) * 2 * kK0Rows + 64;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit; completion is counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// bins [n_rows][row_stride] row-major, of which the first n_bins = sum of the region sizes are used (the allocation is
+// padded by 16 bytes), off [K+1] prefix sums of the region sizes,
+// tile_first [n_tiles+1]: first region that reaches into each tile, out [n_rows][K]
+__global__ void __launch_bounds__(kK0Threads, 1)
+    condense_rows_kernel(const double* __restrict__ bins, long long n_rows, long long row_stride, long long n_bins, const int* __restrict__ off,
+                         const int* __restrict__ tile_first, int K, int n_tiles, double* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_buf = reinterpret_cast<double*>(smem_raw);                                 // [2][kK0Rows][kK0Stride]
+    double* carry = stage_buf + 2 * kK0Rows * kK0Stride;                                     // [2][kK0Rows]
+    uint64_t* full = reinterpret_cast<uint64_t*>(carry + 2 * kK0Rows);                       // [2]
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long n_groups = (n_rows + kK0Rows - 1) / kK0Rows;
+    unsigned uses[2] = {0u, 0u};  // how often each stage has been filled: parity of its barrier phase
+    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long long row0 = g * kK0Rows;
+        const int rows = (int)min((long long)kK0Rows, n_rows - row0);
+        // tile t of this group -> stage s: one bulk copy per row, aligned down to 16 bytes
+        auto issue = [&](int t, int s) {
+            const long long lo = (long long)t * kK0Tile;
+            const int width = (int)min((long long)kK0Tile, n_bins - lo);
+            unsigned total = 0;
+            for (int r = 0; r < rows; ++r) {
+                const long long first = (row0 + r) * row_stride + lo;  // element index of the tile's first bin
+                const int lead = (int)(first & 1);
+                total += (unsigned)(((width + lead + 1) & ~1) * sizeof(double));
+            }
+            mbar_expect_tx(&full[s], total);
+            for (int r = 0; r < rows; ++r) {
+                const long long first = (row0 + r) * row_stride + lo;
+                const int lead = (int)(first & 1);
+                const unsigned bytes = (unsigned)(((width + lead + 1) & ~1) * sizeof(double));
+                tma_load_1d(stage_buf + ((size_t)s * kK0Rows + r) * kK0Stride, bins + first - lead, bytes, &full[s]);
+            }
+        };
+        if (threadIdx.x == 0) issue(0, 0);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int s = t & 1;
+            if (threadIdx.x == 0 && t + 1 < n_tiles) issue(t + 1, s ^ 1);  // stage s^1 was released by the barrier below
+            mbar_wait(&full[s], uses[s] & 1u);
+            uses[s]++;
+            const long long lo = (long long)t * kK0Tile;
+            const long long hi = min(lo + kK0Tile, n_bins);
+            const int r_lo = tile_first[t], r_hi = tile_first[t + 1];  // regions r_lo .. r_hi (inclusive) reach into this tile
+            const int n_reg = r_hi - r_lo + 1;
+            for (int item = threadIdx.x; item < n_reg * rows; item += kK0Threads) {
+                const int row = item / n_reg, r = r_lo + item % n_reg;
+                if (r >= K) continue;
+                const long long s_r = off[r], e_r = off[r + 1];
+                if (e_r <= lo || s_r >= hi) continue;
+                const long long first = (row0 + row) * row_stride + lo;
+                const double* src = stage_buf + ((size_t)s * kK0Rows + row) * kK0Stride + (first & 1) - lo;
+                double acc = s_r < lo ? carry[(t & 1) * kK0Rows + row] : 0.0;
+                const long long b1 = min(e_r, hi);
+                for (long long b = max(s_r, lo); b < b1; ++b) acc += src[b];  // bin order, as the reference adds them
+                if (e_r > hi)
+                    carry[((t + 1) & 1) * kK0Rows + row] = acc;
+                else
+                    out[(row0 + row) * K + r] = acc;
+            }
+            __syncthreads();  // everyone is done with stage s (and with this tile's carries) before it is refilled
+        }
+    }
+}
+
+}  // namespace scicone

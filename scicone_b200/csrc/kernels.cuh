@@ -49,6 +49,7 @@ enum : unsigned {
     TASK_SKIP_AGG = 4u,  // a later task rewrites the same node: only that one enters the aggregate
     TASK_CHAINED = 8u,   // the parent is the task right before this one: its score (and z-term) are still in registers
     TASK_BIG = 16u,      // more events than the staging buffer holds: read from global memory
+    TASK_G_ROW = 32u,    // z-terms come from rows built by K1 (BUILD_G) instead of being evaluated in the serial walk
     PROP_MAX = 1u,       // max scoring (Inference::max_scoring)
     PROP_OD = 2u,        // overdispersed likelihood (globals is_overdispersed)
     PROP_FULL = 4u,      // full table pass (Inference::compute_t_table): no committed state is read
@@ -57,14 +58,23 @@ enum : unsigned {
     PROP_OD_ONLY = 32u,  // no tasks, no aggregate: only the root score
     BUILD_DELTA = 0u,
     BUILD_OD_SLICE = 1u,
-    BUILD_OD_SLICE_LOG = 2u  // non-overdispersed root score slice: sum_k D_k log r_k
+    BUILD_OD_SLICE_LOG = 2u,  // non-overdispersed root score slice: sum_k D_k log r_k
+    BUILD_G = 3u              // z-term row lgamma(S + c1)
 };
 
 struct alignas(16) DevTask {
     double* dst;                 // score row being written
     const double* prefetch_row;  // parent score row of the NEXT task when that task is neither chained nor the root, else null
     double lg_nz, lg_nzp;        // OD: lgamma(nu*z), lgamma(nu*z_parent);  non-OD: log(z), log(z_parent)
-    double nz, nzp;              // OD: nu*z, nu*z_parent
+    union {
+        struct {
+            double nz, nzp;          // OD: nu*z, nu*z_parent: the z-terms lgamma(S + nu*z) are evaluated in the kernel
+        };
+        struct {                     // TASK_G_ROW (long proposals): the z-terms were built as rows by K1 and are only gathered
+            const double* g_row;     // lgamma(S + nu*z)
+            const double* gp_row;    // lgamma(S + nu*z_parent); unused when TASK_REUSE_G
+        };
+    };
     int ev_begin;                // first event record (index into the proposal's event array)
     int node_id;
     unsigned short n_ev;         // number of event records (Node::c_change entries)
@@ -252,6 +262,21 @@ __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned 
     load_log_table<kBuildBlock>(tbl);
     const DevBuild it = reinterpret_cast<const DevBuild*>(arena + off_items)[blockIdx.y];
     const int j0 = blockIdx.x * (kBuildBlock * kBuildCells) + threadIdx.x;
+    if (it.kind == BUILD_G) {  // lgamma(S + nu*z) of one node for every cell (Tree.h:229-231)
+        double d[kBuildCells];
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) {
+            const int j = j0 + q * kBuildBlock;
+            d[q] = j < it.n_cells ? __ldg(it.src + j) : 32.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) {
+            const int j = j0 + q * kBuildBlock;
+            if (j < it.n_cells) it.dst[j] = lgam(d[q] + it.c1, tbl);
+        }
+        return;
+    }
     if (it.kind == BUILD_DELTA) {
         // kBuildCells cells per thread: the loads go out together, and the table copy / item fetch is paid once
         double d[kBuildCells];
@@ -341,9 +366,13 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
         __syncthreads();
         if (!live) continue;
         // the first two delta-row gathers of a node are issued while the node before it is being scored
-        double dn0 = 0.0, dn1 = 0.0;
+        double dn0 = 0.0, dn1 = 0.0, gn = 0.0, gpn = 0.0;
         auto prefetch_gathers = [&](const DevTask& nx) {
             dn0 = dn1 = 0.0;
+            if (od && (nx.flags & TASK_G_ROW)) {  // z-terms of a long proposal: rows built by K1
+                gn = __ldg(nx.g_row + j);
+                if (!(nx.flags & (TASK_ROOT | TASK_REUSE_G))) gpn = __ldg(nx.gp_row + j);
+            }
             if (nx.flags & (TASK_ROOT | TASK_BIG)) return;
             const DevEvent* ev = sm_ev + nx.ev_rel;
             if (nx.n_ev > 0) dn0 = __ldg(ev[0].row + j);
@@ -353,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
         for (int t = 0; t < ck.n_tasks; ++t) {
             const DevTask& tk = sm_task[t];
             const unsigned tf = tk.flags;
-            const double d0 = dn0, d1 = dn1;
+            const double d0 = dn0, d1 = dn1, g_row_val = gn, gp_row_val = gpn;
             if (t + 1 < ck.n_tasks) prefetch_gathers(sm_task[t + 1]);
             const double ps = (tf & TASK_CHAINED) ? sc_prev : ps_next;
             // parent score of the NEXT node: its row was written by this thread at least one node ago (or is committed)
@@ -372,8 +401,13 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                 for (int q = 2; q < 4; ++q) d[q] = (q < ne) ? __ldg(ev[q].row + j) : 0.0;
                 double g = 0.0, gp = 0.0;  // ... the z-terms are evaluated while they are in flight ...
                 if (od) {
-                    g = lgam(S + tk.nz, tbl);
-                    gp = (tf & TASK_REUSE_G) ? g_prev : lgam(S + tk.nzp, tbl);
+                    if (tf & TASK_G_ROW) {
+                        g = g_row_val;
+                        gp = (tf & TASK_REUSE_G) ? g_prev : gp_row_val;
+                    } else {
+                        g = lgam(S + tk.nz, tbl);
+                        gp = (tf & TASK_REUSE_G) ? g_prev : lgam(S + tk.nzp, tbl);
+                    }
                     g_prev = g;
                 }
                 if (od) {  // ... and they are added in event order (Tree.h:214-218)
@@ -403,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                 }
                 sc = ps + x;
             } else if (od)
-                g_prev = lgam(S + tk.nz, tbl);
+                g_prev = (tf & TASK_G_ROW) ? g_row_val : lgam(S + tk.nz, tbl);
             sc_prev = sc;
             tk.dst[j] = sc;
             if (tf & TASK_SKIP_AGG) continue;

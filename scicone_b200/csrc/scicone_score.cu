@@ -17,6 +17,7 @@
 // compute entry point fails with SCICONE_ERR_CUDA.
 #include "../../include/scicone_score.h"
 #include "kernels.cuh"
+#include "condense.cuh"
 #include "parallel_for.hpp"
 
 #include <dlfcn.h>
@@ -379,6 +380,7 @@ struct scicone_dataset {
 
 constexpr size_t kStashRefill = 32, kStashMax = 160;
 constexpr int kDefaultOcc = 8;
+constexpr int kGRowMinTasks = 12;  // from this many rescored nodes on, the z-terms are built as rows by K1
 
 struct scicone_chain {
     scicone_dataset* ds = nullptr;
@@ -415,7 +417,7 @@ struct scicone_chain {
         std::vector<int> child_off, child, fill, ptask, task_of_node, stack;
         std::vector<DevTask> tasks;
         std::vector<DevEvent> events;
-        std::vector<const double*> prow, old_rows;
+        std::vector<const double*> prow, old_rows, g_of_task;
         std::vector<DevUnch> unch;
         std::vector<DevChunk> chunks;
     } scratch;
@@ -713,6 +715,46 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     // the previous node is processed.  Chunks: what is staged in shared memory together.
     std::vector<DevChunk>& chunks = W.chunks;
     chunks.clear();
+    // Long proposals (full passes, nu proposals, large subtrees): the z-terms lgamma(S + nu z) leave the serial walk and
+    // are built as rows by K1, where every (node, cell) pair is independent; the walk then only gathers and adds.
+    const bool g_rows = od && tasks.size() >= (size_t)kGRowMinTasks;
+    if (g_rows) {
+        auto build_g = [&](double arg, const double** out) -> int {
+            double* row = nullptr;
+            CUDA_TRY(ch->row_get(&row));
+            ch->temp_rows.push_back(row);
+            DevBuild it;
+            memset(&it, 0, sizeof it);
+            it.dst = row;
+            it.src = ds->dS;
+            it.c1 = arg;
+            it.kind = BUILD_G;
+            it.n_cells = ds->M;
+            it.row_stride = (long long)ds->Mp;
+            ch->builds.push_back(it);
+            *out = row;
+            return SCICONE_OK;
+        };
+        W.g_of_task.assign(tasks.size(), nullptr);
+        for (size_t i = 0; i < tasks.size(); ++i) {
+            const double nz = tasks[i].nz, nzp = tasks[i].nzp;
+            const bool shares_parent = (tasks[i].flags & TASK_REUSE_G) != 0;  // nu*z_parent is bit-equal to the parent task's nu*z
+            const double* g = nullptr;
+            const double* gp = nullptr;
+            int rc = build_g(nz, &g);
+            if (rc) return rc;
+            W.g_of_task[i] = g;
+            if (!(tasks[i].flags & TASK_ROOT)) {
+                if (shares_parent)
+                    gp = W.g_of_task[ptask[i]];
+                else if ((rc = build_g(nzp, &gp)))
+                    return rc;
+            }
+            tasks[i].g_row = g;
+            tasks[i].gp_row = gp;
+            tasks[i].flags |= TASK_G_ROW;
+        }
+    }
     for (size_t i = 0; i < tasks.size(); ++i) {
         if (ptask[i] >= 0 && ptask[i] == (int)i - 1) tasks[i].flags |= TASK_CHAINED;
         else tasks[i].flags &= (unsigned char)~TASK_REUSE_G;  // the previous node's z-term is only at hand when chained
@@ -1527,6 +1569,75 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
     }
     cudaFree(d_rows); cudaFree(d_ids); cudaFree(d_cn); cudaFree(d_out_id); cudaFree(d_out_col); cudaFree(d_out_cn);
     if (e != cudaSuccess) return fail(SCICONE_ERR_CUDA, "assign_cells_to_nodes: %s", cudaGetErrorString(e));
+    return SCICONE_OK;
+}
+
+int scicone_condense_matrix(int32_t device, const double* D_bins, int64_t n_cells, int64_t n_bins, const int32_t* region_sizes,
+                            int32_t n_regions, double* D_regions, double* kernel_us) {
+    if (!D_bins || !region_sizes || !D_regions || n_cells <= 0 || n_bins <= 0 || n_regions <= 0)
+        return fail(SCICONE_ERR_ARG, "condense_matrix: null buffer or empty matrix");
+    std::vector<int> off(n_regions + 1, 0);
+    for (int r = 0; r < n_regions; ++r) {
+        if (region_sizes[r] <= 0) return fail(SCICONE_ERR_ARG, "condense_matrix: region %d has size %d", r, region_sizes[r]);
+        off[r + 1] = off[r] + region_sizes[r];
+    }
+    const long long n_used = off[n_regions];
+    if (n_used > n_bins) return fail(SCICONE_ERR_ARG, "condense_matrix: region sizes add up to %lld bins, the matrix has %lld", n_used, (long long)n_bins);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev)
+        return fail(SCICONE_ERR_CUDA, "condense_matrix: no such CUDA device; this library has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    const int n_tiles = (int)((n_used + kK0Tile - 1) / kK0Tile);
+    std::vector<int> tile_first(n_tiles + 1, n_regions - 1);
+    for (int t = 0, r = 0; t < n_tiles; ++t) {
+        while (off[r + 1] <= (long long)t * kK0Tile) ++r;
+        tile_first[t] = r;
+    }
+    // rows travel in chunks of at most 512 MB: upload, condense, download
+    const long long chunk_rows = std::max<long long>(kK0Rows, std::min<long long>(n_cells, (512ll << 20) / (n_bins * (long long)sizeof(double))));
+    double *d_bins = nullptr, *d_out = nullptr;
+    int *d_off = nullptr, *d_first = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaMalloc(&d_bins, sizeof(double) * chunk_rows * n_bins + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * chunk_rows * n_regions);
+    if (e == cudaSuccess) e = cudaMalloc(&d_off, sizeof(int) * off.size());
+    if (e == cudaSuccess) e = cudaMalloc(&d_first, sizeof(int) * tile_first.size());
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, tile_first.data(), sizeof(int) * tile_first.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(condense_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK0SmemBytes);
+    double total_us = 0.0;
+    for (long long r0 = 0; e == cudaSuccess && r0 < n_cells; r0 += chunk_rows) {
+        const long long rows = std::min(chunk_rows, (long long)n_cells - r0);
+        e = cudaMemcpyAsync(d_bins, D_bins + r0 * n_bins, sizeof(double) * rows * n_bins, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        const long long groups = (rows + kK0Rows - 1) / kK0Rows;
+        cudaEventRecord(e0, st);
+        condense_rows_kernel<<<(unsigned)std::min<long long>(groups, n_sm), kK0Threads, kK0SmemBytes, st>>>(
+            d_bins, rows, n_bins, n_used, d_off, d_first, n_regions, n_tiles, d_out);
+        cudaEventRecord(e1, st);
+        e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(D_regions + r0 * n_regions, d_out, sizeof(double) * rows * n_regions, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            total_us += 1e3 * ms;
+        }
+    }
+    cudaFree(d_bins); cudaFree(d_out); cudaFree(d_off); cudaFree(d_first);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    if (e != cudaSuccess) return fail(SCICONE_ERR_CUDA, "condense_matrix: %s", cudaGetErrorString(e));
+    if (kernel_us) *kernel_us = total_us;
     return SCICONE_OK;
 }
 

@@ -160,3 +160,15 @@ def log_sum(v):
 def log_replace_sum(s, sub, add, unch):
     sub, add, unch = (np.ascontiguousarray(x, dtype=np.float64) for x in (sub, add, unch))
     return lib().orc_log_replace_sum(s, _dp(sub), len(sub), _dp(add), len(add), _dp(unch), len(unch))
+
+
+def condense_matrix(D_bins, region_sizes):
+    """orc_condense_matrix: the oracle's restatement of Utils::condense_matrix (Utils.cpp:104-138)."""
+    D_bins = np.ascontiguousarray(D_bins, dtype=np.float64)
+    r = np.ascontiguousarray(region_sizes, dtype=np.int32)
+    out = np.empty((D_bins.shape[0], r.size), dtype=np.float64)
+    L = lib()
+    L.orc_condense_matrix.argtypes = [C.POINTER(C.c_double), C.c_int64, C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_double)]
+    rc = L.orc_condense_matrix(_dp(D_bins), D_bins.shape[0], D_bins.shape[1], _ip(r), int(r.size), _dp(out))
+    assert rc == 0
+    return out
