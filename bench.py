@@ -127,6 +127,9 @@ def run_engine(args):
     torch.cuda.set_device(local)
     import torch.distributed as dist
 
+    if world > 1:  # the ranks share the host cores: split them between the libraries' worker pools
+        os.environ.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

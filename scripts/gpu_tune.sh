@@ -5,7 +5,7 @@ TAG=${1:-tune}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 ARGS="--steps 100 --warmup 10 --no_cpu_baseline --no_e2e"
-for occ in 6 8; do
+for occ in 8; do
   SCICONE_OCC=$occ python bench.py $ARGS > "$OUT/occ$occ.json" 2> "$OUT/occ$occ.err"
   python - "$OUT/occ$occ.json" $occ <<'PY'
 import json,sys
@@ -14,7 +14,7 @@ print("occ",sys.argv[2],"ms_per_step",round(b["ms_per_step"],4),"score_us",round
 PY
 done
 SHORT="--steps 6 --warmup 3 --no_cpu_baseline --no_e2e"
-ncu --set full --clock-control none --import-source on -k regex:build_rows -s 80 -c 6 -o "$OUT/prof_build" python bench.py $SHORT > "$OUT/ncu_build.log" 2>&1
+ncu --set full --clock-control none --import-source on -k regex:build_rows -s 34 -c 6 -o "$OUT/prof_build" python bench.py $SHORT > "$OUT/ncu_build.log" 2>&1
 echo "ncu build rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:score_proposals -s 70 -c 3 -o "$OUT/prof" python bench.py $SHORT > "$OUT/ncu_full.log" 2>&1
 echo "ncu score rc=$?"
