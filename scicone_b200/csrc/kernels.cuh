@@ -56,10 +56,9 @@ enum : unsigned {
     PROP_SCRATCH = 8u,   // to_add.size() >= unchanged_vals.size(): recompute the log-sum from scratch
     PROP_WITH_OD = 16u,  // also evaluate the root ("overdispersed") score from its region slices
     PROP_OD_ONLY = 32u,  // no tasks, no aggregate: only the root score
-    BUILD_DELTA = 0u,
     BUILD_OD_SLICE = 1u,
     BUILD_OD_SLICE_LOG = 2u,  // non-overdispersed root score slice: sum_k D_k log r_k
-    BUILD_G = 3u              // z-term row lgamma(S + c1)
+    BUILD_G = 3u              // dst = lgamma(src + c1): lgamma rows L(k, cn) (src = Dt[k]) and z-term rows (src = S)
 };
 
 struct alignas(16) DevTask {
@@ -89,9 +88,9 @@ struct alignas(16) DevChunk {  // tasks [first_task, first_task + n_tasks) and e
 };
 
 struct alignas(16) DevEvent {
-    const double* row;  // OD: delta row;  non-OD: Dt[k]
-    double a, b;        // OD: lgamma((nu*cn)*r) of node / parent;  non-OD: a = log(cn_node) - log(cn_parent)
-    double pad;
+    const double* row;    // OD: lgamma row L(k, cn_node);  non-OD: Dt[k]
+    const double* row_p;  // OD: lgamma row L(k, cn_parent)
+    double a, b;          // OD: lgamma((nu*cn)*r) of node / parent;  non-OD: a = log(cn_node) - log(cn_parent)
 };
 static_assert(sizeof(DevEvent) == 32, "DevEvent is staged as two 16-byte pieces");
 
@@ -99,6 +98,15 @@ struct alignas(16) DevUnch {
     const double* row;
     int id;
     int pad;
+};
+
+// One per proposal at the start of the arena: where its blob is and what its first chunk stages, so that a CTA can issue
+// the header read and the first task / event copies together instead of chasing offsets through the header.
+struct alignas(16) LaunchEntry {
+    unsigned blob_off;   // byte offset of the proposal's blob (DevHeader first, DevTask array right behind it)
+    unsigned n_tasks0;   // tasks of the first chunk
+    unsigned n_ev0;      // staged events of the first chunk
+    unsigned ev_off0;    // byte offset (inside the blob) of the first chunk's first event record
 };
 
 struct alignas(16) DevHeader {
@@ -126,8 +134,8 @@ struct alignas(16) DevHeader {
 
 struct alignas(16) DevBuild {
     double* dst;
-    const double* src;     // BUILD_DELTA: Dt[k];  slices: Dt
-    double c1, c2;         // BUILD_DELTA: (nu*cn)*r, (nu*cn_parent)*r
+    const double* src;     // BUILD_G: Dt[k] or S;  slices: Dt
+    double c1, c2;         // BUILD_G: c1 = (nu*cn)*r or nu*z
     unsigned kind;
     int k0, k1;            // slices: region range
     unsigned off_arg;      // slices: arena offsets of arg[K], cc[K]
@@ -262,22 +270,7 @@ __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned 
     load_log_table<kBuildBlock>(tbl);
     const DevBuild it = reinterpret_cast<const DevBuild*>(arena + off_items)[blockIdx.y];
     const int j0 = blockIdx.x * (kBuildBlock * kBuildCells) + threadIdx.x;
-    if (it.kind == BUILD_G) {  // lgamma(S + nu*z) of one node for every cell (Tree.h:229-231)
-        double d[kBuildCells];
-#pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) {
-            const int j = j0 + q * kBuildBlock;
-            d[q] = j < it.n_cells ? __ldg(it.src + j) : 32.0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) {
-            const int j = j0 + q * kBuildBlock;
-            if (j < it.n_cells) it.dst[j] = lgam(d[q] + it.c1, tbl);
-        }
-        return;
-    }
-    if (it.kind == BUILD_DELTA) {
+    if (it.kind == BUILD_G) {  // one lgamma per cell: L(k, cn) (Tree.h:214-218) or the z-term of a node (Tree.h:229-231)
         // kBuildCells cells per thread: the loads go out together, and the table copy / item fetch is paid once
         double d[kBuildCells];
 #pragma unroll
@@ -289,7 +282,7 @@ __global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned 
 #pragma unroll
         for (int q = 0; q < kBuildCells; ++q) {
             const int j = j0 + q * kBuildBlock;
-            if (j < it.n_cells) it.dst[j] = lgam(d[q] + it.c1, tbl) - lgam(d[q] + it.c2, tbl);
+            if (j < it.n_cells) it.dst[j] = lgam(d[q] + it.c1, tbl);
         }
         return;
     }
@@ -326,11 +319,15 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
     __shared__ double red_buf[kThreads / 32];
     __shared__ double tbl[kLogTableDoubles];
     load_log_table<kThreads>(tbl);
-    __syncthreads();
 
-    const unsigned* blob_off = reinterpret_cast<const unsigned*>(arena);
-    const unsigned char* blob = arena + blob_off[blockIdx.y];
+    const LaunchEntry le = reinterpret_cast<const LaunchEntry*>(arena)[blockIdx.y];
+    const unsigned char* blob = arena + le.blob_off;
     const DevHeader& H = *reinterpret_cast<const DevHeader*>(blob);
+    // first chunk: its records follow from the launch entry alone, so these copies go out together with the header reads
+    for (int q = threadIdx.x; q < (int)le.n_tasks0 * 4; q += kThreads)
+        copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, blob + sizeof(DevHeader) + 16 * q);
+    for (int q = threadIdx.x; q < (int)le.n_ev0 * 2; q += kThreads)
+        copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, blob + le.ev_off0 + 16 * q);
 
     const int j = blockIdx.x * kCells + threadIdx.x;
     const bool live = j < H.n_cells;
@@ -353,17 +350,26 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
     const DevChunk* chunks = reinterpret_cast<const DevChunk*>(blob + H.off_chunks);
 
     const int n_chunks = H.n_chunks;
+    __syncthreads();  // first chunk staged, logarithm table loaded
     for (int c = 0; c < n_chunks; ++c) {
-        const DevChunk ck = chunks[c];
-        const DevTask* tasks = reinterpret_cast<const DevTask*>(blob + H.off_tasks);
-        const DevEvent* events = reinterpret_cast<const DevEvent*>(blob + H.off_events);
-        // ---- stage the task and event records of this chunk
-        __syncthreads();
-        for (int q = threadIdx.x; q < ck.n_tasks * 4; q += kThreads)
-            copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, reinterpret_cast<const unsigned char*>(tasks + ck.first_task) + 16 * q);
-        for (int q = threadIdx.x; q < ck.n_ev * 2; q += kThreads)
-            copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, reinterpret_cast<const unsigned char*>(events + ck.ev_base) + 16 * q);
-        __syncthreads();
+        DevChunk ck;
+        if (c == 0) {
+            ck.first_task = 0;
+            ck.n_tasks = (int)le.n_tasks0;
+            ck.ev_base = 0;
+            ck.n_ev = (int)le.n_ev0;
+        } else {
+            ck = chunks[c];
+            const DevTask* tasks = reinterpret_cast<const DevTask*>(blob + sizeof(DevHeader));
+            const DevEvent* events = reinterpret_cast<const DevEvent*>(blob + H.off_events);
+            // ---- stage the task and event records of this chunk
+            __syncthreads();
+            for (int q = threadIdx.x; q < ck.n_tasks * 4; q += kThreads)
+                copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, reinterpret_cast<const unsigned char*>(tasks + ck.first_task) + 16 * q);
+            for (int q = threadIdx.x; q < ck.n_ev * 2; q += kThreads)
+                copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, reinterpret_cast<const unsigned char*>(events + ck.ev_base) + 16 * q);
+            __syncthreads();
+        }
         if (!live) continue;
         // the first two delta-row gathers of a node are issued while the node before it is being scored
         double dn0 = 0.0, dn1 = 0.0, gn = 0.0, gpn = 0.0;
@@ -375,8 +381,10 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             }
             if (nx.flags & (TASK_ROOT | TASK_BIG)) return;
             const DevEvent* ev = sm_ev + nx.ev_rel;
-            if (nx.n_ev > 0) dn0 = __ldg(ev[0].row + j);
-            if (nx.n_ev > 1) dn1 = __ldg(ev[1].row + j);
+            if (nx.n_ev > 0) {  // first event: node row and (OD) parent row
+                dn0 = __ldg(ev[0].row + j);
+                if (od) dn1 = __ldg(ev[0].row_p + j);
+            }
         };
         prefetch_gathers(sm_task[0]);
         for (int t = 0; t < ck.n_tasks; ++t) {
@@ -394,11 +402,15 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                 const int ne = tk.n_ev;
                 const bool big = tf & TASK_BIG;  // more events than the staging buffer holds (rare): read from global memory
                 const DevEvent* ev = big ? reinterpret_cast<const DevEvent*>(blob + H.off_events) + tk.ev_begin : sm_ev + tk.ev_rel;
-                double d[4];  // gathers 0 and 1 were issued one node ago, 2 and 3 go out now ...
-                d[0] = big ? (ne > 0 ? __ldg(ev[0].row + j) : 0.0) : d0;
-                d[1] = big ? (ne > 1 ? __ldg(ev[1].row + j) : 0.0) : d1;
+                // event 0 was gathered one node ago, events 1 and 2 go out now ...
+                double dq[3], dp[3];
+                dq[0] = big ? (ne > 0 ? __ldg(ev[0].row + j) : 0.0) : d0;
+                dp[0] = (big && od) ? (ne > 0 ? __ldg(ev[0].row_p + j) : 0.0) : d1;
 #pragma unroll
-                for (int q = 2; q < 4; ++q) d[q] = (q < ne) ? __ldg(ev[q].row + j) : 0.0;
+                for (int q = 1; q < 3; ++q) {
+                    dq[q] = (q < ne) ? __ldg(ev[q].row + j) : 0.0;
+                    dp[q] = (od && q < ne) ? __ldg(ev[q].row_p + j) : 0.0;
+                }
                 double g = 0.0, gp = 0.0;  // ... the z-terms are evaluated while they are in flight ...
                 if (od) {
                     if (tf & TASK_G_ROW) {
@@ -412,14 +424,14 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                 }
                 if (od) {  // ... and they are added in event order (Tree.h:214-218)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < 3; ++q)
                         if (q < ne) {
-                            x += d[q];
+                            x += dq[q] - dp[q];
                             x -= ev[q].a;
                             x += ev[q].b;
                         }
-                    for (int q = 4; q < ne; ++q) {
-                        x += __ldg(ev[q].row + j);
+                    for (int q = 3; q < ne; ++q) {
+                        x += __ldg(ev[q].row + j) - __ldg(ev[q].row_p + j);
                         x -= ev[q].a;
                         x += ev[q].b;
                     }
@@ -429,9 +441,9 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                     x += gp;
                 } else {  // Tree.h:221,236-237
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (q < ne) x += d[q] * ev[q].a;
-                    for (int q = 4; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
+                    for (int q = 0; q < 3; ++q)
+                        if (q < ne) x += dq[q] * ev[q].a;
+                    for (int q = 3; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
                     x -= S * tk.lg_nz;
                     x += S * tk.lg_nzp;
                 }
@@ -469,24 +481,33 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             double prev_val = agg_old;
             if (prev_in_new || pm == H.deleted_id) {
                 // the previous argmax was rescored or deleted: first maximum of the unchanged rows in ascending id order
+                // two batches of four loads are kept in flight: the next batch is issued before the current one is compared
                 double cur = -DBL_MAX;
                 int uid = 0;
-                int u = 0;
-                for (; u + 4 <= n_unch; u += 4) {
-                    double v[4];
+                const int n4 = n_unch & ~3;
+                double v[4], w[4];
+                if (n4 > 0) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = __ldcg(unch[u + q].row + j);
+                    for (int q = 0; q < 4; ++q) v[q] = __ldcg(unch[q].row + j);
+                }
+                for (int u = 0; u < n4; u += 4) {
+                    if (u + 4 < n4) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) w[q] = __ldcg(unch[u + 4 + q].row + j);
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         if (v[q] > cur) {
                             cur = v[q];
                             uid = unch[u + q].id;
                         }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = w[q];
                 }
-                for (; u < n_unch; ++u) {
-                    const double v = __ldcg(unch[u].row + j);
-                    if (v > cur) {
-                        cur = v;
+                for (int u = n4; u < n_unch; ++u) {
+                    const double x = __ldcg(unch[u].row + j);
+                    if (x > cur) {
+                        cur = x;
                         uid = unch[u].id;
                     }
                 }

@@ -239,11 +239,9 @@ private:
     std::vector<value_type> v_;
 };
 
-// (region, copy number of the node, copy number of the parent) -> delta row at one nu
+// (region, copy number) -> lgamma row L(k, cn) at one nu
 typedef FlatMap<uint64_t, double*> LCache;
-inline uint64_t lkey(int k, int cn, int cp) {
-    return (uint64_t(uint32_t(k)) << 32) | (uint64_t(uint16_t(cn)) << 16) | uint64_t(uint16_t(cp));
-}
+inline uint64_t lkey(int k, int cn) { return (uint64_t(uint32_t(k)) << 32) | uint64_t(uint32_t(cn)); }
 
 }  // namespace
 
@@ -436,6 +434,7 @@ struct scicone_chain {
         stash.push_back(r);
         if (stash.size() > kStashMax) ds->pool.put_many(stash, kStashMax / 2);
     }
+    LaunchEntry entry = {0u, 0u, 0u, 0u};  // first-chunk descriptor of the compiled blob (blob_off is filled in at submit)
     double cost = 0.0;  // relative device time of the compiled proposal (orders the blobs inside a launch)
 };
 
@@ -651,21 +650,30 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                         const double argP = nu * parent_cn * ds->r[k];
                         ev.a = lgamma(argN);
                         ev.b = lgamma(argP);
-                        double** slotp = &(*L)[lkey(k, cn_i, cp_i)];
-                        if (!*slotp) {  // first use of this (region, copy-number pair) at this nu: K1 builds the row
-                            CUDA_TRY(ch->row_get(slotp));
-                            DevBuild it;
-                            memset(&it, 0, sizeof it);
-                            it.dst = *slotp;
-                            it.src = ds->dDt + (size_t)k * ds->Mp;
-                            it.c1 = argN;
-                            it.c2 = argP;
-                            it.kind = BUILD_DELTA;
-                            it.n_cells = ds->M;
-                            it.row_stride = (long long)ds->Mp;
-                            ch->builds.push_back(it);
+                        // lgamma rows L(k, cn)[j] = lgamma(D[j][k] + (nu*cn)*r_k): built by K1 on first use at this nu, shared
+                        // by every event that touches region k at that copy number (the parent side is most often the
+                        // neutral state, so a region's second row usually exists already)
+                        const double arg[2] = {argN, argP};
+                        const int cn2[2] = {cn_i, cp_i};
+                        const double* rows2[2];
+                        for (int side = 0; side < 2; ++side) {
+                            double** slotp = &(*L)[lkey(k, cn2[side])];
+                            if (!*slotp) {
+                                CUDA_TRY(ch->row_get(slotp));
+                                DevBuild it;
+                                memset(&it, 0, sizeof it);
+                                it.dst = *slotp;
+                                it.src = ds->dDt + (size_t)k * ds->Mp;
+                                it.c1 = arg[side];
+                                it.kind = BUILD_G;  // dst = lgamma(src + c1)
+                                it.n_cells = ds->M;
+                                it.row_stride = (long long)ds->Mp;
+                                ch->builds.push_back(it);
+                            }
+                            rows2[side] = *slotp;
                         }
-                        ev.row = *slotp;
+                        ev.row = rows2[0];
+                        ev.row_p = rows2[1];
                     } else {  // Tree.h:221
                         ev.row = ds->dDt + (size_t)k * ds->Mp;
                         ev.a = log(node_cn) - log(parent_cn);
@@ -840,6 +848,9 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     H.off_od_rows = (unsigned)blob_append(b, slice_rows);
     b.resize(round_up(b.size(), 16));
     memcpy(b.data(), &H, sizeof H);
+    if (H.off_tasks != sizeof(DevHeader)) return fail(SCICONE_ERR_STATE, "internal: task records must follow the header");
+    ch->entry = LaunchEntry{0u, chunks.empty() ? 0u : (unsigned)chunks[0].n_tasks, chunks.empty() ? 0u : (unsigned)chunks[0].n_ev,
+                            chunks.empty() ? 0u : H.off_events + (unsigned)chunks[0].ev_base * (unsigned)sizeof(DevEvent)};
     return SCICONE_OK;
 }
 
@@ -865,13 +876,14 @@ int compile_od_only(scicone_chain* ch, double nu, int slot) {
     ch->alg_bytes = (double)ch->ds->M * 8.0 * ch->ds->K;
     ch->n_scores = 0.0;
     ch->with_od = true;
+    ch->entry = LaunchEntry{0u, 0u, 0u, 0u};
     return SCICONE_OK;
 }
 
 // Queue the compiled blobs of `n` chains (all on one dataset): K1 for the data-only lgamma work they need
 // (if any), then ONE launch of the proposal kernel; returns a ticket.
 int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, unsigned long long* ticket) {
-    const size_t head = round_up(sizeof(unsigned) * n, 16);
+    const size_t head = sizeof(LaunchEntry) * n;
     size_t bytes = head, n_items = 0, aux_bytes = 0;
     for (int i = 0; i < n; ++i) {
         bytes += chains[i]->blob.size();
@@ -887,7 +899,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     scicone_dataset::Segment& g = ds->seg[tk % scicone_dataset::kRing];
     if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
     g.with_od.assign(n, 0);
-    unsigned* offs = reinterpret_cast<unsigned*>(g.h_arena);
+    LaunchEntry* offs = reinterpret_cast<LaunchEntry*>(g.h_arena);
     size_t at = head, item_at = off_items, aux_at = off_aux;
     // grid.y order = longest proposal first (CTAs are dispatched in block-id order): the heavy full-tree
     // rescorings of nu proposals start at once and the short ones fill in behind them.  Results are addressed by
@@ -895,7 +907,6 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return chains[a]->cost > chains[b]->cost; });
-    for (int q = 0; q < n; ++q) offs[q] = 0;
     std::vector<unsigned> blob_at(n);
     for (int i = 0; i < n; ++i) {
         scicone_chain* ch = chains[i];
@@ -905,7 +916,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         if (!ch->build_aux.empty()) memcpy(g.h_arena + aux_at, ch->build_aux.data(), ch->build_aux.size() * sizeof(double));
         for (const DevBuild& src : ch->builds) {
             DevBuild it = src;
-            if (it.kind != BUILD_DELTA) {
+            if (it.kind == BUILD_OD_SLICE || it.kind == BUILD_OD_SLICE_LOG) {
                 it.off_arg += (unsigned)aux_at;
                 it.off_c += (unsigned)aux_at;
             }
@@ -914,7 +925,10 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         }
         aux_at += round_up(ch->build_aux.size() * sizeof(double), 16);
     }
-    for (int q = 0; q < n; ++q) offs[q] = blob_at[order[q]];
+    for (int q = 0; q < n; ++q) {
+        offs[q] = chains[order[q]]->entry;
+        offs[q].blob_off = blob_at[order[q]];
+    }
     CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, ds->stream));
