@@ -49,7 +49,6 @@ enum : unsigned {
     TASK_SKIP_AGG = 4u,  // a later task rewrites the same node: only that one enters the aggregate
     TASK_CHAINED = 8u,   // the parent is the task right before this one: its score (and z-term) are still in registers
     TASK_BIG = 16u,      // more events than the staging buffer holds: read from global memory
-    TASK_G_ROW = 32u,    // z-terms come from rows built by K1 (BUILD_G) instead of being evaluated in the serial walk
     PROP_MAX = 1u,       // max scoring (Inference::max_scoring)
     PROP_OD = 2u,        // overdispersed likelihood (globals is_overdispersed)
     PROP_FULL = 4u,      // full table pass (Inference::compute_t_table): no committed state is read
@@ -67,9 +66,9 @@ struct alignas(16) DevTask {
     double lg_nz, lg_nzp;        // OD: lgamma(nu*z), lgamma(nu*z_parent);  non-OD: log(z), log(z_parent)
     union {
         struct {
-            double nz, nzp;          // OD: nu*z, nu*z_parent: the z-terms lgamma(S + nu*z) are evaluated in the kernel
+            double nz, nzp;          // host side while compiling (and non-OD): nu*z, nu*z_parent
         };
-        struct {                     // TASK_G_ROW (long proposals): the z-terms were built as rows by K1 and are only gathered
+        struct {                     // OD, on the device: the z-terms are rows built by K1 and only gathered in the walk
             const double* g_row;     // lgamma(S + nu*z)
             const double* gp_row;    // lgamma(S + nu*z_parent); unused when TASK_REUSE_G
         };
@@ -129,7 +128,7 @@ struct alignas(16) DevHeader {
     double od_lg_nz, od_nz;  // OD: lgamma(nu*z_root), nu*z_root;  non-OD: od_lg_nz = log(sum_r)
     unsigned off_tasks, off_events, off_old, off_unch, off_od_rows, off_chunks;
     const double* first_parent_row;  // parent score row of task 0 (null for a root)
-    double pad3;
+    const double* od_g_row;          // PROP_WITH_OD, OD: row lgamma(S + nu*z_root) built by K1
 };
 
 struct alignas(16) DevBuild {
@@ -263,31 +262,64 @@ __device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned c
 }
 
 // ---------------------------------------------------------------------------------
-// K1: data-only lgamma work.  grid = (ceil(M / (kBuildBlock * kBuildCells)), n_items).
+// K1: data-only lgamma work.  Persistent grid (up to 4 CTAs per SM) over n_items x ceil(M / (kBuildBlock * kBuildCells)) units.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBuildBlock) build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items) {
+__global__ void __launch_bounds__(kBuildBlock, 4)
+    build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items, int n_items, int blocks_per_row) {
+    // Persistent CTAs: a unit of work is (item, block of kBuildBlock * kBuildCells cells).  A unit is only ~4 lgamma per
+    // thread, so the fixed latencies (table copy, item record, data load: ~2.5 us) are paid once per CTA / hidden by
+    // fetching the next unit's record and data while the current unit is evaluated.
     __shared__ double tbl[kLogTableDoubles];
     load_log_table<kBuildBlock>(tbl);
-    const DevBuild it = reinterpret_cast<const DevBuild*>(arena + off_items)[blockIdx.y];
-    const int j0 = blockIdx.x * (kBuildBlock * kBuildCells) + threadIdx.x;
-    if (it.kind == BUILD_G) {  // one lgamma per cell: L(k, cn) (Tree.h:214-218) or the z-term of a node (Tree.h:229-231)
-        // kBuildCells cells per thread: the loads go out together, and the table copy / item fetch is paid once
+    const DevBuild* items = reinterpret_cast<const DevBuild*>(arena + off_items);
+    const int total = n_items * blocks_per_row;
+    int u = blockIdx.x;
+    // next unit's record (the fields the one-lgamma path needs) and data
+    unsigned nkind = 0;
+    double* ndst = nullptr;
+    const double* nsrc = nullptr;
+    double nc1 = 0.0;
+    int nn = 0;
+    double nd[kBuildCells];
+    auto fetch = [&](int unit) {
+        const DevBuild& it = items[unit / blocks_per_row];
+        nkind = it.kind;
+        ndst = it.dst;
+        nsrc = it.src;
+        nc1 = it.c1;
+        nn = it.n_cells;
+        if (nkind == BUILD_G) {
+            const int j0 = (unit % blocks_per_row) * (kBuildBlock * kBuildCells) + threadIdx.x;
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) {
+                const int j = j0 + q * kBuildBlock;
+                nd[q] = j < nn ? __ldg(nsrc + j) : 32.0;
+            }
+        }
+    };
+    if (u < total) fetch(u);
+    __syncthreads();  // table loaded
+    while (u < total) {
+        const unsigned kind = nkind;
+        double* const dst = ndst;
+        const double c1 = nc1;
+        const int n_cells = nn;
         double d[kBuildCells];
 #pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) {
-            const int j = j0 + q * kBuildBlock;
-            d[q] = j < it.n_cells ? __ldg(it.src + j) : 32.0;
-        }
-        __syncthreads();
+        for (int q = 0; q < kBuildCells; ++q) d[q] = nd[q];
+        const int cur = u;
+        u += gridDim.x;
+        if (u < total) fetch(u);
+        const int j0 = (cur % blocks_per_row) * (kBuildBlock * kBuildCells) + threadIdx.x;
+        if (kind == BUILD_G) {  // one lgamma per cell: L(k, cn) (Tree.h:214-218) or the z-term of a node (Tree.h:229-231)
 #pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) {
-            const int j = j0 + q * kBuildBlock;
-            if (j < it.n_cells) it.dst[j] = lgam(d[q] + it.c1, tbl);
-        }
-        return;
+            for (int q = 0; q < kBuildCells; ++q) {
+                const int j = j0 + q * kBuildBlock;
+                if (j < n_cells) dst[j] = lgam(d[q] + c1, tbl);
+            }
+        } else
+            build_slice(items[cur / blocks_per_row], arena, j0, tbl);
     }
-    __syncthreads();
-    build_slice(it, arena, j0, tbl);
 }
 
 // ---------------------------------------------------------------------------------
@@ -317,8 +349,6 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
     __shared__ __align__(16) DevTask sm_task[kTaskChunk];
     __shared__ __align__(16) DevEvent sm_ev[kEvStage];
     __shared__ double red_buf[kThreads / 32];
-    __shared__ double tbl[kLogTableDoubles];
-    load_log_table<kThreads>(tbl);
 
     const LaunchEntry le = reinterpret_cast<const LaunchEntry*>(arena)[blockIdx.y];
     const unsigned char* blob = arena + le.blob_off;
@@ -350,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
     const DevChunk* chunks = reinterpret_cast<const DevChunk*>(blob + H.off_chunks);
 
     const int n_chunks = H.n_chunks;
-    __syncthreads();  // first chunk staged, logarithm table loaded
+    __syncthreads();  // first chunk staged
     for (int c = 0; c < n_chunks; ++c) {
         DevChunk ck;
         if (c == 0) {
@@ -375,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
         double dn0 = 0.0, dn1 = 0.0, gn = 0.0, gpn = 0.0;
         auto prefetch_gathers = [&](const DevTask& nx) {
             dn0 = dn1 = 0.0;
-            if (od && (nx.flags & TASK_G_ROW)) {  // z-terms of a long proposal: rows built by K1
+            if (od) {  // z-terms: rows built by K1
                 gn = __ldg(nx.g_row + j);
                 if (!(nx.flags & (TASK_ROOT | TASK_REUSE_G))) gpn = __ldg(nx.gp_row + j);
             }
@@ -411,15 +441,10 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                     dq[q] = (q < ne) ? __ldg(ev[q].row + j) : 0.0;
                     dp[q] = (od && q < ne) ? __ldg(ev[q].row_p + j) : 0.0;
                 }
-                double g = 0.0, gp = 0.0;  // ... the z-terms are evaluated while they are in flight ...
+                double g = 0.0, gp = 0.0;  // z-terms lgamma(S + nu z), lgamma(S + nu z_parent): gathered from K1's rows
                 if (od) {
-                    if (tf & TASK_G_ROW) {
-                        g = g_row_val;
-                        gp = (tf & TASK_REUSE_G) ? g_prev : gp_row_val;
-                    } else {
-                        g = lgam(S + tk.nz, tbl);
-                        gp = (tf & TASK_REUSE_G) ? g_prev : lgam(S + tk.nzp, tbl);
-                    }
+                    g = g_row_val;
+                    gp = (tf & TASK_REUSE_G) ? g_prev : gp_row_val;
                     g_prev = g;
                 }
                 if (od) {  // ... and they are added in event order (Tree.h:214-218)
@@ -449,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                 }
                 sc = ps + x;
             } else if (od)
-                g_prev = (tf & TASK_G_ROW) ? g_row_val : lgam(S + tk.nz, tbl);
+                g_prev = g_row_val;
             sc_prev = sc;
             tk.dst[j] = sc;
             if (tf & TASK_SKIP_AGG) continue;
@@ -568,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
         double v = 0.0;
         if (od) {
             v += H.od_lg_nz;
-            v -= lgam(S + H.od_nz, tbl);
+            v -= __ldcg(H.od_g_row + j);
         } else
             v += -S * H.od_lg_nz;
         int s = 0;

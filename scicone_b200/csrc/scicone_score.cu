@@ -250,6 +250,7 @@ struct scicone_dataset {
     int M = 0, K = 0;
     size_t Mp = 0;
     int device = 0;
+    int n_sm = 148;
     double eta = 0;
     bool od = false, maxs = false;
     long long cell_offset = 0, M_global = 0;
@@ -378,7 +379,6 @@ struct scicone_dataset {
 
 constexpr size_t kStashRefill = 32, kStashMax = 160;
 constexpr int kDefaultOcc = 8;
-constexpr int kGRowMinTasks = 12;  // from this many rescored nodes on, the z-terms are built as rows by K1
 
 struct scicone_chain {
     scicone_dataset* ds = nullptr;
@@ -498,6 +498,21 @@ int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const
     if (ds->od) {  // Tree.h:1783-1797 (no eta substitution here, quirk Q2)
         H.od_nz = nu * ds->root_z;
         H.od_lg_nz = lgamma(H.od_nz);
+        {   // lgamma(S + nu z_root) as a K1 row
+            double* row = nullptr;
+            CUDA_TRY(ch->row_get(&row));
+            ch->temp_rows.push_back(row);
+            DevBuild it;
+            memset(&it, 0, sizeof it);
+            it.dst = row;
+            it.src = ds->dS;
+            it.c1 = H.od_nz;
+            it.kind = BUILD_G;
+            it.n_cells = ds->M;
+            it.row_stride = (long long)ds->Mp;
+            ch->builds.push_back(it);
+            H.od_g_row = row;
+        }
         for (int k = 0; k < K; ++k) {
             arg[k] = nu * ds->neutral[k] * ds->r[k];
             cc[k] = lgamma(arg[k]);
@@ -723,9 +738,9 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     // the previous node is processed.  Chunks: what is staged in shared memory together.
     std::vector<DevChunk>& chunks = W.chunks;
     chunks.clear();
-    // Long proposals (full passes, nu proposals, large subtrees): the z-terms lgamma(S + nu z) leave the serial walk and
-    // are built as rows by K1, where every (node, cell) pair is independent; the walk then only gathers and adds.
-    const bool g_rows = od && tasks.size() >= (size_t)kGRowMinTasks;
+    // The z-terms lgamma(S + nu z) are not evaluated in the serial walk: K1 builds them as rows, where every (node, cell)
+    // pair is independent; the walk only gathers and adds (and the proposal kernel carries no lgamma code at all).
+    const bool g_rows = od;
     if (g_rows) {
         auto build_g = [&](double arg, const double** out) -> int {
             double* row = nullptr;
@@ -760,7 +775,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             }
             tasks[i].g_row = g;
             tasks[i].gp_row = gp;
-            tasks[i].flags |= TASK_G_ROW;
         }
     }
     for (size_t i = 0; i < tasks.size(); ++i) {
@@ -900,7 +914,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
     g.with_od.assign(n, 0);
     LaunchEntry* offs = reinterpret_cast<LaunchEntry*>(g.h_arena);
-    size_t at = head, item_at = off_items, aux_at = off_aux;
+    size_t at = head, item_at = off_items;
     // grid.y order = longest proposal first (CTAs are dispatched in block-id order): the heavy full-tree
     // rescorings of nu proposals start at once and the short ones fill in behind them.  Results are addressed by
     // the slot pointers inside each header, so the order of the blobs is free.
@@ -913,17 +927,28 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         blob_at[i] = (unsigned)at;
         memcpy(g.h_arena + at, ch->blob.data(), ch->blob.size());
         at += ch->blob.size();
-        if (!ch->build_aux.empty()) memcpy(g.h_arena + aux_at, ch->build_aux.data(), ch->build_aux.size() * sizeof(double));
-        for (const DevBuild& src : ch->builds) {
-            DevBuild it = src;
-            if (it.kind == BUILD_OD_SLICE || it.kind == BUILD_OD_SLICE_LOG) {
-                it.off_arg += (unsigned)aux_at;
-                it.off_c += (unsigned)aux_at;
+    }
+    // K1 items: the root-score slices (about 24 lgamma per thread and unit) first, the one-lgamma rows behind them,
+    // so the persistent CTAs start with the long units
+    for (int pass = 0; pass < 2; ++pass) {
+        size_t chain_aux = off_aux;
+        for (int i = 0; i < n; ++i) {
+            scicone_chain* ch = chains[i];
+            if (pass == 0 && !ch->build_aux.empty())
+                memcpy(g.h_arena + chain_aux, ch->build_aux.data(), ch->build_aux.size() * sizeof(double));
+            for (const DevBuild& src : ch->builds) {
+                const bool slice = src.kind == BUILD_OD_SLICE || src.kind == BUILD_OD_SLICE_LOG;
+                if (slice != (pass == 0)) continue;
+                DevBuild it = src;
+                if (slice) {
+                    it.off_arg += (unsigned)chain_aux;
+                    it.off_c += (unsigned)chain_aux;
+                }
+                memcpy(g.h_arena + item_at, &it, sizeof it);
+                item_at += sizeof it;
             }
-            memcpy(g.h_arena + item_at, &it, sizeof it);
-            item_at += sizeof it;
+            chain_aux += round_up(ch->build_aux.size() * sizeof(double), 16);
         }
-        aux_at += round_up(ch->build_aux.size() * sizeof(double), 16);
     }
     for (int q = 0; q < n; ++q) {
         offs[q] = chains[order[q]]->entry;
@@ -932,19 +957,21 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, ds->stream));
-        build_rows_kernel<<<dim3((ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells), (unsigned)n_items), kBuildBlock, 0, ds->stream>>>(
-            ds->d_arena, (unsigned)off_items);
+        const int blocks_per_row = (ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells);
+        const long long units = (long long)n_items * blocks_per_row;
+        build_rows_kernel<<<(unsigned)std::min<long long>(units, 4ll * ds->n_sm), kBuildBlock, 0, ds->stream>>>(
+            ds->d_arena, (unsigned)off_items, (int)n_items, blocks_per_row);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
     }
     g.n_items = (int)n_items;
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, ds->stream));
     {   // scoring mode and likelihood are properties of the dataset: one specialisation per launch.  kOcc = CTAs per SM the
-        // register allocation aims at (6 -> 80 registers, 8 -> 64, 10 -> 48); SCICONE_OCC overrides the default for tuning.
+        // register allocation aims at (8 -> 64 registers, 10 -> 48, 12 -> 40); SCICONE_OCC overrides the default for tuning.
         static const int occ = [] {
             const char* e = getenv("SCICONE_OCC");
             const int v = e ? atoi(e) : 0;
-            return (v == 6 || v == 8 || v == 10) ? v : kDefaultOcc;
+            return (v == 8 || v == 10 || v == 12) ? v : kDefaultOcc;
         }();
         const dim3 grid(ds->n_cta, n);
 #define SCICONE_LAUNCH(OCC)                                                                                                \
@@ -954,7 +981,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         else if (ds->od) score_proposals_kernel<false, true, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);          \
         else score_proposals_kernel<false, false, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);                     \
     } while (0)
-        if (occ == 6) SCICONE_LAUNCH(6);
+        if (occ == 12) SCICONE_LAUNCH(12);
         else if (occ == 10) SCICONE_LAUNCH(10);
         else SCICONE_LAUNCH(8);
 #undef SCICONE_LAUNCH
@@ -1147,6 +1174,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
             return cleanup(fail(SCICONE_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__)); \
     } while (0)
     DS_TRY(cudaSetDevice(ds->device));
+    DS_TRY(cudaDeviceGetAttribute(&ds->n_sm, cudaDevAttrMultiProcessorCount, ds->device));
     DS_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     for (scicone_dataset::Segment& g : ds->seg) {
         DS_TRY(cudaEventCreate(&g.evb));
