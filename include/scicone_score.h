@@ -168,6 +168,9 @@ int scicone_batch_compute_t_prime_scores(scicone_chain* const* chains, const sci
                                          const int32_t* node_idx, int32_t n);
 int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, int32_t n);
 
+/* Non-blocking probe of a ticket: *done = 1 when scicone_batch_wait would return at once. */
+int scicone_batch_poll(scicone_dataset* ds, uint64_t ticket, int32_t* done);
+
 /*
  * Accept (Inference.h:867-870: t_sums = t_prime_sums, t_maxs = t_prime_maxs,
  * update_t_scores(), and the proposal's od score / nu become the committed ones)

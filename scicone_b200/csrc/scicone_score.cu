@@ -1407,6 +1407,16 @@ int scicone_batch_wait(scicone_dataset* ds, uint64_t ticket, double* t_prime_sum
     return rc ? rc : wait_proposals(ds, ticket, t_prime_sums, od_scores);
 }
 
+int scicone_batch_poll(scicone_dataset* ds, uint64_t ticket, int32_t* done) {
+    if (!ds || !done) return fail(SCICONE_ERR_ARG, "batch_poll: null argument");
+    scicone_dataset::Segment& g = ds->seg[ticket % scicone_dataset::kRing];
+    if (!g.busy || g.ticket != ticket) return fail(SCICONE_ERR_STATE, "unknown or already collected ticket %llu", (unsigned long long)ticket);
+    cudaError_t e = cudaEventQuery(g.done);
+    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(SCICONE_ERR_CUDA, "batch_poll: %s", cudaGetErrorString(e));
+    *done = e == cudaSuccess ? 1 : 0;
+    return SCICONE_OK;
+}
+
 int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const* t_primes, int32_t n,
                                        double* t_prime_sums, double* od_scores) {
     if (!t_prime_sums) return fail(SCICONE_ERR_ARG, "batch: null output");

@@ -272,9 +272,19 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         }
 
         if (P.verbosity > 0) std::cout << "Inferring the tree using MCMC with " << n_iters << " iterations..." << std::endl;
+        HostPhaseTimes phase;
+        // schedule: "dynamic" (default for several chains on one GPU) launches whatever is ready; "static" moves groups of
+        // chains in lock-step and is what cell-sharded runs need (every rank must issue the same launches)
+        const std::string schedule = a.str("schedule", (world == 1 && n_chains >= 4) ? "dynamic" : "static");
+        auto run_chains = [&](int iters, HostPhaseTimes* t) {
+            if (schedule == "dynamic" && world == 1)
+                infer_mcmc_dynamic(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("min_batch", 0)), t);
+            else
+                infer_mcmc(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("n_groups", 0)), t);
+        };
         const int warmup_iters = static_cast<int>(a.integer("warmup_iters", 0));
         if (warmup_iters > 0) {  // untimed iterations before the measured run (bench.py); the chains simply continue afterwards
-            infer_mcmc(chains, move_probs, warmup_iters, size_limit, static_cast<int>(a.integer("n_groups", 0)));
+            run_chains(warmup_iters, nullptr);
             for (Inference* c : chains) {
                 c->n_accepted = c->n_rejected = 0;
                 c->n_rescored_nodes = c->n_attempts = 0;
@@ -288,8 +298,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         scicone_kernel_launches(ds, &launches0);
         scicone_region_mark(ds, 0);
         auto start = std::chrono::high_resolution_clock::now();
-        HostPhaseTimes phase;
-        infer_mcmc(chains, move_probs, n_iters, size_limit, static_cast<int>(a.integer("n_groups", 0)), &phase);
+        run_chains(n_iters, &phase);
         if (P.verbosity > 0 && n_chains > 1)
             std::cout << "driver thread: chains " << phase.host_us << " us, submit " << phase.submit_us << " us, wait " << phase.wait_us
                       << " us (" << scicone_host_threads() << " host threads)" << std::endl;
@@ -321,7 +330,8 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
                << ",\"gpu_launches\":" << (launches - launches0) << ",\"h2d_bytes\":" << k[0] << ",\"d2h_bytes\":" << k[1]
                << ",\"alg_bytes\":" << k[2] << ",\"n_scores\":" << k[3] << ",\"device_bytes\":" << dev_bytes << ",\"accepted\":" << acc
                << ",\"rejected\":" << rej << ",\"rescored_nodes\":" << resc << ",\"host_threads\":" << scicone_host_threads() << ",\"attempts\":" << attempts << ",\"chain_finish_us\":" << cf << ",\"chain_propose_us\":" << cp
-               << ",\"chain_prepare_us\":" << cq << ",\"chain_max_visit_us\":" << cmax << ",\"host_us\":" << phase.host_us
+               << ",\"chain_prepare_us\":" << cq << ",\"chain_max_visit_us\":" << cmax << ",\"schedule\":\"" << schedule << "\",\"launches\":" << phase.launches << ",\"launched_chains\":" << phase.launched_chains
+               << ",\"host_us\":" << phase.host_us
                << ",\"submit_us\":" << phase.submit_us << ",\"wait_us\":" << phase.wait_us << "}" << std::endl;
         }
 

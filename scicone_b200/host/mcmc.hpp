@@ -13,8 +13,11 @@
 
 #include <cfloat>
 #include <chrono>
+#include <atomic>
 #include <cstring>
+#include <deque>
 #include <iostream>
+#include <thread>
 #include <exception>
 #include <memory>
 #include <mutex>
@@ -493,6 +496,7 @@ inline void parallel_chains(int n, F&& fn) {
 // does not depend on the grouping or on the number of threads.
 struct HostPhaseTimes {  // wall time of the driver thread per phase, microseconds (for --stats_file)
     double host_us = 0, submit_us = 0, wait_us = 0;  // parallel finish+propose+prepare region / launch / waiting for the GPU
+    unsigned long long launches = 0, launched_chains = 0;  // dynamic schedule: number of launches and proposals in them
 };
 
 inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
@@ -589,6 +593,165 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
     };
     for (int it = 0; it <= n_iters; ++it)
         for (Group& g : groups) visit(g, it);
+}
+
+// The same chains under a dynamic schedule (single GPU): no group ever waits for its slowest member.  Worker threads take
+// chains whose launch has come back, finish that iteration, draw and compile the next proposal and hand the chain to the
+// driver thread; the driver launches whatever is ready as soon as `min_batch` chains are (or nothing else is coming),
+// with at most two launches in flight, and feeds completed launches back to the workers.  Batch composition varies from
+// run to run; a chain's own sequence propose -> score -> compare does not, so trajectories are those of infer_mcmc.
+inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
+                               int min_batch = 0, HostPhaseTimes* times = nullptr) {
+    typedef std::chrono::steady_clock Clock;
+    const int B = static_cast<int>(chains.size());
+    if (B == 0 || n_iters <= 0) return;
+    scicone_dataset* ds = chains[0]->ds;
+    if (min_batch <= 0) min_batch = std::max(1, B / 3);
+    parallel_chains(B, [&](int b) {
+        chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
+        chains[b]->open_traces(n_iters);
+    });
+    struct Slot {
+        int iter = 0;             // iteration whose proposal is queued / in flight
+        bool has_result = false;  // total / od of that proposal are in
+        double total = 0.0, od = 0.0;
+    };
+    std::vector<Slot> st(B);
+    std::mutex mu;  // guards work, ready, n_done, n_host
+    std::deque<int> work;     // chains that need host work
+    std::vector<int> ready;   // chains with a compiled proposal, waiting for a launch
+    int n_done = 0, n_host = B;  // finished chains; chains currently owned by the host side (queued or being worked on)
+    std::atomic<bool> stop{false};
+    std::exception_ptr err;
+    for (int b = 0; b < B; ++b) work.push_back(b);
+
+    auto host_work = [&](int b) {
+        Inference* c = chains[b];
+        Slot& s = st[b];
+        const Clock::time_point c0 = Clock::now();
+        if (s.has_result) {
+            int32_t nr = 0;
+            scicone_t_prime_n_rescored(c->chain, &nr);
+            c->rescored_last = static_cast<unsigned>(nr);
+            c->finish(true, s.total, s.od, s.iter);
+            s.has_result = false;
+            ++s.iter;
+        }
+        bool queued = false;
+        while (s.iter < n_iters) {
+            if (c->propose(move_probs, size_limit)) {
+                abi_check(scicone_prepare_t_prime(c->chain));
+                queued = true;
+                break;
+            }
+            c->finish(false, 0.0, 0.0, s.iter);  // nothing to score (move 10, or every attempt failed)
+            ++s.iter;
+        }
+        const double us = std::chrono::duration<double, std::micro>(Clock::now() - c0).count();
+        c->t_propose_us += us;
+        c->t_max_visit_us = std::max(c->t_max_visit_us, us);
+        std::lock_guard<std::mutex> lk(mu);
+        --n_host;
+        if (queued)
+            ready.push_back(b);
+        else
+            ++n_done;
+    };
+    auto worker = [&]() {
+        int idle = 0;
+        while (!stop.load(std::memory_order_acquire)) {
+            int b = -1;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!work.empty()) {
+                    b = work.front();
+                    work.pop_front();
+                }
+            }
+            if (b < 0) {
+                if (++idle > 2000) std::this_thread::yield();
+                continue;
+            }
+            idle = 0;
+            try {
+                host_work(b);
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!err) err = std::current_exception();
+                stop.store(true, std::memory_order_release);
+            }
+        }
+    };
+    const int n_workers = std::max(1, scicone_host_threads() - 1);
+    std::vector<std::thread> pool;
+    for (int i = 0; i < n_workers; ++i) pool.emplace_back(worker);
+
+    struct Flight {
+        uint64_t ticket;
+        std::vector<int> members;
+    };
+    std::deque<Flight> flights;
+    std::vector<scicone_chain*> handles;
+    std::vector<double> totals(B), ods(B);
+    unsigned long long n_launches = 0, n_launched_chains = 0;
+    auto collect = [&](Flight& f) {
+        int rc = scicone_batch_wait(ds, f.ticket, totals.data(), ods.data());
+        if (rc != SCICONE_OK && rc != SCICONE_ERR_NAN) abi_check(rc);
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < f.members.size(); ++i) {
+            Slot& s = st[f.members[i]];
+            s.total = totals[i];
+            s.od = ods[i];
+            s.has_result = true;
+            work.push_back(f.members[i]);
+            ++n_host;
+        }
+    };
+    try {
+        for (;;) {
+            if (stop.load(std::memory_order_acquire)) break;
+            std::vector<int> take;
+            bool all_done = false;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                all_done = n_done == B;
+                const bool nothing_coming = n_host == 0 && flights.empty();
+                if (!ready.empty() && flights.size() < 2 && (static_cast<int>(ready.size()) >= min_batch || nothing_coming || (n_host == 0 && flights.size() < 2)))
+                    take.swap(ready);
+            }
+            if (all_done) break;
+            if (!take.empty()) {
+                std::sort(take.begin(), take.end());
+                handles.clear();
+                for (int b : take) handles.push_back(chains[b]->chain);
+                Flight f;
+                f.members = take;
+                abi_check(scicone_batch_submit(handles.data(), nullptr, static_cast<int32_t>(handles.size()), &f.ticket));
+                flights.push_back(std::move(f));
+                ++n_launches;
+                n_launched_chains += take.size();
+                continue;
+            }
+            if (!flights.empty()) {
+                int32_t done = 0;
+                abi_check(scicone_batch_poll(ds, flights.front().ticket, &done));
+                if (done || flights.size() >= 2) {
+                    collect(flights.front());
+                    flights.pop_front();
+                }
+            }
+        }
+    } catch (...) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!err) err = std::current_exception();
+    }
+    stop.store(true, std::memory_order_release);
+    for (std::thread& t : pool) t.join();
+    if (times) {
+        times->launches = n_launches;
+        times->launched_chains = n_launched_chains;
+    }
+    if (err) std::rethrow_exception(err);
 }
 
 }  // namespace scicone_host
