@@ -36,7 +36,10 @@ constexpr int kCells = 128;         // cells per CTA of the proposal kernel: one
 constexpr int kThreads = kCells;
 constexpr int kMinCtasPerSm = 12;   // register budget of the proposal kernel: 65536 / (10 * 128) = 51 -> 48 registers
 constexpr int kTaskChunk = 32;      // task records staged in shared memory at a time
-constexpr int kEvStage = 96;        // event records staged with them (the rest is read from global memory)
+constexpr int kEvStage = 64;        // event records staged with them (the rest is read from global memory)
+constexpr int kDepth = 4;           // nodes whose gathers are in flight per thread (cp.async ring stages)
+constexpr int kSlots = 6;           // gathers per node and stage: L rows of two events (node, parent side), two z-term rows
+constexpr int kScRing = 4;          // most recent node scores a thread keeps in registers (parent lookups)
 constexpr int kMaxOdSlices = 32;    // region slices of a root score
 constexpr int kCtasPerChunk = 8;    // 8 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
 constexpr int kBuildBlock = 256;    // threads per CTA of the build kernel
@@ -45,9 +48,9 @@ constexpr int kPad = 256;           // row padding (cells)
 
 enum : unsigned {
     TASK_ROOT = 1u,      // tree root: score 0 (Tree::compute_root_score, Tree.h:145-160)
-    TASK_REUSE_G = 2u,   // lgamma(S + nu*z_parent) equals the parent task's lgamma(S + nu*z) in this chunk
     TASK_SKIP_AGG = 4u,  // a later task rewrites the same node: only that one enters the aggregate
-    TASK_CHAINED = 8u,   // the parent is the task right before this one: its score (and z-term) are still in registers
+    TASK_PS_FAR = 8u,    // parent score from global memory, read one node ahead: the committed row of a subtree root's parent,
+                         // or the row this thread wrote more than kScRing nodes ago
     TASK_BIG = 16u,      // more events than the staging buffer holds: read from global memory
     PROP_MAX = 1u,       // max scoring (Inference::max_scoring)
     PROP_OD = 2u,        // overdispersed likelihood (globals is_overdispersed)
@@ -62,23 +65,17 @@ enum : unsigned {
 
 struct alignas(16) DevTask {
     double* dst;                 // score row being written
-    const double* prefetch_row;  // parent score row of the NEXT task when that task is neither chained nor the root, else null
+    const double* parent_row;    // TASK_PS_FAR: where the parent's score lives in global memory
     double lg_nz, lg_nzp;        // OD: lgamma(nu*z), lgamma(nu*z_parent);  non-OD: log(z), log(z_parent)
-    union {
-        struct {
-            double nz, nzp;          // host side while compiling (and non-OD): nu*z, nu*z_parent
-        };
-        struct {                     // OD, on the device: the z-terms are rows built by K1 and only gathered in the walk
-            const double* g_row;     // lgamma(S + nu*z)
-            const double* gp_row;    // lgamma(S + nu*z_parent); unused when TASK_REUSE_G
-        };
-    };
+    const double* g_row;         // OD: z-term row lgamma(S + nu*z) built by K1
+    const double* gp_row;        // OD: z-term row lgamma(S + nu*z_parent) (the parent task's g_row when the arguments are equal)
     int ev_begin;                // first event record (index into the proposal's event array)
     int node_id;
     unsigned short n_ev;         // number of event records (Node::c_change entries)
     unsigned short ev_rel;       // first event record relative to the chunk's staged events
     unsigned char flags;
-    unsigned char pad[3];
+    unsigned char parent_back;   // 1..kScRing: the parent is the task this many positions back (score still in registers)
+    unsigned char pad[2];
 };
 static_assert(sizeof(DevTask) == 64, "DevTask is staged as four 16-byte pieces");
 
@@ -127,7 +124,7 @@ struct alignas(16) DevHeader {
     unsigned* status;     // bit 0: NaN aggregate
     double od_lg_nz, od_nz;  // OD: lgamma(nu*z_root), nu*z_root;  non-OD: od_lg_nz = log(sum_r)
     unsigned off_tasks, off_events, off_old, off_unch, off_od_rows, off_chunks;
-    const double* first_parent_row;  // parent score row of task 0 (null for a root)
+    const double* pad4;
     const double* od_g_row;          // PROP_WITH_OD, OD: row lgamma(S + nu*z_root) built by K1
 };
 
@@ -343,11 +340,22 @@ __global__ void __launch_bounds__(kBuildBlock, 4)
 __device__ __forceinline__ void copy16(void* dst, const void* src) {
     *reinterpret_cast<int4*>(dst) = __ldg(reinterpret_cast<const int4*>(src));
 }
+// 8-byte asynchronous copy global -> this thread's own shared-memory slot (LDGSTS): no register is tied up while the
+// load is in flight, so a thread keeps kDepth nodes x kSlots gathers outstanding
+__device__ __forceinline__ void cp8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
 
 template <bool kMax, bool kOd, int kOcc>
 __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const unsigned char* __restrict__ arena) {
     __shared__ __align__(16) DevTask sm_task[kTaskChunk];
     __shared__ __align__(16) DevEvent sm_ev[kEvStage];
+    __shared__ double ring[kDepth * kSlots][kThreads];  // [stage * kSlots + slot][thread]: every thread owns one column
     __shared__ double red_buf[kThreads / 32];
 
     const LaunchEntry le = reinterpret_cast<const LaunchEntry*>(arena)[blockIdx.y];
@@ -359,7 +367,8 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
     for (int q = threadIdx.x; q < (int)le.n_ev0 * 2; q += kThreads)
         copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, blob + le.ev_off0 + 16 * q);
 
-    const int j = blockIdx.x * kCells + threadIdx.x;
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x * kCells + tid;
     const bool live = j < H.n_cells;
     const unsigned pflags = H.flags;
     constexpr bool od = kOd;
@@ -374,11 +383,9 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
     const int pm = (kMax && incremental) ? H.maxid_old[j] : -1;
     const double agg_old = incremental ? H.sums_old[j] : 0.0;  // fetched now, needed in phase C
 
-    double sc_prev = 0.0, g_prev = 0.0;  // score and lgamma(S + nu z) of the node visited just before
-    double ps_next = 0.0;                // prefetched parent score of the next node
-    if (live && H.first_parent_row) ps_next = __ldcg(H.first_parent_row + j);
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;  // scores of the last kScRing nodes of the walk (s1 = the node just before)
+    static_assert(kScRing == 4, "the register ring is written out for four entries");
     const DevChunk* chunks = reinterpret_cast<const DevChunk*>(blob + H.off_chunks);
-
     const int n_chunks = H.n_chunks;
     __syncthreads();  // first chunk staged
     for (int c = 0; c < n_chunks; ++c) {
@@ -401,30 +408,48 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             __syncthreads();
         }
         if (!live) continue;
-        // the first two delta-row gathers of a node are issued while the node before it is being scored
-        double dn0 = 0.0, dn1 = 0.0, gn = 0.0, gpn = 0.0;
-        auto prefetch_gathers = [&](const DevTask& nx) {
-            dn0 = dn1 = 0.0;
-            if (od) {  // z-terms: rows built by K1
-                gn = __ldg(nx.g_row + j);
-                if (!(nx.flags & (TASK_ROOT | TASK_REUSE_G))) gpn = __ldg(nx.gp_row + j);
-            }
-            if (nx.flags & (TASK_ROOT | TASK_BIG)) return;
-            const DevEvent* ev = sm_ev + nx.ev_rel;
-            if (nx.n_ev > 0) {  // first event: node row and (OD) parent row
-                dn0 = __ldg(ev[0].row + j);
-                if (od) dn1 = __ldg(ev[0].row_p + j);
-            }
-        };
-        prefetch_gathers(sm_task[0]);
-        for (int t = 0; t < ck.n_tasks; ++t) {
+        const int nt = ck.n_tasks;
+        // issue the gathers of staged task t into ring stage t % kDepth (one commit group per task, also when empty)
+        auto issue = [&](int t) {
             const DevTask& tk = sm_task[t];
             const unsigned tf = tk.flags;
-            const double d0 = dn0, d1 = dn1, g_row_val = gn, gp_row_val = gpn;
-            if (t + 1 < ck.n_tasks) prefetch_gathers(sm_task[t + 1]);
-            const double ps = (tf & TASK_CHAINED) ? sc_prev : ps_next;
-            // parent score of the NEXT node: its row was written by this thread at least one node ago (or is committed)
-            if (tk.prefetch_row) ps_next = __ldcg(tk.prefetch_row + j);
+            double* col = &ring[(t % kDepth) * kSlots][tid];
+            if (!(tf & TASK_ROOT)) {
+                if (!(tf & TASK_BIG)) {
+                    const DevEvent* ev = sm_ev + tk.ev_rel;
+                    const int ne = tk.n_ev;
+                    if (ne > 0) {
+                        cp8(col + 0 * kThreads, ev[0].row + j);
+                        if (od) cp8(col + 1 * kThreads, ev[0].row_p + j);
+                    }
+                    if (ne > 1) {
+                        cp8(col + 2 * kThreads, ev[1].row + j);
+                        if (od) cp8(col + 3 * kThreads, ev[1].row_p + j);
+                    }
+                }
+                if (od) {
+                    cp8(col + 4 * kThreads, tk.g_row + j);
+                    cp8(col + 5 * kThreads, tk.gp_row + j);
+                }
+            }
+            cp_commit();
+        };
+#pragma unroll
+        for (int q = 0; q < kDepth; ++q) {
+            if (q < nt)
+                issue(q);
+            else
+                cp_commit();
+        }
+        double ps_far = 0.0;  // parent score that is not in the register ring: plain load, one node ahead
+        if (sm_task[0].flags & TASK_PS_FAR) ps_far = __ldcg(sm_task[0].parent_row + j);
+        for (int t = 0; t < nt; ++t) {
+            const DevTask& tk = sm_task[t];
+            const unsigned tf = tk.flags;
+            const double ps_far_cur = ps_far;
+            if (t + 1 < nt && (sm_task[t + 1].flags & TASK_PS_FAR)) ps_far = __ldcg(sm_task[t + 1].parent_row + j);
+            cp_wait<kDepth - 1>();  // this node's gathers have landed (groups complete in order)
+            const double* col = &ring[(t % kDepth) * kSlots][tid];
             double sc = 0.0;
             // ---- increment  score(node) - score(parent)   (Tree::compute_score, Tree.h:177-238)
             if (!(tf & TASK_ROOT)) {
@@ -432,51 +457,51 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                 const int ne = tk.n_ev;
                 const bool big = tf & TASK_BIG;  // more events than the staging buffer holds (rare): read from global memory
                 const DevEvent* ev = big ? reinterpret_cast<const DevEvent*>(blob + H.off_events) + tk.ev_begin : sm_ev + tk.ev_rel;
-                // event 0 was gathered one node ago, events 1 and 2 go out now ...
-                double dq[3], dp[3];
-                dq[0] = big ? (ne > 0 ? __ldg(ev[0].row + j) : 0.0) : d0;
-                dp[0] = (big && od) ? (ne > 0 ? __ldg(ev[0].row_p + j) : 0.0) : d1;
-#pragma unroll
-                for (int q = 1; q < 3; ++q) {
-                    dq[q] = (q < ne) ? __ldg(ev[q].row + j) : 0.0;
-                    dp[q] = (od && q < ne) ? __ldg(ev[q].row_p + j) : 0.0;
-                }
-                double g = 0.0, gp = 0.0;  // z-terms lgamma(S + nu z), lgamma(S + nu z_parent): gathered from K1's rows
-                if (od) {
-                    g = g_row_val;
-                    gp = (tf & TASK_REUSE_G) ? g_prev : gp_row_val;
-                    g_prev = g;
-                }
-                if (od) {  // ... and they are added in event order (Tree.h:214-218)
-#pragma unroll
-                    for (int q = 0; q < 3; ++q)
-                        if (q < ne) {
-                            x += dq[q] - dp[q];
-                            x -= ev[q].a;
-                            x += ev[q].b;
+                if (od) {  // added in event order (Tree.h:214-218): lgamma rows of the node's and the parent's copy number
+                    if (!big) {
+                        if (ne > 0) {
+                            x += col[0 * kThreads] - col[1 * kThreads];
+                            x -= ev[0].a;
+                            x += ev[0].b;
                         }
-                    for (int q = 3; q < ne; ++q) {
+                        if (ne > 1) {
+                            x += col[2 * kThreads] - col[3 * kThreads];
+                            x -= ev[1].a;
+                            x += ev[1].b;
+                        }
+                    }
+                    for (int q = big ? 0 : 2; q < ne; ++q) {
                         x += __ldg(ev[q].row + j) - __ldg(ev[q].row_p + j);
                         x -= ev[q].a;
                         x += ev[q].b;
                     }
                     x += tk.lg_nz;
                     x -= tk.lg_nzp;
-                    x -= g;
-                    x += gp;
+                    x -= col[4 * kThreads];  // lgamma(S + nu z)
+                    x += col[5 * kThreads];  // lgamma(S + nu z_parent)
                 } else {  // Tree.h:221,236-237
-#pragma unroll
-                    for (int q = 0; q < 3; ++q)
-                        if (q < ne) x += dq[q] * ev[q].a;
-                    for (int q = 3; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
+                    if (!big) {
+                        if (ne > 0) x += col[0 * kThreads] * ev[0].a;
+                        if (ne > 1) x += col[2 * kThreads] * ev[1].a;
+                    }
+                    for (int q = big ? 0 : 2; q < ne; ++q) x += __ldg(ev[q].row + j) * ev[q].a;
                     x -= S * tk.lg_nz;
                     x += S * tk.lg_nzp;
                 }
+                const int back = tk.parent_back;
+                const double ps = back == 1 ? s1 : back == 2 ? s2 : back == 3 ? s3 : back == 4 ? s4 : ps_far_cur;
                 sc = ps + x;
-            } else if (od)
-                g_prev = g_row_val;
-            sc_prev = sc;
+            }
+            s4 = s3;
+            s3 = s2;
+            s2 = s1;
+            s1 = sc;
             tk.dst[j] = sc;
+            // refill this stage with the node kDepth positions ahead
+            if (t + kDepth < nt)
+                issue(t + kDepth);
+            else
+                cp_commit();
             if (tf & TASK_SKIP_AGG) continue;
             const int id = tk.node_id;
             if (kMax && id == pm) prev_in_new = true;
@@ -493,6 +518,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                     new_sumexp += exp(sc - new_max);
             }
         }
+        cp_wait<0>();
     }
 
     double contrib = 0.0, contrib_od = 0.0;
@@ -505,35 +531,22 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             int prev_id = pm;
             double prev_val = agg_old;
             if (prev_in_new || pm == H.deleted_id) {
-                // the previous argmax was rescored or deleted: first maximum of the unchanged rows in ascending id order
-                // two batches of four loads are kept in flight: the next batch is issued before the current one is compared
+                // the previous argmax was rescored or deleted: first maximum of the unchanged rows in ascending id order.
+                // The rows are fetched through the thread's ring, kDepth * kSlots of them in flight.
+                constexpr int kBatch = kDepth * kSlots;
                 double cur = -DBL_MAX;
                 int uid = 0;
-                const int n4 = n_unch & ~3;
-                double v[4], w[4];
-                if (n4 > 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = __ldcg(unch[q].row + j);
-                }
-                for (int u = 0; u < n4; u += 4) {
-                    if (u + 4 < n4) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) w[q] = __ldcg(unch[u + 4 + q].row + j);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (v[q] > cur) {
-                            cur = v[q];
-                            uid = unch[u + q].id;
+                for (int u0 = 0; u0 < n_unch; u0 += kBatch) {
+                    const int nb = min(kBatch, n_unch - u0);
+                    for (int q = 0; q < nb; ++q) cp8(&ring[q][tid], unch[u0 + q].row + j);
+                    cp_commit();
+                    cp_wait<0>();
+                    for (int q = 0; q < nb; ++q) {
+                        const double v = ring[q][tid];
+                        if (v > cur) {
+                            cur = v;
+                            uid = unch[u0 + q].id;
                         }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = w[q];
-                }
-                for (int u = n4; u < n_unch; ++u) {
-                    const double x = __ldcg(unch[u].row + j);
-                    if (x > cur) {
-                        cur = x;
-                        uid = unch[u].id;
                     }
                 }
                 prev_id = uid;
@@ -596,15 +609,14 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             v -= __ldcg(H.od_g_row + j);
         } else
             v += -S * H.od_lg_nz;
-        int s = 0;
-        for (; s + 4 <= ns; s += 4) {
-            double q[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q[i] = __ldcg(slices[s + i] + j);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v += q[i];
+        constexpr int kBatch = kDepth * kSlots;
+        for (int s0 = 0; s0 < ns; s0 += kBatch) {
+            const int nb = min(kBatch, ns - s0);
+            for (int q = 0; q < nb; ++q) cp8(&ring[q][tid], slices[s0 + q] + j);
+            cp_commit();
+            cp_wait<0>();
+            for (int q = 0; q < nb; ++q) v += ring[q][tid];
         }
-        for (; s < ns; ++s) v += __ldcg(slices[s] + j);
         contrib_od = v * (double)H.w[j];
     }
     // ---- weighted sum over cells: Inference::comparison, Inference.h:292-294 ----

@@ -319,10 +319,11 @@ struct scicone_dataset {
     }
     int ensure_arena(size_t bytes) {
         if (bytes <= arena_cap) return SCICONE_OK;
-        size_t cap = std::max<size_t>(bytes * 2, size_t(1) << 16);
+        size_t cap = std::max<size_t>(bytes * 2, size_t(1) << 20);
+        // every queued launch has finished after the synchronize; the totals of tickets that were not collected yet sit in
+        // their own pinned buffers (h_total), which are not touched here
         CUDA_TRY(cudaStreamSynchronize(stream));
         for (Segment& g : seg) {
-            if (g.busy) return fail(SCICONE_ERR_STATE, "staging arena must grow while launches are outstanding");
             if (g.h_arena) cudaFreeHost(g.h_arena);
             g.h_arena = nullptr;
         }
@@ -378,7 +379,7 @@ struct scicone_dataset {
 };
 
 constexpr size_t kStashRefill = 32, kStashMax = 160;
-constexpr int kDefaultOcc = 8;
+constexpr int kDefaultOcc = 7;
 
 struct scicone_chain {
     scicone_dataset* ds = nullptr;
@@ -416,6 +417,8 @@ struct scicone_chain {
         std::vector<DevTask> tasks;
         std::vector<DevEvent> events;
         std::vector<const double*> prow, old_rows, g_of_task;
+        std::vector<double> nz, nzp;
+        std::vector<char> shares;
         std::vector<DevUnch> unch;
         std::vector<DevChunk> chunks;
     } scratch;
@@ -596,12 +599,17 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     std::vector<DevEvent>& events = W.events;
     std::vector<const double*>& prow = W.prow;  // per task: where its parent's score lives
     std::vector<int>& ptask = W.ptask;          // per task: task index of the parent, -1 when the parent is not rescored before
+    std::vector<double>&tnz = W.nz, &tnzp = W.nzp;  // per task: nu*z, nu*z_parent (arguments of the z-terms)
+    std::vector<char>& shares = W.shares;       // per task: nu*z_parent is bit-equal to the parent task's nu*z
     std::vector<int>& task_of_node = W.task_of_node;
     std::vector<int>& stack = W.stack;
     tasks.clear();
     events.clear();
     prow.clear();
     ptask.clear();
+    tnz.clear();
+    tnzp.clear();
+    shares.clear();
     stack.clear();
     task_of_node.assign(T.n, -1);
     for (size_t ri = 0; ri < ch->roots.size(); ++ri) {
@@ -618,12 +626,14 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             tk.node_id = id;
             int parent_task = -1;
             const double* parent_row = nullptr;
+            double nz_v = 0.0, nzp_v = 0.0;
+            bool share_v = false;
             tk.ev_begin = (int)events.size();
             int z_int;
             if (pidx < 0) {  // Tree::compute_root_score, Tree.h:145-160
                 tk.flags = TASK_ROOT;
                 z_int = ds->root_z;
-                tk.nz = nu * (double)z_int;
+                nz_v = nu * (double)z_int;
             } else {
                 const int pid = T.id[pidx];
                 int pz;
@@ -698,12 +708,11 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                 if (events.size() - (size_t)tk.ev_begin > 65535) return fail(SCICONE_ERR_ARG, "more than 65535 events in one node");
                 tk.n_ev = (unsigned short)(events.size() - (size_t)tk.ev_begin);
                 if (od) {  // Tree.h:227-231
-                    tk.nz = nu * zd;
-                    tk.nzp = nu * zp;
-                    tk.lg_nz = lgamma(tk.nz);
-                    tk.lg_nzp = lgamma(tk.nzp);
-                    if (parent_task >= 0 && memcmp(&tasks[parent_task].nz, &tk.nzp, sizeof(double)) == 0)
-                        tk.flags |= TASK_REUSE_G;
+                    nz_v = nu * zd;
+                    nzp_v = nu * zp;
+                    tk.lg_nz = lgamma(nz_v);
+                    tk.lg_nzp = lgamma(nzp_v);
+                    share_v = parent_task >= 0 && memcmp(&tnz[parent_task], &nzp_v, sizeof(double)) == 0;
                 } else {  // Tree.h:236-237
                     tk.lg_nz = log(zd);
                     tk.lg_nzp = log(zp);
@@ -722,6 +731,9 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             tasks.push_back(tk);
             prow.push_back(parent_row);
             ptask.push_back(parent_task);
+            tnz.push_back(nz_v);
+            tnzp.push_back(nzp_v);
+            shares.push_back(share_v ? 1 : 0);
             for (int c = child_off[n + 1] - 1; c >= child_off[n]; --c) stack.push_back(child[c]);
         }
     }
@@ -733,15 +745,14 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         for (size_t i = 0; i < tasks.size(); ++i)
             if (last[tasks[i].node_id] != (int)i) tasks[i].flags |= TASK_SKIP_AGG;
     }
-    // Walk order bookkeeping for the one-thread-per-cell kernel: a node whose parent was visited just before takes the
-    // parent's score (and, with TASK_REUSE_G, its z-term) from registers; any other parent score is prefetched while
-    // the previous node is processed.  Chunks: what is staged in shared memory together.
+    // Walk bookkeeping for the one-thread-per-cell kernel.  z-terms lgamma(S + nu z) are not evaluated in the serial walk:
+    // K1 builds them as rows (every (node, cell) pair is independent) and the walk gathers them, so the proposal kernel
+    // carries no lgamma at all.  Parent scores: a parent visited at most kScRing nodes ago is read from the thread's
+    // shared-memory ring; the committed row of a subtree root's parent is prefetched with the other gathers; a parent
+    // rescored further back is read from the row this thread wrote (plain load, one node ahead).
     std::vector<DevChunk>& chunks = W.chunks;
     chunks.clear();
-    // The z-terms lgamma(S + nu z) are not evaluated in the serial walk: K1 builds them as rows, where every (node, cell)
-    // pair is independent; the walk only gathers and adds (and the proposal kernel carries no lgamma code at all).
-    const bool g_rows = od;
-    if (g_rows) {
+    if (od) {
         auto build_g = [&](double arg, const double** out) -> int {
             double* row = nullptr;
             CUDA_TRY(ch->row_get(&row));
@@ -760,17 +771,15 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         };
         W.g_of_task.assign(tasks.size(), nullptr);
         for (size_t i = 0; i < tasks.size(); ++i) {
-            const double nz = tasks[i].nz, nzp = tasks[i].nzp;
-            const bool shares_parent = (tasks[i].flags & TASK_REUSE_G) != 0;  // nu*z_parent is bit-equal to the parent task's nu*z
             const double* g = nullptr;
             const double* gp = nullptr;
-            int rc = build_g(nz, &g);
+            int rc = build_g(tnz[i], &g);
             if (rc) return rc;
             W.g_of_task[i] = g;
             if (!(tasks[i].flags & TASK_ROOT)) {
-                if (shares_parent)
+                if (shares[i])
                     gp = W.g_of_task[ptask[i]];
-                else if ((rc = build_g(nzp, &gp)))
+                else if ((rc = build_g(tnzp[i], &gp)))
                     return rc;
             }
             tasks[i].g_row = g;
@@ -778,9 +787,15 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         }
     }
     for (size_t i = 0; i < tasks.size(); ++i) {
-        if (ptask[i] >= 0 && ptask[i] == (int)i - 1) tasks[i].flags |= TASK_CHAINED;
-        else tasks[i].flags &= (unsigned char)~TASK_REUSE_G;  // the previous node's z-term is only at hand when chained
-        if (i + 1 < tasks.size() && !(tasks[i + 1].flags & TASK_ROOT) && ptask[i + 1] != (int)i) tasks[i].prefetch_row = prow[i + 1];
+        if (!(tasks[i].flags & TASK_ROOT)) {
+            const int back = ptask[i] >= 0 ? (int)i - ptask[i] : 0;
+            if (back >= 1 && back <= kScRing)
+                tasks[i].parent_back = (unsigned char)back;
+            else {
+                tasks[i].parent_row = prow[i];
+                tasks[i].flags |= TASK_PS_FAR;
+            }
+        }
         if (tasks[i].n_ev > kEvStage) tasks[i].flags |= TASK_BIG;
         const int staged = (tasks[i].flags & TASK_BIG) ? 0 : tasks[i].n_ev;
         if (chunks.empty() || chunks.back().n_tasks >= kTaskChunk || chunks.back().n_ev + staged > kEvStage) {
@@ -829,7 +844,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     memset(&H, 0, sizeof H);
     H.n_tasks = (int)tasks.size();
     H.n_chunks = (int)chunks.size();
-    H.first_parent_row = (!tasks.empty() && !(tasks[0].flags & TASK_ROOT)) ? prow[0] : nullptr;
     H.n_old = (int)old_rows.size();
     H.n_unch = (int)unch.size();
     H.deleted_id = ch->deleted_id;
@@ -967,11 +981,11 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     g.n_items = (int)n_items;
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, ds->stream));
     {   // scoring mode and likelihood are properties of the dataset: one specialisation per launch.  kOcc = CTAs per SM the
-        // register allocation aims at (8 -> 64 registers, 10 -> 48, 12 -> 40); SCICONE_OCC overrides the default for tuning.
+        // register allocation aims at (shared memory - the cp.async ring - allows 7); SCICONE_OCC overrides the default for tuning.
         static const int occ = [] {
             const char* e = getenv("SCICONE_OCC");
             const int v = e ? atoi(e) : 0;
-            return (v == 8 || v == 10 || v == 12) ? v : kDefaultOcc;
+            return (v == 5 || v == 6 || v == 7) ? v : kDefaultOcc;
         }();
         const dim3 grid(ds->n_cta, n);
 #define SCICONE_LAUNCH(OCC)                                                                                                \
@@ -981,9 +995,9 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         else if (ds->od) score_proposals_kernel<false, true, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);          \
         else score_proposals_kernel<false, false, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);                     \
     } while (0)
-        if (occ == 12) SCICONE_LAUNCH(12);
-        else if (occ == 10) SCICONE_LAUNCH(10);
-        else SCICONE_LAUNCH(8);
+        if (occ == 5) SCICONE_LAUNCH(5);
+        else if (occ == 6) SCICONE_LAUNCH(6);
+        else SCICONE_LAUNCH(7);
 #undef SCICONE_LAUNCH
     }
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, ds->stream));
@@ -1204,9 +1218,9 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
         DS_TRY(cudaGetLastError());
     }
 #undef DS_TRY
-    int rc = ds->ensure_slots(4);
+    int rc = ds->ensure_slots(64);
     if (rc) return cleanup(rc);
-    rc = ds->ensure_arena(size_t(1) << 16);
+    rc = ds->ensure_arena(size_t(1) << 20);
     if (rc) return cleanup(rc);
     *out = ds;
     return SCICONE_OK;

@@ -5,7 +5,7 @@ TAG=${1:-tune}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 ARGS="--steps 100 --warmup 10 --no_cpu_baseline --no_e2e"
-for occ in 8 10 12; do
+for occ in 5 6 7; do
   SCICONE_OCC=$occ python bench.py $ARGS > "$OUT/occ$occ.json" 2> "$OUT/occ$occ.err"
   python - "$OUT/occ$occ.json" $occ <<'PY'
 import json,sys
