@@ -41,6 +41,15 @@ sys.path.insert(0, ROOT)
 L2_BYTES = 126e6
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        t = json.load(open(p))
+        return t.get("dram_bytes_per_launch"), t.get("source")
+    return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -222,6 +231,7 @@ def run_engine(args):
 
     if rank == 0:
         peak, peak_src = load_peaks()
+        traffic, traffic_src = load_traffic()
         cells_total = world * M
         iters = B * K
         value = iters * cells_total / (dev_ms * 1e-3)
@@ -253,7 +263,7 @@ def run_engine(args):
                     "score_kernel_us_per_step": host["score_kernel_us"] / K, "build_kernel_us_per_step": host["build_kernel_us"] / K},
             "gpu_launches": int(launches_dev),
             "roofline": {"bound": "hbm", "kernel": "score_proposals_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "alg_bytes_per_launch": cnt_dev["alg_bytes"] / max(1, n_timed),
                          "avg_launch_us": kern_us / max(1, n_timed), "kernel_share_of_step": kern_us * 1e-3 / dev_ms},
             "clocks": clocks,

@@ -28,7 +28,7 @@ echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
 # the batched proposal launches come after the 2 x chains single-chain set-up launches: skip those
 ncu --set full --clock-control none --import-source on -k regex:score_proposals -s 70 -c 3 -o "$OUT/prof" python bench.py $SHORT > "$OUT/ncu_full.log" 2>&1
 echo "ncu full rc=$?" | tee -a "$OUT/summary.txt"
-ncu --set full --clock-control none --import-source on -k regex:build_rows -s 40 -c 4 -o "$OUT/prof_build" python bench.py $SHORT > "$OUT/ncu_build.log" 2>&1
+ncu --set full --clock-control none --import-source on -k regex:build_rows -s 36 -c 4 -o "$OUT/prof_build" python bench.py $SHORT > "$OUT/ncu_build.log" 2>&1
 echo "ncu build rc=$?" | tee -a "$OUT/summary.txt"
 fi
 ls -la "$OUT"
