@@ -311,6 +311,8 @@ def run_native_host(args, data, rank, world, local, dist, comm_unique_id):
                f"--n_iters={args.steps}", f"--warmup_iters={args.warmup}", f"--n_nodes={args.nodes - 1}", "--seed=42", f"--nu={args.nu}",
                "--verbosity=0", f"--max_scoring={'true' if args.max_scoring else 'false'}", f"--postfix=e2e{rank}",
                f"--n_chains={args.chains}", f"--device={local}", f"--stats_file={stats}", "--stats_all_ranks=1"]
+        if args.n_groups:
+            cmd.append(f"--n_groups={args.n_groups}")
         if world > 1:
             cmd += [f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"]
         env = dict(os.environ)
@@ -454,6 +456,7 @@ def main():
     ap.add_argument("--ref_iters_per_step", type=int, default=1)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true", help="skip the native-host run (profiling passes only)")
+    ap.add_argument("--n_groups", type=int, default=0, help="chain groups of the native host's static schedule (cell-sharded runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

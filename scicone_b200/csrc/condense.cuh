@@ -4,7 +4,7 @@
 //
 // The only multi-GB stream of the pipeline (10 000 x 18 000 doubles = 1.44 GB, 100 000 x 20 000 = 16 GB): HBM bound,
 // algorithmic traffic 8 * n_bins read + 8 * n_regions written per row.  One persistent CTA per SM walks groups of
-// kRows rows; a row group is cut into tiles of kTile bins which the TMA unit copies into a two-stage shared-memory ring
+// kK0Rows rows; a row group is cut into tiles of kK0Tile bins which the TMA unit copies into a two-stage shared-memory ring
 // (cp.async.bulk + mbarrier transaction counts, one elected thread issues), so the next tile streams in while the
 // current one is reduced.  A thread owns one (row, region) piece of a tile and adds its bins sequentially; the region
 // that straddles a tile boundary hands its partial sum to the next tile through a per-row carry.
@@ -14,8 +14,8 @@
 
 namespace scicone {
 
-constexpr int kK0Rows = 8;       // rows per group
-constexpr int kK0Tile = 1024;    // bins per tile and row
+constexpr int kK0Rows = 16;      // rows per group
+constexpr int kK0Tile = 512;     // bins per tile and row
 constexpr int kK0Threads = 256;
 constexpr int kK0Stride = kK0Tile + 2;  // doubles per row in a stage: one leading element of slack for 16-byte alignment
 constexpr size_t kK0SmemBytes = sizeof(double) * 2 * kK0Rows * kK0Stride + 2 * sizeof(double) * 2 * kK0Rows + 64;
@@ -108,7 +108,17 @@ __global__ void __launch_bounds__(kK0Threads, 1)
                 const double* src = stage_buf + ((size_t)s * kK0Rows + row) * kK0Stride + (first & 1) - lo;
                 double acc = s_r < lo ? carry[(t & 1) * kK0Rows + row] : 0.0;
                 const long long b1 = min(e_r, hi);
-                for (long long b = max(s_r, lo); b < b1; ++b) acc += src[b];  // bin order, as the reference adds them
+                // bin order, as the reference adds them: the additions form one dependent chain, the shared-memory
+                // loads feeding it are independent and are issued eight at a time
+                long long b = max(s_r, lo);
+                for (; b + 8 <= b1; b += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = src[b + q];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc += v[q];
+                }
+                for (; b < b1; ++b) acc += src[b];
                 if (e_r > hi)
                     carry[((t + 1) & 1) * kK0Rows + row] = acc;
                 else

@@ -560,6 +560,8 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             }
             H.maxid_new[j] = rid;
         } else {  // MathOp::log_replace_sum, MathOp.cpp:307-361
+            // rows are fetched through the thread's ring, kBatch at a time; maxima and sums run over them in list order
+            constexpr int kBatch = kDepth * kSlots;
             bool scratch = (pflags & (PROP_SCRATCH | PROP_FULL)) != 0;
             double sub = 0.0;
             if (!scratch) {  // incremental branch: take the old values out of the old sum
@@ -567,13 +569,27 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
                 const double sum_old = agg_old;
                 const int n_old = H.n_old;
                 double mx = sum_old;
-                for (int o = 0; o < n_old; ++o) {
-                    const double v = __ldcg(old_rows[o] + j);
-                    if (v > mx) mx = v;
+                for (int o0 = 0; o0 < n_old; o0 += kBatch) {
+                    const int nb = min(kBatch, n_old - o0);
+                    for (int q = 0; q < nb; ++q) cp8(&ring[q][tid], old_rows[o0 + q] + j);
+                    cp_commit();
+                    cp_wait<0>();
+                    for (int q = 0; q < nb; ++q) {
+                        const double v = ring[q][tid];
+                        if (v > mx) mx = v;
+                    }
                 }
                 double s = 0.0;
                 s += exp(sum_old - mx);
-                for (int o = 0; o < n_old; ++o) s -= exp(__ldcg(old_rows[o] + j) - mx);
+                for (int o0 = 0; o0 < n_old; o0 += kBatch) {
+                    const int nb = min(kBatch, n_old - o0);
+                    if (n_old > kBatch) {  // more rows than the ring holds: fetch this batch again
+                        for (int q = 0; q < nb; ++q) cp8(&ring[q][tid], old_rows[o0 + q] + j);
+                        cp_commit();
+                        cp_wait<0>();
+                    }
+                    for (int q = 0; q < nb; ++q) s -= exp(ring[q][tid] - mx);
+                }
                 if (s <= 1e-6)
                     scratch = true;  // possible precision loss: recompute from every node
                 else
@@ -581,15 +597,29 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             }
             double mx = new_max;
             if (scratch) {
-                for (int u = 0; u < n_unch; ++u) {
-                    const double v = __ldcg(unch[u].row + j);
-                    if (v > mx) mx = v;
+                for (int u0 = 0; u0 < n_unch; u0 += kBatch) {
+                    const int nb = min(kBatch, n_unch - u0);
+                    for (int q = 0; q < nb; ++q) cp8(&ring[q][tid], unch[u0 + q].row + j);
+                    cp_commit();
+                    cp_wait<0>();
+                    for (int q = 0; q < nb; ++q) {
+                        const double v = ring[q][tid];
+                        if (v > mx) mx = v;
+                    }
                 }
             } else if (sub > mx)
                 mx = sub;
             double s = new_sumexp * exp(new_max - mx);
             if (scratch) {
-                for (int u = 0; u < n_unch; ++u) s += exp(__ldcg(unch[u].row + j) - mx);
+                for (int u0 = 0; u0 < n_unch; u0 += kBatch) {
+                    const int nb = min(kBatch, n_unch - u0);
+                    if (n_unch > kBatch) {
+                        for (int q = 0; q < nb; ++q) cp8(&ring[q][tid], unch[u0 + q].row + j);
+                        cp_commit();
+                        cp_wait<0>();
+                    }
+                    for (int q = 0; q < nb; ++q) s += exp(ring[q][tid] - mx);
+                }
             } else
                 s += exp(sub - mx);
             res = log(s) + mx;
