@@ -4,9 +4,9 @@
 //
 // The only multi-GB stream of the pipeline (10 000 x 18 000 doubles = 1.44 GB, 100 000 x 20 000 = 16 GB): HBM bound,
 // algorithmic traffic 8 * n_bins read + 8 * n_regions written per row.  One persistent CTA per SM walks groups of
-// kK0Rows rows; a row group is cut into tiles of kK0Tile bins which the TMA unit copies into a two-stage shared-memory ring
-// (cp.async.bulk + mbarrier transaction counts, one elected thread issues), so the next tile streams in while the
-// current one is reduced.  A thread owns one (row, region) piece of a tile and adds its bins sequentially; the region
+// kK0Rows rows; a row group is cut into tiles of kK0Tile bins which the TMA unit copies into a shared-memory ring
+// (cp.async.bulk + mbarrier transaction counts, one lane per row issues) of three stages, so two tiles stream in while
+// the current one is reduced.  A thread owns one (row, region) piece of a tile and adds its bins sequentially; the region
 // that straddles a tile boundary hands its partial sum to the next tile through a per-row carry.
 #pragma once
 #include <cstdint>
@@ -17,8 +17,10 @@ namespace scicone {
 constexpr int kK0Rows = 16;      // rows per group
 constexpr int kK0Tile = 512;     // bins per tile and row
 constexpr int kK0Threads = 256;
+constexpr int kK0Stages = 3;     // tiles in flight per CTA (ring depth)
 constexpr int kK0Stride = kK0Tile + 2;  // doubles per row in a stage: one leading element of slack for 16-byte alignment
-constexpr size_t kK0SmemBytes = sizeof(double) * 2 * kK0Rows * kK0Stride + 2 * sizeof(double) * 2 * kK0Rows + 64;
+constexpr size_t kK0SmemBytes = sizeof(double) * kK0Stages * kK0Rows * kK0Stride + sizeof(double) * 2 * kK0Rows + 8 * kK0Stages + 64;
+static_assert(kK0Rows == 16, "the issuing lanes reduce their byte counts over 16 lanes");
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -55,77 +57,78 @@ __global__ void __launch_bounds__(kK0Threads, 1)
     condense_rows_kernel(const double* __restrict__ bins, long long n_rows, long long row_stride, long long n_bins, const int* __restrict__ off,
                          const int* __restrict__ tile_first, int K, int n_tiles, double* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* stage_buf = reinterpret_cast<double*>(smem_raw);                                 // [2][kK0Rows][kK0Stride]
-    double* carry = stage_buf + 2 * kK0Rows * kK0Stride;                                     // [2][kK0Rows]
-    uint64_t* full = reinterpret_cast<uint64_t*>(carry + 2 * kK0Rows);                       // [2]
+    double* stage_buf = reinterpret_cast<double*>(smem_raw);                                  // [kK0Stages][kK0Rows][kK0Stride]
+    double* carry = stage_buf + (size_t)kK0Stages * kK0Rows * kK0Stride;                      // [2][kK0Rows]
+    uint64_t* full = reinterpret_cast<uint64_t*>(carry + 2 * kK0Rows);                        // [kK0Stages]
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int s = 0; s < kK0Stages; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
+    // The CTA's work is one flat sequence of (row group, tile) items, so the ring also runs across group boundaries.
     const long long n_groups = (n_rows + kK0Rows - 1) / kK0Rows;
-    unsigned uses[2] = {0u, 0u};  // how often each stage has been filled: parity of its barrier phase
-    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const long long row0 = g * kK0Rows;
+    const long long my_groups = blockIdx.x < n_groups ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_items = my_groups * n_tiles;
+    // item i -> stage i % kK0Stages: thread 0 arms the barrier with the byte count, the first kK0Rows lanes each issue one
+    // row's bulk copy (aligned down to 16 bytes)
+    auto issue = [&](long long i) {
+        if (threadIdx.x >= kK0Rows) return;
+        const int s = (int)(i % kK0Stages);
+        const long long row0 = (blockIdx.x + (i / n_tiles) * gridDim.x) * kK0Rows;
         const int rows = (int)min((long long)kK0Rows, n_rows - row0);
-        // tile t of this group -> stage s: one bulk copy per row, aligned down to 16 bytes
-        auto issue = [&](int t, int s) {
-            const long long lo = (long long)t * kK0Tile;
-            const int width = (int)min((long long)kK0Tile, n_bins - lo);
-            unsigned total = 0;
-            for (int r = 0; r < rows; ++r) {
-                const long long first = (row0 + r) * row_stride + lo;  // element index of the tile's first bin
-                const int lead = (int)(first & 1);
-                total += (unsigned)(((width + lead + 1) & ~1) * sizeof(double));
-            }
-            mbar_expect_tx(&full[s], total);
-            for (int r = 0; r < rows; ++r) {
-                const long long first = (row0 + r) * row_stride + lo;
-                const int lead = (int)(first & 1);
-                const unsigned bytes = (unsigned)(((width + lead + 1) & ~1) * sizeof(double));
-                tma_load_1d(stage_buf + ((size_t)s * kK0Rows + r) * kK0Stride, bins + first - lead, bytes, &full[s]);
-            }
-        };
-        if (threadIdx.x == 0) issue(0, 0);
-        for (int t = 0; t < n_tiles; ++t) {
-            const int s = t & 1;
-            if (threadIdx.x == 0 && t + 1 < n_tiles) issue(t + 1, s ^ 1);  // stage s^1 was released by the barrier below
-            mbar_wait(&full[s], uses[s] & 1u);
-            uses[s]++;
-            const long long lo = (long long)t * kK0Tile;
-            const long long hi = min(lo + kK0Tile, n_bins);
-            const int r_lo = tile_first[t], r_hi = tile_first[t + 1];  // regions r_lo .. r_hi (inclusive) reach into this tile
-            const int n_reg = r_hi - r_lo + 1;
-            for (int item = threadIdx.x; item < n_reg * rows; item += kK0Threads) {
-                const int row = item / n_reg, r = r_lo + item % n_reg;
-                if (r >= K) continue;
-                const long long s_r = off[r], e_r = off[r + 1];
-                if (e_r <= lo || s_r >= hi) continue;
-                const long long first = (row0 + row) * row_stride + lo;
-                const double* src = stage_buf + ((size_t)s * kK0Rows + row) * kK0Stride + (first & 1) - lo;
-                double acc = s_r < lo ? carry[(t & 1) * kK0Rows + row] : 0.0;
-                const long long b1 = min(e_r, hi);
-                // bin order, as the reference adds them: the additions form one dependent chain, the shared-memory
-                // loads feeding it are independent and are issued eight at a time
-                long long b = max(s_r, lo);
-                for (; b + 8 <= b1; b += 8) {
-                    double v[8];
+        const long long lo = (i % n_tiles) * kK0Tile;
+        const int width = (int)min((long long)kK0Tile, n_bins - lo);
+        const int r = threadIdx.x;
+        const long long first = (row0 + r) * row_stride + lo;  // element index of the tile's first bin in this row
+        const int lead = (int)(first & 1);
+        const unsigned bytes = r < rows ? (unsigned)(((width + lead + 1) & ~1) * sizeof(double)) : 0u;
+        unsigned total = bytes;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = src[b + q];
+        for (int o = 8; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffu, total, o);  // kK0Rows = 16 lanes
+        if (r == 0) mbar_expect_tx(&full[s], total);
+        __syncwarp(0xffffu);
+        if (r < rows) tma_load_1d(stage_buf + ((size_t)s * kK0Rows + r) * kK0Stride, bins + first - lead, bytes, &full[s]);
+    };
+    for (long long i = 0; i < kK0Stages - 1 && i < n_items; ++i) issue(i);
+    for (long long i = 0; i < n_items; ++i) {
+        const int s = (int)(i % kK0Stages);
+        if (i + kK0Stages - 1 < n_items) issue(i + kK0Stages - 1);  // its stage was released by the barrier of item i-1
+        mbar_wait(&full[s], (unsigned)((i / kK0Stages) & 1));
+        const int t = (int)(i % n_tiles);
+        const long long row0 = (blockIdx.x + (i / n_tiles) * gridDim.x) * kK0Rows;
+        const int rows = (int)min((long long)kK0Rows, n_rows - row0);
+        const long long lo = (long long)t * kK0Tile;
+        const long long hi = min(lo + kK0Tile, n_bins);
+        const int r_lo = tile_first[t], r_hi = tile_first[t + 1];  // regions r_lo .. r_hi (inclusive) reach into this tile
+        const int n_reg = r_hi - r_lo + 1;
+        for (int item = threadIdx.x; item < n_reg * rows; item += kK0Threads) {
+            const int row = item / n_reg, r = r_lo + item % n_reg;
+            if (r >= K) continue;
+            const long long s_r = off[r], e_r = off[r + 1];
+            if (e_r <= lo || s_r >= hi) continue;
+            const long long first = (row0 + row) * row_stride + lo;
+            const double* src = stage_buf + ((size_t)s * kK0Rows + row) * kK0Stride + (first & 1) - lo;
+            double acc = s_r < lo ? carry[(t & 1) * kK0Rows + row] : 0.0;
+            const long long b1 = min(e_r, hi);
+            // bin order, as the reference adds them: the additions form one dependent chain, the shared-memory
+            // loads feeding it are independent and are issued eight at a time
+            long long b = max(s_r, lo);
+            for (; b + 8 <= b1; b += 8) {
+                double v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) acc += v[q];
-                }
-                for (; b < b1; ++b) acc += src[b];
-                if (e_r > hi)
-                    carry[((t + 1) & 1) * kK0Rows + row] = acc;
-                else
-                    out[(row0 + row) * K + r] = acc;
+                for (int q = 0; q < 8; ++q) v[q] = src[b + q];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc += v[q];
             }
-            __syncthreads();  // everyone is done with stage s (and with this tile's carries) before it is refilled
+            for (; b < b1; ++b) acc += src[b];
+            if (e_r > hi)
+                carry[((t + 1) & 1) * kK0Rows + row] = acc;
+            else
+                out[(row0 + row) * K + r] = acc;
         }
+        __syncthreads();  // everyone is done with stage s (and with this tile's carries) before it is refilled
     }
 }
 

@@ -104,27 +104,7 @@ struct RowPool {
         const size_t row_bytes = Mp * sizeof(double);
         rows_per_slab = std::max<size_t>(8, std::min<size_t>(512, (size_t(64) << 20) / row_bytes));
     }
-    cudaError_t get(double** out) {
-        std::lock_guard<std::mutex> lk(mu);
-        if (free_rows.empty()) {
-            void* p = nullptr;
-            cudaError_t e = cudaSetDevice(device);  // the calling thread may be a pool worker
-            if (e == cudaSuccess) e = cudaMalloc(&p, rows_per_slab * Mp * sizeof(double));
-            if (e != cudaSuccess) return e;
-            slabs.push_back(p);
-            for (size_t i = rows_per_slab; i-- > 0;) free_rows.push_back(static_cast<double*>(p) + i * Mp);
-            n_rows += rows_per_slab;
-        }
-        *out = free_rows.back();
-        free_rows.pop_back();
-        return cudaSuccess;
-    }
-    void put(double* r) {
-        if (!r) return;
-        std::lock_guard<std::mutex> lk(mu);
-        free_rows.push_back(r);
-    }
-    // bulk forms: one lock for a whole batch (the per-chain stashes below use these)
+    // rows move in batches, one lock per batch (the per-chain stashes use these)
     cudaError_t get_many(size_t n, std::vector<double*>& out) {
         std::lock_guard<std::mutex> lk(mu);
         while (free_rows.size() < n) {
