@@ -41,6 +41,25 @@ sys.path.insert(0, ROOT)
 L2_BYTES = 126e6
 
 
+_RESULT_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one), so the real
+    stdout is kept aside for the result and fd 1 points at stderr for everything else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
+
+
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command (profiles/)."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
@@ -269,7 +288,7 @@ def run_engine(args):
             "clocks": clocks,
         }
         out["cpu_baseline"] = cpu_baseline(args, data) if world == 1 and not args.no_cpu_baseline else None
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -415,7 +434,7 @@ def run_reference(args):
     # one "step" = a bounded sample: every process advances its chain by `iters_per_step` iterations
     iters_per_step = max(1, args.ref_iters_per_step)
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "inference")):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/inference was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/inference was not built (needs /root/reference at build time)"})
         return
     for _ in range(min(W, 1)):
         run_reference_inference(args, data, 2, n_procs, 1)
@@ -436,7 +455,7 @@ def run_reference(args):
            "cpu_baseline": {"value": v, "unit": "cell_iters/s", "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": v, "unit": "cell_iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
@@ -458,6 +477,7 @@ def main():
     ap.add_argument("--no_e2e", action="store_true", help="skip the native-host run (profiling passes only)")
     ap.add_argument("--n_groups", type=int, default=0, help="chain groups of the native host's static schedule (cell-sharded runs)")
     args = ap.parse_args()
+    protect_stdout()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

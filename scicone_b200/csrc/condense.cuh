@@ -14,13 +14,14 @@
 
 namespace scicone {
 
-constexpr int kK0Rows = 16;      // rows per group
-constexpr int kK0Tile = 512;     // bins per tile and row
+constexpr int kK0Rows = 32;      // rows per group
+constexpr int kK0Tile = 128;     // bins per tile and row
 constexpr int kK0Threads = 256;
-constexpr int kK0Stages = 3;     // tiles in flight per CTA (ring depth)
+constexpr int kK0Stages = 2;     // tiles in flight per CTA (ring depth)
+constexpr int kK0MaxIndex = 1536;  // region offsets + tile table entries kept in shared memory (else read from global memory)
 constexpr int kK0Stride = kK0Tile + 2;  // doubles per row in a stage: one leading element of slack for 16-byte alignment
-constexpr size_t kK0SmemBytes = sizeof(double) * kK0Stages * kK0Rows * kK0Stride + sizeof(double) * 2 * kK0Rows + 8 * kK0Stages + 64;
-static_assert(kK0Rows == 16, "the issuing lanes reduce their byte counts over 16 lanes");
+constexpr size_t kK0SmemBytes = sizeof(double) * kK0Stages * kK0Rows * kK0Stride + sizeof(double) * 2 * kK0Rows + 8 * kK0Stages + 64 + sizeof(int) * kK0MaxIndex;
+static_assert(kK0Rows == 32, "the issuing lanes (one warp) reduce their byte counts with full-warp shuffles");
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -53,13 +54,22 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
 // bins [n_rows][row_stride] row-major, of which the first n_bins = sum of the region sizes are used (the allocation is
 // padded by 16 bytes), off [K+1] prefix sums of the region sizes,
 // tile_first [n_tiles+1]: first region that reaches into each tile, out [n_rows][K]
-__global__ void __launch_bounds__(kK0Threads, 1)
+__global__ void __launch_bounds__(kK0Threads, 3)
     condense_rows_kernel(const double* __restrict__ bins, long long n_rows, long long row_stride, long long n_bins, const int* __restrict__ off,
                          const int* __restrict__ tile_first, int K, int n_tiles, double* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_buf = reinterpret_cast<double*>(smem_raw);                                  // [kK0Stages][kK0Rows][kK0Stride]
     double* carry = stage_buf + (size_t)kK0Stages * kK0Rows * kK0Stride;                      // [2][kK0Rows]
     uint64_t* full = reinterpret_cast<uint64_t*>(carry + 2 * kK0Rows);                        // [kK0Stages]
+    int* sm_index = reinterpret_cast<int*>(full + kK0Stages + 1);                             // off[K+1], tile_first[n_tiles+1]
+    // region offsets and the tile table are read for every piece of every tile: keep them in shared memory when they fit
+    const bool index_in_smem = (K + 1) + (n_tiles + 1) <= kK0MaxIndex;
+    if (index_in_smem) {
+        for (int q = threadIdx.x; q <= K; q += kK0Threads) sm_index[q] = off[q];
+        for (int q = threadIdx.x; q <= n_tiles; q += kK0Threads) sm_index[K + 1 + q] = tile_first[q];
+    }
+    const int* offs = index_in_smem ? sm_index : off;
+    const int* firsts = index_in_smem ? sm_index + K + 1 : tile_first;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kK0Stages; ++s) mbar_init(&full[s], 1);
@@ -86,9 +96,9 @@ __global__ void __launch_bounds__(kK0Threads, 1)
         const unsigned bytes = r < rows ? (unsigned)(((width + lead + 1) & ~1) * sizeof(double)) : 0u;
         unsigned total = bytes;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffu, total, o);  // kK0Rows = 16 lanes
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
         if (r == 0) mbar_expect_tx(&full[s], total);
-        __syncwarp(0xffffu);
+        __syncwarp();
         if (r < rows) tma_load_1d(stage_buf + ((size_t)s * kK0Rows + r) * kK0Stride, bins + first - lead, bytes, &full[s]);
     };
     for (long long i = 0; i < kK0Stages - 1 && i < n_items; ++i) issue(i);
@@ -101,12 +111,12 @@ __global__ void __launch_bounds__(kK0Threads, 1)
         const int rows = (int)min((long long)kK0Rows, n_rows - row0);
         const long long lo = (long long)t * kK0Tile;
         const long long hi = min(lo + kK0Tile, n_bins);
-        const int r_lo = tile_first[t], r_hi = tile_first[t + 1];  // regions r_lo .. r_hi (inclusive) reach into this tile
+        const int r_lo = firsts[t], r_hi = firsts[t + 1];  // regions r_lo .. r_hi (inclusive) reach into this tile
         const int n_reg = r_hi - r_lo + 1;
         for (int item = threadIdx.x; item < n_reg * rows; item += kK0Threads) {
             const int row = item / n_reg, r = r_lo + item % n_reg;
             if (r >= K) continue;
-            const long long s_r = off[r], e_r = off[r + 1];
+            const long long s_r = offs[r], e_r = offs[r + 1];
             if (e_r <= lo || s_r >= hi) continue;
             const long long first = (row0 + row) * row_stride + lo;
             const double* src = stage_buf + ((size_t)s * kK0Rows + row) * kK0Stride + (first & 1) - lo;

@@ -1639,8 +1639,8 @@ int scicone_condense_matrix(int32_t device, const double* D_bins, int64_t n_cell
         while (off[r + 1] <= (long long)t * kK0Tile) ++r;
         tile_first[t] = r;
     }
-    // rows travel in chunks of at most 512 MB: upload, condense, download
-    const long long chunk_rows = std::max<long long>(kK0Rows, std::min<long long>(n_cells, (512ll << 20) / (n_bins * (long long)sizeof(double))));
+    // rows travel in chunks of at most 2 GB: upload, condense, download
+    const long long chunk_rows = std::max<long long>(kK0Rows, std::min<long long>(n_cells, (2048ll << 20) / (n_bins * (long long)sizeof(double))));
     double *d_bins = nullptr, *d_out = nullptr;
     int *d_off = nullptr, *d_first = nullptr;
     cudaStream_t st = nullptr;
@@ -1665,7 +1665,7 @@ int scicone_condense_matrix(int32_t device, const double* D_bins, int64_t n_cell
         if (e != cudaSuccess) break;
         const long long groups = (rows + kK0Rows - 1) / kK0Rows;
         cudaEventRecord(e0, st);
-        condense_rows_kernel<<<(unsigned)std::min<long long>(groups, n_sm), kK0Threads, kK0SmemBytes, st>>>(
+        condense_rows_kernel<<<(unsigned)std::min<long long>(groups, 3ll * n_sm), kK0Threads, kK0SmemBytes, st>>>(
             d_bins, rows, n_bins, n_used, d_off, d_first, n_regions, n_tiles, d_out);
         cudaEventRecord(e1, st);
         e = cudaGetLastError();
