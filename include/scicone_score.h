@@ -168,6 +168,14 @@ int scicone_batch_compute_t_prime_scores(scicone_chain* const* chains, const sci
                                          const int32_t* node_idx, int32_t n);
 int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, int32_t n);
 
+/*
+ * Launch streams of a dataset (default 1).  With 2, consecutive batch launches alternate between two streams and overlap
+ * on the device.  One stream serialises launches, which is what allows scicone_accept / scicone_reject before
+ * scicone_batch_wait; with two streams a launch must be collected (scicone_batch_wait) before its chains are settled or
+ * queued again, and at most one launch per stream may be outstanding.  Not available on cell-sharded datasets.
+ */
+int scicone_set_streams(scicone_dataset* ds, int32_t n);
+
 /* Non-blocking probe of a ticket: *done = 1 when scicone_batch_wait would return at once. */
 int scicone_batch_poll(scicone_dataset* ds, uint64_t ticket, int32_t* done);
 

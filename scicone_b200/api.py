@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_build_time_stats", "scicone_kernel_launches",
     "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
     "scicone_parallel_for", "scicone_host_threads", "scicone_test_lgamma", "scicone_prepare_t_prime",
-    "scicone_batch_compute_t_prime_scores", "scicone_batch_settle", "scicone_condense_matrix", "scicone_batch_poll",
+    "scicone_batch_compute_t_prime_scores", "scicone_batch_settle", "scicone_condense_matrix", "scicone_batch_poll", "scicone_set_streams",
 ]
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}

@@ -256,18 +256,28 @@ struct scicone_dataset {
         std::vector<char> with_od;
         bool busy = false;
         unsigned long long ticket = 0;
+        int lane = 0;
+        std::vector<double*> temp_rows;  // rows that only live for this launch: back to the pool when it is collected
     };
     static constexpr int kRing = 8;
     Segment seg[kRing];
     unsigned long long next_ticket = 1;
-    unsigned char* d_arena = nullptr;
+    // Launch lanes: lane l has its own stream, device arena and range of reduction slots.  One lane (default): launches
+    // are serialised by the stream, so accept / reject may be issued before the wait.  Two lanes (scicone_set_streams):
+    // consecutive launches alternate lanes and overlap on the device - K1 of one launch fills the issue slots the
+    // proposal kernel of the other leaves idle; the caller must then collect a launch before it settles its chains.
+    static constexpr int kLanes = 2;
+    int n_lanes = 1;
+    cudaStream_t lane_stream[kLanes] = {nullptr, nullptr};
+    unsigned char* d_arena[kLanes] = {nullptr, nullptr};
     size_t arena_cap = 0;
     // per batch slot: reduction scratch and results
     int n_cta = 0, n_chunks = 0;
     int slots = 0;
     double* d_partial = nullptr;  // [slots][2][n_cta]   (0: tree score, 1: root score)
     double* d_chunk = nullptr;    // [slots][2][n_chunks]
-    double* d_total = nullptr;    // [slots][2]
+    double* d_total = nullptr;    // per lane: [slots][2] doubles, then [slots] status words
+    size_t lane_result_bytes = 0;  // stride of one lane's result block
     unsigned* d_counter = nullptr;
     unsigned* d_status = nullptr;
     // multi-GPU
@@ -289,7 +299,11 @@ struct scicone_dataset {
 
     int drain() {  // wait for every queued launch (results of unclaimed tickets are dropped)
         CUDA_TRY(cudaStreamSynchronize(stream));
-        for (Segment& g : seg) g.busy = false;
+        if (lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(lane_stream[1]));
+        for (Segment& g : seg) {
+            g.busy = false;
+            pool.put_many(g.temp_rows, 0);
+        }
         return SCICONE_OK;
     }
 
@@ -297,28 +311,39 @@ struct scicone_dataset {
         CUDA_TRY(cudaSetDevice(device));
         return SCICONE_OK;
     }
+    int sync_lanes() {  // every queued launch on every lane has finished
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(lane_stream[1]));
+        return SCICONE_OK;
+    }
     int ensure_arena(size_t bytes) {
         if (bytes <= arena_cap) return SCICONE_OK;
         size_t cap = std::max<size_t>(bytes * 2, size_t(1) << 20);
         // every queued launch has finished after the synchronize; the totals of tickets that were not collected yet sit in
         // their own pinned buffers (h_total), which are not touched here
-        CUDA_TRY(cudaStreamSynchronize(stream));
+        int rc0 = sync_lanes();
+        if (rc0) return rc0;
         for (Segment& g : seg) {
             if (g.h_arena) cudaFreeHost(g.h_arena);
             g.h_arena = nullptr;
         }
-        if (d_arena) cudaFree(d_arena);
-        d_arena = nullptr;
+        for (int l = 0; l < kLanes; ++l) {
+            if (d_arena[l]) cudaFree(d_arena[l]);
+            d_arena[l] = nullptr;
+        }
         arena_cap = 0;
         for (Segment& g : seg) CUDA_TRY(cudaMallocHost(&g.h_arena, cap));
-        CUDA_TRY(cudaMalloc(&d_arena, cap));
+        for (int l = 0; l < kLanes; ++l) CUDA_TRY(cudaMalloc(&d_arena[l], cap));
         arena_cap = cap;
         return SCICONE_OK;
     }
+    double* lane_total(int lane) const { return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_total) + lane * lane_result_bytes); }
+    unsigned* lane_status(int lane) const { return reinterpret_cast<unsigned*>(lane_total(lane) + (size_t)slots * 2); }
     int ensure_slots(int n) {
         if (n <= slots) return SCICONE_OK;
         int ns = std::max(n, std::max(4, slots * 2));
-        CUDA_TRY(cudaStreamSynchronize(stream));
+        int rc0 = sync_lanes();
+        if (rc0) return rc0;
         for (Segment& g : seg)
             if (g.busy) return fail(SCICONE_ERR_STATE, "batch size must grow while launches are outstanding");
         cudaFree(d_partial); cudaFree(d_chunk); cudaFree(d_total); cudaFree(d_counter);
@@ -332,15 +357,17 @@ struct scicone_dataset {
             g.h_gather = nullptr;
         }
         slots = 0;
-        CUDA_TRY(cudaMalloc(&d_partial, sizeof(double) * size_t(ns) * 2 * n_cta));
-        CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * size_t(ns) * 2 * n_chunks));
-        CUDA_TRY(cudaMalloc(&d_total, (sizeof(double) * 2 + sizeof(unsigned)) * ns));  // totals, then the status words: one copy back
-        CUDA_TRY(cudaMalloc(&d_counter, sizeof(unsigned) * ns));
-        d_status = reinterpret_cast<unsigned*>(d_total + (size_t)ns * 2);
-        CUDA_TRY(cudaMemset(d_counter, 0, sizeof(unsigned) * ns));
-        CUDA_TRY(cudaMemset(d_status, 0, sizeof(unsigned) * ns));
+        const size_t all = size_t(ns) * kLanes;  // every lane has its own range of ns slots
+        lane_result_bytes = round_up((sizeof(double) * 2 + sizeof(unsigned)) * ns, 16);
+        CUDA_TRY(cudaMalloc(&d_partial, sizeof(double) * all * 2 * n_cta));
+        CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * all * 2 * n_chunks));
+        CUDA_TRY(cudaMalloc(&d_total, lane_result_bytes * kLanes));  // per lane: totals, then the status words: one copy back
+        CUDA_TRY(cudaMalloc(&d_counter, sizeof(unsigned) * all));
+        CUDA_TRY(cudaMemset(d_counter, 0, sizeof(unsigned) * all));
+        CUDA_TRY(cudaMemset(d_total, 0, lane_result_bytes * kLanes));
+        d_status = nullptr;  // addressed per lane: see lane_total / lane_status
         for (Segment& g : seg) {
-            CUDA_TRY(cudaMallocHost(&g.h_total, (sizeof(double) * 2 + sizeof(unsigned)) * ns));
+            CUDA_TRY(cudaMallocHost(&g.h_total, lane_result_bytes));
             g.h_status = reinterpret_cast<unsigned*>(g.h_total + (size_t)ns * 2);
         }
         slots = ns;
@@ -531,8 +558,9 @@ int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const
     return SCICONE_OK;
 }
 
-void fill_header_common(scicone_chain* ch, int slot, DevHeader& H) {
+void fill_header_common(scicone_chain* ch, int lane, int slot, DevHeader& H) {
     scicone_dataset* ds = ch->ds;
+    const size_t gs = (size_t)lane * ds->slots + slot;  // global slot: every lane owns a range of ds->slots slots
     H.n_cells = ds->M;
     H.S = ds->dS;
     H.w = ds->dW;
@@ -540,18 +568,18 @@ void fill_header_common(scicone_chain* ch, int slot, DevHeader& H) {
     H.sums_new = ch->sums[1];
     H.maxid_old = ch->maxid[0];
     H.maxid_new = ch->maxid[1];
-    H.partial = ds->d_partial + (size_t)slot * 2 * ds->n_cta;
-    H.chunk_sums = ds->d_chunk + (size_t)slot * 2 * ds->n_chunks;
-    H.total = ds->d_total + (size_t)slot * 2;
-    H.counter = ds->d_counter + slot;
-    H.status = ds->d_status + slot;
+    H.partial = ds->d_partial + gs * 2 * ds->n_cta;
+    H.chunk_sums = ds->d_chunk + gs * 2 * ds->n_chunks;
+    H.total = ds->lane_total(lane) + (size_t)slot * 2;
+    H.counter = ds->d_counter + gs;
+    H.status = ds->lane_status(lane) + slot;
 }
 
 // The reduction scratch of a compiled blob is chosen when the batch is put together.
-void patch_slot(scicone_chain* ch, int slot) {
+void patch_slot(scicone_chain* ch, int lane, int slot) {
     DevHeader H;
     memcpy(&H, ch->blob.data(), sizeof H);
-    fill_header_common(ch, slot, H);
+    fill_header_common(ch, lane, slot, H);
     memcpy(ch->blob.data(), &H, sizeof H);
 }
 
@@ -829,7 +857,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     H.deleted_id = ch->deleted_id;
     H.flags = (ds->maxs ? PROP_MAX : 0u) | (od ? PROP_OD : 0u) | (full ? PROP_FULL : 0u);
     if (!full && ch->p.size() >= unch.size()) H.flags |= PROP_SCRATCH;  // MathOp.cpp:315
-    fill_header_common(ch, slot, H);
+    fill_header_common(ch, 0, slot, H);  // lane and slot are patched when the batch is put together
     {   // 16 + 8 E_n bytes per rescored cell x node score, 8 N + 12 per cell aggregate
         const double n_table = full ? (double)ch->p.size() : (double)(unch.size() + ch->p.size());
         ch->alg_bytes = (double)ds->M * (16.0 * tasks.size() + 8.0 * events.size() + 8.0 * n_table + 12.0);
@@ -870,7 +898,7 @@ int compile_od_only(scicone_chain* ch, double nu, int slot) {
     memset(&H, 0, sizeof H);
     H.deleted_id = -1;
     H.flags = (ch->ds->od ? PROP_OD : 0u) | PROP_OD_ONLY;
-    fill_header_common(ch, slot, H);
+    fill_header_common(ch, 0, slot, H);
     std::vector<const double*> slice_rows;
     int rc = add_od_request(ch, nu, H, slice_rows);
     if (rc) return rc;
@@ -906,6 +934,14 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     const unsigned long long tk = ds->next_ticket;
     scicone_dataset::Segment& g = ds->seg[tk % scicone_dataset::kRing];
     if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
+    const int lane = ds->n_lanes > 1 ? (int)(tk % ds->n_lanes) : 0;
+    if (ds->n_lanes > 1)  // a lane's slots and arena are reused by every second launch: the previous one must have been collected
+        for (scicone_dataset::Segment& o : ds->seg)
+            if (o.busy && o.lane == lane) return fail(SCICONE_ERR_STATE, "two launches outstanding on one lane: collect a ticket first");
+    cudaStream_t st = lane == 0 ? ds->stream : ds->lane_stream[1];
+    unsigned char* d_arena = ds->d_arena[lane];
+    g.lane = lane;
+    for (int i = 0; i < n; ++i) patch_slot(chains[i], lane, i);
     g.with_od.assign(n, 0);
     LaunchEntry* offs = reinterpret_cast<LaunchEntry*>(g.h_arena);
     size_t at = head, item_at = off_items;
@@ -948,18 +984,18 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         offs[q] = chains[order[q]]->entry;
         offs[q].blob_off = blob_at[order[q]];
     }
-    CUDA_TRY(cudaMemcpyAsync(ds->d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, ds->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, st));
     if (n_items) {
-        if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, ds->stream));
+        if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, st));
         const int blocks_per_row = (ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells);
         const long long units = (long long)n_items * blocks_per_row;
-        build_rows_kernel<<<(unsigned)std::min<long long>(units, 4ll * ds->n_sm), kBuildBlock, 0, ds->stream>>>(
-            ds->d_arena, (unsigned)off_items, (int)n_items, blocks_per_row);
+        build_rows_kernel<<<(unsigned)std::min<long long>(units, 4ll * ds->n_sm), kBuildBlock, 0, st>>>(
+            d_arena, (unsigned)off_items, (int)n_items, blocks_per_row);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
     }
     g.n_items = (int)n_items;
-    if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, ds->stream));
+    if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, st));
     {   // scoring mode and likelihood are properties of the dataset: one specialisation per launch.  kOcc = CTAs per SM the
         // register allocation aims at (shared memory - the cp.async ring - allows 7); SCICONE_OCC overrides the default for tuning.
         static const int occ = [] {
@@ -970,34 +1006,34 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         const dim3 grid(ds->n_cta, n);
 #define SCICONE_LAUNCH(OCC)                                                                                                \
     do {                                                                                                                   \
-        if (ds->maxs && ds->od) score_proposals_kernel<true, true, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);   \
-        else if (ds->maxs) score_proposals_kernel<true, false, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);        \
-        else if (ds->od) score_proposals_kernel<false, true, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);          \
-        else score_proposals_kernel<false, false, OCC><<<grid, kThreads, 0, ds->stream>>>(ds->d_arena);                     \
+        if (ds->maxs && ds->od) score_proposals_kernel<true, true, OCC><<<grid, kThreads, 0, st>>>(d_arena);   \
+        else if (ds->maxs) score_proposals_kernel<true, false, OCC><<<grid, kThreads, 0, st>>>(d_arena);        \
+        else if (ds->od) score_proposals_kernel<false, true, OCC><<<grid, kThreads, 0, st>>>(d_arena);          \
+        else score_proposals_kernel<false, false, OCC><<<grid, kThreads, 0, st>>>(d_arena);                     \
     } while (0)
         if (occ == 5) SCICONE_LAUNCH(5);
         else if (occ == 6) SCICONE_LAUNCH(6);
         else SCICONE_LAUNCH(7);
 #undef SCICONE_LAUNCH
     }
-    if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, ds->stream));
+    if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, st));
     CUDA_TRY(cudaGetLastError());
     ds->n_launches++;
     if (ds->world > 1) {
         // Each rank contributes its per-chunk sums; every rank adds all chunks in global chunk order,
         // so the total does not depend on the number of GPUs.
-        pack_chunks_kernel<<<n, 128, 0, ds->stream>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
+        pack_chunks_kernel<<<n, 128, 0, st>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
         const size_t cnt = (size_t)n * 2 * ds->max_chunks_rank;
-        int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, ds->stream);
+        int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, st);
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
-        CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, st));
     } else
-        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->d_total, (sizeof(double) * 2 + sizeof(unsigned)) * ds->slots, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->lane_total(lane), ds->lane_result_bytes, cudaMemcpyDeviceToHost, st));
     if (ds->world > 1)
-        CUDA_TRY(cudaMemcpyAsync(g.h_status, ds->d_status, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ds->stream));
-    CUDA_TRY(cudaEventRecord(g.done, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(g.h_status, ds->lane_status(lane), sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(g.done, st));
     ds->h2d_bytes += bytes;
     ds->d2h_bytes += (ds->world > 1 ? sizeof(double) * 2 * n * ds->max_chunks_rank * ds->world : sizeof(double) * 2 * n) + sizeof(unsigned) * n;
     for (int i = 0; i < n; ++i) {
@@ -1005,8 +1041,9 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         ds->alg_bytes += ch->alg_bytes;
         ds->n_scores += ch->n_scores;
         g.with_od[i] = ch->with_od;
-        // rows that only lived for this launch go back to the pool: any later use is ordered behind it by the stream
-        for (double* r : ch->temp_rows) ch->row_put(r);
+        // rows that only live for this launch go back to the pool when it is collected (with two lanes a later launch is
+        // not ordered behind this one)
+        g.temp_rows.insert(g.temp_rows.end(), ch->temp_rows.begin(), ch->temp_rows.end());
         ch->temp_rows.clear();
         ch->builds.clear();
         ch->build_aux.clear();
@@ -1025,6 +1062,7 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
     if (!g.busy || g.ticket != ticket) return fail(SCICONE_ERR_STATE, "unknown or already collected ticket %llu", ticket);
     CUDA_TRY(cudaEventSynchronize(g.done));
     g.busy = false;
+    ds->pool.put_many(g.temp_rows, 0);
     const int n = g.n;
     if (ds->profiling) {
         float ms = 0.f;
@@ -1056,7 +1094,7 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
         if (g.h_status[i]) nan = true;
     }
     if (nan) {
-        CUDA_TRY(cudaMemsetAsync(ds->d_status, 0, sizeof(unsigned) * ds->slots, ds->stream));
+        CUDA_TRY(cudaMemsetAsync(ds->lane_status(g.lane), 0, sizeof(unsigned) * ds->slots, g.lane == 0 ? ds->stream : ds->lane_stream[1]));
         return fail(SCICONE_ERR_NAN, "a per-cell aggregate is NaN (reference: assert(!isnan), Inference.h:1150,1191)");
     }
     return SCICONE_OK;
@@ -1092,6 +1130,7 @@ int od_scores(scicone_chain* ch, double nu, double* out) {
 }
 
 int gather_rows(scicone_dataset* ds, const std::vector<const double*>& rows, double* out) {
+    if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
     const int n = (int)rows.size();
     if (n == 0 || ds->M == 0) return SCICONE_OK;
     const double** d_rows = nullptr;
@@ -1115,6 +1154,7 @@ int gather_rows(scicone_dataset* ds, const std::vector<const double*>& rows, dou
 
 template <class T>
 int read_vec(scicone_dataset* ds, const T* dev, T* out, size_t n) {
+    if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
     CUDA_TRY(cudaMemcpyAsync(out, dev, sizeof(T) * n, cudaMemcpyDeviceToHost, ds->stream));
     CUDA_TRY(cudaStreamSynchronize(ds->stream));
     return SCICONE_OK;
@@ -1170,6 +1210,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     DS_TRY(cudaSetDevice(ds->device));
     DS_TRY(cudaDeviceGetAttribute(&ds->n_sm, cudaDevAttrMultiProcessorCount, ds->device));
     DS_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+    ds->lane_stream[0] = ds->stream;
     for (scicone_dataset::Segment& g : ds->seg) {
         DS_TRY(cudaEventCreate(&g.evb));
         DS_TRY(cudaEventCreate(&g.ev0));
@@ -1210,10 +1251,12 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     if (!ds) return;
     cudaSetDevice(ds->device);
     if (ds->stream) cudaStreamSynchronize(ds->stream);
+    if (ds->lane_stream[1]) cudaStreamSynchronize(ds->lane_stream[1]);
     if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm);
     ds->pool.destroy();
     cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW);
-    cudaFree(ds->d_arena); cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
+    for (unsigned char* a : ds->d_arena) cudaFree(a);
+    cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
     cudaFree(ds->d_counter); cudaFree(ds->d_gather); cudaFree(ds->d_send);
     for (scicone_dataset::Segment& g : ds->seg) {
         if (g.h_arena) cudaFreeHost(g.h_arena);
@@ -1226,6 +1269,7 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     }
     for (cudaEvent_t e : ds->region_ev)
         if (e) cudaEventDestroy(e);
+    if (ds->lane_stream[1]) cudaStreamDestroy(ds->lane_stream[1]);
     if (ds->stream) cudaStreamDestroy(ds->stream);
     delete ds;
 }
@@ -1379,10 +1423,7 @@ int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const
                 g_err = job.msg[i];
                 return job.rc[i];
             }
-        for (int i = 0; i < n; ++i) {
-            chains[i]->compiled = true;
-            patch_slot(chains[i], i);
-        }
+        for (int i = 0; i < n; ++i) chains[i]->compiled = true;
     }
     unsigned long long tk = 0;
     rc = submit_proposals(ds, chains, n, &tk);
@@ -1577,6 +1618,7 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
     if (ch->t.empty()) return fail(SCICONE_ERR_STATE, "assign_cells_to_nodes before compute_t_table");
     rc = ds->set_device();
     if (rc) return rc;
+    if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
     const int n = (int)ch->t.size(), M = ds->M, K = ds->K;
     std::vector<const double*> rows;
     std::vector<int> ids;
@@ -1762,6 +1804,20 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
     return ds->ensure_slots(std::max(keep, 4));
 }
 
+int scicone_set_streams(scicone_dataset* ds, int32_t n) {
+    if (!ds || n < 1 || n > scicone_dataset::kLanes) return fail(SCICONE_ERR_ARG, "set_streams: 1 or 2 streams");
+    if (n > 1 && ds->world > 1) return fail(SCICONE_ERR_STATE, "set_streams: cell-sharded datasets launch on one stream (the collective orders them)");
+    int rc = ds->set_device();
+    if (rc) return rc;
+    rc = ds->sync_lanes();
+    if (rc) return rc;
+    for (scicone_dataset::Segment& g : ds->seg)
+        if (g.busy) return fail(SCICONE_ERR_STATE, "set_streams with launches outstanding");
+    if (n > 1 && !ds->lane_stream[1]) CUDA_TRY(cudaStreamCreateWithFlags(&ds->lane_stream[1], cudaStreamNonBlocking));
+    ds->n_lanes = n;
+    return SCICONE_OK;
+}
+
 int scicone_set_profiling(scicone_dataset* ds, int32_t on) {
     if (!ds) return fail(SCICONE_ERR_ARG, "null dataset");
     ds->profiling = on != 0;
@@ -1805,6 +1861,7 @@ int scicone_region_mark(scicone_dataset* ds, int32_t which) {
     int rc = ds->set_device();
     if (rc) return rc;
     if (!ds->region_ev[which]) CUDA_TRY(cudaEventCreate(&ds->region_ev[which]));
+    if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));  // the mark covers both lanes
     CUDA_TRY(cudaEventRecord(ds->region_ev[which], ds->stream));
     return SCICONE_OK;
 }

@@ -278,7 +278,8 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         const std::string schedule = a.str("schedule", (world == 1 && n_chains >= 4) ? "dynamic" : "static");
         auto run_chains = [&](int iters, HostPhaseTimes* t) {
             if (schedule == "dynamic" && world == 1)
-                infer_mcmc_dynamic(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("min_batch", 0)), t);
+                infer_mcmc_dynamic(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("min_batch", 0)), t,
+                                   static_cast<int>(a.integer("n_streams", 2)));
             else
                 infer_mcmc(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("n_groups", 0)), t);
         };

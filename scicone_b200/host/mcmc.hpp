@@ -601,12 +601,15 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
 // with at most two launches in flight, and feeds completed launches back to the workers.  Batch composition varies from
 // run to run; a chain's own sequence propose -> score -> compare does not, so trajectories are those of infer_mcmc.
 inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
-                               int min_batch = 0, HostPhaseTimes* times = nullptr) {
+                               int min_batch = 0, HostPhaseTimes* times = nullptr, int n_streams = 2) {
     typedef std::chrono::steady_clock Clock;
     const int B = static_cast<int>(chains.size());
     if (B == 0 || n_iters <= 0) return;
     scicone_dataset* ds = chains[0]->ds;
     if (min_batch <= 0) min_batch = std::max(1, B / 3);
+    // two launch streams: K1 of one launch overlaps the proposal kernel of the other (a launch is always collected here
+    // before its chains are settled, which is what the second stream requires)
+    if (n_streams > 1) abi_check(scicone_set_streams(ds, 2));
     parallel_chains(B, [&](int b) {
         chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
         chains[b]->open_traces(n_iters);
