@@ -1,0 +1,50 @@
+"""Cell-sharded runs on real GPUs: the same chain on 1 GPU and sharded over 2 GPUs must write
+byte-identical traces - the tree score is assembled from per-1024-cell chunk sums added in global order, so it does not
+depend on the number of GPUs, and neither does any accept decision.  Skipped on boxes with fewer than 2 GPUs (the CPU
+side of the sharding logic is covered by tests/test_sharding_gloo.py)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from host_util import NATIVE, read_outputs
+from scicone_b200.synth import make_counts
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("max_scoring", ["true", "false"])
+def test_two_gpu_run_equals_one_gpu_run(tmp_path, max_scoring):
+    from scicone_b200.api import comm_unique_id
+
+    data = make_counts(5000, 9000, 60, seed=31)  # 5 chunks of 1024 cells: shards of 3 and 2 chunks
+    d = str(tmp_path / "d.csv")
+    r = str(tmp_path / "r.txt")
+    np.savetxt(d, data["D"], delimiter=",", fmt="%.0f")
+    np.savetxt(r, data["region_sizes"], fmt="%d")
+    common = [NATIVE, f"--d_matrix_file={d}", f"--region_sizes_file={r}", "--n_cells=5000", "--n_regions=60", "--n_iters=300",
+              "--n_nodes=12", "--seed=5", "--nu=1.0", "--verbosity=2", f"--max_scoring={max_scoring}"]
+    one = subprocess.run(common + ["--postfix=one", "--device=0"], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stderr[-2000:]
+    uid = comm_unique_id().hex()
+    procs = [subprocess.Popen(common + [f"--postfix=two{k}", f"--device={k}", f"--rank={k}", "--world=2", f"--nccl_id={uid}"],
+                              cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for k in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err[-2000:]
+    for name in ("acceptance_ratio", "markov_chain", "gamma_values"):
+        a = open(os.path.join(str(tmp_path), f"one_{name}.csv")).read()
+        for k in range(2):
+            assert a == open(os.path.join(str(tmp_path), f"two{k}_{name}.csv")).read(), name
+    assert open(os.path.join(str(tmp_path), "one_tree_inferred.txt")).read() == open(os.path.join(str(tmp_path), "two0_tree_inferred.txt")).read()
