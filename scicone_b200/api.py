@@ -360,17 +360,24 @@ class BatchLauncher:
     def run(self):
         return self.wait(self.submit())
 
-    def queue(self, trees, node_idx):
-        """scicone_batch_compute_t_prime_scores: subtree root node_idx[i] of trees[i] on chain i (one call for all chains)."""
+    def marshal_queue(self, trees, node_idx):
+        """Pre-marshalled arguments of queue() (keeps the ctypes array building out of timed loops)."""
         tp = C.POINTER(CTree)
         arr = (tp * self.n)(*[C.pointer(t.ctree) for t in trees])
         idx = (C.c_int32 * self.n)(*[int(i) for i in node_idx])
-        self._keep = trees  # the CTree buffers must outlive the call
+        return (arr, idx, trees)  # the CTree buffers must outlive the call
+
+    def marshal_settle(self, accept):
+        return (C.c_int32 * self.n)(*[1 if a else 0 for a in accept])
+
+    def queue(self, trees=None, node_idx=None, marshalled=None):
+        """scicone_batch_compute_t_prime_scores: subtree root node_idx[i] of trees[i] on chain i (one call for all chains)."""
+        arr, idx, self._keep = marshalled if marshalled is not None else self.marshal_queue(trees, node_idx)
         _check(lib().scicone_batch_compute_t_prime_scores(self._hs, arr, idx, self.n))
 
-    def settle(self, accept):
+    def settle(self, accept=None, marshalled=None):
         """scicone_batch_settle: accept[i] ? accept : reject for every chain."""
-        flags = (C.c_int32 * self.n)(*[1 if a else 0 for a in accept])
+        flags = marshalled if marshalled is not None else self.marshal_settle(accept)
         _check(lib().scicone_batch_settle(self._hs, flags, self.n))
 
 
