@@ -219,6 +219,10 @@ def run_engine(args):
     ds.kernel_time_stats(reset=True)
     ds.counters(reset=True)
     launches1 = ds.kernel_launches()
+    import gc
+
+    gc.collect()
+    gc.disable()  # the traces are ~10^6 small Python objects: no collector pauses inside the timed loop
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ds.region_mark(0)
@@ -233,6 +237,7 @@ def run_engine(args):
         launcher.wait(tk)
     ds.region_mark(1)
     barrier()
+    gc.enable()
     dev_ms = ds.region_elapsed_ms()
     kern_us, n_timed = ds.kernel_time_stats()
     cnt_dev = ds.counters()
