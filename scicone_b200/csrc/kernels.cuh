@@ -131,7 +131,9 @@ struct alignas(16) DevHeader {
 struct alignas(16) DevBuild {
     double* dst;
     const double* src;     // BUILD_G: Dt[k] or S;  slices: Dt
-    double c1, c2;         // BUILD_G: c1 = (nu*cn)*r or nu*z
+    double c1;             // BUILD_G: (nu*cn)*r or nu*z
+    unsigned off_rows;     // OD slices: arena offset of rows[K]: where lgamma(D_k + arg[k]) of region k is also stored (or null)
+    unsigned pad;
     unsigned kind;
     int k0, k1;            // slices: region range
     unsigned off_arg;      // slices: arena offsets of arg[K], cc[K]
@@ -232,15 +234,21 @@ __device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned c
         ok[q] = j0 + q * kBuildBlock < it.n_cells;
     }
     if (it.kind == BUILD_OD_SLICE) {  // Tree.h:1792-1797
+        // lgamma(D_k + nu*neutral_k*r_k) is also the lgamma row L(k, neutral_k) of the tree's events: where the proposal
+        // needs that row, the value is stored on the way instead of being evaluated a second time by a row item
+        double* const* keep = reinterpret_cast<double* const*>(arena + it.off_rows);
         for (int k = it.k0; k < it.k1; ++k) {
             const double* row = it.src + (long long)k * it.row_stride + j0;
             const double a = arg[k], c = cc[k];
+            double* const out = keep[k];
             double d[kBuildCells];
 #pragma unroll
             for (int q = 0; q < kBuildCells; ++q) d[q] = ok[q] ? __ldg(row + q * kBuildBlock) : 32.0;
 #pragma unroll
             for (int q = 0; q < kBuildCells; ++q) {
-                acc[q] += lgam(d[q] + a, tbl);
+                const double v = lgam(d[q] + a, tbl);
+                if (out && ok[q]) out[j0 + q * kBuildBlock] = v;
+                acc[q] += v;
                 acc[q] -= c;
             }
         }

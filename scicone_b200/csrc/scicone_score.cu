@@ -502,9 +502,12 @@ int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const
     scicone_dataset* ds = ch->ds;
     const int K = ds->K;
     const size_t aux0 = ch->build_aux.size();
-    ch->build_aux.resize(aux0 + 2 * (size_t)K);
+    ch->build_aux.resize(aux0 + 3 * (size_t)K, 0.0);
     double* arg = ch->build_aux.data() + aux0;
     double* cc = arg + K;
+    static_assert(sizeof(double*) == sizeof(double), "row pointers share the aux block with the doubles");
+    double** keep = reinterpret_cast<double**>(cc + K);  // rows[K]: lgamma rows the slices fill on the way (null: none)
+    for (int k = 0; k < K; ++k) keep[k] = nullptr;
     if (ds->od) {  // Tree.h:1783-1797 (no eta substitution here, quirk Q2)
         H.od_nz = nu * ds->root_z;
         H.od_lg_nz = lgamma(H.od_nz);
@@ -527,6 +530,23 @@ int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const
             arg[k] = nu * ds->neutral[k] * ds->r[k];
             cc[k] = lgamma(arg[k]);
         }
+        // A queued row item L(k, neutral_k) evaluates lgamma(D_k + arg[k]) - exactly the root term of region k: let the
+        // slice store it and drop the item (about a sixth of the lgamma work of a nu proposal)
+        std::vector<DevBuild>& items = ch->builds;
+        size_t kept = 0;
+        for (size_t i = 0; i < items.size(); ++i) {
+            const DevBuild& it = items[i];
+            bool shared = false;
+            if (it.kind == BUILD_G && it.src >= ds->dDt && it.src < ds->dDt + (size_t)K * ds->Mp) {
+                const int k = (int)((it.src - ds->dDt) / ds->Mp);
+                if (!keep[k] && memcmp(&it.c1, &arg[k], sizeof(double)) == 0) {
+                    keep[k] = it.dst;
+                    shared = true;
+                }
+            }
+            if (!shared) items[kept++] = it;
+        }
+        items.resize(kept);
     } else {  // Tree.h:1799-1806
         H.od_lg_nz = log((double)ds->sum_r);
         for (int k = 0; k < K; ++k) {
@@ -549,6 +569,7 @@ int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const
         it.k1 = (int)((long long)K * (s + 1) / n_slices);
         it.off_arg = (unsigned)(aux0 * sizeof(double));        // relative to the chain's aux block; rebased at submit
         it.off_c = (unsigned)((aux0 + K) * sizeof(double));
+        it.off_rows = (unsigned)((aux0 + 2 * (size_t)K) * sizeof(double));
         it.n_cells = ds->M;
         it.row_stride = (long long)ds->Mp;
         ch->builds.push_back(it);
@@ -973,6 +994,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
                 if (slice) {
                     it.off_arg += (unsigned)chain_aux;
                     it.off_c += (unsigned)chain_aux;
+                    it.off_rows += (unsigned)chain_aux;
                 }
                 memcpy(g.h_arena + item_at, &it, sizeof it);
                 item_at += sizeof it;
