@@ -625,8 +625,10 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     std::vector<int> ready;   // chains with a compiled proposal, waiting for a launch
     int n_done = 0, n_host = B;  // finished chains; chains currently owned by the host side (queued or being worked on)
     std::atomic<bool> stop{false};
+    std::atomic<int> n_work{0};  // size of `work`, readable without the mutex
     std::exception_ptr err;
     for (int b = 0; b < B; ++b) work.push_back(b);
+    n_work.store(B, std::memory_order_release);
 
     auto host_work = [&](int b) {
         Inference* c = chains[b];
@@ -664,15 +666,19 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
         int idle = 0;
         while (!stop.load(std::memory_order_acquire)) {
             int b = -1;
-            {
+            if (n_work.load(std::memory_order_acquire) > 0) {  // idle workers watch the counter, not the mutex
                 std::lock_guard<std::mutex> lk(mu);
                 if (!work.empty()) {
                     b = work.front();
                     work.pop_front();
+                    n_work.fetch_sub(1, std::memory_order_release);
                 }
             }
             if (b < 0) {
-                if (++idle > 2000) std::this_thread::yield();
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+                if (++idle > 20000) std::this_thread::yield();
                 continue;
             }
             idle = 0;
@@ -707,6 +713,7 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
             s.od = ods[i];
             s.has_result = true;
             work.push_back(f.members[i]);
+            n_work.fetch_add(1, std::memory_order_release);
             ++n_host;
         }
     };
