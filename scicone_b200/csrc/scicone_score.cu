@@ -963,7 +963,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     unsigned char* d_arena = ds->d_arena[lane];
     g.lane = lane;
     for (int i = 0; i < n; ++i) patch_slot(chains[i], lane, i);
-    g.with_od.assign(n, 0);
+    g.with_od.assign((size_t)n, 0);
     LaunchEntry* offs = reinterpret_cast<LaunchEntry*>(g.h_arena);
     size_t at = head, item_at = off_items;
     // grid.y order = longest proposal first (CTAs are dispatched in block-id order): the heavy full-tree

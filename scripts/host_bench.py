@@ -30,17 +30,23 @@ def main():
     ap.add_argument("--ref_iters", type=int, default=0)
     ap.add_argument("--max_scoring", default="true")
     ap.add_argument("--extra", default="")
+    ap.add_argument("--cluster_rows", type=int, default=0, help="configs[3]: condense the cells into this many cluster means with cluster_sizes")
     a = ap.parse_args()
     from scicone_b200.synth import SEED, make_counts
 
-    data = make_counts(a.cells, a.bins, a.regions, seed=SEED)
+    data = make_counts(a.cells, a.bins, a.regions, seed=SEED, cluster_rows=a.cluster_rows or None)
+    n_rows = data["D"].shape[0]
     tmp = tempfile.mkdtemp(prefix="hostbench_")
     d = os.path.join(tmp, "d.csv")
-    np.savetxt(d, data["D"], delimiter=",", fmt="%.0f")
+    np.savetxt(d, data["D"], delimiter=",", fmt="%.0f" if not a.cluster_rows else "%.18e")
     r = os.path.join(tmp, "r.txt")
     np.savetxt(r, data["region_sizes"], fmt="%d")
-    common = [f"--d_matrix_file={d}", f"--region_sizes_file={r}", f"--n_cells={a.cells}", f"--n_regions={a.regions}",
+    common = [f"--d_matrix_file={d}", f"--region_sizes_file={r}", f"--n_cells={n_rows}", f"--n_regions={a.regions}",
               f"--n_nodes={a.nodes - 1}", "--seed=42", "--nu=1.0", "--verbosity=1", f"--max_scoring={a.max_scoring}"]
+    if a.cluster_rows:
+        w = os.path.join(tmp, "w.txt")
+        np.savetxt(w, data["cluster_sizes"], fmt="%d")
+        common.append(f"--cluster_sizes_file={w}")
     stats = os.path.join(tmp, "stats.json")
     cmd = [os.path.join(ROOT, "scicone_b200", "bin", "inference")] + common + [f"--n_iters={a.iters}", f"--n_chains={a.chains}",
                                                                                  "--postfix=nat", f"--stats_file={stats}"] + a.extra.split()
@@ -54,6 +60,7 @@ def main():
     s["process_wall_s"] = wall
     s["mcmc_iters_per_s"] = s["n_chains"] * s["n_iters"] / (s["wall_us"] * 1e-6)
     s["cell_iters_per_s"] = s["mcmc_iters_per_s"] * a.cells
+    s["rows"] = n_rows
     s["us_per_step"] = s["wall_us"] / s["n_iters"]
     s["score_kernel_us_per_step"] = s["score_kernel_us"] / s["n_iters"]
     s["build_kernel_us_per_step"] = s["build_kernel_us"] / s["n_iters"]
