@@ -95,6 +95,7 @@ def lib():
         L.scicone_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.scicone_batch_compute_t_prime_scores.argtypes = [C.POINTER(vp), C.POINTER(tp), ip, C.c_int32]
         L.scicone_batch_settle.argtypes = [C.POINTER(vp), ip, C.c_int32]
+        L.scicone_set_streams.argtypes = [vp, C.c_int32]
         L.scicone_condense_matrix.argtypes = [C.c_int32, dp, C.c_int64, C.c_int64, ip, C.c_int32, dp, dp]
         L.scicone_test_lgamma.argtypes = [C.c_int32, dp, C.c_int32, dp]
         L.scicone_accept.argtypes = [vp]
@@ -180,6 +181,10 @@ class Dataset:
 
     def set_profiling(self, on=True):
         _check(lib().scicone_set_profiling(self._h, int(on)))
+
+    def set_streams(self, n):
+        """scicone_set_streams: 2 = consecutive launches alternate between two streams (collect a launch before settling it)."""
+        _check(lib().scicone_set_streams(self._h, int(n)))
 
     def last_kernel_time_us(self):
         out = C.c_double()
