@@ -1,28 +1,28 @@
 // Device side of the B200 tree-scoring engine (sm_100a, fp64, no tensor cores:
-// the path is a sparse gather + scan + reduce, HBM/latency bound).
+// the path is a sparse gather + scan + reduce, latency / issue bound).
 //
 // Layout in HBM (cells are the fastest-varying dimension everywhere, so a warp
 // touches one 256-byte segment per row it reads):
 //   Dt        [K][Mp]   region-major copy of the count matrix D
 //   S         [Mp]      per-cell read total  sum_k D[j][k]   (k ascending, as std::accumulate)
 //   w         [Mp]      cluster sizes (int32, 0 in the padding)
-//   delta rows   [Mp]   Delta(k,cn,cn_p)[j] = lgamma(D[j][k] + (nu*cn)*r_k) - lgamma(D[j][k] + (nu*cn_p)*r_k),
-//                       built once per (region, copy number pair, nu) by build_rows_kernel, then only gathered
+//   lgamma rows  [Mp]   L(k,cn)[j] = lgamma(D[j][k] + (nu*cn)*r_k), built once per (region, copy number, nu) by
+//                       build_rows_kernel, then only gathered; an event contributes L(k,cn_node) - L(k,cn_parent)
+//   z-term rows  [Mp]   lgamma(S[j] + nu*z_node), built by build_rows_kernel for every rescored node of a launch
 //   score rows   [Mp]   one row per tree node: attachment score of every cell to that node
 //   aggregates   [Mp]   per-cell log-sum-exp (or max) over the nodes, + argmax id in max mode
 //
 // Two kernels per batch of proposals:
-//   build_rows_kernel       (K1) every lgamma that is a pure function of the data: missing delta rows and, for
-//                           proposals that change nu, region slices of the root score.  One CTA row per item:
-//                           embarrassingly parallel, fp64-pipe bound.
-//   score_proposals_kernel  (K2-K4) per proposal (grid.y) and per 64-cell tile (grid.x): the increments
-//                           score(node) - score(parent) of all rescored nodes are evaluated by 4 task lanes per
-//                           cell into shared memory (Tree::compute_score, reference scicone/src/Tree.h:163-244, as
-//                           gathers + one large-argument lgamma), then one lane scans them parent-before-child
-//                           (Tree::compute_stack, Tree.h:260-286), folds the new scores into the cell's aggregate
-//                           exactly like Inference::compute_t_prime_sums (scicone/src/Inference.h:1069-1196) /
-//                           MathOp::log_replace_sum (scicone/src/MathOp.cpp:307-361), and the CTA reduces
-//                           aggregate * cluster_size into a partial of the tree score (Inference.h:292-294).
+//   build_rows_kernel       (K1) every lgamma of the path (Tree::compute_score, reference scicone/src/Tree.h:214-231;
+//                           Tree::get_od_root_score, Tree.h:1792-1797): lgamma rows, z-term rows, region slices of the
+//                           root score of proposals that change nu.  Persistent CTAs over (item, cell block) units.
+//   score_proposals_kernel  (K2-K4) per proposal (grid.y) and per 128-cell tile (grid.x), one thread per cell: walks
+//                           the rescored nodes parent-before-child (Tree::compute_stack, Tree.h:260-286) with the
+//                           gathers of the next four nodes in flight (cp.async ring), folds the new scores into the
+//                           cell's aggregate exactly like Inference::compute_t_prime_sums
+//                           (scicone/src/Inference.h:1069-1196) / MathOp::log_replace_sum
+//                           (scicone/src/MathOp.cpp:307-361), and the CTA reduces aggregate * cluster_size into a
+//                           partial of the tree score (Inference.h:292-294).
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -34,7 +34,6 @@ namespace scicone {
 
 constexpr int kCells = 128;         // cells per CTA of the proposal kernel: one thread per cell
 constexpr int kThreads = kCells;
-constexpr int kMinCtasPerSm = 12;   // register budget of the proposal kernel: 65536 / (10 * 128) = 51 -> 48 registers
 constexpr int kTaskChunk = 32;      // task records staged in shared memory at a time
 constexpr int kEvStage = 64;        // event records staged with them (the rest is read from global memory)
 constexpr int kDepth = 4;           // nodes whose gathers are in flight per thread (cp.async ring stages)
