@@ -254,6 +254,8 @@ def run_engine(args):
     # pass 2
     two_lanes = world == 1 and B >= 2
     dev_ms = one_lane_ms
+    two_lane_ms = None
+    value_pass = "one launch of all chains per step on one stream, totals collected with a lag"
     if two_lanes:
         groups = [list(range(0, B // 2)), list(range(B // 2, B))]
         launchers = [BatchLauncher([chains[b] for b in g]) for g in groups]
@@ -284,8 +286,11 @@ def run_engine(args):
         run_two_lanes(base + W, base + W + K)
         ds.region_mark(1)
         barrier()
-        dev_ms = ds.region_elapsed_ms()
-        launches_dev = ds.kernel_launches() - launches2
+        two_lane_ms = ds.region_elapsed_ms()
+        if two_lane_ms < one_lane_ms:  # `value` is the faster of the two ways to drive the device pipeline
+            dev_ms = two_lane_ms
+            launches_dev = ds.kernel_launches() - launches2
+            value_pass = "two groups of chains on two launch lanes"
         ds.set_streams(1)
     gc.enable()
 
@@ -322,7 +327,8 @@ def run_engine(args):
                        "cells_per_gpu": M, "regions": args.regions, "chains": B, "tree_nodes": args.nodes,
                        "max_scoring": int(args.max_scoring), "parallelism": f"cells sharded x{world}" if world > 1 else "1 GPU",
                        "proposal_source": "value: pre-generated valid proposals (scicone_b200.synth.TreeState), accept prob 0.3, "
-                                          + ("two groups of chains on two launch lanes; " if world == 1 else "one launch per step; ")
+                                          + value_pass + f" (one stream: {one_lane_ms / K:.4f} ms/step"
+                                          + (f", two lanes: {two_lane_ms / K:.4f} ms/step" if two_lane_ms is not None else "") + "); "
                                           + "e2e: real MCMC (native host)",
                        "l2": f"inputs larger than L2: {resident / 1e6:.0f} MB of score/lgamma rows + counts resident vs 126 MB L2"},
             "mcmc_iters_per_s": iters / (dev_ms * 1e-3),

@@ -227,6 +227,15 @@ int scicone_condense_matrix(int32_t device, const double* D_bins /* [n_cells][n_
                             double* kernel_us);
 
 /*
+ * Cluster condensation (reference scripts/condense_clusters.py:28-38; pyscicone scicone.py:331-335): means[c][k] = mean of
+ * column k over the rows with assignments[i] == c, rows added in row order (numpy's axis-0 order, so the means equal the
+ * reference's), sizes[c] = number of such rows.  assignments must lie in [0, n_clusters).  Host buffers, device work.
+ */
+int scicone_condense_clusters(int32_t device, const double* D /* [n_cells][n_cols] */, int64_t n_cells, int32_t n_cols,
+                              const int32_t* assignments /* [n_cells] */, int32_t n_clusters,
+                              double* means /* [n_clusters][n_cols] */, int32_t* sizes /* [n_clusters] */);
+
+/*
  * Test hook: the device log-gamma used for every data and z term (reference: libm lgamma called from
  * Tree::compute_score, Tree.h:214-231) evaluated on `n` caller-provided positive arguments.
  */

@@ -155,6 +155,7 @@ int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, in
 int scicone_condense_matrix(int32_t, const double*, int64_t, int64_t, const int32_t*, int32_t, double*, double*) { return fail(-2, "cpu backend: no device"); }
 int scicone_batch_poll(scicone_dataset* ds, uint64_t ticket, int32_t* done) { *done = ds->results.count(ticket) ? 1 : 0; return *done ? 0 : fail(-3, "unknown ticket"); }
 int scicone_set_streams(scicone_dataset*, int32_t) { return 0; }
+int scicone_condense_clusters(int32_t, const double*, int64_t, int32_t, const int32_t*, int32_t, double*, int32_t*) { return fail(-2, "cpu backend: no device"); }
 int scicone_host_threads(void) { return scicone::ForkJoinPool::instance().n_threads(); }
 int scicone_counters(scicone_dataset*, double out[4], int32_t) { out[0] = out[1] = out[2] = out[3] = 0; return 0; }
 int scicone_region_mark(scicone_dataset*, int32_t) { return 0; }

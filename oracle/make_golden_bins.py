@@ -16,3 +16,11 @@ assert np.array_equal(bins, np.round(bins)) and bins.max() < 65536
 np.savez_compressed(os.path.join(HERE, "..", "tests", "golden", "tutorial_bins.npz"), bins=bins.astype(np.uint16),
                     regions=regions, region_sizes=sizes)
 print(bins.shape, regions.shape, sizes)
+
+# cluster condensation golden: the reference's own condensed matrix / sizes for the tutorial's cluster assignments
+assign = np.loadtxt(os.path.join(EX, "5nodes_10regions_10000reads_test_d_mat_segmented_counts_cluster_assignments.txt")).astype(np.int32)
+condensed = np.loadtxt(os.path.join(EX, "5nodes_10regions_10000reads_test_d_mat_segmented_counts_condensed.txt"), delimiter=",")
+csizes = np.loadtxt(os.path.join(EX, "5nodes_10regions_10000reads_test_d_mat_segmented_counts_cluster_sizes.txt")).astype(np.int32)
+np.savez_compressed(os.path.join(HERE, "..", "tests", "golden", "tutorial_clusters.npz"), regions=regions, assignments=assign,
+                    condensed=condensed, cluster_sizes=csizes)
+print(condensed.shape, csizes)

@@ -546,3 +546,23 @@ int orc_condense_matrix(const double* D_bins, int64_t n_cells, int64_t n_bins, c
     }
     return 0;
 }
+
+/* Cluster condensation (reference scripts/condense_clusters.py:28-38: np.mean(input_data[rows of the cluster], axis=0), i.e.
+ * the cluster's rows added one after the other in row order, divided by their number; pyscicone scicone.py:331-335). */
+int orc_condense_clusters(const double* D, int64_t n_cells, int32_t n_cols, const int32_t* assignments, int32_t n_clusters,
+                          double* means, int32_t* sizes) {
+    for (int32_t c = 0; c < n_clusters; ++c) {
+        sizes[c] = 0;
+        for (int32_t k = 0; k < n_cols; ++k) means[(int64_t)c * n_cols + k] = 0.0;
+    }
+    for (int64_t i = 0; i < n_cells; ++i) {
+        const int32_t c = assignments[i];
+        if (c < 0 || c >= n_clusters) return -1;
+        sizes[c]++;
+        for (int32_t k = 0; k < n_cols; ++k) means[(int64_t)c * n_cols + k] += D[i * n_cols + k];
+    }
+    for (int32_t c = 0; c < n_clusters; ++c)
+        for (int32_t k = 0; k < n_cols; ++k)
+            if (sizes[c] > 0) means[(int64_t)c * n_cols + k] /= (double)sizes[c];
+    return 0;
+}

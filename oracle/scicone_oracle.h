@@ -62,6 +62,10 @@ double orc_log_replace_sum(double sum, const double* to_subtract, int n_sub, con
 int orc_condense_matrix(const double* D_bins, int64_t n_cells, int64_t n_bins, const int32_t* region_sizes, int32_t n_regions,
                         double* D_regions);
 
+/* scripts/condense_clusters.py:28-38: per-cluster column means (rows added in row order) and sizes */
+int orc_condense_clusters(const double* D, int64_t n_cells, int32_t n_cols, const int32_t* assignments, int32_t n_clusters,
+                          double* means, int32_t* sizes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_build_time_stats", "scicone_kernel_launches",
     "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
     "scicone_parallel_for", "scicone_host_threads", "scicone_test_lgamma", "scicone_prepare_t_prime",
-    "scicone_batch_compute_t_prime_scores", "scicone_batch_settle", "scicone_condense_matrix", "scicone_batch_poll", "scicone_set_streams",
+    "scicone_batch_compute_t_prime_scores", "scicone_batch_settle", "scicone_condense_matrix", "scicone_batch_poll", "scicone_set_streams", "scicone_condense_clusters",
 ]
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}
@@ -96,6 +96,7 @@ def lib():
         L.scicone_batch_compute_t_prime_scores.argtypes = [C.POINTER(vp), C.POINTER(tp), ip, C.c_int32]
         L.scicone_batch_settle.argtypes = [C.POINTER(vp), ip, C.c_int32]
         L.scicone_set_streams.argtypes = [vp, C.c_int32]
+        L.scicone_condense_clusters.argtypes = [C.c_int32, dp, C.c_int64, C.c_int32, ip, C.c_int32, dp, ip]
         L.scicone_condense_matrix.argtypes = [C.c_int32, dp, C.c_int64, C.c_int64, ip, C.c_int32, dp, dp]
         L.scicone_test_lgamma.argtypes = [C.c_int32, dp, C.c_int32, dp]
         L.scicone_accept.argtypes = [vp]
@@ -409,3 +410,19 @@ def condense_matrix(D_bins, region_sizes, device=0, return_kernel_us=False):
     if rc != 0:
         raise SciconeError(rc, L.scicone_last_error().decode())
     return (out, us.value) if return_kernel_us else out
+
+
+def condense_clusters(D, assignments, n_clusters=None, device=0):
+    """Cluster means and sizes (reference scripts/condense_clusters.py:28-38) on the device: rows added in row order."""
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    a = np.ascontiguousarray(assignments, dtype=np.int32)
+    n = int(a.max()) + 1 if n_clusters is None else int(n_clusters)
+    means = np.empty((n, D.shape[1]), dtype=np.float64)
+    sizes = np.empty(n, dtype=np.int32)
+    L = lib()
+    rc = L.scicone_condense_clusters(int(device), D.ctypes.data_as(C.POINTER(C.c_double)), D.shape[0], D.shape[1],
+                                     a.ctypes.data_as(C.POINTER(C.c_int32)), n, means.ctypes.data_as(C.POINTER(C.c_double)),
+                                     sizes.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise SciconeError(rc, L.scicone_last_error().decode())
+    return means, sizes

@@ -142,4 +142,26 @@ __global__ void __launch_bounds__(kK0Threads, 3)
     }
 }
 
+// Cluster condensation (reference scripts/condense_clusters.py:28-38, pyscicone scicone.py:331-335): the mean of the rows of
+// every cluster, rows added in row order (numpy's axis-0 reduction order).  One thread per (cluster, column); `order`
+// lists the rows sorted by cluster (stable), `first[c] .. first[c+1]` are cluster c's entries.
+__global__ void cluster_means_kernel(const double* __restrict__ D, int K, const int* __restrict__ order, const int* __restrict__ first,
+                                     int n_clusters, double* __restrict__ means) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (k >= K || c >= n_clusters) return;
+    const int b = first[c], e = first[c + 1];
+    double acc = 0.0;
+    int i = b;
+    for (; i + 4 <= e; i += 4) {  // the loads are independent of the running sum: four in flight
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = __ldg(D + (long long)order[i + q] * K + k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc += v[q];
+    }
+    for (; i < e; ++i) acc += __ldg(D + (long long)order[i] * K + k);
+    means[(long long)c * K + k] = e > b ? acc / (double)(e - b) : 0.0;
+}
+
 }  // namespace scicone

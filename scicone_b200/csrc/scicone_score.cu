@@ -1751,6 +1751,47 @@ int scicone_condense_matrix(int32_t device, const double* D_bins, int64_t n_cell
     return SCICONE_OK;
 }
 
+int scicone_condense_clusters(int32_t device, const double* D, int64_t n_cells, int32_t n_cols, const int32_t* assignments,
+                              int32_t n_clusters, double* means, int32_t* sizes) {
+    if (!D || !assignments || !means || !sizes || n_cells <= 0 || n_cols <= 0 || n_clusters <= 0)
+        return fail(SCICONE_ERR_ARG, "condense_clusters: null buffer or empty matrix");
+    std::vector<int> first(n_clusters + 1, 0), order((size_t)n_cells);
+    for (int64_t i = 0; i < n_cells; ++i) {
+        if (assignments[i] < 0 || assignments[i] >= n_clusters)
+            return fail(SCICONE_ERR_ARG, "condense_clusters: assignment %d of row %lld outside [0, %d)", assignments[i], (long long)i, n_clusters);
+        first[assignments[i] + 1]++;
+    }
+    for (int c = 0; c < n_clusters; ++c) {
+        sizes[c] = first[c + 1];
+        first[c + 1] += first[c];
+    }
+    {
+        std::vector<int> fill(first.begin(), first.end() - 1);
+        for (int64_t i = 0; i < n_cells; ++i) order[fill[assignments[i]]++] = (int)i;  // stable: row order inside a cluster
+    }
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev)
+        return fail(SCICONE_ERR_CUDA, "condense_clusters: no such CUDA device; this library has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    double *dD = nullptr, *dM = nullptr;
+    int *dO = nullptr, *dF = nullptr;
+    cudaError_t e = cudaMalloc(&dD, sizeof(double) * n_cells * n_cols);
+    if (e == cudaSuccess) e = cudaMalloc(&dM, sizeof(double) * (size_t)n_clusters * n_cols);
+    if (e == cudaSuccess) e = cudaMalloc(&dO, sizeof(int) * n_cells);
+    if (e == cudaSuccess) e = cudaMalloc(&dF, sizeof(int) * first.size());
+    if (e == cudaSuccess) e = cudaMemcpy(dD, D, sizeof(double) * n_cells * n_cols, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dO, order.data(), sizeof(int) * n_cells, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dF, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        cluster_means_kernel<<<dim3((n_cols + 127) / 128, n_clusters), 128>>>(dD, n_cols, dO, dF, n_clusters, dM);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(means, dM, sizeof(double) * (size_t)n_clusters * n_cols, cudaMemcpyDeviceToHost);
+    cudaFree(dD); cudaFree(dM); cudaFree(dO); cudaFree(dF);
+    if (e != cudaSuccess) return fail(SCICONE_ERR_CUDA, "condense_clusters: %s", cudaGetErrorString(e));
+    return SCICONE_OK;
+}
+
 int scicone_test_lgamma(int32_t device, const double* x, int32_t n, double* out) {
     if (!x || !out || n <= 0) return fail(SCICONE_ERR_ARG, "test_lgamma: bad argument");
     int n_dev = 0;

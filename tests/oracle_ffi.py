@@ -172,3 +172,15 @@ def condense_matrix(D_bins, region_sizes):
     rc = L.orc_condense_matrix(_dp(D_bins), D_bins.shape[0], D_bins.shape[1], _ip(r), int(r.size), _dp(out))
     assert rc == 0
     return out
+
+
+def condense_clusters(D, assignments, n_clusters):
+    """orc_condense_clusters: the oracle's restatement of scripts/condense_clusters.py:28-38."""
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    a = np.ascontiguousarray(assignments, dtype=np.int32)
+    means = np.empty((n_clusters, D.shape[1]), dtype=np.float64)
+    sizes = np.empty(n_clusters, dtype=np.int32)
+    L = lib()
+    L.orc_condense_clusters.argtypes = [C.POINTER(C.c_double), C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    assert L.orc_condense_clusters(_dp(D), D.shape[0], D.shape[1], _ip(a), n_clusters, _dp(means), _ip(sizes)) == 0
+    return means, sizes

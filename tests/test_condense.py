@@ -85,3 +85,36 @@ def test_gpu_condense_config_scale_properties():
     again = condense_matrix(got, np.array([200], dtype=np.int32))
     assert np.array_equal(again[:, 0], bins.sum(axis=1))
     print("condense 10000 x 18000: kernel %.1f us, %.0f GB/s" % (us, bins.nbytes / us / 1e3))
+
+
+# ---- cluster condensation (reference scripts/condense_clusters.py:28-38; pyscicone scicone.py:331-335) -----------------
+def _cluster_golden():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "tutorial_clusters.npz"))
+    return z["regions"], z["assignments"], z["condensed"], z["cluster_sizes"]
+
+
+def test_oracle_cluster_means_match_reference_files():
+    """tests/golden/tutorial_clusters.npz: the reference's condensed matrix and cluster sizes of the tutorial data."""
+    from oracle_ffi import condense_clusters as oracle_clusters
+
+    regions, assign, condensed, sizes = _cluster_golden()
+    means, n = oracle_clusters(regions, assign, len(sizes))
+    assert np.array_equal(n, sizes)
+    assert np.array_equal(means, condensed)
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_means_bit_exact():
+    from oracle_ffi import condense_clusters as oracle_clusters
+    from scicone_b200.api import condense_clusters
+
+    regions, assign, condensed, sizes = _cluster_golden()
+    means, n = condense_clusters(regions, assign)
+    assert np.array_equal(n, sizes) and np.array_equal(means, condensed)
+    rng = np.random.default_rng(21)  # non-integer values, an empty cluster, ragged sizes
+    D = rng.normal(size=(5003, 37)) * 10.0 ** rng.integers(-5, 5, size=(5003, 37))
+    a = rng.integers(0, 40, size=5003).astype(np.int32)
+    a[a == 17] = 16
+    got, gn = condense_clusters(D, a, n_clusters=41)
+    want, wn = oracle_clusters(D, a, 41)
+    assert np.array_equal(gn, wn) and np.array_equal(got, want)
