@@ -340,7 +340,7 @@ def run_engine(args):
                     "accepted": host["accepted"], "rejected": host["rejected"], "gpu_launches": host["gpu_launches"],
                     "score_kernel_us_per_step": host["score_kernel_us"] / K, "build_kernel_us_per_step": host["build_kernel_us"] / K},
             "gpu_launches": int(launches_dev),
-            "roofline": {"bound": "hbm", "kernel": "score_proposals_kernel (+ build_increments_kernel, the K2 increments of long proposals)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "score_proposals_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "alg_bytes_per_launch": cnt_dev["alg_bytes"] / max(1, n_timed),
                          "avg_launch_us": kern_us / max(1, n_timed), "kernel_share_of_step": kern_us * 1e-3 / one_lane_ms,

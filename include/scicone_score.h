@@ -268,7 +268,7 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
  * launch is bracketed by CUDA events on the dataset's stream.
  */
 int scicone_set_profiling(scicone_dataset* ds, int32_t on);
-int scicone_last_kernel_time_us(scicone_dataset* ds, double* us); /* device time of the last launch's K1b + proposal kernel */
+int scicone_last_kernel_time_us(scicone_dataset* ds, double* us); /* device time of the last proposal kernel */
 int scicone_kernel_time_stats(scicone_dataset* ds, double* sum_us, uint64_t* n_timed, int32_t reset);
 int scicone_build_time_stats(scicone_dataset* ds, double* sum_us, uint64_t* n_timed); /* same for build_rows_kernel */
 int scicone_kernel_launches(scicone_dataset* ds, uint64_t* n);

@@ -51,7 +51,6 @@ enum : unsigned {
     TASK_PS_FAR = 8u,    // parent score from global memory, read one node ahead: the committed row of a subtree root's parent,
                          // or the row this thread wrote more than kScRing nodes ago
     TASK_BIG = 16u,      // more events than the staging buffer holds: read from global memory
-    TASK_X = 32u,        // long proposal: the increment comes as a row from K1b, the walk only adds it to the parent's score
     PROP_MAX = 1u,       // max scoring (Inference::max_scoring)
     PROP_OD = 2u,        // overdispersed likelihood (globals is_overdispersed)
     PROP_FULL = 4u,      // full table pass (Inference::compute_t_table): no committed state is read
@@ -76,18 +75,8 @@ struct alignas(16) DevTask {
     unsigned char flags;
     unsigned char parent_back;   // 1..kScRing: the parent is the task this many positions back (score still in registers)
     unsigned char pad[2];
-    const double* x_row;         // TASK_X: the node's increment score(node) - score(parent), built by K1b
-    double pad2;
 };
-static_assert(sizeof(DevTask) == 80, "DevTask is staged as five 16-byte pieces");
-constexpr int kTaskPieces = sizeof(DevTask) / 16;
-
-// K1b work item: the increment row of one task of a long proposal
-struct alignas(16) DevXItem {
-    unsigned blob_off;  // the proposal's blob inside the arena
-    unsigned task;      // task index
-    unsigned pad[2];
-};
+static_assert(sizeof(DevTask) == 64, "DevTask is staged as four 16-byte pieces");
 
 struct alignas(16) DevChunk {  // tasks [first_task, first_task + n_tasks) and events [ev_base, ev_base + n_ev) are staged together
     int first_task, n_tasks, ev_base, n_ev;
@@ -338,71 +327,6 @@ __global__ void __launch_bounds__(kBuildBlock, 4)
 }
 
 // ---------------------------------------------------------------------------------
-// K1b: increment rows of long proposals (full passes, nu proposals, large subtrees).  In the walk of the proposal kernel a
-// thread is alone with its cell, so a proposal of 50 nodes is a chain of 50 x ~150 dependent-ish instructions that no
-// amount of other warps shortens.  The increments score(node) - score(parent) do not depend on the walk: they are
-// evaluated here, one (task, cell) pair per thread slot, with exactly the operations and the order of
-// Tree::compute_score (Tree.h:177-238), and the walk only adds them up.  Runs after K1 (it reads the rows K1 built).
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBuildBlock, 4)
-    build_increments_kernel(const unsigned char* __restrict__ arena, unsigned off_xitems, int n_items, int blocks_per_row) {
-    const DevXItem* items = reinterpret_cast<const DevXItem*>(arena + off_xitems);
-    const int total = n_items * blocks_per_row;
-    for (int u = blockIdx.x; u < total; u += gridDim.x) {
-        const DevXItem it = items[u / blocks_per_row];
-        const unsigned char* blob = arena + it.blob_off;
-        const DevHeader& H = *reinterpret_cast<const DevHeader*>(blob);
-        const DevTask& tk = reinterpret_cast<const DevTask*>(blob + sizeof(DevHeader))[it.task];
-        const DevEvent* ev = reinterpret_cast<const DevEvent*>(blob + H.off_events) + tk.ev_begin;
-        const bool od = H.flags & PROP_OD;
-        const int ne = tk.n_ev;
-        const int j0 = (u % blocks_per_row) * (kBuildBlock * kBuildCells) + threadIdx.x;
-        double x[kBuildCells];
-        bool ok[kBuildCells];
-#pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) {
-            x[q] = 0.0;
-            ok[q] = j0 + q * kBuildBlock < H.n_cells;
-        }
-        for (int e = 0; e < ne; ++e) {
-            const double a = ev[e].a, b = ev[e].b;
-            double dn[kBuildCells], dp[kBuildCells];
-#pragma unroll
-            for (int q = 0; q < kBuildCells; ++q) {
-                const int j = j0 + q * kBuildBlock;
-                dn[q] = ok[q] ? __ldg(ev[e].row + j) : 0.0;
-                dp[q] = (od && ok[q]) ? __ldg(ev[e].row_p + j) : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < kBuildCells; ++q) {
-                if (od) {
-                    x[q] += dn[q] - dp[q];
-                    x[q] -= a;
-                    x[q] += b;
-                } else
-                    x[q] += dn[q] * a;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) {
-            const int j = j0 + q * kBuildBlock;
-            if (!ok[q]) continue;
-            if (od) {
-                x[q] += tk.lg_nz;
-                x[q] -= tk.lg_nzp;
-                x[q] -= __ldg(tk.g_row + j);
-                x[q] += __ldg(tk.gp_row + j);
-            } else {
-                const double S = __ldg(H.S + j);
-                x[q] -= S * tk.lg_nz;
-                x[q] += S * tk.lg_nzp;
-            }
-            const_cast<double*>(tk.x_row)[j] = x[q];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------
 // K2-K4: grid = (ceil(M / kCells), n_proposals), one THREAD per cell.  The arena starts with one 32-bit blob offset
 // per proposal.
 //
@@ -445,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
     const unsigned char* blob = arena + le.blob_off;
     const DevHeader& H = *reinterpret_cast<const DevHeader*>(blob);
     // first chunk: its records follow from the launch entry alone, so these copies go out together with the header reads
-    for (int q = threadIdx.x; q < (int)le.n_tasks0 * kTaskPieces; q += kThreads)
+    for (int q = threadIdx.x; q < (int)le.n_tasks0 * 4; q += kThreads)
         copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, blob + sizeof(DevHeader) + 16 * q);
     for (int q = threadIdx.x; q < (int)le.n_ev0 * 2; q += kThreads)
         copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, blob + le.ev_off0 + 16 * q);
@@ -484,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             const DevEvent* events = reinterpret_cast<const DevEvent*>(blob + H.off_events);
             // ---- stage the task and event records of this chunk
             __syncthreads();
-            for (int q = threadIdx.x; q < ck.n_tasks * kTaskPieces; q += kThreads)
+            for (int q = threadIdx.x; q < ck.n_tasks * 4; q += kThreads)
                 copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, reinterpret_cast<const unsigned char*>(tasks + ck.first_task) + 16 * q);
             for (int q = threadIdx.x; q < ck.n_ev * 2; q += kThreads)
                 copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, reinterpret_cast<const unsigned char*>(events + ck.ev_base) + 16 * q);
@@ -497,9 +421,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             const DevTask& tk = sm_task[t];
             const unsigned tf = tk.flags;
             double* col = &ring[(t % kDepth) * kSlots][tid];
-            if (tf & TASK_X) {
-                cp8(col, tk.x_row + j);
-            } else if (!(tf & TASK_ROOT)) {
+            if (!(tf & TASK_ROOT)) {
                 if (!(tf & TASK_BIG)) {
                     const DevEvent* ev = sm_ev + tk.ev_rel;
                     const int ne = tk.n_ev;
@@ -537,11 +459,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             const double* col = &ring[(t % kDepth) * kSlots][tid];
             double sc = 0.0;
             // ---- increment  score(node) - score(parent)   (Tree::compute_score, Tree.h:177-238)
-            if (tf & TASK_X) {  // long proposal: the increment was built by K1b (same operations, same order)
-                const int back = tk.parent_back;
-                const double ps = back == 1 ? s1 : back == 2 ? s2 : back == 3 ? s3 : back == 4 ? s4 : ps_far_cur;
-                sc = ps + col[0];
-            } else if (!(tf & TASK_ROOT)) {
+            if (!(tf & TASK_ROOT)) {
                 double x = 0.0;
                 const int ne = tk.n_ev;
                 const bool big = tf & TASK_BIG;  // more events than the staging buffer holds (rare): read from global memory

@@ -387,7 +387,6 @@ struct scicone_dataset {
 
 constexpr size_t kStashRefill = 32, kStashMax = 160;
 constexpr int kDefaultOcc = 7;
-constexpr int kXMinTasks = 16;  // from this many rescored nodes on, the increments of a proposal are built by K1b
 
 struct scicone_chain {
     scicone_dataset* ds = nullptr;
@@ -445,7 +444,6 @@ struct scicone_chain {
         stash.push_back(r);
         if (stash.size() > kStashMax) ds->pool.put_many(stash, kStashMax / 2);
     }
-    std::vector<int> x_tasks;  // tasks of the compiled proposal whose increments K1b builds
     LaunchEntry entry = {0u, 0u, 0u, 0u};  // first-chunk descriptor of the compiled blob (blob_off is filled in at submit)
     double cost = 0.0;  // relative device time of the compiled proposal (orders the blobs inside a launch)
 };
@@ -478,7 +476,6 @@ void drop_pending(scicone_chain* ch) {
     ch->pending = false;
     ch->compiled = false;
     ch->evaluated = false;
-    ch->x_tasks.clear();
     ch->deleted_id = -1;
     ch->p_full = false;
     for (double* r : ch->temp_rows) ch->row_put(r);
@@ -818,18 +815,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             tasks[i].gp_row = gp;
         }
     }
-    // Long proposals: the increments are built as rows by K1b and the walk only adds them up
-    ch->x_tasks.clear();
-    if (tasks.size() >= (size_t)kXMinTasks)
-        for (size_t i = 0; i < tasks.size(); ++i) {
-            if ((tasks[i].flags & TASK_ROOT) || tasks[i].n_ev > 64) continue;
-            double* row = nullptr;
-            CUDA_TRY(ch->row_get(&row));
-            ch->temp_rows.push_back(row);
-            tasks[i].x_row = row;
-            tasks[i].flags |= TASK_X;
-            ch->x_tasks.push_back((int)i);
-        }
     for (size_t i = 0; i < tasks.size(); ++i) {
         if (!(tasks[i].flags & TASK_ROOT)) {
             const int back = ptask[i] >= 0 ? (int)i - ptask[i] : 0;
@@ -949,7 +934,6 @@ int compile_od_only(scicone_chain* ch, double nu, int slot) {
     ch->n_scores = 0.0;
     ch->with_od = true;
     ch->entry = LaunchEntry{0u, 0u, 0u, 0u};
-    ch->x_tasks.clear();
     return SCICONE_OK;
 }
 
@@ -963,12 +947,9 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         n_items += chains[i]->builds.size();
         aux_bytes += round_up(chains[i]->build_aux.size() * sizeof(double), 16);
     }
-    size_t n_xitems = 0;
-    for (int i = 0; i < n; ++i) n_xitems += chains[i]->x_tasks.size();
     const size_t off_items = bytes;
     const size_t off_aux = off_items + n_items * sizeof(DevBuild);
-    const size_t off_xitems = off_aux + aux_bytes;
-    bytes = off_xitems + n_xitems * sizeof(DevXItem);
+    bytes = off_aux + aux_bytes;
     int rc = ds->ensure_arena(bytes);
     if (rc) return rc;
     const unsigned long long tk = ds->next_ticket;
@@ -1025,16 +1006,6 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         offs[q] = chains[order[q]]->entry;
         offs[q].blob_off = blob_at[order[q]];
     }
-    {
-        DevXItem* xi = reinterpret_cast<DevXItem*>(g.h_arena + off_xitems);
-        for (int i = 0; i < n; ++i)
-            for (int t : chains[i]->x_tasks) {
-                xi->blob_off = blob_at[i];
-                xi->task = (unsigned)t;
-                xi->pad[0] = xi->pad[1] = 0u;
-                ++xi;
-            }
-    }
     CUDA_TRY(cudaMemcpyAsync(d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, st));
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, st));
@@ -1045,18 +1016,8 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
     }
-    // timing: evb .. ev0 = K1 (every lgamma), ev0 .. ev1 = K1b + the proposal kernel, which together are the K2-K4 of the
-    // algorithmic-bytes accounting (increment, walk, aggregate, reduce)
-    if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, st));
-    if (n_xitems) {
-        const int blocks_per_row = (ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells);
-        const long long units = (long long)n_xitems * blocks_per_row;
-        build_increments_kernel<<<(unsigned)std::min<long long>(units, 4ll * ds->n_sm), kBuildBlock, 0, st>>>(
-            d_arena, (unsigned)off_xitems, (int)n_xitems, blocks_per_row);
-        CUDA_TRY(cudaGetLastError());
-        ds->n_launches++;
-    }
     g.n_items = (int)n_items;
+    if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, st));
     {   // scoring mode and likelihood are properties of the dataset: one specialisation per launch.  kOcc = CTAs per SM the
         // register allocation aims at (shared memory - the cp.async ring - allows 7); SCICONE_OCC overrides the default for tuning.
         static const int occ = [] {
