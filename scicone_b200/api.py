@@ -10,8 +10,10 @@ There is no CPU fallback: loading fails loudly if the CUDA library has not been 
 (``python -c 'import __graft_entry__ as g; g.build()'``) and every compute call raises
 ``SciconeError`` without a CUDA device.
 """
+import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -36,6 +38,18 @@ ABI_SYMBOLS = [
 ]
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}
+
+
+_LIVE = weakref.WeakSet()  # datasets still open: closed at interpreter exit while the CUDA context is alive
+
+
+@atexit.register
+def _close_all():
+    for ds in list(_LIVE):
+        try:
+            ds.close()
+        except Exception:
+            pass
 
 
 class SciconeError(RuntimeError):
@@ -163,10 +177,14 @@ class Dataset:
         self.max_scoring = int(max_scoring)
         self.is_overdispersed = int(is_overdispersed)
         self._h = C.c_void_p()
+        self._chains = weakref.WeakSet()  # chains are destroyed before their dataset, whatever the finalisation order
         _check(lib().scicone_dataset_create(C.byref(self._h), C.byref(desc)))
+        _LIVE.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
+            for ch in list(getattr(self, "_chains", ())):
+                ch.close()
             lib().scicone_dataset_destroy(self._h)
             self._h = None
 
@@ -238,10 +256,12 @@ class Chain:
         self.max_scoring = self.ds.max_scoring
         self._h = C.c_void_p()
         _check(lib().scicone_chain_create(C.byref(self._h), self.ds._h))
+        self.ds._chains.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().scicone_chain_destroy(self._h)
+            if getattr(self.ds, "_h", None):  # a dataset that is already gone took its chains with it
+                lib().scicone_chain_destroy(self._h)
             self._h = None
         if self._own and self.ds is not None:
             self.ds.close()
