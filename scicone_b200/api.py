@@ -182,7 +182,8 @@ class Dataset:
         _LIVE.add(self)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and not getattr(self, "_closing", False):
+            self._closing = True  # a chain that owns this dataset calls back into close()
             for ch in list(getattr(self, "_chains", ())):
                 ch.close()
             lib().scicone_dataset_destroy(self._h)
