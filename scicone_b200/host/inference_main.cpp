@@ -204,8 +204,10 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         if (!learn_nu && !a.has("nu") && a.has("tree_file")) P.is_overdispersed = 0;
 
         // this rank's block of cells (chunk aligned so that totals do not depend on the number of GPUs)
+        // --no_shard (tests): several host processes with the ownership protocol but every one holding all the cells
+        const bool no_shard = a.has("no_shard");
         long lo = 0, hi = n_cells;
-        if (world > 1) {
+        if (world > 1 && !no_shard) {
             const long chunk = 1024, n_chunks = (n_cells + chunk - 1) / chunk;
             const long base = n_chunks / world, extra = n_chunks % world;
             long c0 = 0;
@@ -232,7 +234,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         desc.n_cells_global = n_cells;
         scicone_dataset* ds = nullptr;
         abi_check(scicone_dataset_create(&ds, &desc));
-        if (world > 1) {
+        if (world > 1 && !no_shard) {
             uint8_t id[128];
             hex_to_bytes(a.str("nccl_id"), id, 128);
             abi_check(scicone_dataset_attach_comm(ds, id, rank, world));
@@ -272,6 +274,17 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         }
 
         if (P.verbosity > 0) std::cout << "Inferring the tree using MCMC with " << n_iters << " iterations..." << std::endl;
+        // cell-sharded run: every chain's tree search runs on one rank, the others follow it through a shared-memory
+        // mailbox (mcmc.hpp).  --shm_name names the segment; by default it is derived from the NCCL id of the run.
+        std::unique_ptr<Mailbox> mailbox;
+        if (world > 1 && !a.has("replicated_host")) {
+            std::string shm = a.str("shm_name");
+            if (shm.empty() && a.has("nccl_id")) shm = "/scicone_" + a.str("nccl_id").substr(0, 24);
+            if (shm.empty()) throw std::runtime_error("--shm_name is needed for a multi-process run without --nccl_id");
+            if (shm[0] != '/') shm = "/" + shm;
+            mailbox.reset(new Mailbox());
+            mailbox->open(shm, n_chains, rank == 0);
+        }
         HostPhaseTimes phase;
         // schedule: "dynamic" (default for several chains on one GPU) launches whatever is ready; "static" moves groups of
         // chains in lock-step and is what cell-sharded runs need (every rank must issue the same launches)
@@ -281,7 +294,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
                 infer_mcmc_dynamic(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("min_batch", 0)), t,
                                    static_cast<int>(a.integer("n_streams", 2)));
             else
-                infer_mcmc(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("n_groups", 0)), t);
+                infer_mcmc(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("n_groups", 0)), t, rank, world, mailbox.get());
         };
         const int warmup_iters = static_cast<int>(a.integer("warmup_iters", 0));
         if (warmup_iters > 0) {  // untimed iterations before the measured run (bench.py); the chains simply continue afterwards
@@ -337,9 +350,17 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         }
 
         if (P.verbosity > 0) std::cout << "Writing the inferred tree and cnvs..." << std::endl;
-        for (Inference* inf : chains) {
-            if (world > 1 && rank != 0 && !a.has("write_all_ranks")) {
-                // every rank must still take part in the full pass below (collective), but only rank 0 writes files
+        for (size_t ci = 0; ci < chains.size(); ++ci) {
+            Inference* inf = chains[ci];
+            if (world > 1) {
+                // cell-sharded run: the owner of a chain writes its tree; per-cell outputs would have to be merged over the
+                // ranks and are not produced here
+                const bool owner = mailbox ? static_cast<int>(ci) % world == rank : rank == 0;
+                if (owner) {
+                    std::ofstream f_tree("./" + inf->P.postfix + "_tree_inferred.txt");
+                    inf->best_tree.write(f_tree);
+                }
+                continue;
             }
             // Inference::assign_cells_to_nodes, Inference.h:1311-1377
             inf->t.copy_from(inf->best_tree);
@@ -347,7 +368,6 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
             const int M = desc.n_cells;
             std::vector<int32_t> ids(M), cn(static_cast<size_t>(M) * n_regions);
             abi_check(scicone_assign_cells_to_nodes(inf->chain, &inf->flat.pod, ids.data(), cn.data()));
-            if (world > 1) continue;  // sharded runs report the tree; per-cell outputs are per rank and not merged here
             const std::string& pf = inf->P.postfix;
             if (P.verbosity > 1) {
                 std::ofstream f_ids(pf + "_cell_node_ids.tsv"), f_cn(pf + "_cell_region_cnvs.csv");
@@ -399,11 +419,6 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
                 }
             }
         }
-        if (world > 1 && rank == 0)
-            for (Inference* inf : chains) {
-                std::ofstream f_tree("./" + inf->P.postfix + "_tree_inferred.txt");
-                inf->best_tree.write(f_tree);
-            }
         owned.clear();
         scicone_dataset_destroy(ds);
         if (P.verbosity > 0) std::cout << "Tree inference is successfully completed!" << std::endl;

@@ -15,6 +15,10 @@
 #include <chrono>
 #include <atomic>
 #include <cstring>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <deque>
 #include <iostream>
 #include <thread>
@@ -189,6 +193,7 @@ public:
     void queue(int node) {
         if (!queued) flat.build(t_prime);
         abi_check(scicone_compute_t_prime_scores(chain, &flat.pod, flat.index_of_node[node]));
+        queued_roots.push_back(flat.index_of_node[node]);
         queued = true;
     }
     bool attempt(unsigned size_limit) {
@@ -257,6 +262,7 @@ public:
     bool propose(const std::vector<float>& move_probs, unsigned size_limit) {
         move_id = static_cast<unsigned>(rng.discrete(move_probs.begin(), move_probs.end()));
         queued = false;
+        queued_roots.clear();
         nu_move = false;
         if (move_id == 10) return false;  // handled entirely on the host in finish()
         for (unsigned a = 0; a < 50; ++a) {  // Inference::apply_multiple_times, Inference.h:1462-1498
@@ -282,6 +288,7 @@ public:
             scicone_reject(chain);
             queued = false;
         }
+        queued_roots.clear();
     }
 
     // Inference::comparison (Inference.h:285-516) given the weighted total of t_prime from the device.
@@ -385,6 +392,7 @@ public:
         const int m = n_cells;
         Tree* accepted = &t;
         if (move_id == 10) {  // Gibbs move on the committed tree (Inference.h:731-757)
+            last_decision = -1;
             bool ok = true;
             try {
                 t.genotype_preserving_prune_reattach(gamma);
@@ -403,6 +411,7 @@ public:
             }
         } else {
             bool take = false;
+            last_decision = -1;
             if (scored) {
                 if (nu_move) t_prime.od_score = od;
                 n_rescored_nodes += rescored_last;
@@ -413,6 +422,7 @@ public:
                 }
             }
             const double score_diff = t_prime.posterior_score - t.posterior_score;
+            if (scored) last_decision = take ? 1 : 0;
             if (take) {
                 accepted = &t_prime;
                 if (move_id != 13 && std::abs(score_diff) > 0.1) gamma *= std::exp((1.0 - alpha) * alpha);
@@ -452,6 +462,10 @@ public:
         }
     }
     unsigned rescored_last = 0;
+    std::vector<int32_t> queued_roots;  // entries of flat (the compiled t_prime) queued for rescoring by the current proposal
+    int last_decision = -1;             // outcome of the last scored proposal: 1 accepted, 0 rejected, -1 nothing was scored
+    uint64_t msg_seq = 0;               // cell-sharded runs: messages published (owner) / consumed (follower) for this chain
+    std::vector<unsigned char> msg_buf;
 
     void open_traces(int n_iters) {  // Inference.h:532-538
         n_iters_total = n_iters;
@@ -467,6 +481,152 @@ public:
         if (tracing) f_acc << std::setprecision(P.print_precision) << id << ((iter == n_iters_total - 1) ? "" : ",");
     }
 };
+
+// Cell-sharded runs (one host process per GPU on one node): every chain has ONE owner rank that runs its tree search;
+// the other ranks only need the proposal it drew (to queue and compile it against their own shard's tables) and, one
+// visit later, whether it was accepted.  Both travel through a shared-memory mailbox, one slot per chain: the owner
+// writes the payload and then bumps the sequence number, followers wait for the number they expect.  A slot is not
+// overwritten before every rank has read it: the next message of a chain is only written after the launch that scored
+// the previous one came back, and that launch contains a collective all ranks take part in.
+class Mailbox {
+public:
+    static constexpr size_t kSlotBytes = 1u << 20;
+    struct Slot {
+        std::atomic<uint64_t> seq;
+        uint32_t bytes;
+        uint32_t pad;
+        unsigned char payload[kSlotBytes - 16];
+    };
+    ~Mailbox() {
+        if (base_) munmap(base_, map_bytes_);
+        if (owner_ && !name_.empty()) shm_unlink(name_.c_str());
+    }
+    void open(const std::string& name, int n_chains, bool unlink_at_exit) {
+        name_ = name;
+        owner_ = unlink_at_exit;
+        map_bytes_ = sizeof(Slot) * static_cast<size_t>(n_chains);
+        int fd = shm_open(name.c_str(), O_CREAT | O_RDWR, 0600);
+        if (fd < 0) throw std::runtime_error("shm_open(" + name + ") failed");
+        if (ftruncate(fd, static_cast<off_t>(map_bytes_)) != 0) {
+            close(fd);
+            throw std::runtime_error("ftruncate on the mailbox failed");
+        }
+        base_ = mmap(nullptr, map_bytes_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (base_ == MAP_FAILED) {
+            base_ = nullptr;
+            throw std::runtime_error("mmap of the mailbox failed");
+        }
+        slots_ = static_cast<Slot*>(base_);  // a fresh segment is zero filled: seq = 0
+    }
+    void publish(int chain, uint64_t seq, const std::vector<unsigned char>& msg) {
+        Slot& s = slots_[chain];
+        if (msg.size() > sizeof(s.payload)) throw std::runtime_error("proposal too large for the mailbox slot");
+        std::memcpy(s.payload, msg.data(), msg.size());
+        s.bytes = static_cast<uint32_t>(msg.size());
+        s.seq.store(seq, std::memory_order_release);
+    }
+    const unsigned char* receive(int chain, uint64_t seq, uint32_t* bytes) {
+        Slot& s = slots_[chain];
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while (s.seq.load(std::memory_order_acquire) < seq) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((++spins & 0xffffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
+                throw std::runtime_error("timed out waiting for the owner of chain " + std::to_string(chain));
+        }
+        *bytes = s.bytes;
+        return s.payload;
+    }
+
+private:
+    std::string name_;
+    bool owner_ = false;
+    void* base_ = nullptr;
+    size_t map_bytes_ = 0;
+    Slot* slots_ = nullptr;
+};
+
+// message = {u8 has_decision, u8 accept, u8 scored, u8 pad, i32 n_roots, [tree, roots]}
+inline void pack_message(const Inference& c, bool scored, std::vector<unsigned char>& out) {
+    auto put = [&](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        out.insert(out.end(), b, b + n);
+    };
+    out.clear();
+    const unsigned char head[4] = {static_cast<unsigned char>(c.last_decision >= 0), static_cast<unsigned char>(c.last_decision == 1),
+                                   static_cast<unsigned char>(scored), 0};
+    put(head, 4);
+    const int32_t n_roots = scored ? static_cast<int32_t>(c.queued_roots.size()) : 0;
+    put(&n_roots, 4);
+    if (!scored) return;
+    const scicone_tree& t = c.flat.pod;
+    const int32_t n = t.n_nodes, n_chg = t.chg_off[n], n_gen = t.gen_off[n];
+    const int32_t dims[4] = {n, n_chg, n_gen, 0};
+    put(dims, 16);
+    put(&t.nu, 8);
+    put(t.node_id, 4 * n);
+    put(t.parent, 4 * n);
+    put(t.chg_off, 4 * (n + 1));
+    put(t.gen_off, 4 * (n + 1));
+    put(t.chg_region, 4 * n_chg);
+    put(t.chg_value, 4 * n_chg);
+    put(t.gen_region, 4 * n_gen);
+    put(t.gen_value, 4 * n_gen);
+    put(c.queued_roots.data(), 4 * n_roots);
+}
+
+// follower side: settle the previous proposal of the chain, queue and compile the next one; returns its `scored` flag
+inline bool apply_message(Inference& c, const unsigned char* p, uint32_t bytes) {
+    if (bytes < 8) throw std::runtime_error("short mailbox message");
+    const bool has_decision = p[0] != 0, accept = p[1] != 0, scored = p[2] != 0;
+    int32_t n_roots;
+    std::memcpy(&n_roots, p + 4, 4);
+    if (has_decision) abi_check(accept ? scicone_accept(c.chain) : scicone_reject(c.chain));
+    if (!scored) return false;
+    const unsigned char* q = p + 8;
+    int32_t dims[4];
+    std::memcpy(dims, q, 16);
+    q += 16;
+    const int32_t n = dims[0], n_chg = dims[1], n_gen = dims[2];
+    // the arrays are copied out: the payload is only 4-byte aligned and lives in shared memory
+    FlatTree& f = c.flat;
+    double nu;
+    std::memcpy(&nu, q, 8);
+    q += 8;
+    auto take = [&](std::vector<int32_t>& v, size_t count) {
+        v.resize(count + 1);
+        std::memcpy(v.data(), q, 4 * count);
+        q += 4 * count;
+    };
+    take(f.id, n);
+    take(f.parent, n);
+    take(f.chg_off, n + 1);
+    take(f.gen_off, n + 1);
+    take(f.chg_region, n_chg);
+    take(f.chg_value, n_chg);
+    take(f.gen_region, n_gen);
+    take(f.gen_value, n_gen);
+    f.pod.n_nodes = n;
+    f.pod.node_id = f.id.data();
+    f.pod.parent = f.parent.data();
+    f.pod.chg_off = f.chg_off.data();
+    f.pod.chg_region = f.chg_region.data();
+    f.pod.chg_value = f.chg_value.data();
+    f.pod.gen_off = f.gen_off.data();
+    f.pod.gen_region = f.gen_region.data();
+    f.pod.gen_value = f.gen_value.data();
+    f.pod.nu = nu;
+    for (int32_t r = 0; r < n_roots; ++r) {
+        int32_t idx;
+        std::memcpy(&idx, q + 4 * r, 4);
+        abi_check(scicone_compute_t_prime_scores(c.chain, &f.pod, idx));
+    }
+    abi_check(scicone_prepare_t_prime(c.chain));
+    return true;
+}
 
 // fn(i) for i in [0, n) on the scoring library's worker pool; the first exception is rethrown on the caller.
 template <class F>
@@ -500,7 +660,7 @@ struct HostPhaseTimes {  // wall time of the driver thread per phase, microsecon
 };
 
 inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
-                       int n_groups = 0, HostPhaseTimes* times = nullptr) {
+                       int n_groups = 0, HostPhaseTimes* times = nullptr, int rank = 0, int world = 1, Mailbox* mailbox = nullptr) {
     typedef std::chrono::steady_clock Clock;
     auto us_since = [](Clock::time_point t0) { return std::chrono::duration<double, std::micro>(Clock::now() - t0).count(); };
     HostPhaseTimes local_times;
@@ -552,7 +712,11 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
         }
         T.wait_us += us_since(t0);
         t0 = Clock::now();
+        // Cell-sharded run with a mailbox: a chain's tree search runs on its owner rank only.  Owned chains first (nobody
+        // waits for anybody), then the followers of the other ranks' chains.
+        auto owned = [&](int b) { return mailbox == nullptr || b % world == rank; };
         parallel_chains(n, [&](int i) {
+            if (!owned(g.members[i])) return;
             Inference* c = chains[g.members[i]];
             const Clock::time_point c0 = Clock::now();
             Clock::time_point c1 = c0, c2 = c0;
@@ -564,11 +728,18 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
                 }
                 c->finish(g.scored[i] != 0, g.tot_m[i], g.od_m[i], it - 1);
                 c1 = c2 = Clock::now();
-            }
+            } else
+                c->last_decision = -1;
             if (it < n_iters) {
                 g.scored[i] = c->propose(move_probs, size_limit) ? 1 : 0;
                 c2 = Clock::now();
                 if (g.scored[i]) abi_check(scicone_prepare_t_prime(c->chain));
+            } else
+                g.scored[i] = 0;
+            if (mailbox) {  // the decision about the previous proposal and the next proposal, in one message
+                std::vector<unsigned char>& msg = c->msg_buf;
+                pack_message(*c, g.scored[i] != 0, msg);
+                mailbox->publish(g.members[i], ++c->msg_seq, msg);
             }
             const Clock::time_point c3 = Clock::now();
             auto us = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
@@ -577,6 +748,14 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
             c->t_prepare_us += us(c2, c3);
             c->t_max_visit_us = std::max(c->t_max_visit_us, us(c0, c3));
         });
+        if (mailbox)
+            parallel_chains(n, [&](int i) {
+                if (owned(g.members[i])) return;
+                Inference* c = chains[g.members[i]];
+                uint32_t bytes = 0;
+                const unsigned char* msg = mailbox->receive(g.members[i], ++c->msg_seq, &bytes);
+                g.scored[i] = apply_message(*c, msg, bytes) ? 1 : 0;
+            });
         T.host_us += us_since(t0);
         if (it >= n_iters) return;
         t0 = Clock::now();

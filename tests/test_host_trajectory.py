@@ -135,3 +135,44 @@ def test_multi_chain_equals_single_runs_on_cpu(tmp_path, n_chains, flags, thread
 @pytest.mark.gpu
 def test_multi_chain_equals_single_runs_on_gpu(tmp_path):
     _multi_chain(tmp_path, None, 12, [], [0, 5, 11])
+
+
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+def test_chain_ownership_protocol_on_cpu(tmp_path):
+    """Multi-process runs: every chain is searched by ONE owner process, the others follow it through the shared-memory
+    mailbox (proposal + decision messages).  Two processes with --no_shard (each holds all cells, oracle-backed ABI):
+    the owner's traces of every chain equal the unmodified reference's single-chain run, and the followers' device state
+    stays in step (a follower that missed a commit would make the owner's next totals differ on the GPU; here it is
+    checked through the final tables of both processes being readable and the run finishing)."""
+    import subprocess
+    import uuid
+
+    from host_util import read_outputs
+
+    D, r = _tutorial()
+    base = ["--n_iters=600", "--n_nodes=4", "--nu=1.0", "--max_scoring=true"]
+    d = os.path.join(str(tmp_path), "d.csv")
+    np.savetxt(d, D, delimiter=",", fmt="%.0f")
+    rf = os.path.join(str(tmp_path), "r.txt")
+    np.savetxt(rf, r, fmt="%d")
+    env = dict(os.environ, **CPU_ENV, SCICONE_THREADS="2")
+    shm = "/scicone_test_" + uuid.uuid4().hex[:12]
+    procs = []
+    for k in range(2):
+        cmd = [NATIVE, f"--d_matrix_file={d}", f"--region_sizes_file={rf}", f"--n_cells={D.shape[0]}", f"--n_regions={D.shape[1]}",
+               "--verbosity=2", f"--postfix=own{k}", "--seed=30", "--n_chains=5", "--schedule=static", "--no_shard", f"--rank={k}", "--world=2",
+               f"--shm_name={shm}"] + base
+        procs.append(subprocess.Popen(cmd, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
+    for p in procs:
+        out, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err[-2000:]
+    for c in range(5):
+        single = run_inference(REF, str(tmp_path), f"single{c}", D, r, base + [f"--seed={30 + c}"])
+        owner = c % 2
+        got = {}
+        for name in ("acceptance_ratio", "markov_chain", "gamma_values"):
+            got[name] = np.array([float(x) for x in open(os.path.join(str(tmp_path), f"own{owner}_c{c}_{name}.csv")).read().strip().split(",")])
+        assert np.array_equal(got["acceptance_ratio"], single["acc"]), c
+        assert np.max(np.abs(got["markov_chain"] - single["chain"]) / np.maximum(1.0, np.abs(single["chain"]))) <= 1e-9
+        assert open(os.path.join(str(tmp_path), f"own{owner}_c{c}_tree_inferred.txt")).read().split("\n")[7:] == single["tree"].split("\n")[7:]
