@@ -247,7 +247,7 @@ int scicone_test_lgamma(int32_t device, const double* x, int32_t n, double* out)
  * SURVEY.md section 8b).  The per-chain calls above - scicone_compute_t_prime_scores, scicone_accept,
  * scicone_reject, scicone_t_prime_n_rescored - may be issued concurrently for DIFFERENT chains of one dataset, so
  * a multi-chain host draws, queues and commits its chains inside this loop and launches from the calling thread;
- * scicone_batch_submit compiles its n proposals on the same pool.  Pool size: SCICONE_THREADS, else cores - 1 (<= 16).
+ * scicone_batch_submit compiles its n proposals on the same pool.  Pool size: SCICONE_THREADS, else the cores (<= 16).
  */
 int scicone_parallel_for(int32_t n, void (*fn)(int32_t index, void* ctx), void* ctx);
 int scicone_host_threads(void);

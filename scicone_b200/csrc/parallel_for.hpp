@@ -56,7 +56,7 @@ private:
         int n = 0;
         if (const char* e = std::getenv("SCICONE_THREADS")) n = std::atoi(e);
         if (n <= 0) {
-            n = (int)std::thread::hardware_concurrency() - 1;  // the workers spin between steps: leave a core to the rest of the box
+            n = (int)std::thread::hardware_concurrency();
             if (n > 16) n = 16;
         }
         if (n < 1) n = 1;
