@@ -51,7 +51,6 @@ enum : unsigned {
     TASK_PS_FAR = 8u,    // parent score from global memory, read one node ahead: the committed row of a subtree root's parent,
                          // or the row this thread wrote more than kScRing nodes ago
     TASK_BIG = 16u,      // more events than the staging buffer holds: read from global memory
-    TASK_X = 32u,        // proposal that changes nu: the whole increment is one K1 row (BUILD_X), the walk only adds it up
     PROP_MAX = 1u,       // max scoring (Inference::max_scoring)
     PROP_OD = 2u,        // overdispersed likelihood (globals is_overdispersed)
     PROP_FULL = 4u,      // full table pass (Inference::compute_t_table): no committed state is read
@@ -60,7 +59,6 @@ enum : unsigned {
     PROP_OD_ONLY = 32u,  // no tasks, no aggregate: only the root score
     BUILD_OD_SLICE = 1u,
     BUILD_OD_SLICE_LOG = 2u,  // non-overdispersed root score slice: sum_k D_k log r_k
-    BUILD_X = 4u,             // increment row of a TASK_X task: every lgamma of Tree::compute_score for one node
     BUILD_G = 3u              // dst = lgamma(src + c1): lgamma rows L(k, cn) (src = Dt[k]) and z-term rows (src = S)
 };
 
@@ -68,15 +66,8 @@ struct alignas(16) DevTask {
     double* dst;                 // score row being written
     const double* parent_row;    // TASK_PS_FAR: where the parent's score lives in global memory
     double lg_nz, lg_nzp;        // OD: lgamma(nu*z), lgamma(nu*z_parent);  non-OD: log(z), log(z_parent)
-    union {
-        struct {
-            const double* g_row;   // OD: z-term row lgamma(S + nu*z) built by K1
-            const double* gp_row;  // OD: z-term row lgamma(S + nu*z_parent) (the parent task's g_row when the arguments are equal)
-        };
-        struct {                   // TASK_X: the z-terms are evaluated by K1 inside the increment
-            double nz, nzp;        // nu*z, nu*z_parent
-        };
-    };
+    const double* g_row;         // OD: z-term row lgamma(S + nu*z) built by K1
+    const double* gp_row;        // OD: z-term row lgamma(S + nu*z_parent) (the parent task's g_row when the arguments are equal)
     int ev_begin;                // first event record (index into the proposal's event array)
     int node_id;
     unsigned short n_ev;         // number of event records (Node::c_change entries)
@@ -84,19 +75,8 @@ struct alignas(16) DevTask {
     unsigned char flags;
     unsigned char parent_back;   // 1..kScRing: the parent is the task this many positions back (score still in registers)
     unsigned char pad[2];
-    const double* x_row;         // TASK_X: the node's increment score(node) - score(parent), built by K1 (BUILD_X)
-    double pad2;
 };
-static_assert(sizeof(DevTask) == 80, "DevTask is staged as five 16-byte pieces");
-constexpr int kTaskPieces = sizeof(DevTask) / 16;
-
-// Event of a TASK_X task (proposals that change nu: no lgamma row exists at the proposed nu and none is built)
-struct alignas(16) DevXEvent {
-    const double* src;   // Dt[k]
-    double arg_n, arg_p; // (nu*cn_node)*r_k, (nu*cn_parent)*r_k
-    double a, b;         // lgamma(arg_n), lgamma(arg_p)
-    double pad;
-};
+static_assert(sizeof(DevTask) == 64, "DevTask is staged as four 16-byte pieces");
 
 struct alignas(16) DevChunk {  // tasks [first_task, first_task + n_tasks) and events [ev_base, ev_base + n_ev) are staged together
     int first_task, n_tasks, ev_base, n_ev;
@@ -143,8 +123,7 @@ struct alignas(16) DevHeader {
     unsigned* status;     // bit 0: NaN aggregate
     double od_lg_nz, od_nz;  // OD: lgamma(nu*z_root), nu*z_root;  non-OD: od_lg_nz = log(sum_r)
     unsigned off_tasks, off_events, off_old, off_unch, off_od_rows, off_chunks;
-    unsigned off_xevents;            // DevXEvent records of the TASK_X tasks
-    unsigned pad4;
+    const double* pad4;
     const double* od_g_row;          // PROP_WITH_OD, OD: row lgamma(S + nu*z_root) built by K1
 };
 
@@ -286,49 +265,6 @@ __device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned c
         if (ok[q]) it.dst[j0 + q * kBuildBlock] = acc[q];
 }
 
-// The increment score(node) - score(parent) of one node of a proposal that changes nu, for kBuildCells cells: every
-// lgamma of Tree::compute_score (Tree.h:214-231) evaluated in place, operations in the reference's order.  No lgamma row
-// exists at the proposed nu, and none is written: rows are only worth their bytes once the proposal has been accepted
-// (then they are built on first use, as after any change of nu).  it.off_arg = the proposal's blob, it.k0 = task index.
-__device__ __forceinline__ void build_increment(const DevBuild& it, const unsigned char* __restrict__ arena, int j0, const double* tbl) {
-    const unsigned char* blob = arena + it.off_arg;
-    const DevHeader& H = *reinterpret_cast<const DevHeader*>(blob);
-    const DevTask& tk = reinterpret_cast<const DevTask*>(blob + sizeof(DevHeader))[it.k0];
-    const DevXEvent* ev = reinterpret_cast<const DevXEvent*>(blob + H.off_xevents) + tk.ev_begin;
-    const int ne = tk.n_ev;
-    double x[kBuildCells];
-    bool ok[kBuildCells];
-#pragma unroll
-    for (int q = 0; q < kBuildCells; ++q) {
-        x[q] = 0.0;
-        ok[q] = j0 + q * kBuildBlock < it.n_cells;
-    }
-    for (int e = 0; e < ne; ++e) {
-        const double an = ev[e].arg_n, ap = ev[e].arg_p, a = ev[e].a, b = ev[e].b;
-        const double* row = ev[e].src + j0;
-        double d[kBuildCells];
-#pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) d[q] = ok[q] ? __ldg(row + q * kBuildBlock) : 32.0;
-#pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) {
-            x[q] += lgam(d[q] + an, tbl) - lgam(d[q] + ap, tbl);
-            x[q] -= a;
-            x[q] += b;
-        }
-    }
-    double S[kBuildCells];
-#pragma unroll
-    for (int q = 0; q < kBuildCells; ++q) S[q] = ok[q] ? __ldg(H.S + j0 + q * kBuildBlock) : 32.0;
-#pragma unroll
-    for (int q = 0; q < kBuildCells; ++q) {
-        x[q] += tk.lg_nz;
-        x[q] -= tk.lg_nzp;
-        x[q] -= lgam(S[q] + tk.nz, tbl);
-        x[q] += lgam(S[q] + tk.nzp, tbl);
-        if (ok[q]) const_cast<double*>(tk.x_row)[j0 + q * kBuildBlock] = x[q];
-    }
-}
-
 // ---------------------------------------------------------------------------------
 // K1: data-only lgamma work.  Persistent grid (up to 4 CTAs per SM) over n_items x ceil(M / (kBuildBlock * kBuildCells)) units.
 // ---------------------------------------------------------------------------------
@@ -385,9 +321,7 @@ __global__ void __launch_bounds__(kBuildBlock, 4)
                 const int j = j0 + q * kBuildBlock;
                 if (j < n_cells) dst[j] = lgam(d[q] + c1, tbl);
             }
-        } else if (kind == BUILD_X)
-            build_increment(items[cur / blocks_per_row], arena, j0, tbl);
-        else
+        } else
             build_slice(items[cur / blocks_per_row], arena, j0, tbl);
     }
 }
@@ -435,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
     const unsigned char* blob = arena + le.blob_off;
     const DevHeader& H = *reinterpret_cast<const DevHeader*>(blob);
     // first chunk: its records follow from the launch entry alone, so these copies go out together with the header reads
-    for (int q = threadIdx.x; q < (int)le.n_tasks0 * kTaskPieces; q += kThreads)
+    for (int q = threadIdx.x; q < (int)le.n_tasks0 * 4; q += kThreads)
         copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, blob + sizeof(DevHeader) + 16 * q);
     for (int q = threadIdx.x; q < (int)le.n_ev0 * 2; q += kThreads)
         copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, blob + le.ev_off0 + 16 * q);
@@ -474,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             const DevEvent* events = reinterpret_cast<const DevEvent*>(blob + H.off_events);
             // ---- stage the task and event records of this chunk
             __syncthreads();
-            for (int q = threadIdx.x; q < ck.n_tasks * kTaskPieces; q += kThreads)
+            for (int q = threadIdx.x; q < ck.n_tasks * 4; q += kThreads)
                 copy16(reinterpret_cast<unsigned char*>(sm_task) + 16 * q, reinterpret_cast<const unsigned char*>(tasks + ck.first_task) + 16 * q);
             for (int q = threadIdx.x; q < ck.n_ev * 2; q += kThreads)
                 copy16(reinterpret_cast<unsigned char*>(sm_ev) + 16 * q, reinterpret_cast<const unsigned char*>(events + ck.ev_base) + 16 * q);
@@ -487,9 +421,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             const DevTask& tk = sm_task[t];
             const unsigned tf = tk.flags;
             double* col = &ring[(t % kDepth) * kSlots][tid];
-            if (tf & TASK_X) {
-                cp8(col, tk.x_row + j);
-            } else if (!(tf & TASK_ROOT)) {
+            if (!(tf & TASK_ROOT)) {
                 if (!(tf & TASK_BIG)) {
                     const DevEvent* ev = sm_ev + tk.ev_rel;
                     const int ne = tk.n_ev;
@@ -527,11 +459,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
             const double* col = &ring[(t % kDepth) * kSlots][tid];
             double sc = 0.0;
             // ---- increment  score(node) - score(parent)   (Tree::compute_score, Tree.h:177-238)
-            if (tf & TASK_X) {  // nu proposal: the increment was built by K1 (same operations, same order)
-                const int back = tk.parent_back;
-                const double ps = back == 1 ? s1 : back == 2 ? s2 : back == 3 ? s3 : back == 4 ? s4 : ps_far_cur;
-                sc = ps + col[0];
-            } else if (!(tf & TASK_ROOT)) {
+            if (!(tf & TASK_ROOT)) {
                 double x = 0.0;
                 const int ne = tk.n_ev;
                 const bool big = tf & TASK_BIG;  // more events than the staging buffer holds (rare): read from global memory

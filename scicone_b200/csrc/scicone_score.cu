@@ -423,7 +423,6 @@ struct scicone_chain {
         std::vector<int> child_off, child, fill, ptask, task_of_node, stack;
         std::vector<DevTask> tasks;
         std::vector<DevEvent> events;
-        std::vector<DevXEvent> xevents;
         std::vector<const double*> prow, old_rows, g_of_task;
         std::vector<double> nz, nzp;
         std::vector<char> shares;
@@ -445,7 +444,6 @@ struct scicone_chain {
         stash.push_back(r);
         if (stash.size() > kStashMax) ds->pool.put_many(stash, kStashMax / 2);
     }
-    std::vector<int> x_tasks;  // tasks of the compiled proposal whose increments K1 builds (BUILD_X)
     LaunchEntry entry = {0u, 0u, 0u, 0u};  // first-chunk descriptor of the compiled blob (blob_off is filled in at submit)
     double cost = 0.0;  // relative device time of the compiled proposal (orders the blobs inside a launch)
 };
@@ -478,7 +476,6 @@ void drop_pending(scicone_chain* ch) {
     ch->pending = false;
     ch->compiled = false;
     ch->evaluated = false;
-    ch->x_tasks.clear();
     ch->deleted_id = -1;
     ch->p_full = false;
     for (double* r : ch->temp_rows) ch->row_put(r);
@@ -613,15 +610,9 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     const TreeCopy& T = ch->tp;
     const double nu = T.nu;
     const bool od = ds->od;
-    // A proposal that changes nu finds no lgamma row at its nu.  Building them (one row per (region, copy number) of the
-    // tree) would cost more bytes than the proposal itself and half of them are thrown away with a rejection: its
-    // increments are evaluated as one K1 row per node instead (BUILD_X), and rows at the new nu are only built once it has
-    // been accepted, on first use.
-    const bool fused = od && !full && nu != ch->t_nu;
-    LCache* L = (od && !fused) ? cache_for(ch, nu) : nullptr;
+    LCache* L = od ? cache_for(ch, nu) : nullptr;
     ch->builds.clear();
     ch->build_aux.clear();
-    ch->x_tasks.clear();
 
     // scratch vectors live in the chain: a proposal is compiled every ~100 us per chain, so no heap traffic here
     scicone_chain::Scratch& W = ch->scratch;
@@ -635,8 +626,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
 
     std::vector<DevTask>& tasks = W.tasks;
     std::vector<DevEvent>& events = W.events;
-    std::vector<DevXEvent>& xevents = W.xevents;
-    xevents.clear();
     std::vector<const double*>& prow = W.prow;  // per task: where its parent's score lives
     std::vector<int>& ptask = W.ptask;          // per task: task index of the parent, -1 when the parent is not rescored before
     std::vector<double>&tnz = W.nz, &tnzp = W.nzp;  // per task: nu*z, nu*z_parent (arguments of the z-terms)
@@ -668,7 +657,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             const double* parent_row = nullptr;
             double nz_v = 0.0, nzp_v = 0.0;
             bool share_v = false;
-            tk.ev_begin = fused ? (int)xevents.size() : (int)events.size();
+            tk.ev_begin = (int)events.size();
             int z_int;
             if (pidx < 0) {  // Tree::compute_root_score, Tree.h:145-160
                 tk.flags = TASK_ROOT;
@@ -708,17 +697,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     const int cp_i = T.genotype_at(pidx, k) + ds->neutral[k];
                     const double node_cn = cn_i == 0 ? ds->eta : (double)cn_i;
                     const double parent_cn = cp_i == 0 ? ds->eta : (double)cp_i;
-                    if (fused) {  // Tree.h:214-218, evaluated by K1 from the counts
-                        DevXEvent xe;
-                        memset(&xe, 0, sizeof xe);
-                        xe.src = ds->dDt + (size_t)k * ds->Mp;
-                        xe.arg_n = nu * node_cn * ds->r[k];
-                        xe.arg_p = nu * parent_cn * ds->r[k];
-                        xe.a = lgamma(xe.arg_n);
-                        xe.b = lgamma(xe.arg_p);
-                        xevents.push_back(xe);
-                        continue;
-                    }
                     DevEvent ev;
                     memset(&ev, 0, sizeof ev);
                     if (od) {  // Tree.h:214-218
@@ -756,9 +734,8 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     }
                     events.push_back(ev);
                 }
-                const size_t n_ev_now = (fused ? xevents.size() : events.size()) - (size_t)tk.ev_begin;
-                if (n_ev_now > 65535) return fail(SCICONE_ERR_ARG, "more than 65535 events in one node");
-                tk.n_ev = (unsigned short)n_ev_now;
+                if (events.size() - (size_t)tk.ev_begin > 65535) return fail(SCICONE_ERR_ARG, "more than 65535 events in one node");
+                tk.n_ev = (unsigned short)(events.size() - (size_t)tk.ev_begin);
                 if (od) {  // Tree.h:227-231
                     nz_v = nu * zd;
                     nzp_v = nu * zp;
@@ -804,7 +781,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     // rescored further back is read from the row this thread wrote (plain load, one node ahead).
     std::vector<DevChunk>& chunks = W.chunks;
     chunks.clear();
-    if (od && !fused) {
+    if (od) {
         auto build_g = [&](double arg, const double** out) -> int {
             double* row = nullptr;
             CUDA_TRY(ch->row_get(&row));
@@ -838,18 +815,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             tasks[i].gp_row = gp;
         }
     }
-    if (fused)
-        for (size_t i = 0; i < tasks.size(); ++i) {
-            if (tasks[i].flags & TASK_ROOT) continue;
-            double* row = nullptr;
-            CUDA_TRY(ch->row_get(&row));
-            ch->temp_rows.push_back(row);
-            tasks[i].x_row = row;
-            tasks[i].nz = tnz[i];
-            tasks[i].nzp = tnzp[i];
-            tasks[i].flags |= TASK_X;
-            ch->x_tasks.push_back((int)i);
-        }
     for (size_t i = 0; i < tasks.size(); ++i) {
         if (!(tasks[i].flags & TASK_ROOT)) {
             const int back = ptask[i] >= 0 ? (int)i - ptask[i] : 0;
@@ -860,20 +825,20 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                 tasks[i].flags |= TASK_PS_FAR;
             }
         }
-        if (tasks[i].n_ev > kEvStage && !(tasks[i].flags & TASK_X)) tasks[i].flags |= TASK_BIG;
-        const int staged = (tasks[i].flags & (TASK_BIG | TASK_X)) ? 0 : tasks[i].n_ev;
+        if (tasks[i].n_ev > kEvStage) tasks[i].flags |= TASK_BIG;
+        const int staged = (tasks[i].flags & TASK_BIG) ? 0 : tasks[i].n_ev;
         if (chunks.empty() || chunks.back().n_tasks >= kTaskChunk || chunks.back().n_ev + staged > kEvStage) {
             DevChunk c;
             c.first_task = (int)i;
             c.n_tasks = 0;
-            c.ev_base = (tasks[i].flags & TASK_X) ? 0 : tasks[i].ev_begin;
+            c.ev_base = tasks[i].ev_begin;
             c.n_ev = 0;
             chunks.push_back(c);
         }
         DevChunk& c = chunks.back();
-        tasks[i].ev_rel = (tasks[i].flags & TASK_X) ? 0 : (unsigned short)(tasks[i].ev_begin - c.ev_base);
+        tasks[i].ev_rel = (unsigned short)(tasks[i].ev_begin - c.ev_base);
         c.n_tasks++;
-        if (!(tasks[i].flags & (TASK_BIG | TASK_X))) c.n_ev = tasks[i].ev_begin + tasks[i].n_ev - c.ev_base;
+        if (!(tasks[i].flags & TASK_BIG)) c.n_ev = tasks[i].ev_begin + tasks[i].n_ev - c.ev_base;
     }
     std::vector<const double*>& old_rows = W.old_rows;
     std::vector<DevUnch>& unch = W.unch;
@@ -916,9 +881,9 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     fill_header_common(ch, 0, slot, H);  // lane and slot are patched when the batch is put together
     {   // 16 + 8 E_n bytes per rescored cell x node score, 8 N + 12 per cell aggregate
         const double n_table = full ? (double)ch->p.size() : (double)(unch.size() + ch->p.size());
-        ch->alg_bytes = (double)ds->M * (16.0 * tasks.size() + 8.0 * (events.size() + xevents.size()) + 8.0 * n_table + 12.0);
+        ch->alg_bytes = (double)ds->M * (16.0 * tasks.size() + 8.0 * events.size() + 8.0 * n_table + 12.0);
         ch->n_scores = (double)ds->M * tasks.size();
-        ch->cost = 4.0 * tasks.size() + events.size() + xevents.size() + (full ? 0.0 : 0.5 * unch.size());
+        ch->cost = 4.0 * tasks.size() + events.size() + (full ? 0.0 : 0.5 * unch.size());
     }
     // a proposal that changes nu also needs Inference::compute_t_prime_od_scores (Inference.h:942): evaluated by
     // the same launch unless the caller already asked for it separately
@@ -934,7 +899,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     b.resize(sizeof(DevHeader));
     H.off_tasks = (unsigned)blob_append(b, tasks);
     H.off_events = (unsigned)blob_append(b, events);
-    H.off_xevents = (unsigned)blob_append(b, xevents);
     H.off_chunks = (unsigned)blob_append(b, chunks);
     H.off_old = (unsigned)blob_append(b, old_rows);
     H.off_unch = (unsigned)blob_append(b, unch);
@@ -970,7 +934,6 @@ int compile_od_only(scicone_chain* ch, double nu, int slot) {
     ch->n_scores = 0.0;
     ch->with_od = true;
     ch->entry = LaunchEntry{0u, 0u, 0u, 0u};
-    ch->x_tasks.clear();
     return SCICONE_OK;
 }
 
@@ -981,7 +944,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     size_t bytes = head, n_items = 0, aux_bytes = 0;
     for (int i = 0; i < n; ++i) {
         bytes += chains[i]->blob.size();
-        n_items += chains[i]->builds.size() + chains[i]->x_tasks.size();
+        n_items += chains[i]->builds.size();
         aux_bytes += round_up(chains[i]->build_aux.size() * sizeof(double), 16);
     }
     const size_t off_items = bytes;
@@ -1038,19 +1001,6 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
             }
             chain_aux += round_up(ch->build_aux.size() * sizeof(double), 16);
         }
-        if (pass == 0)  // between the slices and the one-lgamma rows: the increment rows of nu proposals (BUILD_X)
-            for (int i = 0; i < n; ++i)
-                for (int t : chains[i]->x_tasks) {
-                    DevBuild it;
-                    memset(&it, 0, sizeof it);
-                    it.kind = BUILD_X;
-                    it.off_arg = blob_at[i];
-                    it.k0 = t;
-                    it.n_cells = ds->M;
-                    it.row_stride = (long long)ds->Mp;
-                    memcpy(g.h_arena + item_at, &it, sizeof it);
-                    item_at += sizeof it;
-                }
     }
     for (int q = 0; q < n; ++q) {
         offs[q] = chains[order[q]]->entry;
@@ -1569,11 +1519,6 @@ int scicone_accept(scicone_chain* ch) {
         ch->Lt.swap(ch->Lp);
         ch->Lt_nu = ch->Lp_nu;
         ch->Lp_valid = false;
-    } else if (ds->od && ch->Lt_valid && ch->Lt_nu != ch->tp.nu) {
-        // a nu proposal scored without lgamma rows was accepted: the rows of the old nu are dead, those of the new nu are
-        // built on first use
-        release_cache(ch, ch->Lt);
-        ch->Lt_valid = false;
     }
     drop_pending(ch);
     return SCICONE_OK;
