@@ -485,17 +485,20 @@ public:
 // Cell-sharded runs (one host process per GPU on one node): every chain has ONE owner rank that runs its tree search;
 // the other ranks only need the proposal it drew (to queue and compile it against their own shard's tables) and, one
 // visit later, whether it was accepted.  Both travel through a shared-memory mailbox, one slot per chain: the owner
-// writes the payload and then bumps the sequence number, followers wait for the number they expect.  A slot is not
-// overwritten before every rank has read it: the next message of a chain is only written after the launch that scored
-// the previous one came back, and that launch contains a collective all ranks take part in.
+// writes the payload and then bumps the sequence number, followers wait for the number they expect and acknowledge it
+// once they have copied the message out; the owner does not overwrite a slot before every follower has acknowledged the
+// previous message.  (On the GPU the collective inside the launch that scored the previous proposal already orders the
+// two; a visit in which nothing of a group was scored, or a run without collectives, has no such launch.)
 class Mailbox {
 public:
     static constexpr size_t kSlotBytes = 1u << 20;
+    static constexpr int kMaxRanks = 16;
     struct Slot {
         std::atomic<uint64_t> seq;
         uint32_t bytes;
         uint32_t pad;
-        unsigned char payload[kSlotBytes - 16];
+        std::atomic<uint64_t> ack[kMaxRanks];  // last message each rank has consumed
+        unsigned char payload[kSlotBytes - 16 - 8 * kMaxRanks];
     };
     ~Mailbox() {
         if (base_) munmap(base_, map_bytes_);
@@ -519,27 +522,40 @@ public:
         }
         slots_ = static_cast<Slot*>(base_);  // a fresh segment is zero filled: seq = 0
     }
-    void publish(int chain, uint64_t seq, const std::vector<unsigned char>& msg) {
+    template <class Pred>
+    static void spin_until(Pred&& done, const char* what, int chain) {
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while (!done()) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((++spins & 0xfffu) == 0) {
+                std::this_thread::yield();
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
+                    throw std::runtime_error(std::string("timed out waiting for ") + what + " of chain " + std::to_string(chain));
+            }
+        }
+    }
+    // owner: message `seq` of `chain`; `rank` / `world` name the followers whose acknowledgement of seq-1 is awaited
+    void publish(int chain, uint64_t seq, const std::vector<unsigned char>& msg, int rank, int world) {
         Slot& s = slots_[chain];
         if (msg.size() > sizeof(s.payload)) throw std::runtime_error("proposal too large for the mailbox slot");
+        if (world > kMaxRanks) throw std::runtime_error("mailbox: too many ranks");
+        for (int r = 0; r < world; ++r)
+            if (r != rank) spin_until([&] { return s.ack[r].load(std::memory_order_acquire) + 1 >= seq; }, "a follower", chain);
         std::memcpy(s.payload, msg.data(), msg.size());
         s.bytes = static_cast<uint32_t>(msg.size());
         s.seq.store(seq, std::memory_order_release);
     }
     const unsigned char* receive(int chain, uint64_t seq, uint32_t* bytes) {
         Slot& s = slots_[chain];
-        const auto t0 = std::chrono::steady_clock::now();
-        unsigned spins = 0;
-        while (s.seq.load(std::memory_order_acquire) < seq) {
-#if defined(__x86_64__) || defined(__i386__)
-            __builtin_ia32_pause();
-#endif
-            if ((++spins & 0xffffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
-                throw std::runtime_error("timed out waiting for the owner of chain " + std::to_string(chain));
-        }
+        spin_until([&] { return s.seq.load(std::memory_order_acquire) >= seq; }, "the owner", chain);
         *bytes = s.bytes;
         return s.payload;
     }
+    // follower: message `seq` has been copied out of the slot
+    void acknowledge(int chain, uint64_t seq, int rank) { slots_[chain].ack[rank].store(seq, std::memory_order_release); }
 
 private:
     std::string name_;
@@ -739,7 +755,7 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
             if (mailbox) {  // the decision about the previous proposal and the next proposal, in one message
                 std::vector<unsigned char>& msg = c->msg_buf;
                 pack_message(*c, g.scored[i] != 0, msg);
-                mailbox->publish(g.members[i], ++c->msg_seq, msg);
+                mailbox->publish(g.members[i], ++c->msg_seq, msg, rank, world);
             }
             const Clock::time_point c3 = Clock::now();
             auto us = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
@@ -755,6 +771,7 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
                 uint32_t bytes = 0;
                 const unsigned char* msg = mailbox->receive(g.members[i], ++c->msg_seq, &bytes);
                 g.scored[i] = apply_message(*c, msg, bytes) ? 1 : 0;
+                mailbox->acknowledge(g.members[i], c->msg_seq, rank);
             });
         T.host_us += us_since(t0);
         if (it >= n_iters) return;
