@@ -252,7 +252,7 @@ def run_engine(args):
     ds.set_profiling(False)
 
     # pass 2
-    two_lanes = world == 1 and B >= 2
+    two_lanes = B >= 2  # cell-sharded: each lane has a communicator of its own, all ranks launch in the same order
     dev_ms = one_lane_ms
     two_lane_ms = None
     value_pass = "one launch of all chains per step on one stream, totals collected with a lag"
@@ -287,6 +287,11 @@ def run_engine(args):
         ds.region_mark(1)
         barrier()
         two_lane_ms = ds.region_elapsed_ms()
+        if world > 1:  # the choice between the passes is made on the max over ranks, so every rank makes the same one
+            t = torch.tensor([one_lane_ms, two_lane_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            one_lane_ms, two_lane_ms = (float(x) for x in t.cpu())
+            dev_ms = one_lane_ms
         if two_lane_ms < one_lane_ms:  # `value` is the faster of the two ways to drive the device pipeline
             dev_ms = two_lane_ms
             launches_dev = ds.kernel_launches() - launches2
@@ -392,7 +397,9 @@ def run_native_host(args, data, rank, world, local, dist, comm_unique_id):
                "--verbosity=0", f"--max_scoring={'true' if args.max_scoring else 'false'}", f"--postfix=e2e{rank}",
                f"--n_chains={args.chains}", f"--device={local}", f"--stats_file={stats}", "--stats_all_ranks=1"]
         if args.n_groups:
-            cmd.append(f"--n_groups={args.n_groups}")
+            cmd += [f"--n_groups={args.n_groups}", "--schedule=static"]
+        elif world > 1:  # rank 0 composes the launches, the other ranks replay its launch log
+            cmd.append("--schedule=dynamic")
         if world > 1:
             cmd += [f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"]
         env = dict(os.environ)

@@ -172,7 +172,9 @@ int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, in
  * Launch streams of a dataset (default 1).  With 2, consecutive batch launches alternate between two streams and overlap
  * on the device.  One stream serialises launches, which is what allows scicone_accept / scicone_reject before
  * scicone_batch_wait; with two streams a launch must be collected (scicone_batch_wait) before its chains are settled or
- * queued again, and at most one launch per stream may be outstanding.  Not available on cell-sharded datasets.
+ * queued again, and at most one launch per stream may be outstanding.  On a cell-sharded dataset the call is collective
+ * (the second stream gets a communicator of its own, ncclCommSplit) and all ranks must submit their launches in the same
+ * order.
  */
 int scicone_set_streams(scicone_dataset* ds, int32_t n);
 

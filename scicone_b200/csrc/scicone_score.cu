@@ -69,6 +69,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommSplit)(void*, int, int, void**, void*) = nullptr;  // NCCL >= 2.18
     const char* (*GetErrorString)(int) = nullptr;
     bool load() {
         if (handle) return true;
@@ -79,6 +80,7 @@ struct NcclApi {
         CommInitRank = (int (*)(void**, int, UniqueId, int))dlsym(handle, "ncclCommInitRank");
         CommDestroy = (int (*)(void*))dlsym(handle, "ncclCommDestroy");
         AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(handle, "ncclAllGather");
+        CommSplit = (int (*)(void*, int, int, void**, void*))dlsym(handle, "ncclCommSplit");
         GetErrorString = (const char* (*)(int))dlsym(handle, "ncclGetErrorString");
         return GetUniqueId && CommInitRank && CommDestroy && AllGather;
     }
@@ -282,10 +284,11 @@ struct scicone_dataset {
     unsigned* d_status = nullptr;
     // multi-GPU
     void* comm = nullptr;
+    void* comm_lane1 = nullptr;  // second lane: a communicator of its own (ncclCommSplit of `comm`), see scicone_set_streams
     int rank = 0, world = 1;
     int max_chunks_rank = 0;
-    double* d_gather = nullptr;  // [world][slots][max_chunks_rank]
-    double* d_send = nullptr;    // [slots][max_chunks_rank]
+    double* d_gather = nullptr;  // per lane: [world][slots][2][max_chunks_rank]
+    double* d_send = nullptr;    // per lane: [slots][2][max_chunks_rank]
     size_t gather_cap = 0;
     // profiling
     bool profiling = false;
@@ -375,10 +378,10 @@ struct scicone_dataset {
             cudaFree(d_gather); cudaFree(d_send);
             d_gather = d_send = nullptr;
             size_t per_rank = size_t(ns) * 2 * max_chunks_rank;
-            CUDA_TRY(cudaMalloc(&d_send, sizeof(double) * per_rank));
-            CUDA_TRY(cudaMalloc(&d_gather, sizeof(double) * per_rank * world));
+            CUDA_TRY(cudaMalloc(&d_send, sizeof(double) * per_rank * kLanes));
+            CUDA_TRY(cudaMalloc(&d_gather, sizeof(double) * per_rank * world * kLanes));
             for (Segment& g : seg) CUDA_TRY(cudaMallocHost(&g.h_gather, sizeof(double) * per_rank * world));
-            CUDA_TRY(cudaMemset(d_send, 0, sizeof(double) * per_rank));
+            CUDA_TRY(cudaMemset(d_send, 0, sizeof(double) * per_rank * kLanes));
             gather_cap = per_rank;
         }
         return SCICONE_OK;
@@ -1044,13 +1047,15 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     if (ds->world > 1) {
         // Each rank contributes its per-chunk sums; every rank adds all chunks in global chunk order,
         // so the total does not depend on the number of GPUs.
-        pack_chunks_kernel<<<n, 128, 0, st>>>(ds->d_chunk, ds->n_chunks, ds->d_send, ds->max_chunks_rank);
+        double* d_send = ds->d_send + (size_t)lane * ds->gather_cap;
+        double* d_gather = ds->d_gather + (size_t)lane * ds->gather_cap * ds->world;
+        pack_chunks_kernel<<<n, 128, 0, st>>>(ds->d_chunk + (size_t)lane * ds->slots * 2 * ds->n_chunks, ds->n_chunks, d_send, ds->max_chunks_rank);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
         const size_t cnt = (size_t)n * 2 * ds->max_chunks_rank;
-        int nrc = g_nccl.AllGather(ds->d_send, ds->d_gather, cnt, kNcclDouble, ds->comm, st);
+        int nrc = g_nccl.AllGather(d_send, d_gather, cnt, kNcclDouble, lane == 0 ? ds->comm : ds->comm_lane1, st);
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
-        CUDA_TRY(cudaMemcpyAsync(g.h_gather, ds->d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(g.h_gather, d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, st));
     } else
         CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->lane_total(lane), ds->lane_result_bytes, cudaMemcpyDeviceToHost, st));
     if (ds->world > 1)
@@ -1274,6 +1279,7 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     cudaSetDevice(ds->device);
     if (ds->stream) cudaStreamSynchronize(ds->stream);
     if (ds->lane_stream[1]) cudaStreamSynchronize(ds->lane_stream[1]);
+    if (ds->comm_lane1 && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm_lane1);
     if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm);
     ds->pool.destroy();
     cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW);
@@ -1869,7 +1875,6 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
 
 int scicone_set_streams(scicone_dataset* ds, int32_t n) {
     if (!ds || n < 1 || n > scicone_dataset::kLanes) return fail(SCICONE_ERR_ARG, "set_streams: 1 or 2 streams");
-    if (n > 1 && ds->world > 1) return fail(SCICONE_ERR_STATE, "set_streams: cell-sharded datasets launch on one stream (the collective orders them)");
     int rc = ds->set_device();
     if (rc) return rc;
     rc = ds->sync_lanes();
@@ -1877,6 +1882,13 @@ int scicone_set_streams(scicone_dataset* ds, int32_t n) {
     for (scicone_dataset::Segment& g : ds->seg)
         if (g.busy) return fail(SCICONE_ERR_STATE, "set_streams with launches outstanding");
     if (n > 1 && !ds->lane_stream[1]) CUDA_TRY(cudaStreamCreateWithFlags(&ds->lane_stream[1], cudaStreamNonBlocking));
+    if (n > 1 && ds->world > 1 && !ds->comm_lane1) {
+        // cell-sharded: the all-gathers of the two lanes run concurrently, each lane needs its own communicator.  Collective:
+        // every rank calls scicone_set_streams at the same point, and all ranks submit their launches in the same order.
+        if (!g_nccl.CommSplit) return fail(SCICONE_ERR_COMM, "set_streams: this NCCL has no ncclCommSplit (needs >= 2.18)");
+        int nrc = g_nccl.CommSplit(ds->comm, 0, ds->rank, &ds->comm_lane1, nullptr);
+        if (nrc != 0 || !ds->comm_lane1) return fail(SCICONE_ERR_COMM, "ncclCommSplit failed (%d)", nrc);
+    }
     ds->n_lanes = n;
     return SCICONE_OK;
 }

@@ -11,6 +11,7 @@
 #ifndef SCICONE_B200_HOST_MCMC_HPP
 #define SCICONE_B200_HOST_MCMC_HPP
 
+#include <algorithm>
 #include <cfloat>
 #include <chrono>
 #include <atomic>
@@ -504,10 +505,25 @@ public:
         if (base_) munmap(base_, map_bytes_);
         if (owner_ && !name_.empty()) shm_unlink(name_.c_str());
     }
+    // Launch log (dynamic schedule of a cell-sharded run): rank 0 decides which chains go into launch k and writes the
+    // list here; the other ranks submit the same launches in the same order (every launch contains a collective).
+    static constexpr int kLogRing = 64;
+    struct LogHead {
+        std::atomic<uint64_t> consumed[kMaxRanks];  // launches each rank has submitted
+    };
+    struct LogRec {
+        std::atomic<uint64_t> seq;  // k + 1 once the members of launch k are in place
+        int32_t n;
+        int32_t pad;
+        // int32_t members[n_chains] follow
+    };
     void open(const std::string& name, int n_chains, bool unlink_at_exit) {
         name_ = name;
         owner_ = unlink_at_exit;
-        map_bytes_ = sizeof(Slot) * static_cast<size_t>(n_chains);
+        n_chains_ = n_chains;
+        rec_bytes_ = (sizeof(LogRec) + 4 * static_cast<size_t>(n_chains) + 63) / 64 * 64;
+        const size_t slot_bytes = sizeof(Slot) * static_cast<size_t>(n_chains);
+        map_bytes_ = slot_bytes + sizeof(LogHead) + rec_bytes_ * kLogRing;
         int fd = shm_open(name.c_str(), O_CREAT | O_RDWR, 0600);
         if (fd < 0) throw std::runtime_error("shm_open(" + name + ") failed");
         if (ftruncate(fd, static_cast<off_t>(map_bytes_)) != 0) {
@@ -521,6 +537,45 @@ public:
             throw std::runtime_error("mmap of the mailbox failed");
         }
         slots_ = static_cast<Slot*>(base_);  // a fresh segment is zero filled: seq = 0
+        log_head_ = reinterpret_cast<LogHead*>(static_cast<unsigned char*>(base_) + slot_bytes);
+        log_recs_ = static_cast<unsigned char*>(base_) + slot_bytes + sizeof(LogHead);
+    }
+    LogRec* log_rec(uint64_t k) const { return reinterpret_cast<LogRec*>(log_recs_ + rec_bytes_ * (k % kLogRing)); }
+    // rank 0: members of the next launch; returns its index
+    uint64_t log_publish(const std::vector<int>& members, int world) {
+        const uint64_t k = next_launch_++;
+        if (k >= kLogRing)  // the record about to be overwritten must have been submitted everywhere
+            for (int r = 1; r < world; ++r)
+                spin_until([&] { return log_head_->consumed[r].load(std::memory_order_acquire) + kLogRing > k; }, "the launch log", r);
+        LogRec* rec = log_rec(k);
+        rec->n = static_cast<int32_t>(members.size());
+        std::memcpy(reinterpret_cast<unsigned char*>(rec) + sizeof(LogRec), members.data(), 4 * members.size());
+        rec->seq.store(k + 1, std::memory_order_release);
+        return k;
+    }
+    // other ranks: members of the next launch if rank 0 has published it
+    bool log_peek(std::vector<int>& members) const {
+        LogRec* rec = log_rec(next_launch_);
+        const uint64_t seq = rec->seq.load(std::memory_order_acquire);
+        if (seq < next_launch_ + 1) return false;
+        if (seq > next_launch_ + 1) throw std::runtime_error("launch log overrun");
+        members.resize(static_cast<size_t>(rec->n));
+        std::memcpy(members.data(), reinterpret_cast<const unsigned char*>(rec) + sizeof(LogRec), 4 * members.size());
+        return true;
+    }
+    void log_consumed(int rank) { log_head_->consumed[rank].store(++next_launch_, std::memory_order_release); }
+    // non-blocking forms for the dynamic schedule, where a worker thread must never wait for another rank
+    bool can_publish(int chain, uint64_t seq, int rank, int world) const {
+        const Slot& s = slots_[chain];
+        for (int r = 0; r < world; ++r)
+            if (r != rank && s.ack[r].load(std::memory_order_acquire) + 1 < seq) return false;
+        return true;
+    }
+    const unsigned char* try_receive(int chain, uint64_t seq, uint32_t* bytes) const {
+        const Slot& s = slots_[chain];
+        if (s.seq.load(std::memory_order_acquire) < seq) return nullptr;
+        *bytes = s.bytes;
+        return s.payload;
     }
     template <class Pred>
     static void spin_until(Pred&& done, const char* what, int chain) {
@@ -561,8 +616,12 @@ private:
     std::string name_;
     bool owner_ = false;
     void* base_ = nullptr;
-    size_t map_bytes_ = 0;
+    size_t map_bytes_ = 0, rec_bytes_ = 0;
+    int n_chains_ = 0;
     Slot* slots_ = nullptr;
+    LogHead* log_head_ = nullptr;
+    unsigned char* log_recs_ = nullptr;
+    uint64_t next_launch_ = 0;  // launches published (rank 0) / submitted (other ranks) so far
 };
 
 // message = {u8 has_decision, u8 accept, u8 scored, u8 pad, i32 n_roots, [tree, roots]}
@@ -791,29 +850,43 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
         for (Group& g : groups) visit(g, it);
 }
 
-// The same chains under a dynamic schedule (single GPU): no group ever waits for its slowest member.  Worker threads take
-// chains whose launch has come back, finish that iteration, draw and compile the next proposal and hand the chain to the
-// driver thread; the driver launches whatever is ready as soon as `min_batch` chains are (or nothing else is coming),
-// with at most two launches in flight, and feeds completed launches back to the workers.  Batch composition varies from
-// run to run; a chain's own sequence propose -> score -> compare does not, so trajectories are those of infer_mcmc.
+// The same chains under a dynamic schedule: no group ever waits for its slowest member.  Worker threads take chains whose
+// launch has come back, finish that iteration, draw and compile the next proposal and hand the chain to the driver
+// thread; the driver launches whatever is ready as soon as `min_batch` chains are (or nothing else is coming), with at
+// most two launches in flight, and feeds completed launches back to the workers.  Batch composition varies from run to
+// run; a chain's own sequence propose -> score -> compare does not, so trajectories are those of infer_mcmc.
+//
+// Cell-sharded runs (world > 1, with a mailbox): every rank must submit the same launches in the same order.  A chain's
+// search runs on its owner rank, which publishes each scored proposal (with the decision about the previous one); the
+// other ranks compile it against their shard as the message arrives.  Rank 0 composes the launches from the chains that
+// are compiled on rank 0 and writes each list to the launch log; the other ranks replay the log, submitting launch k as
+// soon as its chains are compiled locally.  Nothing ever waits for a later launch, and no worker thread blocks on
+// another rank: a chain whose message (or whose followers' acknowledgement) is not there yet goes back to the queue.
 inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
-                               int min_batch = 0, HostPhaseTimes* times = nullptr, int n_streams = 2) {
+                               int min_batch = 0, HostPhaseTimes* times = nullptr, int n_streams = 2, int rank = 0, int world = 1,
+                               Mailbox* mailbox = nullptr) {
     typedef std::chrono::steady_clock Clock;
     const int B = static_cast<int>(chains.size());
     if (B == 0 || n_iters <= 0) return;
+    if (world > 1 && mailbox == nullptr) throw std::runtime_error("the dynamic schedule of a multi-process run needs the mailbox");
     scicone_dataset* ds = chains[0]->ds;
     if (min_batch <= 0) min_batch = std::max(1, B / 3);
     // two launch streams: K1 of one launch overlaps the proposal kernel of the other (a launch is always collected here
     // before its chains are settled, which is what the second stream requires)
     if (n_streams > 1) abi_check(scicone_set_streams(ds, 2));
+    auto owned = [&](int b) { return mailbox == nullptr || b % world == rank; };
     parallel_chains(B, [&](int b) {
         chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
-        chains[b]->open_traces(n_iters);
+        if (owned(b)) chains[b]->open_traces(n_iters);
     });
     struct Slot {
         int iter = 0;             // iteration whose proposal is queued / in flight
         bool has_result = false;  // total / od of that proposal are in
+        bool to_publish = false;  // owner: the message is packed, the followers have not acknowledged the previous one yet
+        bool queued = false;      //        ... and it carries a scored proposal
         double total = 0.0, od = 0.0;
+        Clock::time_point waiting_since{};  // first unsuccessful poll of the other ranks
+        bool polling = false;
     };
     std::vector<Slot> st(B);
     std::mutex mu;  // guards work, ready, n_done, n_host
@@ -826,37 +899,81 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     for (int b = 0; b < B; ++b) work.push_back(b);
     n_work.store(B, std::memory_order_release);
 
-    auto host_work = [&](int b) {
-        Inference* c = chains[b];
+    // the chain goes back to the queue: the other ranks are not there yet
+    auto poll_again = [&](int b, const char* what) {
         Slot& s = st[b];
-        const Clock::time_point c0 = Clock::now();
-        if (s.has_result) {
-            int32_t nr = 0;
-            scicone_t_prime_n_rescored(c->chain, &nr);
-            c->rescored_last = static_cast<unsigned>(nr);
-            c->finish(true, s.total, s.od, s.iter);
-            s.has_result = false;
-            ++s.iter;
+        if (!s.polling) {
+            s.polling = true;
+            s.waiting_since = Clock::now();
+        } else if (Clock::now() - s.waiting_since > std::chrono::seconds(120))
+            throw std::runtime_error(std::string("timed out waiting for ") + what + " of chain " + std::to_string(b));
+        for (int i = 0; i < 64; ++i) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
         }
-        bool queued = false;
-        while (s.iter < n_iters) {
-            if (c->propose(move_probs, size_limit)) {
-                abi_check(scicone_prepare_t_prime(c->chain));
-                queued = true;
-                break;
-            }
-            c->finish(false, 0.0, 0.0, s.iter);  // nothing to score (move 10, or every attempt failed)
-            ++s.iter;
-        }
-        const double us = std::chrono::duration<double, std::micro>(Clock::now() - c0).count();
-        c->t_propose_us += us;
-        c->t_max_visit_us = std::max(c->t_max_visit_us, us);
+        std::lock_guard<std::mutex> lk(mu);
+        work.push_back(b);
+        n_work.fetch_add(1, std::memory_order_release);
+    };
+    auto hand_over = [&](int b, bool queued) {
+        st[b].polling = false;
         std::lock_guard<std::mutex> lk(mu);
         --n_host;
         if (queued)
             ready.push_back(b);
         else
             ++n_done;
+    };
+    auto host_work = [&](int b) {
+        Inference* c = chains[b];
+        Slot& s = st[b];
+        if (!owned(b)) {  // follower: the owner's decision about the previous proposal and its next one
+            uint32_t bytes = 0;
+            const unsigned char* msg = mailbox->try_receive(b, c->msg_seq + 1, &bytes);
+            if (!msg) return poll_again(b, "the owner");
+            ++c->msg_seq;
+            const bool scored = apply_message(*c, msg, bytes);
+            mailbox->acknowledge(b, c->msg_seq, rank);
+            return hand_over(b, scored);
+        }
+        if (!s.to_publish) {
+            const Clock::time_point c0 = Clock::now();
+            int decision = -1;
+            if (s.has_result) {
+                int32_t nr = 0;
+                scicone_t_prime_n_rescored(c->chain, &nr);
+                c->rescored_last = static_cast<unsigned>(nr);
+                c->finish(true, s.total, s.od, s.iter);
+                decision = c->last_decision;
+                s.has_result = false;
+                ++s.iter;
+            }
+            s.queued = false;
+            while (s.iter < n_iters) {
+                if (c->propose(move_probs, size_limit)) {
+                    abi_check(scicone_prepare_t_prime(c->chain));
+                    s.queued = true;
+                    break;
+                }
+                c->finish(false, 0.0, 0.0, s.iter);  // nothing to score (move 10, or every attempt failed)
+                ++s.iter;
+            }
+            if (mailbox) {  // one message per scored proposal, and a last one that only carries the decision
+                c->last_decision = decision;
+                pack_message(*c, s.queued, c->msg_buf);
+                s.to_publish = true;
+            }
+            const double us = std::chrono::duration<double, std::micro>(Clock::now() - c0).count();
+            c->t_propose_us += us;
+            c->t_max_visit_us = std::max(c->t_max_visit_us, us);
+        }
+        if (s.to_publish) {
+            if (!mailbox->can_publish(b, c->msg_seq + 1, rank, world)) return poll_again(b, "a follower");
+            mailbox->publish(b, ++c->msg_seq, c->msg_buf, rank, world);
+            s.to_publish = false;
+        }
+        hand_over(b, s.queued);
     };
     auto worker = [&]() {
         int idle = 0;
@@ -913,29 +1030,55 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
             ++n_host;
         }
     };
+    auto submit = [&](std::vector<int>& take) {
+        handles.clear();
+        for (int b : take) handles.push_back(chains[b]->chain);
+        Flight f;
+        f.members = take;
+        abi_check(scicone_batch_submit(handles.data(), nullptr, static_cast<int32_t>(handles.size()), &f.ticket));
+        flights.push_back(std::move(f));
+        ++n_launches;
+        n_launched_chains += take.size();
+    };
+    const bool replay = world > 1 && rank != 0;
+    std::vector<int> wanted;  // replaying ranks: members of the next launch of the log
+    bool have_wanted = false;
     try {
         for (;;) {
             if (stop.load(std::memory_order_acquire)) break;
             std::vector<int> take;
             bool all_done = false;
+            if (replay && !have_wanted && flights.size() < 2) have_wanted = mailbox->log_peek(wanted);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 all_done = n_done == B;
-                const bool nothing_coming = n_host == 0 && flights.empty();
-                if (!ready.empty() && flights.size() < 2 && (static_cast<int>(ready.size()) >= min_batch || nothing_coming || (n_host == 0 && flights.size() < 2)))
-                    take.swap(ready);
+                if (replay) {
+                    if (have_wanted && flights.size() < 2) {  // launch k goes out once all of its chains are compiled here
+                        size_t found = 0;
+                        for (int b : wanted)
+                            if (std::find(ready.begin(), ready.end(), b) != ready.end()) ++found;
+                        if (found == wanted.size()) {
+                            for (int b : wanted) ready.erase(std::find(ready.begin(), ready.end(), b));
+                            take = wanted;
+                        }
+                    }
+                } else {
+                    const bool nothing_coming = n_host == 0 && flights.empty();
+                    if (!ready.empty() && flights.size() < 2 && (static_cast<int>(ready.size()) >= min_batch || nothing_coming || (n_host == 0 && flights.size() < 2)))
+                        take.swap(ready);
+                }
             }
             if (all_done) break;
             if (!take.empty()) {
-                std::sort(take.begin(), take.end());
-                handles.clear();
-                for (int b : take) handles.push_back(chains[b]->chain);
-                Flight f;
-                f.members = take;
-                abi_check(scicone_batch_submit(handles.data(), nullptr, static_cast<int32_t>(handles.size()), &f.ticket));
-                flights.push_back(std::move(f));
-                ++n_launches;
-                n_launched_chains += take.size();
+                if (replay) {
+                    submit(take);
+                    mailbox->log_consumed(rank);
+                    have_wanted = false;
+                } else {
+                    std::sort(take.begin(), take.end());
+                    if (world > 1) mailbox->log_publish(take, world);
+                    submit(take);
+                }
                 continue;
             }
             if (!flights.empty()) {

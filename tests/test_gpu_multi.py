@@ -24,8 +24,8 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("max_scoring", ["true", "false"])
-def test_two_gpu_run_equals_one_gpu_run(tmp_path, max_scoring):
+@pytest.mark.parametrize("max_scoring,schedule,n_chains", [("true", "static", 2), ("false", "static", 2), ("true", "dynamic", 6)])
+def test_two_gpu_run_equals_one_gpu_run(tmp_path, max_scoring, schedule, n_chains):
     from scicone_b200.api import comm_unique_id
 
     data = make_counts(5000, 9000, 60, seed=31)  # 5 chunks of 1024 cells: shards of 3 and 2 chunks
@@ -34,7 +34,7 @@ def test_two_gpu_run_equals_one_gpu_run(tmp_path, max_scoring):
     np.savetxt(d, data["D"], delimiter=",", fmt="%.0f")
     np.savetxt(r, data["region_sizes"], fmt="%d")
     common = [NATIVE, f"--d_matrix_file={d}", f"--region_sizes_file={r}", "--n_cells=5000", "--n_regions=60", "--n_iters=300",
-              "--n_nodes=12", "--seed=5", "--nu=1.0", "--verbosity=2", f"--max_scoring={max_scoring}", "--n_chains=2", "--schedule=static"]
+              "--n_nodes=12", "--seed=5", "--nu=1.0", "--verbosity=2", f"--max_scoring={max_scoring}", f"--n_chains={n_chains}", f"--schedule={schedule}", "--min_batch=2"]
     one = subprocess.run(common + ["--postfix=one", "--device=0"], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     assert one.returncode == 0, one.stderr[-2000:]
     uid = comm_unique_id().hex()
@@ -44,7 +44,8 @@ def test_two_gpu_run_equals_one_gpu_run(tmp_path, max_scoring):
         out, err = p.communicate(timeout=600)
         assert p.returncode == 0, err[-2000:]
     # chain c is searched by rank c % 2 (the other rank follows it through the mailbox): its owner wrote the traces
-    for c in range(2):
+    # (dynamic schedule: rank 0 composes the launches on two lanes, rank 1 replays its launch log)
+    for c in range(n_chains):
         for name in ("acceptance_ratio.csv", "markov_chain.csv", "gamma_values.csv", "tree_inferred.txt"):
             a = open(os.path.join(str(tmp_path), f"one_c{c}_{name}")).read()
             assert a == open(os.path.join(str(tmp_path), f"two{c % 2}_c{c}_{name}")).read(), (c, name)

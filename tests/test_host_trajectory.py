@@ -139,12 +139,14 @@ def test_multi_chain_equals_single_runs_on_gpu(tmp_path):
 
 @needs_bins
 @pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
-def test_chain_ownership_protocol_on_cpu(tmp_path):
+@pytest.mark.parametrize("schedule,world,threads", [("static", 2, "2"), ("dynamic", 2, "1"), ("dynamic", 3, "3")])
+def test_chain_ownership_protocol_on_cpu(tmp_path, schedule, world, threads):
     """Multi-process runs: every chain is searched by ONE owner process, the others follow it through the shared-memory
     mailbox (proposal + decision messages).  Two processes with --no_shard (each holds all cells, oracle-backed ABI):
     the owner's traces of every chain equal the unmodified reference's single-chain run, and the followers' device state
     stays in step (a follower that missed a commit would make the owner's next totals differ on the GPU; here it is
-    checked through the final tables of both processes being readable and the run finishing)."""
+    checked through the final tables of both processes being readable and the run finishing).  With the dynamic schedule
+    rank 0 composes the launches and the other ranks replay its launch log."""
     import subprocess
     import uuid
 
@@ -156,12 +158,12 @@ def test_chain_ownership_protocol_on_cpu(tmp_path):
     np.savetxt(d, D, delimiter=",", fmt="%.0f")
     rf = os.path.join(str(tmp_path), "r.txt")
     np.savetxt(rf, r, fmt="%d")
-    env = dict(os.environ, **CPU_ENV, SCICONE_THREADS="2")
+    env = dict(os.environ, **CPU_ENV, SCICONE_THREADS=threads)
     shm = "/scicone_test_" + uuid.uuid4().hex[:12]
     procs = []
-    for k in range(2):
+    for k in range(world):
         cmd = [NATIVE, f"--d_matrix_file={d}", f"--region_sizes_file={rf}", f"--n_cells={D.shape[0]}", f"--n_regions={D.shape[1]}",
-               "--verbosity=2", f"--postfix=own{k}", "--seed=30", "--n_chains=5", "--schedule=static", "--no_shard", f"--rank={k}", "--world=2",
+               "--verbosity=2", f"--postfix=own{k}", "--seed=30", "--n_chains=5", f"--schedule={schedule}", "--min_batch=2", "--no_shard", f"--rank={k}", f"--world={world}",
                f"--shm_name={shm}"] + base
         procs.append(subprocess.Popen(cmd, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
     for p in procs:
@@ -169,7 +171,7 @@ def test_chain_ownership_protocol_on_cpu(tmp_path):
         assert p.returncode == 0, err[-2000:]
     for c in range(5):
         single = run_inference(REF, str(tmp_path), f"single{c}", D, r, base + [f"--seed={30 + c}"])
-        owner = c % 2
+        owner = c % world
         got = {}
         for name in ("acceptance_ratio", "markov_chain", "gamma_values"):
             got[name] = np.array([float(x) for x in open(os.path.join(str(tmp_path), f"own{owner}_c{c}_{name}.csv")).read().strip().split(",")])
