@@ -402,6 +402,7 @@ def run_native_host(args, data, rank, world, local, dist, comm_unique_id):
             cmd.append("--schedule=dynamic")
         if world > 1:
             cmd += [f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"]
+        cmd += args.host_args.split()
         env = dict(os.environ)
         if world > 1:  # the host cores are shared by the ranks
             env.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
@@ -543,6 +544,7 @@ def main():
     ap.add_argument("--ref_iters_per_step", type=int, default=1)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true", help="skip the native-host run (profiling passes only)")
+    ap.add_argument("--host_args", default="", help="extra flags for the native host, space separated (tuning runs)")
     ap.add_argument("--n_groups", type=int, default=0, help="chain groups of the native host's static schedule (cell-sharded runs)")
     args = ap.parse_args()
     protect_stdout()

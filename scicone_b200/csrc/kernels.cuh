@@ -125,7 +125,14 @@ struct alignas(16) DevHeader {
     unsigned off_tasks, off_events, off_old, off_unch, off_od_rows, off_chunks;
     const double* pad4;
     const double* od_g_row;          // PROP_WITH_OD, OD: row lgamma(S + nu*z_root) built by K1
+    // cell-sharded datasets: the chunk sums go straight into every rank's gather buffer over NVLink (peer memory), see
+    // finish_reduction.  xchg_world == 0: single GPU.
+    double* const* xchg_data;               // [world] base of this rank's block in rank p's buffer (lane and parity chosen by the host)
+    unsigned long long* const* xchg_flag;   // [world] this rank's flag row in rank p's buffer
+    unsigned long long xchg_seq;            // number of this launch on its lane
+    int xchg_world, xchg_slot, xchg_stride, xchg_pad;  // stride = chunk sums per rank and value (max_chunks_rank)
 };
+constexpr int kXchgSlots = 128;  // proposals per launch of a cell-sharded dataset
 
 struct alignas(16) DevBuild {
     double* dst;
@@ -178,8 +185,13 @@ __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
 // 1024-cell chunks, then the chunks.  The result does not depend on the CTA
 // schedule, and (because shards are whole chunks) not on the number of GPUs.
 // Two sums travel together: [0] the tree score, [1] the root score (0 when not requested).
+//
+// Cell-sharded datasets: the same CTA stores the chunk sums into the gather buffer of EVERY rank (peer memory, NVLink
+// stores) and then publishes the launch number in the flag word of this (rank, proposal) on every rank - a release at
+// system scope after a CTA barrier, so a rank that sees the flag sees the sums.  No collective kernel runs, and no GPU
+// waits for another one here: only the reader of the sums does (wait_flags_kernel).
 __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum1, double* partial, double* chunk_sums,
-                                                 double* total, unsigned* counter) {
+                                                 double* total, unsigned* counter, const DevHeader& H) {
     __shared__ bool is_last;
     __shared__ double smem_chunks[kThreads];
     const int n_cta = gridDim.x;
@@ -206,6 +218,8 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
                 const int b1 = min(b0 + kCtasPerChunk, n_cta);
                 for (int b = b0; b < b1; ++b) cs += __ldcg(part + b);
                 chunks[c] = cs;
+                for (int p = 0; p < H.xchg_world; ++p)
+                    H.xchg_data[p][((size_t)H.xchg_slot * 2 + v) * H.xchg_stride + c] = cs;
             }
             smem_chunks[threadIdx.x] = cs;
             __syncthreads();
@@ -218,6 +232,41 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
         if (threadIdx.x == 0) total[v] = grand;
     }
     if (threadIdx.x == 0) *counter = 0u;
+    if (H.xchg_world > 0) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < H.xchg_world) {
+            unsigned long long* f = H.xchg_flag[threadIdx.x] + H.xchg_slot;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(H.xchg_seq) : "memory");
+        }
+    }
+}
+
+// Reader side of the exchange: one small CTA waits until every rank has published launch `seq` for the first n proposals
+// (flags of this lane: [world][kXchgSlots]); the copy of the gathered sums to the host follows it on the stream.  A rank
+// that never arrives is reported through the status word (bit 1) after `timeout_ns` instead of hanging the GPU.
+__global__ void wait_flags_kernel(const unsigned long long* flags, int world, int n, unsigned long long seq, unsigned* status,
+                                  unsigned long long timeout_ns) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int idx = threadIdx.x; idx < world * n; idx += blockDim.x) {
+        const unsigned long long* f = flags + (size_t)(idx / n) * kXchgSlots + idx % n;
+        unsigned spins = 0;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= seq) break;
+            if ((++spins & 0x3ffu) == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > timeout_ns) {
+                    atomicOr(status, 2u);
+                    return;
+                }
+            }
+            __nanosleep(200);
+        }
+    }
 }
 
 // A slice of the root score of kBuildCells cells: sum over the regions [k0, k1) (Tree::get_od_root_score, Tree.h:1792-1805).
@@ -665,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, kOcc) score_proposals_kernel(const u
         cta_od = block_sum(contrib_od, red_buf);
         __syncthreads();
     }
-    finish_reduction(cta_sum, cta_od, H.partial, H.chunk_sums, H.total, H.counter);
+    finish_reduction(cta_sum, cta_od, H.partial, H.chunk_sums, H.total, H.counter, H);
 }
 
 // Test hook: the device lgamma on caller-provided arguments (scicone_test_lgamma).

@@ -290,6 +290,24 @@ struct scicone_dataset {
     double* d_gather = nullptr;  // per lane: [world][slots][2][max_chunks_rank]
     double* d_send = nullptr;    // per lane: [slots][2][max_chunks_rank]
     size_t gather_cap = 0;
+    // Exchange of the chunk sums through peer memory (default on cell-sharded datasets; SCICONE_EXCHANGE=nccl selects the
+    // all-gather instead): every rank owns one buffer - flags [kLanes][world][kXchgSlots], then sums
+    // [kLanes][2 (launch parity)][world][kXchgSlots][2][max_chunks_rank] - mapped into all the others (CUDA IPC), and the
+    // last CTA of a proposal stores its sums and its flag into all of them (finish_reduction, kernels.cuh).
+    bool xchg_on = false;
+    unsigned char* xchg = nullptr;
+    std::vector<void*> xchg_peer;                     // base of rank p's buffer in this process (own: xchg)
+    double** d_xchg_data_tab = nullptr;               // device: [kLanes][2][world] where this rank writes in rank p's buffer
+    unsigned long long** d_xchg_flag_tab = nullptr;   // device: [kLanes][world]
+    unsigned long long lane_seq[kLanes] = {0, 0};     // launches submitted per lane (the value published in the flags)
+    size_t xchg_flag_bytes() const { return sizeof(unsigned long long) * kLanes * world * kXchgSlots; }
+    size_t xchg_block() const { return (size_t)kXchgSlots * 2 * max_chunks_rank; }  // doubles of one rank in one (lane, parity) block
+    unsigned long long* xchg_flags(void* base, int lane, int rk) const {
+        return reinterpret_cast<unsigned long long*>(base) + ((size_t)lane * world + rk) * kXchgSlots;
+    }
+    double* xchg_data(void* base, int lane, int parity, int rk) const {
+        return reinterpret_cast<double*>(static_cast<unsigned char*>(base) + xchg_flag_bytes()) + (((size_t)lane * 2 + parity) * world + rk) * xchg_block();
+    }
     // profiling
     bool profiling = false;
     double last_kernel_us = 0.0, sum_kernel_us = 0.0, sum_build_us = 0.0;
@@ -597,6 +615,23 @@ void fill_header_common(scicone_chain* ch, int lane, int slot, DevHeader& H) {
     H.total = ds->lane_total(lane) + (size_t)slot * 2;
     H.counter = ds->d_counter + gs;
     H.status = ds->lane_status(lane) + slot;
+    if (ds->xchg_on) {
+        const unsigned long long seq = ds->lane_seq[lane];
+        H.xchg_data = ds->d_xchg_data_tab + ((size_t)lane * 2 + (seq & 1)) * ds->world;
+        H.xchg_flag = ds->d_xchg_flag_tab + (size_t)lane * ds->world;
+        H.xchg_seq = seq;
+        H.xchg_world = ds->world;
+        H.xchg_slot = slot;
+        H.xchg_stride = ds->max_chunks_rank;
+    } else {
+        H.xchg_data = nullptr;
+        H.xchg_flag = nullptr;
+        H.xchg_seq = 0;
+        H.xchg_world = 0;
+        H.xchg_slot = 0;
+        H.xchg_stride = 0;
+    }
+    H.xchg_pad = 0;
 }
 
 // The reduction scratch of a compiled blob is chosen when the batch is put together.
@@ -965,6 +1000,10 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     cudaStream_t st = lane == 0 ? ds->stream : ds->lane_stream[1];
     unsigned char* d_arena = ds->d_arena[lane];
     g.lane = lane;
+    if (ds->xchg_on) {
+        if (n > kXchgSlots) return fail(SCICONE_ERR_ARG, "at most %d proposals per launch on a cell-sharded dataset", kXchgSlots);
+        ds->lane_seq[lane]++;  // the headers below carry it
+    }
     for (int i = 0; i < n; ++i) patch_slot(chains[i], lane, i);
     g.with_od.assign((size_t)n, 0);
     LaunchEntry* offs = reinterpret_cast<LaunchEntry*>(g.h_arena);
@@ -1044,9 +1083,19 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, st));
     CUDA_TRY(cudaGetLastError());
     ds->n_launches++;
-    if (ds->world > 1) {
-        // Each rank contributes its per-chunk sums; every rank adds all chunks in global chunk order,
-        // so the total does not depend on the number of GPUs.
+    if (ds->world > 1 && ds->xchg_on) {
+        // The proposal kernel has stored this rank's chunk sums into every rank's gather buffer and published its flags;
+        // wait for the flags of all ranks, then bring the gathered sums of the n proposals to the host.  Every rank adds
+        // all chunks in global chunk order, so the total does not depend on the number of GPUs.
+        const unsigned long long seq = ds->lane_seq[lane];
+        wait_flags_kernel<<<1, 128, 0, st>>>(ds->xchg_flags(ds->xchg, lane, 0), ds->world, n, seq, ds->lane_status(lane), 60ull * 1000000000ull);
+        CUDA_TRY(cudaGetLastError());
+        ds->n_launches++;
+        const size_t width = sizeof(double) * (size_t)n * 2 * ds->max_chunks_rank;
+        CUDA_TRY(cudaMemcpy2DAsync(g.h_gather, width, ds->xchg_data(ds->xchg, lane, (int)(seq & 1), 0), sizeof(double) * ds->xchg_block(), width,
+                                   (size_t)ds->world, cudaMemcpyDeviceToHost, st));
+    } else if (ds->world > 1) {
+        // the same exchange as an NCCL all-gather of the packed chunk sums
         double* d_send = ds->d_send + (size_t)lane * ds->gather_cap;
         double* d_gather = ds->d_gather + (size_t)lane * ds->gather_cap * ds->world;
         pack_chunks_kernel<<<n, 128, 0, st>>>(ds->d_chunk + (size_t)lane * ds->slots * 2 * ds->n_chunks, ds->n_chunks, d_send, ds->max_chunks_rank);
@@ -1118,7 +1167,11 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
         }
         if (totals) totals[i] = v[0];
         if (od_scores) od_scores[i] = g.with_od[i] ? v[1] : NAN;
-        if (g.h_status[i]) nan = true;
+        if (g.h_status[i] & 1u) nan = true;
+    }
+    if (ds->world > 1 && (g.h_status[0] & 2u)) {
+        CUDA_TRY(cudaMemsetAsync(ds->lane_status(g.lane), 0, sizeof(unsigned) * ds->slots, g.lane == 0 ? ds->stream : ds->lane_stream[1]));
+        return fail(SCICONE_ERR_COMM, "a rank did not publish its chunk sums within 60 s (launches must be submitted in the same order on all ranks)");
     }
     if (nan) {
         CUDA_TRY(cudaMemsetAsync(ds->lane_status(g.lane), 0, sizeof(unsigned) * ds->slots, g.lane == 0 ? ds->stream : ds->lane_stream[1]));
@@ -1279,6 +1332,12 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     cudaSetDevice(ds->device);
     if (ds->stream) cudaStreamSynchronize(ds->stream);
     if (ds->lane_stream[1]) cudaStreamSynchronize(ds->lane_stream[1]);
+    for (int p = 0; p < (int)ds->xchg_peer.size(); ++p)
+        if (p != ds->rank && ds->xchg_peer[p]) cudaIpcCloseMemHandle(ds->xchg_peer[p]);
+    // the exported buffer itself is NOT freed here: another rank may still have it mapped, and freeing exported memory
+    // before every importer has closed it is undefined; it goes away with the process (a sharded dataset lives as long
+    // as its host process does)
+    cudaFree(ds->d_xchg_data_tab); cudaFree(ds->d_xchg_flag_tab);
     if (ds->comm_lane1 && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm_lane1);
     if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm);
     ds->pool.destroy();
@@ -1836,6 +1895,82 @@ int scicone_comm_unique_id(uint8_t out[128]) {
     return SCICONE_OK;
 }
 
+namespace {
+// all-gather of `cnt` doubles per rank through the communicator (set-up plumbing only)
+int gather_doubles(scicone_dataset* ds, const double* mine, int cnt, std::vector<double>& all) {
+    double *d_one = nullptr, *d_all = nullptr;
+    all.assign((size_t)cnt * ds->world, 0.0);
+    CUDA_TRY(cudaMalloc(&d_one, sizeof(double) * cnt));
+    CUDA_TRY(cudaMalloc(&d_all, sizeof(double) * cnt * ds->world));
+    CUDA_TRY(cudaMemcpyAsync(d_one, mine, sizeof(double) * cnt, cudaMemcpyHostToDevice, ds->stream));
+    int nrc = g_nccl.AllGather(d_one, d_all, cnt, kNcclDouble, ds->comm, ds->stream);
+    if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaStreamSynchronize(ds->stream));
+    cudaFree(d_one);
+    cudaFree(d_all);
+    return SCICONE_OK;
+}
+
+// Map every rank's gather buffer into every process (CUDA IPC over NVLink peer access).  If any rank cannot (no peer
+// access between two devices, IPC unavailable in the container), ALL ranks stay with the NCCL all-gather.
+int setup_peer_exchange(scicone_dataset* ds) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle travels as 8 doubles");
+    const int W = ds->world;
+    const size_t bytes = ds->xchg_flag_bytes() + sizeof(double) * scicone_dataset::kLanes * 2 * W * ds->xchg_block();
+    bool ok = cudaMalloc(&ds->xchg, bytes) == cudaSuccess && cudaMemset(ds->xchg, 0, bytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+    double mine[9] = {0};
+    cudaIpcMemHandle_t h;
+    if (ok) ok = cudaIpcGetMemHandle(&h, ds->xchg) == cudaSuccess;
+    if (ok) memcpy(mine, &h, 64);
+    mine[8] = ok ? 1.0 : 0.0;
+    std::vector<double> all;
+    int rc = gather_doubles(ds, mine, 9, all);
+    if (rc) return rc;
+    for (int p = 0; p < W; ++p) ok = ok && all[(size_t)p * 9 + 8] == 1.0;
+    ds->xchg_peer.assign(W, nullptr);
+    if (ok)
+        for (int p = 0; p < W && ok; ++p) {
+            if (p == ds->rank) {
+                ds->xchg_peer[p] = ds->xchg;
+                continue;
+            }
+            cudaIpcMemHandle_t hp;
+            memcpy(&hp, &all[(size_t)p * 9], 64);
+            ok = cudaIpcOpenMemHandle(&ds->xchg_peer[p], hp, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        }
+    cudaGetLastError();  // a failed probe must not poison later calls
+    // every rank must have mapped every buffer
+    double mapped = ok ? 1.0 : 0.0;
+    rc = gather_doubles(ds, &mapped, 1, all);
+    if (rc) return rc;
+    for (double v : all) ok = ok && v == 1.0;
+    if (!ok) {
+        fprintf(stderr, "libscicone_score: peer-memory exchange unavailable on rank %d, using the NCCL all-gather\n", ds->rank);
+        for (int p = 0; p < W; ++p)
+            if (p != ds->rank && ds->xchg_peer[p]) cudaIpcCloseMemHandle(ds->xchg_peer[p]);
+        ds->xchg_peer.clear();
+        cudaFree(ds->xchg);
+        ds->xchg = nullptr;
+        cudaGetLastError();
+        return SCICONE_OK;
+    }
+    std::vector<double*> data_tab((size_t)scicone_dataset::kLanes * 2 * W);
+    std::vector<unsigned long long*> flag_tab((size_t)scicone_dataset::kLanes * W);
+    for (int l = 0; l < scicone_dataset::kLanes; ++l)
+        for (int p = 0; p < W; ++p) {
+            flag_tab[(size_t)l * W + p] = ds->xchg_flags(ds->xchg_peer[p], l, ds->rank);
+            for (int par = 0; par < 2; ++par) data_tab[((size_t)l * 2 + par) * W + p] = ds->xchg_data(ds->xchg_peer[p], l, par, ds->rank);
+        }
+    CUDA_TRY(cudaMalloc(&ds->d_xchg_data_tab, sizeof(double*) * data_tab.size()));
+    CUDA_TRY(cudaMalloc(&ds->d_xchg_flag_tab, sizeof(unsigned long long*) * flag_tab.size()));
+    CUDA_TRY(cudaMemcpy(ds->d_xchg_data_tab, data_tab.data(), sizeof(double*) * data_tab.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ds->d_xchg_flag_tab, flag_tab.data(), sizeof(unsigned long long*) * flag_tab.size(), cudaMemcpyHostToDevice));
+    ds->xchg_on = true;
+    return SCICONE_OK;
+}
+}  // namespace
+
 int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128], int32_t rank, int32_t world_size) {
     if (!ds || !unique_id || world_size < 1 || rank < 0 || rank >= world_size) return fail(SCICONE_ERR_ARG, "attach_comm: bad argument");
     if (ds->comm) return fail(SCICONE_ERR_STATE, "attach_comm: communicator already attached");
@@ -1855,22 +1990,18 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
     // all ranks must agree on max_chunks_rank: exchange through the communicator
     {
         double mine = (double)ds->max_chunks_rank;
-        double *d_one = nullptr, *d_all = nullptr;
-        std::vector<double> all(world_size);
-        CUDA_TRY(cudaMalloc(&d_one, sizeof(double)));
-        CUDA_TRY(cudaMalloc(&d_all, sizeof(double) * world_size));
-        CUDA_TRY(cudaMemcpyAsync(d_one, &mine, sizeof(double), cudaMemcpyHostToDevice, ds->stream));
-        nrc = g_nccl.AllGather(d_one, d_all, 1, kNcclDouble, ds->comm, ds->stream);
-        if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
-        CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(double) * world_size, cudaMemcpyDeviceToHost, ds->stream));
-        CUDA_TRY(cudaStreamSynchronize(ds->stream));
-        cudaFree(d_one);
-        cudaFree(d_all);
+        std::vector<double> all;
+        rc = gather_doubles(ds, &mine, 1, all);
+        if (rc) return rc;
         for (double v : all) ds->max_chunks_rank = std::max(ds->max_chunks_rank, (int)v);
     }
     const int keep = ds->slots;
     ds->slots = 0;  // force reallocation with the gather buffers
-    return ds->ensure_slots(std::max(keep, 4));
+    rc = ds->ensure_slots(std::max(keep, 4));
+    if (rc) return rc;
+    const char* how = getenv("SCICONE_EXCHANGE");
+    if (how && strcmp(how, "nccl") == 0) return SCICONE_OK;
+    return setup_peer_exchange(ds);
 }
 
 int scicone_set_streams(scicone_dataset* ds, int32_t n) {
@@ -1882,7 +2013,7 @@ int scicone_set_streams(scicone_dataset* ds, int32_t n) {
     for (scicone_dataset::Segment& g : ds->seg)
         if (g.busy) return fail(SCICONE_ERR_STATE, "set_streams with launches outstanding");
     if (n > 1 && !ds->lane_stream[1]) CUDA_TRY(cudaStreamCreateWithFlags(&ds->lane_stream[1], cudaStreamNonBlocking));
-    if (n > 1 && ds->world > 1 && !ds->comm_lane1) {
+    if (n > 1 && ds->world > 1 && !ds->xchg_on && !ds->comm_lane1) {
         // cell-sharded: the all-gathers of the two lanes run concurrently, each lane needs its own communicator.  Collective:
         // every rank calls scicone_set_streams at the same point, and all ranks submit their launches in the same order.
         if (!g_nccl.CommSplit) return fail(SCICONE_ERR_COMM, "set_streams: this NCCL has no ncclCommSplit (needs >= 2.18)");

@@ -19,4 +19,7 @@ run() {  # name, extra bench args
 }
 run dynamic "$@"
 if [ -z "${SKIP_STATIC:-}" ]; then run static --n_groups 2 "$@"; fi
+if [ -n "${NCCL_TOO:-}" ]; then SCICONE_EXCHANGE=nccl run dynamic_nccl "$@"; fi
+if [ -n "${ONE_LANE:-}" ]; then run dynamic_1lane --host_args=--n_streams=1 "$@"; fi
+if [ -n "${MIN_BATCH:-}" ]; then run dynamic_mb$MIN_BATCH --host_args=--min_batch=$MIN_BATCH "$@"; fi
 ls -la "$OUT"

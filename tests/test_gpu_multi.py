@@ -24,8 +24,9 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("max_scoring,schedule,n_chains", [("true", "static", 2), ("false", "static", 2), ("true", "dynamic", 6)])
-def test_two_gpu_run_equals_one_gpu_run(tmp_path, max_scoring, schedule, n_chains):
+@pytest.mark.parametrize("max_scoring,schedule,n_chains,exchange", [("true", "static", 2, "peer"), ("false", "static", 2, "nccl"),
+                                                                     ("true", "dynamic", 6, "peer"), ("false", "dynamic", 6, "nccl")])
+def test_two_gpu_run_equals_one_gpu_run(tmp_path, max_scoring, schedule, n_chains, exchange):
     from scicone_b200.api import comm_unique_id
 
     data = make_counts(5000, 9000, 60, seed=31)  # 5 chunks of 1024 cells: shards of 3 and 2 chunks
@@ -38,11 +39,16 @@ def test_two_gpu_run_equals_one_gpu_run(tmp_path, max_scoring, schedule, n_chain
     one = subprocess.run(common + ["--postfix=one", "--device=0"], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     assert one.returncode == 0, one.stderr[-2000:]
     uid = comm_unique_id().hex()
+    # the chunk sums travel through peer memory (the proposal kernel stores them into every rank's buffer over NVLink) or,
+    # with SCICONE_EXCHANGE=nccl, through an all-gather
+    env = dict(os.environ, SCICONE_EXCHANGE=exchange)
     procs = [subprocess.Popen(common + [f"--postfix=two{k}", f"--device={k}", f"--rank={k}", "--world=2", f"--nccl_id={uid}"],
-                              cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for k in range(2)]
+                              cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for k in range(2)]
     for p in procs:
         out, err = p.communicate(timeout=600)
         assert p.returncode == 0, err[-2000:]
+        if exchange == "peer":
+            assert "peer-memory exchange unavailable" not in err, err[-500:]
     # chain c is searched by rank c % 2 (the other rank follows it through the mailbox): its owner wrote the traces
     # (dynamic schedule: rank 0 composes the launches on two lanes, rank 1 replays its launch log)
     for c in range(n_chains):
