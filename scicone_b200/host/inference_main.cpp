@@ -288,7 +288,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         HostPhaseTimes phase;
         // schedule: "dynamic" (default for several chains on one GPU) launches whatever is ready - in a cell-sharded run
         // rank 0 composes the launches and the other ranks replay its launch log; "static" moves groups of chains in lock-step
-        const std::string schedule = a.str("schedule", (world == 1 && n_chains >= 4) ? "dynamic" : "static");
+        const std::string schedule = a.str("schedule", ((world == 1 || mailbox) && n_chains >= 4) ? "dynamic" : "static");
         auto run_chains = [&](int iters, HostPhaseTimes* t) {
             if (schedule == "dynamic" && (world == 1 || mailbox))
                 infer_mcmc_dynamic(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("min_batch", 0)), t,
