@@ -152,7 +152,10 @@ int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, in
     for (int i = 0; i < n; ++i) if (int r = accept[i] ? scicone_accept(chains[i]) : scicone_reject(chains[i])) rc = r;
     return rc;
 }
-int scicone_condense_matrix(int32_t, const double*, int64_t, int64_t, const int32_t*, int32_t, double*, double*) { return fail(-2, "cpu backend: no device"); }
+int scicone_condense_matrix(int32_t, const double* bins, int64_t n_cells, int64_t n_bins, const int32_t* sizes, int32_t n_regions, double* out, double* us) {
+    if (us) *us = 0.0;
+    return orc_condense_matrix(bins, n_cells, n_bins, sizes, n_regions, out) ? fail(-1, "oracle: condense_matrix failed") : 0;
+}
 int scicone_batch_poll(scicone_dataset* ds, uint64_t ticket, int32_t* done) { *done = ds->results.count(ticket) ? 1 : 0; return *done ? 0 : fail(-3, "unknown ticket"); }
 int scicone_set_streams(scicone_dataset*, int32_t) { return 0; }
 int scicone_condense_clusters(int32_t, const double*, int64_t, int32_t, const int32_t*, int32_t, double*, int32_t*) { return fail(-2, "cpu backend: no device"); }

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "mcmc.hpp"
+#include "csv_reader.hpp"
 
 using namespace scicone_host;
 
@@ -65,26 +66,9 @@ void read_counts(std::vector<double>& mat, int n_cells, int n_regions, const std
             throw std::runtime_error(path + " holds fewer than n_cells x n_regions doubles");
         return;
     }
-    std::ifstream in(path);
-    if (!in) throw std::runtime_error("cannot open " + path);
-    std::string line;
-    int i = 0;
-    while (std::getline(in, line)) {
-        if (i >= n_cells) throw std::runtime_error("more rows in " + path + " than --n_cells");
-        const char* p = line.c_str();
-        int j = 0;
-        while (*p) {
-            char* end = nullptr;
-            double v = std::strtod(p, &end);
-            if (end == p) break;
-            if (j < n_regions) mat[static_cast<size_t>(i) * n_regions + j] = v;
-            ++j;
-            p = end;
-            while (*p == ',' || *p == ' ' || *p == '\r') ++p;
-        }
-        ++i;
-    }
-    if (i != n_cells) throw std::runtime_error("the counts file has " + std::to_string(i) + " rows, --n_cells says " + std::to_string(n_cells));
+    // the reference's format; parsed in parallel on the scoring library's worker pool (csv_reader.hpp)
+    read_counts_csv(mat, n_cells, n_regions, path, [](int n, const std::function<void(int)>& fn) { parallel_chains(n, [&fn](int i) { fn(i); }); },
+                    scicone_host_threads());
 }
 
 // Utils::read_vector (Utils.cpp:141-163): one number per line
@@ -146,7 +130,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         const int rank = static_cast<int>(a.integer("rank", 0)), world = static_cast<int>(a.integer("world", 1));
 
         if (!a.has("region_sizes_file")) { std::cerr << "the region sizes file is not provided." << std::endl; return EXIT_FAILURE; }
-        if (!a.has("d_matrix_file")) { std::cerr << "the D matrix file is not provided." << std::endl; return EXIT_FAILURE; }
+        if (!a.has("d_matrix_file") && !a.has("bins_matrix_file")) { std::cerr << "the D matrix file is not provided." << std::endl; return EXIT_FAILURE; }
         if (!a.has("n_regions")) { std::cerr << "the number of regions is not provided." << std::endl; return EXIT_FAILURE; }
         if (!a.has("n_cells")) { std::cerr << "the number of cells is not provided." << std::endl; return EXIT_FAILURE; }
         const int n_cells = static_cast<int>(a.integer("n_cells", 0));
@@ -164,12 +148,24 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
             std::cout << "Reading the input matrix..." << std::endl;
         }
         std::vector<double> D(static_cast<size_t>(n_cells) * n_regions, 0.0);
-        read_counts(D, n_cells, n_regions, a.str("d_matrix_file"));
+        if (!a.has("bins_matrix_file")) read_counts(D, n_cells, n_regions, a.str("d_matrix_file"));
         if (P.verbosity > 0) std::cout << "Reading the region_sizes file..." << std::endl;
         std::vector<int> region_sizes;
         read_vector(region_sizes, a.str("region_sizes_file"));
         if (static_cast<int>(region_sizes.size()) != n_regions)
             throw std::logic_error("Size of the counts per cell needs to be equal to the number of regions!");  // Tree.h:170-171
+        if (a.has("bins_matrix_file")) {
+            // cells x bins input (what pyscicone holds before scicone.py:276-299 collapses it): the bins of every region are
+            // summed on the device (K0, scicone_condense_matrix = Utils::condense_matrix, Utils.cpp:104-138)
+            if (!a.has("n_bins")) throw std::runtime_error("--bins_matrix_file needs --n_bins");
+            const long n_bins = a.integer("n_bins", 0);
+            std::vector<double> bins(static_cast<size_t>(n_cells) * n_bins, 0.0);
+            read_counts(bins, n_cells, static_cast<int>(n_bins), a.str("bins_matrix_file"));
+            std::vector<int32_t> sizes32(region_sizes.begin(), region_sizes.end());
+            double k0_us = 0.0;
+            abi_check(scicone_condense_matrix(device, bins.data(), n_cells, n_bins, sizes32.data(), n_regions, D.data(), &k0_us));
+            if (P.verbosity > 0) std::cout << "Condensed " << n_bins << " bins into " << n_regions << " regions (" << k0_us << " us on the device)" << std::endl;
+        }
         std::vector<int> cluster_sizes;
         if (a.has("cluster_sizes_file") && !a.str("cluster_sizes_file").empty()) {
             if (P.verbosity > 0) std::cout << "Reading the cluster_sizes file..." << std::endl;
