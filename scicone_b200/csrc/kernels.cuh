@@ -42,7 +42,14 @@ constexpr int kScRing = 4;          // most recent node scores a thread keeps in
 constexpr int kMaxOdSlices = 32;    // region slices of a root score
 constexpr int kCtasPerChunk = 8;    // 8 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
 constexpr int kBuildBlock = 256;    // threads per CTA of the build kernel
-constexpr int kBuildCells = 4;      // cells per thread of the build kernel
+constexpr int kBuildCells = 4;      // cells per thread and step of the build kernel
+constexpr int kUnitSub = 2;         // steps per unit of the build kernel
+constexpr int kUnitCells = kBuildBlock * kBuildCells * kUnitSub;  // 2048 cells per (item, block) unit
+constexpr int kLutBatch = 8;        // cells per thread that a tabulated unit gathers at a time
+constexpr int kLutMax = 2048;       // largest range of counts that is tabulated (host side: the dataset's count-range table)
+constexpr int kLutCap = 4096;       // entries of the shared-memory value table of a CTA (several regions of a slice share it)
+constexpr int kLutGroup = 32;       // regions of a slice tabulated together at most
+static_assert(kLutMax <= kLutCap, "one region's table must fit");
 constexpr int kPad = 256;           // row padding (cells)
 
 enum : unsigned {
@@ -139,7 +146,7 @@ struct alignas(16) DevBuild {
     const double* src;     // BUILD_G: Dt[k] or S;  slices: Dt
     double c1;             // BUILD_G: (nu*cn)*r or nu*z
     unsigned off_rows;     // OD slices: arena offset of rows[K]: where lgamma(D_k + arg[k]) of region k is also stored (or null)
-    unsigned pad;
+    unsigned lut_row;      // BUILD_G: 1 + row of the count-range table that describes src (region k, or K for S); 0: none
     unsigned kind;
     int k0, k1;            // slices: region range
     unsigned off_arg;      // slices: arena offsets of arg[K], cc[K]
@@ -314,64 +321,172 @@ __device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned c
         if (ok[q]) it.dst[j0 + q * kBuildBlock] = acc[q];
 }
 
+// The same slice for a unit whose counts are integers in a narrow range (the normal case: read counts): the CTA tabulates
+// lgamma(v + arg_k) once for every value v the unit's cells can hold in region k, for as many regions of the slice as
+// fit the table, and the cells pick their entries - the same function of the same argument as the direct evaluation,
+// bit for bit, at a fraction of the lgamma work.  `info` = {min, range} pairs of this unit's block, one per region
+// (stride info_stride ints); the caller has checked that every region of the slice has a table there.  A slice whose
+// tables do not fit at once is done in groups of regions, the partial sums waiting in dst in between (the order of
+// the additions of a cell is that of build_slice: regions ascending).
+__device__ __forceinline__ void build_slice_lut(const DevBuild& it, const unsigned char* __restrict__ arena, int base, const double* tbl,
+                                                double* vals, int* offs, const int* __restrict__ info, int info_stride) {
+    const double* arg = reinterpret_cast<const double*>(arena + it.off_arg);
+    const double* cc = reinterpret_cast<const double*>(arena + it.off_c);
+    double* const* keep = reinterpret_cast<double* const*>(arena + it.off_rows);
+    int k = it.k0;
+    while (k < it.k1) {
+        if (threadIdx.x == 0) {  // regions [k, k + n) share the table: offs[i] = first entry of region k + i
+            int tot = 0, n = 0;
+            offs[0] = 0;
+            while (k + n < it.k1 && n < kLutGroup) {
+                const int r = info[(long long)(k + n) * info_stride + 1];
+                if (tot + r > kLutCap) break;
+                tot += r;
+                ++n;
+                offs[n] = tot;
+            }
+            offs[kLutGroup + 1] = n;
+        }
+        __syncthreads();
+        const int n = offs[kLutGroup + 1];
+        const int tot = offs[n];
+        for (int e = threadIdx.x; e < tot; e += kBuildBlock) {
+            int g = 0;
+            while (offs[g + 1] <= e) ++g;
+            const int vmin = info[(long long)(k + g) * info_stride];
+            vals[e] = lgam((double)(vmin + (e - offs[g])) + arg[k + g], tbl);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int b = 0; b < kUnitCells / (kBuildBlock * kLutBatch); ++b) {
+            const int j0 = base + b * kBuildBlock * kLutBatch + threadIdx.x;
+            if (j0 >= it.n_cells) break;  // no barrier inside this loop
+            double acc[kLutBatch];
+            bool ok[kLutBatch];
+#pragma unroll
+            for (int q = 0; q < kLutBatch; ++q) {
+                ok[q] = j0 + q * kBuildBlock < it.n_cells;
+                acc[q] = (k == it.k0 || !ok[q]) ? 0.0 : it.dst[j0 + q * kBuildBlock];
+            }
+            for (int g = 0; g < n; ++g) {
+                const double* row = it.src + (long long)(k + g) * it.row_stride + j0;
+                const double c = cc[k + g];
+                double* const out = keep[k + g];
+                const int shift = offs[g] - info[(long long)(k + g) * info_stride];
+                int idx[kLutBatch];
+#pragma unroll
+                for (int q = 0; q < kLutBatch; ++q) idx[q] = ok[q] ? (int)__ldg(row + q * kBuildBlock) + shift : offs[g];
+#pragma unroll
+                for (int q = 0; q < kLutBatch; ++q) {
+                    const double v = vals[idx[q]];
+                    if (out && ok[q]) out[j0 + q * kBuildBlock] = v;
+                    acc[q] += v;
+                    acc[q] -= c;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kLutBatch; ++q)
+                if (ok[q]) it.dst[j0 + q * kBuildBlock] = acc[q];
+        }
+        __syncthreads();  // the table is rewritten by the next group / unit
+        k += n;
+    }
+}
+
 // ---------------------------------------------------------------------------------
-// K1: data-only lgamma work.  Persistent grid (up to 4 CTAs per SM) over n_items x ceil(M / (kBuildBlock * kBuildCells)) units.
+// K1: data-only lgamma work.  Persistent grid (up to 4 CTAs per SM) over n_items x ceil(M / kUnitCells) units.
+//
+// `lut` (or null) is the dataset's count-range table: for every row of counts (regions 0..K-1, then the row sums S) and
+// every block of kUnitCells cells, {smallest count, number of distinct values to tabulate} - the second is 0 where the
+// counts are not integers, or spread too widely for a table to pay.  A unit with a table evaluates lgamma once per
+// possible count (typically a few hundred) instead of once per cell (2048).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBuildBlock, 4)
-    build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items, int n_items, int blocks_per_row) {
-    // Persistent CTAs: a unit of work is (item, block of kBuildBlock * kBuildCells cells).  A unit is only ~4 lgamma per
-    // thread, so the fixed latencies (table copy, item record, data load: ~2.5 us) are paid once per CTA / hidden by
-    // fetching the next unit's record and data while the current unit is evaluated.
+    build_rows_kernel(const unsigned char* __restrict__ arena, unsigned off_items, int n_items, int blocks_per_row,
+                      const int* __restrict__ lut) {
     __shared__ double tbl[kLogTableDoubles];
+    __shared__ double vals[kLutCap];
+    __shared__ int offs[kLutGroup + 2];
     load_log_table<kBuildBlock>(tbl);
     const DevBuild* items = reinterpret_cast<const DevBuild*>(arena + off_items);
     const int total = n_items * blocks_per_row;
-    int u = blockIdx.x;
-    // next unit's record (the fields the one-lgamma path needs) and data
-    unsigned nkind = 0;
-    double* ndst = nullptr;
-    const double* nsrc = nullptr;
-    double nc1 = 0.0;
-    int nn = 0;
-    double nd[kBuildCells];
-    auto fetch = [&](int unit) {
-        const DevBuild& it = items[unit / blocks_per_row];
-        nkind = it.kind;
-        ndst = it.dst;
-        nsrc = it.src;
-        nc1 = it.c1;
-        nn = it.n_cells;
-        if (nkind == BUILD_G) {
-            const int j0 = (unit % blocks_per_row) * (kBuildBlock * kBuildCells) + threadIdx.x;
+    __syncthreads();  // table loaded
+    for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        const DevBuild& it = items[u / blocks_per_row];
+        const int blk = u % blocks_per_row;
+        const int base = blk * kUnitCells;
+        const unsigned kind = it.kind;
+        if (kind == BUILD_G) {  // one lgamma per cell: L(k, cn) (Tree.h:214-218) or the z-term of a node (Tree.h:229-231)
+            double* const dst = it.dst;
+            const double* const src = it.src;
+            const double c1 = it.c1;
+            const int n_cells = it.n_cells;
+            int vmin = 0, range = 0;
+            if (lut != nullptr && it.lut_row != 0) {
+                const int* info = lut + ((long long)(it.lut_row - 1) * blocks_per_row + blk) * 2;
+                vmin = info[0];
+                range = info[1];
+            }
+            if (range > 0) {  // uniform over the CTA: tabulate, then gather kLutBatch cells per thread at a time
+                int idx[kLutBatch];
+                auto load = [&](int b) {
 #pragma unroll
-            for (int q = 0; q < kBuildCells; ++q) {
-                const int j = j0 + q * kBuildBlock;
-                nd[q] = j < nn ? __ldg(nsrc + j) : 32.0;
+                    for (int q = 0; q < kLutBatch; ++q) {
+                        const int j = base + (b * kLutBatch + q) * kBuildBlock + threadIdx.x;
+                        idx[q] = j < n_cells ? (int)__ldg(src + j) - vmin : 0;
+                    }
+                };
+                load(0);
+                for (int i = threadIdx.x; i < range; i += kBuildBlock) vals[i] = lgam((double)(vmin + i) + c1, tbl);
+                __syncthreads();
+#pragma unroll 1
+                for (int b = 0; b < kUnitCells / (kBuildBlock * kLutBatch); ++b) {
+                    if (base + b * kLutBatch * kBuildBlock >= n_cells) break;  // uniform
+                    double v[kLutBatch];
+#pragma unroll
+                    for (int q = 0; q < kLutBatch; ++q) v[q] = vals[idx[q]];
+                    const int jb = base + b * kLutBatch * kBuildBlock + threadIdx.x;
+                    if (b + 1 < kUnitCells / (kBuildBlock * kLutBatch) && jb + kLutBatch * kBuildBlock - threadIdx.x < n_cells) load(b + 1);
+#pragma unroll
+                    for (int q = 0; q < kLutBatch; ++q) {
+                        const int j = jb + q * kBuildBlock;
+                        if (j < n_cells) dst[j] = v[q];
+                    }
+                }
+                __syncthreads();
+            } else {
+#pragma unroll 1
+                for (int h = 0; h < kUnitSub; ++h) {  // kBuildCells lgamma chains at a time
+                    const int j0 = base + h * kBuildCells * kBuildBlock + threadIdx.x;
+                    if (j0 >= n_cells) break;
+                    double d[kBuildCells];
+#pragma unroll
+                    for (int q = 0; q < kBuildCells; ++q) {
+                        const int j = j0 + q * kBuildBlock;
+                        d[q] = j < n_cells ? __ldg(src + j) : 32.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < kBuildCells; ++q) {
+                        const int j = j0 + q * kBuildBlock;
+                        if (j < n_cells) dst[j] = lgam(d[q] + c1, tbl);
+                    }
+                }
+            }
+        } else {
+            bool tabulated = kind == BUILD_OD_SLICE && lut != nullptr;
+            if (tabulated)
+                for (int k = it.k0; k < it.k1; ++k) tabulated = tabulated && lut[((long long)k * blocks_per_row + blk) * 2 + 1] > 0;
+            if (tabulated) {
+                build_slice_lut(it, arena, base, tbl, vals, offs, lut + (long long)blk * 2, 2 * blocks_per_row);
+                continue;
+            }
+#pragma unroll 1
+            for (int sub = 0; sub < kUnitSub; ++sub) {
+                const int j0 = base + sub * kBuildBlock * kBuildCells + threadIdx.x;
+                if (j0 - threadIdx.x >= it.n_cells) break;
+                build_slice(it, arena, j0, tbl);
             }
         }
-    };
-    if (u < total) fetch(u);
-    __syncthreads();  // table loaded
-    while (u < total) {
-        const unsigned kind = nkind;
-        double* const dst = ndst;
-        const double c1 = nc1;
-        const int n_cells = nn;
-        double d[kBuildCells];
-#pragma unroll
-        for (int q = 0; q < kBuildCells; ++q) d[q] = nd[q];
-        const int cur = u;
-        u += gridDim.x;
-        if (u < total) fetch(u);
-        const int j0 = (cur % blocks_per_row) * (kBuildBlock * kBuildCells) + threadIdx.x;
-        if (kind == BUILD_G) {  // one lgamma per cell: L(k, cn) (Tree.h:214-218) or the z-term of a node (Tree.h:229-231)
-#pragma unroll
-            for (int q = 0; q < kBuildCells; ++q) {
-                const int j = j0 + q * kBuildBlock;
-                if (j < n_cells) dst[j] = lgam(d[q] + c1, tbl);
-            }
-        } else
-            build_slice(items[cur / blocks_per_row], arena, j0, tbl);
     }
 }
 

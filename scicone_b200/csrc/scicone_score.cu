@@ -242,6 +242,9 @@ struct scicone_dataset {
 
     double* dDt = nullptr;
     double* dS = nullptr;
+    // count-range table of K1 (kernels.cuh, build_rows_kernel): [K + 1 rows: regions, then S][blocks of kUnitCells cells]{min, range}
+    int* d_lut = nullptr;
+    double lut_share = 0.0;  // fraction of the (row, block) pairs that are tabulated
     int* dW = nullptr;
     cudaStream_t stream = nullptr;
     RowPool pool;
@@ -1033,6 +1036,10 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
                 const bool slice = src.kind == BUILD_OD_SLICE || src.kind == BUILD_OD_SLICE_LOG;
                 if (slice != (pass == 0)) continue;
                 DevBuild it = src;
+                if (it.kind == BUILD_G && ds->d_lut) {  // which row of counts the item reads: region k, or the row sums
+                    if (it.src == ds->dS) it.lut_row = (unsigned)ds->K + 1;
+                    else if (it.src >= ds->dDt && it.src < ds->dDt + (size_t)ds->K * ds->Mp) it.lut_row = (unsigned)((it.src - ds->dDt) / ds->Mp) + 1;
+                }
                 if (slice) {
                     it.off_arg += (unsigned)chain_aux;
                     it.off_c += (unsigned)chain_aux;
@@ -1051,10 +1058,10 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     CUDA_TRY(cudaMemcpyAsync(d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, st));
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, st));
-        const int blocks_per_row = (ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells);
+        const int blocks_per_row = (ds->M + kUnitCells - 1) / kUnitCells;
         const long long units = (long long)n_items * blocks_per_row;
         build_rows_kernel<<<(unsigned)std::min<long long>(units, 4ll * ds->n_sm), kBuildBlock, 0, st>>>(
-            d_arena, (unsigned)off_items, (int)n_items, blocks_per_row);
+            d_arena, (unsigned)off_items, (int)n_items, blocks_per_row, ds->d_lut);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
     }
@@ -1310,6 +1317,56 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
         dim3 grid((ds->K + 31) / 32, (ds->M + 31) / 32), block(32, 8);
         transpose_kernel<<<grid, block, 0, ds->stream>>>(dD, ds->dDt, ds->M, ds->K, (long long)ds->Mp);
         row_sum_kernel<<<(ds->M + 127) / 128, 128, 0, ds->stream>>>(ds->dDt, ds->dS, ds->M, ds->K, (long long)ds->Mp);
+        // Count-range table: read counts are integers, and the counts of one region over a block of 2048 cells take a few
+        // hundred distinct values - K1 then evaluates lgamma(count + c) once per possible count instead of once per cell
+        // (identical results: the same function of the same argument).  A (row, block) pair is tabulated when all its
+        // values are non-negative integers and the table is at most half as long as the block; SCICONE_LUT=0 turns it off.
+        const char* lut_env = getenv("SCICONE_LUT");
+        if (!(lut_env && atoi(lut_env) == 0)) {
+            const int K = ds->K, M = ds->M;
+            const int bpr = (M + kUnitCells - 1) / kUnitCells;
+            std::vector<int> lut((size_t)(K + 1) * bpr * 2, 0);
+            std::vector<double> lo((size_t)K + 1), hi((size_t)K + 1);
+            std::vector<char> integral((size_t)K + 1);
+            size_t n_tab = 0;
+            for (int b = 0; b < bpr; ++b) {
+                const int j0 = b * kUnitCells, j1 = std::min(M, j0 + kUnitCells);
+                std::fill(lo.begin(), lo.end(), 1e300);
+                std::fill(hi.begin(), hi.end(), -1e300);
+                std::fill(integral.begin(), integral.end(), 1);
+                for (int j = j0; j < j1; ++j) {
+                    const double* row = d->D + (size_t)j * K;
+                    double sum = 0.0;
+                    bool all_int = true;
+                    for (int k = 0; k < K; ++k) {
+                        const double v = row[k];
+                        sum = sum + v;  // the order of row_sum_kernel; exact for integer counts anyway
+                        if (!(v >= 0.0 && v < 1073741824.0 && v == std::floor(v))) {
+                            integral[k] = 0;
+                            all_int = false;
+                        }
+                        lo[k] = std::min(lo[k], v);
+                        hi[k] = std::max(hi[k], v);
+                    }
+                    if (!all_int || !(sum < 1073741824.0)) integral[K] = 0;
+                    lo[K] = std::min(lo[K], sum);
+                    hi[K] = std::max(hi[K], sum);
+                }
+                for (int k = 0; k <= K; ++k) {
+                    if (!integral[k]) continue;
+                    const double range = hi[k] - lo[k] + 1.0;
+                    if (range > (double)kLutMax || 2.0 * range > (double)(j1 - j0)) continue;
+                    lut[((size_t)k * bpr + b) * 2] = (int)lo[k];
+                    lut[((size_t)k * bpr + b) * 2 + 1] = (int)range;
+                    ++n_tab;
+                }
+            }
+            ds->lut_share = (double)n_tab / (double)((size_t)(K + 1) * bpr);
+            if (n_tab) {
+                DS_TRY(cudaMalloc(&ds->d_lut, sizeof(int) * lut.size()));
+                DS_TRY(cudaMemcpy(ds->d_lut, lut.data(), sizeof(int) * lut.size(), cudaMemcpyHostToDevice));
+            }
+        }
         cudaError_t e2 = cudaMemcpyAsync(ds->dW, d->cluster_sizes, sizeof(int) * ds->M, cudaMemcpyHostToDevice, ds->stream);
         cudaError_t e3 = cudaStreamSynchronize(ds->stream);
         cudaFree(dD);
@@ -1341,7 +1398,7 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     if (ds->comm_lane1 && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm_lane1);
     if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm);
     ds->pool.destroy();
-    cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW);
+    cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW); cudaFree(ds->d_lut);
     for (unsigned char* a : ds->d_arena) cudaFree(a);
     cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
     cudaFree(ds->d_counter); cudaFree(ds->d_gather); cudaFree(ds->d_send);

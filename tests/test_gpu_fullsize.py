@@ -118,3 +118,35 @@ def test_config4_shape_weights_scale_the_total_exactly_and_batches_equal_single_
             ch.accept() if step % 2 == 0 else ch.reject()
         if step % 2 == 0:
             tree = t2
+
+
+@pytest.mark.parametrize("M", [10000, 2500])
+def test_tabulated_lgamma_rows_equal_direct_evaluation_bit_for_bit(M, monkeypatch):
+    """K1 evaluates lgamma(count + c) once per possible count of a block of cells when the counts are integers in a
+    narrow range (the dataset's count-range table) - the same function of the same argument, so every total and every
+    score must be IDENTICAL to a dataset created with SCICONE_LUT=0 (direct evaluation per cell), nu proposals (all rows
+    rebuilt, root-score slices) included.  A matrix with some non-integer and some widely spread regions mixes both
+    paths inside one launch."""
+    from scicone_b200.api import Chain, Dataset
+
+    K, N = 200, 30
+    data = make_counts(M, 18000, K, seed=SEED + 3)
+    D = data["D"].copy()
+    if M == 10000:  # (the other case keeps integer counts everywhere: the row sums S are tabulated too)
+        D[:, 5] += 0.5                  # not integers: direct
+        D[::7, 11] += 40000.0           # range too wide: direct
+    kw = dict(neutral_states=data["neutral_states"], cluster_sizes=data["cluster_sizes"], is_overdispersed=1, max_scoring=1)
+    monkeypatch.setenv("SCICONE_LUT", "1")
+    ds_tab = Dataset(D, data["region_sizes"], **kw)
+    monkeypatch.setenv("SCICONE_LUT", "0")
+    ds_dir = Dataset(D, data["region_sizes"], **kw)
+    monkeypatch.delenv("SCICONE_LUT")
+    a, b = Chain(dataset=ds_tab), Chain(dataset=ds_dir)
+    tree = TreeState(K, data["neutral_states"], np.random.default_rng(15), nu=1.0).grow(N)
+    ft = tree.flat()
+    assert a.compute_t_table(ft) == b.compute_t_table(ft)
+    assert a.compute_t_od_scores(ft.nu) == b.compute_t_od_scores(ft.nu)
+    tree, totals = _walk([a, b], tree, 60, np.random.default_rng(16))
+    assert len(totals) > 30 and np.array_equal(totals[:, 0], totals[:, 1])
+    assert np.array_equal(a.read_t_scores(), b.read_t_scores())
+    assert np.array_equal(a.read_t_sums(), b.read_t_sums())
