@@ -328,39 +328,56 @@ __device__ __forceinline__ void build_slice(const DevBuild& it, const unsigned c
 // (stride info_stride ints); the caller has checked that every region of the slice has a table there.  A slice whose
 // tables do not fit at once is done in groups of regions, the partial sums waiting in dst in between (the order of
 // the additions of a cell is that of build_slice: regions ascending).
+struct SliceStage {  // per-region constants of the group of regions whose tables are resident (shared memory)
+    int offs[kLutGroup + 1];  // first table entry of region g
+    int vmin[kLutGroup];
+    int range[kLutGroup];
+    double arg[kLutGroup];
+    double c[kLutGroup];
+    double* keep[kLutGroup];
+    int n;
+};
+
 __device__ __forceinline__ void build_slice_lut(const DevBuild& it, const unsigned char* __restrict__ arena, int base, const double* tbl,
-                                                double* vals, int* offs, const int* __restrict__ info, int info_stride) {
+                                                double* vals, SliceStage& st, const int* __restrict__ info, int info_stride) {
     const double* arg = reinterpret_cast<const double*>(arena + it.off_arg);
     const double* cc = reinterpret_cast<const double*>(arena + it.off_c);
     double* const* keep = reinterpret_cast<double* const*>(arena + it.off_rows);
     int k = it.k0;
     while (k < it.k1) {
-        if (threadIdx.x == 0) {  // regions [k, k + n) share the table: offs[i] = first entry of region k + i
-            int tot = 0, n = 0;
-            offs[0] = 0;
-            while (k + n < it.k1 && n < kLutGroup) {
-                const int r = info[(long long)(k + n) * info_stride + 1];
-                if (tot + r > kLutCap) break;
-                tot += r;
-                ++n;
-                offs[n] = tot;
-            }
-            offs[kLutGroup + 1] = n;
+        // the constants of up to kLutGroup regions, fetched side by side ...
+        if (threadIdx.x < kLutGroup && k + (int)threadIdx.x < it.k1) {
+            const int g = threadIdx.x;
+            st.vmin[g] = info[(long long)(k + g) * info_stride];
+            st.range[g] = info[(long long)(k + g) * info_stride + 1];
+            st.arg[g] = arg[k + g];
+            st.c[g] = cc[k + g];
+            st.keep[g] = keep[k + g];
         }
         __syncthreads();
-        const int n = offs[kLutGroup + 1];
-        const int tot = offs[n];
+        if (threadIdx.x == 0) {  // ... then as many of them as fit the value table: offs[g] = first entry of region k + g
+            int tot = 0, n = 0;
+            st.offs[0] = 0;
+            while (k + n < it.k1 && n < kLutGroup && tot + st.range[n] <= kLutCap) {
+                tot += st.range[n];
+                ++n;
+                st.offs[n] = tot;
+            }
+            st.n = n;
+        }
+        __syncthreads();
+        const int n = st.n;
+        const int tot = st.offs[n];
         for (int e = threadIdx.x; e < tot; e += kBuildBlock) {
             int g = 0;
-            while (offs[g + 1] <= e) ++g;
-            const int vmin = info[(long long)(k + g) * info_stride];
-            vals[e] = lgam((double)(vmin + (e - offs[g])) + arg[k + g], tbl);
+            while (st.offs[g + 1] <= e) ++g;
+            vals[e] = lgam((double)(st.vmin[g] + (e - st.offs[g])) + st.arg[g], tbl);
         }
         __syncthreads();
 #pragma unroll 1
         for (int b = 0; b < kUnitCells / (kBuildBlock * kLutBatch); ++b) {
             const int j0 = base + b * kBuildBlock * kLutBatch + threadIdx.x;
-            if (j0 >= it.n_cells) break;  // no barrier inside this loop
+            if (j0 - (int)threadIdx.x >= it.n_cells) break;  // uniform; no barrier inside this loop anyway
             double acc[kLutBatch];
             bool ok[kLutBatch];
 #pragma unroll
@@ -368,17 +385,25 @@ __device__ __forceinline__ void build_slice_lut(const DevBuild& it, const unsign
                 ok[q] = j0 + q * kBuildBlock < it.n_cells;
                 acc[q] = (k == it.k0 || !ok[q]) ? 0.0 : it.dst[j0 + q * kBuildBlock];
             }
-            for (int g = 0; g < n; ++g) {
-                const double* row = it.src + (long long)(k + g) * it.row_stride + j0;
-                const double c = cc[k + g];
-                double* const out = keep[k + g];
-                const int shift = offs[g] - info[(long long)(k + g) * info_stride];
-                int idx[kLutBatch];
+            // the counts of region g + 1 are in flight while region g is looked up
+            double d[kLutBatch], dn[kLutBatch];
+            const double* row = it.src + (long long)k * it.row_stride + j0;
 #pragma unroll
-                for (int q = 0; q < kLutBatch; ++q) idx[q] = ok[q] ? (int)__ldg(row + q * kBuildBlock) + shift : offs[g];
+            for (int q = 0; q < kLutBatch; ++q) dn[q] = ok[q] ? __ldg(row + q * kBuildBlock) : 0.0;
+            for (int g = 0; g < n; ++g) {
+#pragma unroll
+                for (int q = 0; q < kLutBatch; ++q) d[q] = dn[q];
+                if (g + 1 < n) {
+                    row += it.row_stride;
+#pragma unroll
+                    for (int q = 0; q < kLutBatch; ++q) dn[q] = ok[q] ? __ldg(row + q * kBuildBlock) : 0.0;
+                }
+                const double c = st.c[g];
+                double* const out = st.keep[g];
+                const int shift = st.offs[g] - st.vmin[g];
 #pragma unroll
                 for (int q = 0; q < kLutBatch; ++q) {
-                    const double v = vals[idx[q]];
+                    const double v = vals[ok[q] ? (int)d[q] + shift : st.offs[g]];
                     if (out && ok[q]) out[j0 + q * kBuildBlock] = v;
                     acc[q] += v;
                     acc[q] -= c;
@@ -388,7 +413,7 @@ __device__ __forceinline__ void build_slice_lut(const DevBuild& it, const unsign
             for (int q = 0; q < kLutBatch; ++q)
                 if (ok[q]) it.dst[j0 + q * kBuildBlock] = acc[q];
         }
-        __syncthreads();  // the table is rewritten by the next group / unit
+        __syncthreads();  // the table and the constants are rewritten by the next group / unit
         k += n;
     }
 }
@@ -406,7 +431,7 @@ __global__ void __launch_bounds__(kBuildBlock, 4)
                       const int* __restrict__ lut) {
     __shared__ double tbl[kLogTableDoubles];
     __shared__ double vals[kLutCap];
-    __shared__ int offs[kLutGroup + 2];
+    __shared__ SliceStage stage;
     load_log_table<kBuildBlock>(tbl);
     const DevBuild* items = reinterpret_cast<const DevBuild*>(arena + off_items);
     const int total = n_items * blocks_per_row;
@@ -477,7 +502,7 @@ __global__ void __launch_bounds__(kBuildBlock, 4)
             if (tabulated)
                 for (int k = it.k0; k < it.k1; ++k) tabulated = tabulated && lut[((long long)k * blocks_per_row + blk) * 2 + 1] > 0;
             if (tabulated) {
-                build_slice_lut(it, arena, base, tbl, vals, offs, lut + (long long)blk * 2, 2 * blocks_per_row);
+                build_slice_lut(it, arena, base, tbl, vals, stage, lut + (long long)blk * 2, 2 * blocks_per_row);
                 continue;
             }
 #pragma unroll 1
