@@ -86,6 +86,12 @@ typedef struct scicone_dataset_desc {
 int scicone_abi_version(void);
 const char* scicone_last_error(void);
 
+/*
+ * Uploads the matrix (transposed to region-major on the device) and the per-cell read totals.  D may hold any doubles;
+ * where the counts of a region over a block of 2048 cells are non-negative integers in a narrow range (read counts are),
+ * the lgamma rows of that block are evaluated once per possible count instead of once per cell - the results are
+ * bit-identical either way (environment SCICONE_LUT=0 turns the tabulation off, for A/B runs).
+ */
 int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* desc);
 void scicone_dataset_destroy(scicone_dataset* ds);
 
