@@ -748,7 +748,7 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
     if (G > 4) G = 4;  // the library keeps at most 8 launches in flight
     parallel_chains(B, [&](int b) {
         chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
-        chains[b]->open_traces(n_iters);
+        if (mailbox == nullptr || b % world == rank) chains[b]->open_traces(n_iters);  // a follower writes no traces
     });
     struct Group {
         std::vector<int> members;

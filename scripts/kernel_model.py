@@ -66,4 +66,4 @@ cases = {
 }
 for name, kinds in cases.items():
     s, b, t = launch(kinds)
-    print(f"{name:28s} score(+K1b) {s:7.1f} us   K1 {b:7.1f} us   rescored nodes {t}")
+    print(f"{name:28s} K2-K4 {s:7.1f} us   K1 {b:7.1f} us   rescored nodes {t}")
