@@ -394,7 +394,7 @@ def run_native_host(args, data, rank, world, local, dist, comm_unique_id):
         stats = os.path.join(tmp, f"stats{rank}.json")
         cmd = [exe, f"--d_matrix_file={d}", f"--region_sizes_file={r}", f"--n_cells={full.shape[0]}", f"--n_regions={Kr}",
                f"--n_iters={args.steps}", f"--warmup_iters={args.warmup}", f"--n_nodes={args.nodes - 1}", "--seed=42", f"--nu={args.nu}",
-               "--verbosity=0", f"--max_scoring={'true' if args.max_scoring else 'false'}", f"--postfix=e2e{rank}",
+               "--verbosity=0", "--no_cnv_file=1", f"--max_scoring={'true' if args.max_scoring else 'false'}", f"--postfix=e2e{rank}",
                f"--n_chains={args.chains}", f"--device={local}", f"--stats_file={stats}", "--stats_all_ranks=1"]
         if args.n_groups:
             cmd += [f"--n_groups={args.n_groups}", "--schedule=static"]

@@ -378,6 +378,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
             // Utils::regions_to_bins_cnvs (Utils.cpp:165-188) + the writer of infer_trees.cpp:321-331: cells x bins as text.
             // A region contributes its copy number once per bin; the repeated "v," run of every (value, region width) is
             // copied from a prebuilt pattern instead of being formatted bin by bin (2 G values at configs[4]).
+            if (!a.flag("no_cnv_file", false)) {  // (timing runs skip the cells x bins text: 4 GB per chain at configs[4])
             std::ofstream f_cnvs("./" + pf + "_inferred_cnvs.csv");
             int widest = 0;
             for (int k = 0; k < n_regions; ++k) widest = std::max(widest, region_sizes[k]);
@@ -403,6 +404,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
                 f_cnvs.write(row.data(), static_cast<std::streamsize>(row.size()));
             }
             f_cnvs.flush();
+            }
             if (P.verbosity > 1) {
                 int32_t nn = 0;
                 abi_check(scicone_t_n_nodes(inf->chain, &nn));

@@ -49,7 +49,7 @@ def main():
         common.append(f"--cluster_sizes_file={w}")
     stats = os.path.join(tmp, "stats.json")
     cmd = [os.path.join(ROOT, "scicone_b200", "bin", "inference")] + common + [f"--n_iters={a.iters}", f"--n_chains={a.chains}",
-                                                                                 "--postfix=nat", f"--stats_file={stats}"] + a.extra.split()
+                                                                                 "--postfix=nat", f"--stats_file={stats}", "--no_cnv_file=1"] + a.extra.split()
     t0 = time.perf_counter()
     res = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
     wall = time.perf_counter() - t0
