@@ -870,7 +870,7 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     if (B == 0 || n_iters <= 0) return;
     if (world > 1 && mailbox == nullptr) throw std::runtime_error("the dynamic schedule of a multi-process run needs the mailbox");
     scicone_dataset* ds = chains[0]->ds;
-    if (min_batch <= 0) min_batch = std::max(1, B / 5);  // measured at 32 chains: 6 -> 161.6, 8 -> 163.6, 10 -> 166.4, 12 -> 181.8, 16 -> 221.8 us per iteration
+    if (min_batch <= 0) min_batch = std::max(1, B / 4);  // 32 chains x 10 k cells: 6 -> 161.6, 8 -> 163.6, 10 -> 166.4, 12 -> 181.8 us per iteration; 16 chains x 100 k cells: 3 -> 488, 5 -> 458
     // two launch streams: K1 of one launch overlaps the proposal kernel of the other (a launch is always collected here
     // before its chains are settled, which is what the second stream requires)
     if (n_streams > 1) abi_check(scicone_set_streams(ds, 2));
