@@ -11,6 +11,10 @@
 //   z-term rows  [Mp]   lgamma(S[j] + nu*z_node), built by build_rows_kernel for every rescored node of a launch
 //   score rows   [Mp]   one row per tree node: attachment score of every cell to that node
 //   aggregates   [Mp]   per-cell log-sum-exp (or max) over the nodes, + argmax id in max mode
+//   lut       [K+1][blocks][2]  count-range table: {min, range} of every row of counts per block of kUnitCells cells
+//                       (0 where the counts are not integers in a narrow range): lets K1 evaluate lgamma once per count
+//   gather buffer (multi-GPU) flags + per-rank chunk sums, mapped into every rank: written by finish_reduction of ALL
+//                       ranks over NVLink, read by wait_flags_kernel + one copy to the host
 //
 // Two kernels per batch of proposals:
 //   build_rows_kernel       (K1) every lgamma of the path (Tree::compute_score, reference scicone/src/Tree.h:214-231;
