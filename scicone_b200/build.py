@@ -46,7 +46,7 @@ def build_host(force=False):
     host = os.path.join(HERE, "host")
     bin_dir = os.path.join(HERE, "bin")
     os.makedirs(bin_dir, exist_ok=True)
-    srcs = [os.path.join(host, f) for f in ("inference_main.cpp", "mcmc.hpp", "tree.hpp", "rng_dist.hpp", "csv_reader.hpp")]
+    srcs = [os.path.join(host, f) for f in ("inference_main.cpp", "mcmc.hpp", "tree.hpp", "rng_dist.hpp", "csv_reader.hpp", "cnv_writer.hpp")]
     srcs.append(os.path.join(ROOT, "include", "scicone_score.h"))
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     common = [cxx, "-std=c++17", "-O2", "-fno-fast-math", "-ffp-contract=off", "-Wall", "-Wno-sign-compare", srcs[0],

@@ -17,6 +17,7 @@
 
 #include "mcmc.hpp"
 #include "csv_reader.hpp"
+#include "cnv_writer.hpp"
 
 using namespace scicone_host;
 
@@ -375,36 +376,12 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
             }
             std::ofstream f_tree("./" + pf + "_tree_inferred.txt");
             inf->best_tree.write(f_tree);
-            // Utils::regions_to_bins_cnvs (Utils.cpp:165-188) + the writer of infer_trees.cpp:321-331: cells x bins as text.
-            // A region contributes its copy number once per bin; the repeated "v," run of every (value, region width) is
-            // copied from a prebuilt pattern instead of being formatted bin by bin (2 G values at configs[4]).
-            if (!a.flag("no_cnv_file", false)) {  // (timing runs skip the cells x bins text: 4 GB per chain at configs[4])
-            std::ofstream f_cnvs("./" + pf + "_inferred_cnvs.csv");
-            int widest = 0;
-            for (int k = 0; k < n_regions; ++k) widest = std::max(widest, region_sizes[k]);
-            std::map<int, std::string> pattern;  // copy number -> "v,v,v,..." for the widest region
-            std::string row;
-            for (int j = 0; j < M; ++j) {
-                row.clear();
-                for (int k = 0; k < n_regions; ++k) {
-                    const int v = cn[static_cast<size_t>(j) * n_regions + k];
-                    auto it = pattern.find(v);
-                    if (it == pattern.end()) {
-                        const std::string tok = std::to_string(v) + ",";
-                        std::string rep;
-                        rep.reserve(tok.size() * widest);
-                        for (int b = 0; b < widest; ++b) rep += tok;
-                        it = pattern.emplace(v, std::move(rep)).first;
-                    }
-                    const size_t tok_len = it->second.size() / static_cast<size_t>(widest);
-                    row.append(it->second.data(), tok_len * static_cast<size_t>(region_sizes[k]));
-                }
-                if (!row.empty()) row.pop_back();
-                row.push_back('\n');
-                f_cnvs.write(row.data(), static_cast<std::streamsize>(row.size()));
-            }
-            f_cnvs.flush();
-            }
+            // Utils::regions_to_bins_cnvs (Utils.cpp:165-188) + the writer of infer_trees.cpp:321-331: cells x bins as text,
+            // formatted and written in blocks of rows on the worker pool (cnv_writer.hpp).  Timing runs skip it: 4 GB per
+            // chain at configs[4].
+            if (!a.flag("no_cnv_file", false))
+                write_bins_cnvs("./" + pf + "_inferred_cnvs.csv", cn.data(), M, n_regions, region_sizes,
+                                [](int n, const std::function<void(int)>& fn) { parallel_chains(n, [&fn](int i) { fn(i); }); });
             if (P.verbosity > 1) {
                 int32_t nn = 0;
                 abi_check(scicone_t_n_nodes(inf->chain, &nn));
