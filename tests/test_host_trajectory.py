@@ -178,3 +178,21 @@ def test_chain_ownership_protocol_on_cpu(tmp_path, schedule, world, threads):
         assert np.array_equal(got["acceptance_ratio"], single["acc"]), c
         assert np.max(np.abs(got["markov_chain"] - single["chain"]) / np.maximum(1.0, np.abs(single["chain"]))) <= 1e-9
         assert open(os.path.join(str(tmp_path), f"own{owner}_c{c}_tree_inferred.txt")).read().split("\n")[7:] == single["tree"].split("\n")[7:]
+
+
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+@pytest.mark.parametrize("seed", list(range(9000, 9012)))
+def test_random_configurations_on_cpu(tmp_path, seed):
+    """A slice of scripts/trajectory_sweep.py: random scoring mode, tree size, nu, move weights, tempering, limits, cluster
+    sizes and shapes; the native host must reproduce the unmodified reference run for run."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("trajectory_sweep", os.path.join(root, "scripts", "trajectory_sweep.py"))
+    sweep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sweep)
+    D, r, w, flags = sweep.draw_case(seed)
+    a = run_inference(REF, str(tmp_path), "ref", D, r, flags, w=w)
+    b = run_inference(NATIVE, str(tmp_path), "new", D, r, flags, w=w, env=CPU_ENV)
+    compare_runs(a, b)
