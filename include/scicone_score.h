@@ -34,6 +34,7 @@ extern "C" {
 #endif
 
 #define SCICONE_ABI_VERSION 1
+#define SCICONE_MAX_SHARDED_BATCH 128 /* proposals per launch on a cell-sharded dataset (slots of the gather buffer) */
 
 enum {
     SCICONE_OK = 0,

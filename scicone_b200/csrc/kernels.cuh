@@ -143,7 +143,7 @@ struct alignas(16) DevHeader {
     unsigned long long xchg_seq;            // number of this launch on its lane
     int xchg_world, xchg_slot, xchg_stride, xchg_pad;  // stride = chunk sums per rank and value (max_chunks_rank)
 };
-constexpr int kXchgSlots = 128;  // proposals per launch of a cell-sharded dataset
+constexpr int kXchgSlots = 128;  // proposals per launch of a cell-sharded dataset (SCICONE_MAX_SHARDED_BATCH in the header)
 
 struct alignas(16) DevBuild {
     double* dst;

@@ -409,6 +409,7 @@ struct scicone_dataset {
     }
 };
 
+static_assert(kXchgSlots == SCICONE_MAX_SHARDED_BATCH, "header and kernels disagree");
 constexpr size_t kStashRefill = 32, kStashMax = 160;
 constexpr int kDefaultOcc = 7;
 

@@ -746,6 +746,9 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
     int G = n_groups > 0 ? n_groups : (B >= 8 ? 2 : 1);
     if (G > B) G = B;
     if (G > 4) G = 4;  // the library keeps at most 8 launches in flight
+    if (world > 1 && (B + G - 1) / G > SCICONE_MAX_SHARDED_BATCH)
+        throw std::runtime_error("static schedule: more than " + std::to_string(SCICONE_MAX_SHARDED_BATCH) +
+                                 " chains per group on a cell-sharded dataset - use the dynamic schedule or fewer chains per process");
     parallel_chains(B, [&](int b) {
         chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
         if (mailbox == nullptr || b % world == rank) chains[b]->open_traces(n_iters);  // a follower writes no traces
@@ -1065,7 +1068,13 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
                 } else {
                     const bool nothing_coming = n_host == 0 && flights.empty();
                     if (!ready.empty() && flights.size() < 2 && (static_cast<int>(ready.size()) >= min_batch || nothing_coming || (n_host == 0 && flights.size() < 2)))
+                    {
                         take.swap(ready);
+                        if (world > 1 && take.size() > SCICONE_MAX_SHARDED_BATCH) {  // the rest waits for the next launch
+                            ready.assign(take.begin() + SCICONE_MAX_SHARDED_BATCH, take.end());
+                            take.resize(SCICONE_MAX_SHARDED_BATCH);
+                        }
+                    }
                 }
             }
             if (all_done) break;
