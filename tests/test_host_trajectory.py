@@ -196,3 +196,34 @@ def test_random_configurations_on_cpu(tmp_path, seed):
     a = run_inference(REF, str(tmp_path), "ref", D, r, flags, w=w)
     b = run_inference(NATIVE, str(tmp_path), "new", D, r, flags, w=w, env=CPU_ENV)
     compare_runs(a, b)
+
+
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+def test_cli_errors_match_the_reference(tmp_path):
+    """Same messages as the reference's CLI for missing arguments (infer_trees.cpp:157-176) and for a region-size vector of
+    the wrong length (Tree.h:170-171); the reference aborts on the uncaught exception, the native host exits with 1."""
+    import subprocess
+
+    rng = np.random.default_rng(0)
+    np.savetxt(str(tmp_path / "d.csv"), rng.poisson(50, size=(30, 6)).astype(float), delimiter=",", fmt="%.0f")
+    np.savetxt(str(tmp_path / "r.txt"), rng.integers(3, 9, size=6), fmt="%d")
+    np.savetxt(str(tmp_path / "r5.txt"), rng.integers(3, 9, size=5), fmt="%d")
+    env = dict(os.environ, **CPU_ENV)
+    cases = {
+        "the D matrix file is not provided.": ["--region_sizes_file=r.txt", "--n_cells=30", "--n_regions=6"],
+        "the number of regions is not provided.": ["--d_matrix_file=d.csv", "--region_sizes_file=r.txt", "--n_cells=30"],
+        "the number of cells is not provided.": ["--d_matrix_file=d.csv", "--region_sizes_file=r.txt", "--n_regions=6"],
+        "Size of the counts per cell needs to be equal to the number of regions!":
+            ["--d_matrix_file=d.csv", "--region_sizes_file=r5.txt", "--n_cells=30", "--n_regions=6", "--n_iters=10", "--verbosity=0"],
+    }
+    for message, args in cases.items():
+        ref = subprocess.run([REF] + args, cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+        new = subprocess.run([NATIVE] + args, cwd=str(tmp_path), capture_output=True, text=True, timeout=120, env=env)
+        assert ref.returncode != 0 and new.returncode == 1, (message, ref.returncode, new.returncode)
+        assert message in ref.stdout + ref.stderr, message
+        assert message in new.stdout + new.stderr, message
+    # files that do not exist: the reference dies on an assertion, the native host says which file
+    new = subprocess.run([NATIVE, "--d_matrix_file=nope.csv", "--region_sizes_file=r.txt", "--n_cells=30", "--n_regions=6", "--n_iters=10"],
+                         cwd=str(tmp_path), capture_output=True, text=True, timeout=120, env=env)
+    assert new.returncode == 1 and "cannot open nope.csv" in new.stderr
