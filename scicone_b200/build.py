@@ -55,9 +55,12 @@ def build_host(force=False):
     lib = os.path.join(LIB_DIR, "libscicone_host.so")
     if force or _newer(exe, srcs):
         subprocess.check_call(common + ["-Wl,-rpath,$ORIGIN/../lib", "-o", exe])
+    score = os.path.join(bin_dir, "score")  # the reference's `score` executable (score_tree.cpp), same source file
+    if force or _newer(score, srcs):
+        subprocess.check_call(common + ["-DSCICONE_SCORE_MAIN", "-Wl,-rpath,$ORIGIN/../lib", "-o", score])
     if force or _newer(lib, srcs):
         subprocess.check_call(common + ["-DSCICONE_HOST_NO_MAIN", "-fPIC", "-shared", "-Wl,-rpath,$ORIGIN", "-o", lib])
-    return [exe, lib]
+    return [exe, score, lib]
 
 
 def build_all(force=False, verbose=False):

@@ -404,6 +404,94 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
     }
 }
 
+// The reference's second executable, `score` (scicone/src/score_tree.cpp:31-125): load a tree file, set nu, one full pass
+// (compute_t_table, score_tree.cpp:114) and the root scores (compute_t_od_scores, :115), print the rescored tree.  Same
+// flags, defaults (cf = 1, lambda_r = 2, lambda_c = 1, c_penalise = 1, sum scoring) and output; plus --device.
+extern "C" int scicone_score_main(int argc, char** argv) {
+    try {
+        Args a = parse(argc, argv);
+        Params P;
+        P.print_precision = static_cast<int>(a.integer("print_precision", 15));
+        P.lambda_s = 0.5;
+        P.lambda_r = 2.0;
+        P.lambda_c = 1.0;
+        P.cf = a.num("cf", 1.0);
+        P.c_penalise = 1.0;
+        P.copy_number_limit = 5;
+        P.is_overdispersed = static_cast<unsigned>(a.integer("is_overdispersed", 1));
+        P.eta = 1e-4;
+        P.verbosity = 0;
+        P.postfix = a.str("postfix");
+        const int n_cells = static_cast<int>(a.integer("n_cells", 0));
+        int n_regions = static_cast<int>(a.integer("n_regions", 0));
+        const int ploidy = static_cast<int>(a.integer("ploidy", 2));
+        const double nu = a.num("nu", 1.0);
+        if (n_cells <= 0 || n_regions <= 0) throw std::runtime_error("--n_cells and --n_regions are needed");
+        std::cout << "Reading the input matrix..." << std::endl;
+        std::vector<double> D(static_cast<size_t>(n_cells) * n_regions, 0.0);
+        read_counts(D, n_cells, n_regions, a.str("d_matrix_file"));
+        std::cout << "Reading the region_sizes file..." << std::endl;
+        std::vector<int> region_sizes;
+        read_vector(region_sizes, a.str("region_sizes_file"));
+        if (static_cast<int>(region_sizes.size()) != n_regions)
+            throw std::logic_error("Size of the counts per cell needs to be equal to the number of regions!");  // Tree.h:170-171
+        std::vector<int> cluster_sizes;
+        if (a.has("cluster_sizes_file")) {
+            std::cout << "Reading the cluster_sizes file..." << std::endl;
+            read_vector(cluster_sizes, a.str("cluster_sizes_file"));
+        } else {
+            if (n_cells < 20)
+                std::cout << "Warning: there are only " << n_cells
+                          << " observations. If these are clusters, the cluster_sizes_file parameter should be specified for accurate tree scoring.";
+            cluster_sizes.assign(n_cells, 1);
+        }
+        if (static_cast<int>(cluster_sizes.size()) != n_cells) throw std::runtime_error("the cluster sizes file does not have n_cells lines");
+        std::vector<int> neutral;
+        if (a.has("region_neutral_states_file")) {
+            std::cout << "Reading the region_neutral_states file..." << std::endl;
+            read_vector(neutral, a.str("region_neutral_states_file"));
+        } else {
+            std::cout << "Assuming root to have copy number state " << ploidy << " in all regions" << std::endl;
+            neutral.assign(n_regions, ploidy);
+        }
+        std::vector<int32_t> r32(region_sizes.begin(), region_sizes.end()), n32(neutral.begin(), neutral.end()), w32(cluster_sizes.begin(), cluster_sizes.end());
+        scicone_dataset_desc desc;
+        desc.n_cells = n_cells;
+        desc.n_regions = n_regions;
+        desc.D = D.data();
+        desc.region_sizes = r32.data();
+        desc.neutral_states = n32.data();
+        desc.cluster_sizes = w32.data();
+        desc.eta = P.eta;
+        desc.is_overdispersed = static_cast<int32_t>(P.is_overdispersed);
+        desc.max_scoring = 0;  // Inference's default (Inference.h:51)
+        desc.device = static_cast<int32_t>(a.integer("device", 0));
+        desc.cell_offset = 0;
+        desc.n_cells_global = n_cells;
+        scicone_dataset* ds = nullptr;
+        abi_check(scicone_dataset_create(&ds, &desc));
+        {
+            Inference inf(P, 0, static_cast<unsigned>(n_regions), n_cells, neutral, ploidy, false);
+            inf.attach_chain(ds);
+            inf.initialize_from_file(a.str("tree_file"));
+            inf.t.nu = nu;
+            inf.compute_t_table();
+            inf.compute_t_od_scores();
+            inf.update_t_prime();
+            inf.t.write(std::cout);
+        }
+        scicone_dataset_destroy(ds);
+        return EXIT_SUCCESS;
+    } catch (const std::exception& e) {
+        std::cerr << "score: " << e.what() << std::endl;
+        return EXIT_FAILURE;
+    }
+}
+
 #ifndef SCICONE_HOST_NO_MAIN
+#ifdef SCICONE_SCORE_MAIN
+int main(int argc, char** argv) { return scicone_score_main(argc, argv); }
+#else
 int main(int argc, char** argv) { return scicone_inference_main(argc, argv); }
+#endif
 #endif

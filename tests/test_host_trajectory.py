@@ -227,3 +227,48 @@ def test_cli_errors_match_the_reference(tmp_path):
     new = subprocess.run([NATIVE, "--d_matrix_file=nope.csv", "--region_sizes_file=r.txt", "--n_cells=30", "--n_regions=6", "--n_iters=10"],
                          cwd=str(tmp_path), capture_output=True, text=True, timeout=120, env=env)
     assert new.returncode == 1 and "cannot open nope.csv" in new.stderr
+
+
+def _score_tool(tmp_path, env, exact):
+    """The reference's `score` executable (score_tree.cpp) and scicone_b200/bin/score on a tree inferred from the tutorial
+    matrix: same printed tree; the seven score lines identical (CPU, oracle-backed ABI) or within 1e-9 relative (GPU)."""
+    import subprocess
+
+    D, r = _tutorial()
+    first = run_inference(REF, str(tmp_path), "seed", D, r, ["--n_iters=600", "--n_nodes=5", "--seed=3", "--nu=1.5", "--max_scoring=false"])
+    assert first["tree"]
+    tree_file = os.path.join(str(tmp_path), "seed_tree_inferred.txt")
+    ref_score = os.path.join(os.path.dirname(REF), "score")
+    native_score = os.path.join(os.path.dirname(NATIVE), "score")
+    common = [f"--d_matrix_file={os.path.join(str(tmp_path), 'seed_d.csv')}", f"--region_sizes_file={os.path.join(str(tmp_path), 'seed_r.txt')}",
+              f"--n_cells={D.shape[0]}", f"--n_regions={D.shape[1]}", f"--tree_file={tree_file}"]
+    np.savetxt(os.path.join(str(tmp_path), "seed_d.csv"), D, delimiter=",", fmt="%.0f")
+    np.savetxt(os.path.join(str(tmp_path), "seed_r.txt"), r, fmt="%d")
+    for extra in (["--nu=1.5"], ["--nu=0.4", "--cf=0.5"], ["--is_overdispersed=0"]):
+        a = subprocess.run([ref_score] + common + extra, capture_output=True, text=True, timeout=300)
+        b = subprocess.run([native_score] + common + extra, capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, **env) if env else None)
+        assert a.returncode == 0 and b.returncode == 0, b.stderr[-1000:]
+        if exact:
+            assert a.stdout == b.stdout, extra
+            continue
+        la, lb = a.stdout.strip().split("\n"), b.stdout.strip().split("\n")
+        assert len(la) == len(lb)
+        for x, y in zip(la, lb):
+            if ": " in x and x.split(": ")[0] in ("Tree posterior", "Tree prior", "Event prior", "Log likelihood", "Root score", "Tree score", "Nu"):
+                vx, vy = float(x.split(": ")[1]), float(y.split(": ")[1])
+                assert x.split(": ")[0] == y.split(": ")[0] and abs(vx - vy) <= 1e-9 * max(1.0, abs(vx)), (x, y)
+            else:
+                assert x == y
+
+
+@needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+def test_score_tool_on_cpu(tmp_path):
+    _score_tool(tmp_path, CPU_ENV, exact=True)
+
+
+@needs_bins
+@pytest.mark.gpu
+def test_score_tool_on_gpu(tmp_path):
+    _score_tool(tmp_path, None, exact=False)
