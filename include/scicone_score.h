@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SCICONE_ABI_VERSION 1
+#define SCICONE_ABI_VERSION 2
 #define SCICONE_MAX_SHARDED_BATCH 128 /* proposals per launch on a cell-sharded dataset (slots of the gather buffer) */
 
 enum {
@@ -96,8 +96,24 @@ const char* scicone_last_error(void);
 int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* desc);
 void scicone_dataset_destroy(scicone_dataset* ds);
 
+/*
+ * Optional, before the first launch: set up the reduction scratch for launches of up to max_batch proposals and back
+ * the first `rows` rows of (every rank's partition of) the row pool with memory, so that neither grows inside a timed
+ * loop.  A chain holds one row of n_cells doubles per tree node plus one per node of a queued proposal, four rows of
+ * per-cell aggregates and up to ~35 temporary rows.  No reference counterpart (the reference's tables are std::maps on
+ * the heap).  scicone_max_batch returns the current capacity; the batch size cannot grow while launches are outstanding.
+ */
+int scicone_dataset_reserve(scicone_dataset* ds, int32_t max_batch, int64_t rows);
+int scicone_max_batch(scicone_dataset* ds, int32_t* n);
+
 /* One chain == the score tables of one reference `Inference` object (Inference.h:183-198). */
 int scicone_chain_create(scicone_chain** out, scicone_dataset* ds);
+/*
+ * Cell-sharded runs with one owner rank per chain: the handle the OTHER ranks hold for that chain.  It owns no tables;
+ * it only stages the proposals the owner compiled (scicone_import_t_prime -> scicone_batch_submit -> scicone_accept /
+ * scicone_reject, which merely clear it).
+ */
+int scicone_chain_create_follower(scicone_chain** out, scicone_dataset* ds);
 void scicone_chain_destroy(scicone_chain* ch);
 
 /*
@@ -108,6 +124,13 @@ void scicone_chain_destroy(scicone_chain* ch);
  * (as assign_cells_to_nodes does at Inference.h:1320-1323).
  */
 int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* t_sum);
+/*
+ * The same full pass as a queued proposal: compiled now, launched by scicone_batch_submit (alone or together with other
+ * chains), committed by scicone_accept.  with_od != 0 also evaluates the root score of compute_t_od_scores in that
+ * launch (returned in od_scores[i] by scicone_batch_wait).  This is the form a cell-sharded run uses: the owner of the
+ * chain compiles, every rank launches.
+ */
+int scicone_prepare_t_table(scicone_chain* ch, const scicone_tree* t, int32_t with_od);
 
 /*
  * Inference::compute_t_od_scores (Inference.h:1406-1419) for the committed tree and
@@ -143,6 +166,17 @@ int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t_prime,
  * to the (serial) batch call.  No reference counterpart.
  */
 int scicone_prepare_t_prime(scicone_chain* ch);
+
+/*
+ * Cell-sharded runs: a compiled proposal names every device row by its index in the row pool and nothing by address,
+ * and the rows of a chain come from its owner rank's partition of the pool, so the compiled bytes are valid on every
+ * rank.  The owner exports them after scicone_prepare_t_prime / scicone_prepare_t_table (*bytes receives the size; the
+ * call fails with SCICONE_ERR_ARG if the buffer is smaller), ships them by its own means (the native host uses a
+ * shared-memory mailbox), and the other ranks import them into their follower handle of the chain.  All ranks then
+ * submit the same launches in the same order.  No reference counterpart (the reference is one process).
+ */
+int scicone_export_t_prime(scicone_chain* ch, void* buf, uint64_t capacity, uint64_t* bytes);
+int scicone_import_t_prime(scicone_chain* ch, const void* buf, uint64_t bytes);
 
 /*
  * The same two steps for `n` chains in ONE kernel launch (independent restarts or

@@ -6,6 +6,7 @@
 // with the unmodified reference `inference`.  Nothing in the product loads this library; scoring numbers produced
 // through it are the oracle's, not the engine's, and are never reported as results.
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <string>
@@ -28,6 +29,9 @@ struct scicone_chain {
     scicone_dataset* ds;
     orc_ctx* ctx;
     bool pending = false;
+    bool full_pending = false;  // scicone_prepare_t_table: the queued "proposal" is a full pass
+    int full_with_od = 0;
+    std::vector<int32_t> roots;  // queued subtree roots (what an exported proposal carries)
     // copy of the queued tree
     std::vector<int32_t> id, parent, co, cr, cv, go, gr, gv;
     scicone_tree pod;
@@ -76,9 +80,59 @@ int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* s)
 int scicone_compute_t_od_scores(scicone_chain* ch, double nu, double* od) { return orc_compute_od_scores(ch->ctx, nu, od, nullptr); }
 int scicone_compute_t_prime_od_scores(scicone_chain* ch, double nu, double* od) { return orc_compute_od_scores(ch->ctx, nu, od, nullptr); }
 int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t, int32_t idx) {
-    if (!ch->pending) { ch->keep(t); ch->pending = true; }
+    if (!ch->pending) { ch->keep(t); ch->pending = true; ch->full_pending = false; ch->roots.clear(); }
+    ch->roots.push_back(idx);
     return orc_compute_t_prime_scores(ch->ctx, &ch->pod, idx) ? fail(-3, "oracle: compute_t_prime_scores failed") : 0;
 }
+int scicone_chain_create_follower(scicone_chain** out, scicone_dataset* ds) { return scicone_chain_create(out, ds); }
+int scicone_prepare_t_table(scicone_chain* ch, const scicone_tree* t, int32_t with_od) {
+    ch->keep(t);
+    ch->pending = true;
+    ch->full_pending = true;
+    ch->full_with_od = with_od;
+    ch->roots.clear();
+    return 0;
+}
+// "compiled proposal" of this backend: the queued tree and what to do with it (each process evaluates it on its own copy)
+int scicone_export_t_prime(scicone_chain* ch, void* buf, uint64_t cap, uint64_t* bytes) {
+    if (!ch->pending) return fail(-3, "export without a queued proposal");
+    std::vector<int32_t> m;
+    const int n = ch->pod.n_nodes;
+    m.push_back(ch->full_pending); m.push_back(ch->full_with_od); m.push_back(n); m.push_back((int32_t)ch->roots.size());
+    int64_t nu_bits; std::memcpy(&nu_bits, &ch->pod.nu, 8);
+    m.push_back((int32_t)(nu_bits & 0xffffffff)); m.push_back((int32_t)(nu_bits >> 32));
+    auto put = [&](const std::vector<int32_t>& v, size_t cnt) { m.insert(m.end(), v.begin(), v.begin() + cnt); };
+    put(ch->id, n); put(ch->parent, n); put(ch->co, n + 1); put(ch->go, n + 1);
+    put(ch->cr, ch->co[n]); put(ch->cv, ch->co[n]); put(ch->gr, ch->go[n]); put(ch->gv, ch->go[n]);
+    put(ch->roots, ch->roots.size());
+    *bytes = 4 * m.size();
+    if (!buf || cap < *bytes) return fail(-1, "export: buffer too small");
+    std::memcpy(buf, m.data(), *bytes);
+    return 0;
+}
+int scicone_import_t_prime(scicone_chain* ch, const void* buf, uint64_t bytes) {
+    const int32_t* m = static_cast<const int32_t*>(buf);
+    if (bytes < 24) return fail(-1, "import: short message");
+    std::vector<int32_t> v(m, m + bytes / 4);
+    const int full = v[0], with_od = v[1], n = v[2], n_roots = v[3];
+    int64_t nu_bits = (int64_t)(uint32_t)v[4] | ((int64_t)v[5] << 32);
+    double nu; std::memcpy(&nu, &nu_bits, 8);
+    size_t at = 6;
+    auto take = [&](std::vector<int32_t>& dst, size_t cnt) { dst.assign(v.begin() + at, v.begin() + at + cnt); dst.push_back(0); at += cnt; };
+    std::vector<int32_t> id, parent, co, go, cr, cv, gr, gv, roots;
+    take(id, n); take(parent, n); take(co, n + 1); take(go, n + 1);
+    take(cr, co[n]); take(cv, co[n]); take(gr, go[n]); take(gv, go[n]); take(roots, n_roots);
+    scicone_tree t;
+    t.n_nodes = n; t.node_id = id.data(); t.parent = parent.data(); t.chg_off = co.data(); t.chg_region = cr.data(); t.chg_value = cv.data();
+    t.gen_off = go.data(); t.gen_region = gr.data(); t.gen_value = gv.data(); t.nu = nu;
+    ch->pending = false;
+    if (full) return scicone_prepare_t_table(ch, &t, with_od);
+    for (int i = 0; i < n_roots; ++i)
+        if (int rc = scicone_compute_t_prime_scores(ch, &t, roots[i])) return rc;
+    return 0;
+}
+int scicone_dataset_reserve(scicone_dataset*, int32_t, int64_t) { return 0; }
+int scicone_max_batch(scicone_dataset*, int32_t* n) { *n = 1 << 20; return 0; }
 int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scicone_tree* const*, int32_t n, double* sums, double* ods) {
     for (int i = 0; i < n; ++i)
         if (!chains[i]->pending) return fail(-3, "compute_t_prime_sums without compute_t_prime_scores");
@@ -86,6 +140,14 @@ int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scico
     scicone::ForkJoinPool::instance().run(n, [](int i, void* p) {
         Job& j = *static_cast<Job*>(p);
         scicone_chain* ch = j.chains[i];
+        if (ch->full_pending) {  // full pass queued by scicone_prepare_t_table (commits inside the oracle)
+            if (orc_compute_t_table(ch->ctx, &ch->pod, &j.sums[i])) j.rc[i] = -4;
+            if (j.ods) {
+                j.ods[i] = NAN;
+                if (ch->full_with_od) orc_compute_od_scores(ch->ctx, ch->pod.nu, &j.ods[i], nullptr);
+            }
+            return;
+        }
         if (orc_compute_t_prime_sums(ch->ctx, &ch->pod, &j.sums[i])) j.rc[i] = -4;
         if (j.ods) {
             j.ods[i] = NAN;
@@ -97,8 +159,13 @@ int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scico
     return rc ? fail(rc, "NaN aggregate") : 0;
 }
 int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t, double* s) { return scicone_batch_compute_t_prime_sums(&ch, &t, 1, s, nullptr); }
-int scicone_accept(scicone_chain* ch) { ch->pending = false; ch->t_nu = ch->pod.nu; return orc_accept(ch->ctx, &ch->pod); }
-int scicone_reject(scicone_chain* ch) { ch->pending = false; return orc_reject(ch->ctx); }
+int scicone_accept(scicone_chain* ch) {
+    ch->pending = false;
+    ch->t_nu = ch->pod.nu;
+    if (ch->full_pending) { ch->full_pending = false; return 0; }
+    return orc_accept(ch->ctx, &ch->pod);
+}
+int scicone_reject(scicone_chain* ch) { ch->pending = false; ch->full_pending = false; return orc_reject(ch->ctx); }
 int scicone_t_n_nodes(scicone_chain* ch, int32_t* n) { *n = orc_t_n_nodes(ch->ctx); return 0; }
 int scicone_t_node_ids(scicone_chain* ch, int32_t* ids) { orc_t_node_ids(ch->ctx, ids); return 0; }
 int scicone_read_t_scores(scicone_chain* ch, double* out) { orc_read_t_scores(ch->ctx, out); return 0; }

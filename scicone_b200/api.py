@@ -35,6 +35,8 @@ ABI_SYMBOLS = [
     "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
     "scicone_parallel_for", "scicone_host_threads", "scicone_test_lgamma", "scicone_prepare_t_prime",
     "scicone_batch_compute_t_prime_scores", "scicone_batch_settle", "scicone_condense_matrix", "scicone_batch_poll", "scicone_set_streams", "scicone_condense_clusters",
+    "scicone_dataset_reserve", "scicone_max_batch", "scicone_chain_create_follower", "scicone_prepare_t_table", "scicone_export_t_prime",
+    "scicone_import_t_prime",
 ]
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_STATE", -4: "ERR_NAN", -5: "ERR_COMM"}
@@ -130,6 +132,13 @@ def lib():
         L.scicone_set_profiling.argtypes = [vp, C.c_int32]
         L.scicone_last_kernel_time_us.argtypes = [vp, dp]
         L.scicone_kernel_launches.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.scicone_dataset_reserve.argtypes = [vp, C.c_int32, C.c_int64]
+        L.scicone_max_batch.argtypes = [vp, ip]
+        L.scicone_chain_create_follower.argtypes = [C.POINTER(vp), vp]
+        L.scicone_prepare_t_table.argtypes = [vp, tp, C.c_int32]
+        L.scicone_prepare_t_prime.argtypes = [vp]
+        L.scicone_export_t_prime.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.scicone_import_t_prime.argtypes = [vp, vp, C.c_uint64]
         _lib = L
     return _lib
 
@@ -199,6 +208,15 @@ class Dataset:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _check(lib().scicone_dataset_attach_comm(self._h, buf, rank, world_size))
 
+    def reserve(self, max_batch=0, rows=0):
+        """scicone_dataset_reserve: size the reduction scratch and back the row pool with memory before the first launch."""
+        _check(lib().scicone_dataset_reserve(self._h, int(max_batch), int(rows)))
+
+    def max_batch(self):
+        out = C.c_int32()
+        _check(lib().scicone_max_batch(self._h, C.byref(out)))
+        return out.value
+
     def set_profiling(self, on=True):
         _check(lib().scicone_set_profiling(self._h, int(on)))
 
@@ -250,14 +268,34 @@ class Dataset:
 class Chain:
     """Score tables of one MCMC chain == one reference ``Inference`` object (Inference.h:39-44)."""
 
-    def __init__(self, D=None, region_sizes=None, dataset=None, **kw):
+    def __init__(self, D=None, region_sizes=None, dataset=None, follower=False, **kw):
         self._own = dataset is None
         self.ds = dataset if dataset is not None else Dataset(D, region_sizes, **kw)
         self.M, self.K = self.ds.M, self.ds.K
         self.max_scoring = self.ds.max_scoring
         self._h = C.c_void_p()
-        _check(lib().scicone_chain_create(C.byref(self._h), self.ds._h))
+        # follower: the handle another rank of a cell-sharded run holds for a chain it does not own (import + submit only)
+        _check((lib().scicone_chain_create_follower if follower else lib().scicone_chain_create)(C.byref(self._h), self.ds._h))
         self.ds._chains.add(self)
+
+    def prepare_t_table(self, tree, with_od=False):
+        """Full pass as a queued proposal (scicone_prepare_t_table): launched by a batch submit, committed by accept()."""
+        _check(lib().scicone_prepare_t_table(self._h, tree.byref(), int(with_od)))
+
+    def prepare_t_prime(self):
+        _check(lib().scicone_prepare_t_prime(self._h))
+
+    def export_t_prime(self):
+        """The compiled proposal as bytes (valid on every rank of a cell-sharded run)."""
+        need = C.c_uint64()
+        lib().scicone_export_t_prime(self._h, None, 0, C.byref(need))
+        buf = (C.c_uint8 * need.value)()
+        _check(lib().scicone_export_t_prime(self._h, buf, need.value, C.byref(need)))
+        return bytes(buf)
+
+    def import_t_prime(self, data):
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        _check(lib().scicone_import_t_prime(self._h, buf, len(data)))
 
     def close(self):
         if getattr(self, "_h", None):

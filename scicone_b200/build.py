@@ -2,6 +2,7 @@
 
   scicone_b200/lib/libscicone_score.so   CUDA kernels + C ABI (include/scicone_score.h), sm_100a only
 """
+import glob
 import os
 import shutil
 import subprocess
@@ -33,9 +34,10 @@ def nvcc():
 def build_score_lib(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     out = os.path.join(LIB_DIR, "libscicone_score.so")
-    srcs = [os.path.join(CSRC, "scicone_score.cu"), os.path.join(CSRC, "kernels.cuh"),
-            os.path.join(ROOT, "include", "scicone_score.h")]
-    if force or _newer(out, srcs):
+    srcs = [os.path.join(CSRC, "scicone_score.cu")]
+    deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.hpp")))
+    deps.append(os.path.join(ROOT, "include", "scicone_score.h"))
+    if force or _newer(out, deps):
         cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", out, srcs[0], "-ldl"]
         subprocess.check_call(cmd)
     return out
@@ -46,8 +48,9 @@ def build_host(force=False):
     host = os.path.join(HERE, "host")
     bin_dir = os.path.join(HERE, "bin")
     os.makedirs(bin_dir, exist_ok=True)
-    srcs = [os.path.join(host, f) for f in ("inference_main.cpp", "mcmc.hpp", "tree.hpp", "rng_dist.hpp", "csv_reader.hpp", "cnv_writer.hpp")]
+    srcs = [os.path.join(host, "inference_main.cpp")] + sorted(glob.glob(os.path.join(host, "*.hpp")))
     srcs.append(os.path.join(ROOT, "include", "scicone_score.h"))
+    srcs.append(os.path.join(LIB_DIR, "libscicone_score.so"))
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     common = [cxx, "-std=c++17", "-O2", "-fno-fast-math", "-ffp-contract=off", "-Wall", "-Wno-sign-compare", srcs[0],
               "-L" + LIB_DIR, "-lscicone_score"]

@@ -1,17 +1,21 @@
 // libscicone_score.so - host side of the B200 tree-scoring engine behind include/scicone_score.h.
 //
 // What lives where
-//   dataset  device copy of the count matrix (region-major Dt[K][Mp]), read totals S, cluster sizes w,
-//            the row pool (every device vector of Mp doubles comes from it), one CUDA stream, the pinned
-//            staging arena through which proposals travel, the reduction scratch, the NCCL communicator.
-//   chain    what one reference `Inference` object owns for scoring (scicone/src/Inference.h:39-44):
-//            the committed table t_scores as {node id -> score row, Node::z}, t_sums / t_maxs, the primed
-//            rows of the queued proposal, and the lgamma rows L(k, cn) of the chain's current nu.
+//   dataset  device copy of the count matrix (region-major Dt[K][Mp], 16-bit index matrix It, count-range table), read
+//            totals S, cluster sizes w, the ROW POOL - one contiguous virtual address range per rank whose rows are
+//            addressed by 32-bit indices (physical memory is mapped in as the pool grows, so the base never moves) -
+//            the launch streams, the pinned staging arena through which proposals travel, the reduction scratch, the
+//            NCCL communicator and the peer-mapped gather buffers of a cell-sharded run.
+//   chain    what one reference `Inference` object owns for scoring (scicone/src/Inference.h:39-44): the committed
+//            table t_scores as {node id -> score row, Node::z}, t_sums / t_maxs, the primed rows of the queued proposal.
 //
-// A proposal is compiled on the host into a small "blob" (header, one task per rescored node in
-// parent-before-child order, one event per touched region, aggregate bookkeeping) and evaluated by ONE
-// launch of score_proposals_kernel (kernels.cuh) - for any number of chains at once (grid.y).
-// Accept / reject are pointer swaps; no score is ever copied.
+// A proposal is compiled on the host into a small position-independent "blob" (header, one task per rescored node in
+// parent-before-child order, aggregate bookkeeping - all rows by index) plus the K1 work it needs (one item per rescored
+// node with its events, the slices of a root score) and evaluated by ONE launch of build_increments_kernel +
+// score_proposals_kernel (kernels.cuh) - for any number of chains at once (grid.y).  Because nothing in a compiled
+// proposal is an address, the owner of a chain in a cell-sharded run compiles it ONCE and ships the bytes
+// (scicone_export_t_prime / scicone_import_t_prime); the other ranks only stage them.  Accept / reject are index swaps;
+// no score is ever copied.
 //
 // There is no CPU implementation of any scoring step in this file: without a CUDA device every
 // compute entry point fails with SCICONE_ERR_CUDA.
@@ -20,6 +24,7 @@
 #include "condense.cuh"
 #include "parallel_for.hpp"
 
+#include <cuda.h>  // types of the virtual-memory-management API only: the entry points are resolved at run time
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -31,7 +36,6 @@
 #include <mutex>
 #include <numeric>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 using namespace scicone;
@@ -89,54 +93,180 @@ NcclApi g_nccl;
 constexpr int kNcclDouble = 8;  // ncclFloat64
 
 // ------------------------------------------------------------------------------------------------
-// Pool of device rows (Mp doubles each).  Slabs are only released with the dataset.
+// CUDA virtual memory management (driver API), resolved through the runtime so that the library links against
+// nothing but libcudart and still loads on a machine without a driver (tests/test_abi_cpu.py).
+// ------------------------------------------------------------------------------------------------
+struct DriverApi {
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*Granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    bool loaded = false;
+    bool load() {
+        if (loaded) return true;
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult st;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess && *fn;
+        };
+        loaded = get("cuMemAddressReserve", (void**)&AddressReserve) && get("cuMemAddressFree", (void**)&AddressFree) &&
+                 get("cuMemCreate", (void**)&Create) && get("cuMemRelease", (void**)&Release) && get("cuMemMap", (void**)&Map) &&
+                 get("cuMemUnmap", (void**)&Unmap) && get("cuMemSetAccess", (void**)&SetAccess) &&
+                 get("cuMemGetAllocationGranularity", (void**)&Granularity);
+        return loaded;
+    }
+};
+DriverApi g_drv;
+std::mutex g_drv_mu;
+
+// ------------------------------------------------------------------------------------------------
+// Pool of device rows (Mp doubles each), addressed by index: row r lives at base + r * Mp.  The index space is cut into
+// one partition per rank of a cell-sharded run; a rank hands out rows of its own partition only, so the rows of a chain
+// (allocated by the chain's owner rank) never collide with those of a chain another rank owns, and a compiled proposal
+// names the same rows on every rank.  Physical memory is mapped chunk by chunk into the reserved range as a partition
+// grows - on the owner when it allocates, on the other ranks when a proposal that uses the rows arrives.
 // ------------------------------------------------------------------------------------------------
 struct RowPool {
-    size_t Mp = 0;
-    size_t rows_per_slab = 0;
-    std::vector<double*> free_rows;
-    std::vector<void*> slabs;
-    size_t n_rows = 0;
+    size_t Mp = 0, row_bytes = 0;
     int device = 0;
+    CUdeviceptr base = 0;
+    size_t va_bytes = 0;
+    size_t part_rows = 0, chunk_rows = 0;
+    int n_parts = 1, my_part = 0;
+    struct Part {
+        size_t mapped_rows = 0;
+        std::vector<CUmemGenericAllocationHandle> handles;
+    };
+    std::vector<Part> parts;
+    std::vector<unsigned> free_rows;
+    size_t next_row = 0;  // rows of this rank's partition that were ever handed out
+    size_t in_use = 0;
     std::mutex mu;  // chains of one dataset may be compiled / committed from several host threads
 
-    void init(size_t mp, int dev) {
+    double* base_ptr() const { return reinterpret_cast<double*>(base); }
+    size_t mapped_total() const {
+        size_t n = 0;
+        for (const Part& p : parts) n += p.mapped_rows;
+        return n;
+    }
+    void release_all() {
+        for (int p = 0; p < (int)parts.size(); ++p) {
+            Part& pt = parts[p];
+            if (pt.mapped_rows) g_drv.Unmap(base + (CUdeviceptr)((size_t)p * part_rows * row_bytes), pt.mapped_rows * row_bytes);
+            for (CUmemGenericAllocationHandle h : pt.handles) g_drv.Release(h);
+            pt.handles.clear();
+            pt.mapped_rows = 0;
+        }
+        if (base) g_drv.AddressFree(base, va_bytes);
+        base = 0;
+        va_bytes = 0;
+    }
+    int init(size_t mp, int dev, int parts_n, int mine) {
+        {
+            std::lock_guard<std::mutex> lk(g_drv_mu);
+            if (!g_drv.load()) return fail(SCICONE_ERR_CUDA, "the CUDA driver does not offer the virtual memory management API");
+        }
+        if (in_use) return fail(SCICONE_ERR_STATE, "the row pool cannot be re-partitioned while rows are in use (attach the communicator before creating chains)");
+        if (base) release_all();
         device = dev;
         Mp = mp;
-        const size_t row_bytes = Mp * sizeof(double);
-        rows_per_slab = std::max<size_t>(8, std::min<size_t>(512, (size_t(64) << 20) / row_bytes));
+        row_bytes = Mp * sizeof(double);
+        n_parts = parts_n;
+        my_part = mine;
+        free_rows.clear();
+        next_row = 0;
+        CUmemAllocationProp prop;
+        memset(&prop, 0, sizeof prop);
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = device;
+        size_t gran = 0;
+        if (g_drv.Granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
+            return fail(SCICONE_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+        // chunk = the smallest multiple of 64 rows whose byte size is a multiple of the granularity and at least 32 MB
+        chunk_rows = 64;
+        while ((chunk_rows * row_bytes) % gran != 0 || chunk_rows * row_bytes < (size_t(32) << 20)) chunk_rows += 64;
+        part_rows = std::max<size_t>(chunk_rows * 4, (size_t(1) << 16) / chunk_rows * chunk_rows);
+        for (;;) {
+            va_bytes = part_rows * row_bytes * n_parts;
+            if (g_drv.AddressReserve(&base, va_bytes, gran, 0, 0) == CUDA_SUCCESS) break;
+            base = 0;
+            if (part_rows <= chunk_rows * 4) return fail(SCICONE_ERR_CUDA, "cuMemAddressReserve of %zu bytes failed", va_bytes);
+            part_rows = std::max(chunk_rows * 4, part_rows / 2 / chunk_rows * chunk_rows);
+        }
+        parts.assign(n_parts, Part());
+        return SCICONE_OK;
+    }
+    // the first `rows` rows of partition `part` are backed by memory (callers hold `mu`)
+    int ensure_mapped_locked(int part, size_t rows) {
+        if (part < 0 || part >= n_parts) return fail(SCICONE_ERR_ARG, "row pool: partition %d out of range", part);
+        Part& pt = parts[part];
+        if (rows <= pt.mapped_rows) return SCICONE_OK;
+        if (rows > part_rows) return fail(SCICONE_ERR_CUDA, "row pool: partition of %zu rows exhausted", part_rows);
+        CUDA_TRY(cudaSetDevice(device));
+        CUmemAllocationProp prop;
+        memset(&prop, 0, sizeof prop);
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = device;
+        CUmemAccessDesc acc;
+        memset(&acc, 0, sizeof acc);
+        acc.location = prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        while (pt.mapped_rows < rows) {
+            const size_t bytes = chunk_rows * row_bytes;
+            const CUdeviceptr at = base + (CUdeviceptr)(((size_t)part * part_rows + pt.mapped_rows) * row_bytes);
+            CUmemGenericAllocationHandle h;
+            CUresult r = g_drv.Create(&h, bytes, &prop, 0);
+            if (r != CUDA_SUCCESS) return fail(SCICONE_ERR_CUDA, "row pool: cuMemCreate of %zu bytes failed (%d)", bytes, (int)r);
+            r = g_drv.Map(at, bytes, 0, h, 0);
+            if (r == CUDA_SUCCESS) r = g_drv.SetAccess(at, bytes, &acc, 1);
+            if (r != CUDA_SUCCESS) {
+                g_drv.Release(h);
+                return fail(SCICONE_ERR_CUDA, "row pool: mapping %zu bytes failed (%d)", bytes, (int)r);
+            }
+            pt.handles.push_back(h);
+            pt.mapped_rows += chunk_rows;
+        }
+        return SCICONE_OK;
+    }
+    int ensure_mapped(int part, size_t rows) {
+        std::lock_guard<std::mutex> lk(mu);
+        return ensure_mapped_locked(part, rows);
     }
     // rows move in batches, one lock per batch (the per-chain stashes use these)
-    cudaError_t get_many(size_t n, std::vector<double*>& out) {
+    int get_many(size_t n, std::vector<unsigned>& out) {
         std::lock_guard<std::mutex> lk(mu);
         while (free_rows.size() < n) {
-            void* p = nullptr;
-            cudaError_t e = cudaSetDevice(device);
-            if (e == cudaSuccess) e = cudaMalloc(&p, rows_per_slab * Mp * sizeof(double));
-            if (e != cudaSuccess) return e;
-            slabs.push_back(p);
-            for (size_t i = rows_per_slab; i-- > 0;) free_rows.push_back(static_cast<double*>(p) + i * Mp);
-            n_rows += rows_per_slab;
+            int rc = ensure_mapped_locked(my_part, next_row + chunk_rows);
+            if (rc) return rc;
+            const size_t upto = std::min(parts[my_part].mapped_rows, next_row + chunk_rows);
+            for (size_t r = upto; r-- > next_row;) free_rows.push_back((unsigned)((size_t)my_part * part_rows + r));
+            next_row = upto;
         }
         out.insert(out.end(), free_rows.end() - n, free_rows.end());
         free_rows.resize(free_rows.size() - n);
-        return cudaSuccess;
+        in_use += n;
+        return SCICONE_OK;
     }
-    void put_many(std::vector<double*>& rows, size_t keep) {
+    void put_many(std::vector<unsigned>& rows, size_t keep) {
         if (rows.size() <= keep) return;
         std::lock_guard<std::mutex> lk(mu);
+        in_use -= rows.size() - keep;
         free_rows.insert(free_rows.end(), rows.begin() + keep, rows.end());
         rows.resize(keep);
     }
     void destroy() {
-        for (void* p : slabs) cudaFree(p);
-        slabs.clear();
+        if (g_drv.loaded) release_all();
         free_rows.clear();
     }
 };
 
 struct NodeRow {
-    double* row;
+    unsigned row;
     int z;  // Node::z, an int in the reference (scicone/src/Node.h:25)
 };
 
@@ -221,10 +351,6 @@ private:
     std::vector<value_type> v_;
 };
 
-// (region, copy number) -> lgamma row L(k, cn) at one nu
-typedef FlatMap<uint64_t, double*> LCache;
-inline uint64_t lkey(int k, int cn) { return (uint64_t(uint32_t(k)) << 32) | uint64_t(uint32_t(cn)); }
-
 }  // namespace
 
 // ================================================================================================
@@ -242,15 +368,18 @@ struct scicone_dataset {
 
     double* dDt = nullptr;
     double* dS = nullptr;
-    // count-range table of K1 (kernels.cuh, build_rows_kernel): [K + 1 rows: regions, then S][blocks of kUnitCells cells]{min, range}
+    unsigned short* dIt = nullptr;  // [K][Mp] 16-bit count indices of the tabulated (region, block) pairs
+    unsigned short* dSi = nullptr;  // [Mp] the same for the read totals
+    // count-range table of K1 (kernels.cuh, build_increments_kernel): [K + 1 rows: regions, then S][blocks of unit_cells cells]{min, range}
     int* d_lut = nullptr;
+    int unit_cells = 0, n_blocks = 0;
     double lut_share = 0.0;  // fraction of the (row, block) pairs that are tabulated
     int* dW = nullptr;
     cudaStream_t stream = nullptr;
     RowPool pool;
 
     // staging: a ring of pinned segments (proposal blobs out, totals back) so that launches can be queued
-    // without a host round trip; one device arena (copies and kernels are ordered by the stream)
+    // without a host round trip; one device arena per lane (copies and kernels are ordered by the stream)
     struct Segment {
         unsigned char* h_arena = nullptr;
         double* h_total = nullptr;     // pinned [slots][2]
@@ -262,15 +391,15 @@ struct scicone_dataset {
         bool busy = false;
         unsigned long long ticket = 0;
         int lane = 0;
-        std::vector<double*> temp_rows;  // rows that only live for this launch: back to the pool when it is collected
+        std::vector<unsigned> temp_rows;  // rows that only live for this launch: back to the pool when it is collected
     };
     static constexpr int kRing = 8;
     Segment seg[kRing];
     unsigned long long next_ticket = 1;
     // Launch lanes: lane l has its own stream, device arena and range of reduction slots.  One lane (default): launches
     // are serialised by the stream, so accept / reject may be issued before the wait.  Two lanes (scicone_set_streams):
-    // consecutive launches alternate lanes and overlap on the device - K1 of one launch fills the issue slots the
-    // proposal kernel of the other leaves idle; the caller must then collect a launch before it settles its chains.
+    // consecutive launches alternate lanes and overlap on the device; the caller must then collect a launch before it
+    // settles its chains.
     static constexpr int kLanes = 2;
     int n_lanes = 1;
     cudaStream_t lane_stream[kLanes] = {nullptr, nullptr};
@@ -278,35 +407,35 @@ struct scicone_dataset {
     size_t arena_cap = 0;
     // per batch slot: reduction scratch and results
     int n_cta = 0, n_chunks = 0;
+    int cs_stride = 0;  // chunk sums per slot and value: n_chunks, or the widest shard's count on a cell-sharded dataset
     int slots = 0;
-    double* d_partial = nullptr;  // [slots][2][n_cta]   (0: tree score, 1: root score)
-    double* d_chunk = nullptr;    // [slots][2][n_chunks]
+    double* d_partial = nullptr;  // [lanes][slots][2][n_cta]   (0: tree score, 1: root score)
+    double* d_chunk = nullptr;    // [lanes][slots][2][cs_stride]
     double* d_total = nullptr;    // per lane: [slots][2] doubles, then [slots] status words
     size_t lane_result_bytes = 0;  // stride of one lane's result block
-    unsigned* d_counter = nullptr;
-    unsigned* d_status = nullptr;
+    unsigned* d_counter = nullptr;         // [lanes][slots]
+    unsigned* d_launch_counter = nullptr;  // [lanes]
     // multi-GPU
     void* comm = nullptr;
     void* comm_lane1 = nullptr;  // second lane: a communicator of its own (ncclCommSplit of `comm`), see scicone_set_streams
     int rank = 0, world = 1;
     int max_chunks_rank = 0;
-    double* d_gather = nullptr;  // per lane: [world][slots][2][max_chunks_rank]
-    double* d_send = nullptr;    // per lane: [slots][2][max_chunks_rank]
+    double* d_gather = nullptr;  // NCCL variant, per lane: [world][slots][2][max_chunks_rank]
     size_t gather_cap = 0;
     // Exchange of the chunk sums through peer memory (default on cell-sharded datasets; SCICONE_EXCHANGE=nccl selects the
-    // all-gather instead): every rank owns one buffer - flags [kLanes][world][kXchgSlots], then sums
+    // all-gather instead): every rank owns one buffer - flags [kLanes][world], then sums
     // [kLanes][2 (launch parity)][world][kXchgSlots][2][max_chunks_rank] - mapped into all the others (CUDA IPC), and the
-    // last CTA of a proposal stores its sums and its flag into all of them (finish_reduction, kernels.cuh).
+    // last CTA of a launch stores the launch's sums and its flag into all of them (finish_reduction, kernels.cuh).
     bool xchg_on = false;
     unsigned char* xchg = nullptr;
     std::vector<void*> xchg_peer;                     // base of rank p's buffer in this process (own: xchg)
     double** d_xchg_data_tab = nullptr;               // device: [kLanes][2][world] where this rank writes in rank p's buffer
     unsigned long long** d_xchg_flag_tab = nullptr;   // device: [kLanes][world]
     unsigned long long lane_seq[kLanes] = {0, 0};     // launches submitted per lane (the value published in the flags)
-    size_t xchg_flag_bytes() const { return sizeof(unsigned long long) * kLanes * world * kXchgSlots; }
-    size_t xchg_block() const { return (size_t)kXchgSlots * 2 * max_chunks_rank; }  // doubles of one rank in one (lane, parity) block
+    size_t xchg_flag_bytes() const { return round_up(sizeof(unsigned long long) * kLanes * world, 16); }
+    size_t xchg_block() const { return (size_t)SCICONE_MAX_SHARDED_BATCH * 2 * max_chunks_rank; }  // doubles of one rank in one (lane, parity) block
     unsigned long long* xchg_flags(void* base, int lane, int rk) const {
-        return reinterpret_cast<unsigned long long*>(base) + ((size_t)lane * world + rk) * kXchgSlots;
+        return reinterpret_cast<unsigned long long*>(base) + (size_t)lane * world + rk;
     }
     double* xchg_data(void* base, int lane, int parity, int rk) const {
         return reinterpret_cast<double*>(static_cast<unsigned char*>(base) + xchg_flag_bytes()) + (((size_t)lane * 2 + parity) * world + rk) * xchg_block();
@@ -321,16 +450,6 @@ struct scicone_dataset {
     double alg_bytes = 0.0, n_scores = 0.0;
     cudaEvent_t region_ev[2] = {nullptr, nullptr};
 
-    int drain() {  // wait for every queued launch (results of unclaimed tickets are dropped)
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        if (lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(lane_stream[1]));
-        for (Segment& g : seg) {
-            g.busy = false;
-            pool.put_many(g.temp_rows, 0);
-        }
-        return SCICONE_OK;
-    }
-
     int set_device() const {
         CUDA_TRY(cudaSetDevice(device));
         return SCICONE_OK;
@@ -342,7 +461,7 @@ struct scicone_dataset {
     }
     int ensure_arena(size_t bytes) {
         if (bytes <= arena_cap) return SCICONE_OK;
-        size_t cap = std::max<size_t>(bytes * 2, size_t(1) << 20);
+        size_t cap = std::max<size_t>(bytes * 2, size_t(4) << 20);
         // every queued launch has finished after the synchronize; the totals of tickets that were not collected yet sit in
         // their own pinned buffers (h_total), which are not touched here
         int rc0 = sync_lanes();
@@ -363,16 +482,19 @@ struct scicone_dataset {
     }
     double* lane_total(int lane) const { return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_total) + lane * lane_result_bytes); }
     unsigned* lane_status(int lane) const { return reinterpret_cast<unsigned*>(lane_total(lane) + (size_t)slots * 2); }
+    double* lane_partial(int lane) const { return d_partial + (size_t)lane * slots * 2 * n_cta; }
+    double* lane_chunk(int lane) const { return d_chunk + (size_t)lane * slots * 2 * cs_stride; }
     int ensure_slots(int n) {
         if (n <= slots) return SCICONE_OK;
         int ns = std::max(n, std::max(4, slots * 2));
+        if (world > 1) ns = std::min(std::max(n, ns), std::max(n, SCICONE_MAX_SHARDED_BATCH));
         int rc0 = sync_lanes();
         if (rc0) return rc0;
         for (Segment& g : seg)
-            if (g.busy) return fail(SCICONE_ERR_STATE, "batch size must grow while launches are outstanding");
+            if (g.busy) return fail(SCICONE_ERR_STATE, "the batch size cannot grow while launches are outstanding (scicone_dataset_reserve sets it up front)");
         cudaFree(d_partial); cudaFree(d_chunk); cudaFree(d_total); cudaFree(d_counter);
         d_partial = d_chunk = d_total = nullptr;
-        d_counter = d_status = nullptr;
+        d_counter = nullptr;
         for (Segment& g : seg) {
             if (g.h_total) cudaFreeHost(g.h_total);
             if (g.h_gather) cudaFreeHost(g.h_gather);
@@ -384,115 +506,86 @@ struct scicone_dataset {
         const size_t all = size_t(ns) * kLanes;  // every lane has its own range of ns slots
         lane_result_bytes = round_up((sizeof(double) * 2 + sizeof(unsigned)) * ns, 16);
         CUDA_TRY(cudaMalloc(&d_partial, sizeof(double) * all * 2 * n_cta));
-        CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * all * 2 * n_chunks));
+        CUDA_TRY(cudaMalloc(&d_chunk, sizeof(double) * all * 2 * cs_stride));
         CUDA_TRY(cudaMalloc(&d_total, lane_result_bytes * kLanes));  // per lane: totals, then the status words: one copy back
         CUDA_TRY(cudaMalloc(&d_counter, sizeof(unsigned) * all));
         CUDA_TRY(cudaMemset(d_counter, 0, sizeof(unsigned) * all));
         CUDA_TRY(cudaMemset(d_total, 0, lane_result_bytes * kLanes));
-        d_status = nullptr;  // addressed per lane: see lane_total / lane_status
+        CUDA_TRY(cudaMemset(d_chunk, 0, sizeof(double) * all * 2 * cs_stride));
         for (Segment& g : seg) {
             CUDA_TRY(cudaMallocHost(&g.h_total, lane_result_bytes));
             g.h_status = reinterpret_cast<unsigned*>(g.h_total + (size_t)ns * 2);
         }
         slots = ns;
         if (world > 1) {
-            cudaFree(d_gather); cudaFree(d_send);
-            d_gather = d_send = nullptr;
+            cudaFree(d_gather);
+            d_gather = nullptr;
             size_t per_rank = size_t(ns) * 2 * max_chunks_rank;
-            CUDA_TRY(cudaMalloc(&d_send, sizeof(double) * per_rank * kLanes));
             CUDA_TRY(cudaMalloc(&d_gather, sizeof(double) * per_rank * world * kLanes));
             for (Segment& g : seg) CUDA_TRY(cudaMallocHost(&g.h_gather, sizeof(double) * per_rank * world));
-            CUDA_TRY(cudaMemset(d_send, 0, sizeof(double) * per_rank * kLanes));
             gather_cap = per_rank;
         }
         return SCICONE_OK;
     }
 };
 
-static_assert(kXchgSlots == SCICONE_MAX_SHARDED_BATCH, "header and kernels disagree");
+static_assert(SCICONE_MAX_SHARDED_BATCH == 128, "documented in the header");
 constexpr size_t kStashRefill = 32, kStashMax = 160;
-constexpr int kDefaultOcc = 7;
 
 struct scicone_chain {
     scicone_dataset* ds = nullptr;
+    bool follower = false;  // cell-sharded runs: this rank does not own the chain, it only stages the owner's compiled proposals
     FlatMap<int, NodeRow> t;  // committed table, ascending node id (std::map order of the reference)
-    double* sums[2] = {nullptr, nullptr};  // [0] committed t_sums, [1] primed
-    int* maxid[2] = {nullptr, nullptr};
-    // lgamma rows of the committed nu and of a proposed nu
-    LCache Lt, Lp;
-    double Lt_nu = 0.0, Lp_nu = 0.0;
-    bool Lt_valid = false, Lp_valid = false;
+    unsigned sums[2] = {kNoRow, kNoRow};   // rows: [0] committed t_sums, [1] primed
+    unsigned maxid[2] = {kNoRow, kNoRow};  // rows holding the int32 argmax ids
     double t_nu = 0.0;  // Tree::nu of the committed tree
     bool od_p_valid = false;  // compute_t_prime_od_scores was already called for od_p_nu
     double od_p_nu = 0.0;
     bool with_od = false;     // the compiled proposal carries the root-score part
     // queued proposal
     bool pending = false;
-    bool compiled = false;  // the queued proposal's blob is built (scicone_prepare_t_prime or the batch call)
+    bool compiled = false;  // the queued proposal's blob is built (scicone_prepare_t_prime, an import, or the batch call)
     bool evaluated = false;
     TreeCopy tp;
     std::vector<int> roots;
     FlatMap<int, NodeRow> p;  // rescored node id -> primed row
     int deleted_id = -1;
     bool p_full = false;
-    // blob under construction, the data-only lgamma work it needs first (K1 items + their per-region arrays),
-    // and rows that only live for this launch (root-score slices)
+    // compiled proposal: the blob, the K1 work it needs first (items + their events / per-region constants), and rows that
+    // only live for this launch (root-score slices, increments of nodes that are rescored twice)
     std::vector<unsigned char> blob;
-    std::vector<DevBuild> builds;
-    std::vector<double> build_aux;
-    std::vector<double*> temp_rows;
+    std::vector<DevItem> items;
+    std::vector<unsigned char> aux;
+    std::vector<unsigned> temp_rows;
     double alg_bytes = 0.0, n_scores = 0.0;
-    // rows handed out by the dataset's pool in bulk: the chain takes and returns rows here without a lock, so chains
-    // compiled / committed on different host threads do not meet at the pool's mutex on every row
     struct Scratch {
         std::vector<int> child_off, child, fill, ptask, task_of_node, stack;
         std::vector<DevTask> tasks;
-        std::vector<DevEvent> events;
-        std::vector<const double*> prow, old_rows, g_of_task;
-        std::vector<double> nz, nzp;
-        std::vector<char> shares;
+        std::vector<unsigned> prow, old_rows, slice_rows;
         std::vector<DevUnch> unch;
-        std::vector<DevChunk> chunks;
     } scratch;
-    std::vector<double*> stash;
-    cudaError_t row_get(double** out) {
+    // rows handed out by the dataset's pool in bulk: the chain takes and returns rows here without a lock, so chains
+    // compiled / committed on different host threads do not meet at the pool's mutex on every row
+    std::vector<unsigned> stash;
+    int row_get(unsigned* out) {
         if (stash.empty()) {
-            cudaError_t e = ds->pool.get_many(kStashRefill, stash);
-            if (e != cudaSuccess) return e;
+            int rc = ds->pool.get_many(kStashRefill, stash);
+            if (rc) return rc;
         }
         *out = stash.back();
         stash.pop_back();
-        return cudaSuccess;
+        return SCICONE_OK;
     }
-    void row_put(double* r) {
-        if (!r) return;
+    void row_put(unsigned r) {
+        if (r == kNoRow) return;
         stash.push_back(r);
         if (stash.size() > kStashMax) ds->pool.put_many(stash, kStashMax / 2);
     }
-    LaunchEntry entry = {0u, 0u, 0u, 0u};  // first-chunk descriptor of the compiled blob (blob_off is filled in at submit)
+    LaunchEntry entry = {0u, 0u, 0u, 0u};  // first-chunk descriptor of the compiled blob (blob_off, slot are filled in at submit)
     double cost = 0.0;  // relative device time of the compiled proposal (orders the blobs inside a launch)
 };
 
 namespace {
-
-void release_cache(scicone_chain* ch, LCache& c) {
-    for (auto& kv : c) ch->row_put(kv.second);
-    c.clear();
-}
-
-LCache* cache_for(scicone_chain* ch, double nu) {
-    if (ch->Lt_valid && ch->Lt_nu == nu) return &ch->Lt;
-    if (!ch->Lt_valid) {
-        ch->Lt_valid = true;
-        ch->Lt_nu = nu;
-        return &ch->Lt;
-    }
-    if (ch->Lp_valid && ch->Lp_nu == nu) return &ch->Lp;
-    release_cache(ch, ch->Lp);
-    ch->Lp_valid = true;
-    ch->Lp_nu = nu;
-    return &ch->Lp;
-}
 
 void drop_pending(scicone_chain* ch) {
     for (auto& kv : ch->p) ch->row_put(kv.second.row);
@@ -503,158 +596,87 @@ void drop_pending(scicone_chain* ch) {
     ch->evaluated = false;
     ch->deleted_id = -1;
     ch->p_full = false;
-    for (double* r : ch->temp_rows) ch->row_put(r);
+    for (unsigned r : ch->temp_rows) ch->row_put(r);
     ch->temp_rows.clear();
     ch->od_p_valid = false;
     ch->with_od = false;
-    release_cache(ch, ch->Lp);
-    ch->Lp_valid = false;
 }
 
 template <class T>
-size_t blob_append(std::vector<unsigned char>& b, const std::vector<T>& v) {
+size_t bytes_append(std::vector<unsigned char>& b, const T* v, size_t n) {
     size_t off = round_up(b.size(), 16);
-    b.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
-    if (!v.empty()) memcpy(b.data() + off, v.data(), v.size() * sizeof(T));
+    b.resize(off + std::max<size_t>(round_up(n * sizeof(T), 16), 16));
+    if (n) memcpy(b.data() + off, v, n * sizeof(T));
     return off;
 }
+template <class T>
+size_t bytes_append(std::vector<unsigned char>& b, const std::vector<T>& v) {
+    return bytes_append(b, v.data(), v.size());
+}
 
-constexpr int kOdRegionsPerSlice = 6;  // 200 regions -> 32 slices: enough CTAs for one nu proposal to fill the GPU
+constexpr int kOdRegionsPerSlice = 6;  // 200 regions -> 32 slices: enough units for one nu proposal to fill the GPU
 
-// Root-score request (Tree::get_od_root_score, Tree.h:1774-1810): K1 items that reduce slices of the regions
-// into temporary rows; the proposal kernel adds the slices and the two cell-level terms.
-int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<const double*>& slice_rows) {
+// Root-score request (Tree::get_od_root_score, Tree.h:1774-1810): K1 items that reduce slices of the regions into
+// temporary rows; the proposal kernel adds the slices and the two cell-level terms.
+int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<unsigned>& slice_rows) {
     scicone_dataset* ds = ch->ds;
     const int K = ds->K;
-    const size_t aux0 = ch->build_aux.size();
-    ch->build_aux.resize(aux0 + 3 * (size_t)K, 0.0);
-    double* arg = ch->build_aux.data() + aux0;
-    double* cc = arg + K;
-    static_assert(sizeof(double*) == sizeof(double), "row pointers share the aux block with the doubles");
-    double** keep = reinterpret_cast<double**>(cc + K);  // rows[K]: lgamma rows the slices fill on the way (null: none)
-    for (int k = 0; k < K; ++k) keep[k] = nullptr;
+    std::vector<double> arg(2 * (size_t)K, 0.0);  // arg[K], then c[K]
+    double* cc = arg.data() + K;
     if (ds->od) {  // Tree.h:1783-1797 (no eta substitution here, quirk Q2)
         H.od_nz = nu * ds->root_z;
         H.od_lg_nz = lgamma(H.od_nz);
         {   // lgamma(S + nu z_root) as a K1 row
-            double* row = nullptr;
-            CUDA_TRY(ch->row_get(&row));
+            unsigned row = kNoRow;
+            int rc = ch->row_get(&row);
+            if (rc) return rc;
             ch->temp_rows.push_back(row);
-            DevBuild it;
+            DevItem it;
             memset(&it, 0, sizeof it);
+            it.kind = ITEM_G_ROW;
             it.dst = row;
-            it.src = ds->dS;
-            it.c1 = H.od_nz;
-            it.kind = BUILD_G;
-            it.n_cells = ds->M;
-            it.row_stride = (long long)ds->Mp;
-            ch->builds.push_back(it);
+            it.nz = H.od_nz;
+            ch->items.push_back(it);
             H.od_g_row = row;
         }
         for (int k = 0; k < K; ++k) {
             arg[k] = nu * ds->neutral[k] * ds->r[k];
             cc[k] = lgamma(arg[k]);
         }
-        // A queued row item L(k, neutral_k) evaluates lgamma(D_k + arg[k]) - exactly the root term of region k: let the
-        // slice store it and drop the item (about a sixth of the lgamma work of a nu proposal)
-        std::vector<DevBuild>& items = ch->builds;
-        size_t kept = 0;
-        for (size_t i = 0; i < items.size(); ++i) {
-            const DevBuild& it = items[i];
-            bool shared = false;
-            if (it.kind == BUILD_G && it.src >= ds->dDt && it.src < ds->dDt + (size_t)K * ds->Mp) {
-                const int k = (int)((it.src - ds->dDt) / ds->Mp);
-                if (!keep[k] && memcmp(&it.c1, &arg[k], sizeof(double)) == 0) {
-                    keep[k] = it.dst;
-                    shared = true;
-                }
-            }
-            if (!shared) items[kept++] = it;
-        }
-        items.resize(kept);
     } else {  // Tree.h:1799-1806
         H.od_lg_nz = log((double)ds->sum_r);
-        for (int k = 0; k < K; ++k) {
-            arg[k] = log((double)ds->r[k]);
-            cc[k] = 0.0;
-        }
+        for (int k = 0; k < K; ++k) arg[k] = log((double)ds->r[k]);
     }
+    const unsigned aux_off = (unsigned)bytes_append(ch->aux, arg);
     const int n_slices = std::max(1, std::min(kMaxOdSlices, K / kOdRegionsPerSlice));
     for (int s = 0; s < n_slices; ++s) {
-        double* row = nullptr;
-        CUDA_TRY(ch->row_get(&row));
+        unsigned row = kNoRow;
+        int rc = ch->row_get(&row);
+        if (rc) return rc;
         ch->temp_rows.push_back(row);
         slice_rows.push_back(row);
-        DevBuild it;
+        DevItem it;
         memset(&it, 0, sizeof it);
+        it.kind = ds->od ? ITEM_SLICE_OD : ITEM_SLICE_MN;
         it.dst = row;
-        it.src = ds->dDt;
-        it.kind = ds->od ? BUILD_OD_SLICE : BUILD_OD_SLICE_LOG;
+        it.aux_off = aux_off;  // relative to the chain's aux block; rebased at submit
         it.k0 = (int)((long long)K * s / n_slices);
         it.k1 = (int)((long long)K * (s + 1) / n_slices);
-        it.off_arg = (unsigned)(aux0 * sizeof(double));        // relative to the chain's aux block; rebased at submit
-        it.off_c = (unsigned)((aux0 + K) * sizeof(double));
-        it.off_rows = (unsigned)((aux0 + 2 * (size_t)K) * sizeof(double));
-        it.n_cells = ds->M;
-        it.row_stride = (long long)ds->Mp;
-        ch->builds.push_back(it);
+        ch->items.push_back(it);
     }
     H.n_od_slices = n_slices;
     H.flags |= PROP_WITH_OD;
     return SCICONE_OK;
 }
 
-void fill_header_common(scicone_chain* ch, int lane, int slot, DevHeader& H) {
-    scicone_dataset* ds = ch->ds;
-    const size_t gs = (size_t)lane * ds->slots + slot;  // global slot: every lane owns a range of ds->slots slots
-    H.n_cells = ds->M;
-    H.S = ds->dS;
-    H.w = ds->dW;
-    H.sums_old = ch->sums[0];
-    H.sums_new = ch->sums[1];
-    H.maxid_old = ch->maxid[0];
-    H.maxid_new = ch->maxid[1];
-    H.partial = ds->d_partial + gs * 2 * ds->n_cta;
-    H.chunk_sums = ds->d_chunk + gs * 2 * ds->n_chunks;
-    H.total = ds->lane_total(lane) + (size_t)slot * 2;
-    H.counter = ds->d_counter + gs;
-    H.status = ds->lane_status(lane) + slot;
-    if (ds->xchg_on) {
-        const unsigned long long seq = ds->lane_seq[lane];
-        H.xchg_data = ds->d_xchg_data_tab + ((size_t)lane * 2 + (seq & 1)) * ds->world;
-        H.xchg_flag = ds->d_xchg_flag_tab + (size_t)lane * ds->world;
-        H.xchg_seq = seq;
-        H.xchg_world = ds->world;
-        H.xchg_slot = slot;
-        H.xchg_stride = ds->max_chunks_rank;
-    } else {
-        H.xchg_data = nullptr;
-        H.xchg_flag = nullptr;
-        H.xchg_seq = 0;
-        H.xchg_world = 0;
-        H.xchg_slot = 0;
-        H.xchg_stride = 0;
-    }
-    H.xchg_pad = 0;
-}
-
-// The reduction scratch of a compiled blob is chosen when the batch is put together.
-void patch_slot(scicone_chain* ch, int lane, int slot) {
-    DevHeader H;
-    memcpy(&H, ch->blob.data(), sizeof H);
-    fill_header_common(ch, lane, slot, H);
-    memcpy(ch->blob.data(), &H, sizeof H);
-}
-
-// Compile the queued proposal of `ch` into ch->blob (+ ch->builds).  `slot` selects the reduction scratch.
-int compile_proposal(scicone_chain* ch, int slot, bool full) {
+// Compile the queued proposal of `ch` into ch->blob (+ ch->items, ch->aux).
+int compile_proposal(scicone_chain* ch, bool full, bool full_with_od) {
     scicone_dataset* ds = ch->ds;
     const TreeCopy& T = ch->tp;
     const double nu = T.nu;
     const bool od = ds->od;
-    LCache* L = od ? cache_for(ch, nu) : nullptr;
-    ch->builds.clear();
-    ch->build_aux.clear();
+    ch->items.clear();
+    ch->aux.clear();
 
     // scratch vectors live in the chain: a proposal is compiled every ~100 us per chain, so no heap traffic here
     scicone_chain::Scratch& W = ch->scratch;
@@ -667,22 +689,17 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     for (int i = 1; i < T.n; ++i) child[fill[T.parent[i]]++] = i;
 
     std::vector<DevTask>& tasks = W.tasks;
-    std::vector<DevEvent>& events = W.events;
-    std::vector<const double*>& prow = W.prow;  // per task: where its parent's score lives
-    std::vector<int>& ptask = W.ptask;          // per task: task index of the parent, -1 when the parent is not rescored before
-    std::vector<double>&tnz = W.nz, &tnzp = W.nzp;  // per task: nu*z, nu*z_parent (arguments of the z-terms)
-    std::vector<char>& shares = W.shares;       // per task: nu*z_parent is bit-equal to the parent task's nu*z
+    std::vector<unsigned>& prow = W.prow;  // per task: row that holds its parent's score
+    std::vector<int>& ptask = W.ptask;     // per task: task index of the parent, -1 when the parent is not rescored before
     std::vector<int>& task_of_node = W.task_of_node;
     std::vector<int>& stack = W.stack;
     tasks.clear();
-    events.clear();
     prow.clear();
     ptask.clear();
-    tnz.clear();
-    tnzp.clear();
-    shares.clear();
     stack.clear();
     task_of_node.assign(T.n, -1);
+    size_t n_events = 0;
+    std::vector<DevEvent> evs;  // events of the node being compiled
     for (size_t ri = 0; ri < ch->roots.size(); ++ri) {
         const int root = ch->roots[ri];
         stack.push_back(root);
@@ -696,15 +713,13 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
             memset(&tk, 0, sizeof tk);
             tk.node_id = id;
             int parent_task = -1;
-            const double* parent_row = nullptr;
-            double nz_v = 0.0, nzp_v = 0.0;
-            bool share_v = false;
-            tk.ev_begin = (int)events.size();
+            unsigned parent_row = kNoRow;
+            DevItem item;
+            memset(&item, 0, sizeof item);
             int z_int;
             if (pidx < 0) {  // Tree::compute_root_score, Tree.h:145-160
                 tk.flags = TASK_ROOT;
                 z_int = ds->root_z;
-                nz_v = nu * (double)z_int;
             } else {
                 const int pid = T.id[pidx];
                 int pz;
@@ -725,6 +740,7 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                 // Tree::compute_score, Tree.h:177-198: z = parent.z + sum_k r_k (cn_node - cn_parent)
                 double zd = (double)pz;
                 const double zp = (double)pz;
+                evs.clear();
                 for (int e = T.chg_off[n]; e < T.chg_off[n + 1]; ++e) {
                     const int k = T.chg_region[e];
                     const int cn_i = T.genotype_at(n, k) + ds->neutral[k];
@@ -732,79 +748,59 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                     const double node_cn = cn_i == 0 ? ds->eta : (double)cn_i;
                     const double parent_cn = cp_i == 0 ? ds->eta : (double)cp_i;
                     zd += ds->r[k] * (node_cn - parent_cn);
-                }
-                for (int e = T.chg_off[n]; e < T.chg_off[n + 1]; ++e) {
-                    const int k = T.chg_region[e];
-                    const int cn_i = T.genotype_at(n, k) + ds->neutral[k];
-                    const int cp_i = T.genotype_at(pidx, k) + ds->neutral[k];
-                    const double node_cn = cn_i == 0 ? ds->eta : (double)cn_i;
-                    const double parent_cn = cp_i == 0 ? ds->eta : (double)cp_i;
                     DevEvent ev;
                     memset(&ev, 0, sizeof ev);
-                    if (od) {  // Tree.h:214-218
-                        const double argN = nu * node_cn * ds->r[k];
-                        const double argP = nu * parent_cn * ds->r[k];
-                        ev.a = lgamma(argN);
-                        ev.b = lgamma(argP);
-                        // lgamma rows L(k, cn)[j] = lgamma(D[j][k] + (nu*cn)*r_k): built by K1 on first use at this nu, shared
-                        // by every event that touches region k at that copy number (the parent side is most often the
-                        // neutral state, so a region's second row usually exists already)
-                        const double arg[2] = {argN, argP};
-                        const int cn2[2] = {cn_i, cp_i};
-                        const double* rows2[2];
-                        for (int side = 0; side < 2; ++side) {
-                            double** slotp = &(*L)[lkey(k, cn2[side])];
-                            if (!*slotp) {
-                                CUDA_TRY(ch->row_get(slotp));
-                                DevBuild it;
-                                memset(&it, 0, sizeof it);
-                                it.dst = *slotp;
-                                it.src = ds->dDt + (size_t)k * ds->Mp;
-                                it.c1 = arg[side];
-                                it.kind = BUILD_G;  // dst = lgamma(src + c1)
-                                it.n_cells = ds->M;
-                                it.row_stride = (long long)ds->Mp;
-                                ch->builds.push_back(it);
-                            }
-                            rows2[side] = *slotp;
-                        }
-                        ev.row = rows2[0];
-                        ev.row_p = rows2[1];
-                    } else {  // Tree.h:221
-                        ev.row = ds->dDt + (size_t)k * ds->Mp;
+                    ev.k = k;
+                    if (od) {  // Tree.h:214-218: x += lgamma(D_k + argN) - lgamma(D_k + argP); x -= lgamma(argN); x += lgamma(argP)
+                        ev.argN = nu * node_cn * ds->r[k];
+                        ev.argP = nu * parent_cn * ds->r[k];
+                        ev.a = lgamma(ev.argN);
+                        ev.b = lgamma(ev.argP);
+                    } else  // Tree.h:221
                         ev.a = log(node_cn) - log(parent_cn);
-                    }
-                    events.push_back(ev);
+                    evs.push_back(ev);
                 }
-                if (events.size() - (size_t)tk.ev_begin > 65535) return fail(SCICONE_ERR_ARG, "more than 65535 events in one node");
-                tk.n_ev = (unsigned short)(events.size() - (size_t)tk.ev_begin);
+                item.kind = od ? ITEM_NODE_OD : ITEM_NODE_MN;
+                item.n_ev = (int)evs.size();
+                item.aux_off = evs.empty() ? 0u : (unsigned)bytes_append(ch->aux, evs);
+                n_events += evs.size();
                 if (od) {  // Tree.h:227-231
-                    nz_v = nu * zd;
-                    nzp_v = nu * zp;
-                    tk.lg_nz = lgamma(nz_v);
-                    tk.lg_nzp = lgamma(nzp_v);
-                    share_v = parent_task >= 0 && memcmp(&tnz[parent_task], &nzp_v, sizeof(double)) == 0;
+                    item.nz = nu * zd;
+                    item.nzp = nu * zp;
+                    item.lg_nz = lgamma(item.nz);
+                    item.lg_nzp = lgamma(item.nzp);
                 } else {  // Tree.h:236-237
-                    tk.lg_nz = log(zd);
-                    tk.lg_nzp = log(zp);
+                    item.lg_nz = log(zd);
+                    item.lg_nzp = log(zp);
                 }
                 z_int = (int)zd;  // Tree.h:241 into the int Node::z (quirk Q1)
             }
             auto own = ch->p.find(id);
             if (own == ch->p.end()) {
-                double* row = nullptr;
-                CUDA_TRY(ch->row_get(&row));
+                unsigned row = kNoRow;
+                int rc = ch->row_get(&row);
+                if (rc) return rc;
                 own = ch->p.emplace(id, NodeRow{row, z_int}).first;
-            } else
+                tk.inc = row;
+            } else {
+                // the node is rescored a second time by this proposal (overlapping subtree roots of a label swap): the score
+                // goes to the same row, the increment of this visit waits in a row of its own
                 own->second.z = z_int;
+                unsigned row = kNoRow;
+                int rc = ch->row_get(&row);
+                if (rc) return rc;
+                ch->temp_rows.push_back(row);
+                tk.inc = row;
+            }
             tk.dst = own->second.row;
+            if (!(tk.flags & TASK_ROOT)) {
+                item.dst = tk.inc;
+                ch->items.push_back(item);
+            }
             task_of_node[n] = (int)tasks.size();
             tasks.push_back(tk);
             prow.push_back(parent_row);
             ptask.push_back(parent_task);
-            tnz.push_back(nz_v);
-            tnzp.push_back(nzp_v);
-            shares.push_back(share_v ? 1 : 0);
             for (int c = child_off[n + 1] - 1; c >= child_off[n]; --c) stack.push_back(child[c]);
         }
     }
@@ -816,73 +812,20 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
         for (size_t i = 0; i < tasks.size(); ++i)
             if (last[tasks[i].node_id] != (int)i) tasks[i].flags |= TASK_SKIP_AGG;
     }
-    // Walk bookkeeping for the one-thread-per-cell kernel.  z-terms lgamma(S + nu z) are not evaluated in the serial walk:
-    // K1 builds them as rows (every (node, cell) pair is independent) and the walk gathers them, so the proposal kernel
-    // carries no lgamma at all.  Parent scores: a parent visited at most kScRing nodes ago is read from the thread's
-    // shared-memory ring; the committed row of a subtree root's parent is prefetched with the other gathers; a parent
-    // rescored further back is read from the row this thread wrote (plain load, one node ahead).
-    std::vector<DevChunk>& chunks = W.chunks;
-    chunks.clear();
-    if (od) {
-        auto build_g = [&](double arg, const double** out) -> int {
-            double* row = nullptr;
-            CUDA_TRY(ch->row_get(&row));
-            ch->temp_rows.push_back(row);
-            DevBuild it;
-            memset(&it, 0, sizeof it);
-            it.dst = row;
-            it.src = ds->dS;
-            it.c1 = arg;
-            it.kind = BUILD_G;
-            it.n_cells = ds->M;
-            it.row_stride = (long long)ds->Mp;
-            ch->builds.push_back(it);
-            *out = row;
-            return SCICONE_OK;
-        };
-        W.g_of_task.assign(tasks.size(), nullptr);
-        for (size_t i = 0; i < tasks.size(); ++i) {
-            const double* g = nullptr;
-            const double* gp = nullptr;
-            int rc = build_g(tnz[i], &g);
-            if (rc) return rc;
-            W.g_of_task[i] = g;
-            if (!(tasks[i].flags & TASK_ROOT)) {
-                if (shares[i])
-                    gp = W.g_of_task[ptask[i]];
-                else if ((rc = build_g(tnzp[i], &gp)))
-                    return rc;
-            }
-            tasks[i].g_row = g;
-            tasks[i].gp_row = gp;
-        }
-    }
+    // Walk bookkeeping for the one-thread-per-cell kernel.  Parent scores: a parent visited at most kScRing nodes ago is
+    // still in the thread's registers; the committed row of a subtree root's parent, or a parent rescored further back, is
+    // read from its row (plain load, one node ahead).
     for (size_t i = 0; i < tasks.size(); ++i) {
-        if (!(tasks[i].flags & TASK_ROOT)) {
-            const int back = ptask[i] >= 0 ? (int)i - ptask[i] : 0;
-            if (back >= 1 && back <= kScRing)
-                tasks[i].parent_back = (unsigned char)back;
-            else {
-                tasks[i].parent_row = prow[i];
-                tasks[i].flags |= TASK_PS_FAR;
-            }
+        if (tasks[i].flags & TASK_ROOT) continue;
+        const int back = ptask[i] >= 0 ? (int)i - ptask[i] : 0;
+        if (back >= 1 && back <= kScRing)
+            tasks[i].parent_back = (unsigned)back;
+        else {
+            tasks[i].parent_row = prow[i];
+            tasks[i].flags |= TASK_PS_FAR;
         }
-        if (tasks[i].n_ev > kEvStage) tasks[i].flags |= TASK_BIG;
-        const int staged = (tasks[i].flags & TASK_BIG) ? 0 : tasks[i].n_ev;
-        if (chunks.empty() || chunks.back().n_tasks >= kTaskChunk || chunks.back().n_ev + staged > kEvStage) {
-            DevChunk c;
-            c.first_task = (int)i;
-            c.n_tasks = 0;
-            c.ev_base = tasks[i].ev_begin;
-            c.n_ev = 0;
-            chunks.push_back(c);
-        }
-        DevChunk& c = chunks.back();
-        tasks[i].ev_rel = (unsigned short)(tasks[i].ev_begin - c.ev_base);
-        c.n_tasks++;
-        if (!(tasks[i].flags & TASK_BIG)) c.n_ev = tasks[i].ev_begin + tasks[i].n_ev - c.ev_base;
     }
-    std::vector<const double*>& old_rows = W.old_rows;
+    std::vector<unsigned>& old_rows = W.old_rows;
     std::vector<DevUnch>& unch = W.unch;
     old_rows.clear();
     unch.clear();
@@ -906,7 +849,6 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
                 DevUnch u;
                 u.row = kv.second.row;
                 u.id = kv.first;
-                u.pad = 0;
                 unch.push_back(u);
             }
     }
@@ -914,83 +856,90 @@ int compile_proposal(scicone_chain* ch, int slot, bool full) {
     DevHeader H;
     memset(&H, 0, sizeof H);
     H.n_tasks = (int)tasks.size();
-    H.n_chunks = (int)chunks.size();
     H.n_old = (int)old_rows.size();
     H.n_unch = (int)unch.size();
     H.deleted_id = ch->deleted_id;
     H.flags = (ds->maxs ? PROP_MAX : 0u) | (od ? PROP_OD : 0u) | (full ? PROP_FULL : 0u);
     if (!full && ch->p.size() >= unch.size()) H.flags |= PROP_SCRATCH;  // MathOp.cpp:315
-    fill_header_common(ch, 0, slot, H);  // lane and slot are patched when the batch is put together
-    {   // 16 + 8 E_n bytes per rescored cell x node score, 8 N + 12 per cell aggregate
-        const double n_table = full ? (double)ch->p.size() : (double)(unch.size() + ch->p.size());
-        ch->alg_bytes = (double)ds->M * (16.0 * tasks.size() + 8.0 * events.size() + 8.0 * n_table + 12.0);
-        ch->n_scores = (double)ds->M * tasks.size();
-        ch->cost = 4.0 * tasks.size() + events.size() + (full ? 0.0 : 0.5 * unch.size());
-    }
+    H.sums_old = ch->sums[0];
+    H.sums_new = ch->sums[1];
+    H.maxid_old = ch->maxid[0];
+    H.maxid_new = ch->maxid[1];
+    H.od_g_row = kNoRow;
     // a proposal that changes nu also needs Inference::compute_t_prime_od_scores (Inference.h:942): evaluated by
     // the same launch unless the caller already asked for it separately
-    std::vector<const double*> slice_rows;
-    ch->with_od = !full && nu != ch->t_nu && !(ch->od_p_valid && ch->od_p_nu == nu);
+    std::vector<unsigned>& slice_rows = W.slice_rows;
+    slice_rows.clear();
+    ch->with_od = full ? full_with_od : (nu != ch->t_nu && !(ch->od_p_valid && ch->od_p_nu == nu));
+    const bool whole_tree = full || (ch->roots.size() == 1 && T.parent[ch->roots[0]] < 0);
+    {   // SURVEY.md section 8d.  Delta move: 16 + 8 E_n bytes per rescored cell x node score, 8 N + 12 per cell aggregate.
+        // Full pass / nu move: 8 K (the cell's row of D) + 8 N (scores written) + 8 N + 12 (aggregate).
+        const double n_table = full ? (double)ch->p.size() : (double)(unch.size() + ch->p.size());
+        if (whole_tree)
+            ch->alg_bytes = (double)ds->M * (8.0 * ds->K + 8.0 * tasks.size() + 8.0 * n_table + 12.0);
+        else
+            ch->alg_bytes = (double)ds->M * (16.0 * tasks.size() + 8.0 * n_events + 8.0 * n_table + 12.0);
+        ch->n_scores = (double)ds->M * tasks.size();
+        ch->cost = 2.0 * tasks.size() + (full ? 0.0 : 0.5 * unch.size());
+    }
     if (ch->with_od) {
         int rc = add_od_request(ch, nu, H, slice_rows);
         if (rc) return rc;
-        ch->alg_bytes += (double)ds->M * 8.0 * ds->K;
+        if (!whole_tree) ch->alg_bytes += (double)ds->M * 8.0 * ds->K;
     }
     std::vector<unsigned char>& b = ch->blob;
     b.clear();
     b.resize(sizeof(DevHeader));
-    H.off_tasks = (unsigned)blob_append(b, tasks);
-    H.off_events = (unsigned)blob_append(b, events);
-    H.off_chunks = (unsigned)blob_append(b, chunks);
-    H.off_old = (unsigned)blob_append(b, old_rows);
-    H.off_unch = (unsigned)blob_append(b, unch);
-    H.off_od_rows = (unsigned)blob_append(b, slice_rows);
-    b.resize(round_up(b.size(), 16));
+    const size_t off_tasks = bytes_append(b, tasks);
+    H.off_old = (unsigned)bytes_append(b, old_rows);
+    H.off_unch = (unsigned)bytes_append(b, unch);
+    H.off_od_rows = (unsigned)bytes_append(b, slice_rows);
     memcpy(b.data(), &H, sizeof H);
-    if (H.off_tasks != sizeof(DevHeader)) return fail(SCICONE_ERR_STATE, "internal: task records must follow the header");
-    ch->entry = LaunchEntry{0u, chunks.empty() ? 0u : (unsigned)chunks[0].n_tasks, chunks.empty() ? 0u : (unsigned)chunks[0].n_ev,
-                            chunks.empty() ? 0u : H.off_events + (unsigned)chunks[0].ev_base * (unsigned)sizeof(DevEvent)};
+    if (off_tasks != sizeof(DevHeader)) return fail(SCICONE_ERR_STATE, "internal: task records must follow the header");
+    ch->entry = LaunchEntry{0u, (unsigned)std::min<size_t>(tasks.size(), kTaskChunk), 0u, 0u};
     return SCICONE_OK;
 }
 
 // A blob that only evaluates the root score at `nu` (Inference::compute_t_od_scores, Inference.h:1406-1419).
-int compile_od_only(scicone_chain* ch, double nu, int slot) {
-    ch->builds.clear();
-    ch->build_aux.clear();
+int compile_od_only(scicone_chain* ch, double nu) {
+    ch->items.clear();
+    ch->aux.clear();
     DevHeader H;
     memset(&H, 0, sizeof H);
     H.deleted_id = -1;
     H.flags = (ch->ds->od ? PROP_OD : 0u) | PROP_OD_ONLY;
-    fill_header_common(ch, 0, slot, H);
-    std::vector<const double*> slice_rows;
+    H.sums_old = H.sums_new = ch->sums[0];
+    H.maxid_old = H.maxid_new = ch->maxid[0];
+    H.od_g_row = kNoRow;
+    std::vector<unsigned> slice_rows;
     int rc = add_od_request(ch, nu, H, slice_rows);
     if (rc) return rc;
     std::vector<unsigned char>& b = ch->blob;
     b.clear();
     b.resize(sizeof(DevHeader));
-    H.off_tasks = H.off_events = H.off_old = H.off_unch = (unsigned)b.size();
-    H.off_od_rows = (unsigned)blob_append(b, slice_rows);
-    b.resize(round_up(b.size(), 16));
+    H.off_old = H.off_unch = (unsigned)b.size();
+    H.off_od_rows = (unsigned)bytes_append(b, slice_rows);
     memcpy(b.data(), &H, sizeof H);
     ch->alg_bytes = (double)ch->ds->M * 8.0 * ch->ds->K;
     ch->n_scores = 0.0;
+    ch->cost = 1.0;
     ch->with_od = true;
     ch->entry = LaunchEntry{0u, 0u, 0u, 0u};
     return SCICONE_OK;
 }
 
-// Queue the compiled blobs of `n` chains (all on one dataset): K1 for the data-only lgamma work they need
-// (if any), then ONE launch of the proposal kernel; returns a ticket.
+// Queue the compiled proposals of `n` chains (all on one dataset): K1 for the increments and slices they need, then ONE
+// launch of the proposal kernel; returns a ticket.
 int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, unsigned long long* ticket) {
     const size_t head = sizeof(LaunchEntry) * n;
     size_t bytes = head, n_items = 0, aux_bytes = 0;
     for (int i = 0; i < n; ++i) {
         bytes += chains[i]->blob.size();
-        n_items += chains[i]->builds.size();
-        aux_bytes += round_up(chains[i]->build_aux.size() * sizeof(double), 16);
+        n_items += chains[i]->items.size();
+        aux_bytes += round_up(chains[i]->aux.size(), 16);
     }
     const size_t off_items = bytes;
-    const size_t off_aux = off_items + n_items * sizeof(DevBuild);
+    const size_t off_aux = off_items + n_items * sizeof(DevItem);
     bytes = off_aux + aux_bytes;
     int rc = ds->ensure_arena(bytes);
     if (rc) return rc;
@@ -1004,17 +953,15 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     cudaStream_t st = lane == 0 ? ds->stream : ds->lane_stream[1];
     unsigned char* d_arena = ds->d_arena[lane];
     g.lane = lane;
-    if (ds->xchg_on) {
-        if (n > kXchgSlots) return fail(SCICONE_ERR_ARG, "at most %d proposals per launch on a cell-sharded dataset", kXchgSlots);
-        ds->lane_seq[lane]++;  // the headers below carry it
-    }
-    for (int i = 0; i < n; ++i) patch_slot(chains[i], lane, i);
+    if (ds->world > 1 && n > SCICONE_MAX_SHARDED_BATCH)
+        return fail(SCICONE_ERR_ARG, "at most %d proposals per launch on a cell-sharded dataset", SCICONE_MAX_SHARDED_BATCH);
+    if (ds->xchg_on) ds->lane_seq[lane]++;
     g.with_od.assign((size_t)n, 0);
     LaunchEntry* offs = reinterpret_cast<LaunchEntry*>(g.h_arena);
     size_t at = head, item_at = off_items;
     // grid.y order = longest proposal first (CTAs are dispatched in block-id order): the heavy full-tree
     // rescorings of nu proposals start at once and the short ones fill in behind them.  Results are addressed by
-    // the slot pointers inside each header, so the order of the blobs is free.
+    // the slot in each launch entry, so the order of the blobs is free.
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return chains[a]->cost > chains[b]->cost; });
@@ -1025,92 +972,99 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         memcpy(g.h_arena + at, ch->blob.data(), ch->blob.size());
         at += ch->blob.size();
     }
-    // K1 items: the root-score slices (about 24 lgamma per thread and unit) first, the one-lgamma rows behind them,
-    // so the persistent CTAs start with the long units
+    // K1 items: the root-score slices (several table builds and ~6 look-ups per cell) first, the node increments behind
+    // them, so the persistent CTAs start with the long units
     for (int pass = 0; pass < 2; ++pass) {
         size_t chain_aux = off_aux;
         for (int i = 0; i < n; ++i) {
             scicone_chain* ch = chains[i];
-            if (pass == 0 && !ch->build_aux.empty())
-                memcpy(g.h_arena + chain_aux, ch->build_aux.data(), ch->build_aux.size() * sizeof(double));
-            for (const DevBuild& src : ch->builds) {
-                const bool slice = src.kind == BUILD_OD_SLICE || src.kind == BUILD_OD_SLICE_LOG;
+            if (pass == 0 && !ch->aux.empty()) memcpy(g.h_arena + chain_aux, ch->aux.data(), ch->aux.size());
+            for (const DevItem& src : ch->items) {
+                const bool slice = src.kind == ITEM_SLICE_OD || src.kind == ITEM_SLICE_MN;
                 if (slice != (pass == 0)) continue;
-                DevBuild it = src;
-                if (it.kind == BUILD_G && ds->d_lut) {  // which row of counts the item reads: region k, or the row sums
-                    if (it.src == ds->dS) it.lut_row = (unsigned)ds->K + 1;
-                    else if (it.src >= ds->dDt && it.src < ds->dDt + (size_t)ds->K * ds->Mp) it.lut_row = (unsigned)((it.src - ds->dDt) / ds->Mp) + 1;
-                }
-                if (slice) {
-                    it.off_arg += (unsigned)chain_aux;
-                    it.off_c += (unsigned)chain_aux;
-                    it.off_rows += (unsigned)chain_aux;
-                }
+                DevItem it = src;
+                it.aux_off += (unsigned)chain_aux;
                 memcpy(g.h_arena + item_at, &it, sizeof it);
                 item_at += sizeof it;
             }
-            chain_aux += round_up(ch->build_aux.size() * sizeof(double), 16);
+            chain_aux += round_up(ch->aux.size(), 16);
         }
     }
     for (int q = 0; q < n; ++q) {
         offs[q] = chains[order[q]]->entry;
         offs[q].blob_off = blob_at[order[q]];
+        offs[q].slot = (unsigned)order[q];
     }
     CUDA_TRY(cudaMemcpyAsync(d_arena, g.h_arena, bytes, cudaMemcpyHostToDevice, st));
+    LaunchParams P;
+    memset(&P, 0, sizeof P);
+    P.arena = d_arena;
+    P.rows = ds->pool.base_ptr();
+    P.stride = (long long)ds->Mp;
+    P.Dt = ds->dDt;
+    P.It = ds->dIt;
+    P.S = ds->dS;
+    P.Si = ds->dSi;
+    P.w = ds->dW;
+    P.lut = ds->d_lut;
+    P.n_cells = ds->M;
+    P.n_blocks = ds->n_blocks;
+    P.unit_cells = ds->unit_cells;
+    P.n_regions = ds->K;
+    P.partial = ds->lane_partial(lane);
+    P.chunk_sums = ds->lane_chunk(lane);
+    P.total = ds->lane_total(lane);
+    P.counter = ds->d_counter + (size_t)lane * ds->slots;
+    P.status = ds->lane_status(lane);
+    P.n_cta = ds->n_cta;
+    P.n_red_chunks = ds->n_chunks;
+    P.cs_stride = ds->cs_stride;
+    P.n_props = n;
+    P.launch_counter = ds->d_launch_counter + lane;
+    if (ds->xchg_on) {
+        const unsigned long long seq = ds->lane_seq[lane];
+        P.xchg_data = ds->d_xchg_data_tab + ((size_t)lane * 2 + (seq & 1)) * ds->world;
+        P.xchg_flag = ds->d_xchg_flag_tab + (size_t)lane * ds->world;
+        P.xchg_seq = seq;
+        P.xchg_world = ds->world;
+    }
+    P.off_items = (unsigned)off_items;
+    P.n_items = (int)n_items;
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, st));
-        const int blocks_per_row = (ds->M + kUnitCells - 1) / kUnitCells;
-        const long long units = (long long)n_items * blocks_per_row;
-        build_rows_kernel<<<(unsigned)std::min<long long>(units, 4ll * ds->n_sm), kBuildBlock, 0, st>>>(
-            d_arena, (unsigned)off_items, (int)n_items, blocks_per_row, ds->d_lut);
+        const long long units = (long long)n_items * ds->n_blocks;
+        build_increments_kernel<<<(unsigned)std::min<long long>(units, 4ll * ds->n_sm), kBuildBlock, 0, st>>>(P);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
     }
     g.n_items = (int)n_items;
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, st));
-    {   // scoring mode and likelihood are properties of the dataset: one specialisation per launch.  kOcc = CTAs per SM the
-        // register allocation aims at (shared memory - the cp.async ring - allows 7); SCICONE_OCC overrides the default for tuning.
-        static const int occ = [] {
-            const char* e = getenv("SCICONE_OCC");
-            const int v = e ? atoi(e) : 0;
-            return (v == 5 || v == 6 || v == 7) ? v : kDefaultOcc;
-        }();
+    {   // the scoring mode is a property of the dataset: one specialisation per launch
         const dim3 grid(ds->n_cta, n);
-#define SCICONE_LAUNCH(OCC)                                                                                                \
-    do {                                                                                                                   \
-        if (ds->maxs && ds->od) score_proposals_kernel<true, true, OCC><<<grid, kThreads, 0, st>>>(d_arena);   \
-        else if (ds->maxs) score_proposals_kernel<true, false, OCC><<<grid, kThreads, 0, st>>>(d_arena);        \
-        else if (ds->od) score_proposals_kernel<false, true, OCC><<<grid, kThreads, 0, st>>>(d_arena);          \
-        else score_proposals_kernel<false, false, OCC><<<grid, kThreads, 0, st>>>(d_arena);                     \
-    } while (0)
-        if (occ == 5) SCICONE_LAUNCH(5);
-        else if (occ == 6) SCICONE_LAUNCH(6);
-        else SCICONE_LAUNCH(7);
-#undef SCICONE_LAUNCH
+        if (ds->maxs)
+            score_proposals_kernel<true><<<grid, kThreads, 0, st>>>(P);
+        else
+            score_proposals_kernel<false><<<grid, kThreads, 0, st>>>(P);
     }
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, st));
     CUDA_TRY(cudaGetLastError());
     ds->n_launches++;
     if (ds->world > 1 && ds->xchg_on) {
-        // The proposal kernel has stored this rank's chunk sums into every rank's gather buffer and published its flags;
+        // The proposal kernel has stored this rank's chunk sums into every rank's gather buffer and published its flag;
         // wait for the flags of all ranks, then bring the gathered sums of the n proposals to the host.  Every rank adds
         // all chunks in global chunk order, so the total does not depend on the number of GPUs.
         const unsigned long long seq = ds->lane_seq[lane];
-        wait_flags_kernel<<<1, 128, 0, st>>>(ds->xchg_flags(ds->xchg, lane, 0), ds->world, n, seq, ds->lane_status(lane), 60ull * 1000000000ull);
+        wait_flags_kernel<<<1, 32, 0, st>>>(ds->xchg_flags(ds->xchg, lane, 0), ds->world, seq, ds->lane_status(lane), 60ull * 1000000000ull);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
         const size_t width = sizeof(double) * (size_t)n * 2 * ds->max_chunks_rank;
         CUDA_TRY(cudaMemcpy2DAsync(g.h_gather, width, ds->xchg_data(ds->xchg, lane, (int)(seq & 1), 0), sizeof(double) * ds->xchg_block(), width,
                                    (size_t)ds->world, cudaMemcpyDeviceToHost, st));
     } else if (ds->world > 1) {
-        // the same exchange as an NCCL all-gather of the packed chunk sums
-        double* d_send = ds->d_send + (size_t)lane * ds->gather_cap;
+        // the same exchange as an NCCL all-gather of the chunk sums (every rank's slots are zero-padded to the same width)
         double* d_gather = ds->d_gather + (size_t)lane * ds->gather_cap * ds->world;
-        pack_chunks_kernel<<<n, 128, 0, st>>>(ds->d_chunk + (size_t)lane * ds->slots * 2 * ds->n_chunks, ds->n_chunks, d_send, ds->max_chunks_rank);
-        CUDA_TRY(cudaGetLastError());
-        ds->n_launches++;
         const size_t cnt = (size_t)n * 2 * ds->max_chunks_rank;
-        int nrc = g_nccl.AllGather(d_send, d_gather, cnt, kNcclDouble, lane == 0 ? ds->comm : ds->comm_lane1, st);
+        int nrc = g_nccl.AllGather(ds->lane_chunk(lane), d_gather, cnt, kNcclDouble, lane == 0 ? ds->comm : ds->comm_lane1, st);
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
         CUDA_TRY(cudaMemcpyAsync(g.h_gather, d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, st));
     } else
@@ -1129,8 +1083,8 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         // not ordered behind this one)
         g.temp_rows.insert(g.temp_rows.end(), ch->temp_rows.begin(), ch->temp_rows.end());
         ch->temp_rows.clear();
-        ch->builds.clear();
-        ch->build_aux.clear();
+        ch->items.clear();
+        ch->aux.clear();
     }
     g.busy = true;
     g.n = n;
@@ -1188,14 +1142,15 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
     return SCICONE_OK;
 }
 
-int launch_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, double* totals) {
+int launch_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, double* totals, double* ods) {
     unsigned long long tk = 0;
     int rc = submit_proposals(ds, chains, n, &tk);
-    return rc ? rc : wait_proposals(ds, tk, totals, nullptr);
+    return rc ? rc : wait_proposals(ds, tk, totals, ods);
 }
 
 int od_scores(scicone_chain* ch, double nu, double* out) {
     scicone_dataset* ds = ch->ds;
+    if (ch->follower) return fail(SCICONE_ERR_STATE, "a follower chain only stages imported proposals");
     if (ch->compiled && !ch->evaluated) return fail(SCICONE_ERR_STATE, "root scores must be requested before scicone_prepare_t_prime");
     int rc = ds->set_device();
     if (rc) return rc;
@@ -1205,33 +1160,39 @@ int od_scores(scicone_chain* ch, double nu, double* out) {
     std::vector<unsigned char> keep;
     keep.swap(ch->blob);
     const bool keep_with_od = ch->with_od;
-    rc = compile_od_only(ch, nu, 0);
+    const LaunchEntry keep_entry = ch->entry;
+    std::vector<unsigned> keep_temp;
+    keep_temp.swap(ch->temp_rows);
+    rc = compile_od_only(ch, nu);
     double od = 0.0;
     unsigned long long tk = 0;
     if (!rc) rc = submit_proposals(ds, &ch, 1, &tk);
     if (!rc) rc = wait_proposals(ds, tk, nullptr, &od);
+    for (unsigned r : ch->temp_rows) ch->row_put(r);  // only after a failed compile / submit: a submitted launch took them over
+    ch->temp_rows.swap(keep_temp);
     keep.swap(ch->blob);
     ch->with_od = keep_with_od;
+    ch->entry = keep_entry;
     if (rc) return rc;
     if (out) *out = od;
     return SCICONE_OK;
 }
 
-int gather_rows(scicone_dataset* ds, const std::vector<const double*>& rows, double* out) {
+int gather_rows(scicone_dataset* ds, const std::vector<unsigned>& rows, double* out) {
     if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
     const int n = (int)rows.size();
     if (n == 0 || ds->M == 0) return SCICONE_OK;
-    const double** d_rows = nullptr;
+    unsigned* d_rows = nullptr;
     double* d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_rows, sizeof(double*) * n));
+    CUDA_TRY(cudaMalloc(&d_rows, sizeof(unsigned) * n));
     cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)n * ds->M);
     if (e != cudaSuccess) {
         cudaFree(d_rows);
         return fail(SCICONE_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
     }
-    cudaMemcpyAsync(d_rows, rows.data(), sizeof(double*) * n, cudaMemcpyHostToDevice, ds->stream);
+    cudaMemcpyAsync(d_rows, rows.data(), sizeof(unsigned) * n, cudaMemcpyHostToDevice, ds->stream);
     dim3 grid((n + 31) / 32, (ds->M + 31) / 32), block(32, 8);
-    gather_rows_kernel<<<grid, block, 0, ds->stream>>>(d_rows, n, ds->M, d_out);
+    gather_rows_kernel<<<grid, block, 0, ds->stream>>>(ds->pool.base_ptr(), (long long)ds->Mp, d_rows, n, ds->M, d_out);
     cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n * ds->M, cudaMemcpyDeviceToHost, ds->stream);
     e = cudaStreamSynchronize(ds->stream);
     cudaFree(d_rows);
@@ -1241,12 +1202,24 @@ int gather_rows(scicone_dataset* ds, const std::vector<const double*>& rows, dou
 }
 
 template <class T>
-int read_vec(scicone_dataset* ds, const T* dev, T* out, size_t n) {
+int read_row(scicone_dataset* ds, unsigned row, T* out, size_t n) {
+    if (row == kNoRow) return fail(SCICONE_ERR_STATE, "the chain holds no such table on this rank");
     if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
-    CUDA_TRY(cudaMemcpyAsync(out, dev, sizeof(T) * n, cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaMemcpyAsync(out, ds->pool.base_ptr() + (size_t)row * ds->Mp, sizeof(T) * n, cudaMemcpyDeviceToHost, ds->stream));
     CUDA_TRY(cudaStreamSynchronize(ds->stream));
     return SCICONE_OK;
 }
+
+// Wire format of an exported proposal (scicone_export_t_prime): this head, then the blob, the K1 items and their aux
+// block.  Everything in it is rank independent: rows are indices into the row pool, and the rows of a chain come from
+// its owner's partition of the pool.
+struct ExportHead {
+    unsigned magic, blob_bytes, n_items, aux_bytes;
+    unsigned with_od, part, rows_needed, full;
+    double alg_bytes_per_cell, n_scores_per_cell, cost, pad;
+    LaunchEntry entry;
+};
+constexpr unsigned kExportMagic = 0x53433242u;  // "SC2B"
 
 }  // namespace
 
@@ -1284,7 +1257,11 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     }
     ds->n_cta = (ds->M + kCells - 1) / kCells;
     ds->n_chunks = (ds->n_cta + kCtasPerChunk - 1) / kCtasPerChunk;
-    ds->pool.init(ds->Mp, ds->device);
+    ds->cs_stride = ds->n_chunks;
+    // K1 works on blocks of unit_cells cells: as few blocks of at most kUnitMax cells as cover the shard, equally sized
+    ds->n_blocks = (ds->M + kUnitMax - 1) / kUnitMax;
+    ds->unit_cells = (int)round_up((size_t)(ds->M + ds->n_blocks - 1) / ds->n_blocks, kPad);
+    ds->n_blocks = (ds->M + ds->unit_cells - 1) / ds->unit_cells;
     auto cleanup = [&](int rc) {
         scicone_dataset_destroy(ds);
         return rc;
@@ -1296,7 +1273,12 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
             return cleanup(fail(SCICONE_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__)); \
     } while (0)
     DS_TRY(cudaSetDevice(ds->device));
+    DS_TRY(cudaFree(0));  // the primary context exists before the driver API is used
     DS_TRY(cudaDeviceGetAttribute(&ds->n_sm, cudaDevAttrMultiProcessorCount, ds->device));
+    {
+        int rc = ds->pool.init(ds->Mp, ds->device, 1, 0);
+        if (rc) return cleanup(rc);
+    }
     DS_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     ds->lane_stream[0] = ds->stream;
     for (scicone_dataset::Segment& g : ds->seg) {
@@ -1306,11 +1288,17 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
         DS_TRY(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     }
     DS_TRY(cudaMalloc(&ds->dDt, sizeof(double) * ds->Mp * ds->K));
+    DS_TRY(cudaMalloc(&ds->dIt, sizeof(unsigned short) * ds->Mp * ds->K));
     DS_TRY(cudaMalloc(&ds->dS, sizeof(double) * ds->Mp));
+    DS_TRY(cudaMalloc(&ds->dSi, sizeof(unsigned short) * ds->Mp));
     DS_TRY(cudaMalloc(&ds->dW, sizeof(int) * ds->Mp));
+    DS_TRY(cudaMalloc(&ds->d_launch_counter, sizeof(unsigned) * scicone_dataset::kLanes));
+    DS_TRY(cudaMemsetAsync(ds->d_launch_counter, 0, sizeof(unsigned) * scicone_dataset::kLanes, ds->stream));
     DS_TRY(cudaMemsetAsync(ds->dDt, 0, sizeof(double) * ds->Mp * ds->K, ds->stream));
+    DS_TRY(cudaMemsetAsync(ds->dIt, 0, sizeof(unsigned short) * ds->Mp * ds->K, ds->stream));
     DS_TRY(cudaMemsetAsync(ds->dW, 0, sizeof(int) * ds->Mp, ds->stream));
     DS_TRY(cudaMemsetAsync(ds->dS, 0, sizeof(double) * ds->Mp, ds->stream));
+    DS_TRY(cudaMemsetAsync(ds->dSi, 0, sizeof(unsigned short) * ds->Mp, ds->stream));
     {
         double* dD = nullptr;
         DS_TRY(cudaMalloc(&dD, sizeof(double) * (size_t)ds->M * ds->K));
@@ -1318,20 +1306,20 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
         dim3 grid((ds->K + 31) / 32, (ds->M + 31) / 32), block(32, 8);
         transpose_kernel<<<grid, block, 0, ds->stream>>>(dD, ds->dDt, ds->M, ds->K, (long long)ds->Mp);
         row_sum_kernel<<<(ds->M + 127) / 128, 128, 0, ds->stream>>>(ds->dDt, ds->dS, ds->M, ds->K, (long long)ds->Mp);
-        // Count-range table: read counts are integers, and the counts of one region over a block of 2048 cells take a few
-        // hundred distinct values - K1 then evaluates lgamma(count + c) once per possible count instead of once per cell
-        // (identical results: the same function of the same argument).  A (row, block) pair is tabulated when all its
-        // values are non-negative integers and the table is at most half as long as the block; SCICONE_LUT=0 turns it off.
+        // Count-range table: read counts are integers, and the counts of one region over a block of a few thousand cells
+        // take a few hundred distinct values - K1 then evaluates lgamma(count + c) once per possible count instead of once
+        // per cell (identical results: the same function of the same argument).  A (row, block) pair is tabulated when all
+        // its values are non-negative integers and the table is at most half as long as the block; SCICONE_LUT=0 turns it off.
+        const int K = ds->K, M = ds->M;
+        const int bpr = ds->n_blocks;
+        std::vector<int> lut((size_t)(K + 1) * bpr * 2, 0);
         const char* lut_env = getenv("SCICONE_LUT");
         if (!(lut_env && atoi(lut_env) == 0)) {
-            const int K = ds->K, M = ds->M;
-            const int bpr = (M + kUnitCells - 1) / kUnitCells;
-            std::vector<int> lut((size_t)(K + 1) * bpr * 2, 0);
             std::vector<double> lo((size_t)K + 1), hi((size_t)K + 1);
             std::vector<char> integral((size_t)K + 1);
             size_t n_tab = 0;
             for (int b = 0; b < bpr; ++b) {
-                const int j0 = b * kUnitCells, j1 = std::min(M, j0 + kUnitCells);
+                const int j0 = b * ds->unit_cells, j1 = std::min(M, j0 + ds->unit_cells);
                 std::fill(lo.begin(), lo.end(), 1e300);
                 std::fill(hi.begin(), hi.end(), -1e300);
                 std::fill(integral.begin(), integral.end(), 1);
@@ -1356,20 +1344,20 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
                 for (int k = 0; k <= K; ++k) {
                     if (!integral[k]) continue;
                     const double range = hi[k] - lo[k] + 1.0;
-                    if (range > (double)kLutMax || 2.0 * range > (double)(j1 - j0)) continue;
+                    if (range > (double)kLutMax || 2.0 * range > (double)std::max(j1 - j0, 2)) continue;
                     lut[((size_t)k * bpr + b) * 2] = (int)lo[k];
                     lut[((size_t)k * bpr + b) * 2 + 1] = (int)range;
                     ++n_tab;
                 }
             }
             ds->lut_share = (double)n_tab / (double)((size_t)(K + 1) * bpr);
-            if (n_tab) {
-                DS_TRY(cudaMalloc(&ds->d_lut, sizeof(int) * lut.size()));
-                DS_TRY(cudaMemcpy(ds->d_lut, lut.data(), sizeof(int) * lut.size(), cudaMemcpyHostToDevice));
-            }
         }
+        DS_TRY(cudaMalloc(&ds->d_lut, sizeof(int) * lut.size()));
+        DS_TRY(cudaMemcpyAsync(ds->d_lut, lut.data(), sizeof(int) * lut.size(), cudaMemcpyHostToDevice, ds->stream));
+        index_kernel<<<dim3((M + 255) / 256, K + 1), 256, 0, ds->stream>>>(ds->dDt, ds->dS, ds->d_lut, M, K, (long long)ds->Mp, bpr, ds->unit_cells,
+                                                                            ds->dIt, ds->dSi);
         cudaError_t e2 = cudaMemcpyAsync(ds->dW, d->cluster_sizes, sizeof(int) * ds->M, cudaMemcpyHostToDevice, ds->stream);
-        cudaError_t e3 = cudaStreamSynchronize(ds->stream);
+        cudaError_t e3 = cudaStreamSynchronize(ds->stream);  // `lut` and the caller's buffers are read until here
         cudaFree(dD);
         DS_TRY(e1);
         DS_TRY(e2);
@@ -1379,7 +1367,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
 #undef DS_TRY
     int rc = ds->ensure_slots(64);
     if (rc) return cleanup(rc);
-    rc = ds->ensure_arena(size_t(1) << 20);
+    rc = ds->ensure_arena(size_t(4) << 20);
     if (rc) return cleanup(rc);
     *out = ds;
     return SCICONE_OK;
@@ -1399,10 +1387,10 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     if (ds->comm_lane1 && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm_lane1);
     if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm);
     ds->pool.destroy();
-    cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW); cudaFree(ds->d_lut);
+    cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW); cudaFree(ds->d_lut); cudaFree(ds->dIt); cudaFree(ds->dSi);
     for (unsigned char* a : ds->d_arena) cudaFree(a);
     cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
-    cudaFree(ds->d_counter); cudaFree(ds->d_gather); cudaFree(ds->d_send);
+    cudaFree(ds->d_counter); cudaFree(ds->d_gather); cudaFree(ds->d_launch_counter);
     for (scicone_dataset::Segment& g : ds->seg) {
         if (g.h_arena) cudaFreeHost(g.h_arena);
         if (g.h_total) cudaFreeHost(g.h_total);
@@ -1419,45 +1407,72 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     delete ds;
 }
 
-int scicone_chain_create(scicone_chain** out, scicone_dataset* ds) {
+int scicone_dataset_reserve(scicone_dataset* ds, int32_t max_batch, int64_t rows) {
+    if (!ds || max_batch < 0 || rows < 0) return fail(SCICONE_ERR_ARG, "dataset_reserve: bad argument");
+    int rc = ds->set_device();
+    if (rc) return rc;
+    if (max_batch > 0) {
+        if (ds->world > 1) max_batch = std::min<int32_t>(max_batch, SCICONE_MAX_SHARDED_BATCH);
+        rc = ds->ensure_slots(max_batch);
+        if (rc) return rc;
+    }
+    for (int p = 0; p < ds->pool.n_parts && rows > 0; ++p) {
+        rc = ds->pool.ensure_mapped(p, std::min<size_t>((size_t)rows, ds->pool.part_rows));
+        if (rc) return rc;
+    }
+    return SCICONE_OK;
+}
+
+int scicone_max_batch(scicone_dataset* ds, int32_t* n) {
+    if (!ds || !n) return fail(SCICONE_ERR_ARG, "null argument");
+    *n = ds->slots;
+    return SCICONE_OK;
+}
+
+static int chain_create(scicone_chain** out, scicone_dataset* ds, bool follower) {
     if (!out || !ds) return fail(SCICONE_ERR_ARG, "chain_create: null argument");
     *out = nullptr;
     int rc = ds->set_device();
     if (rc) return rc;
     scicone_chain* ch = new scicone_chain();
     ch->ds = ds;
-    for (int i = 0; i < 2; ++i) {
-        cudaError_t e = cudaMalloc(&ch->sums[i], sizeof(double) * ds->Mp);
-        if (e == cudaSuccess) e = cudaMalloc(&ch->maxid[i], sizeof(int) * ds->Mp);
-        if (e == cudaSuccess) e = cudaMemsetAsync(ch->sums[i], 0, sizeof(double) * ds->Mp, ds->stream);
-        if (e == cudaSuccess) e = cudaMemsetAsync(ch->maxid[i], 0, sizeof(int) * ds->Mp, ds->stream);
-        if (e != cudaSuccess) {
-            scicone_chain_destroy(ch);
-            return fail(SCICONE_ERR_CUDA, "chain_create: %s", cudaGetErrorString(e));
+    ch->follower = follower;
+    if (!follower)
+        for (int i = 0; i < 2 && !rc; ++i) {
+            rc = ch->row_get(&ch->sums[i]);
+            if (!rc) rc = ch->row_get(&ch->maxid[i]);
         }
+    if (rc) {
+        scicone_chain_destroy(ch);
+        return rc;
     }
     *out = ch;
     return SCICONE_OK;
 }
+int scicone_chain_create(scicone_chain** out, scicone_dataset* ds) { return chain_create(out, ds, false); }
+int scicone_chain_create_follower(scicone_chain** out, scicone_dataset* ds) { return chain_create(out, ds, true); }
 
 void scicone_chain_destroy(scicone_chain* ch) {
     if (!ch) return;
     scicone_dataset* ds = ch->ds;
     cudaSetDevice(ds->device);
     cudaStreamSynchronize(ds->stream);
-    drop_pending(ch);
-    for (auto& kv : ch->t) ch->row_put(kv.second.row);
-    release_cache(ch, ch->Lt);
-    ds->pool.put_many(ch->stash, 0);
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(ch->sums[i]);
-        cudaFree(ch->maxid[i]);
+    if (ds->lane_stream[1]) cudaStreamSynchronize(ds->lane_stream[1]);
+    if (!ch->follower) {
+        drop_pending(ch);
+        for (auto& kv : ch->t) ch->row_put(kv.second.row);
+        for (int i = 0; i < 2; ++i) {
+            ch->row_put(ch->sums[i]);
+            ch->row_put(ch->maxid[i]);
+        }
+        ds->pool.put_many(ch->stash, 0);
     }
     delete ch;
 }
 
-int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* t_sum) {
+int scicone_prepare_t_table(scicone_chain* ch, const scicone_tree* t, int32_t with_od) {
     if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    if (ch->follower) return fail(SCICONE_ERR_STATE, "a follower chain only stages imported proposals");
     scicone_dataset* ds = ch->ds;
     int rc = validate_tree(t, ds->K);
     if (rc) return rc;
@@ -1466,18 +1481,26 @@ int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* t_
     drop_pending(ch);
     for (auto& kv : ch->t) ch->row_put(kv.second.row);
     ch->t.clear();
-    if (ch->Lt_valid && ch->Lt_nu != t->nu) {
-        release_cache(ch, ch->Lt);
-        ch->Lt_valid = false;
-    }
     ch->tp.assign(t);
     ch->roots.assign(1, 0);
     ch->pending = true;
     ch->p_full = true;
+    rc = compile_proposal(ch, true, with_od != 0);
+    if (rc) {
+        drop_pending(ch);
+        return rc;
+    }
+    ch->compiled = true;
+    return SCICONE_OK;
+}
+
+int scicone_compute_t_table(scicone_chain* ch, const scicone_tree* t, double* t_sum) {
+    int rc = scicone_prepare_t_table(ch, t, 0);
+    if (rc) return rc;
+    scicone_dataset* ds = ch->ds;
     rc = ds->ensure_slots(1);
-    if (!rc) rc = compile_proposal(ch, 0, true);
     double total = 0.0;
-    if (!rc) rc = launch_proposals(ds, &ch, 1, &total);
+    if (!rc) rc = launch_proposals(ds, &ch, 1, &total, nullptr);
     if (rc && rc != SCICONE_ERR_NAN) {
         drop_pending(ch);
         return rc;
@@ -1504,6 +1527,7 @@ int scicone_compute_t_prime_od_scores(scicone_chain* ch, double nu, double* od_s
 
 int scicone_compute_t_prime_scores(scicone_chain* ch, const scicone_tree* t_prime, int32_t node_idx) {
     if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    if (ch->follower) return fail(SCICONE_ERR_STATE, "a follower chain only stages imported proposals");
     if (ch->t.empty()) return fail(SCICONE_ERR_STATE, "compute_t_prime_scores before compute_t_table");
     if (ch->evaluated) return fail(SCICONE_ERR_STATE, "the previous proposal was neither accepted nor rejected");
     if (ch->compiled) return fail(SCICONE_ERR_STATE, "compute_t_prime_scores after scicone_prepare_t_prime");
@@ -1524,12 +1548,77 @@ int scicone_prepare_t_prime(scicone_chain* ch) {
     if (!ch->pending || ch->roots.empty()) return fail(SCICONE_ERR_STATE, "prepare_t_prime without compute_t_prime_scores");
     if (ch->evaluated) return fail(SCICONE_ERR_STATE, "proposal already evaluated");
     if (ch->compiled) return SCICONE_OK;
-    int rc = compile_proposal(ch, 0, false);
+    int rc = compile_proposal(ch, false, false);
     if (rc) {
         drop_pending(ch);
         return rc;
     }
     ch->compiled = true;
+    return SCICONE_OK;
+}
+
+int scicone_export_t_prime(scicone_chain* ch, void* buf, uint64_t capacity, uint64_t* bytes) {
+    if (!ch || !bytes) return fail(SCICONE_ERR_ARG, "export_t_prime: null argument");
+    if (ch->follower) return fail(SCICONE_ERR_STATE, "export_t_prime on a follower chain");
+    if (!ch->compiled || ch->evaluated) return fail(SCICONE_ERR_STATE, "export_t_prime needs a compiled proposal that has not been submitted");
+    const size_t need = sizeof(ExportHead) + ch->blob.size() + ch->items.size() * sizeof(DevItem) + ch->aux.size();
+    *bytes = need;
+    if (!buf || capacity < need) return fail(SCICONE_ERR_ARG, "export_t_prime: the buffer holds %llu bytes, the proposal needs %zu", (unsigned long long)capacity, need);
+    scicone_dataset* ds = ch->ds;
+    ExportHead h;
+    memset(&h, 0, sizeof h);
+    h.magic = kExportMagic;
+    h.blob_bytes = (unsigned)ch->blob.size();
+    h.n_items = (unsigned)ch->items.size();
+    h.aux_bytes = (unsigned)ch->aux.size();
+    h.with_od = ch->with_od ? 1u : 0u;
+    h.part = (unsigned)ds->pool.my_part;
+    h.rows_needed = (unsigned)ds->pool.next_row;
+    h.full = ch->p_full ? 1u : 0u;
+    h.alg_bytes_per_cell = ch->alg_bytes / (double)ds->M;  // the importer scales by its own shard
+    h.n_scores_per_cell = ch->n_scores / (double)ds->M;
+    h.cost = ch->cost;
+    h.entry = ch->entry;
+    unsigned char* o = static_cast<unsigned char*>(buf);
+    memcpy(o, &h, sizeof h);
+    o += sizeof h;
+    memcpy(o, ch->blob.data(), ch->blob.size());
+    o += ch->blob.size();
+    if (!ch->items.empty()) memcpy(o, ch->items.data(), ch->items.size() * sizeof(DevItem));
+    o += ch->items.size() * sizeof(DevItem);
+    if (!ch->aux.empty()) memcpy(o, ch->aux.data(), ch->aux.size());
+    return SCICONE_OK;
+}
+
+int scicone_import_t_prime(scicone_chain* ch, const void* buf, uint64_t bytes) {
+    if (!ch || !buf) return fail(SCICONE_ERR_ARG, "import_t_prime: null argument");
+    if (!ch->follower) return fail(SCICONE_ERR_STATE, "import_t_prime needs a follower chain (scicone_chain_create_follower)");
+    if (ch->compiled && !ch->evaluated) return fail(SCICONE_ERR_STATE, "import_t_prime: the previous proposal was not submitted");
+    if (bytes < sizeof(ExportHead)) return fail(SCICONE_ERR_ARG, "import_t_prime: short message");
+    ExportHead h;
+    memcpy(&h, buf, sizeof h);
+    if (h.magic != kExportMagic || bytes < sizeof h + (size_t)h.blob_bytes + (size_t)h.n_items * sizeof(DevItem) + h.aux_bytes)
+        return fail(SCICONE_ERR_ARG, "import_t_prime: malformed message");
+    scicone_dataset* ds = ch->ds;
+    int rc = ds->pool.ensure_mapped((int)h.part, h.rows_needed);  // the owner may have grown its partition
+    if (rc) return rc;
+    const unsigned char* in = static_cast<const unsigned char*>(buf) + sizeof h;
+    ch->blob.assign(in, in + h.blob_bytes);
+    in += h.blob_bytes;
+    ch->items.resize(h.n_items);
+    if (h.n_items) memcpy(ch->items.data(), in, (size_t)h.n_items * sizeof(DevItem));
+    in += (size_t)h.n_items * sizeof(DevItem);
+    ch->aux.assign(in, in + h.aux_bytes);
+    ch->with_od = h.with_od != 0;
+    ch->p_full = h.full != 0;
+    ch->alg_bytes = h.alg_bytes_per_cell * ds->M;
+    ch->n_scores = h.n_scores_per_cell * ds->M;
+    ch->cost = h.cost;
+    ch->entry = h.entry;
+    ch->roots.assign(1, 0);
+    ch->pending = true;
+    ch->compiled = true;
+    ch->evaluated = false;
     return SCICONE_OK;
 }
 
@@ -1541,7 +1630,7 @@ int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const
         if (!chains[i]->pending || chains[i]->roots.empty())
             return fail(SCICONE_ERR_STATE, "compute_t_prime_sums without compute_t_prime_scores (chain %d)", i);
         if (chains[i]->evaluated) return fail(SCICONE_ERR_STATE, "proposal of chain %d already evaluated", i);
-        if (t_primes && t_primes[i] && t_primes[i]->n_nodes != chains[i]->tp.n)
+        if (t_primes && t_primes[i] && !chains[i]->follower && t_primes[i]->n_nodes != chains[i]->tp.n)
             return fail(SCICONE_ERR_ARG, "batch: t_prime of chain %d differs from the tree given to compute_t_prime_scores", i);
     }
     int rc = ds->set_device();
@@ -1559,7 +1648,7 @@ int scicone_batch_submit(scicone_chain* const* chains, const scicone_tree* const
         scicone::ForkJoinPool::instance().run((int)job.todo.size(), [](int q, void* ctx) {
             Job& j = *static_cast<Job*>(ctx);
             const int i = j.todo[q];
-            j.rc[i] = compile_proposal(j.chains[i], i, false);
+            j.rc[i] = compile_proposal(j.chains[i], false, false);
             if (j.rc[i]) j.msg[i] = g_err;  // thread-local in the worker
         }, &job);
         for (int i = 0; i < n; ++i)
@@ -1616,8 +1705,11 @@ int scicone_compute_t_prime_sums(scicone_chain* ch, const scicone_tree* t_prime,
 int scicone_accept(scicone_chain* ch) {
     if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
     if (!ch->pending || !ch->evaluated) return fail(SCICONE_ERR_STATE, "accept without an evaluated proposal");
-    scicone_dataset* ds = ch->ds;
-    // Inference::update_t_scores, Inference.h:996-1012 - as pointer swaps
+    if (ch->follower) {  // the owner's index swaps are all there is: the next imported proposal names the new rows
+        ch->pending = ch->compiled = ch->evaluated = false;
+        return SCICONE_OK;
+    }
+    // Inference::update_t_scores, Inference.h:996-1012 - as index swaps
     for (auto& kv : ch->p) {
         auto it = ch->t.find(kv.first);
         if (it != ch->t.end()) {
@@ -1637,18 +1729,16 @@ int scicone_accept(scicone_chain* ch) {
     ch->t_nu = ch->tp.nu;
     std::swap(ch->sums[0], ch->sums[1]);    // t_sums = t_prime_sums, Inference.h:867
     std::swap(ch->maxid[0], ch->maxid[1]);  // t_maxs = t_prime_maxs, Inference.h:868
-    if (ds->od && ch->Lp_valid && ch->Lp_nu == ch->tp.nu) {  // the proposal's nu becomes the chain's nu
-        release_cache(ch, ch->Lt);
-        ch->Lt.swap(ch->Lp);
-        ch->Lt_nu = ch->Lp_nu;
-        ch->Lp_valid = false;
-    }
     drop_pending(ch);
     return SCICONE_OK;
 }
 
 int scicone_reject(scicone_chain* ch) {
     if (!ch) return fail(SCICONE_ERR_ARG, "null chain");
+    if (ch->follower) {
+        ch->pending = ch->compiled = ch->evaluated = false;
+        return SCICONE_OK;
+    }
     drop_pending(ch);
     return SCICONE_OK;
 }
@@ -1710,31 +1800,31 @@ int scicone_read_t_scores(scicone_chain* ch, double* out) {
     if (!ch || !out) return fail(SCICONE_ERR_ARG, "null argument");
     int rc = ch->ds->set_device();
     if (rc) return rc;
-    std::vector<const double*> rows;
+    std::vector<unsigned> rows;
     for (auto& kv : ch->t) rows.push_back(kv.second.row);
     return gather_rows(ch->ds, rows, out);
 }
 int scicone_read_t_sums(scicone_chain* ch, double* out) {
     if (!ch || !out) return fail(SCICONE_ERR_ARG, "null argument");
-    return read_vec(ch->ds, ch->sums[0], out, ch->ds->M);
+    return read_row(ch->ds, ch->sums[0], out, ch->ds->M);
 }
 int scicone_read_t_maxs(scicone_chain* ch, int32_t* ids, double* vals) {
     if (!ch || !ids || !vals) return fail(SCICONE_ERR_ARG, "null argument");
     if (!ch->ds->maxs) return fail(SCICONE_ERR_STATE, "t_maxs only exists with max_scoring");
-    int rc = read_vec(ch->ds, ch->maxid[0], ids, ch->ds->M);
-    return rc ? rc : read_vec(ch->ds, ch->sums[0], vals, ch->ds->M);
+    int rc = read_row(ch->ds, ch->maxid[0], ids, ch->ds->M);
+    return rc ? rc : read_row(ch->ds, ch->sums[0], vals, ch->ds->M);
 }
 int scicone_read_t_prime_sums(scicone_chain* ch, double* out) {
     if (!ch || !out) return fail(SCICONE_ERR_ARG, "null argument");
     if (!ch->evaluated) return fail(SCICONE_ERR_STATE, "no evaluated proposal");
-    return read_vec(ch->ds, ch->sums[1], out, ch->ds->M);
+    return read_row(ch->ds, ch->sums[1], out, ch->ds->M);
 }
 int scicone_read_t_prime_maxs(scicone_chain* ch, int32_t* ids, double* vals) {
     if (!ch || !ids || !vals) return fail(SCICONE_ERR_ARG, "null argument");
     if (!ch->evaluated) return fail(SCICONE_ERR_STATE, "no evaluated proposal");
     if (!ch->ds->maxs) return fail(SCICONE_ERR_STATE, "t_prime_maxs only exists with max_scoring");
-    int rc = read_vec(ch->ds, ch->maxid[1], ids, ch->ds->M);
-    return rc ? rc : read_vec(ch->ds, ch->sums[1], vals, ch->ds->M);
+    int rc = read_row(ch->ds, ch->maxid[1], ids, ch->ds->M);
+    return rc ? rc : read_row(ch->ds, ch->sums[1], vals, ch->ds->M);
 }
 int scicone_t_prime_n_rescored(scicone_chain* ch, int32_t* n) {
     if (!ch || !n) return fail(SCICONE_ERR_ARG, "null argument");
@@ -1746,7 +1836,7 @@ int scicone_read_t_prime_scores(scicone_chain* ch, int32_t* ids, double* out) {
     if (!ch->evaluated) return fail(SCICONE_ERR_STATE, "no evaluated proposal");
     int rc = ch->ds->set_device();
     if (rc) return rc;
-    std::vector<const double*> rows;
+    std::vector<unsigned> rows;
     int i = 0;
     for (auto& kv : ch->p) {
         if (ids) ids[i++] = kv.first;
@@ -1765,7 +1855,7 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
     if (rc) return rc;
     if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
     const int n = (int)ch->t.size(), M = ds->M, K = ds->K;
-    std::vector<const double*> rows;
+    std::vector<unsigned> rows;
     std::vector<int> ids;
     std::vector<int> cn((size_t)n * K);
     for (auto& kv : ch->t) {
@@ -1779,19 +1869,19 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
         rows.push_back(kv.second.row);
         ids.push_back(kv.first);
     }
-    const double** d_rows = nullptr;
+    unsigned* d_rows = nullptr;
     int *d_ids = nullptr, *d_cn = nullptr, *d_out_id = nullptr, *d_out_col = nullptr, *d_out_cn = nullptr;
-    cudaError_t e = cudaMalloc(&d_rows, sizeof(double*) * n);
+    cudaError_t e = cudaMalloc(&d_rows, sizeof(unsigned) * n);
     if (e == cudaSuccess) e = cudaMalloc(&d_ids, sizeof(int) * n);
     if (e == cudaSuccess) e = cudaMalloc(&d_cn, sizeof(int) * (size_t)n * K);
     if (e == cudaSuccess) e = cudaMalloc(&d_out_id, sizeof(int) * M);
     if (e == cudaSuccess) e = cudaMalloc(&d_out_col, sizeof(int) * M);
     if (e == cudaSuccess && cell_region_cn) e = cudaMalloc(&d_out_cn, sizeof(int) * (size_t)M * K);
     if (e == cudaSuccess) {
-        cudaMemcpyAsync(d_rows, rows.data(), sizeof(double*) * n, cudaMemcpyHostToDevice, ds->stream);
+        cudaMemcpyAsync(d_rows, rows.data(), sizeof(unsigned) * n, cudaMemcpyHostToDevice, ds->stream);
         cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ds->stream);
         cudaMemcpyAsync(d_cn, cn.data(), sizeof(int) * (size_t)n * K, cudaMemcpyHostToDevice, ds->stream);
-        argmax_kernel<<<(M + 127) / 128, 128, 0, ds->stream>>>(d_rows, d_ids, n, M, d_out_id, d_out_col);
+        argmax_kernel<<<(M + 127) / 128, 128, 0, ds->stream>>>(ds->pool.base_ptr(), (long long)ds->Mp, d_rows, d_ids, n, M, d_out_id, d_out_col);
         cudaMemcpyAsync(cell_node_ids, d_out_id, sizeof(int) * M, cudaMemcpyDeviceToHost, ds->stream);
         if (cell_region_cn) {
             const long long tot = (long long)M * K;
@@ -2035,6 +2125,9 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
     if (!g_nccl.load()) return fail(SCICONE_ERR_COMM, "libnccl.so.2 not found");
     int rc = ds->set_device();
     if (rc) return rc;
+    // one partition of the row pool per rank: the rows of a chain come from its owner's partition on every rank
+    rc = ds->pool.init(ds->Mp, ds->device, world_size, rank);
+    if (rc) return rc;
     NcclApi::UniqueId id;
     memcpy(&id, unique_id, 128);
     int nrc = g_nccl.CommInitRank(&ds->comm, world_size, id, rank);
@@ -2053,8 +2146,9 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
         if (rc) return rc;
         for (double v : all) ds->max_chunks_rank = std::max(ds->max_chunks_rank, (int)v);
     }
+    ds->cs_stride = ds->max_chunks_rank;
     const int keep = ds->slots;
-    ds->slots = 0;  // force reallocation with the gather buffers
+    ds->slots = 0;  // force reallocation with the gather buffers and the common chunk width
     rc = ds->ensure_slots(std::max(keep, 4));
     if (rc) return rc;
     const char* how = getenv("SCICONE_EXCHANGE");
@@ -2139,7 +2233,7 @@ int scicone_region_elapsed_ms(scicone_dataset* ds, double* ms) {
 }
 int scicone_device_bytes(scicone_dataset* ds, uint64_t* bytes) {
     if (!ds || !bytes) return fail(SCICONE_ERR_ARG, "null argument");
-    *bytes = (uint64_t)(ds->pool.n_rows - ds->pool.free_rows.size()) * ds->Mp * sizeof(double) + (uint64_t)ds->Mp * ds->K * sizeof(double);
+    *bytes = (uint64_t)ds->pool.in_use * ds->Mp * sizeof(double) + (uint64_t)ds->Mp * ds->K * (sizeof(double) + sizeof(unsigned short));
     return SCICONE_OK;
 }
 int scicone_kernel_launches(scicone_dataset* ds, uint64_t* n) {

@@ -214,6 +214,8 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
             hi = std::min<long>(c1 * chunk, n_cells);
             if (hi <= lo) throw std::runtime_error("this rank has no cells: use fewer GPUs");
         }
+        if (static_cast<int>(cluster_sizes.size()) != n_cells) throw std::runtime_error("the cluster sizes file does not have n_cells lines");
+        if (static_cast<int>(neutral.size()) != n_regions) throw std::runtime_error("the region neutral states file does not have n_regions lines");
         std::vector<int32_t> r32(region_sizes.begin(), region_sizes.end()), n32(neutral.begin(), neutral.end()),
             w32(cluster_sizes.begin() + lo, cluster_sizes.begin() + hi);
         scicone_dataset_desc desc;
@@ -239,16 +241,42 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
         const bool stats = a.has("stats_file");
         if (stats) scicone_set_profiling(ds, 1);
 
+        // cell-sharded run: every chain's tree search runs on ONE rank (chain c -> rank c mod world), which compiles each
+        // proposal once and ships the compiled bytes through a shared-memory mailbox (mcmc.hpp); the other ranks hold a
+        // follower handle of the chain and only stage those bytes.  --shm_name names the segment; by default it is derived
+        // from the NCCL id of the run.  --replicated_host: every rank runs every chain's search itself (no mailbox).
+        std::unique_ptr<Mailbox> mailbox;
+        if (world > 1 && !a.has("replicated_host")) {
+            std::string shm = a.str("shm_name");
+            if (shm.empty() && a.has("nccl_id")) shm = "/scicone_" + a.str("nccl_id").substr(0, 24);
+            if (shm.empty()) throw std::runtime_error("--shm_name is needed for a multi-process run without --nccl_id");
+            if (shm[0] != '/') shm = "/" + shm;
+            mailbox.reset(new Mailbox());
+            mailbox->open(shm, n_chains, rank, world);
+        }
+        if (world > 1 && !mailbox && seed == -1)
+            throw std::runtime_error("--replicated_host needs --seed: every rank must draw the same chains");
+        auto owner_of = [&](int c) { return mailbox ? c % world : rank; };
+        {   // the row pool and the reduction scratch are sized before the first launch, not inside the timed loop
+            const int per_rank = (n_chains + world - 1) / world;
+            const long rows_per_chain = 3L * (n_nodes + 24) + 48;
+            abi_check(scicone_dataset_reserve(ds, world > 1 ? std::min(n_chains, SCICONE_MAX_SHARDED_BATCH) : n_chains,
+                                              static_cast<int64_t>(mailbox || world == 1 ? per_rank : n_chains) * rows_per_chain));
+        }
+
         std::vector<std::unique_ptr<Inference>> owned;
         std::vector<Inference*> chains;
         for (int c = 0; c < n_chains; ++c) {
             Params Pc = P;
             if (n_chains > 1) Pc.postfix = P.postfix + "_c" + std::to_string(c);
+            const bool mine = owner_of(c) == rank;
             owned.emplace_back(new Inference(Pc, seed == -1 ? -1 : seed + c, static_cast<unsigned>(n_regions), n_cells, neutral, ploidy, max_scoring));
             Inference* inf = owned.back().get();
-            inf->attach_chain(ds);
+            inf->attach_chain(ds, !mine);
             inf->gamma = gamma;
             inf->alpha = alpha;
+            chains.push_back(inf);
+            if (!mine) continue;  // the owner draws the start tree; a follower never sees a tree
             if (random_init) {
                 if (P.verbosity > 0 && c == 0) std::cout << "Trying to randomly initialise a valid tree with " << 10000 << " iterations." << std::endl;
                 try {
@@ -262,26 +290,51 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
                 inf->initialize_from_file(a.str("tree_file"));
                 nu = inf->t.nu;
             }
-            if (a.has("nu") && !a.has("tree_file")) inf->t.nu = inf->t_prime.nu = nu;
-            else if (a.has("nu") && a.has("tree_file")) inf->t.nu = inf->t_prime.nu = nu;  // nu == the file's value (infer_trees.cpp:247)
-            inf->compute_t_table();
-            inf->compute_t_od_scores();
-            inf->update_t_prime();
-            chains.push_back(inf);
+            if (a.has("nu")) inf->t.nu = inf->t_prime.nu = nu;  // with --tree_file, nu == the file's value (infer_trees.cpp:247)
+            if (!mailbox) {
+                inf->compute_t_table();
+                inf->compute_t_od_scores();
+                inf->update_t_prime();
+            }
+        }
+        if (mailbox) {
+            // Full passes of the start trees (Inference::compute_t_table + compute_t_od_scores, infer_trees.cpp:285-286) as
+            // launches of all ranks: the owner compiles and publishes, everybody stages and launches, the owner commits.
+            int32_t max_batch = 0;
+            abi_check(scicone_max_batch(ds, &max_batch));
+            max_batch = std::min<int32_t>(max_batch, SCICONE_MAX_SHARDED_BATCH);
+            for (int c0 = 0; c0 < n_chains; c0 += max_batch) {
+                const int c1 = std::min(n_chains, c0 + max_batch);
+                std::vector<scicone_chain*> handles;
+                for (int c = c0; c < c1; ++c) {
+                    Inference* inf = chains[c];
+                    if (owner_of(c) == rank) {
+                        inf->prepare_t_table();
+                        inf->last_decision = -1;
+                        pack_message(*inf, true, inf->msg_buf);
+                        mailbox->publish(c, ++inf->msg_seq, inf->msg_buf, rank, world);
+                    } else {
+                        uint32_t bytes = 0;
+                        const unsigned char* msg = mailbox->receive(c, ++inf->msg_seq, &bytes);
+                        apply_message(*inf, msg, bytes);
+                        mailbox->acknowledge(c, inf->msg_seq, rank);
+                    }
+                    handles.push_back(inf->chain);
+                }
+                std::vector<double> sums(handles.size()), ods(handles.size());
+                abi_check(scicone_batch_compute_t_prime_sums(handles.data(), nullptr, static_cast<int32_t>(handles.size()), sums.data(), ods.data()));
+                for (int c = c0; c < c1; ++c) {
+                    Inference* inf = chains[c];
+                    if (owner_of(c) == rank) {
+                        inf->finish_t_table(sums[c - c0], ods[c - c0]);
+                        inf->update_t_prime();
+                    } else
+                        abi_check(scicone_accept(inf->chain));
+                }
+            }
         }
 
         if (P.verbosity > 0) std::cout << "Inferring the tree using MCMC with " << n_iters << " iterations..." << std::endl;
-        // cell-sharded run: every chain's tree search runs on one rank, the others follow it through a shared-memory
-        // mailbox (mcmc.hpp).  --shm_name names the segment; by default it is derived from the NCCL id of the run.
-        std::unique_ptr<Mailbox> mailbox;
-        if (world > 1 && !a.has("replicated_host")) {
-            std::string shm = a.str("shm_name");
-            if (shm.empty() && a.has("nccl_id")) shm = "/scicone_" + a.str("nccl_id").substr(0, 24);
-            if (shm.empty()) throw std::runtime_error("--shm_name is needed for a multi-process run without --nccl_id");
-            if (shm[0] != '/') shm = "/" + shm;
-            mailbox.reset(new Mailbox());
-            mailbox->open(shm, n_chains, rank == 0);
-        }
         HostPhaseTimes phase;
         // schedule: "dynamic" (default for several chains on one GPU) launches whatever is ready - in a cell-sharded run
         // rank 0 composes the launches and the other ranks replay its launch log; "static" moves groups of chains in lock-step
@@ -454,6 +507,8 @@ extern "C" int scicone_score_main(int argc, char** argv) {
             std::cout << "Assuming root to have copy number state " << ploidy << " in all regions" << std::endl;
             neutral.assign(n_regions, ploidy);
         }
+        if (static_cast<int>(cluster_sizes.size()) != n_cells) throw std::runtime_error("the cluster sizes file does not have n_cells lines");
+        if (static_cast<int>(neutral.size()) != n_regions) throw std::runtime_error("the region neutral states file does not have n_regions lines");
         std::vector<int32_t> r32(region_sizes.begin(), region_sizes.end()), n32(neutral.begin(), neutral.end()), w32(cluster_sizes.begin(), cluster_sizes.end());
         scicone_dataset_desc desc;
         desc.n_cells = n_cells;

@@ -119,10 +119,14 @@ public:
     ~Inference() {
         if (chain) scicone_chain_destroy(chain);
     }
-    void attach_chain(scicone_dataset* dataset) {
+    // follower: a cell-sharded run in which another rank owns this chain - the handle only stages the owner's compiled
+    // proposals (scicone_import_t_prime); no tree search runs here
+    void attach_chain(scicone_dataset* dataset, bool follower = false) {
         ds = dataset;
-        abi_check(scicone_chain_create(&chain, ds));
+        is_follower = follower;
+        abi_check(follower ? scicone_chain_create_follower(&chain, ds) : scicone_chain_create(&chain, ds));
     }
+    bool is_follower = false;
 
     // ---- initial tree (Inference::random_initialize, Inference.h:99-156) ------------------------------------------
     void random_initialize(unsigned n_nodes, int max_iters, int max_regions_per_node = 1) {
@@ -183,6 +187,20 @@ public:
         t.total_attachment_score = sum;
         t.prior_score = log_tree_prior(n_cells, static_cast<int>(t.n_nodes));
         t.posterior_score = log_tree_posterior(sum, n_cells, t);
+    }
+    // The same full pass in two halves, for cell-sharded runs: the owner compiles it (with the root score of
+    // compute_t_od_scores in the same launch), every rank launches it, the owner commits the result.
+    void prepare_t_table() {
+        flat.build(t);
+        abi_check(scicone_prepare_t_table(chain, &flat.pod, 1));
+    }
+    void finish_t_table(double sum, double od) {
+        abi_check(scicone_accept(chain));
+        t_total = sum;
+        t.total_attachment_score = sum;
+        t.prior_score = log_tree_prior(n_cells, static_cast<int>(t.n_nodes));
+        t.posterior_score = log_tree_posterior(sum, n_cells, t);
+        t.od_score = od;
     }
     void compute_t_od_scores() {  // Inference::compute_t_od_scores, Inference.h:1406-1419
         double od = 0.0;
@@ -467,6 +485,7 @@ public:
     int last_decision = -1;             // outcome of the last scored proposal: 1 accepted, 0 rejected, -1 nothing was scored
     uint64_t msg_seq = 0;               // cell-sharded runs: messages published (owner) / consumed (follower) for this chain
     std::vector<unsigned char> msg_buf;
+    size_t export_cap = 0;              // bytes the last exported proposal needed (sizes the next message buffer)
 
     void open_traces(int n_iters) {  // Inference.h:532-538
         n_iters_total = n_iters;
@@ -517,28 +536,80 @@ public:
         int32_t pad;
         // int32_t members[n_chains] follow
     };
-    void open(const std::string& name, int n_chains, bool unlink_at_exit) {
+    // Rank 0 creates the segment (replacing a stale one that a crashed run may have left under the same name) and zeroes
+    // it; every other rank maps it, says hello with its pid and waits for rank 0's echo - a rank that mapped a stale
+    // segment gets no echo, notices that the name now leads to another segment, and maps that one.
+    struct Hello {
+        std::atomic<uint64_t> said[kMaxRanks], echoed[kMaxRanks];
+    };
+    void open(const std::string& name, int n_chains, int rank, int world) {
+        if (world > kMaxRanks) throw std::runtime_error("mailbox: too many ranks");
         name_ = name;
-        owner_ = unlink_at_exit;
+        owner_ = rank == 0;
         n_chains_ = n_chains;
         rec_bytes_ = (sizeof(LogRec) + 4 * static_cast<size_t>(n_chains) + 63) / 64 * 64;
         const size_t slot_bytes = sizeof(Slot) * static_cast<size_t>(n_chains);
-        map_bytes_ = slot_bytes + sizeof(LogHead) + rec_bytes_ * kLogRing;
-        int fd = shm_open(name.c_str(), O_CREAT | O_RDWR, 0600);
-        if (fd < 0) throw std::runtime_error("shm_open(" + name + ") failed");
-        if (ftruncate(fd, static_cast<off_t>(map_bytes_)) != 0) {
+        map_bytes_ = slot_bytes + sizeof(LogHead) + rec_bytes_ * kLogRing + sizeof(Hello);
+        const uint64_t me = static_cast<uint64_t>(getpid());
+        const auto t0 = std::chrono::steady_clock::now();
+        auto expired = [&] { return std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120); };
+        auto map_fd = [&](int fd) {
+            base_ = mmap(nullptr, map_bytes_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+            if (base_ == MAP_FAILED) {
+                base_ = nullptr;
+                close(fd);
+                throw std::runtime_error("mmap of the mailbox failed");
+            }
+            slots_ = static_cast<Slot*>(base_);
+            log_head_ = reinterpret_cast<LogHead*>(static_cast<unsigned char*>(base_) + slot_bytes);
+            log_recs_ = static_cast<unsigned char*>(base_) + slot_bytes + sizeof(LogHead);
+            hello_ = reinterpret_cast<Hello*>(log_recs_ + rec_bytes_ * kLogRing);
+        };
+        if (rank == 0) {
+            shm_unlink(name.c_str());
+            int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+            if (fd < 0) throw std::runtime_error("shm_open(" + name + ") failed");
+            if (ftruncate(fd, static_cast<off_t>(map_bytes_)) != 0) {  // a fresh segment is zero filled: every seq / ack / hello is 0
+                close(fd);
+                throw std::runtime_error("ftruncate on the mailbox failed");
+            }
+            map_fd(fd);
             close(fd);
-            throw std::runtime_error("ftruncate on the mailbox failed");
+            for (int r = 1; r < world; ++r) {
+                uint64_t who = 0;
+                while ((who = hello_->said[r].load(std::memory_order_acquire)) == 0) {
+                    if (expired()) throw std::runtime_error("mailbox: rank " + std::to_string(r) + " did not arrive");
+                    std::this_thread::sleep_for(std::chrono::microseconds(200));
+                }
+                hello_->echoed[r].store(who, std::memory_order_release);
+            }
+            return;
         }
-        base_ = mmap(nullptr, map_bytes_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-        close(fd);
-        if (base_ == MAP_FAILED) {
+        for (;;) {
+            if (expired()) throw std::runtime_error("mailbox: rank 0 did not create " + name);
+            int fd = shm_open(name.c_str(), O_RDWR, 0600);
+            struct stat st_mine;
+            if (fd < 0 || fstat(fd, &st_mine) != 0 || static_cast<size_t>(st_mine.st_size) < map_bytes_) {
+                if (fd >= 0) close(fd);
+                std::this_thread::sleep_for(std::chrono::microseconds(500));
+                continue;
+            }
+            map_fd(fd);
+            close(fd);
+            hello_->said[rank].store(me, std::memory_order_release);
+            bool stale = false;
+            while (hello_->echoed[rank].load(std::memory_order_acquire) != me && !stale) {
+                if (expired()) throw std::runtime_error("mailbox: no answer from rank 0");
+                std::this_thread::sleep_for(std::chrono::microseconds(500));
+                int fd2 = shm_open(name.c_str(), O_RDWR, 0600);  // does the name still lead to the segment that is mapped here?
+                struct stat st_now;
+                stale = fd2 < 0 || fstat(fd2, &st_now) != 0 || st_now.st_ino != st_mine.st_ino;
+                if (fd2 >= 0) close(fd2);
+            }
+            if (!stale) return;
+            munmap(base_, map_bytes_);
             base_ = nullptr;
-            throw std::runtime_error("mmap of the mailbox failed");
         }
-        slots_ = static_cast<Slot*>(base_);  // a fresh segment is zero filled: seq = 0
-        log_head_ = reinterpret_cast<LogHead*>(static_cast<unsigned char*>(base_) + slot_bytes);
-        log_recs_ = static_cast<unsigned char*>(base_) + slot_bytes + sizeof(LogHead);
     }
     LogRec* log_rec(uint64_t k) const { return reinterpret_cast<LogRec*>(log_recs_ + rec_bytes_ * (k % kLogRing)); }
     // rank 0: members of the next launch; returns its index
@@ -620,86 +691,47 @@ private:
     int n_chains_ = 0;
     Slot* slots_ = nullptr;
     LogHead* log_head_ = nullptr;
+    Hello* hello_ = nullptr;
     unsigned char* log_recs_ = nullptr;
     uint64_t next_launch_ = 0;  // launches published (rank 0) / submitted (other ranks) so far
 };
 
-// message = {u8 has_decision, u8 accept, u8 scored, u8 pad, i32 n_roots, [tree, roots]}
-inline void pack_message(const Inference& c, bool scored, std::vector<unsigned char>& out) {
-    auto put = [&](const void* p, size_t n) {
-        const unsigned char* b = static_cast<const unsigned char*>(p);
-        out.insert(out.end(), b, b + n);
-    };
-    out.clear();
-    const unsigned char head[4] = {static_cast<unsigned char>(c.last_decision >= 0), static_cast<unsigned char>(c.last_decision == 1),
-                                   static_cast<unsigned char>(scored), 0};
-    put(head, 4);
-    const int32_t n_roots = scored ? static_cast<int32_t>(c.queued_roots.size()) : 0;
-    put(&n_roots, 4);
-    if (!scored) return;
-    const scicone_tree& t = c.flat.pod;
-    const int32_t n = t.n_nodes, n_chg = t.chg_off[n], n_gen = t.gen_off[n];
-    const int32_t dims[4] = {n, n_chg, n_gen, 0};
-    put(dims, 16);
-    put(&t.nu, 8);
-    put(t.node_id, 4 * n);
-    put(t.parent, 4 * n);
-    put(t.chg_off, 4 * (n + 1));
-    put(t.gen_off, 4 * (n + 1));
-    put(t.chg_region, 4 * n_chg);
-    put(t.chg_value, 4 * n_chg);
-    put(t.gen_region, 4 * n_gen);
-    put(t.gen_value, 4 * n_gen);
-    put(c.queued_roots.data(), 4 * n_roots);
+// message = {u8 has_decision, u8 accept, u8 scored, u8 pad, u32 payload bytes, payload}.  The payload is the owner's COMPILED
+// proposal (scicone_export_t_prime): it names device rows by index only and is valid on every rank, so a follower neither
+// sees the tree nor repeats any of the owner's work - it stages the bytes for the next launch.
+inline void pack_message(Inference& c, bool scored, std::vector<unsigned char>& out) {
+    uint64_t need = 0;
+    if (scored) {
+        size_t cap = std::max<size_t>(c.export_cap, 8192);
+        out.resize(8 + cap);
+        int rc = scicone_export_t_prime(c.chain, out.data() + 8, cap, &need);
+        if (rc != SCICONE_OK && need > cap) {
+            cap = static_cast<size_t>(need) * 2;
+            out.resize(8 + cap);
+            rc = scicone_export_t_prime(c.chain, out.data() + 8, cap, &need);
+        }
+        abi_check(rc);
+        c.export_cap = cap;
+    }
+    out.resize(8 + static_cast<size_t>(need));
+    out[0] = static_cast<unsigned char>(c.last_decision >= 0);
+    out[1] = static_cast<unsigned char>(c.last_decision == 1);
+    out[2] = static_cast<unsigned char>(scored);
+    out[3] = 0;
+    const uint32_t n32 = static_cast<uint32_t>(need);
+    std::memcpy(out.data() + 4, &n32, 4);
 }
 
-// follower side: settle the previous proposal of the chain, queue and compile the next one; returns its `scored` flag
+// follower side: settle the previous proposal of the chain, stage the next one; returns its `scored` flag
 inline bool apply_message(Inference& c, const unsigned char* p, uint32_t bytes) {
     if (bytes < 8) throw std::runtime_error("short mailbox message");
     const bool has_decision = p[0] != 0, accept = p[1] != 0, scored = p[2] != 0;
-    int32_t n_roots;
-    std::memcpy(&n_roots, p + 4, 4);
+    uint32_t n32;
+    std::memcpy(&n32, p + 4, 4);
     if (has_decision) abi_check(accept ? scicone_accept(c.chain) : scicone_reject(c.chain));
     if (!scored) return false;
-    const unsigned char* q = p + 8;
-    int32_t dims[4];
-    std::memcpy(dims, q, 16);
-    q += 16;
-    const int32_t n = dims[0], n_chg = dims[1], n_gen = dims[2];
-    // the arrays are copied out: the payload is only 4-byte aligned and lives in shared memory
-    FlatTree& f = c.flat;
-    double nu;
-    std::memcpy(&nu, q, 8);
-    q += 8;
-    auto take = [&](std::vector<int32_t>& v, size_t count) {
-        v.resize(count + 1);
-        std::memcpy(v.data(), q, 4 * count);
-        q += 4 * count;
-    };
-    take(f.id, n);
-    take(f.parent, n);
-    take(f.chg_off, n + 1);
-    take(f.gen_off, n + 1);
-    take(f.chg_region, n_chg);
-    take(f.chg_value, n_chg);
-    take(f.gen_region, n_gen);
-    take(f.gen_value, n_gen);
-    f.pod.n_nodes = n;
-    f.pod.node_id = f.id.data();
-    f.pod.parent = f.parent.data();
-    f.pod.chg_off = f.chg_off.data();
-    f.pod.chg_region = f.chg_region.data();
-    f.pod.chg_value = f.chg_value.data();
-    f.pod.gen_off = f.gen_off.data();
-    f.pod.gen_region = f.gen_region.data();
-    f.pod.gen_value = f.gen_value.data();
-    f.pod.nu = nu;
-    for (int32_t r = 0; r < n_roots; ++r) {
-        int32_t idx;
-        std::memcpy(&idx, q + 4 * r, 4);
-        abi_check(scicone_compute_t_prime_scores(c.chain, &f.pod, idx));
-    }
-    abi_check(scicone_prepare_t_prime(c.chain));
+    if (bytes < 8 + n32) throw std::runtime_error("truncated mailbox message");
+    abi_check(scicone_import_t_prime(c.chain, p + 8, n32));
     return true;
 }
 
@@ -749,6 +781,7 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
     if (world > 1 && (B + G - 1) / G > SCICONE_MAX_SHARDED_BATCH)
         throw std::runtime_error("static schedule: more than " + std::to_string(SCICONE_MAX_SHARDED_BATCH) +
                                  " chains per group on a cell-sharded dataset - use the dynamic schedule or fewer chains per process");
+    abi_check(scicone_dataset_reserve(ds, (B + G - 1) / G, 0));  // the reduction scratch cannot grow while a launch is outstanding
     parallel_chains(B, [&](int b) {
         chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
         if (mailbox == nullptr || b % world == rank) chains[b]->open_traces(n_iters);  // a follower writes no traces
@@ -877,6 +910,11 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     // two launch streams: K1 of one launch overlaps the proposal kernel of the other (a launch is always collected here
     // before its chains are settled, which is what the second stream requires)
     if (n_streams > 1) abi_check(scicone_set_streams(ds, 2));
+    // the reduction scratch is sized once, before the first launch: a launch never has more proposals than it has slots
+    abi_check(scicone_dataset_reserve(ds, world > 1 ? std::min(B, SCICONE_MAX_SHARDED_BATCH) : B, 0));
+    int32_t max_batch = 0;
+    abi_check(scicone_max_batch(ds, &max_batch));
+    if (world > 1 && max_batch > SCICONE_MAX_SHARDED_BATCH) max_batch = SCICONE_MAX_SHARDED_BATCH;
     auto owned = [&](int b) { return mailbox == nullptr || b % world == rank; };
     parallel_chains(B, [&](int b) {
         chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
@@ -1070,9 +1108,9 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
                     if (!ready.empty() && flights.size() < 2 && (static_cast<int>(ready.size()) >= min_batch || nothing_coming || (n_host == 0 && flights.size() < 2)))
                     {
                         take.swap(ready);
-                        if (world > 1 && take.size() > SCICONE_MAX_SHARDED_BATCH) {  // the rest waits for the next launch
-                            ready.assign(take.begin() + SCICONE_MAX_SHARDED_BATCH, take.end());
-                            take.resize(SCICONE_MAX_SHARDED_BATCH);
+                        if (static_cast<int>(take.size()) > max_batch) {  // the rest waits for the next launch
+                            ready.assign(take.begin() + max_batch, take.end());
+                            take.resize(static_cast<size_t>(max_batch));
                         }
                     }
                 }

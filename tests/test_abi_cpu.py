@@ -24,7 +24,7 @@ def test_header_symbols_are_exported():
     assert declared == set(api.ABI_SYMBOLS), declared ^ set(api.ABI_SYMBOLS)
     for name in sorted(declared):
         assert hasattr(L, name), name
-    assert L.scicone_abi_version() == 1
+    assert L.scicone_abi_version() == 2
 
 
 def test_no_cpu_fallback():
