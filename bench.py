@@ -183,6 +183,7 @@ def run_engine(args):
     # identical proposal streams on every rank (the tree is replicated, only cells are sharded)
     ref_data = make_counts(64, args.bins, args.regions, seed=SEED)  # only region count / neutral states matter here
     traces = build_chain_traces(ref_data, B, args.nodes, 2 * (W + K), SEED, args.nu)
+    ds.reserve(B, B * (3 * (args.nodes + 24) + 48))  # reduction scratch and row pool are sized before the first launch
     chains = [Chain(dataset=ds) for _ in range(B)]
     for ch, (start, _) in zip(chains, traces):
         ch.compute_t_table(start)

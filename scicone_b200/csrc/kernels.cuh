@@ -3,26 +3,27 @@
 //
 // Layout in HBM (cells are the fastest-varying dimension everywhere, so a warp touches one contiguous segment per row):
 //   Dt   [K][Mp] f64   region-major copy of the count matrix D
-//   It   [K][Mp] u16   D[j][k] - min(k, block of j) where the counts of region k over that block of cells are integers
-//                      in a narrow range (read counts are): the index into the per-event value tables of K1
+//   It   [K][Mp] u16   D[j][k] - min_k where the counts of region k over the shard's cells are integers in a narrow
+//                      range (read counts are): the index into the per-event value tables of K1
 //   S    [Mp]    f64   per-cell read total sum_k D[j][k] (k ascending, as std::accumulate);  Si [Mp] u16 the same as index
 //   w    [Mp]    i32   cluster sizes (0 in the padding)
-//   lut  [K+1][blocks][2] i32  {min, range} of every row of counts (regions, then S) per block of `unit_cells` cells
+//   lut  [K+1][2] i32  {min, range} of every row of counts (regions, then S) over the shard's cells
 //                      (range 0: not tabulated - non-integer counts, or spread too widely for a table to pay)
+//   tables (per launch lane) f64  the value tables K1a builds for the launch's events / z-terms / root-score regions
 //   row pool  [rows][Mp] f64   ONE contiguous virtual range per rank, addressed by 32-bit row indices: score rows
 //                      (one per tree node and chain), per-cell aggregates and argmax ids, root-score slices.  Proposals
 //                      refer to rows by index only, so a compiled proposal is valid on every rank of a cell-sharded run.
 //   gather buffer (multi-GPU)  flags + per-rank chunk sums, mapped into every rank, written over NVLink by the last
 //                      CTA of a launch (finish_reduction), read by wait_flags_kernel + one copy to the host
 //
-// Two kernels per batch of proposals:
-//   build_increments_kernel (K1)  for every rescored (cell, node): score(node) - score(parent), i.e. all of
-//                           Tree::compute_score (reference scicone/src/Tree.h:163-244) but the final addition - every pair
-//                           is independent of every other, so this part is embarrassingly parallel.  The data terms
-//                           lgamma(D + a_node) - lgamma(D + a_parent) of an event are looked up in a table over the
-//                           possible counts that the CTA builds in shared memory (a few hundred lgamma instead of one
-//                           per cell); also the region slices of the root score of proposals that change nu
-//                           (Tree::get_od_root_score, Tree.h:1774-1810).  Persistent CTAs over (item, cell block) units.
+// Three kernels per batch of proposals:
+//   build_tables_kernel (K1a) + build_increments_kernel (K1b)  for every rescored (cell, node): score(node) -
+//                           score(parent), i.e. all of Tree::compute_score (reference scicone/src/Tree.h:163-244) but the
+//                           final addition - every pair is independent of every other, so this part is embarrassingly
+//                           parallel.  The data terms lgamma(D + a_node) - lgamma(D + a_parent) of an event are looked
+//                           up in a table over the possible counts (a few hundred lgamma instead of one per cell); also
+//                           the region slices of the root score of proposals that change nu
+//                           (Tree::get_od_root_score, Tree.h:1774-1810).
 //   score_proposals_kernel  (K2-K4) per proposal (grid.y) and per 128-cell tile (grid.x), one thread per cell: walks the
 //                           rescored nodes parent-before-child (Tree::compute_stack, Tree.h:260-286), score = parent
 //                           score + increment (the increments of the next eight nodes are in flight in registers),
@@ -48,11 +49,7 @@ constexpr int kMaxOdSlices = 32;    // region slices of a root score
 constexpr int kCtasPerChunk = 8;    // 8 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
 constexpr int kBuildBlock = 256;    // threads per CTA of the build kernel
 constexpr int kBuildCells = 4;      // cells per thread and step of the build kernel
-constexpr int kUnitMax = 4096;      // cells per (item, block) unit of the build kernel at most
-constexpr int kLutMax = 2048;       // largest range of counts that is tabulated (host side: the dataset's count-range table)
-constexpr int kLutCap = 4096;       // entries of the shared-memory value table of a CTA
-constexpr int kLutGroup = 16;       // events of a node / regions of a slice whose tables are resident together
-static_assert(kLutMax <= kLutCap / 2, "one region's table and the z-term tables must fit together");
+constexpr int kLutMax = 4096;       // largest range of counts that is tabulated (host side: the dataset's count-range table)
 constexpr int kPad = 256;           // row padding (cells)
 constexpr unsigned kNoRow = 0xffffffffu;
 
@@ -85,8 +82,9 @@ struct LaunchParams {
     const double* S;
     const unsigned short* Si;
     const int* w;
-    const int* lut;
-    int n_cells, n_blocks, unit_cells, n_regions;
+    const int* lut;   // [K + 1][2]
+    double* tables;   // table arena of this launch's lane
+    int n_cells, n_regions;
     // reduction scratch of the launch's lane, indexed by slot (position of the proposal in the caller's list)
     double* partial;     // [slots][2][n_cta]   (0: tree score, 1: root score)
     double* chunk_sums;  // [slots][2][cs_stride]
@@ -147,7 +145,8 @@ struct alignas(16) DevEvent {
     double argN, argP;  // OD: (nu*cn)*r of node / parent
     double a, b;        // OD: lgamma(argN), lgamma(argP);  non-OD: a = log(cn_node) - log(cn_parent)
     int k;              // region
-    int pad[3];
+    unsigned tab;       // rank-local, filled at submit: first entry of the event's table in the launch's table arena (kNoRow: none)
+    int pad[2];
 };
 static_assert(sizeof(DevEvent) == 48, "");
 
@@ -159,7 +158,8 @@ struct alignas(16) DevItem {
     double nz, nzp;        // NODE_OD: nu*z, nu*z_parent;  G_ROW: nz = c
     double lg_nz, lg_nzp;  // NODE_OD: lgamma(nz), lgamma(nzp);  NODE_MN: log(z), log(z_parent)
     int k0, k1;            // SLICE: region range
-    unsigned pad[2];
+    unsigned g_tab;        // rank-local, filled at submit: NODE_OD: the two z-term tables;  G_ROW: its table (kNoRow: none)
+    unsigned pad;
 };
 static_assert(sizeof(DevItem) == 64, "");
 
@@ -296,331 +296,241 @@ __global__ void wait_flags_kernel(const unsigned long long* flags, int world, un
 }
 
 // ---------------------------------------------------------------------------------
-// K1: every lgamma of the path.  Persistent grid (up to 4 CTAs per SM) over n_items x n_blocks units; a unit is one item
-// (the increment of one rescored node, a slice of a root score, a cell-level root term) on one block of unit_cells cells.
+// K1: every lgamma of the path, in two kernels without a barrier between threads that do different work.
 //
-// Read counts are integers, and the counts of one region over a block of a few thousand cells take a few hundred
-// distinct values: the dataset's count-range table `lut` says, for every row of counts (regions 0..K-1, then the row
-// sums S) and every block, {smallest count, number of values to tabulate} - 0 where the counts are not integers or
-// spread too widely.  A unit evaluates lgamma once per possible count into a shared-memory table and its cells pick
-// their entries through the 16-bit index matrix It: the same function of the same argument as a direct evaluation, bit
-// for bit, at a fraction of the lgamma work.  Rows without a table are evaluated directly from Dt in the same loop.
+// Read counts are integers, and the counts of one region over a shard's cells take a few hundred distinct values: the
+// dataset's count-range table `lut` says, for every row of counts (regions 0..K-1, then the row sums S), {smallest count,
+// number of values to tabulate} - 0 where the counts are not integers or spread too widely.  For such a row a lgamma
+// term is a function of a few hundred possible arguments only:
+//   build_tables_kernel (K1a)     one CTA per item evaluates its tables over the possible counts into the launch's table
+//                                 arena: per event lgamma(v + a_node) - lgamma(v + a_parent), per node the two z-term
+//                                 tables lgamma(s + nu z), lgamma(s + nu z_parent), per region of a root-score slice
+//                                 lgamma(v + nu neutral_k r_k).  A few hundred lgamma per table instead of one per cell.
+//   build_increments_kernel (K1b) one thread per (item, 4 cells): picks the entries through the 16-bit index matrix It
+//                                 and adds them in the reference's order - the same function of the same argument as a
+//                                 direct evaluation, bit for bit.  Rows without a table (non-integer data: cluster means)
+//                                 are evaluated directly from Dt in the same loop (kDirect).
 // ---------------------------------------------------------------------------------
-struct TabStage {  // per-table constants of the group whose tables are resident (shared memory)
-    int offs[kLutGroup + 1];  // first table entry of member g
-    int vmin[kLutGroup];
-    int tab[kLutGroup];  // 1: tabulated on this block
-    int k[kLutGroup];    // region
-    double p0[kLutGroup], p1[kLutGroup], p2[kLutGroup], p3[kLutGroup];  // events: argN, argP, a, b;  slice regions: arg, c
-    int n;
-};
-
-__global__ void __launch_bounds__(kBuildBlock, 4) build_increments_kernel(const __grid_constant__ LaunchParams P) {
+__global__ void __launch_bounds__(128) build_tables_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ double tbl[kLogTableDoubles];
-    __shared__ double vals[kLutCap];
-    __shared__ TabStage st;
-    load_log_table<kBuildBlock>(tbl);
+    load_log_table<128>(tbl);
     const unsigned char* __restrict__ arena = P.arena;
-    const DevItem* items = reinterpret_cast<const DevItem*>(arena + P.off_items);
-    const int total = P.n_items * P.n_blocks;
-    const int lut_stride = 2 * P.n_blocks;  // ints per row of the count-range table
-    const long long stride = P.stride;
-    const int steps = (P.unit_cells + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells);
+    const DevItem& it = reinterpret_cast<const DevItem*>(arena + P.off_items)[blockIdx.x];
+    const int* __restrict__ lut = P.lut;
+    double* __restrict__ T = P.tables;
+    const unsigned kind = it.kind;
     __syncthreads();  // logarithm table loaded
-    for (int u = blockIdx.x; u < total; u += gridDim.x) {
-        const DevItem& it = items[u / P.n_blocks];
-        const int blk = u % P.n_blocks;
-        const int base = blk * P.unit_cells;
-        const int lim = min(P.n_cells, base + P.unit_cells);  // cells [base, lim) belong to this unit
-        const int* info = P.lut + blk * 2;  // {min, range} of row r of the counts at info[r * lut_stride]
-        const unsigned kind = it.kind;
-        double* const dst = P.rows + (long long)it.dst * stride;
-        if (kind == ITEM_NODE_OD) {
-            // score(node) - score(parent) in the reference's operation order (Tree::compute_score, Tree.h:212-231): for every
-            // event x += lgamma(D_k + a_node) - lgamma(D_k + a_parent); x -= lgamma(a_node); x += lgamma(a_parent); then the
-            // four z-terms.  Events are taken in groups whose tables fit the shared-memory table together (one group almost
-            // always); the z-term tables lgamma(S + nu z), lgamma(S + nu z_parent) stay resident in front of them.
-            const DevEvent* ev = reinterpret_cast<const DevEvent*>(arena + it.aux_off);
-            const int n_ev = it.n_ev;
-            // the two z-term tables take at most half of the value table, so that any event's table fits behind them
-            const int s_min = info[(long long)P.n_regions * lut_stride];
-            const int s_raw = info[(long long)P.n_regions * lut_stride + 1];
-            const int s_range = s_raw <= kLutCap / 4 ? s_raw : 0;
-            const int g_entries = 2 * s_range;
+    if (kind == ITEM_NODE_OD) {
+        const DevEvent* ev = reinterpret_cast<const DevEvent*>(arena + it.aux_off);
+        for (int e = 0; e < it.n_ev; ++e) {
+            const unsigned off = ev[e].tab;
+            if (off == kNoRow) continue;
+            const int vmin = lut[2 * ev[e].k], range = lut[2 * ev[e].k + 1];
+            const double aN = ev[e].argN, aP = ev[e].argP;
+            for (int i = threadIdx.x; i < range; i += 128) {
+                const double v = (double)(vmin + i);
+                T[off + i] = lgam(v + aN, tbl) - lgam(v + aP, tbl);  // Tree.h:214-218, one rounding of the difference as there
+            }
+        }
+        if (it.g_tab != kNoRow) {  // Tree.h:229-231
+            const int smin = lut[2 * P.n_regions], srange = lut[2 * P.n_regions + 1];
             const double nz = it.nz, nzp = it.nzp;
-            int e0 = 0;
-            bool first = true;
-            do {
-                if (threadIdx.x < kLutGroup && e0 + (int)threadIdx.x < n_ev) {
-                    const int g = threadIdx.x;
-                    const DevEvent& e = ev[e0 + g];
-                    st.k[g] = e.k;
-                    st.p0[g] = e.argN;
-                    st.p1[g] = e.argP;
-                    st.p2[g] = e.a;
-                    st.p3[g] = e.b;
-                    st.vmin[g] = info[(long long)e.k * lut_stride];
-                    st.tab[g] = info[(long long)e.k * lut_stride + 1];  // range for now
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    int tot = 0, n = 0;
-                    st.offs[0] = 0;
-                    while (e0 + n < n_ev && n < kLutGroup && g_entries + tot + st.tab[n] <= kLutCap) {
-                        tot += st.tab[n];
-                        ++n;
-                        st.offs[n] = tot;
-                    }
-                    st.n = n;
-                }
-                __syncthreads();
-                const int n = st.n;
-                const int tot = st.offs[n];
-                for (int e = threadIdx.x; e < tot; e += kBuildBlock) {
-                    int g = 0;
-                    while (st.offs[g + 1] <= e) ++g;
-                    const double v = (double)(st.vmin[g] + (e - st.offs[g]));
-                    vals[g_entries + e] = lgam(v + st.p0[g], tbl) - lgam(v + st.p1[g], tbl);
-                }
-                if (first)
-                    for (int e = threadIdx.x; e < s_range; e += kBuildBlock) {
-                        const double v = (double)(s_min + e);
-                        vals[e] = lgam(v + nz, tbl);
-                        vals[s_range + e] = lgam(v + nzp, tbl);
-                    }
-                __syncthreads();
-                const bool last = e0 + n >= n_ev;
-#pragma unroll 1
-                for (int h = 0; h < steps; ++h) {
-                    const int j0 = base + h * kBuildBlock * kBuildCells + threadIdx.x;
-                    if (j0 - (int)threadIdx.x >= lim) break;  // uniform
-                    double x[kBuildCells];
-                    bool ok[kBuildCells];
-#pragma unroll
-                    for (int q = 0; q < kBuildCells; ++q) {
-                        ok[q] = j0 + q * kBuildBlock < lim;
-                        x[q] = (first || !ok[q]) ? 0.0 : dst[j0 + q * kBuildBlock];
-                    }
-                    for (int g = 0; g < n; ++g) {
-                        const long long row = (long long)st.k[g] * stride + j0;
-                        double d[kBuildCells];
-                        if (st.offs[g + 1] > st.offs[g]) {  // tabulated on this block
-                            const unsigned short* ir = P.It + row;
-                            const double* tv = vals + g_entries + st.offs[g];
-                            unsigned idx[kBuildCells];
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(ir + q * kBuildBlock) : 0u;
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) d[q] = tv[idx[q]];
-                        } else {
-                            const double* dr = P.Dt + row;
-                            const double aN = st.p0[g], aP = st.p1[g];
-                            double c[kBuildCells];
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) c[q] = ok[q] ? __ldg(dr + q * kBuildBlock) : 32.0;
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) d[q] = lgam(c[q] + aN, tbl) - lgam(c[q] + aP, tbl);
-                        }
-                        const double a = st.p2[g], b = st.p3[g];
-#pragma unroll
-                        for (int q = 0; q < kBuildCells; ++q) {
-                            x[q] += d[q];
-                            x[q] -= a;
-                            x[q] += b;
-                        }
-                    }
-                    if (last) {  // Tree.h:227-231
-                        double gn[kBuildCells], gp[kBuildCells];
-                        if (s_range > 0) {
-                            unsigned idx[kBuildCells];
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(P.Si + j0 + q * kBuildBlock) : 0u;
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) {
-                                gn[q] = vals[idx[q]];
-                                gp[q] = vals[s_range + idx[q]];
-                            }
-                        } else {
-                            double s[kBuildCells];
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) s[q] = ok[q] ? __ldg(P.S + j0 + q * kBuildBlock) : 32.0;
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) {
-                                gn[q] = lgam(s[q] + nz, tbl);
-                                gp[q] = lgam(s[q] + nzp, tbl);
-                            }
-                        }
-                        const double lg_nz = it.lg_nz, lg_nzp = it.lg_nzp;
-#pragma unroll
-                        for (int q = 0; q < kBuildCells; ++q) {
-                            x[q] += lg_nz;
-                            x[q] -= lg_nzp;
-                            x[q] -= gn[q];
-                            x[q] += gp[q];
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < kBuildCells; ++q)
-                        if (ok[q]) dst[j0 + q * kBuildBlock] = x[q];
-                }
-                __syncthreads();  // the tables and the constants are rewritten by the next group / unit
-                e0 += n > 0 ? n : 1;  // n == 0 only when there are no events at all
-                first = false;
-            } while (e0 < n_ev);
-        } else if (kind == ITEM_NODE_MN) {  // Tree.h:221,236-237
-            const DevEvent* ev = reinterpret_cast<const DevEvent*>(arena + it.aux_off);
-            const int n_ev = it.n_ev;
-            const double lg_nz = it.lg_nz, lg_nzp = it.lg_nzp;
-#pragma unroll 1
-            for (int h = 0; h < steps; ++h) {
-                const int j0 = base + h * kBuildBlock * kBuildCells + threadIdx.x;
-                if (j0 - (int)threadIdx.x >= lim) break;
-                double x[kBuildCells];
-                bool ok[kBuildCells];
-#pragma unroll
-                for (int q = 0; q < kBuildCells; ++q) {
-                    ok[q] = j0 + q * kBuildBlock < lim;
-                    x[q] = 0.0;
-                }
-                for (int e = 0; e < n_ev; ++e) {
-                    const double* dr = P.Dt + (long long)ev[e].k * stride + j0;
-                    const double a = ev[e].a;
-#pragma unroll
-                    for (int q = 0; q < kBuildCells; ++q)
-                        if (ok[q]) x[q] += __ldg(dr + q * kBuildBlock) * a;
-                }
-#pragma unroll
-                for (int q = 0; q < kBuildCells; ++q)
-                    if (ok[q]) {
-                        const double s = __ldg(P.S + j0 + q * kBuildBlock);
-                        x[q] -= s * lg_nz;
-                        x[q] += s * lg_nzp;
-                        dst[j0 + q * kBuildBlock] = x[q];
-                    }
+            for (int i = threadIdx.x; i < srange; i += 128) {
+                const double v = (double)(smin + i);
+                T[it.g_tab + i] = lgam(v + nz, tbl);
+                T[it.g_tab + srange + i] = lgam(v + nzp, tbl);
             }
-        } else if (kind == ITEM_SLICE_OD) {
-            // sum over the regions [k0, k1) of lgamma(D_k + nu*neutral_k*r_k) - lgamma(nu*neutral_k*r_k), regions ascending
-            // (Tree::get_od_root_score, Tree.h:1792-1797); regions in groups whose tables fit together, the partial sums
-            // waiting in dst in between
-            const double* arg = reinterpret_cast<const double*>(arena + it.aux_off);
-            const double* cc = arg + P.n_regions;
-            int k = it.k0;
-            bool first = true;
-            while (k < it.k1) {
-                if (threadIdx.x < kLutGroup && k + (int)threadIdx.x < it.k1) {
-                    const int g = threadIdx.x;
-                    st.k[g] = k + g;
-                    st.p0[g] = arg[k + g];
-                    st.p1[g] = cc[k + g];
-                    st.vmin[g] = info[(long long)(k + g) * lut_stride];
-                    st.tab[g] = info[(long long)(k + g) * lut_stride + 1];
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    int tot = 0, n = 0;
-                    st.offs[0] = 0;
-                    while (k + n < it.k1 && n < kLutGroup && tot + st.tab[n] <= kLutCap) {
-                        tot += st.tab[n];
-                        ++n;
-                        st.offs[n] = tot;
-                    }
-                    st.n = n;
-                }
-                __syncthreads();
-                const int n = st.n;
-                const int tot = st.offs[n];
-                for (int e = threadIdx.x; e < tot; e += kBuildBlock) {
-                    int g = 0;
-                    while (st.offs[g + 1] <= e) ++g;
-                    vals[e] = lgam((double)(st.vmin[g] + (e - st.offs[g])) + st.p0[g], tbl);
-                }
-                __syncthreads();
-#pragma unroll 1
-                for (int h = 0; h < steps; ++h) {
-                    const int j0 = base + h * kBuildBlock * kBuildCells + threadIdx.x;
-                    if (j0 - (int)threadIdx.x >= lim) break;
-                    double acc[kBuildCells];
-                    bool ok[kBuildCells];
-#pragma unroll
-                    for (int q = 0; q < kBuildCells; ++q) {
-                        ok[q] = j0 + q * kBuildBlock < lim;
-                        acc[q] = (first || !ok[q]) ? 0.0 : dst[j0 + q * kBuildBlock];
-                    }
-                    for (int g = 0; g < n; ++g) {
-                        const long long row = (long long)st.k[g] * stride + j0;
-                        double v[kBuildCells];
-                        if (st.offs[g + 1] > st.offs[g]) {
-                            const unsigned short* ir = P.It + row;
-                            const double* tv = vals + st.offs[g];
-                            unsigned idx[kBuildCells];
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(ir + q * kBuildBlock) : 0u;
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) v[q] = tv[idx[q]];
-                        } else {
-                            const double* dr = P.Dt + row;
-                            const double a = st.p0[g];
-                            double c[kBuildCells];
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) c[q] = ok[q] ? __ldg(dr + q * kBuildBlock) : 32.0;
-#pragma unroll
-                            for (int q = 0; q < kBuildCells; ++q) v[q] = lgam(c[q] + a, tbl);
-                        }
-                        const double c = st.p1[g];
-#pragma unroll
-                        for (int q = 0; q < kBuildCells; ++q) {
-                            acc[q] += v[q];
-                            acc[q] -= c;
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < kBuildCells; ++q)
-                        if (ok[q]) dst[j0 + q * kBuildBlock] = acc[q];
-                }
-                __syncthreads();
-                k += n;
-                first = false;
-            }
-        } else if (kind == ITEM_SLICE_MN) {  // Tree.h:1803-1805
-            const double* arg = reinterpret_cast<const double*>(arena + it.aux_off);
-#pragma unroll 1
-            for (int h = 0; h < steps; ++h) {
-                const int j0 = base + h * kBuildBlock * kBuildCells + threadIdx.x;
-                if (j0 - (int)threadIdx.x >= lim) break;
-                double acc[kBuildCells];
-                bool ok[kBuildCells];
-#pragma unroll
-                for (int q = 0; q < kBuildCells; ++q) {
-                    ok[q] = j0 + q * kBuildBlock < lim;
-                    acc[q] = 0.0;
-                }
-                for (int k = it.k0; k < it.k1; ++k) {
-                    const double* dr = P.Dt + (long long)k * stride + j0;
-                    const double a = arg[k];
-#pragma unroll
-                    for (int q = 0; q < kBuildCells; ++q)
-                        if (ok[q]) acc[q] += __ldg(dr + q * kBuildBlock) * a;
-                }
-#pragma unroll
-                for (int q = 0; q < kBuildCells; ++q)
-                    if (ok[q]) dst[j0 + q * kBuildBlock] = acc[q];
-            }
-        } else {  // ITEM_G_ROW: dst = lgamma(S + c)
-            const int s_min = info[(long long)P.n_regions * lut_stride], s_range = info[(long long)P.n_regions * lut_stride + 1];
+        }
+    } else if (kind == ITEM_SLICE_OD) {  // Tree.h:1792-1797
+        const double* arg = reinterpret_cast<const double*>(arena + it.aux_off);
+        const unsigned* taboff = reinterpret_cast<const unsigned*>(arg + 2 * P.n_regions);
+        for (int k = it.k0; k < it.k1; ++k) {
+            const unsigned off = taboff[k];
+            if (off == kNoRow) continue;
+            const int vmin = lut[2 * k], range = lut[2 * k + 1];
+            const double a = arg[k];
+            for (int i = threadIdx.x; i < range; i += 128) T[off + i] = lgam((double)(vmin + i) + a, tbl);
+        }
+    } else if (kind == ITEM_G_ROW) {
+        if (it.g_tab != kNoRow) {
+            const int smin = lut[2 * P.n_regions], srange = lut[2 * P.n_regions + 1];
             const double c1 = it.nz;
-            for (int e = threadIdx.x; e < s_range; e += kBuildBlock) vals[e] = lgam((double)(s_min + e) + c1, tbl);
-            __syncthreads();
-#pragma unroll 1
-            for (int h = 0; h < steps; ++h) {
-                const int j0 = base + h * kBuildBlock * kBuildCells + threadIdx.x;
-                if (j0 - (int)threadIdx.x >= lim) break;
+            for (int i = threadIdx.x; i < srange; i += 128) T[it.g_tab + i] = lgam((double)(smin + i) + c1, tbl);
+        }
+    }
+}
+
+template <bool kDirect>  // kDirect: some row of this shard has no table - the logarithm table is needed
+__global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __grid_constant__ LaunchParams P) {
+    __shared__ double tbl[kDirect ? kLogTableDoubles : 1];
+    if (kDirect) {
+        load_log_table<kBuildBlock>(tbl);
+        __syncthreads();
+    }
+    const unsigned char* __restrict__ arena = P.arena;
+    const DevItem& it = reinterpret_cast<const DevItem*>(arena + P.off_items)[blockIdx.y];
+    const double* __restrict__ T = P.tables;
+    const long long stride = P.stride;
+    const unsigned kind = it.kind;
+    double* const dst = P.rows + (long long)it.dst * stride;
+    const int j0 = blockIdx.x * (kBuildBlock * kBuildCells) + threadIdx.x;
+    bool ok[kBuildCells];
 #pragma unroll
-                for (int q = 0; q < kBuildCells; ++q) {
-                    const int j = j0 + q * kBuildBlock;
-                    if (j < lim) dst[j] = s_range > 0 ? vals[__ldg(P.Si + j)] : lgam(__ldg(P.S + j) + c1, tbl);
-                }
+    for (int q = 0; q < kBuildCells; ++q) ok[q] = j0 + q * kBuildBlock < P.n_cells;
+    if (kind == ITEM_NODE_OD) {
+        // score(node) - score(parent) in the reference's operation order (Tree::compute_score, Tree.h:212-231): for every
+        // event x += lgamma(D_k + a_node) - lgamma(D_k + a_parent); x -= lgamma(a_node); x += lgamma(a_parent); then the
+        // four z-terms
+        const DevEvent* ev = reinterpret_cast<const DevEvent*>(arena + it.aux_off);
+        double x[kBuildCells];
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) x[q] = 0.0;
+        const int n_ev = it.n_ev;
+        for (int e = 0; e < n_ev; ++e) {
+            const unsigned off = ev[e].tab;
+            const long long row = (long long)ev[e].k * stride + j0;
+            double d[kBuildCells];
+            if (off != kNoRow) {
+                const unsigned short* ir = P.It + row;
+                unsigned idx[kBuildCells];
+#pragma unroll
+                for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(ir + q * kBuildBlock) : 0u;
+#pragma unroll
+                for (int q = 0; q < kBuildCells; ++q) d[q] = __ldg(T + off + idx[q]);
+            } else if (kDirect) {
+                const double* dr = P.Dt + row;
+                const double aN = ev[e].argN, aP = ev[e].argP;
+                double c[kBuildCells];
+#pragma unroll
+                for (int q = 0; q < kBuildCells; ++q) c[q] = ok[q] ? __ldg(dr + q * kBuildBlock) : 32.0;
+#pragma unroll
+                for (int q = 0; q < kBuildCells; ++q) d[q] = lgam(c[q] + aN, tbl) - lgam(c[q] + aP, tbl);
             }
-            __syncthreads();
+            const double a = ev[e].a, b = ev[e].b;
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) {
+                x[q] += d[q];
+                x[q] -= a;
+                x[q] += b;
+            }
+        }
+        double gn[kBuildCells], gp[kBuildCells];
+        if (it.g_tab != kNoRow) {
+            const int srange = P.lut[2 * P.n_regions + 1];
+            unsigned idx[kBuildCells];
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(P.Si + j0 + q * kBuildBlock) : 0u;
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) {
+                gn[q] = __ldg(T + it.g_tab + idx[q]);
+                gp[q] = __ldg(T + it.g_tab + srange + idx[q]);
+            }
+        } else if (kDirect) {
+            const double nz = it.nz, nzp = it.nzp;
+            double s[kBuildCells];
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) s[q] = ok[q] ? __ldg(P.S + j0 + q * kBuildBlock) : 32.0;
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) {
+                gn[q] = lgam(s[q] + nz, tbl);
+                gp[q] = lgam(s[q] + nzp, tbl);
+            }
+        }
+        const double lg_nz = it.lg_nz, lg_nzp = it.lg_nzp;
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) {  // Tree.h:227-231
+            x[q] += lg_nz;
+            x[q] -= lg_nzp;
+            x[q] -= gn[q];
+            x[q] += gp[q];
+            if (ok[q]) dst[j0 + q * kBuildBlock] = x[q];
+        }
+    } else if (kind == ITEM_NODE_MN) {  // Tree.h:221,236-237
+        const DevEvent* ev = reinterpret_cast<const DevEvent*>(arena + it.aux_off);
+        const double lg_nz = it.lg_nz, lg_nzp = it.lg_nzp;
+        double x[kBuildCells];
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) x[q] = 0.0;
+        for (int e = 0; e < it.n_ev; ++e) {
+            const double* dr = P.Dt + (long long)ev[e].k * stride + j0;
+            const double a = ev[e].a;
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q)
+                if (ok[q]) x[q] += __ldg(dr + q * kBuildBlock) * a;
+        }
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q)
+            if (ok[q]) {
+                const double s = __ldg(P.S + j0 + q * kBuildBlock);
+                x[q] -= s * lg_nz;
+                x[q] += s * lg_nzp;
+                dst[j0 + q * kBuildBlock] = x[q];
+            }
+    } else if (kind == ITEM_SLICE_OD) {
+        // sum over the regions [k0, k1) of lgamma(D_k + nu*neutral_k*r_k) - lgamma(nu*neutral_k*r_k), regions ascending
+        // (Tree::get_od_root_score, Tree.h:1792-1797)
+        const double* arg = reinterpret_cast<const double*>(arena + it.aux_off);
+        const double* cc = arg + P.n_regions;
+        const unsigned* taboff = reinterpret_cast<const unsigned*>(arg + 2 * P.n_regions);
+        double acc[kBuildCells];
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) acc[q] = 0.0;
+        for (int k = it.k0; k < it.k1; ++k) {
+            const unsigned off = taboff[k];
+            const long long row = (long long)k * stride + j0;
+            double v[kBuildCells];
+            if (off != kNoRow) {
+                const unsigned short* ir = P.It + row;
+                unsigned idx[kBuildCells];
+#pragma unroll
+                for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(ir + q * kBuildBlock) : 0u;
+#pragma unroll
+                for (int q = 0; q < kBuildCells; ++q) v[q] = __ldg(T + off + idx[q]);
+            } else if (kDirect) {
+                const double* dr = P.Dt + row;
+                const double a = arg[k];
+                double c[kBuildCells];
+#pragma unroll
+                for (int q = 0; q < kBuildCells; ++q) c[q] = ok[q] ? __ldg(dr + q * kBuildBlock) : 32.0;
+#pragma unroll
+                for (int q = 0; q < kBuildCells; ++q) v[q] = lgam(c[q] + a, tbl);
+            }
+            const double c = cc[k];
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q) {
+                acc[q] += v[q];
+                acc[q] -= c;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q)
+            if (ok[q]) dst[j0 + q * kBuildBlock] = acc[q];
+    } else if (kind == ITEM_SLICE_MN) {  // Tree.h:1803-1805
+        const double* arg = reinterpret_cast<const double*>(arena + it.aux_off);
+        double acc[kBuildCells];
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) acc[q] = 0.0;
+        for (int k = it.k0; k < it.k1; ++k) {
+            const double* dr = P.Dt + (long long)k * stride + j0;
+            const double a = arg[k];
+#pragma unroll
+            for (int q = 0; q < kBuildCells; ++q)
+                if (ok[q]) acc[q] += __ldg(dr + q * kBuildBlock) * a;
+        }
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q)
+            if (ok[q]) dst[j0 + q * kBuildBlock] = acc[q];
+    } else {  // ITEM_G_ROW: dst = lgamma(S + c)
+        const double c1 = it.nz;
+#pragma unroll
+        for (int q = 0; q < kBuildCells; ++q) {
+            const int j = j0 + q * kBuildBlock;
+            if (j < P.n_cells) {
+                if (it.g_tab != kNoRow)
+                    dst[j] = __ldg(T + it.g_tab + __ldg(P.Si + j));
+                else if (kDirect)
+                    dst[j] = lgam(__ldg(P.S + j) + c1, tbl);
+            }
         }
     }
 }
@@ -875,16 +785,15 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
     finish_reduction(cta_sum, cta_od, le.slot, P);
 }
 
-// Dataset set-up: the 16-bit index matrix of the tabulated (row, block) pairs.  Row K of the table describes S.
+// Dataset set-up: the 16-bit index matrix of the tabulated rows.  Row K of the table describes S.
 __global__ void index_kernel(const double* __restrict__ Dt, const double* __restrict__ S, const int* __restrict__ lut, int M, int K,
-                             long long Mp, int n_blocks, int unit_cells, unsigned short* __restrict__ It, unsigned short* __restrict__ Si) {
+                             long long Mp, unsigned short* __restrict__ It, unsigned short* __restrict__ Si) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (j >= M) return;
-    const int blk = j / unit_cells;
-    const int* info = lut + ((long long)k * n_blocks + blk) * 2;
+    const int vmin = lut[2 * k], range = lut[2 * k + 1];
     const double v = k < K ? Dt[(long long)k * Mp + j] : S[j];
-    const unsigned short idx = info[1] > 0 ? (unsigned short)((int)v - info[0]) : (unsigned short)0;
+    const unsigned short idx = range > 0 ? (unsigned short)((int)v - vmin) : (unsigned short)0;
     if (k < K)
         It[(long long)k * Mp + j] = idx;
     else

@@ -370,10 +370,13 @@ struct scicone_dataset {
     double* dS = nullptr;
     unsigned short* dIt = nullptr;  // [K][Mp] 16-bit count indices of the tabulated (region, block) pairs
     unsigned short* dSi = nullptr;  // [Mp] the same for the read totals
-    // count-range table of K1 (kernels.cuh, build_increments_kernel): [K + 1 rows: regions, then S][blocks of unit_cells cells]{min, range}
+    // count-range table of K1 (kernels.cuh): [K + 1 rows: regions, then S]{min, range}; the host keeps a copy to lay out the
+    // value tables of a launch
     int* d_lut = nullptr;
-    int unit_cells = 0, n_blocks = 0;
-    double lut_share = 0.0;  // fraction of the (row, block) pairs that are tabulated
+    std::vector<int> lut;
+    bool all_tab = false;    // every row has a table: K1b needs no direct lgamma evaluation
+    double* d_tables[2] = {nullptr, nullptr};  // per lane: value tables of the launch in flight
+    size_t tables_cap = 0;                     // doubles per lane
     int* dW = nullptr;
     cudaStream_t stream = nullptr;
     RowPool pool;
@@ -478,6 +481,20 @@ struct scicone_dataset {
         for (Segment& g : seg) CUDA_TRY(cudaMallocHost(&g.h_arena, cap));
         for (int l = 0; l < kLanes; ++l) CUDA_TRY(cudaMalloc(&d_arena[l], cap));
         arena_cap = cap;
+        return SCICONE_OK;
+    }
+    int ensure_tables(size_t doubles) {
+        if (doubles <= tables_cap) return SCICONE_OK;
+        int rc0 = sync_lanes();
+        if (rc0) return rc0;
+        const size_t cap = std::max<size_t>(doubles * 2, size_t(1) << 20);
+        for (int l = 0; l < kLanes; ++l) {
+            if (d_tables[l]) cudaFree(d_tables[l]);
+            d_tables[l] = nullptr;
+        }
+        tables_cap = 0;
+        for (int l = 0; l < kLanes; ++l) CUDA_TRY(cudaMalloc(&d_tables[l], sizeof(double) * cap));
+        tables_cap = cap;
         return SCICONE_OK;
     }
     double* lane_total(int lane) const { return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_total) + lane * lane_result_bytes); }
@@ -621,7 +638,7 @@ constexpr int kOdRegionsPerSlice = 6;  // 200 regions -> 32 slices: enough units
 int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<unsigned>& slice_rows) {
     scicone_dataset* ds = ch->ds;
     const int K = ds->K;
-    std::vector<double> arg(2 * (size_t)K, 0.0);  // arg[K], then c[K]
+    std::vector<double> arg(2 * (size_t)K + ((size_t)K + 1) / 2, 0.0);  // arg[K], c[K], then room for K 32-bit table offsets (filled at submit)
     double* cc = arg.data() + K;
     if (ds->od) {  // Tree.h:1783-1797 (no eta substitution here, quirk Q2)
         H.od_nz = nu * ds->root_z;
@@ -972,24 +989,58 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         memcpy(g.h_arena + at, ch->blob.data(), ch->blob.size());
         at += ch->blob.size();
     }
-    // K1 items: the root-score slices (several table builds and ~6 look-ups per cell) first, the node increments behind
-    // them, so the persistent CTAs start with the long units
+    // K1 items: the root-score slices (~6 look-ups per cell) first, the node increments behind them.  The value tables of
+    // the launch are laid out here, per rank: which rows of counts have a table, and how long it is, depends on the shard.
+    const int* lut = ds->lut.data();
+    const int K = ds->K;
+    const int s_range = lut[2 * K + 1];
+    size_t tab_at = 0;
     for (int pass = 0; pass < 2; ++pass) {
         size_t chain_aux = off_aux;
         for (int i = 0; i < n; ++i) {
             scicone_chain* ch = chains[i];
             if (pass == 0 && !ch->aux.empty()) memcpy(g.h_arena + chain_aux, ch->aux.data(), ch->aux.size());
+            bool slices_laid_out = false;
             for (const DevItem& src : ch->items) {
                 const bool slice = src.kind == ITEM_SLICE_OD || src.kind == ITEM_SLICE_MN;
                 if (slice != (pass == 0)) continue;
                 DevItem it = src;
                 it.aux_off += (unsigned)chain_aux;
+                it.g_tab = kNoRow;
+                if (it.kind == ITEM_NODE_OD) {
+                    DevEvent* ev = reinterpret_cast<DevEvent*>(g.h_arena + it.aux_off);
+                    for (int e = 0; e < it.n_ev; ++e) {
+                        const int range = lut[2 * ev[e].k + 1];
+                        ev[e].tab = range > 0 ? (unsigned)tab_at : kNoRow;
+                        tab_at += (size_t)range;
+                    }
+                    if (s_range > 0) {
+                        it.g_tab = (unsigned)tab_at;
+                        tab_at += 2 * (size_t)s_range;
+                    }
+                } else if (it.kind == ITEM_G_ROW) {
+                    if (s_range > 0) {
+                        it.g_tab = (unsigned)tab_at;
+                        tab_at += (size_t)s_range;
+                    }
+                } else if (it.kind == ITEM_SLICE_OD && !slices_laid_out) {  // one table per region, shared by the chain's slices
+                    unsigned* taboff = reinterpret_cast<unsigned*>(g.h_arena + it.aux_off + 2 * (size_t)K * sizeof(double));
+                    for (int k = 0; k < K; ++k) {
+                        const int range = lut[2 * k + 1];
+                        taboff[k] = range > 0 ? (unsigned)tab_at : kNoRow;
+                        tab_at += (size_t)range;
+                    }
+                    slices_laid_out = true;
+                }
                 memcpy(g.h_arena + item_at, &it, sizeof it);
                 item_at += sizeof it;
             }
             chain_aux += round_up(ch->aux.size(), 16);
         }
     }
+    if (tab_at >= 0xffffff00ull) return fail(SCICONE_ERR_ARG, "the value tables of one launch exceed 2^32 entries");
+    rc = ds->ensure_tables(tab_at);
+    if (rc) return rc;
     for (int q = 0; q < n; ++q) {
         offs[q] = chains[order[q]]->entry;
         offs[q].blob_off = blob_at[order[q]];
@@ -1007,9 +1058,8 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     P.Si = ds->dSi;
     P.w = ds->dW;
     P.lut = ds->d_lut;
+    P.tables = ds->d_tables[lane];
     P.n_cells = ds->M;
-    P.n_blocks = ds->n_blocks;
-    P.unit_cells = ds->unit_cells;
     P.n_regions = ds->K;
     P.partial = ds->lane_partial(lane);
     P.chunk_sums = ds->lane_chunk(lane);
@@ -1032,8 +1082,16 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     P.n_items = (int)n_items;
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, st));
-        const long long units = (long long)n_items * ds->n_blocks;
-        build_increments_kernel<<<(unsigned)std::min<long long>(units, 4ll * ds->n_sm), kBuildBlock, 0, st>>>(P);
+        if (n_items > 65535) return fail(SCICONE_ERR_ARG, "more than 65535 rescored nodes in one launch");
+        if (tab_at > 0) {
+            build_tables_kernel<<<(unsigned)n_items, 128, 0, st>>>(P);
+            ds->n_launches++;
+        }
+        const dim3 bgrid((ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells), (unsigned)n_items);
+        if (ds->all_tab)
+            build_increments_kernel<false><<<bgrid, kBuildBlock, 0, st>>>(P);
+        else
+            build_increments_kernel<true><<<bgrid, kBuildBlock, 0, st>>>(P);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
     }
@@ -1258,10 +1316,6 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     ds->n_cta = (ds->M + kCells - 1) / kCells;
     ds->n_chunks = (ds->n_cta + kCtasPerChunk - 1) / kCtasPerChunk;
     ds->cs_stride = ds->n_chunks;
-    // K1 works on blocks of unit_cells cells: as few blocks of at most kUnitMax cells as cover the shard, equally sized
-    ds->n_blocks = (ds->M + kUnitMax - 1) / kUnitMax;
-    ds->unit_cells = (int)round_up((size_t)(ds->M + ds->n_blocks - 1) / ds->n_blocks, kPad);
-    ds->n_blocks = (ds->M + ds->unit_cells - 1) / ds->unit_cells;
     auto cleanup = [&](int rc) {
         scicone_dataset_destroy(ds);
         return rc;
@@ -1306,56 +1360,49 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
         dim3 grid((ds->K + 31) / 32, (ds->M + 31) / 32), block(32, 8);
         transpose_kernel<<<grid, block, 0, ds->stream>>>(dD, ds->dDt, ds->M, ds->K, (long long)ds->Mp);
         row_sum_kernel<<<(ds->M + 127) / 128, 128, 0, ds->stream>>>(ds->dDt, ds->dS, ds->M, ds->K, (long long)ds->Mp);
-        // Count-range table: read counts are integers, and the counts of one region over a block of a few thousand cells
-        // take a few hundred distinct values - K1 then evaluates lgamma(count + c) once per possible count instead of once
-        // per cell (identical results: the same function of the same argument).  A (row, block) pair is tabulated when all
-        // its values are non-negative integers and the table is at most half as long as the block; SCICONE_LUT=0 turns it off.
+        // Count-range table: read counts are integers, and the counts of one region over the cells of a shard take a few
+        // hundred distinct values - K1 then evaluates lgamma(count + c) once per possible count instead of once per cell
+        // (identical results: the same function of the same argument).  A row of counts is tabulated when all its values are
+        // non-negative integers and the table is at most half as long as the row; SCICONE_LUT=0 turns it off.
         const int K = ds->K, M = ds->M;
-        const int bpr = ds->n_blocks;
-        std::vector<int> lut((size_t)(K + 1) * bpr * 2, 0);
+        std::vector<int>& lut = ds->lut;
+        lut.assign((size_t)(K + 1) * 2, 0);
         const char* lut_env = getenv("SCICONE_LUT");
         if (!(lut_env && atoi(lut_env) == 0)) {
-            std::vector<double> lo((size_t)K + 1), hi((size_t)K + 1);
-            std::vector<char> integral((size_t)K + 1);
-            size_t n_tab = 0;
-            for (int b = 0; b < bpr; ++b) {
-                const int j0 = b * ds->unit_cells, j1 = std::min(M, j0 + ds->unit_cells);
-                std::fill(lo.begin(), lo.end(), 1e300);
-                std::fill(hi.begin(), hi.end(), -1e300);
-                std::fill(integral.begin(), integral.end(), 1);
-                for (int j = j0; j < j1; ++j) {
-                    const double* row = d->D + (size_t)j * K;
-                    double sum = 0.0;
-                    bool all_int = true;
-                    for (int k = 0; k < K; ++k) {
-                        const double v = row[k];
-                        sum = sum + v;  // the order of row_sum_kernel; exact for integer counts anyway
-                        if (!(v >= 0.0 && v < 1073741824.0 && v == std::floor(v))) {
-                            integral[k] = 0;
-                            all_int = false;
-                        }
-                        lo[k] = std::min(lo[k], v);
-                        hi[k] = std::max(hi[k], v);
+            std::vector<double> lo((size_t)K + 1, 1e300), hi((size_t)K + 1, -1e300);
+            std::vector<char> integral((size_t)K + 1, 1);
+            for (int j = 0; j < M; ++j) {
+                const double* row = d->D + (size_t)j * K;
+                double sum = 0.0;
+                bool all_int = true;
+                for (int k = 0; k < K; ++k) {
+                    const double v = row[k];
+                    sum = sum + v;  // the order of row_sum_kernel; exact for integer counts anyway
+                    if (!(v >= 0.0 && v < 1073741824.0 && v == std::floor(v))) {
+                        integral[k] = 0;
+                        all_int = false;
                     }
-                    if (!all_int || !(sum < 1073741824.0)) integral[K] = 0;
-                    lo[K] = std::min(lo[K], sum);
-                    hi[K] = std::max(hi[K], sum);
+                    lo[k] = std::min(lo[k], v);
+                    hi[k] = std::max(hi[k], v);
                 }
-                for (int k = 0; k <= K; ++k) {
-                    if (!integral[k]) continue;
-                    const double range = hi[k] - lo[k] + 1.0;
-                    if (range > (double)kLutMax || 2.0 * range > (double)std::max(j1 - j0, 2)) continue;
-                    lut[((size_t)k * bpr + b) * 2] = (int)lo[k];
-                    lut[((size_t)k * bpr + b) * 2 + 1] = (int)range;
-                    ++n_tab;
-                }
+                if (!all_int || !(sum < 1073741824.0)) integral[K] = 0;
+                lo[K] = std::min(lo[K], sum);
+                hi[K] = std::max(hi[K], sum);
             }
-            ds->lut_share = (double)n_tab / (double)((size_t)(K + 1) * bpr);
+            ds->all_tab = true;
+            for (int k = 0; k <= K; ++k) {
+                const double range = hi[k] - lo[k] + 1.0;
+                if (!integral[k] || range > (double)kLutMax || 2.0 * range > (double)std::max(M, 2)) {
+                    ds->all_tab = false;
+                    continue;
+                }
+                lut[(size_t)k * 2] = (int)lo[k];
+                lut[(size_t)k * 2 + 1] = (int)range;
+            }
         }
         DS_TRY(cudaMalloc(&ds->d_lut, sizeof(int) * lut.size()));
         DS_TRY(cudaMemcpyAsync(ds->d_lut, lut.data(), sizeof(int) * lut.size(), cudaMemcpyHostToDevice, ds->stream));
-        index_kernel<<<dim3((M + 255) / 256, K + 1), 256, 0, ds->stream>>>(ds->dDt, ds->dS, ds->d_lut, M, K, (long long)ds->Mp, bpr, ds->unit_cells,
-                                                                            ds->dIt, ds->dSi);
+        index_kernel<<<dim3((M + 255) / 256, K + 1), 256, 0, ds->stream>>>(ds->dDt, ds->dS, ds->d_lut, M, K, (long long)ds->Mp, ds->dIt, ds->dSi);
         cudaError_t e2 = cudaMemcpyAsync(ds->dW, d->cluster_sizes, sizeof(int) * ds->M, cudaMemcpyHostToDevice, ds->stream);
         cudaError_t e3 = cudaStreamSynchronize(ds->stream);  // `lut` and the caller's buffers are read until here
         cudaFree(dD);
@@ -1368,6 +1415,8 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     int rc = ds->ensure_slots(64);
     if (rc) return cleanup(rc);
     rc = ds->ensure_arena(size_t(4) << 20);
+    if (rc) return cleanup(rc);
+    rc = ds->ensure_tables(size_t(1) << 20);
     if (rc) return cleanup(rc);
     *out = ds;
     return SCICONE_OK;
@@ -1391,6 +1440,7 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     for (unsigned char* a : ds->d_arena) cudaFree(a);
     cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
     cudaFree(ds->d_counter); cudaFree(ds->d_gather); cudaFree(ds->d_launch_counter);
+    for (double* t : ds->d_tables) cudaFree(t);
     for (scicone_dataset::Segment& g : ds->seg) {
         if (g.h_arena) cudaFreeHost(g.h_arena);
         if (g.h_total) cudaFreeHost(g.h_total);
