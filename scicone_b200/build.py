@@ -63,7 +63,12 @@ def build_host(force=False):
         subprocess.check_call(common + ["-DSCICONE_SCORE_MAIN", "-Wl,-rpath,$ORIGIN/../lib", "-o", score])
     if force or _newer(lib, srcs):
         subprocess.check_call(common + ["-DSCICONE_HOST_NO_MAIN", "-fPIC", "-shared", "-Wl,-rpath,$ORIGIN", "-o", lib])
-    return [exe, score, lib]
+    # restarts over the GPUs of a box + best-of-N / robustness / retries (pyscicone's learn_tree_parallel): no library needed
+    learn = os.path.join(bin_dir, "learn_tree")
+    learn_src = os.path.join(host, "learn_tree_main.cpp")
+    if force or _newer(learn, [learn_src]):
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", learn_src, "-o", learn])
+    return [exe, score, lib, learn]
 
 
 def build_all(force=False, verbose=False):

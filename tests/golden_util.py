@@ -31,10 +31,31 @@ def subtree_roots(tree, rescored_ids):
 
 
 def rel_err(a, b):
+    """Largest relative error over the FINITE entries.  Non-finite entries (an int-truncated Node::z of 0 gives
+    lgamma(0) = inf and inf - inf = NaN on both sides, Tree.h:227-231) must sit at exactly the same positions and be of
+    the same kind (NaN / +inf / -inf) on both sides; otherwise the error is infinite, so a NaN that only one side
+    produces can never pass a tolerance check."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        a, b = np.broadcast_arrays(a, b)
     if a.size == 0:
         return 0.0
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    if not np.array_equal(fa, fb):
+        return float("inf")
+    if not fa.all():
+        na, nb = a[~fa], b[~fa]
+        if not np.array_equal(np.isnan(na), np.isnan(nb)) or not np.array_equal(na[~np.isnan(na)], nb[~np.isnan(nb)]):
+            return float("inf")
+        if not fa.any():
+            return 0.0
+        a, b = a[fa], b[fa]
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+def worse(worst, err):
+    """max() that cannot lose a NaN: Python's max(0.0, nan) is 0.0."""
+    return err if not (err <= worst) else worst
 
 
 def replay(doc, chain, check, od_of=None):

@@ -8,7 +8,7 @@ Node ids, argmax ids and rescored-id sets must match exactly.
 import numpy as np
 import pytest
 
-from golden_util import chain_kwargs, golden_names, load_golden, rel_err, replay
+from golden_util import chain_kwargs, golden_names, load_golden, rel_err, replay, worse
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +26,7 @@ def _check_factory(worst):
             worst["argmax_mismatch"] += int(np.sum(np.asarray(got) != np.asarray(want)))
             return
         e = rel_err(got, want)
-        worst[what] = max(worst.get(what, 0.0), e)
+        worst[what] = worse(worst.get(what, 0.0), e)
         assert e <= TOL, (what, step, e)
 
     return check

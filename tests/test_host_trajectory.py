@@ -86,6 +86,36 @@ def test_native_host_on_gpu(tmp_path, case):
     _both(tmp_path, case, None)
 
 
+def _config2_full():
+    # configs[2] at full size for the scoring path: 10 000 cells x 200 regions, 50-node trees.  Only the bin count is
+    # reduced (4 000 instead of 18 000): bins enter nothing but the width of the inferred_cnvs.csv text, which both
+    # hosts write and the comparison reads in full (40 MB instead of 360 MB per run).
+    d = make_counts(10000, 4000, 200, seed=12)
+    return d["D"], d["region_sizes"], None
+
+
+FULL_CASES = {
+    "config2_full_max": (_config2_full, ["--n_iters=150", "--n_nodes=49", "--seed=42", "--nu=1.0", "--max_scoring=true"]),
+    "config2_full_sum": (_config2_full, ["--n_iters=150", "--n_nodes=49", "--seed=43", "--nu=1.0", "--max_scoring=false"]),
+}
+
+
+@needs_bins
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(FULL_CASES))
+def test_native_host_on_gpu_at_config2_size(tmp_path, case):
+    """Inference::infer_mcmc (Inference.h:544-913) at BASELINE configs[2] size against the unmodified reference binary:
+    identical accepted-move sequence, final tree and per-cell outputs, per-move scores within 1e-9 relative - strict
+    comparison, no knife-edge allowance."""
+    data, extra = FULL_CASES[case]
+    D, r, w = data()
+    a = run_inference(REF, str(tmp_path), "ref", D, r, extra, w=w, env={"OMP_NUM_THREADS": str(os.cpu_count() or 1)}, timeout=1500)
+    b = run_inference(NATIVE, str(tmp_path), "new", D, r, extra, w=w, timeout=600)
+    rel = compare_runs(a, b)
+    assert int(np.sum(a["acc"] >= 0)) > 5, "the run must accept some moves to mean anything"
+    print(case, "accepted", int(np.sum(a["acc"] >= 0)), "of", a["acc"].size, "max rel diff", rel)
+
+
 @needs_bins
 @pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
 def test_tree_file_start_on_cpu(tmp_path):
@@ -139,14 +169,15 @@ def test_multi_chain_equals_single_runs_on_gpu(tmp_path):
 
 @needs_bins
 @pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
-@pytest.mark.parametrize("schedule,world,threads", [("static", 2, "2"), ("dynamic", 2, "1"), ("dynamic", 3, "3")])
-def test_chain_ownership_protocol_on_cpu(tmp_path, schedule, world, threads):
+@pytest.mark.parametrize("schedule,world,threads,warmup", [("static", 2, "2", 0), ("dynamic", 2, "1", 0), ("dynamic", 3, "3", 0), ("dynamic", 2, "2", 150)])
+def test_chain_ownership_protocol_on_cpu(tmp_path, schedule, world, threads, warmup):
     """Multi-process runs: every chain is searched by ONE owner process, the others follow it through the shared-memory
     mailbox (proposal + decision messages).  Two processes with --no_shard (each holds all cells, oracle-backed ABI):
     the owner's traces of every chain equal the unmodified reference's single-chain run, and the followers' device state
     stays in step (a follower that missed a commit would make the owner's next totals differ on the GPU; here it is
     checked through the final tables of both processes being readable and the run finishing).  With the dynamic schedule
-    rank 0 composes the launches and the other ranks replay its launch log."""
+    rank 0 composes the launches and the other ranks replay its launch log.  `warmup`: --warmup_iters splits the run into an
+    untimed and a timed phase (bench.py); the chains continue across the mark, so the trajectory is that of one run."""
     import subprocess
     import uuid
 
@@ -154,6 +185,7 @@ def test_chain_ownership_protocol_on_cpu(tmp_path, schedule, world, threads):
 
     D, r = _tutorial()
     base = ["--n_iters=600", "--n_nodes=4", "--nu=1.0", "--max_scoring=true"]
+    split = [f"--n_iters={600 - warmup}", f"--warmup_iters={warmup}"] if warmup else []
     d = os.path.join(str(tmp_path), "d.csv")
     np.savetxt(d, D, delimiter=",", fmt="%.0f")
     rf = os.path.join(str(tmp_path), "r.txt")
@@ -164,7 +196,7 @@ def test_chain_ownership_protocol_on_cpu(tmp_path, schedule, world, threads):
     for k in range(world):
         cmd = [NATIVE, f"--d_matrix_file={d}", f"--region_sizes_file={rf}", f"--n_cells={D.shape[0]}", f"--n_regions={D.shape[1]}",
                "--verbosity=2", f"--postfix=own{k}", "--seed=30", "--n_chains=5", f"--schedule={schedule}", "--min_batch=2", "--no_shard", f"--rank={k}", f"--world={world}",
-               f"--shm_name={shm}"] + base
+               f"--shm_name={shm}"] + base + split
         procs.append(subprocess.Popen(cmd, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
     for p in procs:
         out, err = p.communicate(timeout=600)

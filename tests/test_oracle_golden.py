@@ -7,7 +7,7 @@ to the last bit on scores and aggregates; we allow 1e-13 relative to stay robust
 import numpy as np
 import pytest
 
-from golden_util import chain_kwargs, golden_names, load_golden, rel_err, replay
+from golden_util import chain_kwargs, golden_names, load_golden, rel_err, replay, worse
 from oracle_ffi import OracleChain
 
 TOL = 1e-13
@@ -24,7 +24,7 @@ def test_port_replays_reference_trace(name):
             assert list(got) == list(want), (what, step, got, want)
             return
         e = rel_err(got, want)
-        worst[what] = max(worst.get(what, 0.0), e)
+        worst[what] = worse(worst.get(what, 0.0), e)
         assert e <= TOL, (what, step, e)
 
     replay(doc, chain, check)

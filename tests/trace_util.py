@@ -1,7 +1,7 @@
 """Drive two chains (CUDA engine and oracle port) through the same random proposal trace."""
 import numpy as np
 
-from golden_util import rel_err
+from golden_util import rel_err, worse
 from scicone_b200.synth import TreeState, make_counts
 
 
@@ -17,9 +17,9 @@ def run_trace(gpu, cpu, tree, n_moves, tol, kinds=None, check_tables_every=10):
     worst = {"total": 0.0, "t_prime_scores": 0.0, "t_prime_sums": 0.0, "t_scores": 0.0, "od": 0.0, "argmax_mismatch": 0}
     ft = tree.flat()
     a, b = gpu.compute_t_table(ft), cpu.compute_t_table(ft)
-    worst["total"] = max(worst["total"], abs(a - b) / max(1.0, abs(b)))
+    worst["total"] = worse(worst["total"], rel_err(a, b))
     a, b = gpu.compute_t_od_scores(ft.nu), cpu.compute_t_od_scores(ft.nu)
-    worst["od"] = max(worst["od"], abs(a - b) / max(1.0, abs(b)))
+    worst["od"] = worse(worst["od"], rel_err(a, b))
     worst["t_scores"] = rel_err(gpu.read_t_scores(), cpu.read_t_scores())
     kw = {} if kinds is None else {"kinds": kinds}
     n_done = 0
@@ -31,18 +31,18 @@ def run_trace(gpu, cpu, tree, n_moves, tol, kinds=None, check_tables_every=10):
         ft = t2.flat()
         if kind == "nu":
             a, b = gpu.compute_t_prime_od_scores(ft.nu), cpu.compute_t_prime_od_scores(ft.nu)
-            worst["od"] = max(worst["od"], abs(a - b) / max(1.0, abs(b)))
+            worst["od"] = worse(worst["od"], rel_err(a, b))
         for rid in roots:
             idx = ft.index_of(rid)
             gpu.compute_t_prime_scores(ft, idx)
             cpu.compute_t_prime_scores(ft, idx)
         a, b = gpu.compute_t_prime_sums(ft), cpu.compute_t_prime_sums(ft)
-        worst["total"] = max(worst["total"], abs(a - b) / max(1.0, abs(b)))
+        worst["total"] = worse(worst["total"], rel_err(a, b))
         gi, gs = gpu.read_t_prime_scores()
         ci, cs = cpu.read_t_prime_scores()
         assert list(gi) == list(ci), (step, kind, gi, ci)
-        worst["t_prime_scores"] = max(worst["t_prime_scores"], rel_err(gs, cs))
-        worst["t_prime_sums"] = max(worst["t_prime_sums"], rel_err(gpu.read_t_prime_sums(), cpu.read_t_prime_sums()))
+        worst["t_prime_scores"] = worse(worst["t_prime_scores"], rel_err(gs, cs))
+        worst["t_prime_sums"] = worse(worst["t_prime_sums"], rel_err(gpu.read_t_prime_sums(), cpu.read_t_prime_sums()))
         if gpu.max_scoring:
             g_ids, _ = gpu.read_t_prime_maxs()
             c_ids, c_vals = cpu.read_t_prime_maxs()
@@ -69,9 +69,9 @@ def run_trace(gpu, cpu, tree, n_moves, tol, kinds=None, check_tables_every=10):
         n_done += 1
         if n_done % check_tables_every == 0:
             assert list(gpu.t_node_ids()) == list(cpu.t_node_ids())
-            worst["t_scores"] = max(worst["t_scores"], rel_err(gpu.read_t_scores(), cpu.read_t_scores()))
+            worst["t_scores"] = worse(worst["t_scores"], rel_err(gpu.read_t_scores(), cpu.read_t_scores()))
     assert list(gpu.t_node_ids()) == list(cpu.t_node_ids())
-    worst["t_scores"] = max(worst["t_scores"], rel_err(gpu.read_t_scores(), cpu.read_t_scores()))
+    worst["t_scores"] = worse(worst["t_scores"], rel_err(gpu.read_t_scores(), cpu.read_t_scores()))
     for k, v in worst.items():
         if k.startswith("argmax"):
             continue
