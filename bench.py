@@ -5,24 +5,29 @@
     python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU `inference` on the host cores
 
 Workload (BASELINE.json configs[2], the "10k cells" headline): synthetic 10 000 cells x 18 000 bins collapsed to
-200 regions PER GPU, B independent MCMC chains (restarts, as pyscicone's learn_tree_parallel runs them) advanced in
-lock-step on trees of ~50 nodes.  One STEP = one MCMC iteration of every chain = ONE launch of the fused
-score/aggregate/reduce kernel over B proposals (+ the cell-shard all-gather when N > 1).
+200 regions PER GPU, B independent MCMC chains (restarts, as pyscicone's learn_tree_parallel runs them) on trees of ~50
+nodes.  One STEP = one MCMC iteration of every chain.  The run starts from the cells x BINS matrix: the bins -> regions
+collapse (K0, Utils::condense_matrix) runs on the device first and its output - checked against the region-level
+matrix it was expanded from - is the count matrix of everything that follows.
 
 Metric: cell x MCMC-iterations per second ("cell_iters/s" = chain iterations/s x cells), which aggregates over
 cell-sharded GPUs (weak scaling: every rank holds its own 10 000 cells) and over chains, and which the
 reference's `inference` timer yields directly (iterations/s x cells).  Chain iterations/s and cell x node
 attachment scores/s are reported next to it.
 
-  value  device pipeline: proposals (pre-generated valid moves, scicone_b200.synth.TreeState; pre-drawn accept coins)
-         of two groups of chains that take turns on two launch lanes, so a launch is always in flight while the other
-         group is settled and queued; count matrix / score tables / lgamma rows resident in HBM, region timed with CUDA
-         events on the engine's stream.  (`roofline` comes from a first pass with one launch per step on one stream,
-         where the proposal kernel runs alone and its CUDA-event durations are clean.)
-  e2e    the real MCMC: this repo's native host (scicone_b200/bin/inference - the reference's CLI, move set, priors and
-         accept rule on top of the C ABI) runs the same B restarts with the same flags and seeds as the reference arm;
-         every step stages its proposal blobs from host memory, launches, and reads the B totals back before the chains
-         can decide.  Timer = the host's own clock around infer_mcmc, exactly what the reference arm reports.
+  e2e    THE HEADLINE.  The real MCMC: this repo's native host (scicone_b200/bin/inference - the reference's CLI, move
+         set, priors and accept rule on top of the C ABI) runs the same B restarts with the same flags and seeds as the
+         reference arm; every step stages its proposals from host memory, launches, and reads the B totals back before
+         the chains can decide.  Timer = the host's own clock around infer_mcmc, exactly what the reference arm reports.
+         `roofline_e2e` / `roofline_k1` are the kernels' numbers INSIDE this run.
+  value  device pipeline with everything resident in HBM: pre-generated valid proposals (scicone_b200.synth.TreeState,
+         six move kinds at the weights of the reference's default mix, pre-drawn accept coins) driven through the ctypes
+         mirror of the C ABI, region timed with CUDA events on the engine's stream.  `roofline` comes from its first pass
+         (one launch of all chains per step on one stream, where the proposal kernel runs alone).
+  also   `other_configs`: the other named shapes of BASELINE.json through the same native host - configs[1] (1 000 x 50),
+         configs[3] (cluster-tree restarts over the GPUs, scicone_b200/bin/learn_tree), configs[4] (100 000 cells, cell-
+         sharded over the N GPUs) - and for N > 1 `sharded_equals_single`: a 5 000-cell run sharded over the N GPUs must
+         write byte-identical traces to the same run on one GPU.
 """
 import argparse
 import json
@@ -62,9 +67,23 @@ def emit(obj):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
 
 
+def workload_config(args, world):
+    """The workload both arms run - the same dict on both lines."""
+    B, M = args.chains, args.cells
+    resident = (B * (args.nodes + 4) * M * 8 + M * args.regions * 10) / 1e6
+    return {"workload": f"configs[2]: {M} cells x {args.bins} bins -> {args.regions} regions per GPU, {B} chains x "
+                        f"~{args.nodes}-node trees, overdispersed, {'max' if args.max_scoring else 'sum'} scoring, default move mix",
+            "cells_per_gpu": M, "bins": args.bins, "regions": args.regions, "chains": B, "tree_nodes": args.nodes,
+            "max_scoring": int(args.max_scoring), "n_gpus": world,
+            "parallelism": f"cells sharded x{world}" if world > 1 else "1 GPU",
+            "l2": f"inputs larger than L2: ~{resident:.0f} MB of score rows + counts resident per GPU vs 126 MB L2"}
+
+
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(p):
         t = json.load(open(p))
         return t.get("dram_bytes_per_launch"), t.get("source")
@@ -163,8 +182,8 @@ def run_engine(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from scicone_b200.api import BatchLauncher, Chain, Dataset, comm_unique_id
-    from scicone_b200.synth import SEED, make_counts
+    from scicone_b200.api import BatchLauncher, Chain, Dataset, comm_unique_id, condense_matrix
+    from scicone_b200.synth import SEED, expand_to_bins, make_counts
 
     K, W, B = args.steps, args.warmup, args.chains
     M = args.cells
@@ -174,6 +193,21 @@ def run_engine(args):
         shard = make_counts(M, args.bins, args.regions, seed=SEED + 1000 * rank)
         shard["region_sizes"] = data["region_sizes"]
         data = shard if rank > 0 else data
+    # K0: the run starts from cells x bins; the device collapses the bins of every region (Utils::condense_matrix) and the
+    # result - which must equal the region-level matrix the bins were expanded from - is the count matrix of the run
+    k0 = None
+    if not args.no_k0:
+        bins_mat = expand_to_bins(data["D"], data["region_sizes"], seed=SEED + rank)
+        k0_us = []
+        for _ in range(3):
+            D_k0, us = condense_matrix(bins_mat, data["region_sizes"], device=local, return_kernel_us=True)
+            k0_us.append(us)
+        if not np.array_equal(D_k0, data["D"]):
+            raise SystemExit("bench.py: the device bins->regions collapse does not reproduce the region-level matrix")
+        k0_bytes = 8.0 * bins_mat.shape[0] * (bins_mat.shape[1] + args.regions)
+        k0 = {"us": float(np.median(k0_us)), "alg_bytes": k0_bytes, "rows": int(bins_mat.shape[0]), "bins": int(bins_mat.shape[1])}
+        data["D"] = D_k0
+        del bins_mat
     ds = Dataset(data["D"], data["region_sizes"], neutral_states=data["neutral_states"], cluster_sizes=data["cluster_sizes"],
                  is_overdispersed=1, max_scoring=args.max_scoring, device=local, cell_offset=rank * M, n_cells_global=world * M)
     if world > 1:
@@ -301,15 +335,29 @@ def run_engine(args):
     gc.enable()
 
     # ---------------- e2e: the native MCMC host on the same matrix (all ranks: cell-sharded run of ONE set of chains)
-    host = None if args.no_e2e else run_native_host(args, data, rank, world, local, dist if world > 1 else None, comm_unique_id)
-    e2e_s = host["wall_us"] * 1e-6 if host else float("nan")
+    dd = dist if world > 1 else None
+    host = None if args.no_e2e else run_native_host(args, data, rank, world, local, dd, comm_unique_id, profile_kernels=True)
+    timed = None if args.no_e2e else run_native_host(args, data, rank, world, local, dd, comm_unique_id, profile_kernels=False)
+    e2e_s = timed["wall_us"] * 1e-6 if timed else float("nan")
+    if host and timed:
+        host["wall_us_with_kernel_events"] = host["wall_us"]
+        for key in ("wall_us", "h2d_bytes", "d2h_bytes", "accepted", "rejected", "gpu_launches", "launches", "launched_chains", "host_threads"):
+            host[key] = timed[key]
     clocks = sampler.stop() if sampler else None
+    others = None if (args.no_e2e or args.no_other_configs) else other_configs(args, rank, world, local, dd, comm_unique_id)
+    equal = sharded_equals_single(rank, world, local, dist, comm_unique_id) if (world > 1 and not args.no_e2e) else None
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, kern_us], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, kern_us, k0["us"] if k0 else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, kern_us = (float(x) for x in t.cpu())
+        dev_ms, e2e_s, kern_us, k0_us_max = (float(x) for x in t.cpu())
+        if k0:
+            k0["us"] = k0_us_max
+        if host:  # the kernels' times inside the e2e run: max over ranks as well
+            t = torch.tensor([host["score_kernel_us"], host["build_kernel_us"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            host["score_kernel_us"], host["build_kernel_us"] = (float(x) for x in t.cpu())
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -320,38 +368,62 @@ def run_engine(args):
         e2e = iters * cells_total / e2e_s
         if host is None:  # profiling runs (--no_e2e): placeholders, never a bench line
             host = {"h2d_bytes": 0, "d2h_bytes": 0, "host_threads": 0, "accepted": 0, "rejected": 0, "gpu_launches": 0,
-                    "score_kernel_us": 0.0, "build_kernel_us": 0.0}
+                    "score_kernel_us": 0.0, "build_kernel_us": 0.0, "alg_bytes": 0.0, "build_alg_bytes": 0.0, "build_lgamma": 0.0,
+                    "score_kernel_launches": 0, "build_kernel_launches": 0, "launches": 0, "launched_chains": 0}
         achieved = cnt_dev["alg_bytes"] / (kern_us * 1e-6) / 1e9 if kern_us > 0 else 0.0
-        resident = ds.device_bytes()
+
+        def roof(alg_bytes, us, **more):
+            gbs = alg_bytes / (us * 1e-6) / 1e9 if us > 0 else 0.0
+            return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, **more}
+
         out = {
             "metric": "mcmc_cell_iters_per_s", "value": value, "unit": "cell_iters/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"configs[2]: {M} cells x {args.bins} bins -> {args.regions} regions per GPU, "
-                                   f"{B} chains x ~{args.nodes}-node trees, overdispersed, "
-                                   f"{'max' if args.max_scoring else 'sum'} scoring, default move mix",
-                       "cells_per_gpu": M, "regions": args.regions, "chains": B, "tree_nodes": args.nodes,
-                       "max_scoring": int(args.max_scoring), "parallelism": f"cells sharded x{world}" if world > 1 else "1 GPU",
-                       "proposal_source": "value: pre-generated valid proposals (scicone_b200.synth.TreeState), accept prob 0.3, "
-                                          + value_pass + f" (one stream: {one_lane_ms / K:.4f} ms/step"
-                                          + (f", two lanes: {two_lane_ms / K:.4f} ms/step" if two_lane_ms is not None else "") + "); "
-                                          + "e2e: real MCMC (native host)",
-                       "l2": f"inputs larger than L2: {resident / 1e6:.0f} MB of score/lgamma rows + counts resident vs 126 MB L2"},
+            "config": workload_config(args, world),
+            "value_how": "device pipeline, inputs resident in HBM: pre-generated valid proposals (scicone_b200.synth.TreeState: "
+                         "prune/reattach, swap, add/remove, insert, delete, nu at equal weights - the reference's default mix has "
+                         "condense/split in place of a second insert/delete), accept prob 0.3; " + value_pass
+                         + f" (one stream: {one_lane_ms / K:.4f} ms/step"
+                         + (f", two lanes: {two_lane_ms / K:.4f} ms/step" if two_lane_ms is not None else "") + ")",
             "mcmc_iters_per_s": iters / (dev_ms * 1e-3),
             "scores_per_s": cnt_dev["n_scores"] * world / (dev_ms * 1e-3),
-            "e2e": {"value": e2e, "unit": "cell_iters/s", "mcmc_iters_per_s": iters / e2e_s, "ms_per_step": 1e3 * e2e_s / K,
+            "e2e": {"value": e2e, "unit": "cell_iters/s", "mcmc_iters_per_s": iters / e2e_s, "mcmc_iters_per_s_per_chain": K / e2e_s,
+                    "ms_per_step": 1e3 * e2e_s / K,
                     "h2d_bytes_per_step": host["h2d_bytes"] / K, "d2h_bytes_per_step": host["d2h_bytes"] / K,
                     "what": "scicone_b200/bin/inference (native MCMC host on the C ABI): real moves + Metropolis-Hastings, "
-                            f"{B} restarts (seeds 42..), {host['host_threads']} host threads, timer around infer_mcmc",
+                            f"{B} restarts (seeds 42..), {host['host_threads']} host threads per rank, timer around infer_mcmc; the warm-up "
+                            "iterations are a phase of the same call (all chains stop at the mark, nothing in flight, then the clock starts)",
                     "accepted": host["accepted"], "rejected": host["rejected"], "gpu_launches": host["gpu_launches"],
-                    "score_kernel_us_per_step": host["score_kernel_us"] / K, "build_kernel_us_per_step": host["build_kernel_us"] / K},
+                    "launches": host["launches"], "proposals_per_launch": host["launched_chains"] / max(1, host["launches"]),
+                    "score_kernel_us_per_step": host["score_kernel_us"] / K, "build_kernel_us_per_step": host["build_kernel_us"] / K,
+                    "kernel_times_from": "a second identical run (same seeds, same trajectories) with CUDA events around every kernel; that run took "
+                                         f"{host.get('wall_us_with_kernel_events', 0) * 1e-3 / K:.4f} ms per step"},
             "gpu_launches": int(launches_dev),
-            "roofline": {"bound": "hbm", "kernel": "score_proposals_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "alg_bytes_per_launch": cnt_dev["alg_bytes"] / max(1, n_timed),
-                         "avg_launch_us": kern_us / max(1, n_timed), "kernel_share_of_step": kern_us * 1e-3 / one_lane_ms,
-                         "measured_in": "pass 1: one launch of all chains per step on one stream (the kernel runs alone); "
-                                        f"{one_lane_ms / K:.4f} ms per step there"},
+            "roofline": roof(cnt_dev["alg_bytes"], kern_us, kernel="score_proposals_kernel", traffic=traffic, traffic_source=traffic_src,
+                             peak_source=peak_src, alg_bytes_per_launch=cnt_dev["alg_bytes"] / max(1, n_timed),
+                             avg_launch_us=kern_us / max(1, n_timed), kernel_share_of_step=kern_us * 1e-3 / one_lane_ms,
+                             bytes_model="SURVEY.md 8d: 16 + 8 E_n per rescored cell x node, 8 N + 12 per cell aggregate; "
+                                         "nu move / full pass: 8 K + 16 N + 12 per cell",
+                             measured_in="value pass 1: one launch of all chains per step on one stream (the kernel runs alone); "
+                                         f"{one_lane_ms / K:.4f} ms per step there"),
+            # the same kernel inside the REAL MCMC (launches of ~10 proposals, two to three in flight, other kernels beside it)
+            "roofline_e2e": roof(host["alg_bytes"], host["score_kernel_us"], kernel="score_proposals_kernel",
+                                 launches=host["score_kernel_launches"],
+                                 avg_launch_us=host["score_kernel_us"] / max(1, host["score_kernel_launches"]),
+                                 measured_in="e2e run: CUDA events around every launch of the proposal kernel, summed (max over ranks)"),
+            # K1a + K1b (tables and increments of the proposals that rescore the whole tree, root-score slices)
+            "roofline_k1": roof(host["build_alg_bytes"], host["build_kernel_us"], kernel="build_tables_kernel + build_slices_kernel",
+                                launches=host["build_kernel_launches"], lgamma_per_s=host["build_lgamma"] / (host["build_kernel_us"] * 1e-6)
+                                if host["build_kernel_us"] > 0 else 0.0,
+                                bytes_model="per rescored node of a tabulated proposal and cell: 8 written + 2 (count index) or 8 (count) read per "
+                                            "event; per root-score slice and cell: 8 written + 2 or 8 per region",
+                                measured_in="e2e run: CUDA events around K1a + K1b of every launch that has them"),
+            "roofline_k0": roof(k0["alg_bytes"], k0["us"], kernel="condense_rows_kernel", rows=k0["rows"], bins=k0["bins"], kernel_us=k0["us"],
+                                bytes_model="8 n_bins read + 8 K written per row",
+                                measured_in="dataset set-up of this run: median of 3 collapses of the rank's cells x bins matrix, CUDA events") if k0 else None,
+            "other_configs": others,
+            "sharded_equals_single": equal,
             "clocks": clocks,
         }
         out["cpu_baseline"] = cpu_baseline(args, data) if world == 1 and not args.no_cpu_baseline else None
@@ -362,59 +434,215 @@ def run_engine(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_native_host(args, data, rank, world, local, dist, comm_unique_id):
-    """Real MCMC through the C ABI: scicone_b200/bin/inference with the reference arm's flags, B restarts in one process
-    per GPU.  With world > 1 the ranks' matrices are stacked into one (world x cells)-cell matrix and every rank's host
-    takes its chunk-aligned block of rows (cells sharded, tree replicated, NCCL all-gather of the chunk sums)."""
+def host_run(tag, D_full, region_sizes, rank, world, local, dist, comm_unique_id, n_chains, n_nodes, steps, warmup, max_scoring, nu,
+             extra=(), cluster_sizes=None, ranks=None):
+    """One run of scicone_b200/bin/inference (the native MCMC host on the C ABI) over `world` GPUs - every rank starts its own
+    process on its own device, cells sharded, tree replicated - or, with ranks=[0], on rank 0's GPU alone while the others
+    wait.  D_full is only read on rank 0 (it writes the matrix to a directory all ranks of the box see).  Returns the
+    stats JSON of this rank's process (None on ranks that did not run)."""
     exe = os.path.join(ROOT, "scicone_b200", "bin", "inference")
     if not os.path.exists(exe):
         raise SystemExit("bench.py: scicone_b200/bin/inference is missing - run __graft_entry__.build()")
-    M, Kr = data["D"].shape
+    solo = ranks is not None
+    w_run = 1 if solo else world
+    if world > 1:
+        box = [tempfile.mkdtemp(prefix=f"scicone_{tag}_") if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        tmp = box[0]
+        uid = [comm_unique_id().hex() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        shape = [tuple(D_full.shape) if rank == 0 else None]
+        dist.broadcast_object_list(shape, src=0)
+        n_rows, Kr = shape[0]
+    else:
+        tmp, uid = tempfile.mkdtemp(prefix=f"scicone_{tag}_"), [None]
+        n_rows, Kr = D_full.shape
+    try:
+        d = os.path.join(tmp, "d.f64")
+        r = os.path.join(tmp, "r.txt")
+        wf = os.path.join(tmp, "w.txt")
+        if rank == 0:
+            np.ascontiguousarray(D_full, dtype="<f8").tofile(d)
+            np.savetxt(r, region_sizes, fmt="%d")
+            if cluster_sizes is not None:
+                np.savetxt(wf, cluster_sizes, fmt="%d")
+        if world > 1:
+            dist.barrier()
+        out = None
+        if not solo or rank in ranks:
+            stats = os.path.join(tmp, f"stats{rank}.json")
+            cmd = [exe, f"--d_matrix_file={d}", f"--region_sizes_file={r}", f"--n_cells={n_rows}", f"--n_regions={Kr}",
+                   f"--n_iters={steps}", f"--warmup_iters={warmup}", f"--n_nodes={n_nodes}", "--seed=42", f"--nu={nu}",
+                   "--verbosity=0", "--no_cnv_file=1", f"--max_scoring={'true' if max_scoring else 'false'}", f"--postfix={tag}{rank}",
+                   f"--n_chains={n_chains}", f"--device={local}", f"--stats_file={stats}", "--stats_all_ranks=1"]
+            if cluster_sizes is not None:
+                cmd.append(f"--cluster_sizes_file={wf}")
+            if w_run > 1:  # rank 0 composes the launches, the other ranks replay its launch log
+                cmd += ["--schedule=dynamic", f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"]
+            cmd += list(extra)
+            env = dict(os.environ)
+            if w_run > 1:  # the host cores are shared by the ranks
+                env.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+            res = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, env=env)
+            if res.returncode != 0:
+                raise SystemExit(f"bench.py: native host failed ({tag}):\n" + res.stdout[-2000:] + res.stderr[-2000:])
+            out = json.load(open(stats))
+        if world > 1:
+            dist.barrier()
+        return out
+    finally:
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_native_host(args, data, rank, world, local, dist, comm_unique_id, profile_kernels):
+    """The e2e leg: real MCMC on the bench workload.  With world > 1 the ranks' matrices are stacked into one (world x
+    cells)-cell matrix and every rank's host takes its chunk-aligned block of rows.  profile_kernels: CUDA events around
+    every kernel (three event records per launch, and the collect waits for the kernel to retire instead of for its
+    results) - the timed run goes without, a second identical run (same seeds, same trajectories) yields the per-kernel times."""
+    full = data["D"]
     if world > 1:
         import torch
 
         mine = torch.from_numpy(np.ascontiguousarray(data["D"])).cuda()
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
-        full = torch.cat(parts).cpu().numpy()
-        box = [tempfile.mkdtemp(prefix="scicone_e2e_") if rank == 0 else None]
+        full = torch.cat(parts).cpu().numpy() if rank == 0 else None
+    extra = args.host_args.split() + [f"--profile_kernels={1 if profile_kernels else 0}"]
+    if args.n_groups:
+        extra += [f"--n_groups={args.n_groups}", "--schedule=static"]
+    return host_run("e2e", full, data["region_sizes"], rank, world, local, dist, comm_unique_id, args.chains, args.nodes - 1, args.steps,
+                    args.warmup, args.max_scoring, args.nu, extra=extra)
+
+
+def max_over_ranks(dist, world, x):
+    if world == 1:
+        return x
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.cpu()[0])
+
+
+def other_configs(args, rank, world, local, dist, comm_unique_id):
+    """The other named shapes of BASELINE.json through the same native host, each a short real-MCMC run (same K and W):
+    configs[1] 1 000 cells x 10 000 bins -> 50 regions (N = 1 only), configs[3] cluster-tree restarts spread over the N
+    GPUs by scicone_b200/bin/learn_tree (replicas only, no collective), configs[4] 100 000 cells x 20 000 bins -> 200 regions,
+    cell-sharded over the N GPUs (strong scaling: the same matrix on 1 GPU is timed beside it)."""
+    from scicone_b200.synth import SEED, make_counts
+
+    K, W = args.steps, args.warmup
+    out = {}
+    noprof = ["--profile_kernels=0"]  # timed runs: no CUDA events around the kernels
+
+    def record(st, wall_s, n_chains, n_cells, n_gpus, **more):
+        rec = {"mcmc_iters_per_s": n_chains * K / wall_s, "cell_iters_per_s": n_chains * K * n_cells / wall_s, "ms_per_step": 1e3 * wall_s / K,
+               "chains": n_chains, "cells": n_cells, "n_gpus": n_gpus, "steps": K, "warmup": W}
+        if st is not None:
+            rec.update({"accepted": st["accepted"], "rejected": st["rejected"], "launches": st["launches"], "alg_bytes_per_step": st["alg_bytes"] / K})
+        rec.update(more)
+        return rec
+
+    if world == 1:
+        d1 = make_counts(1000, 10000, 50, seed=SEED + 11)
+        st = host_run("c1", d1["D"], d1["region_sizes"], rank, world, local, dist, comm_unique_id, args.chains, 49, K, W, args.max_scoring, args.nu, extra=noprof)
+        out["configs[1]"] = record(st, st["wall_us"] * 1e-6, args.chains, 1000, 1, what="1 000 cells x 10 000 bins -> 50 regions, 50-node trees")
+    # configs[4]
+    n4, c4 = 100000, 16
+    d4 = make_counts(n4, 20000, 200, seed=SEED + 14) if rank == 0 else None
+    D4 = d4["D"] if rank == 0 else None
+    r4 = d4["region_sizes"] if rank == 0 else None
+    if world > 1:
+        box = [r4]
         dist.broadcast_object_list(box, src=0)
-        tmp = box[0]
-        uid = [comm_unique_id().hex() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-    else:
-        full, tmp, uid = data["D"], tempfile.mkdtemp(prefix="scicone_e2e_"), [None]
+        r4 = box[0]
+    st1 = host_run("c4one", D4, r4, rank, world, local, dist, comm_unique_id, c4, 49, K, W, args.max_scoring, args.nu, ranks=[0], extra=noprof)
+    one_s = max_over_ranks(dist, world, st1["wall_us"] * 1e-6 if st1 else 0.0)
+    rec = {"what": "100 000 cells x 20 000 bins -> 200 regions, 16 chains, 50-node trees; strong scaling of ONE matrix",
+           "one_gpu": record(st1, one_s, c4, n4, 1) if rank == 0 else None}
+    if world > 1:
+        stn = host_run("c4", D4, r4, rank, world, local, dist, comm_unique_id, c4, 49, K, W, args.max_scoring, args.nu, extra=noprof)
+        n_s = max_over_ranks(dist, world, stn["wall_us"] * 1e-6)
+        rec["sharded"] = record(stn, n_s, c4, n4, world)
+        rec["speedup_vs_one_gpu"] = one_s / n_s
+        rec["strong_scaling_efficiency"] = one_s / n_s / world
+    out["configs[4]"] = rec
+    # configs[3]: cluster-tree mode - condensed centroids with cluster_sizes, many restarts in parallel across the GPUs
+    if rank == 0:
+        d3 = make_counts(10000, 18000, 200, seed=SEED + 13, cluster_rows=40)
+        tmp = tempfile.mkdtemp(prefix="scicone_c3_")
+        try:
+            np.ascontiguousarray(d3["D"], dtype="<f8").tofile(os.path.join(tmp, "d.f64"))
+            np.savetxt(os.path.join(tmp, "r.txt"), d3["region_sizes"], fmt="%d")
+            np.savetxt(os.path.join(tmp, "w.txt"), d3["cluster_sizes"], fmt="%d")
+            n_reps, iters = 32 * world, 2000
+            cmd = [os.path.join(ROOT, "scicone_b200", "bin", "learn_tree"), f"--n_reps={n_reps}", f"--n_gpus={world}", "--max_tries=1",
+                   "--postfix=c3", "--d_matrix_file=d.f64", "--region_sizes_file=r.txt", "--cluster_sizes_file=w.txt",
+                   f"--n_cells={d3['D'].shape[0]}", "--n_regions=200", f"--n_iters={iters}", "--n_nodes=10", f"--nu={args.nu}", "--verbosity=1",
+                   "--no_cnv_file=1", f"--max_scoring={'true' if args.max_scoring else 'false'}"]
+            t0 = time.perf_counter()
+            res = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+            wall = time.perf_counter() - t0
+            if res.returncode != 0:
+                raise SystemExit("bench.py: learn_tree failed:\n" + res.stdout[-2000:] + res.stderr[-2000:])
+            times = [int(x) * 1e-6 for x in re.findall(r"Time taken by infer_mcmc function: (\d+) microseconds", res.stdout)]
+            lt = json.load(open(os.path.join(tmp, "c3_learn_tree.json")))
+            out["configs[3]"] = {"what": f"cluster-tree mode: 10 000 cells condensed to {d3['D'].shape[0]} centroids with cluster_sizes, {n_reps} restarts x "
+                                         f"{iters} iterations over {world} GPU(s) by bin/learn_tree (replicas only); best-of-N + robustness as pyscicone",
+                                 "mcmc_iters_per_s": n_reps * iters / max(times) if times else None, "process_wall_s": wall, "restarts": n_reps,
+                                 "iters_per_restart": iters, "n_gpus": world, "robustness": lt["robustness"], "best_score": lt["best_score"],
+                                 "best_restart": lt["best_rep"]}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    if world > 1:
+        dist.barrier()
+    return out
+
+
+def sharded_equals_single(rank, world, local, dist, comm_unique_id):
+    """The N-GPU parity check of tests/test_gpu_multi.py inside the bench (the GPU test box has one GPU): the same 6 chains on
+    5 000 cells on ONE GPU and cell-sharded over the N GPUs must write byte-identical traces and final trees."""
+    from scicone_b200.synth import make_counts
+
+    exe = os.path.join(ROOT, "scicone_b200", "bin", "inference")
+    n_cells = 1024 * max(5, world) - 120  # every rank gets at least one 1024-cell chunk, the last one ragged
+    box = [tempfile.mkdtemp(prefix="scicone_eq_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    tmp = box[0]
+    uid = [comm_unique_id().hex() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    n_chains = 6
+    common = [exe, "--d_matrix_file=d.f64", "--region_sizes_file=r.txt", f"--n_cells={n_cells}", "--n_regions=60", "--n_iters=300", "--n_nodes=12",
+              "--seed=5", "--nu=1.0", "--verbosity=2", "--max_scoring=true", f"--n_chains={n_chains}", "--schedule=dynamic", "--min_batch=2", "--no_cnv_file=1"]
+    ok = True
     try:
-        d = os.path.join(tmp, "d.f64")
-        r = os.path.join(tmp, "r.txt")
         if rank == 0:
-            np.ascontiguousarray(full, dtype="<f8").tofile(d)
-            np.savetxt(r, data["region_sizes"], fmt="%d")
-        if world > 1:
-            dist.barrier()
-        stats = os.path.join(tmp, f"stats{rank}.json")
-        cmd = [exe, f"--d_matrix_file={d}", f"--region_sizes_file={r}", f"--n_cells={full.shape[0]}", f"--n_regions={Kr}",
-               f"--n_iters={args.steps}", f"--warmup_iters={args.warmup}", f"--n_nodes={args.nodes - 1}", "--seed=42", f"--nu={args.nu}",
-               "--verbosity=0", "--no_cnv_file=1", f"--max_scoring={'true' if args.max_scoring else 'false'}", f"--postfix=e2e{rank}",
-               f"--n_chains={args.chains}", f"--device={local}", f"--stats_file={stats}", "--stats_all_ranks=1"]
-        if args.n_groups:
-            cmd += [f"--n_groups={args.n_groups}", "--schedule=static"]
-        elif world > 1:  # rank 0 composes the launches, the other ranks replay its launch log
-            cmd.append("--schedule=dynamic")
-        if world > 1:
-            cmd += [f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"]
-        cmd += args.host_args.split()
+            data = make_counts(n_cells, 9000, 60, seed=31)
+            np.ascontiguousarray(data["D"], dtype="<f8").tofile(os.path.join(tmp, "d.f64"))
+            np.savetxt(os.path.join(tmp, "r.txt"), data["region_sizes"], fmt="%d")
+            one = subprocess.run(common + ["--postfix=one", f"--device={local}"], cwd=tmp, capture_output=True, text=True)
+            ok = one.returncode == 0
+        dist.barrier()
         env = dict(os.environ)
-        if world > 1:  # the host cores are shared by the ranks
-            env.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
-        res = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, env=env)
-        if res.returncode != 0:
-            raise SystemExit("bench.py: native host failed:\n" + res.stdout[-2000:] + res.stderr[-2000:])
-        out = json.load(open(stats))
-        if world > 1:
-            dist.barrier()
-        return out
+        env.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+        res = subprocess.run(common + [f"--postfix=shard{rank}", f"--device={local}", f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"],
+                             cwd=tmp, capture_output=True, text=True, env=env)
+        flag = [res.returncode == 0]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, flag)
+        ok = ok and all(g[0] for g in gathered)
+        if rank == 0 and ok:
+            for c in range(n_chains):  # chain c is searched (and its traces written) by rank c % world
+                for name in ("acceptance_ratio.csv", "markov_chain.csv", "gamma_values.csv", "tree_inferred.txt"):
+                    a = open(os.path.join(tmp, f"one_c{c}_{name}")).read()
+                    b = open(os.path.join(tmp, f"shard{c % world}_c{c}_{name}")).read()
+                    ok = ok and a == b
+        out = [ok]
+        dist.broadcast_object_list(out, src=0)
+        return bool(out[0])
     finally:
+        dist.barrier()
         if rank == 0:
             shutil.rmtree(tmp, ignore_errors=True)
 
@@ -490,6 +718,9 @@ def cpu_baseline(args, data):
 
 
 def run_reference(args):
+    """The reference arm: the UNMODIFIED reference `inference` (oracle/_ref) on the box's host cores, on OUR arm's config -
+    the same matrix shape, the same number of chains (one single-threaded process per chain, all running at once: the
+    reference is one chain per process and pyscicone runs restarts exactly so), the same seeds, flags and metric."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
@@ -499,7 +730,7 @@ def run_reference(args):
     M = args.cells * world  # our arm's config at N GPUs: every GPU holds args.cells cells
     data = make_counts(M, args.bins, args.regions, seed=SEED)
     cores = os.cpu_count() or 1
-    n_procs = max(1, min(cores, args.chains))
+    n_procs = max(1, args.chains)
     K, W = args.steps, args.warmup
     # one "step" = a bounded sample: every process advances its chain by `iters_per_step` iterations
     iters_per_step = max(1, args.ref_iters_per_step)
@@ -513,15 +744,13 @@ def run_reference(args):
     wall = time.perf_counter() - t0
     v = res["iters_per_s"] * M
     sample = (f"{n_procs} concurrent restarts (seeds 42..) of the unmodified reference `inference` (oracle/_ref, -O3 -fopenmp, no ASan), "
-              f"OMP_NUM_THREADS=1 each, {iters_per_step * K} iterations each on {M} cells x {args.regions} regions, "
-              f"random {args.nodes}-node start trees; rate = iterations / max infer_mcmc time")
+              f"OMP_NUM_THREADS=1 each on {cores} cores, {iters_per_step * K} iterations each on {M} cells x {args.regions} regions, "
+              f"random {args.nodes}-node start trees; rate = chains x iterations / max infer_mcmc time")
     out = {"impl": "reference", "metric": "mcmc_cell_iters_per_s", "value": v, "unit": "cell_iters/s", "n_gpus": world, "steps": K,
            "warmup": W, "ms_per_step": 1e3 * res["mcmc_s_max"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"configs[2]: {M} cells x {args.bins} bins -> {args.regions} regions, {n_procs} chains x "
-                                  f"{args.nodes}-node trees, overdispersed, {'max' if args.max_scoring else 'sum'} scoring, default move mix",
-                      "cells": M, "regions": args.regions, "chains": n_procs, "tree_nodes": args.nodes},
-           "mcmc_iters_per_s": res["iters_per_s"], "wall_s": wall,
+           "config": workload_config(args, world),
+           "mcmc_iters_per_s": res["iters_per_s"], "mcmc_iters_per_s_per_chain": res["iters_per_s"] / n_procs, "wall_s": wall,
            "cpu_baseline": {"value": v, "unit": "cell_iters/s", "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": v, "unit": "cell_iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -545,6 +774,8 @@ def main():
     ap.add_argument("--ref_iters_per_step", type=int, default=1)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true", help="skip the native-host run (profiling passes only)")
+    ap.add_argument("--no_k0", action="store_true", help="start from the region-level matrix (profiling passes only)")
+    ap.add_argument("--no_other_configs", action="store_true", help="skip the configs[1]/[3]/[4] sub-records")
     ap.add_argument("--host_args", default="", help="extra flags for the native host, space separated (tuning runs)")
     ap.add_argument("--n_groups", type=int, default=0, help="chain groups of the native host's static schedule (cell-sharded runs)")
     args = ap.parse_args()

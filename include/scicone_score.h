@@ -247,6 +247,9 @@ int scicone_read_t_prime_sums(scicone_chain* ch, double* out /* [n_cells] */);
 int scicone_read_t_prime_maxs(scicone_chain* ch, int32_t* ids, double* vals);
 /* t_prime_scores: rescored node ids (ascending) and their [n_cells][n_rescored] matrix. */
 int scicone_t_prime_n_rescored(scicone_chain* ch, int32_t* n);
+/* Relative device cost of the compiled (or imported) proposal of `ch`: about 2 per rescored node + 0.5 per unchanged node.
+   A scheduler can use it to keep whole-tree rescorings (nu moves) out of the launches of the small proposals. */
+int scicone_t_prime_cost(scicone_chain* ch, double* cost);
 int scicone_read_t_prime_scores(scicone_chain* ch, int32_t* ids, double* out);
 
 /*
@@ -317,6 +320,10 @@ int scicone_build_time_stats(scicone_dataset* ds, double* sum_us, uint64_t* n_ti
 int scicone_kernel_launches(scicone_dataset* ds, uint64_t* n);
 /* out = {bytes staged host->device, device->host, algorithmic bytes, cell x node scores} of all launches */
 int scicone_counters(scicone_dataset* ds, double out[4], int32_t reset);
+/* out = {algorithmic bytes, lgamma evaluations} of the table / increment kernels (K1a, K1b) of all launches: per rescored node
+   of a tabulated proposal and cell 8 bytes written + 2 (count index) or 8 (count) read per event; per root-score slice
+   and cell 8 written + 2 or 8 per region */
+int scicone_build_counters(scicone_dataset* ds, double out[2], int32_t reset);
 /* CUDA events on the dataset's stream bracketing a timed region (which = 0 start, 1 end). */
 int scicone_region_mark(scicone_dataset* ds, int32_t which);
 int scicone_region_elapsed_ms(scicone_dataset* ds, double* ms);

@@ -174,6 +174,7 @@ int scicone_read_t_maxs(scicone_chain* ch, int32_t* ids, double* v) { orc_read_t
 int scicone_read_t_prime_sums(scicone_chain* ch, double* out) { orc_read_t_prime_sums(ch->ctx, out); return 0; }
 int scicone_read_t_prime_maxs(scicone_chain* ch, int32_t* ids, double* v) { orc_read_t_prime_maxs(ch->ctx, ids, v); return 0; }
 int scicone_t_prime_n_rescored(scicone_chain* ch, int32_t* n) { *n = orc_t_prime_n_rescored(ch->ctx); return 0; }
+int scicone_t_prime_cost(scicone_chain*, double* cost) { *cost = 1.0; return 0; }
 int scicone_read_t_prime_scores(scicone_chain* ch, int32_t* ids, double* out) { orc_read_t_prime_scores(ch->ctx, ids, out); return 0; }
 int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int32_t* ids, int32_t* cn) { orc_assign_cells_to_nodes(ch->ctx, t, ids, cn); return 0; }
 int scicone_comm_unique_id(uint8_t*) { return fail(-5, "cpu backend: no communicator"); }
@@ -205,6 +206,7 @@ int scicone_set_profiling(scicone_dataset*, int32_t) { return 0; }
 int scicone_last_kernel_time_us(scicone_dataset*, double* us) { *us = 0; return 0; }
 int scicone_kernel_time_stats(scicone_dataset*, double* s, uint64_t* n, int32_t) { if (s) *s = 0; if (n) *n = 0; return 0; }
 int scicone_build_time_stats(scicone_dataset*, double* s, uint64_t* n) { if (s) *s = 0; if (n) *n = 0; return 0; }
+int scicone_build_counters(scicone_dataset*, double out[2], int32_t) { out[0] = out[1] = 0; return 0; }
 int scicone_kernel_launches(scicone_dataset*, uint64_t* n) { *n = 0; return 0; }
 int scicone_parallel_for(int32_t n, void (*fn)(int32_t, void*), void* ctx) { scicone::ForkJoinPool::instance().run(n, fn, ctx); return 0; }
 int scicone_test_lgamma(int32_t, const double*, int32_t, double*) { return fail(-2, "cpu backend: no device lgamma"); }

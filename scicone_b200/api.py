@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "scicone_t_node_ids", "scicone_read_t_scores", "scicone_read_t_sums", "scicone_read_t_maxs",
     "scicone_read_t_prime_sums", "scicone_read_t_prime_maxs", "scicone_t_prime_n_rescored",
     "scicone_read_t_prime_scores", "scicone_assign_cells_to_nodes", "scicone_comm_unique_id",
-    "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_build_time_stats", "scicone_kernel_launches",
+    "scicone_dataset_attach_comm", "scicone_set_profiling", "scicone_last_kernel_time_us", "scicone_kernel_time_stats", "scicone_build_time_stats", "scicone_build_counters", "scicone_t_prime_cost", "scicone_kernel_launches",
     "scicone_counters", "scicone_region_mark", "scicone_region_elapsed_ms", "scicone_device_bytes",
     "scicone_parallel_for", "scicone_host_threads", "scicone_test_lgamma", "scicone_prepare_t_prime",
     "scicone_batch_compute_t_prime_scores", "scicone_batch_settle", "scicone_condense_matrix", "scicone_batch_poll", "scicone_set_streams", "scicone_condense_clusters",
@@ -105,6 +105,7 @@ def lib():
         L.scicone_batch_wait.argtypes = [vp, C.c_uint64, dp, dp]
         L.scicone_kernel_time_stats.argtypes = [vp, dp, C.POINTER(C.c_uint64), C.c_int32]
         L.scicone_build_time_stats.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
+        L.scicone_build_counters.argtypes = [vp, dp, C.c_int32]
         L.scicone_counters.argtypes = [vp, dp, C.c_int32]
         L.scicone_region_mark.argtypes = [vp, C.c_int32]
         L.scicone_region_elapsed_ms.argtypes = [vp, dp]
@@ -245,6 +246,11 @@ class Dataset:
         out = np.zeros(4)
         _check(lib().scicone_counters(self._h, _dp(out), int(reset)))
         return dict(h2d_bytes=out[0], d2h_bytes=out[1], alg_bytes=out[2], n_scores=out[3])
+
+    def build_counters(self, reset=False):
+        out = np.zeros(2)
+        _check(lib().scicone_build_counters(self._h, _dp(out), int(reset)))
+        return dict(alg_bytes=out[0], n_lgamma=out[1])
 
     def region_mark(self, which):
         _check(lib().scicone_region_mark(self._h, int(which)))

@@ -14,7 +14,7 @@
 //                      (one per tree node and chain), per-cell aggregates and argmax ids, root-score slices.  Proposals
 //                      refer to rows by index only, so a compiled proposal is valid on every rank of a cell-sharded run.
 //   gather buffer (multi-GPU)  flags + per-rank chunk sums, mapped into every rank, written over NVLink by the last
-//                      CTA of a launch (finish_reduction), read by wait_flags_kernel + one copy to the host
+//                      CTA of a launch (finish_reduction), read and added up by gather_totals_kernel, which writes the totals into pinned host memory
 //
 // Three kernels per batch of proposals:
 //   build_tables_kernel (K1a) + build_increments_kernel (K1b)  for every rescored (cell, node): score(node) -
@@ -92,6 +92,12 @@ struct LaunchParams {
     unsigned* counter;   // [slots] arrival counters of the last-CTA reduction
     unsigned* status;    // [slots] bit 0: NaN aggregate
     int n_cta, n_red_chunks, cs_stride, n_props;
+    // single-GPU datasets: the results go straight into pinned host memory (no copy, no event): totals [slots][2], status
+    // [slots], then the launch's ticket in *h_flag once every proposal of the launch is in
+    double* h_total;
+    unsigned* h_status;
+    unsigned long long* h_flag;
+    unsigned long long ticket;
     // cell-sharded datasets (xchg_world > 0): the chunk sums of the whole launch go straight into every rank's gather
     // buffer over NVLink (peer memory), see finish_reduction
     unsigned* launch_counter;               // proposals of this launch whose reduction has finished
@@ -203,7 +209,7 @@ __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
 // into the gather buffer of every rank (peer memory: 16-byte NVLink stores, all threads) and then publishes the launch
 // number in this rank's flag word on every rank - one release at system scope per peer after a CTA barrier, so a rank
 // that sees the flag sees the sums.  No collective kernel runs and no GPU waits for another one here: only the reader of
-// the sums does (wait_flags_kernel).
+// the sums does (gather_totals_kernel).
 __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum1, unsigned slot, const LaunchParams& P) {
     __shared__ int role;  // 0: nothing left to do, 1: last CTA of the proposal, 2: ... and of the launch
     __shared__ double smem_chunks[kThreads];
@@ -244,6 +250,28 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
         if (threadIdx.x == 0) P.total[(size_t)slot * 2 + v] = grand;
     }
     if (threadIdx.x == 0) P.counter[slot] = 0u;
+    if (P.h_flag) {
+        // host-visible results: the CTA that finishes the LAST proposal of the launch copies every total and status word of
+        // the launch into pinned host memory, then - one fence at system scope later - the launch's ticket
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();  // this proposal's totals are visible before the launch counter moves
+            const unsigned done = atomicAdd(P.launch_counter, 1u);
+            role = (done == (unsigned)P.n_props - 1) ? 2 : 1;
+        }
+        __syncthreads();
+        if (role != 2) return;
+        __threadfence();
+        for (int q = threadIdx.x; q < 2 * P.n_props; q += kThreads) P.h_total[q] = __ldcg(P.total + q);
+        for (int q = threadIdx.x; q < P.n_props; q += kThreads) P.h_status[q] = __ldcg(P.status + q);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *P.launch_counter = 0u;
+            *reinterpret_cast<volatile unsigned long long*>(P.h_flag) = P.ticket;
+        }
+        return;
+    }
     if (P.xchg_world == 0) return;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -268,11 +296,18 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
     }
 }
 
-// Reader side of the exchange: one warp waits until every rank has published launch `seq` on this lane (flags[world]);
-// the copy of the gathered sums to the host follows it on the stream.  A rank that never arrives is reported through the
-// status word (bit 1) after `timeout_ns` instead of hanging the GPU.
-__global__ void wait_flags_kernel(const unsigned long long* flags, int world, unsigned long long seq, unsigned* status,
-                                  unsigned long long timeout_ns) {
+// Reader side of the exchange: one CTA waits until every rank has published launch `seq` on this lane (flags[world]), then
+// adds, per proposal, the chunk sums of all ranks in GLOBAL chunk order (rank 0's chunks, rank 1's, ... - shards are whole
+// chunks in cell order, so this is the order a single GPU adds them in and the total does not depend on the number of
+// GPUs) and writes totals, status words and the launch's ticket straight into pinned host memory.
+// A rank that never arrives is reported through status bit 1 after `timeout_ns` instead of hanging the GPU.
+__global__ void __launch_bounds__(128) gather_totals_kernel(const unsigned long long* flags, int world, unsigned long long seq, const double* gathered,
+                                                            long long rank_stride, int n_props, int chunks_per_rank, const unsigned* status_dev,
+                                                            double* h_total, unsigned* h_status, unsigned long long* h_flag,
+                                                            unsigned long long ticket, unsigned long long timeout_ns) {
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (int idx = threadIdx.x; idx < world; idx += blockDim.x) {
@@ -286,13 +321,27 @@ __global__ void wait_flags_kernel(const unsigned long long* flags, int world, un
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
                 if (t - t0 > timeout_ns) {
-                    atomicOr(status, 2u);
-                    return;
+                    timed_out = 1;
+                    break;
                 }
             }
             __nanosleep(100);
         }
     }
+    __syncthreads();
+    __threadfence_system();
+    for (int idx = threadIdx.x; idx < 2 * n_props; idx += blockDim.x) {
+        double v = 0.0;
+        for (int rk = 0; rk < world; ++rk) {
+            const volatile double* c = gathered + rk * rank_stride + (long long)idx * chunks_per_rank;
+            for (int q = 0; q < chunks_per_rank; ++q) v += c[q];
+        }
+        h_total[idx] = v;
+    }
+    for (int idx = threadIdx.x; idx < n_props; idx += blockDim.x) h_status[idx] = __ldcg(status_dev + idx) | (timed_out && idx == 0 ? 2u : 0u);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(h_flag) = ticket;
 }
 
 // ---------------------------------------------------------------------------------
@@ -658,31 +707,76 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
 
     constexpr int kBatch = 8;  // rows in flight per thread in the aggregate phases
     double contrib = 0.0, contrib_od = 0.0;
+    const int n_unch = H.n_unch;
+    const DevUnch* unch = reinterpret_cast<const DevUnch*>(blob + H.off_unch);
+    // Max scoring, Inference.h:1086-1152: a cell whose previous argmax was rescored or deleted needs the first maximum of
+    // the UNCHANGED rows in ascending id order.  Few cells do (those attached inside the moved subtree), but most warps
+    // hold one: the warp scans for them together - lane l reads rows l, l + 32, ... of the cell's column (independent
+    // loads, four cells per round), then a shuffle reduction picks the maximum, equal values going to the lower id (the
+    // rows are listed in ascending id order, so that is the first one).
+    double rescan_val = 0.0;
+    int rescan_id = 0;
+    if (kMax && !(pflags & (PROP_OD_ONLY | PROP_FULL)) && n_unch > 0) {  // uniform over the CTA
+        const bool need = live && (prev_in_new || pm == H.deleted_id);
+        unsigned todo = __ballot_sync(0xffffffffu, need);
+        const int lane = tid & 31;
+        const double* const warp_rows = P.rows + (blockIdx.x * kCells + (tid & ~31));
+        constexpr int kCellsPerRound = 4;
+        while (todo) {
+            int src[kCellsPerRound];
+#pragma unroll
+            for (int c = 0; c < kCellsPerRound; ++c) {
+                src[c] = todo ? __ffs(todo) - 1 : -1;
+                if (todo) todo &= todo - 1;
+            }
+            double best[kCellsPerRound];
+            int bid[kCellsPerRound];
+#pragma unroll
+            for (int c = 0; c < kCellsPerRound; ++c) {
+                best[c] = -DBL_MAX;
+                bid[c] = 0x7fffffff;
+            }
+            for (int u = lane; u < n_unch; u += 32) {
+                const DevUnch un = unch[u];
+                const long long at = (long long)un.row * stride;
+                double v[kCellsPerRound];
+#pragma unroll
+                for (int c = 0; c < kCellsPerRound; ++c) v[c] = src[c] >= 0 ? __ldcg(warp_rows + at + src[c]) : -DBL_MAX;
+#pragma unroll
+                for (int c = 0; c < kCellsPerRound; ++c)
+                    if (v[c] > best[c]) {
+                        best[c] = v[c];
+                        bid[c] = un.id;
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < kCellsPerRound; ++c) {
+                if (src[c] < 0) continue;  // uniform over the warp
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best[c], o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bid[c], o);
+                    if (ov > best[c] || (ov == best[c] && oi < bid[c])) {
+                        best[c] = ov;
+                        bid[c] = oi;
+                    }
+                }
+                if (lane == src[c] && best[c] > -DBL_MAX) {
+                    rescan_val = best[c];
+                    rescan_id = bid[c];
+                }
+            }
+        }
+    }
     if (live && !(pflags & PROP_OD_ONLY)) {
         // ---- per-cell aggregate: Inference::compute_t_prime_sums ----
-        const int n_unch = H.n_unch;
-        const DevUnch* unch = reinterpret_cast<const DevUnch*>(blob + H.off_unch);
         double res;
         if (kMax) {  // Inference.h:1086-1152
             int prev_id = pm;
             double prev_val = agg_old;
-            if (prev_in_new || pm == H.deleted_id) {
-                // the previous argmax was rescored or deleted: first maximum of the unchanged rows in ascending id order
-                double cur = -DBL_MAX;
-                int uid = 0;
-                for (int u0 = 0; u0 < n_unch; u0 += kBatch) {
-                    double v[kBatch];
-#pragma unroll
-                    for (int q = 0; q < kBatch; ++q) v[q] = u0 + q < n_unch ? __ldcg(rows + (long long)unch[u0 + q].row * stride) : -DBL_MAX;
-#pragma unroll
-                    for (int q = 0; q < kBatch; ++q)
-                        if (v[q] > cur) {
-                            cur = v[q];
-                            uid = unch[u0 + q].id;
-                        }
-                }
-                prev_id = uid;
-                prev_val = cur > -DBL_MAX ? cur : 0.0;  // value-initialised std::pair when nothing is unchanged
+            if (prev_in_new || pm == H.deleted_id) {  // value-initialised std::pair when nothing is unchanged
+                prev_id = rescan_id;
+                prev_val = rescan_val;
             }
             res = new_max;
             int rid = new_id;

@@ -28,6 +28,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -375,7 +376,7 @@ struct scicone_dataset {
     int* d_lut = nullptr;
     std::vector<int> lut;
     bool all_tab = false;    // every row has a table: K1b needs no direct lgamma evaluation
-    double* d_tables[2] = {nullptr, nullptr};  // per lane: value tables of the launch in flight
+    double* d_tables[4] = {nullptr, nullptr, nullptr, nullptr};  // per lane: value tables of the launch in flight
     size_t tables_cap = 0;                     // doubles per lane
     int* dW = nullptr;
     cudaStream_t stream = nullptr;
@@ -387,11 +388,14 @@ struct scicone_dataset {
         unsigned char* h_arena = nullptr;
         double* h_total = nullptr;     // pinned [slots][2]
         unsigned* h_status = nullptr;  // pinned [slots]
+        unsigned long long* h_flag = nullptr;  // pinned: ticket of the launch whose results are in h_total / h_status
         double* h_gather = nullptr;    // pinned [world][slots][2][max_chunks_rank]
         cudaEvent_t evb = nullptr, ev0 = nullptr, ev1 = nullptr, done = nullptr;
         int n = 0, n_items = 0;
         std::vector<char> with_od;
         bool busy = false;
+        bool direct = false;  // the kernel writes totals, status and the ticket into this segment's pinned buffers
+        bool summed = false;  // cell-sharded: h_total already holds the sums over all ranks (gather_totals_kernel)
         unsigned long long ticket = 0;
         int lane = 0;
         std::vector<unsigned> temp_rows;  // rows that only live for this launch: back to the pool when it is collected
@@ -403,10 +407,10 @@ struct scicone_dataset {
     // are serialised by the stream, so accept / reject may be issued before the wait.  Two lanes (scicone_set_streams):
     // consecutive launches alternate lanes and overlap on the device; the caller must then collect a launch before it
     // settles its chains.
-    static constexpr int kLanes = 2;
+    static constexpr int kLanes = 4;
     int n_lanes = 1;
-    cudaStream_t lane_stream[kLanes] = {nullptr, nullptr};
-    unsigned char* d_arena[kLanes] = {nullptr, nullptr};
+    cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned char* d_arena[kLanes] = {nullptr, nullptr, nullptr, nullptr};
     size_t arena_cap = 0;
     // per batch slot: reduction scratch and results
     int n_cta = 0, n_chunks = 0;
@@ -420,7 +424,7 @@ struct scicone_dataset {
     unsigned* d_launch_counter = nullptr;  // [lanes]
     // multi-GPU
     void* comm = nullptr;
-    void* comm_lane1 = nullptr;  // second lane: a communicator of its own (ncclCommSplit of `comm`), see scicone_set_streams
+    void* comm_lane[4] = {nullptr, nullptr, nullptr, nullptr};  // lanes 1..: a communicator of their own (ncclCommSplit of `comm`), see scicone_set_streams
     int rank = 0, world = 1;
     int max_chunks_rank = 0;
     double* d_gather = nullptr;  // NCCL variant, per lane: [world][slots][2][max_chunks_rank]
@@ -434,7 +438,7 @@ struct scicone_dataset {
     std::vector<void*> xchg_peer;                     // base of rank p's buffer in this process (own: xchg)
     double** d_xchg_data_tab = nullptr;               // device: [kLanes][2][world] where this rank writes in rank p's buffer
     unsigned long long** d_xchg_flag_tab = nullptr;   // device: [kLanes][world]
-    unsigned long long lane_seq[kLanes] = {0, 0};     // launches submitted per lane (the value published in the flags)
+    unsigned long long lane_seq[kLanes] = {0, 0, 0, 0};     // launches submitted per lane (the value published in the flags)
     size_t xchg_flag_bytes() const { return round_up(sizeof(unsigned long long) * kLanes * world, 16); }
     size_t xchg_block() const { return (size_t)SCICONE_MAX_SHARDED_BATCH * 2 * max_chunks_rank; }  // doubles of one rank in one (lane, parity) block
     unsigned long long* xchg_flags(void* base, int lane, int rk) const {
@@ -445,12 +449,14 @@ struct scicone_dataset {
     }
     // profiling
     bool profiling = false;
+    bool direct_results = true;  // SCICONE_DIRECT_RESULTS=0: results travel by a stream-ordered copy + event instead
     double last_kernel_us = 0.0, sum_kernel_us = 0.0, sum_build_us = 0.0;
     unsigned long long n_timed = 0, n_build_timed = 0;
     unsigned long long n_launches = 0;
     // bookkeeping for the bench: bytes staged per direction, algorithmic bytes / scores of the launched proposals
     unsigned long long h2d_bytes = 0, d2h_bytes = 0;
     double alg_bytes = 0.0, n_scores = 0.0;
+    double k1_bytes = 0.0, k1_lgamma = 0.0;  // K1a / K1b: algorithmic bytes and lgamma evaluations
     cudaEvent_t region_ev[2] = {nullptr, nullptr};
 
     int set_device() const {
@@ -458,8 +464,8 @@ struct scicone_dataset {
         return SCICONE_OK;
     }
     int sync_lanes() {  // every queued launch on every lane has finished
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        if (lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(lane_stream[1]));
+        for (int l = 0; l < kLanes; ++l)
+            if (lane_stream[l]) CUDA_TRY(cudaStreamSynchronize(lane_stream[l]));
         return SCICONE_OK;
     }
     int ensure_arena(size_t bytes) {
@@ -530,8 +536,10 @@ struct scicone_dataset {
         CUDA_TRY(cudaMemset(d_total, 0, lane_result_bytes * kLanes));
         CUDA_TRY(cudaMemset(d_chunk, 0, sizeof(double) * all * 2 * cs_stride));
         for (Segment& g : seg) {
-            CUDA_TRY(cudaMallocHost(&g.h_total, lane_result_bytes));
+            CUDA_TRY(cudaMallocHost(&g.h_total, lane_result_bytes + 16));
             g.h_status = reinterpret_cast<unsigned*>(g.h_total + (size_t)ns * 2);
+            g.h_flag = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(g.h_total) + lane_result_bytes);
+            *g.h_flag = 0ull;
         }
         slots = ns;
         if (world > 1) {
@@ -963,11 +971,20 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     const unsigned long long tk = ds->next_ticket;
     scicone_dataset::Segment& g = ds->seg[tk % scicone_dataset::kRing];
     if (g.busy) return fail(SCICONE_ERR_STATE, "more than %d launches outstanding: collect a ticket first", scicone_dataset::kRing);
-    const int lane = ds->n_lanes > 1 ? (int)(tk % ds->n_lanes) : 0;
-    if (ds->n_lanes > 1)  // a lane's slots and arena are reused by every second launch: the previous one must have been collected
+    // A lane's slots, arena and table arena belong to one launch at a time.  Cell-sharded datasets: launch k goes to lane
+    // k mod n_lanes on every rank (the gather buffers are per lane), so launches must be collected in order; one GPU: any
+    // free lane, so a short launch can be collected, and its lane reused, while a long one is still running.
+    int lane = 0;
+    if (ds->n_lanes > 1) {
+        bool used[scicone_dataset::kLanes] = {false, false, false, false};
         for (scicone_dataset::Segment& o : ds->seg)
-            if (o.busy && o.lane == lane) return fail(SCICONE_ERR_STATE, "two launches outstanding on one lane: collect a ticket first");
-    cudaStream_t st = lane == 0 ? ds->stream : ds->lane_stream[1];
+            if (o.busy) used[o.lane] = true;
+        lane = (int)(tk % ds->n_lanes);
+        if (ds->world == 1)
+            for (int l = 0; l < ds->n_lanes && used[lane]; ++l) lane = l;
+        if (used[lane]) return fail(SCICONE_ERR_STATE, "every launch lane has a launch outstanding: collect a ticket first");
+    }
+    cudaStream_t st = ds->lane_stream[lane];
     unsigned char* d_arena = ds->d_arena[lane];
     g.lane = lane;
     if (ds->world > 1 && n > SCICONE_MAX_SHARDED_BATCH)
@@ -995,6 +1012,22 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     const int K = ds->K;
     const int s_range = lut[2 * K + 1];
     size_t tab_at = 0;
+    // SCICONE_TABLES=0: every lgamma term is evaluated directly in K1b (2 per event and cell) and K1a does not run - measured
+    // on configs[2] this is a wash for launches of small proposals (one kernel less, 8 x the lgamma work: 142 against 144 us
+    // per MCMC iteration of 32 chains) and a loss for nu moves, so tables are the default; the switch stays as a test hook.
+    static const int tables_mode = [] {
+        const char* e = getenv("SCICONE_TABLES");
+        return e ? atoi(e) : -1;
+    }();
+    std::vector<char> direct_chain(n, 0);
+    bool any_direct = false;
+    for (int i = 0; i < n; ++i) {
+        size_t n_ev = 0;
+        for (const DevItem& it : chains[i]->items)
+            if (it.kind == ITEM_NODE_OD) n_ev += (size_t)it.n_ev;
+        direct_chain[i] = tables_mode == 0;
+        any_direct = any_direct || (direct_chain[i] && n_ev > 0);
+    }
     for (int pass = 0; pass < 2; ++pass) {
         size_t chain_aux = off_aux;
         for (int i = 0; i < n; ++i) {
@@ -1010,11 +1043,11 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
                 if (it.kind == ITEM_NODE_OD) {
                     DevEvent* ev = reinterpret_cast<DevEvent*>(g.h_arena + it.aux_off);
                     for (int e = 0; e < it.n_ev; ++e) {
-                        const int range = lut[2 * ev[e].k + 1];
+                        const int range = direct_chain[i] ? 0 : lut[2 * ev[e].k + 1];
                         ev[e].tab = range > 0 ? (unsigned)tab_at : kNoRow;
                         tab_at += (size_t)range;
                     }
-                    if (s_range > 0) {
+                    if (s_range > 0 && !direct_chain[i]) {
                         it.g_tab = (unsigned)tab_at;
                         tab_at += 2 * (size_t)s_range;
                     }
@@ -1031,6 +1064,31 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
                         tab_at += (size_t)range;
                     }
                     slices_laid_out = true;
+                }
+                {   // bookkeeping for the bench (scicone_build_counters): bytes K1b moves per cell, lgamma evaluations of K1a / K1b
+                    const double M = (double)ds->M;
+                    if (it.kind == ITEM_NODE_OD) {
+                        const DevEvent* ev = reinterpret_cast<const DevEvent*>(g.h_arena + it.aux_off);
+                        for (int e = 0; e < it.n_ev; ++e) {
+                            const int range = ev[e].tab != kNoRow ? lut[2 * ev[e].k + 1] : 0;
+                            ds->k1_bytes += M * (range > 0 ? 2.0 : 8.0);
+                            ds->k1_lgamma += 2.0 * (range > 0 ? range : M);
+                        }
+                        ds->k1_bytes += M * (8.0 + (it.g_tab != kNoRow ? 2.0 : 8.0));
+                        ds->k1_lgamma += 2.0 * (it.g_tab != kNoRow ? s_range : M);
+                    } else if (it.kind == ITEM_NODE_MN)
+                        ds->k1_bytes += M * (16.0 + 8.0 * it.n_ev);
+                    else if (it.kind == ITEM_G_ROW) {
+                        ds->k1_bytes += M * (8.0 + (s_range > 0 ? 2.0 : 8.0));
+                        ds->k1_lgamma += s_range > 0 ? s_range : M;
+                    } else {
+                        ds->k1_bytes += M * 8.0;
+                        for (int k = it.k0; k < it.k1; ++k) {
+                            const int range = it.kind == ITEM_SLICE_OD ? lut[2 * k + 1] : 0;
+                            ds->k1_bytes += M * (range > 0 ? 2.0 : 8.0);
+                            if (it.kind == ITEM_SLICE_OD) ds->k1_lgamma += range > 0 ? range : M;  // one table per region and chain, or one evaluation per cell
+                        }
+                    }
                 }
                 memcpy(g.h_arena + item_at, &it, sizeof it);
                 item_at += sizeof it;
@@ -1078,6 +1136,13 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         P.xchg_seq = seq;
         P.xchg_world = ds->world;
     }
+    const bool direct_results = ds->world == 1 && ds->direct_results;
+    if (direct_results) {
+        P.h_total = g.h_total;
+        P.h_status = g.h_status;
+        P.h_flag = g.h_flag;
+        P.ticket = tk;
+    }
     P.off_items = (unsigned)off_items;
     P.n_items = (int)n_items;
     if (n_items) {
@@ -1088,7 +1153,7 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
             ds->n_launches++;
         }
         const dim3 bgrid((ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells), (unsigned)n_items);
-        if (ds->all_tab)
+        if (ds->all_tab && !any_direct)
             build_increments_kernel<false><<<bgrid, kBuildBlock, 0, st>>>(P);
         else
             build_increments_kernel<true><<<bgrid, kBuildBlock, 0, st>>>(P);
@@ -1107,31 +1172,35 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, st));
     CUDA_TRY(cudaGetLastError());
     ds->n_launches++;
+    bool gathered_direct = false;
     if (ds->world > 1 && ds->xchg_on) {
-        // The proposal kernel has stored this rank's chunk sums into every rank's gather buffer and published its flag;
-        // wait for the flags of all ranks, then bring the gathered sums of the n proposals to the host.  Every rank adds
-        // all chunks in global chunk order, so the total does not depend on the number of GPUs.
+        // The proposal kernel has stored this rank's chunk sums into every rank's gather buffer and published its flag; one
+        // small kernel waits for the flags of all ranks, adds all chunks in global chunk order (so the total does not depend
+        // on the number of GPUs) and writes the n totals, the status words and the ticket into this
+        // launch's pinned host buffers: no copy, no event.
         const unsigned long long seq = ds->lane_seq[lane];
-        wait_flags_kernel<<<1, 32, 0, st>>>(ds->xchg_flags(ds->xchg, lane, 0), ds->world, seq, ds->lane_status(lane), 60ull * 1000000000ull);
+        gather_totals_kernel<<<1, 128, 0, st>>>(ds->xchg_flags(ds->xchg, lane, 0), ds->world, seq, ds->xchg_data(ds->xchg, lane, (int)(seq & 1), 0),
+                                                (long long)ds->xchg_block(), n, ds->max_chunks_rank, ds->lane_status(lane), g.h_total, g.h_status,
+                                                g.h_flag, tk, 60ull * 1000000000ull);
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
-        const size_t width = sizeof(double) * (size_t)n * 2 * ds->max_chunks_rank;
-        CUDA_TRY(cudaMemcpy2DAsync(g.h_gather, width, ds->xchg_data(ds->xchg, lane, (int)(seq & 1), 0), sizeof(double) * ds->xchg_block(), width,
-                                   (size_t)ds->world, cudaMemcpyDeviceToHost, st));
+        gathered_direct = true;
     } else if (ds->world > 1) {
         // the same exchange as an NCCL all-gather of the chunk sums (every rank's slots are zero-padded to the same width)
         double* d_gather = ds->d_gather + (size_t)lane * ds->gather_cap * ds->world;
         const size_t cnt = (size_t)n * 2 * ds->max_chunks_rank;
-        int nrc = g_nccl.AllGather(ds->lane_chunk(lane), d_gather, cnt, kNcclDouble, lane == 0 ? ds->comm : ds->comm_lane1, st);
+        int nrc = g_nccl.AllGather(ds->lane_chunk(lane), d_gather, cnt, kNcclDouble, lane == 0 ? ds->comm : ds->comm_lane[lane], st);
         if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?");
         CUDA_TRY(cudaMemcpyAsync(g.h_gather, d_gather, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, st));
-    } else
+    } else if (!direct_results)
         CUDA_TRY(cudaMemcpyAsync(g.h_total, ds->lane_total(lane), ds->lane_result_bytes, cudaMemcpyDeviceToHost, st));
-    if (ds->world > 1)
+    if (ds->world > 1 && !gathered_direct)
         CUDA_TRY(cudaMemcpyAsync(g.h_status, ds->lane_status(lane), sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(g.done, st));
+    g.direct = direct_results || gathered_direct;
+    g.summed = gathered_direct;
+    if (!g.direct) CUDA_TRY(cudaEventRecord(g.done, st));
     ds->h2d_bytes += bytes;
-    ds->d2h_bytes += (ds->world > 1 ? sizeof(double) * 2 * n * ds->max_chunks_rank * ds->world : sizeof(double) * 2 * n) + sizeof(unsigned) * n;
+    ds->d2h_bytes += (ds->world > 1 && !gathered_direct ? sizeof(double) * 2 * n * ds->max_chunks_rank * ds->world : sizeof(double) * 2 * n) + sizeof(unsigned) * n;
     for (int i = 0; i < n; ++i) {
         scicone_chain* ch = chains[i];
         ds->alg_bytes += ch->alg_bytes;
@@ -1156,12 +1225,30 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
 int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* totals, double* od_scores) {
     scicone_dataset::Segment& g = ds->seg[ticket % scicone_dataset::kRing];
     if (!g.busy || g.ticket != ticket) return fail(SCICONE_ERR_STATE, "unknown or already collected ticket %llu", ticket);
-    CUDA_TRY(cudaEventSynchronize(g.done));
+    if (g.direct) {
+        // the last CTA of the launch (or, cell-sharded, the gather kernel) publishes the ticket after the totals (system-scope
+        // fences): spin on it, and look at the stream from time to time so that a failed launch is reported, not waited for
+        volatile unsigned long long* flag = g.h_flag;
+        unsigned spins = 0;
+        while (*flag != ticket) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((++spins & 0xffffu) == 0) {
+                cudaError_t e = cudaStreamQuery(ds->lane_stream[g.lane]);
+                if (e != cudaSuccess && e != cudaErrorNotReady) return fail(SCICONE_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+                if (e == cudaSuccess && *flag != ticket) return fail(SCICONE_ERR_CUDA, "the launch finished without publishing its results");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else
+        CUDA_TRY(cudaEventSynchronize(g.done));
     g.busy = false;
     ds->pool.put_many(g.temp_rows, 0);
     const int n = g.n;
     if (ds->profiling) {
         float ms = 0.f;
+        if (g.direct) CUDA_TRY(cudaEventSynchronize(g.ev1));  // the results are published before the kernel has retired
         CUDA_TRY(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
         ds->last_kernel_us = 1e3 * ms;
         ds->sum_kernel_us += ds->last_kernel_us;
@@ -1175,7 +1262,7 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
     bool nan = false;
     for (int i = 0; i < n; ++i) {
         double v[2] = {0.0, 0.0};
-        if (ds->world > 1) {
+        if (ds->world > 1 && !g.summed) {
             for (int q2 = 0; q2 < 2; ++q2)
                 for (int rk = 0; rk < ds->world; ++rk) {
                     const double* c = g.h_gather + (((size_t)rk * n + i) * 2 + q2) * ds->max_chunks_rank;
@@ -1190,11 +1277,11 @@ int wait_proposals(scicone_dataset* ds, unsigned long long ticket, double* total
         if (g.h_status[i] & 1u) nan = true;
     }
     if (ds->world > 1 && (g.h_status[0] & 2u)) {
-        CUDA_TRY(cudaMemsetAsync(ds->lane_status(g.lane), 0, sizeof(unsigned) * ds->slots, g.lane == 0 ? ds->stream : ds->lane_stream[1]));
+        CUDA_TRY(cudaMemsetAsync(ds->lane_status(g.lane), 0, sizeof(unsigned) * ds->slots, ds->lane_stream[g.lane]));
         return fail(SCICONE_ERR_COMM, "a rank did not publish its chunk sums within 60 s (launches must be submitted in the same order on all ranks)");
     }
     if (nan) {
-        CUDA_TRY(cudaMemsetAsync(ds->lane_status(g.lane), 0, sizeof(unsigned) * ds->slots, g.lane == 0 ? ds->stream : ds->lane_stream[1]));
+        CUDA_TRY(cudaMemsetAsync(ds->lane_status(g.lane), 0, sizeof(unsigned) * ds->slots, ds->lane_stream[g.lane]));
         return fail(SCICONE_ERR_NAN, "a per-cell aggregate is NaN (reference: assert(!isnan), Inference.h:1150,1191)");
     }
     return SCICONE_OK;
@@ -1237,7 +1324,8 @@ int od_scores(scicone_chain* ch, double nu, double* out) {
 }
 
 int gather_rows(scicone_dataset* ds, const std::vector<unsigned>& rows, double* out) {
-    if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
+    for (int l = 1; l < scicone_dataset::kLanes; ++l)
+        if (ds->lane_stream[l]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[l]));
     const int n = (int)rows.size();
     if (n == 0 || ds->M == 0) return SCICONE_OK;
     unsigned* d_rows = nullptr;
@@ -1262,7 +1350,8 @@ int gather_rows(scicone_dataset* ds, const std::vector<unsigned>& rows, double* 
 template <class T>
 int read_row(scicone_dataset* ds, unsigned row, T* out, size_t n) {
     if (row == kNoRow) return fail(SCICONE_ERR_STATE, "the chain holds no such table on this rank");
-    if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
+    for (int l = 1; l < scicone_dataset::kLanes; ++l)
+        if (ds->lane_stream[l]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[l]));
     CUDA_TRY(cudaMemcpyAsync(out, ds->pool.base_ptr() + (size_t)row * ds->Mp, sizeof(T) * n, cudaMemcpyDeviceToHost, ds->stream));
     CUDA_TRY(cudaStreamSynchronize(ds->stream));
     return SCICONE_OK;
@@ -1412,6 +1501,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
         DS_TRY(cudaGetLastError());
     }
 #undef DS_TRY
+    if (const char* e = getenv("SCICONE_DIRECT_RESULTS")) ds->direct_results = atoi(e) != 0;
     int rc = ds->ensure_slots(64);
     if (rc) return cleanup(rc);
     rc = ds->ensure_arena(size_t(4) << 20);
@@ -1426,14 +1516,16 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     if (!ds) return;
     cudaSetDevice(ds->device);
     if (ds->stream) cudaStreamSynchronize(ds->stream);
-    if (ds->lane_stream[1]) cudaStreamSynchronize(ds->lane_stream[1]);
+    for (int l = 1; l < scicone_dataset::kLanes; ++l)
+        if (ds->lane_stream[l]) cudaStreamSynchronize(ds->lane_stream[l]);
     for (int p = 0; p < (int)ds->xchg_peer.size(); ++p)
         if (p != ds->rank && ds->xchg_peer[p]) cudaIpcCloseMemHandle(ds->xchg_peer[p]);
     // the exported buffer itself is NOT freed here: another rank may still have it mapped, and freeing exported memory
     // before every importer has closed it is undefined; it goes away with the process (a sharded dataset lives as long
     // as its host process does)
     cudaFree(ds->d_xchg_data_tab); cudaFree(ds->d_xchg_flag_tab);
-    if (ds->comm_lane1 && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm_lane1);
+    for (void* c : ds->comm_lane)
+        if (c && g_nccl.CommDestroy) g_nccl.CommDestroy(c);
     if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm);
     ds->pool.destroy();
     cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW); cudaFree(ds->d_lut); cudaFree(ds->dIt); cudaFree(ds->dSi);
@@ -1452,7 +1544,8 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     }
     for (cudaEvent_t e : ds->region_ev)
         if (e) cudaEventDestroy(e);
-    if (ds->lane_stream[1]) cudaStreamDestroy(ds->lane_stream[1]);
+    for (int l = 1; l < scicone_dataset::kLanes; ++l)
+        if (ds->lane_stream[l]) cudaStreamDestroy(ds->lane_stream[l]);
     if (ds->stream) cudaStreamDestroy(ds->stream);
     delete ds;
 }
@@ -1507,7 +1600,8 @@ void scicone_chain_destroy(scicone_chain* ch) {
     scicone_dataset* ds = ch->ds;
     cudaSetDevice(ds->device);
     cudaStreamSynchronize(ds->stream);
-    if (ds->lane_stream[1]) cudaStreamSynchronize(ds->lane_stream[1]);
+    for (int l = 1; l < scicone_dataset::kLanes; ++l)
+        if (ds->lane_stream[l]) cudaStreamSynchronize(ds->lane_stream[l]);
     if (!ch->follower) {
         drop_pending(ch);
         for (auto& kv : ch->t) ch->row_put(kv.second.row);
@@ -1730,6 +1824,10 @@ int scicone_batch_poll(scicone_dataset* ds, uint64_t ticket, int32_t* done) {
     if (!ds || !done) return fail(SCICONE_ERR_ARG, "batch_poll: null argument");
     scicone_dataset::Segment& g = ds->seg[ticket % scicone_dataset::kRing];
     if (!g.busy || g.ticket != ticket) return fail(SCICONE_ERR_STATE, "unknown or already collected ticket %llu", (unsigned long long)ticket);
+    if (g.direct) {
+        *done = *static_cast<volatile unsigned long long*>(g.h_flag) == ticket ? 1 : 0;
+        return SCICONE_OK;
+    }
     cudaError_t e = cudaEventQuery(g.done);
     if (e != cudaSuccess && e != cudaErrorNotReady) return fail(SCICONE_ERR_CUDA, "batch_poll: %s", cudaGetErrorString(e));
     *done = e == cudaSuccess ? 1 : 0;
@@ -1881,6 +1979,12 @@ int scicone_t_prime_n_rescored(scicone_chain* ch, int32_t* n) {
     *n = (int32_t)ch->p.size();
     return SCICONE_OK;
 }
+int scicone_t_prime_cost(scicone_chain* ch, double* cost) {
+    if (!ch || !cost) return fail(SCICONE_ERR_ARG, "null argument");
+    if (!ch->compiled) return fail(SCICONE_ERR_STATE, "no compiled proposal");
+    *cost = ch->cost;
+    return SCICONE_OK;
+}
 int scicone_read_t_prime_scores(scicone_chain* ch, int32_t* ids, double* out) {
     if (!ch || !out) return fail(SCICONE_ERR_ARG, "null argument");
     if (!ch->evaluated) return fail(SCICONE_ERR_STATE, "no evaluated proposal");
@@ -1903,7 +2007,8 @@ int scicone_assign_cells_to_nodes(scicone_chain* ch, const scicone_tree* t, int3
     if (ch->t.empty()) return fail(SCICONE_ERR_STATE, "assign_cells_to_nodes before compute_t_table");
     rc = ds->set_device();
     if (rc) return rc;
-    if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));
+    for (int l = 1; l < scicone_dataset::kLanes; ++l)
+        if (ds->lane_stream[l]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[l]));
     const int n = (int)ch->t.size(), M = ds->M, K = ds->K;
     std::vector<unsigned> rows;
     std::vector<int> ids;
@@ -1992,7 +2097,7 @@ int scicone_condense_matrix(int32_t device, const double* D_bins, int64_t n_cell
         if (e != cudaSuccess) break;
         const long long groups = (rows + kK0Rows - 1) / kK0Rows;
         cudaEventRecord(e0, st);
-        condense_rows_kernel<<<(unsigned)std::min<long long>(groups, 3ll * n_sm), kK0Threads, kK0SmemBytes, st>>>(
+        condense_rows_kernel<<<(unsigned)std::min<long long>(groups, (long long)n_sm), kK0Threads, kK0SmemBytes, st>>>(
             d_bins, rows, n_bins, n_used, d_off, d_first, n_regions, n_tiles, d_out);
         cudaEventRecord(e1, st);
         e = cudaGetLastError();
@@ -2207,20 +2312,24 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
 }
 
 int scicone_set_streams(scicone_dataset* ds, int32_t n) {
-    if (!ds || n < 1 || n > scicone_dataset::kLanes) return fail(SCICONE_ERR_ARG, "set_streams: 1 or 2 streams");
+    if (!ds || n < 1 || n > scicone_dataset::kLanes) return fail(SCICONE_ERR_ARG, "set_streams: 1 to %d streams", scicone_dataset::kLanes);
     int rc = ds->set_device();
     if (rc) return rc;
     rc = ds->sync_lanes();
     if (rc) return rc;
     for (scicone_dataset::Segment& g : ds->seg)
         if (g.busy) return fail(SCICONE_ERR_STATE, "set_streams with launches outstanding");
-    if (n > 1 && !ds->lane_stream[1]) CUDA_TRY(cudaStreamCreateWithFlags(&ds->lane_stream[1], cudaStreamNonBlocking));
-    if (n > 1 && ds->world > 1 && !ds->xchg_on && !ds->comm_lane1) {
-        // cell-sharded: the all-gathers of the two lanes run concurrently, each lane needs its own communicator.  Collective:
+    for (int l = 1; l < n; ++l)
+        if (!ds->lane_stream[l]) CUDA_TRY(cudaStreamCreateWithFlags(&ds->lane_stream[l], cudaStreamNonBlocking));
+    if (n > 1 && ds->world > 1 && !ds->xchg_on) {
+        // cell-sharded: the all-gathers of the lanes run concurrently, each lane needs its own communicator.  Collective:
         // every rank calls scicone_set_streams at the same point, and all ranks submit their launches in the same order.
         if (!g_nccl.CommSplit) return fail(SCICONE_ERR_COMM, "set_streams: this NCCL has no ncclCommSplit (needs >= 2.18)");
-        int nrc = g_nccl.CommSplit(ds->comm, 0, ds->rank, &ds->comm_lane1, nullptr);
-        if (nrc != 0 || !ds->comm_lane1) return fail(SCICONE_ERR_COMM, "ncclCommSplit failed (%d)", nrc);
+        for (int l = 1; l < n; ++l) {
+            if (ds->comm_lane[l]) continue;
+            int nrc = g_nccl.CommSplit(ds->comm, 0, ds->rank, &ds->comm_lane[l], nullptr);
+            if (nrc != 0 || !ds->comm_lane[l]) return fail(SCICONE_ERR_COMM, "ncclCommSplit failed (%d)", nrc);
+        }
     }
     ds->n_lanes = n;
     return SCICONE_OK;
@@ -2264,12 +2373,20 @@ int scicone_counters(scicone_dataset* ds, double out[4], int32_t reset) {
     }
     return SCICONE_OK;
 }
+int scicone_build_counters(scicone_dataset* ds, double out[2], int32_t reset) {
+    if (!ds || !out) return fail(SCICONE_ERR_ARG, "null argument");
+    out[0] = ds->k1_bytes;
+    out[1] = ds->k1_lgamma;
+    if (reset) ds->k1_bytes = ds->k1_lgamma = 0.0;
+    return SCICONE_OK;
+}
 int scicone_region_mark(scicone_dataset* ds, int32_t which) {
     if (!ds || which < 0 || which > 1) return fail(SCICONE_ERR_ARG, "region_mark: bad argument");
     int rc = ds->set_device();
     if (rc) return rc;
     if (!ds->region_ev[which]) CUDA_TRY(cudaEventCreate(&ds->region_ev[which]));
-    if (ds->n_lanes > 1 && ds->lane_stream[1]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[1]));  // the mark covers both lanes
+    for (int l = 1; l < scicone_dataset::kLanes; ++l)  // the mark covers every lane
+        if (ds->lane_stream[l]) CUDA_TRY(cudaStreamSynchronize(ds->lane_stream[l]));
     CUDA_TRY(cudaEventRecord(ds->region_ev[which], ds->stream));
     return SCICONE_OK;
 }

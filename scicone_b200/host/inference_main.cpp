@@ -239,7 +239,7 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
             abi_check(scicone_dataset_attach_comm(ds, id, rank, world));
         }
         const bool stats = a.has("stats_file");
-        if (stats) scicone_set_profiling(ds, 1);
+        if (stats && a.flag("profile_kernels", true)) scicone_set_profiling(ds, 1);  // CUDA events around every kernel (per-kernel times of the stats file)
 
         // cell-sharded run: every chain's tree search runs on ONE rank (chain c -> rank c mod world), which compiles each
         // proposal once and ships the compiled bytes through a shared-memory mailbox (mcmc.hpp); the other ranks hold a
@@ -336,33 +336,41 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
 
         if (P.verbosity > 0) std::cout << "Inferring the tree using MCMC with " << n_iters << " iterations..." << std::endl;
         HostPhaseTimes phase;
+        phase.want_timeline = a.flag("timeline", false);
         // schedule: "dynamic" (default for several chains on one GPU) launches whatever is ready - in a cell-sharded run
         // rank 0 composes the launches and the other ranks replay its launch log; "static" moves groups of chains in lock-step
         const std::string schedule = a.str("schedule", ((world == 1 || mailbox) && n_chains >= 4) ? "dynamic" : "static");
-        auto run_chains = [&](int iters, HostPhaseTimes* t) {
-            if (schedule == "dynamic" && (world == 1 || mailbox))
-                infer_mcmc_dynamic(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("min_batch", 0)), t,
-                                   static_cast<int>(a.integer("n_streams", 2)), rank, world, mailbox.get());
-            else
-                infer_mcmc(chains, move_probs, iters, size_limit, static_cast<int>(a.integer("n_groups", 0)), t, rank, world, mailbox.get());
-        };
+        const bool dynamic = schedule == "dynamic" && (world == 1 || mailbox);
+        // --warmup_iters (bench.py): untimed iterations before the measured run; the chains simply continue afterwards
         const int warmup_iters = static_cast<int>(a.integer("warmup_iters", 0));
-        if (warmup_iters > 0) {  // untimed iterations before the measured run (bench.py); the chains simply continue afterwards
-            run_chains(warmup_iters, nullptr);
+        double k0[4];
+        uint64_t launches0 = 0;
+        std::chrono::high_resolution_clock::time_point start;
+        auto mark = [&]() {  // everything before this point is warm-up: counters back to zero, clocks started
             for (Inference* c : chains) {
                 c->n_accepted = c->n_rejected = 0;
                 c->n_rescored_nodes = c->n_attempts = 0;
                 c->t_finish_us = c->t_propose_us = c->t_prepare_us = c->t_max_visit_us = 0;
             }
+            scicone_counters(ds, k0, 1);
+            scicone_build_counters(ds, k0, 1);
+            scicone_kernel_time_stats(ds, nullptr, nullptr, 1);
+            scicone_kernel_launches(ds, &launches0);
+            scicone_region_mark(ds, 0);
+            start = std::chrono::high_resolution_clock::now();
+        };
+        if (dynamic) {
+            // one call: the warm-up iterations are a phase of their own (all chains stop at the mark, nothing in flight),
+            // then the clock starts; worker threads and launch lanes are those of a long run
+            if (warmup_iters <= 0) mark();
+            infer_mcmc_dynamic(chains, move_probs, n_iters, size_limit, static_cast<int>(a.integer("min_batch", 0)), &phase,
+                               static_cast<int>(a.integer("n_streams", 2)), rank, world, mailbox.get(), std::max(0, warmup_iters), mark);
+        } else {
+            const int n_groups = static_cast<int>(a.integer("n_groups", 0));
+            if (warmup_iters > 0) infer_mcmc(chains, move_probs, warmup_iters, size_limit, n_groups, nullptr, rank, world, mailbox.get());
+            mark();
+            infer_mcmc(chains, move_probs, n_iters, size_limit, n_groups, &phase, rank, world, mailbox.get());
         }
-        double k0[4];
-        scicone_counters(ds, k0, 1);
-        scicone_kernel_time_stats(ds, nullptr, nullptr, 1);
-        uint64_t launches0 = 0;
-        scicone_kernel_launches(ds, &launches0);
-        scicone_region_mark(ds, 0);
-        auto start = std::chrono::high_resolution_clock::now();
-        run_chains(n_iters, &phase);
         if (P.verbosity > 0 && n_chains > 1)
             std::cout << "driver thread: chains " << phase.host_us << " us, submit " << phase.submit_us << " us, wait " << phase.wait_us
                       << " us (" << scicone_host_threads() << " host threads)" << std::endl;
@@ -376,6 +384,8 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
             double k[4], kern_us = 0, build_us = 0;
             uint64_t n_timed = 0, n_build = 0, launches = 0;
             scicone_counters(ds, k, 0);
+            double kb[2] = {0, 0};
+            scicone_build_counters(ds, kb, 0);
             scicone_kernel_time_stats(ds, &kern_us, &n_timed, 0);
             scicone_build_time_stats(ds, &build_us, &n_build);
             scicone_kernel_launches(ds, &launches);
@@ -392,11 +402,18 @@ extern "C" int scicone_inference_main(int argc, char** argv) {
                << ",\"wall_us\":" << duration.count() << ",\"device_region_ms\":" << region_ms << ",\"score_kernel_us\":" << kern_us
                << ",\"score_kernel_launches\":" << n_timed << ",\"build_kernel_us\":" << build_us << ",\"build_kernel_launches\":" << n_build
                << ",\"gpu_launches\":" << (launches - launches0) << ",\"h2d_bytes\":" << k[0] << ",\"d2h_bytes\":" << k[1]
-               << ",\"alg_bytes\":" << k[2] << ",\"n_scores\":" << k[3] << ",\"device_bytes\":" << dev_bytes << ",\"accepted\":" << acc
+               << ",\"alg_bytes\":" << k[2] << ",\"n_scores\":" << k[3] << ",\"build_alg_bytes\":" << kb[0] << ",\"build_lgamma\":" << kb[1] << ",\"device_bytes\":" << dev_bytes << ",\"accepted\":" << acc
                << ",\"rejected\":" << rej << ",\"rescored_nodes\":" << resc << ",\"host_threads\":" << scicone_host_threads() << ",\"attempts\":" << attempts << ",\"chain_finish_us\":" << cf << ",\"chain_propose_us\":" << cp
                << ",\"chain_prepare_us\":" << cq << ",\"chain_max_visit_us\":" << cmax << ",\"schedule\":\"" << schedule << "\",\"launches\":" << phase.launches << ",\"launched_chains\":" << phase.launched_chains
                << ",\"host_us\":" << phase.host_us
-               << ",\"submit_us\":" << phase.submit_us << ",\"wait_us\":" << phase.wait_us << "}" << std::endl;
+               << ",\"submit_us\":" << phase.submit_us << ",\"wait_us\":" << phase.wait_us;
+            if (phase.want_timeline) {
+                sf << ",\"timeline\":[";
+                for (size_t i = 0; i < phase.timeline.size(); ++i)
+                    sf << (i ? "," : "") << "[" << std::setprecision(9) << phase.timeline[i][0] << "," << phase.timeline[i][1] << "," << phase.timeline[i][2] << "]";
+                sf << "]";
+            }
+            sf << "}" << std::endl;
         }
 
         if (P.verbosity > 0) std::cout << "Writing the inferred tree and cnvs..." << std::endl;

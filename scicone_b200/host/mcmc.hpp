@@ -12,6 +12,7 @@
 #define SCICONE_B200_HOST_MCMC_HPP
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <chrono>
 #include <atomic>
@@ -24,6 +25,7 @@
 #include <iostream>
 #include <thread>
 #include <exception>
+#include <functional>
 #include <memory>
 #include <mutex>
 
@@ -764,6 +766,9 @@ inline void parallel_chains(int n, F&& fn) {
 struct HostPhaseTimes {  // wall time of the driver thread per phase, microseconds (for --stats_file)
     double host_us = 0, submit_us = 0, wait_us = 0;  // parallel finish+propose+prepare region / launch / waiting for the GPU
     unsigned long long launches = 0, launched_chains = 0;  // dynamic schedule: number of launches and proposals in them
+    // --timeline=1: {microseconds since the mark, 0 = submit / 1 = collected, proposals in the launch} per event of the driver thread
+    bool want_timeline = false;
+    std::vector<std::array<double, 3>> timeline;
 };
 
 inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
@@ -898,18 +903,28 @@ inline void infer_mcmc(std::vector<Inference*>& chains, const std::vector<float>
 // are compiled on rank 0 and writes each list to the launch log; the other ranks replay the log, submitting launch k as
 // soon as its chains are compiled locally.  Nothing ever waits for a later launch, and no worker thread blocks on
 // another rank: a chain whose message (or whose followers' acknowledgement) is not there yet goes back to the queue.
+//
+// `n_warmup` > 0 (timing runs): the first n_warmup iterations of every chain are a separate phase - when ALL chains have
+// finished them and every launch has been collected (host and device idle, the same state as between two calls) the
+// driver calls `at_mark` (which starts the caller's clock) and releases the chains for the n_iters measured iterations.
+// Worker threads, streams and buffers stay as they are across the mark, as they would in a long run.
 inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vector<float>& move_probs, int n_iters, unsigned size_limit,
                                int min_batch = 0, HostPhaseTimes* times = nullptr, int n_streams = 2, int rank = 0, int world = 1,
-                               Mailbox* mailbox = nullptr) {
+                               Mailbox* mailbox = nullptr, int n_warmup = 0, const std::function<void()>& at_mark = nullptr) {
     typedef std::chrono::steady_clock Clock;
     const int B = static_cast<int>(chains.size());
     if (B == 0 || n_iters <= 0) return;
+    const int n_total = n_warmup + n_iters;
+    std::atomic<int> limit{n_warmup > 0 ? n_warmup : n_total};  // iterations the chains may run in the current phase
     if (world > 1 && mailbox == nullptr) throw std::runtime_error("the dynamic schedule of a multi-process run needs the mailbox");
     scicone_dataset* ds = chains[0]->ds;
     if (min_batch <= 0) min_batch = std::max(1, B / 4);  // 32 chains x 10 k cells: 6 -> 161.6, 8 -> 163.6, 10 -> 166.4, 12 -> 181.8 us per iteration; 16 chains x 100 k cells: 3 -> 488, 5 -> 458
     // two launch streams: K1 of one launch overlaps the proposal kernel of the other (a launch is always collected here
     // before its chains are settled, which is what the second stream requires)
-    if (n_streams > 1) abi_check(scicone_set_streams(ds, 2));
+    n_streams = std::max(1, std::min(n_streams, 4));
+    if (n_streams > 1) abi_check(scicone_set_streams(ds, n_streams));
+    const size_t max_flights = static_cast<size_t>(std::max(2, n_streams));
+    const bool split_heavy = getenv("SCICONE_SPLIT_HEAVY") ? atoi(getenv("SCICONE_SPLIT_HEAVY")) != 0 : false;  // measured: 191 us per iteration of 32 chains with the split, 176 without
     // the reduction scratch is sized once, before the first launch: a launch never has more proposals than it has slots
     abi_check(scicone_dataset_reserve(ds, world > 1 ? std::min(B, SCICONE_MAX_SHARDED_BATCH) : B, 0));
     int32_t max_batch = 0;
@@ -918,7 +933,7 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     auto owned = [&](int b) { return mailbox == nullptr || b % world == rank; };
     parallel_chains(B, [&](int b) {
         chains[b]->best_tree.copy_from(chains[b]->t);  // Inference.h:540
-        if (owned(b)) chains[b]->open_traces(n_iters);
+        if (owned(b)) chains[b]->open_traces(n_total);
     });
     struct Slot {
         int iter = 0;             // iteration whose proposal is queued / in flight
@@ -926,6 +941,7 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
         bool to_publish = false;  // owner: the message is packed, the followers have not acknowledged the previous one yet
         bool queued = false;      //        ... and it carries a scored proposal
         double total = 0.0, od = 0.0;
+        bool heavy = false;  // the queued proposal rescores many nodes (a nu move): it goes into a launch of its own kind
         Clock::time_point waiting_since{};  // first unsuccessful poll of the other ranks
         bool polling = false;
     };
@@ -959,6 +975,11 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     };
     auto hand_over = [&](int b, bool queued) {
         st[b].polling = false;
+        if (queued) {
+            double cost = 0.0;
+            abi_check(scicone_t_prime_cost(chains[b]->chain, &cost));
+            st[b].heavy = cost >= 40.0;
+        }
         std::lock_guard<std::mutex> lk(mu);
         --n_host;
         if (queued)
@@ -991,7 +1012,8 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
                 ++s.iter;
             }
             s.queued = false;
-            while (s.iter < n_iters) {
+            const int lim = limit.load(std::memory_order_acquire);
+            while (s.iter < lim) {
                 if (c->propose(move_probs, size_limit)) {
                     abi_check(scicone_prepare_t_prime(c->chain));
                     s.queued = true;
@@ -1057,9 +1079,15 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     std::vector<scicone_chain*> handles;
     std::vector<double> totals(B), ods(B);
     unsigned long long n_launches = 0, n_launched_chains = 0;
+    Clock::time_point t_mark = Clock::now();
+    auto note = [&](double kind, size_t n) {
+        if (times && times->want_timeline)
+            times->timeline.push_back({std::chrono::duration<double, std::micro>(Clock::now() - t_mark).count(), kind, static_cast<double>(n)});
+    };
     auto collect = [&](Flight& f) {
         int rc = scicone_batch_wait(ds, f.ticket, totals.data(), ods.data());
         if (rc != SCICONE_OK && rc != SCICONE_ERR_NAN) abi_check(rc);
+        note(1, f.members.size());
         std::lock_guard<std::mutex> lk(mu);
         for (size_t i = 0; i < f.members.size(); ++i) {
             Slot& s = st[f.members[i]];
@@ -1077,6 +1105,7 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
         Flight f;
         f.members = take;
         abi_check(scicone_batch_submit(handles.data(), nullptr, static_cast<int32_t>(handles.size()), &f.ticket));
+        note(0, take.size());
         flights.push_back(std::move(f));
         ++n_launches;
         n_launched_chains += take.size();
@@ -1089,12 +1118,12 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
             if (stop.load(std::memory_order_acquire)) break;
             std::vector<int> take;
             bool all_done = false;
-            if (replay && !have_wanted && flights.size() < 2) have_wanted = mailbox->log_peek(wanted);
+            if (replay && !have_wanted && flights.size() < max_flights) have_wanted = mailbox->log_peek(wanted);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 all_done = n_done == B;
                 if (replay) {
-                    if (have_wanted && flights.size() < 2) {  // launch k goes out once all of its chains are compiled here
+                    if (have_wanted && flights.size() < max_flights) {  // launch k goes out once all of its chains are compiled here
                         size_t found = 0;
                         for (int b : wanted)
                             if (std::find(ready.begin(), ready.end(), b) != ready.end()) ++found;
@@ -1105,17 +1134,43 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
                     }
                 } else {
                     const bool nothing_coming = n_host == 0 && flights.empty();
-                    if (!ready.empty() && flights.size() < 2 && (static_cast<int>(ready.size()) >= min_batch || nothing_coming || (n_host == 0 && flights.size() < 2)))
+                    if (!ready.empty() && flights.size() < max_flights && (static_cast<int>(ready.size()) >= min_batch || nothing_coming || n_host == 0))
                     {
                         take.swap(ready);
+                        // Whole-tree rescorings (nu moves) need the table / increment kernels in front of the proposal
+                        // kernel; a launch of small proposals is ONE kernel.  Keep the two kinds apart: the heavy ones go
+                        // first, the small ones follow in the next launch (on another lane).
+                        if (split_heavy) {
+                            size_t n_heavy = 0;
+                            for (int b : take) n_heavy += st[b].heavy ? 1 : 0;
+                            if (n_heavy > 0 && n_heavy < take.size()) {
+                                std::vector<int> heavy;
+                                for (int b : take) (st[b].heavy ? heavy : ready).push_back(b);
+                                take.swap(heavy);
+                            }
+                        }
                         if (static_cast<int>(take.size()) > max_batch) {  // the rest waits for the next launch
-                            ready.assign(take.begin() + max_batch, take.end());
+                            ready.insert(ready.end(), take.begin() + max_batch, take.end());
                             take.resize(static_cast<size_t>(max_batch));
                         }
                     }
                 }
             }
-            if (all_done) break;
+            if (all_done) {
+                if (limit.load(std::memory_order_acquire) >= n_total) break;
+                // end of the warm-up phase: every chain has stopped at the mark and nothing is in flight
+                if (at_mark) at_mark();
+                t_mark = Clock::now();
+                if (times) times->timeline.clear();
+                n_launches = n_launched_chains = 0;
+                std::lock_guard<std::mutex> lk(mu);
+                limit.store(n_total, std::memory_order_release);
+                n_done = 0;
+                n_host = B;
+                for (int b = 0; b < B; ++b) work.push_back(b);
+                n_work.store(B, std::memory_order_release);
+                continue;
+            }
             if (!take.empty()) {
                 if (replay) {
                     submit(take);
@@ -1129,9 +1184,20 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
                 continue;
             }
             if (!flights.empty()) {
-                int32_t done = 0;
-                abi_check(scicone_batch_poll(ds, flights.front().ticket, &done));
-                if (done || flights.size() >= 2) {
+                // one GPU: whichever launch has come back (a launch of small proposals overtakes a whole-tree rescoring that
+                // was submitted before it); cell-sharded: in order - launch k uses lane k mod n on every rank
+                const size_t n_look = world == 1 ? flights.size() : 1;
+                bool got = false;
+                for (size_t f = 0; f < n_look && !got; ++f) {
+                    int32_t done = 0;
+                    abi_check(scicone_batch_poll(ds, flights[f].ticket, &done));
+                    if (done) {
+                        collect(flights[f]);
+                        flights.erase(flights.begin() + static_cast<std::ptrdiff_t>(f));
+                        got = true;
+                    }
+                }
+                if (!got && flights.size() >= max_flights) {
                     collect(flights.front());
                     flights.pop_front();
                 }

@@ -168,6 +168,15 @@ def test_multi_chain_equals_single_runs_on_gpu(tmp_path):
 
 
 @needs_bins
+@pytest.mark.gpu
+def test_more_chains_than_the_initial_slot_count_on_gpu(tmp_path):
+    """70 chains under the dynamic schedule: the library's reduction scratch starts with 64 slots and cannot grow while a
+    launch is outstanding, so the driver must reserve it up front (scicone_dataset_reserve) - launches of 65+ proposals
+    while another launch is in flight used to abort the run."""
+    _multi_chain(tmp_path, None, 70, ["--min_batch=66"], [0, 37, 69])
+
+
+@needs_bins
 @pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
 @pytest.mark.parametrize("schedule,world,threads,warmup", [("static", 2, "2", 0), ("dynamic", 2, "1", 0), ("dynamic", 3, "3", 0), ("dynamic", 2, "2", 150)])
 def test_chain_ownership_protocol_on_cpu(tmp_path, schedule, world, threads, warmup):
