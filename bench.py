@@ -389,7 +389,7 @@ def run_engine(args):
             "mcmc_iters_per_s": iters / (dev_ms * 1e-3),
             "scores_per_s": cnt_dev["n_scores"] * world / (dev_ms * 1e-3),
             "e2e": {"value": e2e, "unit": "cell_iters/s", "mcmc_iters_per_s": iters / e2e_s, "mcmc_iters_per_s_per_chain": K / e2e_s,
-                    "ms_per_step": 1e3 * e2e_s / K,
+                    "ms_per_step": 1e3 * e2e_s / K, "warmup_steps": e2e_warmup(args),
                     "h2d_bytes_per_step": host["h2d_bytes"] / K, "d2h_bytes_per_step": host["d2h_bytes"] / K,
                     "what": "scicone_b200/bin/inference (native MCMC host on the C ABI): real moves + Metropolis-Hastings, "
                             f"{B} restarts (seeds 42..), {host['host_threads']} host threads per rank, timer around infer_mcmc; the warm-up "
@@ -512,7 +512,14 @@ def run_native_host(args, data, rank, world, local, dist, comm_unique_id, profil
     if args.n_groups:
         extra += [f"--n_groups={args.n_groups}", "--schedule=static"]
     return host_run("e2e", full, data["region_sizes"], rank, world, local, dist, comm_unique_id, args.chains, args.nodes - 1, args.steps,
-                    args.warmup, args.max_scoring, args.nu, extra=extra)
+                    e2e_warmup(args), args.max_scoring, args.nu, extra=extra)
+
+
+def e2e_warmup(args):
+    """Untimed iterations in front of the K timed ones of the e2e leg: at least W, and at least 25 - the host side of an MCMC
+    iteration (tree moves on 16 threads, their allocator arenas and caches) is not warm after 5 iterations of 32 chains,
+    and a real run has thousands of iterations.  The number used is reported as e2e.warmup_steps."""
+    return max(args.warmup, args.e2e_min_warmup)
 
 
 def max_over_ranks(dist, world, x):
@@ -774,6 +781,7 @@ def main():
     ap.add_argument("--ref_iters_per_step", type=int, default=1)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true", help="skip the native-host run (profiling passes only)")
+    ap.add_argument("--e2e_min_warmup", type=int, default=25, help="the e2e leg runs at least this many untimed iterations first")
     ap.add_argument("--no_k0", action="store_true", help="start from the region-level matrix (profiling passes only)")
     ap.add_argument("--no_other_configs", action="store_true", help="skip the configs[1]/[3]/[4] sub-records")
     ap.add_argument("--host_args", default="", help="extra flags for the native host, space separated (tuning runs)")

@@ -191,8 +191,9 @@ int scicone_batch_compute_t_prime_sums(scicone_chain* const* chains, const scico
                                        int32_t n, double* t_prime_sums, double* od_scores /* [n] or NULL */);
 
 /*
- * Pipelined form of the batch call: submit queues the copy-in, the kernel and the copy-out on the
- * dataset's stream and returns at once; wait blocks until that launch is done and returns its totals.
+ * Pipelined form of the batch call: submit queues the copy-in and the kernels on the dataset's stream and
+ * returns at once; the last CTA of the launch writes the totals and the ticket into pinned host memory, and
+ * wait spins on that ticket (no device-to-host copy, no event) and returns the totals.
  * Accept / reject of the submitted proposals are host-side pointer swaps and may be issued before the
  * wait (later launches are ordered behind earlier ones by the stream).  At most 8 tickets may be
  * outstanding.  Reads (scicone_read_*) always see the finished state.
@@ -210,12 +211,14 @@ int scicone_batch_compute_t_prime_scores(scicone_chain* const* chains, const sci
 int scicone_batch_settle(scicone_chain* const* chains, const int32_t* accept, int32_t n);
 
 /*
- * Launch streams of a dataset (default 1).  With 2, consecutive batch launches alternate between two streams and overlap
- * on the device.  One stream serialises launches, which is what allows scicone_accept / scicone_reject before
- * scicone_batch_wait; with two streams a launch must be collected (scicone_batch_wait) before its chains are settled or
- * queued again, and at most one launch per stream may be outstanding.  On a cell-sharded dataset the call is collective
- * (the second stream gets a communicator of its own, ncclCommSplit) and all ranks must submit their launches in the same
- * order.
+ * Launch lanes of a dataset (default 1, at most 4).  A lane is a stream with its own device arena, table arena and
+ * reduction slots; launches on different lanes overlap on the device.  One lane serialises launches, which is what allows
+ * scicone_accept / scicone_reject before scicone_batch_wait; with several lanes a launch must be collected
+ * (scicone_batch_wait) before its chains are settled or queued again, and at most one launch per lane may be outstanding.
+ * On one GPU a launch takes any free lane and launches may be collected in any order; on a cell-sharded dataset launch k
+ * uses lane k mod n on every rank, all ranks must submit their launches in the same order and collect them in order, and
+ * the call is collective when the exchange runs over NCCL (every further lane gets a communicator of its own,
+ * ncclCommSplit).
  */
 int scicone_set_streams(scicone_dataset* ds, int32_t n);
 

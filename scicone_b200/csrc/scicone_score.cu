@@ -106,6 +106,8 @@ struct DriverApi {
     CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
     CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
     CUresult (*Granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     bool loaded = false;
     bool load() {
         if (loaded) return true;
@@ -117,6 +119,7 @@ struct DriverApi {
                  get("cuMemCreate", (void**)&Create) && get("cuMemRelease", (void**)&Release) && get("cuMemMap", (void**)&Map) &&
                  get("cuMemUnmap", (void**)&Unmap) && get("cuMemSetAccess", (void**)&SetAccess) &&
                  get("cuMemGetAllocationGranularity", (void**)&Granularity);
+        get("cuTensorMapEncodeTiled", (void**)&TensorMapEncodeTiled);  // optional: K0 falls back to one-row copies without it
         return loaded;
     }
 };
@@ -2065,16 +2068,10 @@ int scicone_condense_matrix(int32_t device, const double* D_bins, int64_t n_cell
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev)
         return fail(SCICONE_ERR_CUDA, "condense_matrix: no such CUDA device; this library has no CPU fallback");
     CUDA_TRY(cudaSetDevice(device));
-    const int n_tiles = (int)((n_used + kK0Tile - 1) / kK0Tile);
-    std::vector<int> tile_first(n_tiles + 1, n_regions - 1);
-    for (int t = 0, r = 0; t < n_tiles; ++t) {
-        while (off[r + 1] <= (long long)t * kK0Tile) ++r;
-        tile_first[t] = r;
-    }
     // rows travel in chunks of at most 2 GB: upload, condense, download
     const long long chunk_rows = std::max<long long>(kK0Rows, std::min<long long>(n_cells, (2048ll << 20) / (n_bins * (long long)sizeof(double))));
     double *d_bins = nullptr, *d_out = nullptr;
-    int *d_off = nullptr, *d_first = nullptr;
+    int *d_off = nullptr, *d_blocks = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int n_sm = 148;
@@ -2085,20 +2082,69 @@ int scicone_condense_matrix(int32_t device, const double* D_bins, int64_t n_cell
     if (e == cudaSuccess) e = cudaMalloc(&d_bins, sizeof(double) * chunk_rows * n_bins + 16);
     if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * chunk_rows * n_regions);
     if (e == cudaSuccess) e = cudaMalloc(&d_off, sizeof(int) * off.size());
-    if (e == cudaSuccess) e = cudaMalloc(&d_first, sizeof(int) * tile_first.size());
+    if (e == cudaSuccess) e = cudaMalloc(&d_blocks, sizeof(int) * (kK0MaxBlocks + 2));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_first, tile_first.data(), sizeof(int) * tile_first.size(), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(condense_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK0SmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(condense_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kK0SmemBudget + 8 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(condense_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kK0SmemBudget + 8 * 1024));
+    {
+        std::lock_guard<std::mutex> lk(g_drv_mu);
+        g_drv.load();
+    }
+    // a tensor map needs a row pitch that is a multiple of 16 bytes (and coordinates that fit 32 bits)
+    const bool tensor = g_drv.TensorMapEncodeTiled && n_bins % 2 == 0 && n_bins < (1ll << 31) && !(getenv("SCICONE_K0_ROWCOPIES") && atoi(getenv("SCICONE_K0_ROWCOPIES")));
     double total_us = 0.0;
     for (long long r0 = 0; e == cudaSuccess && r0 < n_cells; r0 += chunk_rows) {
         const long long rows = std::min(chunk_rows, (long long)n_cells - r0);
         e = cudaMemcpyAsync(d_bins, D_bins + r0 * n_bins, sizeof(double) * rows * n_bins, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) break;
         const long long groups = (rows + kK0Rows - 1) / kK0Rows;
+        // Work items = row groups x region blocks: enough of them to give every warp slot of the GPU a few, but none shorter
+        // than ~16 tiles (the ring has to fill and drain per item).  Blocks hold about the same number of bins each.
+        int n_blocks = (int)std::max<long long>(1, std::min<long long>({(long long)kK0MaxBlocks, (long long)n_regions, n_used / 600 + 1,
+                                                                         (3ll * n_sm * kK0MaxWarps + groups - 1) / groups}));
+        std::vector<int> blocks(1, 0);
+        for (int b = 1; b < n_blocks; ++b) {
+            const long long want = n_used * b / n_blocks;
+            int r = blocks.back() + 1;
+            while (r < n_regions && off[r] < want) ++r;
+            if (r >= n_regions) break;
+            blocks.push_back(r);
+        }
+        blocks.push_back(n_regions);
+        n_blocks = (int)blocks.size() - 1;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_blocks, blocks.data(), sizeof(int) * blocks.size(), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        const long long n_work = groups * n_blocks;
+        // warps per CTA and ring depth: the active warps of an SM together keep ~100 KB or more in flight
+        const int wpc = (int)std::max<long long>(1, std::min<long long>(kK0MaxWarps, (n_work + n_sm - 1) / n_sm));
+        const size_t index_bytes = (size_t)(n_regions + 1 <= kK0MaxIndex ? n_regions + 1 : 0) * sizeof(int);
+        const size_t stage_bytes = k0_stage_bytes(tensor);
+        const int n_stages = (int)std::max<size_t>(2, std::min<size_t>(kK0MaxStages, (kK0SmemBudget - index_bytes) / ((size_t)wpc * (stage_bytes + 8))));
+        const size_t smem = (size_t)wpc * n_stages * (stage_bytes + 8) + index_bytes + 16;
+        const unsigned grid = (unsigned)std::min<long long>(n_sm, (n_work + wpc - 1) / wpc);
+        CUtensorMap map;
+        memset(&map, 0, sizeof map);
+        bool use_tensor = tensor;
+        if (use_tensor) {
+            const cuuint64_t dims[2] = {(cuuint64_t)n_bins, (cuuint64_t)rows};
+            const cuuint64_t strides[1] = {(cuuint64_t)n_bins * sizeof(double)};
+            const cuuint32_t box[2] = {(cuuint32_t)kK0TileTensor, (cuuint32_t)kK0Rows};
+            const cuuint32_t estr[2] = {1, 1};
+            CUresult cr = g_drv.TensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_bins, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            use_tensor = cr == CUDA_SUCCESS;
+        }
         cudaEventRecord(e0, st);
-        condense_rows_kernel<<<(unsigned)std::min<long long>(groups, (long long)n_sm), kK0Threads, kK0SmemBytes, st>>>(
-            d_bins, rows, n_bins, n_used, d_off, d_first, n_regions, n_tiles, d_out);
+        if (use_tensor)
+            condense_rows_kernel<true><<<grid, 32 * wpc, smem, st>>>(map, d_bins, rows, n_bins, n_used, d_off, n_regions, n_stages, d_blocks, n_blocks, d_out);
+        else {  // one-row copies: 33 KB stages, so fewer warps per CTA
+            const size_t sb = k0_stage_bytes(false);
+            const int wpc1 = (int)std::max<size_t>(1, std::min<size_t>((size_t)wpc, (kK0SmemBudget - index_bytes) / (2 * (sb + 8))));
+            const int ns = (int)std::max<size_t>(2, std::min<size_t>(kK0MaxStages, (kK0SmemBudget - index_bytes) / ((size_t)wpc1 * (sb + 8))));
+            const unsigned grid1 = (unsigned)std::min<long long>(n_sm, (n_work + wpc1 - 1) / wpc1);
+            condense_rows_kernel<false><<<grid1, 32 * wpc1, (size_t)wpc1 * ns * (sb + 8) + index_bytes + 16, st>>>(map, d_bins, rows, n_bins, n_used, d_off, n_regions,
+                                                                                                               ns, d_blocks, n_blocks, d_out);
+        }
         cudaEventRecord(e1, st);
         e = cudaGetLastError();
         if (e == cudaSuccess)
@@ -2110,7 +2156,7 @@ int scicone_condense_matrix(int32_t device, const double* D_bins, int64_t n_cell
             total_us += 1e3 * ms;
         }
     }
-    cudaFree(d_bins); cudaFree(d_out); cudaFree(d_off); cudaFree(d_first);
+    cudaFree(d_bins); cudaFree(d_out); cudaFree(d_off); cudaFree(d_blocks);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (st) cudaStreamDestroy(st);
