@@ -487,6 +487,11 @@ def host_run(tag, D_full, region_sizes, rank, world, local, dist, comm_unique_id
             if res.returncode != 0:
                 raise SystemExit(f"bench.py: native host failed ({tag}):\n" + res.stdout[-2000:] + res.stderr[-2000:])
             out = json.load(open(stats))
+            if solo and world > 1:
+                open(os.path.join(tmp, f"done{rank}"), "w").close()
+        elif world > 1:  # a rank that sits this run out waits for a file, not in an NCCL barrier (which spins on its GPU and core)
+            while not all(os.path.exists(os.path.join(tmp, f"done{r}")) for r in ranks):
+                time.sleep(0.02)
         if world > 1:
             dist.barrier()
         return out
@@ -575,7 +580,17 @@ def other_configs(args, rank, world, local, dist, comm_unique_id):
         rec["speedup_vs_one_gpu"] = one_s / n_s
         rec["strong_scaling_efficiency"] = one_s / n_s / world
     out["configs[4]"] = rec
-    # configs[3]: cluster-tree mode - condensed centroids with cluster_sizes, many restarts in parallel across the GPUs
+    # configs[3]: cluster-tree mode - condensed centroids with cluster_sizes, many restarts in parallel across the GPUs.
+    # learn_tree runs one inference process per GPU; the other ranks of this bench must leave their GPUs alone meanwhile (a
+    # rank waiting in an NCCL barrier keeps a spinning kernel on its GPU), so they wait for a file instead.
+    sentinel = None
+    if world > 1:
+        box = [tempfile.mktemp(prefix="scicone_c3_done_") if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        sentinel = box[0]
+        import torch
+
+        torch.cuda.synchronize()
     if rank == 0:
         d3 = make_counts(10000, 18000, 200, seed=SEED + 13, cluster_rows=40)
         tmp = tempfile.mkdtemp(prefix="scicone_c3_")
@@ -602,8 +617,15 @@ def other_configs(args, rank, world, local, dist, comm_unique_id):
                                  "best_restart": lt["best_rep"]}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
+            if sentinel:
+                open(sentinel, "w").close()
+    elif sentinel:
+        while not os.path.exists(sentinel):
+            time.sleep(0.05)
     if world > 1:
         dist.barrier()
+        if rank == 0:
+            os.unlink(sentinel)
     return out
 
 

@@ -223,9 +223,11 @@ struct Rng {
 };
 
 // lgamma of small integers by the running sum the reference memoises (Lgamma.cpp:10-33): lg(0)=inf, lg(1)=lg(2)=0,
-// lg(n) = lg(n-1) + log(n-1).  Kept as a running sum (not ::lgamma) so that priors round identically.
+// lg(n) = lg(n-1) + log(n-1).  Kept as a running sum (not ::lgamma) so that priors round identically.  One table per
+// thread: chains are advanced by several host threads at once, and a shared table that grows under a reader is a heap
+// corruption (seen as a rare "double free or corruption" in sum-scoring runs); the running sum is the same in every thread.
 inline double lgamma_int(unsigned long n) {
-    static std::vector<double> table = {std::numeric_limits<double>::infinity(), 0.0, 0.0};
+    thread_local std::vector<double> table = {std::numeric_limits<double>::infinity(), 0.0, 0.0};
     while (table.size() - 1 < n) table.push_back(table.back() + std::log(static_cast<double>(table.size() - 1)));
     return table[n];
 }

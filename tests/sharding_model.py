@@ -1,10 +1,11 @@
-"""Cell sharding across the GPUs of one box.
+"""NumPy model of the cell-shard reduction - test infrastructure for tests/test_sharding_gloo.py, not
+part of the product: the product's reduction is finish_reduction / gather_totals_kernel in scicone_b200/csrc/kernels.cuh.
 
 Every per-cell quantity of the scoring path is independent across cells; the only cross-cell step is the weighted
 sum over cells (reference: scicone/src/Inference.h:292-294).  Cells are split into contiguous shards whose
 boundaries fall on multiples of CHUNK cells; every rank reduces its cells to one partial per chunk (CHUNK = the
-16 x 64-cell CTAs of kernels.cuh), all ranks exchange the chunk partials (NCCL all-gather inside
-libscicone_score.so; `gloo` in the CPU tests) and add them in global chunk order.  Because the order of additions is
+8 x 128-cell CTAs of kernels.cuh: kCtasPerChunk x kCells), all ranks exchange the chunk partials (peer-memory stores or an
+NCCL all-gather inside libscicone_score.so; `gloo` in the CPU tests) and add them in global chunk order.  Because the order of additions is
 fixed by the chunk grid and not by the rank layout, the tree score is bit-identical for 1, 2, 4 or 8 GPUs.
 """
 import numpy as np
@@ -28,7 +29,7 @@ def max_chunks_per_rank(n_cells, world_size, chunk=CHUNK):
     return max((b - a + chunk - 1) // chunk for a, b in shard_bounds(n_cells, world_size, chunk))
 
 
-def chunk_partials(values, weights, chunk=CHUNK, cta=64):
+def chunk_partials(values, weights, chunk=CHUNK, cta=128):
     """Per-chunk partial sums of values*weights with the kernel's reduction shape: xor-shuffle tree inside a warp,
     warps added in order inside a CTA, CTAs added in order inside a chunk (kernels.cuh block_sum/finish_reduction)."""
     v = np.asarray(values, dtype=np.float64) * np.asarray(weights, dtype=np.float64)

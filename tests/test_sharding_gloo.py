@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from scicone_b200 import sharding  # noqa: E402
+import sharding_model as sharding  # noqa: E402
 
 
 def _free_port():
