@@ -79,6 +79,14 @@ def workload_config(args, world):
             "l2": f"inputs larger than L2: ~{resident:.0f} MB of score rows + counts resident per GPU vs 126 MB L2"}
 
 
+def threads_per_rank(world):
+    """Host threads of one rank's process.  They spin while they wait (an MCMC iteration is ~100 us), so the ranks together
+    must leave a core or two per rank to everything else on the box - a spinning thread that loses its core to the scheduler
+    stalls every rank of a cell-sharded run for a time slice."""
+    cores = os.cpu_count() or 1
+    return max(2, cores // world - 1) if world > 1 else cores
+
+
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command (profiles/)."""
     p = os.path.join(ROOT, "profiles", "r2_traffic.json")
@@ -177,7 +185,7 @@ def run_engine(args):
     import torch.distributed as dist
 
     if world > 1:  # the ranks share the host cores: split them between the libraries' worker pools
-        os.environ.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+        os.environ.setdefault("SCICONE_THREADS", str(threads_per_rank(world)))
 
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -481,12 +489,15 @@ def host_run(tag, D_full, region_sizes, rank, world, local, dist, comm_unique_id
                 cmd += ["--schedule=dynamic", f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"]
             cmd += list(extra)
             env = dict(os.environ)
-            if w_run > 1:  # the host cores are shared by the ranks
-                env.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+            env["SCICONE_THREADS"] = str(threads_per_rank(w_run))  # a run on one GPU has the box's cores to itself (the other ranks sleep)
             res = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, env=env)
             if res.returncode != 0:
                 raise SystemExit(f"bench.py: native host failed ({tag}):\n" + res.stdout[-2000:] + res.stderr[-2000:])
             out = json.load(open(stats))
+            keep = os.environ.get("SCICONE_BENCH_KEEP_STATS")  # tuning runs: keep every rank's stats file (launch timeline etc.)
+            if keep:
+                os.makedirs(keep, exist_ok=True)
+                shutil.copy(stats, os.path.join(keep, f"{tag}_stats{rank}_{int(time.time() * 1000) % 100000}.json"))
             if solo and world > 1:
                 open(os.path.join(tmp, f"done{rank}"), "w").close()
         elif world > 1:  # a rank that sits this run out waits for a file, not in an NCCL barrier (which spins on its GPU and core)
@@ -654,7 +665,7 @@ def sharded_equals_single(rank, world, local, dist, comm_unique_id):
             ok = one.returncode == 0
         dist.barrier()
         env = dict(os.environ)
-        env.setdefault("SCICONE_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+        env.setdefault("SCICONE_THREADS", str(threads_per_rank(world)))
         res = subprocess.run(common + [f"--postfix=shard{rank}", f"--device={local}", f"--rank={rank}", f"--world={world}", f"--nccl_id={uid[0]}"],
                              cwd=tmp, capture_output=True, text=True, env=env)
         flag = [res.returncode == 0]

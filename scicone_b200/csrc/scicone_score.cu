@@ -138,7 +138,8 @@ struct RowPool {
     int device = 0;
     CUdeviceptr base = 0;
     size_t va_bytes = 0;
-    size_t part_rows = 0, chunk_rows = 0;
+    static constexpr size_t kPartRows = 65536;  // rows of the index space per rank: the same on every rank
+    size_t part_rows = 0, chunk_rows = 0, part_cap = 0;
     int n_parts = 1, my_part = 0;
     struct Part {
         size_t mapped_rows = 0;
@@ -193,13 +194,17 @@ struct RowPool {
         // chunk = the smallest multiple of 64 rows whose byte size is a multiple of the granularity and at least 32 MB
         chunk_rows = 64;
         while ((chunk_rows * row_bytes) % gran != 0 || chunk_rows * row_bytes < (size_t(32) << 20)) chunk_rows += 64;
-        part_rows = std::max<size_t>(chunk_rows * 4, (size_t(1) << 16) / chunk_rows * chunk_rows);
-        for (;;) {
-            va_bytes = part_rows * row_bytes * n_parts;
-            if (g_drv.AddressReserve(&base, va_bytes, gran, 0, 0) == CUDA_SUCCESS) break;
+        // The partition size is part of the row INDEX (row = partition * part_rows + r) and compiled proposals travel between
+        // ranks, so it must not depend on anything rank-local (the chunk size does: it follows from this shard's padded cell
+        // count).  Rows are padded to 256 cells, so partition bases are 2 MB aligned.  A partition is usable up to its last
+        // whole chunk.
+        part_rows = kPartRows;
+        part_cap = part_rows / chunk_rows * chunk_rows;
+        if (part_cap == 0) return fail(SCICONE_ERR_CUDA, "row pool: a mapping chunk of %zu rows exceeds the partition of %zu rows", chunk_rows, part_rows);
+        va_bytes = part_rows * row_bytes * n_parts;
+        if (g_drv.AddressReserve(&base, va_bytes, gran, 0, 0) != CUDA_SUCCESS) {
             base = 0;
-            if (part_rows <= chunk_rows * 4) return fail(SCICONE_ERR_CUDA, "cuMemAddressReserve of %zu bytes failed", va_bytes);
-            part_rows = std::max(chunk_rows * 4, part_rows / 2 / chunk_rows * chunk_rows);
+            return fail(SCICONE_ERR_CUDA, "cuMemAddressReserve of %zu bytes failed", va_bytes);
         }
         parts.assign(n_parts, Part());
         return SCICONE_OK;
@@ -209,7 +214,7 @@ struct RowPool {
         if (part < 0 || part >= n_parts) return fail(SCICONE_ERR_ARG, "row pool: partition %d out of range", part);
         Part& pt = parts[part];
         if (rows <= pt.mapped_rows) return SCICONE_OK;
-        if (rows > part_rows) return fail(SCICONE_ERR_CUDA, "row pool: partition of %zu rows exhausted", part_rows);
+        if (rows > part_cap) return fail(SCICONE_ERR_CUDA, "row pool: partition of %zu rows exhausted", part_cap);
         CUDA_TRY(cudaSetDevice(device));
         CUmemAllocationProp prop;
         memset(&prop, 0, sizeof prop);
@@ -1563,7 +1568,7 @@ int scicone_dataset_reserve(scicone_dataset* ds, int32_t max_batch, int64_t rows
         if (rc) return rc;
     }
     for (int p = 0; p < ds->pool.n_parts && rows > 0; ++p) {
-        rc = ds->pool.ensure_mapped(p, std::min<size_t>((size_t)rows, ds->pool.part_rows));
+        rc = ds->pool.ensure_mapped(p, std::min<size_t>((size_t)rows, ds->pool.part_cap));
         if (rc) return rc;
     }
     return SCICONE_OK;

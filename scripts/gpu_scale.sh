@@ -15,7 +15,7 @@ run() {  # name, bench args
   echo "bench $name rc=$?" | tee -a "$OUT/summary.txt"; tail -3 "$OUT/bench_$name.err"; grep real "$OUT/time_$name.txt"
 }
 run driver --steps 20 --warmup 5
-run long --steps 200 --warmup 20 --no_other_configs
+run long --steps 200 --warmup 20 --no_other_configs --host_args=--timeline=1
 if [ -n "${MORE:-}" ]; then run long_s3 --steps 200 --warmup 20 --no_other_configs --host_args=--n_streams=3; fi
 python - "$OUT" <<'PY'
 import json,sys
