@@ -964,7 +964,9 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
             s.waiting_since = Clock::now();
         } else if (Clock::now() - s.waiting_since > std::chrono::seconds(120))
             throw std::runtime_error(std::string("timed out waiting for ") + what + " of chain " + std::to_string(b));
-        for (int i = 0; i < 64; ++i) {
+        // a short breath, not a long one: a rank follows up to B - B/world chains through this queue, and the time one lap
+        // takes is the delay with which it notices a proposal the owner has published
+        for (int i = 0; i < 4; ++i) {
 #if defined(__x86_64__) || defined(__i386__)
             __builtin_ia32_pause();
 #endif
