@@ -555,7 +555,7 @@ def other_configs(args, rank, world, local, dist, comm_unique_id):
     cell-sharded over the N GPUs (strong scaling: the same matrix on 1 GPU is timed beside it)."""
     from scicone_b200.synth import SEED, make_counts
 
-    K, W = args.steps, args.warmup
+    K, W = args.steps, e2e_warmup(args)  # the same number of untimed iterations as the e2e leg
     out = {}
     noprof = ["--profile_kernels=0"]  # timed runs: no CUDA events around the kernels
 
