@@ -414,7 +414,13 @@ def run_engine(args):
                              bytes_model="SURVEY.md 8d: 16 + 8 E_n per rescored cell x node, 8 N + 12 per cell aggregate; "
                                          "nu move / full pass: 8 K + 16 N + 12 per cell",
                              measured_in="value pass 1: one launch of all chains per step on one stream (the kernel runs alone); "
-                                         f"{one_lane_ms / K:.4f} ms per step there"),
+                                         f"{one_lane_ms / K:.4f} ms per step there",
+                             note="algorithmic bytes are what the reference's algorithm touches per unit (SURVEY.md 8d); this kernel reads "
+                                  "only the rows an aggregate needs and takes the data terms from 2-byte count indices and L2-resident tables, "
+                                  "so its DRAM traffic (`traffic`) is a fraction of them and frac can exceed 1: the kernel is bound by the latency "
+                                  "of dependent row gathers and by issue slots (ncu: issue active 48 %, DRAM 15 %), not by HBM bandwidth; "
+                                  "roofline_e2e is the same kernel inside the real MCMC",
+                             traffic_over_algorithmic=(traffic / (cnt_dev["alg_bytes"] / max(1, n_timed))) if traffic else None),
             # the same kernel inside the REAL MCMC (launches of ~10 proposals, two to three in flight, other kernels beside it)
             "roofline_e2e": roof(host["alg_bytes"], host["score_kernel_us"], kernel="score_proposals_kernel",
                                  launches=host["score_kernel_launches"],

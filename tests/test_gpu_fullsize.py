@@ -88,8 +88,15 @@ def test_config4_shape_weights_scale_the_total_exactly_and_batches_equal_single_
     ds1 = Dataset(D, base["region_sizes"], neutral_states=base["neutral_states"], cluster_sizes=w1, max_scoring=1)
     ds2 = Dataset(D, base["region_sizes"], neutral_states=base["neutral_states"], cluster_sizes=2 * w1, max_scoring=1)
     a, b, c = Chain(dataset=ds1), Chain(dataset=ds2), Chain(dataset=ds1)
+    # the oracle on a random subset of the cells (every per-cell quantity is independent of the other cells): it walks the
+    # same proposals as chain a and is compared at the end
+    subset = np.sort(np.random.default_rng(10).choice(M, 200, replace=False))
+    cpu = OracleChain(D=D[subset], region_sizes=base["region_sizes"], neutral_states=base["neutral_states"], cluster_sizes=w1[subset],
+                      is_overdispersed=1, max_scoring=1)
     ft = tree.flat()
     ta, tb = a.compute_t_table(ft), b.compute_t_table(ft)
+    cpu.compute_t_table(ft)
+    assert rel_err(a.read_t_sums()[subset], cpu.read_t_sums()) <= 1e-9
     assert tb == 2.0 * ta  # a power-of-two weight scales every term and every partial sum exactly
     assert b.compute_t_od_scores(ft.nu) == 2.0 * a.compute_t_od_scores(ft.nu)
     c.compute_t_table(ft)
@@ -98,9 +105,10 @@ def test_config4_shape_weights_scale_the_total_exactly_and_batches_equal_single_
     for step in range(6):
         t2, roots, kind = tree.propose(kinds=KINDS)
         f2 = t2.flat()
-        for ch in (a, b):
+        for ch in (a, b, cpu):
             for rid in roots:
                 ch.compute_t_prime_scores(f2, f2.index_of(rid))
+        cpu.compute_t_prime_sums(f2)
         # chain c gets a different proposal; a and c share a dataset and go out in ONE launch
         t3, roots3, _ = other.propose(kinds=KINDS)
         f3 = t3.flat()
@@ -114,10 +122,18 @@ def test_config4_shape_weights_scale_the_total_exactly_and_batches_equal_single_
             c.compute_t_prime_scores(f3, f3.index_of(rid))
         assert c.compute_t_prime_sums(f3) == tot[1]
         c.reject()
+        # the proposal's per-cell aggregates and argmax ids on the subset against the oracle, before it is settled
+        assert rel_err(a.read_t_prime_sums()[subset], cpu.read_t_prime_sums()) <= 1e-9
+        assert rel_err(np.asarray(a.read_t_prime_maxs()[1])[subset], cpu.read_t_prime_maxs()[1]) <= 1e-9  # (ids may differ at exact ties)
         for ch in (a, b):
             ch.accept() if step % 2 == 0 else ch.reject()
+        cpu.accept(f2) if step % 2 == 0 else cpu.reject()
         if step % 2 == 0:
             tree = t2
+    # the committed tables after the walk: scores of the subset against the oracle
+    assert list(a.t_node_ids()) == list(cpu.t_node_ids())
+    assert rel_err(a.read_t_scores()[subset], cpu.read_t_scores()) <= 1e-9
+    assert rel_err(a.read_t_sums()[subset], cpu.read_t_sums()) <= 1e-9
 
 
 @pytest.mark.parametrize("M", [10000, 2500])
