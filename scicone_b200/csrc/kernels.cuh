@@ -47,6 +47,7 @@ constexpr int kGroup = 8;           // nodes whose increments are in flight per 
 constexpr int kScRing = 4;          // most recent node scores a thread keeps in registers (parent lookups)
 constexpr int kMaxOdSlices = 32;    // region slices of a root score
 constexpr int kCtasPerChunk = 8;    // 8 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
+constexpr int kTablesBlock = 256;   // threads per CTA of the table kernel (K1a)
 constexpr int kBuildBlock = 256;    // threads per CTA of the build kernel
 constexpr int kBuildCells = 4;      // cells per thread and step of the build kernel
 constexpr int kLutMax = 4096;       // largest range of counts that is tabulated (host side: the dataset's count-range table)
@@ -64,11 +65,15 @@ enum : unsigned {
     PROP_SCRATCH = 8u,   // to_add.size() >= unchanged_vals.size(): recompute the log-sum from scratch
     PROP_WITH_OD = 16u,  // also evaluate the root ("overdispersed") score from its region slices
     PROP_OD_ONLY = 32u,  // no tasks, no aggregate: only the root score
+    PROP_OD_HIST = 64u,  // the region part of the root score comes from the dataset's count histograms (ITEM_OD_HIST): one
+                         // number per item in the table arena instead of one slice row per cell
     ITEM_NODE_OD = 1u,   // increment of one node, Dirichlet-multinomial branch (Tree.h:212-231)
     ITEM_NODE_MN = 2u,   // increment of one node, multinomial branch (Tree.h:221,236-237)
     ITEM_SLICE_OD = 3u,  // slice of the root score (Tree.h:1792-1797)
     ITEM_SLICE_MN = 4u,  // non-overdispersed root score slice: sum_k D_k log r_k (Tree.h:1803-1805)
-    ITEM_G_ROW = 5u      // dst = lgamma(S + c): the cell-level term of the root score
+    ITEM_G_ROW = 5u,     // dst = lgamma(S + c): the cell-level term of the root score
+    ITEM_OD_HIST = 6u    // K1a only: sum over the regions [k0, k1) and the possible counts v of
+                         // hist_k[v] * (lgamma(v + nu*neutral_k*r_k) - lgamma(nu*neutral_k*r_k)) -> one number (g_tab)
 };
 
 // Everything that differs between the ranks of a cell-sharded run (addresses, shard size, reduction scratch) travels as
@@ -108,6 +113,13 @@ struct LaunchParams {
     // K1
     unsigned off_items;
     int n_items;
+    // Root score from count histograms (datasets whose counts are integers in a narrow range in every region): hist holds,
+    // region after region, sum_j cluster_size_j [D_jk == gmin_k + i] over ALL cells of the run (every rank of a cell-sharded
+    // run holds the same global histogram, so every rank computes the same number and only `od_owner` adds it to its sums)
+    const double* hist;
+    const int* glut;           // [K][2] {gmin_k, range_k}
+    const unsigned* hist_off;  // [K + 1] first entry of region k
+    int od_owner;
 };
 
 struct alignas(16) DevTask {
@@ -142,7 +154,9 @@ struct alignas(16) DevHeader {
     unsigned maxid_old, maxid_new;  // rows holding int32 argmax ids
     unsigned od_g_row;              // PROP_WITH_OD, OD: row lgamma(S + nu*z_root) built by K1
     unsigned off_old;               // u32 rows whose values leave the aggregate
-    unsigned off_unch, off_od_rows, pad0, pad1;
+    unsigned off_unch, off_od_rows;
+    unsigned od_dot_tab;            // PROP_OD_HIST: rank-local, filled at submit: first of the n_od_slices numbers of the ITEM_OD_HIST items
+    unsigned pad1;
     double od_lg_nz, od_nz;  // OD: lgamma(nu*z_root), nu*z_root;  non-OD: od_lg_nz = log(sum_r)
 };
 static_assert(sizeof(DevHeader) % 16 == 0, "the task records follow the header");
@@ -188,6 +202,13 @@ __device__ __forceinline__ double lgam(double x, const double* tbl) {
     return lgamma(x);
 }
 
+// Programmatic dependent launch (sm_90+): K1a -> K1b -> proposal kernel (-> gather kernel) are launched back to back on one
+// stream with programmatic stream serialization, so the next kernel's CTAs are scheduled, and run their prologue (which
+// only reads the staged arena and committed rows), while the previous kernel drains; `pdl_wait` blocks until the previous
+// kernel has completed and its writes are visible.  Both are no-ops in a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
     // fixed-shape reduction: xor-shuffle tree inside each warp, warps added in order
 #pragma unroll
@@ -210,7 +231,7 @@ __device__ __forceinline__ double block_sum(double v, double* warp_buf) {
 // number in this rank's flag word on every rank - one release at system scope per peer after a CTA barrier, so a rank
 // that sees the flag sees the sums.  No collective kernel runs and no GPU waits for another one here: only the reader of
 // the sums does (gather_totals_kernel).
-__device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum1, unsigned slot, const LaunchParams& P) {
+__device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum1, bool with_od, unsigned slot, const LaunchParams& P) {
     __shared__ int role;  // 0: nothing left to do, 1: last CTA of the proposal, 2: ... and of the launch
     __shared__ double smem_chunks[kThreads];
     const int n_cta = P.n_cta;
@@ -218,7 +239,7 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
     double* partial = P.partial + (size_t)slot * 2 * n_cta;
     if (threadIdx.x == 0) {
         partial[blockIdx.x] = cta_sum0;
-        partial[n_cta + blockIdx.x] = cta_sum1;
+        if (with_od) partial[n_cta + blockIdx.x] = cta_sum1;
         __threadfence();
         const unsigned ticket = atomicAdd(P.counter + slot, 1u);
         role = (ticket == gridDim.x - 1) ? 1 : 0;
@@ -227,8 +248,13 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
     if (role == 0) return;
     __threadfence();
     for (int v = 0; v < 2; ++v) {
-        const double* part = partial + (size_t)v * n_cta;
         double* chunks = P.chunk_sums + ((size_t)slot * 2 + v) * P.cs_stride;
+        if (v == 1 && !with_od) {  // no root score was asked for: zeros, without the round of loads and barriers
+            for (int c = threadIdx.x; c < P.cs_stride; c += kThreads) chunks[c] = 0.0;
+            if (threadIdx.x == 0) P.total[(size_t)slot * 2 + 1] = 0.0;
+            break;
+        }
+        const double* part = partial + (size_t)v * n_cta;
         double grand = 0.0;
         for (int base = 0; base < P.cs_stride; base += kThreads) {
             const int c = base + threadIdx.x;
@@ -282,11 +308,26 @@ __device__ __forceinline__ void finish_reduction(double cta_sum0, double cta_sum
     __syncthreads();
     if (role != 2) return;
     __threadfence();
+    // every 16-byte piece is loaded once and stored to all ranks: the stores to peer memory are fire-and-forget, the loads
+    // (four in flight per thread) are the only round trips of this loop
     const int n16 = P.n_props * P.cs_stride;  // 16-byte pieces: 2 * n_props * cs_stride doubles, contiguous from slot 0
     const double2* src = reinterpret_cast<const double2*>(P.chunk_sums);
-    for (int p = 0; p < P.xchg_world; ++p) {
-        double2* dst = reinterpret_cast<double2*>(P.xchg_data[p]);
-        for (int q = threadIdx.x; q < n16; q += kThreads) dst[q] = __ldcg(src + q);
+    constexpr int kPieces = 4;
+    for (int q0 = threadIdx.x; q0 < n16; q0 += kThreads * kPieces) {
+        double2 v[kPieces];
+#pragma unroll
+        for (int i = 0; i < kPieces; ++i) {
+            const int q = q0 + i * kThreads;
+            v[i] = q < n16 ? __ldcg(src + q) : make_double2(0.0, 0.0);
+        }
+        for (int p = 0; p < P.xchg_world; ++p) {
+            double2* dst = reinterpret_cast<double2*>(P.xchg_data[p]);
+#pragma unroll
+            for (int i = 0; i < kPieces; ++i) {
+                const int q = q0 + i * kThreads;
+                if (q < n16) dst[q] = v[i];
+            }
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) *P.launch_counter = 0u;
@@ -307,6 +348,7 @@ __global__ void __launch_bounds__(128) gather_totals_kernel(const unsigned long 
                                                             unsigned long long ticket, unsigned long long timeout_ns) {
     __shared__ int timed_out;
     if (threadIdx.x == 0) timed_out = 0;
+    pdl_wait();  // this rank's proposal kernel has completed (status words, its own flag)
     __syncthreads();
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -360,9 +402,11 @@ __global__ void __launch_bounds__(128) gather_totals_kernel(const unsigned long 
 //                                 direct evaluation, bit for bit.  Rows without a table (non-integer data: cluster means)
 //                                 are evaluated directly from Dt in the same loop (kDirect).
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) build_tables_kernel(const __grid_constant__ LaunchParams P) {
+__global__ void __launch_bounds__(kTablesBlock) build_tables_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ double tbl[kLogTableDoubles];
-    load_log_table<128>(tbl);
+    __shared__ double red[kTablesBlock / 32];
+    pdl_launch_dependents();
+    load_log_table<kTablesBlock>(tbl);
     const unsigned char* __restrict__ arena = P.arena;
     const DevItem& it = reinterpret_cast<const DevItem*>(arena + P.off_items)[blockIdx.x];
     const int* __restrict__ lut = P.lut;
@@ -376,7 +420,7 @@ __global__ void __launch_bounds__(128) build_tables_kernel(const __grid_constant
             if (off == kNoRow) continue;
             const int vmin = lut[2 * ev[e].k], range = lut[2 * ev[e].k + 1];
             const double aN = ev[e].argN, aP = ev[e].argP;
-            for (int i = threadIdx.x; i < range; i += 128) {
+            for (int i = threadIdx.x; i < range; i += kTablesBlock) {
                 const double v = (double)(vmin + i);
                 T[off + i] = lgam(v + aN, tbl) - lgam(v + aP, tbl);  // Tree.h:214-218, one rounding of the difference as there
             }
@@ -384,7 +428,7 @@ __global__ void __launch_bounds__(128) build_tables_kernel(const __grid_constant
         if (it.g_tab != kNoRow) {  // Tree.h:229-231
             const int smin = lut[2 * P.n_regions], srange = lut[2 * P.n_regions + 1];
             const double nz = it.nz, nzp = it.nzp;
-            for (int i = threadIdx.x; i < srange; i += 128) {
+            for (int i = threadIdx.x; i < srange; i += kTablesBlock) {
                 const double v = (double)(smin + i);
                 T[it.g_tab + i] = lgam(v + nz, tbl);
                 T[it.g_tab + srange + i] = lgam(v + nzp, tbl);
@@ -398,16 +442,46 @@ __global__ void __launch_bounds__(128) build_tables_kernel(const __grid_constant
             if (off == kNoRow) continue;
             const int vmin = lut[2 * k], range = lut[2 * k + 1];
             const double a = arg[k];
-            for (int i = threadIdx.x; i < range; i += 128) T[off + i] = lgam((double)(vmin + i) + a, tbl);
+            for (int i = threadIdx.x; i < range; i += kTablesBlock) T[off + i] = lgam((double)(vmin + i) + a, tbl);
+        }
+    } else if (kind == ITEM_OD_HIST) {
+        // Region part of Tree::get_od_root_score (Tree.h:1792-1797) summed over the cells FIRST: the cells only enter through
+        // how often each count occurs, sum_j w_j (lgamma(D_jk + a_k) - lgamma(a_k)) = sum_v hist_k[v] (lgamma(v + a_k) - lgamma(a_k)),
+        // a few hundred lgamma per region instead of a look-up per cell.  Fixed order: thread t takes the entries t, t + 256, ...
+        // of each region in turn, then a fixed-shape reduction - the number does not depend on the schedule.
+        const double* arg = reinterpret_cast<const double*>(arena + it.aux_off);
+        const double* cc = arg + P.n_regions;
+        double acc = 0.0;
+        for (int k = it.k0; k < it.k1; ++k) {
+            const int vmin = P.glut[2 * k], range = P.glut[2 * k + 1];
+            const double* h = P.hist + P.hist_off[k];
+            const double a = arg[k], c = cc[k];
+            for (int i = threadIdx.x; i < range; i += kTablesBlock) {
+                const double w = h[i];
+                if (w != 0.0) acc += w * (lgam((double)(vmin + i) + a, tbl) - c);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int i = 0; i < kTablesBlock / 32; ++i) s += red[i];
+            T[it.g_tab] = s;
         }
     } else if (kind == ITEM_G_ROW) {
         if (it.g_tab != kNoRow) {
             const int smin = lut[2 * P.n_regions], srange = lut[2 * P.n_regions + 1];
             const double c1 = it.nz;
-            for (int i = threadIdx.x; i < srange; i += 128) T[it.g_tab + i] = lgam((double)(smin + i) + c1, tbl);
+            for (int i = threadIdx.x; i < srange; i += kTablesBlock) T[it.g_tab + i] = lgam((double)(smin + i) + c1, tbl);
         }
     }
 }
+
+// Entries of the value tables K1a wrote: an ordinary cached load, not the read-only path - with programmatic launches this
+// kernel's lifetime overlaps K1a's, so the tables are not read-only data of this kernel.
+__device__ __forceinline__ double ld_table(const double* p) { return __ldca(p); }
 
 template <bool kDirect>  // kDirect: some row of this shard has no table - the logarithm table is needed
 __global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __grid_constant__ LaunchParams P) {
@@ -416,9 +490,10 @@ __global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __g
         load_log_table<kBuildBlock>(tbl);
         __syncthreads();
     }
+    pdl_launch_dependents();
     const unsigned char* __restrict__ arena = P.arena;
-    const DevItem& it = reinterpret_cast<const DevItem*>(arena + P.off_items)[blockIdx.y];
-    const double* __restrict__ T = P.tables;
+    const DevItem it = reinterpret_cast<const DevItem*>(arena + P.off_items)[blockIdx.y];  // by value: read before the wait
+    const double* T = P.tables;
     const long long stride = P.stride;
     const unsigned kind = it.kind;
     double* const dst = P.rows + (long long)it.dst * stride;
@@ -426,6 +501,7 @@ __global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __g
     bool ok[kBuildCells];
 #pragma unroll
     for (int q = 0; q < kBuildCells; ++q) ok[q] = j0 + q * kBuildBlock < P.n_cells;
+    pdl_wait();  // the value tables of K1a are complete from here on
     if (kind == ITEM_NODE_OD) {
         // score(node) - score(parent) in the reference's operation order (Tree::compute_score, Tree.h:212-231): for every
         // event x += lgamma(D_k + a_node) - lgamma(D_k + a_parent); x -= lgamma(a_node); x += lgamma(a_parent); then the
@@ -445,7 +521,7 @@ __global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __g
 #pragma unroll
                 for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(ir + q * kBuildBlock) : 0u;
 #pragma unroll
-                for (int q = 0; q < kBuildCells; ++q) d[q] = __ldg(T + off + idx[q]);
+                for (int q = 0; q < kBuildCells; ++q) d[q] = ld_table(T + off + idx[q]);
             } else if (kDirect) {
                 const double* dr = P.Dt + row;
                 const double aN = ev[e].argN, aP = ev[e].argP;
@@ -471,8 +547,8 @@ __global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __g
             for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(P.Si + j0 + q * kBuildBlock) : 0u;
 #pragma unroll
             for (int q = 0; q < kBuildCells; ++q) {
-                gn[q] = __ldg(T + it.g_tab + idx[q]);
-                gp[q] = __ldg(T + it.g_tab + srange + idx[q]);
+                gn[q] = ld_table(T + it.g_tab + idx[q]);
+                gp[q] = ld_table(T + it.g_tab + srange + idx[q]);
             }
         } else if (kDirect) {
             const double nz = it.nz, nzp = it.nzp;
@@ -534,7 +610,7 @@ __global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __g
 #pragma unroll
                 for (int q = 0; q < kBuildCells; ++q) idx[q] = ok[q] ? (unsigned)__ldg(ir + q * kBuildBlock) : 0u;
 #pragma unroll
-                for (int q = 0; q < kBuildCells; ++q) v[q] = __ldg(T + off + idx[q]);
+                for (int q = 0; q < kBuildCells; ++q) v[q] = ld_table(T + off + idx[q]);
             } else if (kDirect) {
                 const double* dr = P.Dt + row;
                 const double a = arg[k];
@@ -576,7 +652,7 @@ __global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __g
             const int j = j0 + q * kBuildBlock;
             if (j < P.n_cells) {
                 if (it.g_tab != kNoRow)
-                    dst[j] = __ldg(T + it.g_tab + __ldg(P.Si + j));
+                    dst[j] = ld_table(T + it.g_tab + __ldg(P.Si + j));
                 else if (kDirect)
                     dst[j] = lgam(__ldg(P.S + j) + c1, tbl);
             }
@@ -610,6 +686,7 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
     __shared__ __align__(16) DevTask sm_task[kTaskChunk];
     __shared__ double red_buf[kThreads / 32];
 
+    pdl_launch_dependents();
     const unsigned char* __restrict__ arena = P.arena;
     const LaunchEntry le = reinterpret_cast<const LaunchEntry*>(arena)[blockIdx.y];
     const unsigned char* blob = arena + le.blob_off;
@@ -638,6 +715,8 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
     double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;  // scores of the last kScRing nodes of the walk (s1 = the node just before)
     static_assert(kScRing == 4, "the register ring is written out for four entries");
     const int n_tasks = H.n_tasks;
+    // everything above reads the staged arena and committed rows only; the increments K1b wrote are read from here on
+    pdl_wait();
     __syncthreads();  // first chunk staged
     for (int c0 = 0; c0 < n_tasks; c0 += kTaskChunk) {
         const int nt = min(kTaskChunk, n_tasks - c0);
@@ -850,7 +929,7 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
         // Tree::get_od_root_score (Tree.h:1774-1810) from the region slices K1 prepared;
         // Inference::compute_t_prime_od_scores, Inference.h:1421-1433
         const unsigned* slices = reinterpret_cast<const unsigned*>(blob + H.off_od_rows);
-        const int ns = H.n_od_slices;
+        const int ns = (pflags & PROP_OD_HIST) ? 0 : H.n_od_slices;  // PROP_OD_HIST: the region part is added once per proposal, below
         double v = 0.0;
         if (pflags & PROP_OD) {
             v += H.od_lg_nz;
@@ -875,8 +954,16 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
     if (pflags & PROP_WITH_OD) {  // uniform per proposal
         cta_od = block_sum(contrib_od, red_buf);
         __syncthreads();
+        if ((pflags & PROP_OD_HIST) && blockIdx.x == 0 && threadIdx.x == 0 && P.od_owner) {
+            // region part of the root score: the numbers the ITEM_OD_HIST items of K1a left in the table arena, added in item
+            // order into the partial of the first CTA of the run's first shard (the histograms cover ALL cells of the run)
+            const double* dots = P.tables + H.od_dot_tab;
+            double r = 0.0;
+            for (int s = 0; s < H.n_od_slices; ++s) r += __ldcg(dots + s);
+            cta_od += r;
+        }
     }
-    finish_reduction(cta_sum, cta_od, le.slot, P);
+    finish_reduction(cta_sum, cta_od, (pflags & PROP_WITH_OD) != 0, le.slot, P);
 }
 
 // Dataset set-up: the 16-bit index matrix of the tabulated rows.  Row K of the table describes S.
@@ -892,6 +979,19 @@ __global__ void index_kernel(const double* __restrict__ Dt, const double* __rest
         It[(long long)k * Mp + j] = idx;
     else
         Si[j] = idx;
+}
+
+// Dataset set-up: weighted count histograms of the regions, hist[hist_off[k] + D_jk - gmin_k] += cluster_size_j.  The sums
+// are integers held in doubles (exact, so the order of the atomic additions does not matter).
+__global__ void hist_kernel(const double* __restrict__ Dt, const int* __restrict__ w, const int* __restrict__ glut,
+                            const unsigned* __restrict__ hist_off, int M, long long Mp, double* __restrict__ hist) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (j >= M) return;
+    const int wj = w[j];
+    if (wj == 0) return;
+    const int i = (int)Dt[(long long)k * Mp + j] - glut[2 * k];
+    if (i >= 0 && i < glut[2 * k + 1]) atomicAdd(hist + hist_off[k] + i, (double)wj);
 }
 
 // Test hook: the device lgamma on caller-provided arguments (scicone_test_lgamma).

@@ -384,6 +384,20 @@ struct scicone_dataset {
     int* d_lut = nullptr;
     std::vector<int> lut;
     bool all_tab = false;    // every row has a table: K1b needs no direct lgamma evaluation
+    // Root score from count histograms (kernels.cuh, ITEM_OD_HIST): when every region's counts are integers in a narrow
+    // range, the region part of Tree::get_od_root_score summed over the cells is a function of how often each count occurs.
+    // The histograms cover ALL cells of the run: a cell-sharded dataset sums its shard's histograms with the other ranks'
+    // at scicone_dataset_attach_comm (integers: exact), so every rank holds the same table and the root score does not
+    // depend on the number of GPUs.  raw_*: per row of counts (regions, then S) {min, max, all integers} of this shard.
+    std::vector<double> raw_lo, raw_hi;
+    std::vector<char> raw_int;
+    bool od_hist_allowed = true;  // SCICONE_OD_HIST=0: per-cell slices as for non-integer data (test hook)
+    bool od_hist = false;
+    std::vector<int> glut;            // [K][2] {gmin_k, range_k} over all cells of the run
+    std::vector<unsigned> hist_off;   // [K + 1]
+    int* d_glut = nullptr;
+    unsigned* d_hist_off = nullptr;
+    double* d_hist = nullptr;
     double* d_tables[4] = {nullptr, nullptr, nullptr, nullptr};  // per lane: value tables of the launch in flight
     size_t tables_cap = 0;                     // doubles per lane
     int* dW = nullptr;
@@ -458,6 +472,7 @@ struct scicone_dataset {
     // profiling
     bool profiling = false;
     bool direct_results = true;  // SCICONE_DIRECT_RESULTS=0: results travel by a stream-ordered copy + event instead
+    bool pdl = true;             // SCICONE_PDL=0: K1a, K1b and the proposal kernel are launched the ordinary, fully serialised way
     double last_kernel_us = 0.0, sum_kernel_us = 0.0, sum_build_us = 0.0;
     unsigned long long n_timed = 0, n_build_timed = 0;
     unsigned long long n_launches = 0;
@@ -648,6 +663,7 @@ size_t bytes_append(std::vector<unsigned char>& b, const std::vector<T>& v) {
 }
 
 constexpr int kOdRegionsPerSlice = 6;  // 200 regions -> 32 slices: enough units for one nu proposal to fill the GPU
+constexpr int kOdRegionsPerHistItem = 3, kMaxOdHistItems = 96;  // histogram form: ~7 lgamma per thread of a K1a item at 200 regions
 
 // Root-score request (Tree::get_od_root_score, Tree.h:1774-1810): K1 items that reduce slices of the regions into
 // temporary rows; the proposal kernel adds the slices and the two cell-level terms.
@@ -681,6 +697,25 @@ int add_od_request(scicone_chain* ch, double nu, DevHeader& H, std::vector<unsig
         for (int k = 0; k < K; ++k) arg[k] = log((double)ds->r[k]);
     }
     const unsigned aux_off = (unsigned)bytes_append(ch->aux, arg);
+    if (ds->od_hist) {
+        // The region part summed over the cells first (kernels.cuh, ITEM_OD_HIST): K1a items of a few regions each leave one
+        // number apiece in the table arena; no slice rows, no per-cell look-ups.  The cell-level term lgamma(S + nu z_root)
+        // stays per cell (the row requested above), so the sum over the cells keeps its chunk order.
+        const int n_hist = std::max(1, std::min(kMaxOdHistItems, (K + kOdRegionsPerHistItem - 1) / kOdRegionsPerHistItem));
+        for (int s = 0; s < n_hist; ++s) {
+            DevItem it;
+            memset(&it, 0, sizeof it);
+            it.kind = ITEM_OD_HIST;
+            it.dst = kNoRow;
+            it.aux_off = aux_off;
+            it.k0 = (int)((long long)K * s / n_hist);
+            it.k1 = (int)((long long)K * (s + 1) / n_hist);
+            ch->items.push_back(it);
+        }
+        H.n_od_slices = n_hist;
+        H.flags |= PROP_WITH_OD | PROP_OD_HIST;
+        return SCICONE_OK;
+    }
     const int n_slices = std::max(1, std::min(kMaxOdSlices, K / kOdRegionsPerSlice));
     for (int s = 0; s < n_slices; ++s) {
         unsigned row = kNoRow;
@@ -1036,19 +1071,26 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         direct_chain[i] = tables_mode == 0;
         any_direct = any_direct || (direct_chain[i] && n_ev > 0);
     }
-    for (int pass = 0; pass < 2; ++pass) {
+    size_t n_k1b_items = 0;  // the ITEM_OD_HIST items (pass 2) are K1a work only: they sit behind everything K1b looks at
+    for (int pass = 0; pass < 3; ++pass) {
         size_t chain_aux = off_aux;
         for (int i = 0; i < n; ++i) {
             scicone_chain* ch = chains[i];
             if (pass == 0 && !ch->aux.empty()) memcpy(g.h_arena + chain_aux, ch->aux.data(), ch->aux.size());
-            bool slices_laid_out = false;
+            bool slices_laid_out = false, dots_laid_out = false;
             for (const DevItem& src : ch->items) {
                 const bool slice = src.kind == ITEM_SLICE_OD || src.kind == ITEM_SLICE_MN;
-                if (slice != (pass == 0)) continue;
+                if ((slice ? 0 : src.kind == ITEM_OD_HIST ? 2 : 1) != pass) continue;
+                if (pass < 2) n_k1b_items++;
                 DevItem it = src;
                 it.aux_off += (unsigned)chain_aux;
                 it.g_tab = kNoRow;
-                if (it.kind == ITEM_NODE_OD) {
+                if (it.kind == ITEM_OD_HIST) {  // one number per item, consecutive per chain; the header learns where they start
+                    if (!dots_laid_out) reinterpret_cast<DevHeader*>(g.h_arena + blob_at[i])->od_dot_tab = (unsigned)tab_at;
+                    dots_laid_out = true;
+                    it.g_tab = (unsigned)tab_at;
+                    tab_at += 1;
+                } else if (it.kind == ITEM_NODE_OD) {
                     DevEvent* ev = reinterpret_cast<DevEvent*>(g.h_arena + it.aux_off);
                     for (int e = 0; e < it.n_ev; ++e) {
                         const int range = direct_chain[i] ? 0 : lut[2 * ev[e].k + 1];
@@ -1089,6 +1131,11 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
                     else if (it.kind == ITEM_G_ROW) {
                         ds->k1_bytes += M * (8.0 + (s_range > 0 ? 2.0 : 8.0));
                         ds->k1_lgamma += s_range > 0 ? s_range : M;
+                    } else if (it.kind == ITEM_OD_HIST) {
+                        for (int k = it.k0; k < it.k1; ++k) {
+                            ds->k1_bytes += 8.0 * ds->glut[2 * (size_t)k + 1];
+                            ds->k1_lgamma += ds->glut[2 * (size_t)k + 1];
+                        }
                     } else {
                         ds->k1_bytes += M * 8.0;
                         for (int k = it.k0; k < it.k1; ++k) {
@@ -1153,33 +1200,55 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
     }
     P.off_items = (unsigned)off_items;
     P.n_items = (int)n_items;
+    P.hist = ds->d_hist;
+    P.glut = ds->d_glut;
+    P.hist_off = ds->d_hist_off;
+    P.od_owner = ds->rank == 0 ? 1 : 0;
+    // K1a -> K1b -> proposal kernel (-> gather kernel): each of them may be scheduled while its predecessor drains and waits
+    // (griddepcontrol.wait) before it reads what the predecessor wrote.  Only a kernel that directly follows another kernel
+    // of this launch gets the attribute; with kernel events on, the kernels are serialised the ordinary way so that the
+    // events bracket one kernel each.
+    const bool pdl = ds->pdl && !ds->profiling;
+    bool after_kernel = false;  // the previous operation on the stream is a kernel of this launch
+    auto launch = [&](auto kernel, dim3 grid, unsigned block) -> cudaError_t {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(block);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (pdl && after_kernel) ? 1 : 0;
+        after_kernel = true;
+        ds->n_launches++;
+        return cudaLaunchKernelEx(&cfg, kernel, P);
+    };
     if (n_items) {
         if (ds->profiling) CUDA_TRY(cudaEventRecord(g.evb, st));
         if (n_items > 65535) return fail(SCICONE_ERR_ARG, "more than 65535 rescored nodes in one launch");
-        if (tab_at > 0) {
-            build_tables_kernel<<<(unsigned)n_items, 128, 0, st>>>(P);
-            ds->n_launches++;
+        if (tab_at > 0) CUDA_TRY(launch(build_tables_kernel, dim3((unsigned)n_items), kTablesBlock));
+        if (n_k1b_items) {
+            const dim3 bgrid((ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells), (unsigned)n_k1b_items);
+            if (ds->all_tab && !any_direct)
+                CUDA_TRY(launch(build_increments_kernel<false>, bgrid, kBuildBlock));
+            else
+                CUDA_TRY(launch(build_increments_kernel<true>, bgrid, kBuildBlock));
         }
-        const dim3 bgrid((ds->M + kBuildBlock * kBuildCells - 1) / (kBuildBlock * kBuildCells), (unsigned)n_items);
-        if (ds->all_tab && !any_direct)
-            build_increments_kernel<false><<<bgrid, kBuildBlock, 0, st>>>(P);
-        else
-            build_increments_kernel<true><<<bgrid, kBuildBlock, 0, st>>>(P);
         CUDA_TRY(cudaGetLastError());
-        ds->n_launches++;
     }
     g.n_items = (int)n_items;
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev0, st));
     {   // the scoring mode is a property of the dataset: one specialisation per launch
         const dim3 grid(ds->n_cta, n);
         if (ds->maxs)
-            score_proposals_kernel<true><<<grid, kThreads, 0, st>>>(P);
+            CUDA_TRY(launch(score_proposals_kernel<true>, grid, kThreads));
         else
-            score_proposals_kernel<false><<<grid, kThreads, 0, st>>>(P);
+            CUDA_TRY(launch(score_proposals_kernel<false>, grid, kThreads));
     }
     if (ds->profiling) CUDA_TRY(cudaEventRecord(g.ev1, st));
     CUDA_TRY(cudaGetLastError());
-    ds->n_launches++;
     bool gathered_direct = false;
     if (ds->world > 1 && ds->xchg_on) {
         // The proposal kernel has stored this rank's chunk sums into every rank's gather buffer and published its flag; one
@@ -1187,9 +1256,22 @@ int submit_proposals(scicone_dataset* ds, scicone_chain* const* chains, int n, u
         // on the number of GPUs) and writes the n totals, the status words and the ticket into this
         // launch's pinned host buffers: no copy, no event.
         const unsigned long long seq = ds->lane_seq[lane];
-        gather_totals_kernel<<<1, 128, 0, st>>>(ds->xchg_flags(ds->xchg, lane, 0), ds->world, seq, ds->xchg_data(ds->xchg, lane, (int)(seq & 1), 0),
-                                                (long long)ds->xchg_block(), n, ds->max_chunks_rank, ds->lane_status(lane), g.h_total, g.h_status,
-                                                g.h_flag, tk, 60ull * 1000000000ull);
+        {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(1);
+            cfg.blockDim = dim3(128);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = pdl ? 1 : 0;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, gather_totals_kernel, (const unsigned long long*)ds->xchg_flags(ds->xchg, lane, 0), (int)ds->world, seq,
+                                        (const double*)ds->xchg_data(ds->xchg, lane, (int)(seq & 1), 0), (long long)ds->xchg_block(), n,
+                                        (int)ds->max_chunks_rank, (const unsigned*)ds->lane_status(lane), g.h_total, g.h_status, g.h_flag,
+                                        (unsigned long long)tk, 60ull * 1000000000ull));
+        }
         CUDA_TRY(cudaGetLastError());
         ds->n_launches++;
         gathered_direct = true;
@@ -1376,6 +1458,93 @@ struct ExportHead {
 };
 constexpr unsigned kExportMagic = 0x53433242u;  // "SC2B"
 
+// all-gather of `cnt` doubles per rank through the communicator (set-up plumbing only)
+int gather_doubles(scicone_dataset* ds, const double* mine, int cnt, std::vector<double>& all) {
+    double *d_one = nullptr, *d_all = nullptr;
+    all.assign((size_t)cnt * ds->world, 0.0);
+    CUDA_TRY(cudaMalloc(&d_one, sizeof(double) * cnt));
+    CUDA_TRY(cudaMalloc(&d_all, sizeof(double) * cnt * ds->world));
+    CUDA_TRY(cudaMemcpyAsync(d_one, mine, sizeof(double) * cnt, cudaMemcpyHostToDevice, ds->stream));
+    int nrc = g_nccl.AllGather(d_one, d_all, cnt, kNcclDouble, ds->comm, ds->stream);
+    if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaStreamSynchronize(ds->stream));
+    cudaFree(d_one);
+    cudaFree(d_all);
+    return SCICONE_OK;
+}
+
+
+// Count histograms for the root score (scicone_dataset::od_hist).  One GPU: from the shard's own count ranges, at
+// scicone_dataset_create.  Cell-sharded: again at scicone_dataset_attach_comm - the ranks agree on the global range of every
+// region, histogram their shards over it and add the histograms up (integers, exact), so every rank ends up with the
+// same table.  Not used (od_hist stays false, the per-cell slices do the work) when a region holds non-integer counts or
+// counts spread over more than kLutMax values, or with the multinomial likelihood.
+int build_od_hist(scicone_dataset* ds) {
+    const int K = ds->K;
+    ds->od_hist = false;
+    cudaFree(ds->d_glut);
+    cudaFree(ds->d_hist_off);
+    cudaFree(ds->d_hist);
+    ds->d_glut = nullptr;
+    ds->d_hist_off = nullptr;
+    ds->d_hist = nullptr;
+    const bool have = ds->raw_int.size() == (size_t)K + 1;
+    std::vector<double> st(3 * (size_t)K + 1, 0.0);
+    for (int k = 0; k < K && have; ++k) {
+        st[k] = ds->raw_lo[k];
+        st[(size_t)K + k] = ds->raw_hi[k];
+        st[2 * (size_t)K + k] = ds->raw_int[k] ? 1.0 : 0.0;
+    }
+    st[3 * (size_t)K] = (have && ds->od && ds->od_hist_allowed) ? 1.0 : 0.0;
+    if (ds->world > 1) {
+        std::vector<double> all;
+        int rc = gather_doubles(ds, st.data(), (int)st.size(), all);
+        if (rc) return rc;
+        for (int p = 0; p < ds->world; ++p) {
+            const double* o = all.data() + (size_t)p * st.size();
+            for (int k = 0; k < K; ++k) {
+                st[k] = std::min(st[k], o[k]);
+                st[(size_t)K + k] = std::max(st[(size_t)K + k], o[(size_t)K + k]);
+                st[2 * (size_t)K + k] = std::min(st[2 * (size_t)K + k], o[2 * (size_t)K + k]);
+            }
+            st[3 * (size_t)K] = std::min(st[3 * (size_t)K], o[3 * (size_t)K]);
+        }
+    }
+    bool ok = st[3 * (size_t)K] == 1.0;
+    for (int k = 0; k < K && ok; ++k) ok = st[2 * (size_t)K + k] == 1.0 && st[(size_t)K + k] - st[k] + 1.0 <= (double)kLutMax;
+    if (!ok) return SCICONE_OK;
+    ds->glut.assign((size_t)K * 2, 0);
+    ds->hist_off.assign((size_t)K + 1, 0u);
+    for (int k = 0; k < K; ++k) {
+        ds->glut[2 * (size_t)k] = (int)st[k];
+        ds->glut[2 * (size_t)k + 1] = (int)(st[(size_t)K + k] - st[k] + 1.0);
+        ds->hist_off[(size_t)k + 1] = ds->hist_off[k] + (unsigned)ds->glut[2 * (size_t)k + 1];
+    }
+    const size_t n = ds->hist_off[K];
+    CUDA_TRY(cudaMalloc(&ds->d_glut, sizeof(int) * ds->glut.size()));
+    CUDA_TRY(cudaMalloc(&ds->d_hist_off, sizeof(unsigned) * ds->hist_off.size()));
+    CUDA_TRY(cudaMalloc(&ds->d_hist, sizeof(double) * n));
+    CUDA_TRY(cudaMemcpyAsync(ds->d_glut, ds->glut.data(), sizeof(int) * ds->glut.size(), cudaMemcpyHostToDevice, ds->stream));
+    CUDA_TRY(cudaMemcpyAsync(ds->d_hist_off, ds->hist_off.data(), sizeof(unsigned) * ds->hist_off.size(), cudaMemcpyHostToDevice, ds->stream));
+    CUDA_TRY(cudaMemsetAsync(ds->d_hist, 0, sizeof(double) * n, ds->stream));
+    hist_kernel<<<dim3((ds->M + 255) / 256, K), 256, 0, ds->stream>>>(ds->dDt, ds->dW, ds->d_glut, ds->d_hist_off, ds->M, (long long)ds->Mp, ds->d_hist);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ds->stream));
+    if (ds->world > 1) {
+        std::vector<double> mine(n), all;
+        CUDA_TRY(cudaMemcpy(mine.data(), ds->d_hist, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        int rc = gather_doubles(ds, mine.data(), (int)n, all);
+        if (rc) return rc;
+        std::fill(mine.begin(), mine.end(), 0.0);
+        for (int p = 0; p < ds->world; ++p)
+            for (size_t i = 0; i < n; ++i) mine[i] += all[(size_t)p * n + i];
+        CUDA_TRY(cudaMemcpy(ds->d_hist, mine.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    ds->od_hist = true;
+    return SCICONE_OK;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1486,6 +1655,9 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
                 lo[K] = std::min(lo[K], sum);
                 hi[K] = std::max(hi[K], sum);
             }
+            ds->raw_lo = lo;
+            ds->raw_hi = hi;
+            ds->raw_int = integral;
             ds->all_tab = true;
             for (int k = 0; k <= K; ++k) {
                 const double range = hi[k] - lo[k] + 1.0;
@@ -1510,7 +1682,11 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     }
 #undef DS_TRY
     if (const char* e = getenv("SCICONE_DIRECT_RESULTS")) ds->direct_results = atoi(e) != 0;
-    int rc = ds->ensure_slots(64);
+    if (const char* e = getenv("SCICONE_OD_HIST")) ds->od_hist_allowed = atoi(e) != 0;
+    if (const char* e = getenv("SCICONE_PDL")) ds->pdl = atoi(e) != 0;
+    int rc = build_od_hist(ds);
+    if (rc) return cleanup(rc);
+    rc = ds->ensure_slots(64);
     if (rc) return cleanup(rc);
     rc = ds->ensure_arena(size_t(4) << 20);
     if (rc) return cleanup(rc);
@@ -1537,6 +1713,7 @@ void scicone_dataset_destroy(scicone_dataset* ds) {
     if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ds->comm);
     ds->pool.destroy();
     cudaFree(ds->dDt); cudaFree(ds->dS); cudaFree(ds->dW); cudaFree(ds->d_lut); cudaFree(ds->dIt); cudaFree(ds->dSi);
+    cudaFree(ds->d_glut); cudaFree(ds->d_hist_off); cudaFree(ds->d_hist);
     for (unsigned char* a : ds->d_arena) cudaFree(a);
     cudaFree(ds->d_partial); cudaFree(ds->d_chunk); cudaFree(ds->d_total);
     cudaFree(ds->d_counter); cudaFree(ds->d_gather); cudaFree(ds->d_launch_counter);
@@ -2250,22 +2427,6 @@ int scicone_comm_unique_id(uint8_t out[128]) {
 }
 
 namespace {
-// all-gather of `cnt` doubles per rank through the communicator (set-up plumbing only)
-int gather_doubles(scicone_dataset* ds, const double* mine, int cnt, std::vector<double>& all) {
-    double *d_one = nullptr, *d_all = nullptr;
-    all.assign((size_t)cnt * ds->world, 0.0);
-    CUDA_TRY(cudaMalloc(&d_one, sizeof(double) * cnt));
-    CUDA_TRY(cudaMalloc(&d_all, sizeof(double) * cnt * ds->world));
-    CUDA_TRY(cudaMemcpyAsync(d_one, mine, sizeof(double) * cnt, cudaMemcpyHostToDevice, ds->stream));
-    int nrc = g_nccl.AllGather(d_one, d_all, cnt, kNcclDouble, ds->comm, ds->stream);
-    if (nrc != 0) return fail(SCICONE_ERR_COMM, "ncclAllGather failed (%d)", nrc);
-    CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(double) * cnt * ds->world, cudaMemcpyDeviceToHost, ds->stream));
-    CUDA_TRY(cudaStreamSynchronize(ds->stream));
-    cudaFree(d_one);
-    cudaFree(d_all);
-    return SCICONE_OK;
-}
-
 // Map every rank's gather buffer into every process (CUDA IPC over NVLink peer access).  If any rank cannot (no peer
 // access between two devices, IPC unavailable in the container), ALL ranks stay with the NCCL all-gather.
 int setup_peer_exchange(scicone_dataset* ds) {
@@ -2353,6 +2514,8 @@ int scicone_dataset_attach_comm(scicone_dataset* ds, const uint8_t unique_id[128
         for (double v : all) ds->max_chunks_rank = std::max(ds->max_chunks_rank, (int)v);
     }
     ds->cs_stride = ds->max_chunks_rank;
+    rc = build_od_hist(ds);  // the histograms of the root score cover all cells of the run: summed over the ranks here
+    if (rc) return rc;
     const int keep = ds->slots;
     ds->slots = 0;  // force reallocation with the gather buffers and the common chunk width
     rc = ds->ensure_slots(std::max(keep, 4));
