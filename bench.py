@@ -84,7 +84,9 @@ def threads_per_rank(world):
     must leave a core or two per rank to everything else on the box - a spinning thread that loses its core to the scheduler
     stalls every rank of a cell-sharded run for a time slice."""
     cores = os.cpu_count() or 1
-    return max(2, cores // world - 1) if world > 1 else cores
+    # one GPU: 16 spinning threads on a 16-core box gave 20-step windows of 136-214 us per step (a worker that loses its core
+    # in the middle of a visit holds its chain for a time slice), 12 threads 134-139; 300-step runs are the same for 12-16
+    return max(2, cores // world - 1) if world > 1 else max(2, cores - 4)
 
 
 def load_traffic():
@@ -538,9 +540,9 @@ def run_native_host(args, data, rank, world, local, dist, comm_unique_id, profil
 
 
 def e2e_warmup(args):
-    """Untimed iterations in front of the K timed ones of the e2e leg: at least W, and at least 25 - the host side of an MCMC
-    iteration (tree moves on 16 threads, their allocator arenas and caches) is not warm after 5 iterations of 32 chains,
-    and a real run has thousands of iterations.  The number used is reported as e2e.warmup_steps."""
+    """Untimed iterations in front of the K timed ones of the e2e leg: at least W, and at least 100 (about 12 ms) - the host
+    side of an MCMC iteration (tree moves on a dozen threads, their allocator arenas and caches) is not warm after 5
+    iterations of 32 chains, and a real run has thousands of iterations.  The number used is reported as e2e.warmup_steps."""
     return max(args.warmup, args.e2e_min_warmup)
 
 
@@ -820,7 +822,7 @@ def main():
     ap.add_argument("--ref_iters_per_step", type=int, default=1)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true", help="skip the native-host run (profiling passes only)")
-    ap.add_argument("--e2e_min_warmup", type=int, default=25, help="the e2e leg runs at least this many untimed iterations first")
+    ap.add_argument("--e2e_min_warmup", type=int, default=100, help="the e2e leg runs at least this many untimed iterations first")
     ap.add_argument("--no_k0", action="store_true", help="start from the region-level matrix (profiling passes only)")
     ap.add_argument("--no_other_configs", action="store_true", help="skip the configs[1]/[3]/[4] sub-records")
     ap.add_argument("--host_args", default="", help="extra flags for the native host, space separated (tuning runs)")

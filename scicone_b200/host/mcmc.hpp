@@ -918,7 +918,11 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     std::atomic<int> limit{n_warmup > 0 ? n_warmup : n_total};  // iterations the chains may run in the current phase
     if (world > 1 && mailbox == nullptr) throw std::runtime_error("the dynamic schedule of a multi-process run needs the mailbox");
     scicone_dataset* ds = chains[0]->ds;
-    if (min_batch <= 0) min_batch = std::max(1, B / 4);  // 32 chains x 10 k cells: 6 -> 161.6, 8 -> 163.6, 10 -> 166.4, 12 -> 181.8 us per iteration; 16 chains x 100 k cells: 3 -> 488, 5 -> 458
+    // Measured (us per iteration of all chains).  32 chains x 10 k cells, one GPU, 300 iterations: 1 -> 110, 2 -> 104-119,
+    // 4 -> 106, 8 -> 110 (a launch of few small proposals costs little more than its latency, so waiting for company does
+    // not pay).  16 chains x 100 k cells: 3 -> 488, 5 -> 458 (launches are bandwidth work there).  Cell-sharded runs keep the
+    // larger batch: every launch also costs a round of messages.
+    if (min_batch <= 0) min_batch = std::max(1, (world == 1 && chains[0]->n_cells <= 20000) ? B / 8 : B / 4);
     // two launch streams: K1 of one launch overlaps the proposal kernel of the other (a launch is always collected here
     // before its chains are settled, which is what the second stream requires)
     n_streams = std::max(1, std::min(n_streams, 4));
@@ -956,6 +960,8 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     for (int b = 0; b < B; ++b) work.push_back(b);
     n_work.store(B, std::memory_order_release);
 
+    Clock::time_point t_mark = Clock::now();
+    std::vector<std::array<double, 3>> done_at;  // --timeline: {microseconds since the mark, 2, chain} when a chain has finished its phase (guarded by mu)
     // the chain goes back to the queue: the other ranks are not there yet
     auto poll_again = [&](int b, const char* what) {
         Slot& s = st[b];
@@ -986,8 +992,10 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
         --n_host;
         if (queued)
             ready.push_back(b);
-        else
+        else {
             ++n_done;
+            if (times && times->want_timeline) done_at.push_back({std::chrono::duration<double, std::micro>(Clock::now() - t_mark).count(), 2.0, static_cast<double>(b)});
+        }
     };
     auto host_work = [&](int b) {
         Inference* c = chains[b];
@@ -1015,9 +1023,12 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
             }
             s.queued = false;
             const int lim = limit.load(std::memory_order_acquire);
+            double dbg_prep = 0.0;
             while (s.iter < lim) {
                 if (c->propose(move_probs, size_limit)) {
+                    const Clock::time_point p0 = Clock::now();
                     abi_check(scicone_prepare_t_prime(c->chain));
+                    dbg_prep = std::chrono::duration<double, std::micro>(Clock::now() - p0).count();
                     s.queued = true;
                     break;
                 }
@@ -1030,6 +1041,9 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
                 s.to_publish = true;
             }
             const double us = std::chrono::duration<double, std::micro>(Clock::now() - c0).count();
+            // SCICONE_DEBUG_VISITS=1: note visits whose tree work (everything but the compile) took more than 40 us
+            static const bool debug_visits = getenv("SCICONE_DEBUG_VISITS") != nullptr;
+            if (debug_visits && us - dbg_prep > 40.0) fprintf(stderr, "visit chain %d iter %d move %u us %.1f prep %.1f\n", b, s.iter, c->move_id, us - dbg_prep, dbg_prep);
             c->t_propose_us += us;
             c->t_max_visit_us = std::max(c->t_max_visit_us, us);
         }
@@ -1081,7 +1095,6 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     std::vector<scicone_chain*> handles;
     std::vector<double> totals(B), ods(B);
     unsigned long long n_launches = 0, n_launched_chains = 0;
-    Clock::time_point t_mark = Clock::now();
     auto note = [&](double kind, size_t n) {
         if (times && times->want_timeline)
             times->timeline.push_back({std::chrono::duration<double, std::micro>(Clock::now() - t_mark).count(), kind, static_cast<double>(n)});
@@ -1162,10 +1175,11 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
                 if (limit.load(std::memory_order_acquire) >= n_total) break;
                 // end of the warm-up phase: every chain has stopped at the mark and nothing is in flight
                 if (at_mark) at_mark();
-                t_mark = Clock::now();
                 if (times) times->timeline.clear();
                 n_launches = n_launched_chains = 0;
                 std::lock_guard<std::mutex> lk(mu);
+                t_mark = Clock::now();
+                done_at.clear();
                 limit.store(n_total, std::memory_order_release);
                 n_done = 0;
                 n_host = B;
@@ -1214,6 +1228,7 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
     if (times) {
         times->launches = n_launches;
         times->launched_chains = n_launched_chains;
+        times->timeline.insert(times->timeline.end(), done_at.begin(), done_at.end());
     }
     if (err) std::rethrow_exception(err);
 }

@@ -56,6 +56,9 @@ def main():
     if res.returncode != 0:
         print(res.stdout[-2000:], res.stderr[-2000:])
         raise SystemExit(1)
+    for line in res.stderr.splitlines():  # SCICONE_DEBUG_VISITS=1: the host's notes about slow visits
+        if line.startswith("visit"):
+            print(line, file=sys.stderr)
     s = json.load(open(stats))
     s["process_wall_s"] = wall
     s["mcmc_iters_per_s"] = s["n_chains"] * s["n_iters"] / (s["wall_us"] * 1e-6)
