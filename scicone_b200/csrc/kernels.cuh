@@ -44,7 +44,7 @@ constexpr int kCells = 128;         // cells per CTA of the proposal kernel: one
 constexpr int kThreads = kCells;
 constexpr int kTaskChunk = 64;      // task records staged in shared memory at a time
 constexpr int kGroup = 8;           // nodes whose increments are in flight per thread (two register buffers of this size)
-constexpr int kScRing = 4;          // most recent node scores a thread keeps in registers (parent lookups)
+constexpr int kScRing = 16;         // most recent node scores of a thread's walk that stay in its column of a shared-memory ring (parent lookups)
 constexpr int kMaxOdSlices = 32;    // region slices of a root score
 constexpr int kCtasPerChunk = 8;    // 8 CTAs = 1024 cells: fixed-order reduction unit (multi-GPU invariant)
 constexpr int kTablesBlock = 256;   // threads per CTA of the table kernel (K1a)
@@ -128,7 +128,7 @@ struct alignas(16) DevTask {
     unsigned parent_row;  // TASK_PS_FAR: row that holds the parent's score
     int node_id;
     unsigned flags;
-    unsigned parent_back;  // 1..kScRing: the parent is the task this many positions back (score still in registers)
+    unsigned parent_back;  // 1..kScRing: the parent is the task this many positions back (1: register, else the thread's ring column)
     unsigned pad[2];
 };
 static_assert(sizeof(DevTask) == 32, "DevTask is staged as two 16-byte pieces");
@@ -685,6 +685,8 @@ template <bool kMax>
 __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __grid_constant__ LaunchParams P) {
     __shared__ __align__(16) DevTask sm_task[kTaskChunk];
     __shared__ double red_buf[kThreads / 32];
+    // the last kScRing scores of every thread's walk, one column per thread (no thread reads another one's column: no barrier)
+    __shared__ double sc_ring[kScRing][kThreads];
 
     pdl_launch_dependents();
     const unsigned char* __restrict__ arena = P.arena;
@@ -712,8 +714,13 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
     const int pm = (kMax && incremental) ? reinterpret_cast<const int*>(P.rows + (long long)H.maxid_old * stride)[j] : -1;
     const double agg_old = incremental ? rows[(long long)H.sums_old * stride] : 0.0;  // fetched now, needed in phase C
 
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;  // scores of the last kScRing nodes of the walk (s1 = the node just before)
-    static_assert(kScRing == 4, "the register ring is written out for four entries");
+    // Row addresses: base + row * (bytes per row) with a 32-bit row index and a 32-bit row pitch is ONE multiply-add
+    // (IMAD.WIDE.U32) - the walk below is bound by the instructions one warp issues, not by memory.
+    const unsigned pitch = (unsigned)(stride * (long long)sizeof(double));  // < 2^32: scicone_dataset_create bounds the cell count
+    unsigned char* const col = reinterpret_cast<unsigned char*>(rows);
+    auto at = [&](unsigned row) -> double* { return reinterpret_cast<double*>(col + (unsigned long long)row * pitch); };
+    double prev = 0.0;  // score of the task just before (the parent of a first child: about half of a depth-first walk)
+    static_assert((kScRing & (kScRing - 1)) == 0, "ring slots are taken modulo a power of two");
     const int n_tasks = H.n_tasks;
     // everything above reads the staged arena and committed rows only; the increments K1b wrote are read from here on
     pdl_wait();
@@ -729,13 +736,13 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
         if (!live) continue;
         auto load_inc = [&](int t) -> double {
             const DevTask& tk = sm_task[t];
-            return (t < nt && !(tk.flags & TASK_ROOT)) ? __ldcg(rows + (long long)tk.inc * stride) : 0.0;
+            return (t < nt && !(tk.flags & TASK_ROOT)) ? __ldcg(at(tk.inc)) : 0.0;
         };
         double nxt[kGroup];
 #pragma unroll
         for (int q = 0; q < kGroup; ++q) nxt[q] = load_inc(q);
-        double ps_far = 0.0;  // parent score that is not in the register ring: plain load, one node ahead
-        if (sm_task[0].flags & TASK_PS_FAR) ps_far = __ldcg(rows + (long long)sm_task[0].parent_row * stride);
+        double ps_far = 0.0;  // parent score that is not in the ring: plain load, one node ahead
+        if (sm_task[0].flags & TASK_PS_FAR) ps_far = __ldcg(at(sm_task[0].parent_row));
         for (int t0 = 0; t0 < nt; t0 += kGroup) {
             double cur[kGroup];
 #pragma unroll
@@ -751,18 +758,19 @@ __global__ void __launch_bounds__(kThreads, 6) score_proposals_kernel(const __gr
                     const DevTask& tk = sm_task[t];
                     const unsigned tf = tk.flags;
                     const double ps_far_cur = ps_far;
-                    if (t + 1 < nt && (sm_task[t + 1].flags & TASK_PS_FAR)) ps_far = __ldcg(rows + (long long)sm_task[t + 1].parent_row * stride);
+                    if (t + 1 < nt && (sm_task[t + 1].flags & TASK_PS_FAR)) ps_far = __ldcg(at(sm_task[t + 1].parent_row));
+                    // ring slot = position of the task in the proposal's walk modulo the ring size (chunks start on multiples of it)
+                    static_assert(kTaskChunk % kScRing == 0, "ring slots of the chunked walk");
+                    const int slot = (t0 + q) & (kScRing - 1);
                     double sc = 0.0;
                     if (!(tf & TASK_ROOT)) {  // Tree.h:241: score = parent score + increment
                         const unsigned back = tk.parent_back;
-                        const double ps = back == 1 ? s1 : back == 2 ? s2 : back == 3 ? s3 : back == 4 ? s4 : ps_far_cur;
+                        const double ps = back == 1 ? prev : back != 0 ? sc_ring[(slot - (int)back) & (kScRing - 1)][tid] : ps_far_cur;
                         sc = ps + cur[q];
                     }
-                    s4 = s3;
-                    s3 = s2;
-                    s2 = s1;
-                    s1 = sc;
-                    rows[(long long)tk.dst * stride] = sc;
+                    prev = sc;
+                    sc_ring[slot][tid] = sc;
+                    *at(tk.dst) = sc;
                     if (!(tf & TASK_SKIP_AGG)) {
                         const int id = tk.node_id;
                         if (kMax && id == pm) prev_in_new = true;

@@ -881,8 +881,8 @@ int compile_proposal(scicone_chain* ch, bool full, bool full_with_od) {
             if (last[tasks[i].node_id] != (int)i) tasks[i].flags |= TASK_SKIP_AGG;
     }
     // Walk bookkeeping for the one-thread-per-cell kernel.  Parent scores: a parent visited at most kScRing nodes ago is
-    // still in the thread's registers; the committed row of a subtree root's parent, or a parent rescored further back, is
-    // read from its row (plain load, one node ahead).
+    // still in the thread's column of the shared-memory ring (the node just before: in a register); the committed row of a
+    // subtree root's parent, or a parent rescored further back, is read from its row (plain load, one node ahead).
     for (size_t i = 0; i < tasks.size(); ++i) {
         if (tasks[i].flags & TASK_ROOT) continue;
         const int back = ptask[i] >= 0 ? (int)i - ptask[i] : 0;
@@ -1558,6 +1558,7 @@ int scicone_dataset_create(scicone_dataset** out, const scicone_dataset_desc* d)
     *out = nullptr;
     if (d->n_cells <= 0 || d->n_regions <= 0 || !d->D || !d->region_sizes || !d->neutral_states || !d->cluster_sizes)
         return fail(SCICONE_ERR_ARG, "dataset_create: empty matrix or null buffer (n_cells=%d, n_regions=%d)", d->n_cells, d->n_regions);
+    if (d->n_cells > 400000000) return fail(SCICONE_ERR_ARG, "dataset_create: at most 400 000 000 cells per dataset (the kernels address a row with a 32-bit byte pitch)");
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
