@@ -162,6 +162,43 @@ def test_multi_chain_equals_single_runs_on_cpu(tmp_path, n_chains, flags, thread
 
 
 @needs_bins
+@pytest.mark.skipif(not os.path.exists(os.path.join(CPU_BACKEND_DIR, "libscicone_score.so")), reason="cpu_backend not built")
+def test_timeline_records_every_launch_and_every_chain(tmp_path):
+    """--timeline=1 (timing runs): the stats file lists every submit (kind 0) and collect (1) of the measured phase with
+    the number of proposals, and the moment each chain finished it (2, chain) - what profiles/r2b_timeline_* was made from.
+    The warm-up phase leaves no entries, and the trajectories are those of a run without it."""
+    import json
+    import subprocess
+
+    from host_util import read_outputs
+
+    D, r = _tutorial()
+    base = ["--n_nodes=4", "--nu=1.0", "--max_scoring=true", "--seed=20", "--n_chains=6"]
+    d = os.path.join(str(tmp_path), "d.csv")
+    np.savetxt(d, D, delimiter=",", fmt="%.0f")
+    rf = os.path.join(str(tmp_path), "r.txt")
+    np.savetxt(rf, r, fmt="%d")
+    e = dict(os.environ, **dict(CPU_ENV, SCICONE_THREADS="3"))
+    common = [NATIVE, f"--d_matrix_file={d}", f"--region_sizes_file={rf}", f"--n_cells={D.shape[0]}", f"--n_regions={D.shape[1]}", "--verbosity=2"] + base
+    stats = os.path.join(str(tmp_path), "stats.json")
+    res = subprocess.run(common + ["--postfix=tl", "--n_iters=60", "--warmup_iters=40", "--timeline=1", f"--stats_file={stats}"],
+                         cwd=str(tmp_path), capture_output=True, text=True, env=e, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    st = json.load(open(stats))
+    tl = np.array(st["timeline"])
+    sub, col, done = tl[tl[:, 1] == 0], tl[tl[:, 1] == 1], tl[tl[:, 1] == 2]
+    assert len(sub) == len(col) == st["launches"] > 0
+    assert sub[:, 2].sum() == col[:, 2].sum() == st["launched_chains"] <= 6 * 60
+    assert sorted(done[:, 2].astype(int)) == list(range(6))  # every chain finished the measured phase exactly once
+    assert tl[:, 0].min() >= 0 and done[:, 0].max() <= st["wall_us"] + 1000
+    # the same 100 iterations in one phase walk the same trajectories
+    res = subprocess.run(common + ["--postfix=plain", "--n_iters=100"], cwd=str(tmp_path), capture_output=True, text=True, env=e, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    for c in (0, 5):
+        compare_runs(read_outputs(str(tmp_path), f"plain_c{c}"), read_outputs(str(tmp_path), f"tl_c{c}"))
+
+
+@needs_bins
 @pytest.mark.gpu
 def test_multi_chain_equals_single_runs_on_gpu(tmp_path):
     _multi_chain(tmp_path, None, 12, [], [0, 5, 11])
