@@ -22,8 +22,9 @@
 //                           final addition - every pair is independent of every other, so this part is embarrassingly
 //                           parallel.  The data terms lgamma(D + a_node) - lgamma(D + a_parent) of an event are looked
 //                           up in a table over the possible counts (a few hundred lgamma instead of one per cell); also
-//                           the region slices of the root score of proposals that change nu
-//                           (Tree::get_od_root_score, Tree.h:1774-1810).
+//                           the root score of proposals that change nu (Tree::get_od_root_score, Tree.h:1774-1810):
+//                           from the dataset's count histograms (one number per few regions, K1a only) or, for
+//                           non-integer data, as per-cell region slices.
 //   score_proposals_kernel  (K2-K4) per proposal (grid.y) and per 128-cell tile (grid.x), one thread per cell: walks the
 //                           rescored nodes parent-before-child (Tree::compute_stack, Tree.h:260-286), score = parent
 //                           score + increment (the increments of the next eight nodes are in flight in registers),
@@ -666,16 +667,17 @@ __global__ void __launch_bounds__(kBuildBlock) build_increments_kernel(const __g
 // A thread walks the rescored nodes of its proposal parent-before-child (Tree::compute_stack, Tree.h:260-286):
 //   stage   (CTA) task records of the next kTaskChunk nodes -> shared memory, one coalesced 16-byte copy per thread
 //   score   score = parent score + increment (K1 left the increment in the node's own row): the increments of the next
-//           kGroup nodes are loaded into registers while the current kGroup are consumed; the parent's score is one of the
-//           last four scores (registers) or was read one node ahead from the row this thread wrote earlier / from the
-//           committed table; row written, running max / online log-sum-exp
+//           kGroup nodes are loaded into registers while the current kGroup are consumed; the parent's score is the previous
+//           node's (register), one of the thread's last kScRing scores (its column of a shared-memory ring) or was read one
+//           node ahead from the row this thread wrote earlier / from the committed table; row written, running max / online log-sum-exp
 //   C       aggregate (Inference::compute_t_prime_sums): the unchanged rows are only read by cells that need them,
 //           eight loads in flight
-//   D       root score from its region slices (nu proposals)
+//   D       root score (nu proposals): the cell-level term, plus the region slices where the dataset has no count histograms
 //   reduce  aggregate * cluster_size -> warp shuffle -> CTA partial -> fixed-order chunk / grand totals (last CTA)
-// There is no per-cell state in shared memory, so occupancy is bounded by registers only and the only barriers are the
-// two around each staging step; with B proposals x M cells >= 300 k threads the SMs stay full (LPT order of the
-// proposals in grid.y handles the long full-tree rescorings of nu proposals).
+// The only per-cell state in shared memory is the thread's own column of the score ring (16 KB per CTA: six CTAs per SM
+// still fit, registers stay the bound), so the only barriers are the two around each staging step; with B proposals x M
+// cells >= 300 k threads the SMs stay full (LPT order of the proposals in grid.y handles the long full-tree rescorings
+// of nu proposals).
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void copy16(void* dst, const void* src) {
     *reinterpret_cast<int4*>(dst) = __ldg(reinterpret_cast<const int4*>(src));
