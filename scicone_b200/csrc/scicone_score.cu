@@ -152,11 +152,6 @@ struct RowPool {
     std::mutex mu;  // chains of one dataset may be compiled / committed from several host threads
 
     double* base_ptr() const { return reinterpret_cast<double*>(base); }
-    size_t mapped_total() const {
-        size_t n = 0;
-        for (const Part& p : parts) n += p.mapped_rows;
-        return n;
-    }
     void release_all() {
         for (int p = 0; p < (int)parts.size(); ++p) {
             Part& pt = parts[p];
