@@ -86,7 +86,8 @@ def threads_per_rank(world):
     cores = os.cpu_count() or 1
     # one GPU: 16 spinning threads on a 16-core box gave 20-step windows of 136-214 us per step (a worker that loses its core
     # in the middle of a visit holds its chain for a time slice), 12 threads 134-139; 300-step runs are the same for 12-16
-    return max(2, cores // world - 1) if world > 1 else max(2, cores - 4)
+    # (the host work of 32 chains keeps ~6 cores busy; more than a dozen spinning workers only add contention on a bigger box)
+    return max(2, cores // world - 1) if world > 1 else max(2, min(12, cores - 4))
 
 
 def load_traffic():
