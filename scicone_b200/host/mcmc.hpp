@@ -227,6 +227,7 @@ public:
             }
             case 2: case 3: {  // apply_swap, :1054
                 std::vector<int> nodes = t_prime.swap_labels(move_id == 3);
+                if (nodes.empty()) return false;  // rejected draw (tree.hpp: rejected_nodes)
                 for (int n : nodes) queue(n);
                 return true;
             }
@@ -1024,6 +1025,7 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
             s.queued = false;
             const int lim = limit.load(std::memory_order_acquire);
             double dbg_prep = 0.0;
+            const unsigned long long dbg_att0 = c->n_attempts;
             while (s.iter < lim) {
                 if (c->propose(move_probs, size_limit)) {
                     const Clock::time_point p0 = Clock::now();
@@ -1043,7 +1045,8 @@ inline void infer_mcmc_dynamic(std::vector<Inference*>& chains, const std::vecto
             const double us = std::chrono::duration<double, std::micro>(Clock::now() - c0).count();
             // SCICONE_DEBUG_VISITS=1: note visits whose tree work (everything but the compile) took more than 40 us
             static const bool debug_visits = getenv("SCICONE_DEBUG_VISITS") != nullptr;
-            if (debug_visits && us - dbg_prep > 40.0) fprintf(stderr, "visit chain %d iter %d move %u us %.1f prep %.1f\n", b, s.iter, c->move_id, us - dbg_prep, dbg_prep);
+            if (debug_visits && us - dbg_prep > 40.0)
+                fprintf(stderr, "visit chain %d iter %d move %u us %.1f prep %.1f attempts %llu\n", b, s.iter, c->move_id, us - dbg_prep, dbg_prep, c->n_attempts - dbg_att0);
             c->t_propose_us += us;
             c->t_max_visit_us = std::max(c->t_max_visit_us, us);
         }

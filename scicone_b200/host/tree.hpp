@@ -698,6 +698,14 @@ public:
         return out;
     }
 
+    // A move that cannot be applied to the nodes it drew.  The reference throws std::logic_error at these points and its
+    // retry loop (Inference::apply_multiple_times, Inference.h:1462-1498) catches it, undoes t_prime and tries again -
+    // exactly what it does when a move returns false, so the failure is RETURNED here (same draws, same control flow):
+    // unwinding an exception costs ~5 us per attempt, and a chain whose 50 attempts all fail sits that much longer
+    // outside the launch pipeline.  The reference's message stays as the argument.
+    static int rejected(const char* /*why*/) { return -1; }
+    static std::vector<int> rejected_nodes(const char* /*why*/) { return std::vector<int>(); }
+
     int prune_reattach(bool weighted) {  // Tree.h:544-621
         if (order.size() <= 2) throw InvalidMove("prune and reattach move does not make sense when there is only one node besides the root");
         int pruned = weighted ? weighted_sample() : uniform_sample(false);
@@ -727,9 +735,9 @@ public:
             while (a == b);
         }
         if (pool[a].c_change == pool[b].c_change)
-            throw std::logic_error("swapping 2 nodes with the same labels does not make sense, the move will be rejected");
+            return rejected_nodes("swapping 2 nodes with the same labels does not make sense, the move will be rejected");
         if (pool[a].parent == pool[b].parent && pool[a].first_child == -1 && pool[b].first_child == -1)
-            throw std::logic_error("swapping the sibling leaves will have no impact, move will be rejected.");
+            return rejected_nodes("swapping the sibling leaves will have no impact, move will be rejected.");
         dirty = true;
         pool[a].c_change.swap(pool[b].c_change);
         std::vector<int> out;
@@ -820,7 +828,7 @@ public:
         std::vector<double> omega = omega_insert_delete(weighted, max_scoring);
         int rescore;
         if (rng->uniform_real01() < 0.5) {  // insert
-            if (order.size() >= size_limit) throw std::logic_error("Tree size limit is reached, insert node move will be rejected!");
+            if (order.size() >= size_limit) return rejected("Tree size limit is reached, insert node move will be rejected!");
             int parent = order[rng->discrete(chi.begin(), chi.end())];
             EventMap labels = random_labels(1, 0.1);  // default arguments of the reference, not the chain's lambda_r (quirk Q14)
             std::vector<int> kids = children(parent);
@@ -833,7 +841,7 @@ public:
                 }
             rescore = fresh;
         } else {  // delete
-            if (order.size() <= 1) throw std::logic_error("Root cannot be deleted, delete move will be rejected");
+            if (order.size() <= 1) return rejected("Root cannot be deleted, delete move will be rejected");
             int idx = rng->discrete(omega.begin(), omega.end());
             dirty = true;
             rescore = remove_node(descendents(root, false)[idx]);
@@ -852,9 +860,9 @@ public:
         std::vector<int> below_root = descendents(root, false);
         int rescore;
         if (u < 0.5) {  // split
-            if (order.size() >= size_limit) throw std::logic_error("Tree size limit is reached, split move will be rejected!");
+            if (order.size() >= size_limit) return rejected("Tree size limit is reached, split move will be rejected!");
             int node = below_root[rng->discrete(chi.begin(), chi.end())];  // index into the unfiltered walk (quirk Q8)
-            if (pool[node].c_change.size() == 1) throw std::logic_error("Nodes with single events in a single region cannot be split");
+            if (pool[node].c_change.size() == 1) return rejected("Nodes with single events in a single region cannot be split");
             EventMap upper, lower;
             for (auto const& e : pool[node].c_change) {
                 bool sign = rng->coin();
@@ -880,11 +888,11 @@ public:
                 }
             rescore = node;
         } else {  // condense: delete a node and push its events into the parent
-            if (order.size() <= 2) throw std::logic_error("condensing nodes does not make sense when there are 2 or less nodes. Root has to be neutral.");
+            if (order.size() <= 2) return rejected("condensing nodes does not make sense when there are 2 or less nodes. Root has to be neutral.");
             int node = below_root[rng->discrete(omega.begin(), omega.end())];
             int par = pool[node].parent;
             if (all_zero(pool[node].c_change) || all_zero(pool[par].c_change))
-                throw std::logic_error("cannot condense a node with an empty node (root)");
+                return rejected("cannot condense a node with an empty node (root)");
             EventMap merged = pool[par].c_change;
             for (auto const& e : pool[node].c_change) {
                 int v = e.second;
@@ -896,7 +904,7 @@ public:
                     merged[e.first] = v;
             }
             if (merged.size() == 1 && merged.begin()->second == 1)
-                throw std::logic_error("Nodes cannot be combined if they result in a single event");
+                return rejected("Nodes cannot be combined if they result in a single event");
             dirty = true;
             pool[par].c_change = merged;
             rescore = remove_node(node);
@@ -922,7 +930,7 @@ public:
         if (order.size() <= 1) throw InvalidMove("add common ancestor does not make sense when there is 1 node or less. ");
         int parent = uniform_sample(true);
         std::vector<int> sibs = children(parent);
-        if (sibs.size() < 2) throw std::logic_error("Can not create common ancestor from less than 2 siblings.");
+        if (sibs.size() < 2) return rejected("Can not create common ancestor from less than 2 siblings.");
         std::vector<int> idx(sibs.size());
         std::iota(idx.begin(), idx.end(), 0);  // sibling positions double as sampling weights (quirk Q9)
         int ia = rng->discrete(idx.begin(), idx.end());
@@ -931,7 +939,7 @@ public:
         sibs.erase(sibs.begin() + ia);
         int b = sibs[rng->discrete(idx.begin(), idx.end())];
         EventMap common = shared_events(a, b);
-        if (common.empty()) throw std::logic_error("Can not create common ancestor from siblings with no intersection.");
+        if (common.empty()) return rejected("Can not create common ancestor from siblings with no intersection.");
         dirty = true;
         for (auto const& e : common)
             for (int n : {a, b}) {
@@ -940,7 +948,7 @@ public:
                 if (ev.at(e.first) == 0) ev.erase(e.first);
             }
         for (int n : {a, b})
-            if (pool[n].c_change.empty()) throw std::logic_error("Can not create common ancestor if a child would become empty.");
+            if (pool[n].c_change.empty()) return rejected("Can not create common ancestor if a child would become empty.");
         int anc = new_child(parent, common);
         for (int n : {a, b}) {
             detach(n);
