@@ -421,7 +421,7 @@ def run_engine(args):
                              note="algorithmic bytes are what the reference's algorithm touches per unit (SURVEY.md 8d); this kernel reads "
                                   "only the rows an aggregate needs and takes the data terms from 2-byte count indices and L2-resident tables, "
                                   "so its DRAM traffic (`traffic`) is a fraction of them and frac can exceed 1: the kernel is bound by the latency "
-                                  "of dependent row gathers and by issue slots (ncu: issue active 48 %, DRAM 15 %), not by HBM bandwidth; "
+                                  "of dependent row gathers and by issue slots (ncu: issue active 42 %, DRAM 14 %), not by HBM bandwidth; "
                                   "roofline_e2e is the same kernel inside the real MCMC",
                              traffic_over_algorithmic=(traffic / (cnt_dev["alg_bytes"] / max(1, n_timed))) if traffic else None),
             # the same kernel inside the REAL MCMC (launches of ~10 proposals, two to three in flight, other kernels beside it)
@@ -429,12 +429,13 @@ def run_engine(args):
                                  launches=host["score_kernel_launches"],
                                  avg_launch_us=host["score_kernel_us"] / max(1, host["score_kernel_launches"]),
                                  measured_in="e2e run: CUDA events around every launch of the proposal kernel, summed (max over ranks)"),
-            # K1a + K1b (tables and increments of the proposals that rescore the whole tree, root-score slices)
-            "roofline_k1": roof(host["build_alg_bytes"], host["build_kernel_us"], kernel="build_tables_kernel + build_slices_kernel",
+            # K1a + K1b (value tables and increments of every rescored node, the root score of nu proposals)
+            "roofline_k1": roof(host["build_alg_bytes"], host["build_kernel_us"], kernel="build_tables_kernel + build_increments_kernel",
                                 launches=host["build_kernel_launches"], lgamma_per_s=host["build_lgamma"] / (host["build_kernel_us"] * 1e-6)
                                 if host["build_kernel_us"] > 0 else 0.0,
                                 bytes_model="per rescored node of a tabulated proposal and cell: 8 written + 2 (count index) or 8 (count) read per "
-                                            "event; per root-score slice and cell: 8 written + 2 or 8 per region",
+                                            "event; root score: 8 per histogram entry (datasets with count histograms), else per slice and cell "
+                                            "8 written + 2 or 8 per region; the kernels are launch-floor bound, the byte fraction only documents that",
                                 measured_in="e2e run: CUDA events around K1a + K1b of every launch that has them"),
             "roofline_k0": roof(k0["alg_bytes"], k0["us"], kernel="condense_rows_kernel", rows=k0["rows"], bins=k0["bins"], kernel_us=k0["us"],
                                 bytes_model="8 n_bins read + 8 K written per row",
